@@ -1,0 +1,154 @@
+/*
+ * nerf_b200.h -- C ABI of the B200-native NeRF ray-render hot path (libnerf_b200.so).
+ *
+ * The reference (Sahar-E/NeRF-and-DietNeRF) has no FFI layer: its boundary for this path is the set of
+ * Python functions in src/UtilsCV.py, src/UtilsNeuralRadianceField.py, src/NeRF.py and src/DietNeRF.py.
+ * Each entry point below names the reference function (file:line, relative to the reference root) it
+ * replaces.  The Python host package (nerf-and-dietnerf_b200/) keeps the reference's names and argument
+ * order and calls these symbols through ctypes; INTEGRATION.md shows the binding.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer owned by the caller unless the name ends in _host;
+ *     tensors are row-major, contiguous, fp32 unless stated;
+ *   - `stream` is a cudaStream_t passed as void*; no call synchronises, allocates or frees device memory;
+ *   - return value 0 = ok, negative = error (NERF_E_*); nerf_last_error() gives the thread-local message;
+ *   - there is NO CPU fallback: without a CUDA device every compute call returns NERF_E_CUDA.
+ *   - RNG: Philox4x32-10, key = seed, counter = (global ray index, draw/4, stream id, step); see
+ *     oracle/philox.py for the exact stream (stream id 0 = stratified jitter, 1 = importance uniforms).
+ */
+#ifndef NERF_B200_H
+#define NERF_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NERF_OK 0
+#define NERF_E_ARG (-1)     /* bad argument (shape, null pointer, unsupported config) */
+#define NERF_E_CUDA (-2)    /* CUDA runtime error (message in nerf_last_error) */
+#define NERF_E_UNSUPPORTED (-3)
+
+/* MLP arithmetic modes.  FP32: SIMT fp32 GEMMs (1e-5 parity mode).  BF16: tcgen05/TMEM tensor-core
+ * chain, bf16 operands, fp32 accumulate (1e-3 parity mode). */
+#define NERF_MODE_FP32 0
+#define NERF_MODE_BF16 1
+
+/* Network hyper-parameters: the `neural_net:` block of the reference YAML (src/NeRF.py:35-53,
+ * src/ConfigurationKeys.py). */
+typedef struct nerf_net_cfg {
+  int32_t n_pos_enc_xyz;   /* n_pos_enc_dim_xyz  (L_xyz; 5 in every reference config) */
+  int32_t n_pos_enc_view;  /* n_pos_enc_view_dir (L_view; 4 or 2) */
+  int32_t n_angles;        /* n_angles_for_model: 0 (no view input), 1 ([x,z]) or 2 ([x,y,z]) */
+  int32_t hidden;          /* hidden_layer_dim (256) */
+  int32_t last_hidden;     /* last_hidden_layer_dim (128) */
+  float leaky_alpha;       /* leaky_relu_alpha (0.05) */
+} nerf_net_cfg;
+
+const char* nerf_version(void);
+const char* nerf_last_error(void);
+
+/* Number of fp32 parameters of one net, laid out [W0 (in,out) row-major, b0, W1, b1, ...] in Keras layer
+ * creation order (src/NeRF.py:263-286 / :312-337).  514332 for the standard config. */
+int64_t nerf_param_count(const nerf_net_cfg* cfg);
+/* Widths of the encoded inputs: 3+6*L_xyz and 2*L_view*(n_angles+1) (0 when n_angles==0). */
+int32_t nerf_xyz_enc_dim(const nerf_net_cfg* cfg);
+int32_t nerf_view_enc_dim(const nerf_net_cfg* cfg);
+
+/* ---- rays ------------------------------------------------------------------------------------------ */
+/* get_rays_directions (src/UtilsCV.py:467-499) + origin broadcast (src/NeRF.py:209,
+ * src/UtilsNeuralRadianceField.py:177) for pixels [ray_begin, ray_begin+n_rays) of an h x w image
+ * (ray index = y*w+x).  c2w_host: 16 floats, row-major 4x4, HOST memory.  dirs4/origs4: (n_rays,4). */
+int nerf_ray_directions(const float* c2w_host, float fov, int32_t h, int32_t w, int64_t ray_begin,
+                        int64_t n_rays, float* dirs4, float* origs4, void* stream);
+
+/* get_z_values(z_start,z_end,N,1,S)[:,0,:] (src/UtilsCV.py:565-581; call sites src/NeRF.py:127,146).
+ * jitter_or_null: (N,S) uniforms to use instead of the Philox stream (tests). z: (N,S). */
+int nerf_stratified_z(float z_start, float z_end, int64_t n_rays, int32_t n_samples,
+                      const float* jitter_or_null, uint64_t seed, uint32_t step, uint64_t ray_offset,
+                      float* z, void* stream);
+
+/* sample_along_rays (src/UtilsCV.py:584-599): out (N,S,4) = origin + dir * z. */
+int nerf_sample_along_rays(const float* origs4, const float* dirs4, const float* z, int64_t n_rays,
+                           int32_t n_samples, float* coords4, void* stream);
+
+/* get_view_directions (src/UtilsCV.py:124-143): out (N*S, n_angles+1); n_angles must be 1 or 2. */
+int nerf_view_directions(const float* dirs4, int64_t n_rays, int32_t n_samples, int32_t n_angles,
+                         float* view_dirs, void* stream);
+
+/* positional_encoding_for_xyz / _for_views (src/UtilsNeuralRadianceField.py:68-85 / :52-65).
+ * x: (M,C) (C==3 for xyz); out: (M, C+2*L*C) resp. (M, 2*L*C). */
+int nerf_posenc_xyz(const float* xyz, int64_t m, int32_t L, float* out, void* stream);
+int nerf_posenc_views(const float* x, int64_t m, int32_t c, int32_t L, float* out, void* stream);
+/* Gradient of positional_encoding_for_xyz w.r.t. xyz (what TF autodiff produces inside NeRF.train_step). */
+int nerf_posenc_xyz_bwd(const float* xyz, const float* d_out, int64_t m, int32_t L, float* d_xyz, void* stream);
+
+/* Fused K1 for the MLP input: sample_along_rays[..., :3] -> both encodings, never materialising the
+ * (N,S,4) coordinates (src/UtilsNeuralRadianceField.py:204-205,229-231).  view_enc may be null when
+ * cfg->n_angles == 0.  xyz_enc: (N*S, 3+6L); view_enc: (N*S, Dv). */
+int nerf_encode_samples(const nerf_net_cfg* cfg, const float* origs4, const float* dirs4, const float* z,
+                        int64_t n_rays, int32_t n_samples, float* xyz_enc, float* view_enc, void* stream);
+/* Backward of the xyz half of nerf_encode_samples w.r.t. z: d_z (N,S) += sum_c d_xyz_c * dir_c. */
+int nerf_encode_samples_bwd_z(const nerf_net_cfg* cfg, const float* origs4, const float* dirs4,
+                              const float* z, const float* d_xyz_enc, int64_t n_rays, int32_t n_samples,
+                              float* d_z, int32_t accumulate, void* stream);
+
+/* ---- MLP (model_predict, src/UtilsNeuralRadianceField.py:214-234; nets src/NeRF.py:248-340) ------------ */
+/* Bytes of activations nerf_mlp_fwd saves for nerf_mlp_bwd (0 rows -> 0). */
+int64_t nerf_mlp_saved_bytes(const nerf_net_cfg* cfg, int64_t m, int32_t mode);
+/* Scratch bytes nerf_mlp_fwd / nerf_mlp_bwd need. */
+int64_t nerf_mlp_workspace_bytes(const nerf_net_cfg* cfg, int64_t m, int32_t mode, int32_t backward);
+/* out4 (M,4) = [r,g,b,sigma] raw.  saved_or_null: activations for backward.  packed_or_null: bf16 weight
+ * pack from nerf_pack_weights (required for NERF_MODE_BF16). */
+int nerf_mlp_fwd(const nerf_net_cfg* cfg, const float* params, const void* packed_or_null,
+                 const float* xyz_enc, const float* view_enc, int64_t m, float* out4, void* saved_or_null,
+                 void* workspace, int32_t mode, void* stream);
+/* grads (+= , same layout as params); d_xyz_enc_or_null (M, Dx) is written when non-null. */
+int nerf_mlp_bwd(const nerf_net_cfg* cfg, const float* params, const void* packed_or_null,
+                 const float* xyz_enc, const float* view_enc, const void* saved, const float* d_out4,
+                 int64_t m, float* grads, float* d_xyz_enc_or_null, void* workspace, int32_t mode,
+                 void* stream);
+/* bf16 weight pack for the tensor-core path (re-run after every optimizer step). */
+int64_t nerf_packed_bytes(const nerf_net_cfg* cfg);
+int nerf_pack_weights(const nerf_net_cfg* cfg, const float* params, void* packed, void* stream);
+
+/* ---- alpha compositing (ray_marching, src/UtilsNeuralRadianceField.py:88-115) ------------------------- */
+/* raw4 (N,S,4), z (N,S).  Outputs (any may be null): rgb (N,3), weights/cumprod/alpha (N,S),
+ * rgb_s (N,S,3), depth (N) = sum w z (src/ExecutionRun.py:346), acc (N) = sum w. */
+int nerf_composite_fwd(const float* raw4, const float* z, int64_t n_rays, int32_t n_samples, float* rgb,
+                       float* weights, float* cumprod, float* alpha, float* rgb_s, float* depth, float* acc,
+                       void* stream);
+/* Gradients TF autodiff gives for ray_marching (cumprod gradient = div_no_nan form).  d_weights_or_null:
+ * extra upstream gradient on `weights` (from the importance sampler).  d_z_or_null: written when non-null. */
+int nerf_composite_bwd(const float* raw4, const float* z, const float* d_rgb, const float* d_weights_or_null,
+                       int64_t n_rays, int32_t n_samples, float* d_raw4, float* d_z_or_null, void* stream);
+
+/* ---- hierarchical sampling (get_z_vals_from_prob_dist_func, src/UtilsCV.py:502-539) ------------------- */
+/* weights,z: (N,S); z_new: (N,Nf) sorted.  u_or_null: (N,Nf) uniforms replacing the Philox stream.
+ * Optional outputs: idx (N,Nf) int32 searchsorted results in DRAW order, perm (N,Nf) int32 sort
+ * permutation (z_new[k] = z_unsorted[perm[k]]), u_out (N,Nf) the uniforms used. */
+int nerf_sample_pdf_fwd(const float* weights, const float* z, int64_t n_rays, int32_t n_samples,
+                        int32_t n_new, const float* u_or_null, uint64_t seed, uint32_t step,
+                        uint64_t ray_offset, float* z_new, int32_t* idx_or_null, int32_t* perm_or_null,
+                        float* u_out_or_null, void* stream);
+/* d_weights (N,S) written: gradient of z_new w.r.t. weights contracted with d_z_new (N,Nf, sorted order). */
+int nerf_sample_pdf_bwd(const float* weights, const float* z, const float* u, const int32_t* perm,
+                        const float* d_z_new, int64_t n_rays, int32_t n_samples, int32_t n_new,
+                        float* d_weights, void* stream);
+/* z = sort(concat(z_a, z_b)) per ray (src/NeRF.py:132); both inputs sorted ascending. out: (N,Sa+Sb). */
+int nerf_merge_sorted(const float* z_a, int32_t sa, const float* z_b, int32_t sb, int64_t n_rays, float* out,
+                      void* stream);
+
+/* ---- loss / optimizer (src/NeRF.py:151,157,164-176) -------------------------------------------------- */
+/* d_rgb = loss_weight * 2 (rgb-target) / (3*n_total); sums[0] += sum((rgb-target)^2) (caller zeroes). */
+int nerf_mse_fwd_bwd(const float* rgb, const float* target, int64_t n_rays, int64_t n_total_rays,
+                     float loss_weight, float* sq_err_sum, float* d_rgb, void* stream);
+/* Keras-2.7 Adam update, t = 1-based step. */
+int nerf_adam_step(float* params, const float* grads, float* m, float* v, int64_t n, float lr, float beta1,
+                   float beta2, float eps, int64_t t, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NERF_B200_H */

@@ -1,0 +1,34 @@
+"""YAML configuration keys read by the render/train hot path.
+
+The key STRINGS are the config-file contract of the reference (src/ConfigurationKeys.py) and are kept verbatim so
+the reference's config_files/*.yaml load unchanged; only the keys the hot path and its immediate callers read are
+listed here.
+"""
+# top-level blocks
+NEURAL_NET = 'neural_net'
+RENDER = 'render'
+TRAINING = 'training'
+
+# neural_net:
+TYPE_OF_MODEL = 'type_of_model'
+HIDDEN_LAYER_DIM = 'hidden_layer_dim'
+LAST_HIDDEN_LAYER_DIM = 'last_hidden_layer_dim'
+LEAKY_RELU_ALPHA = 'leaky_relu_alpha'
+N_POS_ENC_DIM_XYZ = 'n_pos_enc_dim_xyz'
+N_POS_ENC_VIEW_DIR = 'n_pos_enc_view_dir'
+N_ANGLES_FOR_MODEL = 'n_angles_for_model'
+N_RAYS_IN_BATCH_TRAIN = 'n_rays_in_batch_train'
+N_RAYS_IN_BATCH_RENDER = 'n_rays_in_batch_render'
+
+# render:
+N_RENDER_SAMPLES_COARSE = 'n_render_samples_coarse'
+N_RENDER_SAMPLES_FINE = 'n_render_samples_fine'
+NEAR_DEPTH_RENDER = 'near_depth_render'
+FAR_DEPTH_RENDER = 'far_depth_render'
+
+# training:
+N_EPOCHS = 'n_epochs'
+OPTIMIZER_LR = 'optimizer_lr'
+
+NERF_MODEL = 'NeRF'
+DIETNERF_MODEL = 'DietNeRF'

@@ -1,0 +1,378 @@
+"""NeRF model: drop-in for the render/train step of the reference's src/NeRF.py, on hand-written sm_100a kernels.
+
+Keeps the reference's surface -- ``NeRF(net_config, render_config, near_boundary, far_boundary)`` (:27),
+``render`` (:109), ``call`` (:96), ``train_step`` (:136), ``render_rays`` (:180), ``render_image`` (:190),
+``init_network`` (:59), ``get_nerf_model_path`` (:343) and the YAML keys of src/ConfigurationKeys.py -- but is not a
+Keras model: parameters are two flat fp32 device vectors, the train step is an explicit forward + hand-written
+backward (no autograd tape) over the C ABI, and ray batches can be sharded over the GPUs of one box with a single
+NCCL all-reduce of the gradients per step.
+"""
+import math
+from pathlib import Path
+from typing import Dict
+
+import torch
+
+from . import _lib
+from ._lib import NetCfg, call, f32c, ptr
+from .ConfigurationKeys import (HIDDEN_LAYER_DIM, LAST_HIDDEN_LAYER_DIM, LEAKY_RELU_ALPHA, N_ANGLES_FOR_MODEL,
+                                N_POS_ENC_DIM_XYZ, N_POS_ENC_VIEW_DIR, N_RAYS_IN_BATCH_RENDER, N_RAYS_IN_BATCH_TRAIN,
+                                N_RENDER_SAMPLES_COARSE, N_RENDER_SAMPLES_FINE)
+from .network import NerfMLP
+from .optimizers import Adam
+from .UtilsCV import get_rays_directions, get_z_vals_from_prob_dist_func, get_z_values, rng
+from .UtilsNeuralRadianceField import get_psnr, split_to_batches
+from . import UtilsNeuralRadianceField as _unrf
+
+DIRNAME_TO_SAVE_WEIGHTS = 'saved_weights'
+NAME_NERF_MODEL_FILE = 'NeRF_model_epoch_{:03}.h5'
+
+
+def net_cfg_from_dict(net_config: Dict) -> NetCfg:
+    """YAML ``neural_net:`` block -> struct nerf_net_cfg (strict key lookups like the reference, KeyError if missing)."""
+    return NetCfg(int(net_config[N_POS_ENC_DIM_XYZ]), int(net_config[N_POS_ENC_VIEW_DIR]),
+                  int(net_config[N_ANGLES_FOR_MODEL]), int(net_config[HIDDEN_LAYER_DIM]),
+                  int(net_config[LAST_HIDDEN_LAYER_DIM]), float(net_config[LEAKY_RELU_ALPHA]))
+
+
+class _StepWorkspace:
+    """Device buffers of one train step for a fixed number of rays (allocated once, reused every step)."""
+
+    def __init__(self, model, n):
+        dev = model.device
+        f = lambda *shape: torch.empty(shape, dtype=torch.float32, device=dev)
+        sc, sf = model.n_render_samples_coarse, model.n_render_samples_fine
+        mc = model.model_coarse
+        self.n = n
+        self.z_c = f(n, sc)
+        self.xyz_c = f(n * sc, mc.dx)
+        self.view_c = f(n * sc, mc.dv) if mc.dv else None
+        self.raw_c = f(n, sc, 4)
+        self.rgb_c = f(n, 3)
+        self.w_c = f(n, sc)
+        self.d_rgb_c = f(n, 3)
+        self.d_raw_c = f(n, sc, 4)
+        self.saved_c = torch.empty(max(mc.saved_bytes(n * sc), 16), dtype=torch.uint8, device=dev)
+        self.sums = torch.zeros(2, dtype=torch.float32, device=dev)
+        m_max = n * max(sc, sf)
+        self.ws_fwd = torch.empty(max(mc.workspace_bytes(m_max, False), 16), dtype=torch.uint8, device=dev)
+        self.ws_bwd = torch.empty(max(mc.workspace_bytes(m_max, True), 16), dtype=torch.uint8, device=dev)
+        if model.model_fine is not None:
+            self.z_f = f(n, sf)
+            self.u = f(n, sf)
+            self.perm = torch.empty((n, sf), dtype=torch.int32, device=dev)
+            self.xyz_f = f(n * sf, mc.dx)
+            self.view_f = f(n * sf, mc.dv) if mc.dv else None
+            self.raw_f = f(n, sf, 4)
+            self.rgb_f = f(n, 3)
+            self.d_rgb_f = f(n, 3)
+            self.d_raw_f = f(n, sf, 4)
+            self.d_z_f = f(n, sf)
+            self.d_xyz_f = f(n * sf, mc.dx)
+            self.d_w_c = f(n, sc)
+            self.saved_f = torch.empty(max(mc.saved_bytes(n * sf), 16), dtype=torch.uint8, device=dev)
+
+
+class NeRF:
+    """The NeRF model (coarse + optional fine network) with its render and train step."""
+
+    # loss = COARSE_LOSS_WEIGHT * MSE_coarse + MSE_fine  (1 for NeRF, src/NeRF.py:151-157; DietNeRF overrides)
+    COARSE_LOSS_WEIGHT = 1.0
+
+    def __init__(self, net_config: Dict, render_config: Dict, near_boundary: float, far_boundary: float, *,
+                 mode: str = "bf16", device=None, seed=None, stop_grad_z: bool = False):
+        """
+        :param net_config:      ``neural_net`` block of the config file.
+        :param render_config:   ``render`` block of the config file.
+        :param mode:            (extension) "bf16" tensor-core path or "fp32" parity path.
+        :param stop_grad_z:     (extension, default False = reference behaviour) detach the importance samples.
+        """
+        self.device = device or torch.device("cuda", torch.cuda.current_device())
+        self.mode = mode
+        self.net_cfg = net_cfg_from_dict(net_config)
+        self.model_coarse = NeRF.init_network(net_config, mode=mode, device=self.device,
+                                              seed=None if seed is None else 2 * seed)
+        if render_config[N_RENDER_SAMPLES_FINE] > 0:
+            self.model_fine = NeRF.init_network(net_config, mode=mode, device=self.device,
+                                                seed=None if seed is None else 2 * seed + 1)
+        else:
+            self.model_fine = None
+
+        self.batch_size_render = net_config[N_RAYS_IN_BATCH_RENDER]
+        self.batch_size_train = net_config[N_RAYS_IN_BATCH_TRAIN]
+        self.near_boundary = float(near_boundary)
+        self.far_boundary = float(far_boundary)
+        self.n_render_samples_coarse = int(render_config[N_RENDER_SAMPLES_COARSE])
+        self.n_render_samples_fine = int(render_config[N_RENDER_SAMPLES_FINE])
+        self.n_pos_enc_dim_xyz = self.net_cfg.n_pos_enc_xyz
+        self.n_pos_enc_view_dir = self.net_cfg.n_pos_enc_view
+        self.n_angles_for_model = self.net_cfg.n_angles
+        self.stop_grad_z = stop_grad_z
+
+        self.optimizer = None
+        self.seed = 0 if seed is None else int(seed)
+        self.step_counter = 0           # Philox `step` of the next train step
+        self._ws = {}
+        self._grads = None
+        # data-parallel state (set by distribute())
+        self.world_size, self.rank, self._process_group = 1, 0, None
+
+    # ---- construction helpers --------------------------------------------------------------------------------
+    @staticmethod
+    def init_network(net_config: Dict, mode: str = "bf16", device=None, seed=None) -> NerfMLP:
+        """Initialise one network from the config (xyz+view when n_angles_for_model > 0, else xyz only)."""
+        return NerfMLP(net_cfg_from_dict(net_config), mode=mode, device=device, seed=seed)
+
+    @staticmethod
+    def get_nerf_model_path(save_location: Path, epoch_number: int) -> Path:
+        return Path(save_location) / DIRNAME_TO_SAVE_WEIGHTS / NAME_NERF_MODEL_FILE.format(epoch_number)
+
+    def compile(self, optimizer=None, **kwargs):
+        """Keras-style: attach the optimizer (``Adam(learning_rate)``)."""
+        self.optimizer = optimizer if optimizer is not None else Adam(**kwargs)
+        return self
+
+    def distribute(self, process_group=None):
+        """Shard every train batch over the ranks of ``process_group`` (one process per GPU, NCCL)."""
+        import torch.distributed as dist
+        self._process_group = process_group
+        self.world_size = dist.get_world_size(process_group)
+        self.rank = dist.get_rank(process_group)
+        return self
+
+    @property
+    def trainable_variables(self):
+        v = list(self.model_coarse.trainable_variables)
+        if self.model_fine is not None:
+            v += self.model_fine.trainable_variables
+        return v
+
+    def get_config(self):
+        return {
+            'near_boundary': self.near_boundary, 'far_boundary': self.far_boundary,
+            'n_render_samples_coarse': self.n_render_samples_coarse,
+            'n_render_samples_fine': self.n_render_samples_fine,
+            'n_positional_encoding': self.n_pos_enc_dim_xyz, 'n_enc_phi_theta': self.n_pos_enc_view_dir,
+            'n_angles_for_model': self.n_angles_for_model, 'mode': self.mode,
+        }
+
+    # ---- rendering ---------------------------------------------------------------------------------------------
+    def render_rays(self, model, rays_orig, rays_dirs, z):
+        """Render rays with ``model`` (5-tuple of ray_marching), autograd-aware.  Mirrors src/NeRF.py:180-188."""
+        return _unrf.render_rays(model, rays_orig, rays_dirs, z, self.n_pos_enc_dim_xyz, self.n_pos_enc_view_dir,
+                                 self.n_angles_for_model)
+
+    def _render_rays_fused(self, model, rays_orig, rays_dirs, z, lean=False):
+        """Inference-only fast path: fused encode -> MLP -> compositing, no autograd bookkeeping."""
+        n, s = z.shape
+        dev = z.device
+        xyz = torch.empty((n * s, model.dx), dtype=torch.float32, device=dev)
+        view = torch.empty((n * s, model.dv), dtype=torch.float32, device=dev) if model.dv else None
+        call("nerf_encode_samples", model.cfg_ref, ptr(rays_orig), ptr(rays_dirs), ptr(z), n, s, ptr(xyz), ptr(view))
+        raw = torch.empty((n, s, 4), dtype=torch.float32, device=dev)
+        ws = model._buffer("ws_fwd", model.workspace_bytes(n * s, False))
+        call("nerf_mlp_fwd", model.cfg_ref, ptr(model.params), ptr(model.packed_for(model.params)), ptr(xyz), ptr(view),
+             n * s, ptr(raw), None, ptr(ws), model.mode_id)
+        with torch.no_grad():
+            if lean:
+                return _unrf.ray_marching_lean(raw, z)
+            return _unrf.ray_marching(raw, z)
+
+    def render(self, rays_orig, rays_dirs, n_render_samples_c=None, n_render_samples_f=None, *, seed=None, step=0,
+               ray_offset=0, jitter=None, u=None):
+        """Render rays: returns (render_result, weights, cumprod, alpha, rgb, z) like src/NeRF.py:109-134.
+
+        Keyword-only extensions pin the random stream (``seed/step/ray_offset``) or the draws themselves
+        (``jitter`` (N,S_c), ``u`` (N,N_f)); the reference draws unseeded tf.random.uniform values.
+        """
+        rays_orig, rays_dirs = f32c(rays_orig, self.device), f32c(rays_dirs, self.device)
+        n = rays_orig.shape[0]
+        n_c = n_render_samples_c if n_render_samples_c else self.n_render_samples_coarse
+        if seed is None and jitter is None:
+            seed, step = rng.next_step()
+        with torch.no_grad():
+            z = get_z_values(self.near_boundary, self.far_boundary, n, 1, n_c, jitter=jitter, seed=seed, step=step,
+                             ray_offset=ray_offset)[:, 0, :]
+            out = self._render_rays_fused(self.model_coarse, rays_orig, rays_dirs, z)
+            if self.model_fine is not None:
+                n_f = n_render_samples_f if n_render_samples_f else self.n_render_samples_fine
+                z_from_dist = get_z_vals_from_prob_dist_func(out[1], z, n_f, u=u, seed=seed if u is None else None,
+                                                             step=step, ray_offset=ray_offset)
+                z_all = torch.empty((n, n_f + n_c), dtype=torch.float32, device=self.device)
+                call("nerf_merge_sorted", ptr(z_from_dist), n_f, ptr(z), n_c, n, ptr(z_all))
+                z = z_all
+                out = self._render_rays_fused(self.model_fine, rays_orig, rays_dirs, z)
+        return out + (z,)
+
+    def call(self, inputs, training=None, mask=None):
+        rays_orig, rays_dirs = inputs
+        return self.render(rays_orig, rays_dirs)[0]
+
+    __call__ = call
+
+    def render_image(self, c2w, fov, h, w, batch_size_input=None, n_render_samples_c=None, n_render_samples_f=None, *,
+                     seed=None, step=0):
+        """Render an h x w image: returns (rgb (h,w,3), weights, cumprod, alpha (h,w,S), rgb_s (h,w,S,3), z (h,w,S))."""
+        rays_dirs, rays_orig = get_rays_directions(h, w, fov, c2w, return_origins=True)
+        rays_dirs = rays_dirs.reshape(h * w, 4)
+        batch_size = batch_size_input if batch_size_input else self.batch_size_render
+        if seed is None:
+            seed, step = rng.next_step()
+        parts = []
+        offset = 0
+        for o, d in zip(split_to_batches(rays_orig, batch_size), split_to_batches(rays_dirs, batch_size)):
+            parts.append(self.render(o, d, n_render_samples_c, n_render_samples_f, seed=seed, step=step,
+                                     ray_offset=offset))
+            offset += o.shape[0]
+        cat = [torch.cat([p[i] for p in parts], dim=0) for i in range(6)]
+        return (cat[0].reshape(h, w, 3), cat[1].reshape(h, w, -1), cat[2].reshape(h, w, -1), cat[3].reshape(h, w, -1),
+                cat[4].reshape(h, w, -1, 3), cat[5].reshape(h, w, -1))
+
+    def render_image_lean(self, c2w, fov, h, w, batch_size_input=None, *, seed=None, step=0, ray_begin=0, n_rays=None):
+        """Video-path render (extension): only rgb (n,3), depth (n) = sum w z (src/ExecutionRun.py:346) and acc (n),
+        for rays [ray_begin, ray_begin+n_rays) of the frame -- the unit a GPU takes when a frame is row-sharded."""
+        n_total = h * w if n_rays is None else int(n_rays)
+        dirs, orig = get_rays_directions(h, w, fov, c2w, ray_begin=ray_begin, n_rays=n_total, return_origins=True)
+        batch_size = batch_size_input if batch_size_input else self.batch_size_render
+        if seed is None:
+            seed, step = rng.next_step()
+        n_c, n_f = self.n_render_samples_coarse, self.n_render_samples_fine
+        rgbs, depths, accs = [], [], []
+        with torch.no_grad():
+            for s0 in range(0, n_total, batch_size):
+                o, d = orig[s0:s0 + batch_size], dirs[s0:s0 + batch_size]
+                n = o.shape[0]
+                off = ray_begin + s0
+                z = get_z_values(self.near_boundary, self.far_boundary, n, 1, n_c, seed=seed, step=step,
+                                 ray_offset=off)[:, 0, :]
+                rgb, wts, depth, acc = self._render_rays_fused(self.model_coarse, o, d, z, lean=True)
+                if self.model_fine is not None:
+                    z_f = get_z_vals_from_prob_dist_func(wts, z, n_f, seed=seed, step=step, ray_offset=off)
+                    z_all = torch.empty((n, n_f + n_c), dtype=torch.float32, device=self.device)
+                    call("nerf_merge_sorted", ptr(z_f), n_f, ptr(z), n_c, n, ptr(z_all))
+                    rgb, wts, depth, acc = self._render_rays_fused(self.model_fine, o, d, z_all, lean=True)
+                rgbs.append(rgb)
+                depths.append(depth)
+                accs.append(acc)
+        return torch.cat(rgbs), torch.cat(depths), torch.cat(accs)
+
+    # ---- training ----------------------------------------------------------------------------------------------------
+    def _workspace(self, n):
+        ws = self._ws.get(n)
+        if ws is None:
+            ws = _StepWorkspace(self, n)
+            self._ws[n] = ws
+        return ws
+
+    def _grad_buffer(self):
+        if self._grads is None:
+            n = self.model_coarse.n_params + (self.model_fine.n_params if self.model_fine is not None else 0)
+            self._grads = torch.zeros(n + 2, dtype=torch.float32, device=self.device)  # [+2]: sq-error sums ride along
+        return self._grads
+
+    def forward_backward(self, rays_orig, rays_dirs, real_rgb, *, n_total_rays=None, ray_offset=0, seed=None, step=None,
+                         jitter=None, u=None):
+        """Loss and parameter gradients of one batch (src/NeRF.py:145-164 without the optimizer).
+
+        Returns (grads_coarse, grads_fine, sums) where sums = [sum sq err coarse, sum sq err fine] over THIS
+        shard and the gradients are already divided by the GLOBAL element count 3*n_total_rays.
+        """
+        n = rays_orig.shape[0]
+        n_total = n if n_total_rays is None else int(n_total_rays)
+        w = self._workspace(n)
+        mc, mf = self.model_coarse, self.model_fine
+        sc, sf = self.n_render_samples_coarse, self.n_render_samples_fine
+        seed = self.seed if seed is None else seed
+        step = self.step_counter if step is None else step
+        g = self._grad_buffer()
+        g.zero_()
+        g_c = g[:mc.n_params]
+        g_f = g[mc.n_params:mc.n_params + mf.n_params] if mf is not None else None
+        sums = g[-2:]
+        o, d, y = rays_orig, rays_dirs, real_rgb
+
+        # coarse forward
+        call("nerf_stratified_z", self.near_boundary, self.far_boundary, n, sc, ptr(jitter), seed, step, ray_offset,
+             ptr(w.z_c))
+        call("nerf_encode_samples", mc.cfg_ref, ptr(o), ptr(d), ptr(w.z_c), n, sc, ptr(w.xyz_c), ptr(w.view_c))
+        call("nerf_mlp_fwd", mc.cfg_ref, ptr(mc.params), ptr(mc.packed_for(mc.params)), ptr(w.xyz_c), ptr(w.view_c),
+             n * sc, ptr(w.raw_c), ptr(w.saved_c), ptr(w.ws_fwd), mc.mode_id)
+        call("nerf_composite_fwd", ptr(w.raw_c), ptr(w.z_c), n, sc, ptr(w.rgb_c), ptr(w.w_c), None, None, None, None,
+             None)
+        call("nerf_mse_fwd_bwd", ptr(w.rgb_c), ptr(y), n, n_total, self.COARSE_LOSS_WEIGHT, ptr(sums[0:1]),
+             ptr(w.d_rgb_c))
+        d_w_c = None
+        if mf is not None:
+            # fine forward on the n_f importance samples only (src/NeRF.py:155-156)
+            call("nerf_sample_pdf_fwd", ptr(w.w_c), ptr(w.z_c), n, sc, sf, ptr(u), seed, step, ray_offset, ptr(w.z_f),
+                 None, ptr(w.perm), ptr(w.u))
+            call("nerf_encode_samples", mf.cfg_ref, ptr(o), ptr(d), ptr(w.z_f), n, sf, ptr(w.xyz_f), ptr(w.view_f))
+            call("nerf_mlp_fwd", mf.cfg_ref, ptr(mf.params), ptr(mf.packed_for(mf.params)), ptr(w.xyz_f),
+                 ptr(w.view_f), n * sf, ptr(w.raw_f), ptr(w.saved_f), ptr(w.ws_fwd), mf.mode_id)
+            call("nerf_composite_fwd", ptr(w.raw_f), ptr(w.z_f), n, sf, ptr(w.rgb_f), None, None, None, None, None,
+                 None)
+            call("nerf_mse_fwd_bwd", ptr(w.rgb_f), ptr(y), n, n_total, 1.0, ptr(sums[1:2]), ptr(w.d_rgb_f))
+            # fine backward
+            through_z = not self.stop_grad_z
+            call("nerf_composite_bwd", ptr(w.raw_f), ptr(w.z_f), ptr(w.d_rgb_f), None, n, sf, ptr(w.d_raw_f),
+                 ptr(w.d_z_f) if through_z else None)
+            call("nerf_mlp_bwd", mf.cfg_ref, ptr(mf.params), ptr(mf.packed_for(mf.params)), ptr(w.xyz_f),
+                 ptr(w.view_f), ptr(w.saved_f), ptr(w.d_raw_f), n * sf, ptr(g_f), ptr(w.d_xyz_f) if through_z else None,
+                 ptr(w.ws_bwd), mf.mode_id)
+            if through_z:
+                # z_f -> xyz -> PE -> fine net, and z_f -> delta in the fine compositing, reach the coarse weights
+                call("nerf_encode_samples_bwd_z", mf.cfg_ref, ptr(o), ptr(d), ptr(w.z_f), ptr(w.d_xyz_f), n, sf,
+                     ptr(w.d_z_f), 1)
+                call("nerf_sample_pdf_bwd", ptr(w.w_c), ptr(w.z_c), ptr(w.u), ptr(w.perm), ptr(w.d_z_f), n, sc, sf,
+                     ptr(w.d_w_c))
+                d_w_c = w.d_w_c
+        # coarse backward
+        call("nerf_composite_bwd", ptr(w.raw_c), ptr(w.z_c), ptr(w.d_rgb_c), ptr(d_w_c), n, sc, ptr(w.d_raw_c), None)
+        call("nerf_mlp_bwd", mc.cfg_ref, ptr(mc.params), ptr(mc.packed_for(mc.params)), ptr(w.xyz_c), ptr(w.view_c),
+             ptr(w.saved_c), ptr(w.d_raw_c), n * sc, ptr(g_c), None, ptr(w.ws_bwd), mc.mode_id)
+        return g_c, g_f, sums
+
+    def _metrics(self, sums, n_total):
+        mse_c = sums[0] / (3.0 * n_total)
+        metrics = {}
+        loss = self.COARSE_LOSS_WEIGHT * mse_c
+        metrics["psnr_coarse"] = get_psnr(mse_c)
+        if self.model_fine is not None:
+            mse_f = sums[1] / (3.0 * n_total)
+            loss = loss + mse_f
+            metrics["psnr_fine"] = get_psnr(mse_f)
+        return {"loss": loss, **metrics}
+
+    def train_step(self, data) -> Dict:
+        """One optimisation step on a batch (rays_orig (B,4), rays_dirs (B,4), real_rgb (B,3)).
+
+        Returns the metrics dict {"loss", "psnr_coarse", "psnr_fine"} as device scalars (src/NeRF.py:170-178).
+        Host tensors are copied to the device here (pinned memory makes the copy asynchronous).  With
+        ``distribute()`` every rank passes the SAME global batch and works on its contiguous shard.
+        """
+        if self.optimizer is None:
+            raise RuntimeError("call compile(optimizer=Adam(lr)) before train_step")
+        rays_orig, rays_dirs, real_rgb = data
+        n_total = rays_orig.shape[0]
+        lo, hi = 0, n_total
+        if self.world_size > 1:
+            per = (n_total + self.world_size - 1) // self.world_size
+            lo, hi = min(n_total, self.rank * per), min(n_total, (self.rank + 1) * per)
+        to_dev = lambda t: t[lo:hi].to(device=self.device, dtype=torch.float32, non_blocking=True).contiguous()
+        o, d, y = to_dev(rays_orig), to_dev(rays_dirs), to_dev(real_rgb)
+        self.forward_backward(o, d, y, n_total_rays=n_total, ray_offset=lo)
+        g = self._grad_buffer()
+        if self.world_size > 1:
+            import torch.distributed as dist
+            dist.all_reduce(g, op=dist.ReduceOp.SUM, group=self._process_group)
+        self.apply_gradients(g)
+        self.step_counter += 1
+        return self._metrics(g[-2:], n_total)
+
+    def apply_gradients(self, g):
+        mc, mf = self.model_coarse, self.model_fine
+        n = mc.n_params + (mf.n_params if mf is not None else 0)
+        self.optimizer.apply_flat([mc.params] + ([mf.params] if mf is not None else []), g[:n])
+        mc.mark_updated()
+        if mf is not None:
+            mf.mark_updated()

@@ -1,0 +1,123 @@
+"""ctypes binding of libnerf_b200.so (the C ABI declared in include/nerf_b200.h).
+
+There is no CPU fallback: if the shared library is missing this module raises at import of the first op,
+and every compute entry point returns an error without a CUDA device.  PyTorch is used only for device
+memory and streams; tensors are handed over as raw device pointers.
+"""
+import ctypes
+import os
+from ctypes import POINTER, Structure, c_char_p, c_float, c_int32, c_int64, c_uint32, c_uint64, c_void_p
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libnerf_b200.so")
+
+MODE_FP32 = 0
+MODE_BF16 = 1
+
+
+class NetCfg(Structure):
+    """Mirror of struct nerf_net_cfg."""
+    _fields_ = [("n_pos_enc_xyz", c_int32), ("n_pos_enc_view", c_int32), ("n_angles", c_int32),
+                ("hidden", c_int32), ("last_hidden", c_int32), ("leaky_alpha", c_float)]
+
+
+class NerfLibraryError(RuntimeError):
+    pass
+
+
+_P = c_void_p
+_CFG = POINTER(NetCfg)
+
+# name -> (restype, argtypes); kept in the same order as include/nerf_b200.h
+SIGNATURES = {
+    "nerf_version": (c_char_p, []),
+    "nerf_last_error": (c_char_p, []),
+    "nerf_param_count": (c_int64, [_CFG]),
+    "nerf_xyz_enc_dim": (c_int32, [_CFG]),
+    "nerf_view_enc_dim": (c_int32, [_CFG]),
+    "nerf_ray_directions": (c_int32, [POINTER(c_float), c_float, c_int32, c_int32, c_int64, c_int64, _P, _P, _P]),
+    "nerf_stratified_z": (c_int32, [c_float, c_float, c_int64, c_int32, _P, c_uint64, c_uint32, c_uint64, _P, _P]),
+    "nerf_sample_along_rays": (c_int32, [_P, _P, _P, c_int64, c_int32, _P, _P]),
+    "nerf_view_directions": (c_int32, [_P, c_int64, c_int32, c_int32, _P, _P]),
+    "nerf_posenc_xyz": (c_int32, [_P, c_int64, c_int32, _P, _P]),
+    "nerf_posenc_views": (c_int32, [_P, c_int64, c_int32, c_int32, _P, _P]),
+    "nerf_posenc_xyz_bwd": (c_int32, [_P, _P, c_int64, c_int32, _P, _P]),
+    "nerf_encode_samples": (c_int32, [_CFG, _P, _P, _P, c_int64, c_int32, _P, _P, _P]),
+    "nerf_encode_samples_bwd_z": (c_int32, [_CFG, _P, _P, _P, _P, c_int64, c_int32, _P, c_int32, _P]),
+    "nerf_mlp_saved_bytes": (c_int64, [_CFG, c_int64, c_int32]),
+    "nerf_mlp_workspace_bytes": (c_int64, [_CFG, c_int64, c_int32, c_int32]),
+    "nerf_mlp_fwd": (c_int32, [_CFG, _P, _P, _P, _P, c_int64, _P, _P, _P, c_int32, _P]),
+    "nerf_mlp_bwd": (c_int32, [_CFG, _P, _P, _P, _P, _P, _P, c_int64, _P, _P, _P, c_int32, _P]),
+    "nerf_packed_bytes": (c_int64, [_CFG]),
+    "nerf_pack_weights": (c_int32, [_CFG, _P, _P, _P]),
+    "nerf_composite_fwd": (c_int32, [_P, _P, c_int64, c_int32, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "nerf_composite_bwd": (c_int32, [_P, _P, _P, _P, c_int64, c_int32, _P, _P, _P]),
+    "nerf_sample_pdf_fwd": (c_int32, [_P, _P, c_int64, c_int32, c_int32, _P, c_uint64, c_uint32, c_uint64, _P, _P, _P,
+                                      _P, _P]),
+    "nerf_sample_pdf_bwd": (c_int32, [_P, _P, _P, _P, _P, c_int64, c_int32, c_int32, _P, _P]),
+    "nerf_merge_sorted": (c_int32, [_P, c_int32, _P, c_int32, c_int64, _P, _P]),
+    "nerf_mse_fwd_bwd": (c_int32, [_P, _P, c_int64, c_int64, c_float, _P, _P, _P]),
+    "nerf_adam_step": (c_int32, [_P, _P, _P, _P, c_int64, c_float, c_float, c_float, c_float, c_int64, _P]),
+}
+
+_lib = None
+
+
+def load():
+    """Load libnerf_b200.so once; raise loudly when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise NerfLibraryError(
+            f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(nvcc, sm_100a). There is no CPU fallback.")
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the .so does not export a declared symbol
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def ptr(t):
+    """Device pointer of a contiguous tensor (None -> NULL)."""
+    if t is None:
+        return None
+    assert t.is_contiguous(), "tensor must be contiguous"
+    return t.data_ptr()
+
+
+def stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def check(status, what):
+    if status != 0:
+        msg = load().nerf_last_error().decode()
+        raise NerfLibraryError(f"{what} failed ({status}): {msg}")
+
+
+def call(name, *args):
+    """Call an int-returning entry point on the current torch CUDA stream and raise on error."""
+    lib = load()
+    status = getattr(lib, name)(*args, stream())
+    check(status, name)
+
+
+def require_cuda(t, name="tensor"):
+    if not (isinstance(t, torch.Tensor) and t.is_cuda):
+        raise NerfLibraryError(f"{name} must be a CUDA tensor: this framework has no CPU path")
+    return t
+
+
+def f32c(t, device=None):
+    """float32 contiguous CUDA tensor from tensor / ndarray / list."""
+    if not isinstance(t, torch.Tensor):
+        t = torch.as_tensor(t)
+    if device is None:
+        device = t.device if t.is_cuda else torch.device("cuda", torch.cuda.current_device())
+    return t.to(device=device, dtype=torch.float32).contiguous()

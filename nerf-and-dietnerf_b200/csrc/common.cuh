@@ -1,0 +1,122 @@
+// Shared helpers for libnerf_b200.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/nerf_b200.h"
+
+namespace nerf {
+
+void set_error(const char* fmt, ...);
+
+#define NERF_CHECK_ARG(cond, msg)                         \
+  do {                                                    \
+    if (!(cond)) {                                        \
+      nerf::set_error("%s: %s", __func__, msg);           \
+      return NERF_E_ARG;                                  \
+    }                                                     \
+  } while (0)
+
+#define NERF_CHECK_LAUNCH()                                                              \
+  do {                                                                                   \
+    cudaError_t e__ = cudaGetLastError();                                                \
+    if (e__ != cudaSuccess) {                                                            \
+      nerf::set_error("%s: CUDA error: %s", __func__, cudaGetErrorString(e__));          \
+      return NERF_E_CUDA;                                                                \
+    }                                                                                    \
+  } while (0)
+
+#define NERF_CUDA(call)                                                                  \
+  do {                                                                                   \
+    cudaError_t e__ = (call);                                                            \
+    if (e__ != cudaSuccess) {                                                            \
+      nerf::set_error("%s: %s failed: %s", __func__, #call, cudaGetErrorString(e__));    \
+      return NERF_E_CUDA;                                                                \
+    }                                                                                    \
+  } while (0)
+
+constexpr int kNumSMs = 148;  // B200
+
+inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// ---- network geometry ---------------------------------------------------------------------------------
+struct LayerDesc {
+  int in, out;
+  int64_t w_off, b_off;  // offsets (floats) into the flat parameter vector
+};
+
+struct NetGeom {
+  int dx, dv, hidden, last_hidden, n_layers;
+  bool view;
+  LayerDesc layers[12];
+  int64_t n_params;
+};
+
+inline bool make_geom(const nerf_net_cfg* cfg, NetGeom* g) {
+  if (!cfg || cfg->n_pos_enc_xyz < 0 || cfg->n_pos_enc_xyz > 16 || cfg->n_angles < 0 || cfg->n_angles > 2 ||
+      cfg->hidden <= 0 || cfg->last_hidden <= 0 || cfg->n_pos_enc_view < 0 || cfg->n_pos_enc_view > 16)
+    return false;
+  g->dx = 3 + 6 * cfg->n_pos_enc_xyz;
+  g->view = cfg->n_angles > 0;
+  g->dv = g->view ? 2 * cfg->n_pos_enc_view * (cfg->n_angles + 1) : 0;
+  g->hidden = cfg->hidden;
+  g->last_hidden = cfg->last_hidden;
+  int H = cfg->hidden, HL = cfg->last_hidden, n = 0;
+  int ins[12], outs[12];
+  ins[n] = g->dx; outs[n++] = H;
+  for (int i = 0; i < 3; ++i) { ins[n] = H; outs[n++] = H; }
+  ins[n] = g->dx + H; outs[n++] = H;
+  for (int i = 0; i < 3; ++i) { ins[n] = H; outs[n++] = H; }
+  if (g->view) {
+    ins[n] = H + g->dv; outs[n++] = HL;  // last hidden
+    ins[n] = HL; outs[n++] = 3;          // rgb
+    ins[n] = H + g->dv; outs[n++] = 1;   // sigma
+  } else {
+    ins[n] = H; outs[n++] = H;
+    ins[n] = H; outs[n++] = HL;
+    ins[n] = HL; outs[n++] = 3;
+    ins[n] = H; outs[n++] = 1;
+  }
+  g->n_layers = n;
+  int64_t off = 0;
+  for (int i = 0; i < n; ++i) {
+    g->layers[i].in = ins[i];
+    g->layers[i].out = outs[i];
+    g->layers[i].w_off = off;
+    off += (int64_t)ins[i] * outs[i];
+    g->layers[i].b_off = off;
+    off += outs[i];
+  }
+  g->n_params = off;
+  return true;
+}
+
+// ---- Philox4x32-10 (same stream as oracle/philox.py) -----------------------------------------------------
+#ifdef __CUDACC__
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+    uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+    c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+    k.x += 0x9E3779B9u;
+    k.y += 0xBB67AE85u;
+  }
+  return c;
+}
+
+__device__ __forceinline__ float bits_to_uniform(uint32_t w) {
+  return __uint_as_float((w & 0x7FFFFFu) | 0x3F800000u) - 1.0f;
+}
+
+// four uniforms: draws 4*block .. 4*block+3 of (ray, stream, step)
+__device__ __forceinline__ float4 philox_uniform4(uint64_t seed, uint32_t ray, uint32_t block, uint32_t stream_id,
+                                                  uint32_t step) {
+  uint4 r = philox4x32_10(make_uint4(ray, block, stream_id, step),
+                          make_uint2((uint32_t)(seed & 0xFFFFFFFFu), (uint32_t)(seed >> 32)));
+  return make_float4(bits_to_uniform(r.x), bits_to_uniform(r.y), bits_to_uniform(r.z), bits_to_uniform(r.w));
+}
+#endif
+
+}  // namespace nerf

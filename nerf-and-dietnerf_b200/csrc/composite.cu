@@ -1,0 +1,285 @@
+// K3: alpha compositing (ray_marching, src/UtilsNeuralRadianceField.py:88-115) forward and backward.
+//
+// HBM-bound: 44 B/sample + 12 B/ray with every reference output, 24 B/sample lean.
+// One warp per ray (= one scan segment).  Sample s of the ray lives in lane (s % 32), block (s / 32), so every
+// load/store instruction of the warp touches one contiguous 128/512-byte span.  The exclusive cumprod of
+// (1-alpha) is a Kogge-Stone warp-shuffle scan per 32-sample block with a running carry across blocks; the
+// backward needs the mirrored reverse exclusive cumsum of g*w.
+#include "common.cuh"
+
+namespace nerf {
+
+constexpr unsigned kFull = 0xffffffffu;
+
+__device__ __forceinline__ float warp_incl_scan_mul(float v, int lane) {
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    float o = __shfl_up_sync(kFull, v, d);
+    if (lane >= d) v *= o;
+  }
+  return v;
+}
+
+__device__ __forceinline__ float warp_incl_rscan_add(float v, int lane) {
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    float o = __shfl_down_sync(kFull, v, d);
+    if (lane + d < 32) v += o;
+  }
+  return v;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(kFull, v, d);
+  return v;
+}
+
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+// per-sample forward quantities
+struct SampleFwd {
+  float sigma, delta, alpha, x;  // x = 1 - alpha
+};
+
+__device__ __forceinline__ SampleFwd sample_fwd(float raw_sigma, float z_cur, float z_next, bool last) {
+  SampleFwd r;
+  r.sigma = fmaxf(raw_sigma, 0.f);
+  r.delta = last ? 1e9f : z_next - z_cur;
+  r.alpha = 1.0f - expf(-r.sigma * r.delta);
+  r.x = 1.0f - r.alpha;
+  return r;
+}
+
+template <int C>
+__global__ void __launch_bounds__(256) composite_fwd_kernel(const float4* __restrict__ raw4, const float* __restrict__ z,
+                                                            int64_t n_rays, int S, float* __restrict__ rgb,
+                                                            float* __restrict__ weights, float* __restrict__ cumprod,
+                                                            float* __restrict__ alpha_out, float* __restrict__ rgb_s,
+                                                            float* __restrict__ depth, float* __restrict__ acc) {
+  const int lane = threadIdx.x & 31;
+  const int64_t ray = blockIdx.x * (int64_t)(blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (ray >= n_rays) return;
+  const float4* raw_r = raw4 + ray * S;
+  const float* z_r = z + ray * S;
+
+  float4 raw[C];
+  float zc[C];
+#pragma unroll
+  for (int k = 0; k < C; ++k) {
+    int s = k * 32 + lane;
+    if (s < S) {
+      raw[k] = __ldcs(raw_r + s);
+      zc[k] = __ldcs(z_r + s);
+    } else {
+      raw[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+      zc[k] = 0.f;
+    }
+  }
+  float carry = 1.0f;
+  float r_acc = 0.f, g_acc = 0.f, b_acc = 0.f, d_acc = 0.f, a_acc = 0.f;
+#pragma unroll
+  for (int k = 0; k < C; ++k) {
+    int s = k * 32 + lane;
+    if (k * 32 >= S) break;
+    // z of the next sample: lane+1 of this block, or lane 0 of the next block
+    float z_next = __shfl_down_sync(kFull, zc[k], 1);
+    float z_next_blk = (k + 1 < C) ? __shfl_sync(kFull, zc[(k + 1 < C) ? k + 1 : k], 0) : 0.f;
+    if (lane == 31) z_next = z_next_blk;
+    bool valid = s < S;
+    SampleFwd f = sample_fwd(raw[k].w, zc[k], z_next, s == S - 1);
+    float x = valid ? f.x : 1.0f;
+    float incl = warp_incl_scan_mul(x, lane);
+    float excl = __shfl_up_sync(kFull, incl, 1);
+    if (lane == 0) excl = 1.0f;
+    float T = carry * excl;
+    carry *= __shfl_sync(kFull, incl, 31);
+    if (valid) {
+      float w = f.alpha * T;
+      float cr = sigmoidf_(raw[k].x), cg = sigmoidf_(raw[k].y), cb = sigmoidf_(raw[k].z);
+      r_acc += w * cr;
+      g_acc += w * cg;
+      b_acc += w * cb;
+      d_acc += w * zc[k];
+      a_acc += w;
+      int64_t o = ray * S + s;
+      if (weights) __stcs(weights + o, w);
+      if (cumprod) __stcs(cumprod + o, T);
+      if (alpha_out) __stcs(alpha_out + o, f.alpha);
+      if (rgb_s) {
+        __stcs(rgb_s + o * 3 + 0, cr);
+        __stcs(rgb_s + o * 3 + 1, cg);
+        __stcs(rgb_s + o * 3 + 2, cb);
+      }
+    }
+  }
+  r_acc = warp_sum(r_acc);
+  g_acc = warp_sum(g_acc);
+  b_acc = warp_sum(b_acc);
+  if (depth) d_acc = warp_sum(d_acc);
+  if (acc) a_acc = warp_sum(a_acc);
+  if (lane == 0) {
+    if (rgb) {
+      rgb[ray * 3 + 0] = r_acc;
+      rgb[ray * 3 + 1] = g_acc;
+      rgb[ray * 3 + 2] = b_acc;
+    }
+    if (depth) depth[ray] = d_acc;
+    if (acc) acc[ray] = a_acc;
+  }
+}
+
+template <int C>
+__global__ void __launch_bounds__(256) composite_bwd_kernel(const float4* __restrict__ raw4, const float* __restrict__ z,
+                                                            const float* __restrict__ d_rgb,
+                                                            const float* __restrict__ d_weights, int64_t n_rays, int S,
+                                                            float4* __restrict__ d_raw4, float* __restrict__ d_z) {
+  const int lane = threadIdx.x & 31;
+  const int64_t ray = blockIdx.x * (int64_t)(blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (ray >= n_rays) return;
+  const float4* raw_r = raw4 + ray * S;
+  const float* z_r = z + ray * S;
+  const float dr = __ldg(d_rgb + ray * 3 + 0), dg = __ldg(d_rgb + ray * 3 + 1), db = __ldg(d_rgb + ray * 3 + 2);
+
+  float4 raw[C];
+  float zc[C], T[C], gw[C], g[C];
+  SampleFwd f[C];
+#pragma unroll
+  for (int k = 0; k < C; ++k) {
+    int s = k * 32 + lane;
+    if (s < S) {
+      raw[k] = __ldcs(raw_r + s);
+      zc[k] = __ldcs(z_r + s);
+    } else {
+      raw[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+      zc[k] = 0.f;
+    }
+  }
+  // forward scan: T, w, g = dL/dw
+  float carry = 1.0f;
+#pragma unroll
+  for (int k = 0; k < C; ++k) {
+    int s = k * 32 + lane;
+    float z_next = __shfl_down_sync(kFull, zc[k], 1);
+    float z_next_blk = __shfl_sync(kFull, zc[(k + 1 < C) ? k + 1 : k], 0);
+    if (lane == 31) z_next = z_next_blk;
+    bool valid = s < S;
+    f[k] = sample_fwd(raw[k].w, zc[k], z_next, s == S - 1);
+    float x = valid ? f[k].x : 1.0f;
+    float incl = warp_incl_scan_mul(x, lane);
+    float excl = __shfl_up_sync(kFull, incl, 1);
+    if (lane == 0) excl = 1.0f;
+    T[k] = carry * excl;
+    carry *= __shfl_sync(kFull, incl, 31);
+    float cr = sigmoidf_(raw[k].x), cg = sigmoidf_(raw[k].y), cb = sigmoidf_(raw[k].z);
+    float gi = dr * cr + dg * cg + db * cb;
+    if (d_weights && valid) gi += __ldcs(d_weights + ray * S + s);
+    g[k] = valid ? gi : 0.f;
+    gw[k] = valid ? gi * f[k].alpha * T[k] : 0.f;
+  }
+  // reverse exclusive cumsum of g*w, then the per-sample gradients
+  float rcarry = 0.f;
+  float dd_first_of_next = 0.f;  // unused placeholder to keep the structure explicit
+  (void)dd_first_of_next;
+  float ddelta[C];
+#pragma unroll
+  for (int k = C - 1; k >= 0; --k) {
+    int s = k * 32 + lane;
+    bool valid = s < S;
+    float incl = warp_incl_rscan_add(gw[k], lane);
+    float excl = __shfl_down_sync(kFull, incl, 1);
+    if (lane == 31) excl = 0.f;
+    float R = rcarry + excl;
+    rcarry += __shfl_sync(kFull, incl, 0);
+    float x = f[k].x;
+    // TF: d cumprod / d x = div_no_nan(R, x); d alpha = g*T - that
+    float dalpha = g[k] * T[k] - (x == 0.f ? 0.f : R / x);
+    float dsig = dalpha * x * f[k].delta;
+    float ddel = (s == S - 1) ? 0.f : dalpha * x * f[k].sigma;
+    ddelta[k] = valid ? ddel : 0.f;
+    if (valid) {
+      float w = f[k].alpha * T[k];
+      float cr = sigmoidf_(raw[k].x), cg = sigmoidf_(raw[k].y), cb = sigmoidf_(raw[k].z);
+      float4 o;
+      o.x = w * dr * cr * (1.f - cr);
+      o.y = w * dg * cg * (1.f - cg);
+      o.z = w * db * cb * (1.f - cb);
+      o.w = raw[k].w > 0.f ? dsig : 0.f;
+      __stcs(d_raw4 + ray * S + s, o);
+    }
+  }
+  if (d_z) {
+    // d z_s = d delta_{s-1} - d delta_s
+#pragma unroll
+    for (int k = 0; k < C; ++k) {
+      int s = k * 32 + lane;
+      float prev = __shfl_up_sync(kFull, ddelta[k], 1);
+      float prev_blk = __shfl_sync(kFull, ddelta[(k > 0) ? k - 1 : 0], 31);
+      if (lane == 0) prev = (k > 0) ? prev_blk : 0.f;
+      if (s < S) __stcs(d_z + ray * S + s, prev - ddelta[k]);
+    }
+  }
+}
+
+template <int C>
+static int launch_fwd(const float* raw4, const float* z, int64_t n, int S, float* rgb, float* w, float* T, float* a,
+                      float* rgb_s, float* depth, float* acc, cudaStream_t st) {
+  const int warps = 8;
+  composite_fwd_kernel<C><<<(unsigned)ceil_div(n, warps), warps * 32, 0, st>>>((const float4*)raw4, z, n, S, rgb, w, T, a,
+                                                                              rgb_s, depth, acc);
+  return 0;
+}
+template <int C>
+static int launch_bwd(const float* raw4, const float* z, const float* d_rgb, const float* d_w, int64_t n, int S,
+                      float* d_raw4, float* d_z, cudaStream_t st) {
+  const int warps = 8;
+  composite_bwd_kernel<C><<<(unsigned)ceil_div(n, warps), warps * 32, 0, st>>>((const float4*)raw4, z, d_rgb, d_w, n, S,
+                                                                              (float4*)d_raw4, d_z);
+  return 0;
+}
+
+}  // namespace nerf
+
+using namespace nerf;
+
+#define DISPATCH_C(S, CALL)                 \
+  do {                                      \
+    int c__ = ((S) + 31) / 32;              \
+    if (c__ <= 1) { CALL(1); }              \
+    else if (c__ <= 2) { CALL(2); }         \
+    else if (c__ <= 4) { CALL(4); }         \
+    else if (c__ <= 6) { CALL(6); }         \
+    else if (c__ <= 8) { CALL(8); }         \
+    else if (c__ <= 16) { CALL(16); }       \
+    else { CALL(32); }                      \
+  } while (0)
+
+extern "C" {
+
+int nerf_composite_fwd(const float* raw4, const float* z, int64_t n_rays, int32_t n_samples, float* rgb, float* weights,
+                       float* cumprod, float* alpha, float* rgb_s, float* depth, float* acc, void* stream) {
+  NERF_CHECK_ARG(raw4 && z, "null input");
+  NERF_CHECK_ARG(n_rays >= 0 && n_samples > 0 && n_samples <= 1024, "n_samples must be in [1,1024]");
+  if (n_rays == 0) return NERF_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+#define CALL(C) launch_fwd<C>(raw4, z, n_rays, n_samples, rgb, weights, cumprod, alpha, rgb_s, depth, acc, st)
+  DISPATCH_C(n_samples, CALL);
+#undef CALL
+  NERF_CHECK_LAUNCH();
+  return NERF_OK;
+}
+
+int nerf_composite_bwd(const float* raw4, const float* z, const float* d_rgb, const float* d_weights_or_null,
+                       int64_t n_rays, int32_t n_samples, float* d_raw4, float* d_z_or_null, void* stream) {
+  NERF_CHECK_ARG(raw4 && z && d_rgb && d_raw4, "null pointer");
+  NERF_CHECK_ARG(n_rays >= 0 && n_samples > 0 && n_samples <= 1024, "n_samples must be in [1,1024]");
+  if (n_rays == 0) return NERF_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+#define CALL(C) launch_bwd<C>(raw4, z, d_rgb, d_weights_or_null, n_rays, n_samples, d_raw4, d_z_or_null, st)
+  DISPATCH_C(n_samples, CALL);
+#undef CALL
+  NERF_CHECK_LAUNCH();
+  return NERF_OK;
+}
+
+}  // extern "C"

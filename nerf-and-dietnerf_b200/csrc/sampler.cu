@@ -1,0 +1,259 @@
+// Hierarchical (inverse-CDF) sampling: get_z_vals_from_prob_dist_func, src/UtilsCV.py:502-539, forward and the
+// gradient w.r.t. `weights` that TF autodiff produces inside NeRF.train_step (the reference does not detach
+// z_from_dist, src/NeRF.py:155), plus the per-ray sorted merge of src/NeRF.py:132.
+//
+// Bit-exact indices: the searchsorted result depends on the fp32 summation order of reduce_sum and cumsum.
+// The canonical order (shared with oracle/nerf_oracle.py) is sequential left-to-right fp32 with IEEE division,
+// so one lane walks the S<=1024 entries of a ray that the whole warp staged in shared memory with coalesced
+// loads; everything else (pdf, search, interpolation, rank sort) is lane-parallel.  1 KB/ray of HBM traffic.
+#include "common.cuh"
+
+namespace nerf {
+
+constexpr unsigned kFullMask = 0xffffffffu;
+constexpr int kWarpsPerBlock = 4;
+
+struct RayCdf {
+  float* w;    // [S] weights, then pdf
+  float* cdf;  // [S]
+  float* z;    // [S]
+};
+
+// Stage one ray and build pdf/cdf in the canonical order. Returns (sum + eps).
+__device__ __forceinline__ float build_cdf(const float* __restrict__ weights, const float* __restrict__ z, int S,
+                                           int lane, float* sw, float* scdf, float* sz) {
+  for (int i = lane; i < S; i += 32) {
+    sw[i] = __ldcs(weights + i);
+    sz[i] = __ldcs(z + i);
+  }
+  __syncwarp();
+  float total = 0.f;
+  if (lane == 0) {
+    for (int i = 0; i < S; ++i) total = __fadd_rn(total, sw[i]);
+  }
+  total = __shfl_sync(kFullMask, total, 0);
+  const float denom = __fadd_rn(total, 1e-7f);  // EPS, src/UtilsCV.py:30
+  for (int i = lane; i < S; i += 32) scdf[i] = __fdiv_rn(sw[i], denom);  // pdf for now
+  __syncwarp();
+  if (lane == 0) {
+    float run = 0.f;
+    for (int i = 0; i < S; ++i) {
+      run = __fadd_rn(run, scdf[i]);
+      scdf[i] = run;
+    }
+  }
+  __syncwarp();
+  return denom;
+}
+
+struct Draw {
+  int b, t;
+  float lo, hi, zlo, zhi, den;
+  bool floored;
+};
+
+__device__ __forceinline__ Draw locate(const float* scdf, const float* sz, int S, float u, int* idx_out) {
+  // idx = #{i : cdf_i < u}  (tf.searchsorted side='left')
+  int lo_i = 0, hi_i = S;
+  while (lo_i < hi_i) {
+    int mid = (lo_i + hi_i) >> 1;
+    if (scdf[mid] < u) lo_i = mid + 1; else hi_i = mid;
+  }
+  int idx = lo_i;
+  if (idx_out) *idx_out = idx;
+  Draw d;
+  d.b = max(0, idx - 1);
+  d.t = min(S - 1, idx);
+  d.lo = scdf[d.b];
+  d.hi = scdf[d.t];
+  int zb = min(max(d.b, 0), S - 2), zt = min(max(d.t, 0), S - 2);
+  d.zlo = __fmul_rn(0.5f, __fadd_rn(sz[zb + 1], sz[zb]));
+  d.zhi = __fmul_rn(0.5f, __fadd_rn(sz[zt + 1], sz[zt]));
+  float den = __fsub_rn(d.hi, d.lo);
+  d.floored = den < 1e-5f;
+  d.den = d.floored ? 1e-5f : den;
+  return d;
+}
+
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+sample_pdf_fwd_kernel(const float* __restrict__ weights, const float* __restrict__ z, int64_t n_rays, int S, int Nf,
+                      const float* __restrict__ u_in, uint64_t seed, uint32_t step, uint64_t ray_offset,
+                      float* __restrict__ z_new, int* __restrict__ idx_out, int* __restrict__ perm_out,
+                      float* __restrict__ u_out) {
+  extern __shared__ float smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t ray = blockIdx.x * (int64_t)kWarpsPerBlock + warp;
+  if (ray >= n_rays) return;
+  float* base = smem + (size_t)warp * (3 * S + Nf);
+  float *sw = base, *scdf = base + S, *sz = base + 2 * S, *szs = base + 3 * S;
+  build_cdf(weights + ray * S, z + ray * S, S, lane, sw, scdf, sz);
+
+  const int n_blocks = (Nf + 3) / 4;
+  for (int blk = lane; blk < n_blocks; blk += 32) {
+    float u4[4];
+    if (u_in) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) u4[k] = (blk * 4 + k < Nf) ? __ldcs(u_in + ray * Nf + blk * 4 + k) : 0.f;
+    } else {
+      float4 r = philox_uniform4(seed, (uint32_t)(ray + ray_offset), (uint32_t)blk, 1u, step);
+      u4[0] = r.x; u4[1] = r.y; u4[2] = r.z; u4[3] = r.w;
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      int j = blk * 4 + k;
+      if (j >= Nf) break;
+      int idx;
+      Draw d = locate(scdf, sz, S, u4[k], &idx);
+      float t = __fdiv_rn(__fsub_rn(u4[k], d.lo), d.den);
+      szs[j] = __fadd_rn(d.zlo, __fmul_rn(t, __fsub_rn(d.zhi, d.zlo)));
+      if (idx_out) idx_out[ray * Nf + j] = idx;
+      if (u_out) u_out[ray * Nf + j] = u4[k];
+    }
+  }
+  __syncwarp();
+  // stable rank sort (tf.sort ascending; ties keep draw order like the oracle's stable sort)
+  for (int j = lane; j < Nf; j += 32) {
+    float v = szs[j];
+    int rank = 0;
+    for (int k = 0; k < Nf; ++k) {
+      float o = szs[k];
+      rank += (o < v) || (o == v && k < j);
+    }
+    z_new[ray * Nf + rank] = v;
+    if (perm_out) perm_out[ray * Nf + rank] = j;
+  }
+}
+
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+sample_pdf_bwd_kernel(const float* __restrict__ weights, const float* __restrict__ z, const float* __restrict__ u,
+                      const int* __restrict__ perm, const float* __restrict__ d_z_new, int64_t n_rays, int S, int Nf,
+                      float* __restrict__ d_weights) {
+  extern __shared__ float smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t ray = blockIdx.x * (int64_t)kWarpsPerBlock + warp;
+  if (ray >= n_rays) return;
+  // layout per warp: w[S] cdf[S] z[S] dcdf[S] | dzs[Nf] dlo[Nf] dhi[Nf] bt[Nf] (ints)
+  float* base = smem + (size_t)warp * (4 * S + 4 * Nf);
+  float *sw = base, *scdf = base + S, *sz = base + 2 * S, *sdc = base + 3 * S;
+  float *sdz = base + 4 * S, *sdlo = sdz + Nf, *sdhi = sdlo + Nf;
+  int* sbt = reinterpret_cast<int*>(sdhi + Nf);
+  const float denom = build_cdf(weights + ray * S, z + ray * S, S, lane, sw, scdf, sz);
+
+  for (int k = lane; k < Nf; k += 32) sdz[perm[ray * Nf + k]] = __ldcs(d_z_new + ray * Nf + k);
+  for (int i = lane; i < S; i += 32) sdc[i] = 0.f;
+  __syncwarp();
+  for (int j = lane; j < Nf; j += 32) {
+    float uj = __ldcs(u + ray * Nf + j);
+    Draw d = locate(scdf, sz, S, uj, nullptr);
+    float dt = sdz[j] * (d.zhi - d.zlo);
+    float num = uj - d.lo;
+    float dlo = -dt / d.den, dhi = 0.f;
+    if (!d.floored) {
+      float q = dt * num / (d.den * d.den);
+      dlo += q;
+      dhi = -q;
+    }
+    sdlo[j] = dlo;
+    sdhi[j] = dhi;
+    sbt[j] = d.b | (d.t << 16);
+  }
+  __syncwarp();
+  if (lane == 0) {
+    // deterministic scatter-add of the per-draw cdf gradients, then reverse cumsum -> d pdf (in place)
+    for (int j = 0; j < Nf; ++j) {
+      int b = sbt[j] & 0xffff, t = sbt[j] >> 16;
+      sdc[b] += sdlo[j];
+      sdc[t] += sdhi[j];
+    }
+    float run = 0.f;
+    for (int i = S - 1; i >= 0; --i) {
+      run += sdc[i];
+      sdc[i] = run;
+    }
+  }
+  __syncwarp();
+  // pdf = w / denom, denom = sum(w) + eps :  d w_k = dpdf_k/denom - sum_j dpdf_j w_j / denom^2
+  float part = 0.f;
+  for (int i = lane; i < S; i += 32) part += sdc[i] * sw[i];
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) part += __shfl_xor_sync(kFullMask, part, d);
+  const float corr = part / (denom * denom);
+  for (int i = lane; i < S; i += 32) d_weights[ray * S + i] = sdc[i] / denom - corr;
+}
+
+__global__ void merge_sorted_kernel(const float* __restrict__ a, int sa, const float* __restrict__ b, int sb,
+                                    int64_t n_rays, float* __restrict__ out) {
+  const int st = sa + sb;
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n_rays * st) return;
+  int64_t ray = i / st;
+  int j = (int)(i % st);
+  const float* ar = a + ray * sa;
+  const float* br = b + ray * sb;
+  float v;
+  int rank;
+  if (j < sa) {  // element of a: rank = j + #{b < v}
+    v = ar[j];
+    int lo = 0, hi = sb;
+    while (lo < hi) { int m = (lo + hi) >> 1; if (br[m] < v) lo = m + 1; else hi = m; }
+    rank = j + lo;
+  } else {       // element of b: rank = jb + #{a <= v}
+    int jb = j - sa;
+    v = br[jb];
+    int lo = 0, hi = sa;
+    while (lo < hi) { int m = (lo + hi) >> 1; if (ar[m] <= v) lo = m + 1; else hi = m; }
+    rank = jb + lo;
+  }
+  out[ray * st + rank] = v;
+}
+
+}  // namespace nerf
+
+using namespace nerf;
+
+extern "C" {
+
+int nerf_sample_pdf_fwd(const float* weights, const float* z, int64_t n_rays, int32_t n_samples, int32_t n_new,
+                        const float* u_or_null, uint64_t seed, uint32_t step, uint64_t ray_offset, float* z_new,
+                        int32_t* idx_or_null, int32_t* perm_or_null, float* u_out_or_null, void* stream) {
+  NERF_CHECK_ARG(weights && z && z_new, "null pointer");
+  NERF_CHECK_ARG(n_rays >= 0 && n_samples >= 2 && n_samples <= 1024 && n_new > 0 && n_new <= 1024,
+                 "need 2 <= n_samples <= 1024 and 1 <= n_new <= 1024");
+  if (n_rays == 0) return NERF_OK;
+  size_t smem = (size_t)kWarpsPerBlock * (3 * n_samples + n_new) * sizeof(float);
+  if (smem > 48 * 1024)
+    NERF_CUDA(cudaFuncSetAttribute(sample_pdf_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  sample_pdf_fwd_kernel<<<(unsigned)ceil_div(n_rays, kWarpsPerBlock), kWarpsPerBlock * 32, smem, (cudaStream_t)stream>>>(
+      weights, z, n_rays, n_samples, n_new, u_or_null, seed, step, ray_offset, z_new, idx_or_null, perm_or_null,
+      u_out_or_null);
+  NERF_CHECK_LAUNCH();
+  return NERF_OK;
+}
+
+int nerf_sample_pdf_bwd(const float* weights, const float* z, const float* u, const int32_t* perm, const float* d_z_new,
+                        int64_t n_rays, int32_t n_samples, int32_t n_new, float* d_weights, void* stream) {
+  NERF_CHECK_ARG(weights && z && u && perm && d_z_new && d_weights, "null pointer");
+  NERF_CHECK_ARG(n_rays >= 0 && n_samples >= 2 && n_samples <= 1024 && n_new > 0 && n_new <= 1024,
+                 "need 2 <= n_samples <= 1024 and 1 <= n_new <= 1024");
+  if (n_rays == 0) return NERF_OK;
+  size_t smem = (size_t)kWarpsPerBlock * (4 * n_samples + 4 * n_new) * sizeof(float);
+  if (smem > 48 * 1024)
+    NERF_CUDA(cudaFuncSetAttribute(sample_pdf_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  sample_pdf_bwd_kernel<<<(unsigned)ceil_div(n_rays, kWarpsPerBlock), kWarpsPerBlock * 32, smem, (cudaStream_t)stream>>>(
+      weights, z, u, perm, d_z_new, n_rays, n_samples, n_new, d_weights);
+  NERF_CHECK_LAUNCH();
+  return NERF_OK;
+}
+
+int nerf_merge_sorted(const float* z_a, int32_t sa, const float* z_b, int32_t sb, int64_t n_rays, float* out,
+                      void* stream) {
+  NERF_CHECK_ARG(z_a && z_b && out, "null pointer");
+  NERF_CHECK_ARG(sa > 0 && sb > 0 && n_rays >= 0, "bad shape");
+  if (n_rays == 0) return NERF_OK;
+  int64_t total = n_rays * (sa + sb);
+  merge_sorted_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, (cudaStream_t)stream>>>(z_a, sa, z_b, sb, n_rays, out);
+  NERF_CHECK_LAUNCH();
+  return NERF_OK;
+}
+
+}  // extern "C"

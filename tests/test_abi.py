@@ -1,0 +1,77 @@
+"""CPU checks of the drop-in boundary: the C-ABI library builds, loads, and exports exactly the symbols that
+include/nerf_b200.h declares; argument errors are reported without a GPU; the host mirror keeps the reference's
+names.  No compute is launched here."""
+import ctypes
+import os
+import re
+
+import pytest
+
+from conftest import ROOT
+
+
+def _header_symbols():
+    text = open(os.path.join(ROOT, "include", "nerf_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(nerf_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol(pkg):
+    lib = ctypes.CDLL(pkg.LIB_PATH)
+    names = _header_symbols()
+    assert len(names) >= 25
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/nerf_b200.h but not exported"
+    assert set(pkg._lib.SIGNATURES) == set(names), "ctypes table and header disagree"
+
+
+def test_version_and_geometry(pkg):
+    lib = pkg.load()
+    assert b"sm_100a" in lib.nerf_version()
+    cfg = pkg.NetCfg(5, 4, 2, 256, 128, 0.05)
+    assert lib.nerf_param_count(ctypes.byref(cfg)) == 514332          # 514 332 params/net
+    assert lib.nerf_xyz_enc_dim(ctypes.byref(cfg)) == 33
+    assert lib.nerf_view_enc_dim(ctypes.byref(cfg)) == 24
+    cfg0 = pkg.NetCfg(5, 4, 0, 256, 128, 0.05)
+    assert lib.nerf_view_enc_dim(ctypes.byref(cfg0)) == 0
+    from oracle import nerf_oracle as O
+    assert lib.nerf_param_count(ctypes.byref(cfg0)) == O.NetCfg(5, 4, 0).n_params
+    cfg1 = pkg.NetCfg(5, 2, 1, 256, 128, 0.05)
+    assert lib.nerf_view_enc_dim(ctypes.byref(cfg1)) == 8
+
+
+def test_argument_errors_are_reported(pkg):
+    lib = pkg.load()
+    # n_angles_for_model outside {1,2}: the reference raises Exception('... should be 1 or 2.') (src/UtilsCV.py:138)
+    st = lib.nerf_view_directions(ctypes.c_void_p(16), 1, 1, 3, ctypes.c_void_p(16), None)
+    assert st == -1 and b"should be 1 or 2" in lib.nerf_last_error()
+    st = lib.nerf_composite_fwd(None, None, 1, 64, None, None, None, None, None, None, None, None)
+    assert st == -1
+    bad = pkg.NetCfg(5, 4, 7, 256, 128, 0.05)
+    assert lib.nerf_param_count(ctypes.byref(bad)) < 0
+
+
+def test_host_mirror_keeps_reference_names(pkg):
+    ucv, unrf = pkg.UtilsCV, pkg.UtilsNeuralRadianceField
+    for name in ("get_rays_directions", "get_z_values", "get_z_vals_from_prob_dist_func", "sample_along_rays",
+                 "get_view_directions"):
+        assert callable(getattr(ucv, name))
+    for name in ("split_to_batches", "positional_encoding_for_views", "positional_encoding_for_xyz", "ray_marching",
+                 "get_psnr", "get_psnr_for_image", "prepare_ds", "c2w_to_rays_prepare_ds", "render_rays",
+                 "model_predict", "get_num_of_batches"):
+        assert callable(getattr(unrf, name))
+    for name in ("render", "call", "train_step", "render_rays", "render_image", "init_network", "get_nerf_model_path"):
+        assert hasattr(pkg.NeRFModel, name)
+    assert pkg.DietNeRFModel.COARSE_LOSS_WEIGHT == 2.0
+    assert str(pkg.NeRFModel.get_nerf_model_path("x", 7)).endswith("saved_weights/NeRF_model_epoch_007.h5")
+    assert unrf.get_num_of_batches(4096, 70, 50, 50) == 42
+    assert unrf.get_size_of_splits(4096, 10000) == [4096, 4096, 1808]
+    assert unrf.get_size_of_splits(4096, 2500) == [2500]
+    assert unrf.get_size_of_splits(100, 200) == [100, 100]
+
+
+def test_missing_library_fails_loudly(pkg, monkeypatch):
+    monkeypatch.setattr(pkg._lib, "_lib", None)
+    monkeypatch.setattr(pkg._lib, "LIB_PATH", "/nonexistent/libnerf_b200.so")
+    with pytest.raises(pkg.NerfLibraryError):
+        pkg._lib.load()

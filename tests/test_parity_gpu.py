@@ -1,0 +1,407 @@
+"""GPU parity tests: every kernel of the hot path, called through the C ABI / host mirror, against the CPU oracle
+on the same seeded inputs.  Tolerances (stated by BASELINE.json north_star):
+  * sample indices: bit-exact for a fixed RNG stream;
+  * fp32 mode: rendered rgb/depth within 1e-5 max-abs;
+  * bf16 mode: within 1e-3 max-abs.
+"""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import FAR, NEAR, net_config, oracle_cfg, random_rays, render_config, sphere_pose, test_params
+from oracle import nerf_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+FP32_TOL = 1e-5
+BF16_TOL = 1e-3
+
+
+def dev(t):
+    return t.cuda().contiguous()
+
+
+# ---- K1: rays, depths, positions, encodings ---------------------------------------------------------------------------
+@pytest.mark.parametrize("h,w", [(50, 50), (17, 31), (256, 256)])
+def test_ray_directions(pkg, h, w):
+    c2w = sphere_pose(0.7, 0.3, 1.1)
+    ref = O.get_rays_directions(h, w, 0.46134, c2w)
+    got = pkg.UtilsCV.get_rays_directions(h, w, 0.46134, c2w)
+    assert got.shape == (h, w, 4)
+    assert (got.cpu() - ref).abs().max().item() < 1e-6
+    assert torch.all(got[..., 3] == 0)
+    orig, dirs, rgb = pkg.UtilsNeuralRadianceField.c2w_to_rays_prepare_ds(c2w, 0.46134, torch.rand(h, w, 3))
+    assert orig.shape == (h * w, 4) and torch.equal(orig[0].cpu(), torch.tensor(c2w[:, 3]))
+    # sharded range == slice of the full image
+    part = pkg.UtilsCV.get_rays_directions(h, w, 0.46134, c2w, ray_begin=h * w // 3, n_rays=h * w // 2)
+    assert torch.equal(part, got.reshape(-1, 4)[h * w // 3: h * w // 3 + h * w // 2])
+
+
+@pytest.mark.parametrize("n,s", [(1, 64), (2500, 64), (333, 55), (64, 1)])
+def test_stratified_z_bit_exact(pkg, n, s):
+    jit = O.stratified_jitter(5, 9, n, s, ray_offset=100)
+    ref = O.get_z_values(NEAR, FAR, n, s, jit)
+    got = pkg.UtilsCV.get_z_values(NEAR, FAR, n, 1, s, seed=5, step=9, ray_offset=100)[:, 0, :]
+    assert torch.equal(got.cpu(), ref), "Philox stream or z arithmetic differs from the oracle"
+    got2 = pkg.UtilsCV.get_z_values(NEAR, FAR, n, 1, s, jitter=dev(jit))[:, 0, :]
+    assert torch.equal(got2.cpu(), ref)
+    if s > 1:
+        assert torch.all(got[:, 1:] > got[:, :-1])          # strictly increasing
+        assert got.min().item() >= np.float32(NEAR)          # last sample may overshoot far (reference quirk)
+
+
+def test_sample_along_rays_and_view_dirs(pkg):
+    o, d = random_rays(300, 1)
+    z = O.get_z_values(NEAR, FAR, 300, 64, torch.rand(300, 64))
+    ref = O.sample_along_rays(o, d, z)
+    got = pkg.UtilsCV.sample_along_rays(dev(o), dev(d), dev(z))
+    assert torch.equal(got.cpu(), ref)
+    for a in (1, 2):
+        refv = O.get_view_directions(ref[..., :3], d, a)
+        gotv = pkg.UtilsCV.get_view_directions(got[..., :3], dev(d), a)
+        assert torch.equal(gotv.cpu(), refv)
+    with pytest.raises(Exception, match="should be 1 or 2"):
+        pkg.UtilsCV.get_view_directions(got[..., :3], dev(d), 3)
+
+
+@pytest.mark.parametrize("L", [0, 1, 5, 10])
+def test_posenc_xyz(pkg, L):
+    x = (torch.rand(1000, 3, generator=torch.Generator().manual_seed(L)) * 4 - 2)
+    ref = O.positional_encoding_for_xyz(x, L)
+    got = pkg.UtilsNeuralRadianceField.positional_encoding_for_xyz(dev(x), L)
+    assert got.shape == ref.shape == (1000, 3 + 6 * L)
+    # arguments reach 2^(L-1)*pi*|x|: one ulp of the argument is the error floor of any sin/cos implementation
+    tol = 2e-6 * max(1.0, 2.0 ** (L - 5))
+    assert (got.cpu() - ref).abs().max().item() < tol
+
+
+@pytest.mark.parametrize("c,L", [(3, 4), (2, 4), (3, 2)])
+def test_posenc_views(pkg, c, L):
+    x = torch.randn(777, c, generator=torch.Generator().manual_seed(c * 10 + L))
+    ref = O.positional_encoding_for_views(x, L)
+    got = pkg.UtilsNeuralRadianceField.positional_encoding_for_views(dev(x), L)
+    assert got.shape == ref.shape == (777, 2 * L * c)
+    assert (got.cpu() - ref).abs().max().item() < 2e-6
+
+
+def test_posenc_xyz_backward(pkg):
+    x = (torch.rand(500, 3) * 2 - 1).requires_grad_(True)
+    g = torch.randn(500, 33)
+    O.positional_encoding_for_xyz(x, 5).backward(g)
+    xd = dev(x.detach()).requires_grad_(True)
+    pkg.UtilsNeuralRadianceField.positional_encoding_for_xyz(xd, 5).backward(dev(g))
+    assert (xd.grad.cpu() - x.grad).abs().max().item() < 1e-4 * x.grad.abs().max().item()
+
+
+def test_encode_samples_matches_unfused(pkg):
+    import ctypes
+    o, d = random_rays(100, 2)
+    z = O.get_z_values(NEAR, FAR, 100, 64, torch.rand(100, 64))
+    for a, lv in ((2, 4), (1, 4), (2, 2), (0, 4)):
+        cfg = pkg.NetCfg(5, lv, a, 256, 128, 0.05)
+        dx, dv = 33, 2 * lv * (a + 1) if a else 0
+        xyz = torch.empty(6400, dx, device="cuda")
+        view = torch.empty(6400, dv, device="cuda") if dv else None
+        pkg._lib.call("nerf_encode_samples", ctypes.byref(cfg), dev(o).data_ptr(), dev(d).data_ptr(),
+                      dev(z).data_ptr(), 100, 64, xyz.data_ptr(), view.data_ptr() if dv else None)
+        coords = O.sample_along_rays(o, d, z)[..., :3]
+        assert (xyz.cpu() - O.positional_encoding_for_xyz(coords.reshape(-1, 3), 5)).abs().max().item() < 2e-6
+        if dv:
+            refv = O.positional_encoding_for_views(O.get_view_directions(coords, d, a), lv)
+            assert (view.cpu() - refv).abs().max().item() < 2e-6
+
+
+# ---- K3: compositing ---------------------------------------------------------------------------------------------------
+def _raw_and_z(n, s, seed, sigma_scale=40.0):
+    g = torch.Generator().manual_seed(seed)
+    raw = torch.randn(n, s, 4, generator=g)
+    raw[..., 3] = raw[..., 3] * sigma_scale           # relu -> about half empty, half very dense (alpha saturates)
+    raw[: n // 8, :, 3] = -1.0                         # completely empty rays
+    raw[n // 8: n // 4, 0, 3] = 1e4                    # opaque at the first sample
+    z = O.get_z_values(NEAR, FAR, n, s, torch.rand(n, s, generator=g)) if s > 1 else torch.full((n, 1), 1.0)
+    return raw, z
+
+
+@pytest.mark.parametrize("n,s", [(4096, 64), (1000, 128), (999, 192), (50, 165), (33, 1), (7, 300), (3, 1000)])
+def test_composite_forward(pkg, n, s):
+    raw, z = _raw_and_z(n, s, s)
+    ref = O.ray_marching(raw, z)
+    got = pkg.UtilsNeuralRadianceField.ray_marching(dev(raw), dev(z))
+    names = ["rgb", "weights", "cumprod", "alpha", "rgb_s"]
+    for name, r, g_ in zip(names, ref, got):
+        assert g_.shape == r.shape
+        assert (g_.cpu() - r).abs().max().item() < 2e-6, name
+    rgb, w, depth, acc = pkg.UtilsNeuralRadianceField.ray_marching_lean(dev(raw), dev(z))
+    rd, ra = O.depth_and_acc(ref[1], z)
+    assert (depth.cpu() - rd).abs().max().item() < 1e-5 and (acc.cpu() - ra).abs().max().item() < 2e-6
+    assert torch.equal(rgb, got[0]) and torch.equal(w, got[1])
+    assert acc.max().item() <= 1.0 + 1e-5
+
+
+@pytest.mark.parametrize("n,s,with_dw", [(512, 64, True), (300, 128, False), (100, 192, True), (20, 165, True),
+                                         (5, 300, True)])
+def test_composite_backward(pkg, n, s, with_dw):
+    raw, z = _raw_and_z(n, s, 100 + s, sigma_scale=8.0)
+    g = torch.Generator().manual_seed(s)
+    d_rgb = torch.randn(n, 3, generator=g)
+    d_w = torch.randn(n, s, generator=g) if with_dw else None
+    raw_r, z_r = raw.clone().requires_grad_(True), z.clone().requires_grad_(True)
+    out = O.ray_marching(raw_r, z_r)
+    loss = (out[0] * d_rgb).sum() + ((out[1] * d_w).sum() if with_dw else 0.0)
+    loss.backward()
+    raw_g, z_g = dev(raw).requires_grad_(True), dev(z).requires_grad_(True)
+    got = pkg.UtilsNeuralRadianceField.ray_marching(raw_g, z_g)
+    lg = (got[0] * dev(d_rgb)).sum() + ((got[1] * dev(d_w)).sum() if with_dw else 0.0)
+    lg.backward()
+    scale = raw_r.grad.abs().max().item()
+    assert (raw_g.grad.cpu() - raw_r.grad).abs().max().item() < 2e-5 * max(scale, 1.0)
+    zscale = z_r.grad.abs().max().item()
+    assert (z_g.grad.cpu() - z_r.grad).abs().max().item() < 2e-5 * max(zscale, 1.0)
+
+
+def test_composite_full_size_properties(pkg):
+    """BASELINE size (one 256x256 frame, 192 samples): size-independent invariants of the compositing."""
+    n, s = 65536, 192
+    g = torch.Generator(device="cuda").manual_seed(0)
+    raw = torch.randn(n, s, 4, device="cuda", generator=g)
+    raw[..., 3] *= 20
+    z = torch.sort(torch.rand(n, s, device="cuda", generator=g) * 2 + 0.5, dim=-1).values
+    rgb, w, T, alpha, rgb_s = pkg.UtilsNeuralRadianceField.ray_marching(raw, z)
+    assert torch.all(T[:, 1:] <= T[:, :-1] + 1e-7) and torch.all(T[:, 0] == 1)
+    assert (w - alpha * T).abs().max().item() < 1e-6
+    assert w.sum(-1).max().item() <= 1 + 1e-4
+    # acc + final transmittance == 1 (telescoping sum), rgb is a convex combination of the per-sample colours
+    assert ((w.sum(-1) + T[:, -1] * (1 - alpha[:, -1])) - 1).abs().max().item() < 1e-4
+    assert rgb.min().item() >= 0 and rgb.max().item() <= 1 + 1e-5
+    # linearity of the backward in d_rgb
+    raw.requires_grad_(True)
+    r1 = pkg.UtilsNeuralRadianceField.ray_marching(raw, z)[0]
+    d = torch.randn_like(r1)
+    g1, = torch.autograd.grad(r1, raw, d, retain_graph=True)
+    g2, = torch.autograd.grad(r1, raw, 3 * d)
+    assert (3 * g1 - g2).abs().max().item() < 1e-4 * g2.abs().max().item()
+
+
+# ---- hierarchical sampling -----------------------------------------------------------------------------------------------
+def _weights_and_z(n, s, seed):
+    g = torch.Generator().manual_seed(seed)
+    raw, z = _raw_and_z(n, s, seed, sigma_scale=10.0)
+    w = O.ray_marching(raw, z)[1]
+    w[: max(1, n // 16)] = 0.0                      # empty rays: all samples collapse onto mid[S-2]
+    return w.contiguous(), z
+
+
+@pytest.mark.parametrize("n,s,nf", [(2048, 64, 128), (257, 64, 64), (100, 55, 110), (10, 2, 5), (64, 192, 128)])
+def test_sample_pdf_bit_exact(pkg, n, s, nf):
+    w, z = _weights_and_z(n, s, nf)
+    u = O.importance_uniforms(3, 4, n, nf, ray_offset=17)
+    ref_z, ref_idx, ref_perm, ref_unsorted = O.get_z_vals_from_prob_dist_func(w, z, nf, u, return_aux=True)
+    got_z, got_idx, got_perm = pkg.UtilsCV.get_z_vals_from_prob_dist_func(dev(w), dev(z), nf, seed=3, step=4,
+                                                                          ray_offset=17, return_aux=True)
+    assert torch.equal(got_idx.cpu(), ref_idx), "searchsorted indices differ (must be bit-exact)"
+    assert torch.equal(got_z.cpu(), ref_z), "sorted samples differ"
+    assert torch.equal(got_perm.cpu(), ref_perm)
+    assert 0 <= int(got_idx.min()) and int(got_idx.max()) <= s
+    # explicit uniforms give the same answer as the Philox stream
+    got2 = pkg.UtilsCV.get_z_vals_from_prob_dist_func(dev(w), dev(z), nf, u=dev(u))
+    assert torch.equal(got2.cpu(), ref_z)
+    # empty rays collapse onto the last mid-point
+    mid_last = 0.5 * (z[0, -1] + z[0, -2])
+    assert torch.all(got_z[0].cpu() == mid_last)
+
+
+def test_sample_pdf_backward(pkg):
+    n, s, nf = 300, 64, 128
+    w, z = _weights_and_z(n, s, 77)
+    w = w + 1e-3 * torch.rand(n, s)
+    u = torch.rand(n, nf, generator=torch.Generator().manual_seed(1))
+    g = torch.randn(n, nf, generator=torch.Generator().manual_seed(2))
+    wr = w.clone().requires_grad_(True)
+    O.get_z_vals_from_prob_dist_func(wr, z, nf, u).backward(g)
+    wg = dev(w).requires_grad_(True)
+    pkg.UtilsCV.get_z_vals_from_prob_dist_func(wg, dev(z), nf, u=dev(u)).backward(dev(g))
+    err = (wg.grad.cpu() - wr.grad).abs().max().item()
+    assert err < 1e-4 * wr.grad.abs().max().item(), err
+
+
+def test_sample_pdf_full_size_properties(pkg):
+    n, s, nf = 65536, 64, 128
+    g = torch.Generator(device="cuda").manual_seed(0)
+    w = torch.rand(n, s, device="cuda", generator=g) ** 4
+    z = pkg.UtilsCV.get_z_values(NEAR, FAR, n, 1, s, seed=1, step=0)[:, 0, :]
+    z_new = pkg.UtilsCV.get_z_vals_from_prob_dist_func(w, z, nf, seed=1, step=0)
+    assert torch.all(z_new[:, 1:] >= z_new[:, :-1]), "output must be sorted"
+    mid = 0.5 * (z[:, 1:] + z[:, :-1])
+    assert torch.all(z_new >= mid[:, :1]) and torch.all(z_new <= mid[:, -1:])
+    # same stream -> idempotent; different step -> different draws
+    assert torch.equal(z_new, pkg.UtilsCV.get_z_vals_from_prob_dist_func(w, z, nf, seed=1, step=0))
+    assert not torch.equal(z_new, pkg.UtilsCV.get_z_vals_from_prob_dist_func(w, z, nf, seed=1, step=1))
+    # merge == sort(concat)
+    out = torch.empty(n, s + nf, device="cuda")
+    pkg._lib.call("nerf_merge_sorted", z_new.data_ptr(), nf, z.data_ptr(), s, n, out.data_ptr())
+    assert torch.equal(out, torch.sort(torch.cat([z_new, z], -1), -1).values)
+
+
+# ---- K2/K4: MLP ---------------------------------------------------------------------------------------------------------
+def _mlp_inputs(cfg, m, seed):
+    g = torch.Generator().manual_seed(seed)
+    xyz = O.positional_encoding_for_xyz(torch.rand(m, 3, generator=g) * 2 - 1, cfg.n_pos_enc_xyz)
+    view = None
+    if cfg.n_angles:
+        view = O.positional_encoding_for_views(torch.randn(m, cfg.n_angles + 1, generator=g), cfg.n_pos_enc_view)
+    return xyz, view
+
+
+@pytest.mark.parametrize("mode,tol", [("fp32", FP32_TOL), ("bf16", 4e-2)])
+@pytest.mark.parametrize("n_angles,l_view,m", [(2, 4, 1000), (2, 4, 128), (1, 4, 300), (2, 2, 257), (0, 4, 300)])
+def test_mlp_forward(pkg, mode, tol, n_angles, l_view, m):
+    ocfg = oracle_cfg(n_angles, l_view)
+    p = O.glorot_params(ocfg.shapes, 5, bias_scale=0.1)
+    xyz, view = _mlp_inputs(ocfg, m, 6)
+    ref = O.mlp_forward(p, ocfg.shapes, xyz, view)
+    net = pkg.NerfMLP(pkg.NetCfg(5, l_view, n_angles, 256, 128, 0.05), mode=mode)
+    net.set_params(p)
+    with torch.no_grad():
+        got = net(dev(xyz), dev(view) if view is not None else None)
+    assert got.shape == (m, 4)
+    assert (got.cpu() - ref).abs().max().item() < tol
+    if mode == "bf16":   # tight check against the oracle with the same bf16 operand rounding
+        ref_b = O.mlp_forward(p, ocfg.shapes, xyz, view, emulate_bf16=True)
+        assert (got.cpu() - ref_b).abs().max().item() < 2e-3
+
+
+@pytest.mark.parametrize("mode,tol", [("fp32", 1e-4), ("bf16", 3e-2)])
+@pytest.mark.parametrize("n_angles,l_view,m", [(2, 4, 700), (1, 4, 130), (0, 4, 200)])
+def test_mlp_backward(pkg, mode, tol, n_angles, l_view, m):
+    ocfg = oracle_cfg(n_angles, l_view)
+    p = O.glorot_params(ocfg.shapes, 8, bias_scale=0.1)
+    xyz, view = _mlp_inputs(ocfg, m, 9)
+    g = torch.randn(m, 4, generator=torch.Generator().manual_seed(10))
+    pr, xr = p.clone().requires_grad_(True), xyz.clone().requires_grad_(True)
+    O.mlp_forward(pr, ocfg.shapes, xr, view).backward(g)
+    net = pkg.NerfMLP(pkg.NetCfg(5, l_view, n_angles, 256, 128, 0.05), mode=mode)
+    net.set_params(p)
+    pg = net.params.requires_grad_(True)
+    xg = dev(xyz).requires_grad_(True)
+    net(xg, dev(view) if view is not None else None).backward(dev(g))
+    rel_p = ((pg.grad.cpu() - pr.grad).norm() / pr.grad.norm()).item()
+    rel_x = ((xg.grad.cpu() - xr.grad).norm() / xr.grad.norm()).item()
+    assert rel_p < tol and rel_x < tol, (rel_p, rel_x)
+
+
+# ---- render / train step -------------------------------------------------------------------------------------------------
+def _model(pkg, mode, n_angles=2, l_view=4, n_c=64, n_f=128, cls=None, **kw):
+    ocfg = oracle_cfg(n_angles, l_view)
+    pc, pf = test_params(ocfg, 1), test_params(ocfg, 2)
+    cls = cls or pkg.NeRFModel
+    model = cls(net_config(n_angles, l_view), render_config(n_c, n_f), NEAR, FAR, mode=mode, seed=7, **kw)
+    model.model_coarse.set_params(pc)
+    if model.model_fine is not None:
+        model.model_fine.set_params(pf)
+    return model, ocfg, pc, (pf if n_f > 0 else None)
+
+
+@pytest.mark.parametrize("mode,tol", [("fp32", FP32_TOL), ("bf16", BF16_TOL)])
+@pytest.mark.parametrize("n_angles,n_c,n_f,n", [(2, 64, 128, 500), (0, 64, 128, 130), (1, 64, 64, 77), (2, 64, 0, 100)])
+def test_render(pkg, mode, tol, n_angles, n_c, n_f, n):
+    model, ocfg, pc, pf = _model(pkg, mode, n_angles, 4, n_c, n_f)
+    o, d = random_rays(n, 3)
+    jit = O.stratified_jitter(7, 2, n, n_c, ray_offset=40)
+    u = O.importance_uniforms(7, 2, n, n_f, ray_offset=40) if n_f else None
+    ref = O.render(pc, pf, ocfg, NEAR, FAR, o, d, n_c, n_f, jit, u)
+    got = model.render(dev(o), dev(d), seed=7, step=2, ray_offset=40)
+    assert len(got) == 6
+    s_out = n_c + n_f if n_f else n_c
+    assert got[0].shape == (n, 3) and got[1].shape == (n, s_out) and got[4].shape == (n, s_out, 3)
+    if mode == "fp32":
+        assert torch.equal(got[5].cpu(), ref[5]) or (got[5].cpu() - ref[5]).abs().max().item() < 1e-5
+    err = (got[0].cpu() - ref[0]).abs().max().item()
+    assert err < tol, f"rgb max-abs error {err}"
+    depth_ref, _ = O.depth_and_acc(ref[1], ref[5])
+    depth = (got[1] * got[5]).sum(-1)
+    assert (depth.cpu() - depth_ref).abs().max().item() < tol * 10   # depth is in scene units (~2.5), not [0,1]
+
+
+def test_render_image_ragged_batches(pkg):
+    model, ocfg, pc, pf = _model(pkg, "fp32")
+    c2w = sphere_pose(0.3, 0.2)
+    h = w = 20
+    ref = O.render_image(pc, pf, ocfg, NEAR, FAR, c2w, 0.69, h, w, 150, 64, 128, seed=5, step=1)
+    got = model.render_image(c2w, 0.69, h, w, 150, seed=5, step=1)     # 400 rays = 150 + 150 + 100
+    assert got[0].shape == (h, w, 3) and got[1].shape == (h, w, 192) and got[4].shape == (h, w, 192, 3)
+    assert (got[0].cpu() - ref[0]).abs().max().item() < FP32_TOL
+    # result must not depend on the batch size (global ray index keys the RNG)
+    got2 = model.render_image(c2w, 0.69, h, w, 400, seed=5, step=1)
+    assert (got2[0] - got[0]).abs().max().item() < 1e-6
+    rgb, depth, acc = model.render_image_lean(c2w, 0.69, h, w, 150, seed=5, step=1)
+    assert (rgb.reshape(h, w, 3) - got[0]).abs().max().item() < 1e-6
+    assert (depth.reshape(h, w) - (got[1] * got[5]).sum(-1)).abs().max().item() < 1e-5
+
+
+@pytest.mark.parametrize("mode,tol", [("fp32", 2e-4), ("bf16", 5e-2)])
+@pytest.mark.parametrize("diet", [False, True])
+def test_train_step_gradients(pkg, mode, tol, diet):
+    n = 192
+    model, ocfg, pc, pf = _model(pkg, mode, cls=pkg.DietNeRFModel if diet else None)
+    o, d = random_rays(n, 4)
+    y = torch.rand(n, 3, generator=torch.Generator().manual_seed(5))
+    jit, u = O.stratified_jitter(7, 0, n, 64), O.importance_uniforms(7, 0, n, 128)
+    metrics, gc, gf, out = O.train_step(pc, pf, ocfg, NEAR, FAR, o, d, y, 64, 128, jit, u, dietnerf=diet)
+    g_c, g_f, sums = model.forward_backward(dev(o), dev(d), dev(y), seed=7, step=0)
+    rel_c = ((g_c.cpu() - gc).norm() / gc.norm()).item()
+    rel_f = ((g_f.cpu() - gf).norm() / gf.norm()).item()
+    assert rel_c < tol and rel_f < tol, (rel_c, rel_f)
+    m = model._metrics(sums, n)
+    ltol = 1e-5 if mode == "fp32" else 2e-3
+    assert abs(m["loss"].item() - metrics["loss"].item()) < ltol
+    assert abs(m["psnr_coarse"].item() - metrics["psnr_coarse"].item()) < (1e-3 if mode == "fp32" else 0.05)
+    assert abs(m["psnr_fine"].item() - metrics["psnr_fine"].item()) < (1e-3 if mode == "fp32" else 0.05)
+
+
+def test_train_step_coarse_gradient_needs_the_sampler_path(pkg):
+    """The reference does not detach z_from_dist: the fine loss reaches the coarse net.  stop_grad_z=True is the
+    documented deviation and must differ."""
+    n = 128
+    model, ocfg, pc, pf = _model(pkg, "fp32")
+    o, d = random_rays(n, 6)
+    y = torch.rand(n, 3)
+    g_ref = model.forward_backward(dev(o), dev(d), dev(y), seed=7, step=0)[0].clone()
+    model.stop_grad_z = True
+    g_sg = model.forward_backward(dev(o), dev(d), dev(y), seed=7, step=0)[0].clone()
+    assert (g_ref - g_sg).norm().item() > 1e-3 * g_ref.norm().item()
+
+
+def test_adam_and_full_train_step(pkg):
+    n = 160
+    model, ocfg, pc, pf = _model(pkg, "fp32")
+    model.compile(optimizer=pkg.Adam(5e-4))
+    o, d = random_rays(n, 8)
+    y = torch.rand(n, 3, generator=torch.Generator().manual_seed(1))
+    p_c, p_f = pc.clone(), pf.clone()
+    mc, vc, mf, vf = (torch.zeros_like(pc) for _ in range(4))
+    for t in range(1, 4):
+        jit, u = O.stratified_jitter(7, t - 1, n, 64), O.importance_uniforms(7, t - 1, n, 128)
+        ref_m, gc, gf, _ = O.train_step(p_c, p_f, ocfg, NEAR, FAR, o, d, y, 64, 128, jit, u)
+        p_c, mc, vc = O.adam_step(p_c, gc, mc, vc, t, 5e-4)
+        p_f, mf, vf = O.adam_step(p_f, gf, mf, vf, t, 5e-4)
+        m = model.train_step((o, d, y))          # host tensors: the step copies them to the device
+        assert abs(m["loss"].item() - ref_m["loss"].item()) < 5e-5
+    # Adam's first steps move every weight by ~lr regardless of gradient scale: compare the parameter deltas
+    dc = model.model_coarse.params.cpu() - pc
+    assert ((dc - (p_c - pc)).norm() / (p_c - pc).norm()).item() < 2e-2
+    df = model.model_fine.params.cpu() - pf
+    assert ((df - (p_f - pf)).norm() / (p_f - pf).norm()).item() < 2e-2
+
+
+def test_training_reduces_loss(pkg):
+    """A few hundred bf16 steps on a synthetic target must reduce the loss (end-to-end sanity of fwd+bwd+Adam)."""
+    model = pkg.NeRFModel(net_config(), render_config(), NEAR, FAR, mode="bf16", seed=3)
+    model.compile(optimizer=pkg.Adam(5e-4))
+    o, d = random_rays(1024, 9)
+    y = (0.5 + 0.5 * torch.sin(d[:, :3] * 3)).contiguous()
+    first = model.train_step((o, d, y))["loss"].item()
+    for _ in range(150):
+        last = model.train_step((o, d, y))["loss"].item()
+    assert math.isfinite(last) and last < 0.7 * first, (first, last)
