@@ -31,7 +31,7 @@ class _MlpFn(torch.autograd.Function):
     def forward(ctx, params, xyz_enc, view_enc, model):
         m = xyz_enc.shape[0]
         out = torch.empty((m, 4), dtype=torch.float32, device=xyz_enc.device)
-        need_grad = torch.is_grad_enabled() and (params.requires_grad or xyz_enc.requires_grad)
+        need_grad = bool(ctx.needs_input_grad[0] or ctx.needs_input_grad[1])
         saved = (torch.empty(max(model.saved_bytes(m), 16), dtype=torch.uint8, device=xyz_enc.device)
                  if need_grad else None)
         ws = model._buffer("ws_fwd", model.workspace_bytes(m, False))
@@ -74,6 +74,9 @@ class NerfMLP:
         assert self.n_params == sum(i * o + o for i, o in self.shapes)
         self.dx = int(load().nerf_xyz_enc_dim(self.cfg_ref))
         self.dv = int(load().nerf_view_enc_dim(self.cfg_ref))
+        if self.mode_id == MODE_BF16 and int(load().nerf_packed_bytes(self.cfg_ref)) < 0:
+            raise _lib.NerfLibraryError("mode='bf16' does not support this network: "
+                                        + load().nerf_last_error().decode() + " (use mode='fp32')")
         self.params = self._glorot_init(seed).to(self.device)
         self._buffers = {}
         self._packed = None

@@ -292,7 +292,7 @@ def ray_marching(model_output: torch.Tensor, z_values: torch.Tensor):
     sigma_a = torch.relu(model_output[..., 3])                                   # :100
     net_rgb_output = torch.sigmoid(model_output[..., :3])                        # :101
     delta = z_values[..., 1:] - z_values[..., :-1]                               # :104
-    inf = torch.full_like(delta[..., :1], 1e9)                                   # :105
+    inf = torch.full(z_values.shape[:-1] + (1,), 1e9, dtype=F32)                # :105
     delta = torch.cat([delta, inf], dim=-1)                                      # :106
     alpha = 1.0 - torch.exp(-sigma_a * delta)                                    # :111
     cumprod = _ExclusiveCumprodTF.apply(1.0 - alpha)                             # :112

@@ -23,7 +23,7 @@ def oracle_cfg(n_angles=2, l_view=4):
     return O.NetCfg(5, l_view, n_angles, 256, 128, 0.05)
 
 
-def test_params(cfg, seed, sigma_gain=30.0, sigma_bias=0.5):
+def make_params(cfg, seed, sigma_gain=30.0, sigma_bias=0.5):
     """Glorot weights, random biases, and a sharpened sigma head: rays see empty space AND opaque surfaces
     (alpha saturates), which exercises the div_no_nan branch of the cumprod gradient and empty-ray collapse."""
     p = O.glorot_params(cfg.shapes, seed, bias_scale=0.1)

@@ -1,0 +1,88 @@
+"""Per-kernel timing probe (CUDA events, L2-exceeding inputs): MLP forward/backward TFLOP/s and compositing GB/s.
+Usage (on the GPU box): python tools/kernel_probe.py [--rays 4096] [--mode bf16]"""
+import argparse
+import ctypes
+import importlib
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+pkg = importlib.import_module("nerf-and-dietnerf_b200")
+
+MAC_FWD = 512152  # per sample, SURVEY 8d
+
+
+def timeit(fn, iters=10, warmup=3):
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(iters)]
+    for a, b in evs:
+        a.record()
+        fn()
+        b.record()
+    torch.cuda.synchronize()
+    ts = sorted(a.elapsed_time(b) for a, b in evs)
+    return ts[len(ts) // 2], ts[0]
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--rays", type=int, default=4096)
+    ap.add_argument("--mode", default="bf16")
+    ap.add_argument("--bwd", action="store_true")
+    args = ap.parse_args()
+    call, ptr = pkg._lib.call, pkg._lib.ptr
+    cfg = pkg.NetCfg(5, 4, 2, 256, 128, 0.05)
+    net = pkg.NerfMLP(cfg, mode=args.mode, seed=0)
+    for s in (64, 128, 192):
+        m = args.rays * s
+        xyz = torch.randn(m, 33, device="cuda")
+        view = torch.randn(m, 24, device="cuda")
+        out = torch.empty(m, 4, device="cuda")
+        ws = torch.empty(max(net.workspace_bytes(m, False), 16), dtype=torch.uint8, device="cuda")
+        saved = torch.empty(max(net.saved_bytes(m), 16), dtype=torch.uint8, device="cuda")
+        packed = net.packed_for(net.params)
+        for label, sv in (("infer", None), ("train(save acts)", saved)):
+            f = lambda: call("nerf_mlp_fwd", net.cfg_ref, ptr(net.params), ptr(packed), ptr(xyz), ptr(view), m, ptr(out),
+                             ptr(sv), ptr(ws), net.mode_id)
+            med, best = timeit(f)
+            print(f"mlp_fwd[{args.mode}] {label:18s} M={m:8d}: {med:8.3f} ms  {2 * MAC_FWD * m / med / 1e9:8.1f} TFLOP/s "
+                  f"(best {2 * MAC_FWD * m / best / 1e9:.1f})")
+        if args.bwd:
+            d_out = torch.randn(m, 4, device="cuda")
+            grads = torch.zeros(net.n_params, device="cuda")
+            d_xyz = torch.empty(m, 33, device="cuda")
+            wsb = torch.empty(max(net.workspace_bytes(m, True), 16), dtype=torch.uint8, device="cuda")
+            f = lambda: call("nerf_mlp_bwd", net.cfg_ref, ptr(net.params), ptr(packed), ptr(xyz), ptr(view), ptr(saved),
+                             ptr(d_out), m, ptr(grads), ptr(d_xyz), ptr(wsb), net.mode_id)
+            med, best = timeit(f)
+            flops = 2 * (512152 + 509056) * m
+            print(f"mlp_bwd[{args.mode}]                    M={m:8d}: {med:8.3f} ms  {flops / med / 1e9:8.1f} TFLOP/s")
+    # compositing: one 256x256 frame
+    for n, s in ((65536, 192), (65536, 64), (4096 * 16, 128)):
+        raw = torch.randn(n, s, 4, device="cuda")
+        z = torch.sort(torch.rand(n, s, device="cuda"), -1).values
+        rgb = torch.empty(n, 3, device="cuda"); w = torch.empty(n, s, device="cuda"); T = torch.empty(n, s, device="cuda")
+        al = torch.empty(n, s, device="cuda"); rs = torch.empty(n, s, 3, device="cuda")
+        dep = torch.empty(n, device="cuda"); acc = torch.empty(n, device="cuda")
+        f = lambda: call("nerf_composite_fwd", ptr(raw), ptr(z), n, s, ptr(rgb), ptr(w), ptr(T), ptr(al), ptr(rs), None, None)
+        med, best = timeit(f)
+        byts = n * (s * 44 + 12)
+        print(f"composite_fwd full  N={n} S={s}: {med * 1e3:8.1f} us  {byts / med / 1e6:8.1f} GB/s")
+        f = lambda: call("nerf_composite_fwd", ptr(raw), ptr(z), n, s, ptr(rgb), ptr(w), None, None, None, ptr(dep), ptr(acc))
+        med, best = timeit(f)
+        byts = n * (s * 24 + 20)
+        print(f"composite_fwd lean  N={n} S={s}: {med * 1e3:8.1f} us  {byts / med / 1e6:8.1f} GB/s")
+        d_rgb = torch.randn(n, 3, device="cuda"); d_raw = torch.empty_like(raw); d_z = torch.empty_like(z)
+        f = lambda: call("nerf_composite_bwd", ptr(raw), ptr(z), ptr(d_rgb), ptr(w), n, s, ptr(d_raw), ptr(d_z))
+        med, best = timeit(f)
+        byts = n * (s * 44 + 12)
+        print(f"composite_bwd       N={n} S={s}: {med * 1e3:8.1f} us  {byts / med / 1e6:8.1f} GB/s")
+
+
+if __name__ == "__main__":
+    main()
