@@ -350,8 +350,6 @@ class NeRF:
         Host tensors are copied to the device here (pinned memory makes the copy asynchronous).  With
         ``distribute()`` every rank passes the SAME global batch and works on its contiguous shard.
         """
-        if self.optimizer is None:
-            raise RuntimeError("call compile(optimizer=Adam(lr)) before train_step")
         rays_orig, rays_dirs, real_rgb = data
         n_total = rays_orig.shape[0]
         lo, hi = 0, n_total
@@ -359,15 +357,24 @@ class NeRF:
             per = (n_total + self.world_size - 1) // self.world_size
             lo, hi = min(n_total, self.rank * per), min(n_total, (self.rank + 1) * per)
         to_dev = lambda t: t[lo:hi].to(device=self.device, dtype=torch.float32, non_blocking=True).contiguous()
-        o, d, y = to_dev(rays_orig), to_dev(rays_dirs), to_dev(real_rgb)
-        self.forward_backward(o, d, y, n_total_rays=n_total, ray_offset=lo)
+        return self.train_step_local(to_dev(rays_orig), to_dev(rays_dirs), to_dev(real_rgb), n_total, lo)
+
+    def train_step_local(self, rays_orig, rays_dirs, real_rgb, n_total_rays, ray_offset=0) -> Dict:
+        """Train step on THIS rank's shard of a global batch of ``n_total_rays`` rays (device tensors).
+
+        Gradients are normalised by the global ray count, summed over ranks with ONE all-reduce (the two squared-error
+        sums ride in the same buffer), and the identical Adam update is applied on every rank.
+        """
+        if self.optimizer is None:
+            raise RuntimeError("call compile(optimizer=Adam(lr)) before train_step")
+        self.forward_backward(rays_orig, rays_dirs, real_rgb, n_total_rays=n_total_rays, ray_offset=ray_offset)
         g = self._grad_buffer()
         if self.world_size > 1:
             import torch.distributed as dist
             dist.all_reduce(g, op=dist.ReduceOp.SUM, group=self._process_group)
         self.apply_gradients(g)
         self.step_counter += 1
-        return self._metrics(g[-2:], n_total)
+        return self._metrics(g[-2:], n_total_rays)
 
     def apply_gradients(self, g):
         mc, mf = self.model_coarse, self.model_fine

@@ -101,10 +101,22 @@ def check(status, what):
         raise NerfLibraryError(f"{what} failed ({status}): {msg}")
 
 
+# kernels launched per C-ABI call (bf16 mode; the fp32 MLP launches one GEMM per layer and is counted separately)
+KERNELS_PER_CALL = {"nerf_mlp_fwd": 1, "nerf_mlp_bwd": 2, "nerf_pack_weights": 2}
+launch_count = 0            # kernels launched through call() since import (bench.py reads the delta)
+event_hook = None           # optional callable(name) -> context manager, used by bench.py to time single calls
+
+
 def call(name, *args):
     """Call an int-returning entry point on the current torch CUDA stream and raise on error."""
+    global launch_count
     lib = load()
-    status = getattr(lib, name)(*args, stream())
+    if event_hook is not None:
+        with event_hook(name):
+            status = getattr(lib, name)(*args, stream())
+    else:
+        status = getattr(lib, name)(*args, stream())
+    launch_count += KERNELS_PER_CALL.get(name, 1)
     check(status, name)
 
 

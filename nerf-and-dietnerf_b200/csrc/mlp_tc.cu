@@ -15,76 +15,9 @@
 //     CUDA cores from the fp32 registers of the last epilogue;
 //   * training mode stores each layer's bf16 activation tile to HBM with bulk S2G copies in the swizzled tile-panel
 //     format the backward kernels load back verbatim.
-#include <string.h>
-
-#include "common.cuh"
-#include "tc_common.cuh"
+#include "mlp_tc.cuh"
 
 namespace nerf {
-
-using namespace tc;
-
-constexpr int kTileM = 128;
-constexpr int kPanelBytes = 128 * 128;            // [128 rows][64 bf16]
-constexpr int kActPanels = 4;                     // 256 features
-constexpr int kStageBytes = 32768;                // one weight chunk: [<=256][64] bf16
-constexpr int kStages = 2;
-constexpr int kInpViewCol = 40;                   // first view-encoding column of the input panel
-constexpr int kMaxChunks = 40;
-constexpr int kThreadsFwd = 320;
-constexpr int kSavedPanelsPerTile = 8 * kActPanels + 2;  // h1..h8 (4 panels each) + last hidden (2 panels)
-
-// shared memory map (offsets from a 1024-aligned base)
-constexpr int kSmemAct = 0;                                          // [2 tiles][4 panels]
-constexpr int kSmemInp = kSmemAct + 2 * kActPanels * kPanelBytes;    // [2 tiles]
-constexpr int kSmemStage = kSmemInp + 2 * kPanelBytes;               // [kStages]
-constexpr int kSmemBar = kSmemStage + kStages * kStageBytes;
-constexpr int kSmemTotal = kSmemBar + 256;
-constexpr int kSmemAlloc = kSmemTotal + 1024;
-
-struct TcPlan {
-  uint32_t chunk_off[kMaxChunks];    // byte offset of the chunk in the packed buffer
-  uint32_t chunk_bytes[kMaxChunks];
-  int8_t a_src[kMaxChunks];          // 0..3 = activation panel, 4 = input panel
-  int8_t layer_first[12], layer_nchunks[12];
-  int16_t layer_n[12];               // UMMA N of the layer
-  int32_t n_layers, n_chunks;
-  uint32_t bias_off;                 // fp32 [9][256] (layer 8: b8[128], b_sigma, zeros)
-  uint32_t w_rgb_off;                // fp32 float4 [128] = (W9[j][0], W9[j][1], W9[j][2], 0)
-  uint32_t b_rgb_off;                // fp32 [4]
-  uint32_t total_bytes;
-};
-
-static bool make_plan(const NetGeom& g, TcPlan* p) {
-  if (!g.view || g.hidden != 256 || g.last_hidden != 128 || g.dx > kInpViewCol || g.dv > 64 - kInpViewCol) return false;
-  memset(p, 0, sizeof(*p));
-  int c = 0;
-  uint32_t off = 0;
-  auto add = [&](int layer, int n, int src) {
-    p->chunk_off[c] = off;
-    p->chunk_bytes[c] = (uint32_t)n * 128u;
-    p->a_src[c] = (int8_t)src;
-    off += (uint32_t)n * 128u;
-    if (p->layer_nchunks[layer] == 0) p->layer_first[layer] = (int8_t)c;
-    p->layer_nchunks[layer]++;
-    p->layer_n[layer] = (int16_t)n;
-    ++c;
-  };
-  add(0, 256, 4);
-  for (int l = 1; l <= 3; ++l) for (int k = 0; k < 4; ++k) add(l, 256, k);
-  add(4, 256, 4);
-  for (int k = 0; k < 4; ++k) add(4, 256, k);
-  for (int l = 5; l <= 7; ++l) for (int k = 0; k < 4; ++k) add(l, 256, k);
-  for (int k = 0; k < 4; ++k) add(8, 144, k);
-  add(8, 144, 4);
-  p->n_layers = 9;
-  p->n_chunks = c;
-  p->bias_off = off;        off += 9 * 256 * 4;
-  p->w_rgb_off = off;       off += 128 * 16;
-  p->b_rgb_off = off;       off += 16;
-  p->total_bytes = off;
-  return true;
-}
 
 // ---- weight packing -----------------------------------------------------------------------------------------------------
 // One thread per bf16 element of every chunk, plus the fp32 tail (biases, rgb head).
@@ -150,8 +83,7 @@ struct FwdBars {
   uint32_t tmem_base;
 };
 
-__device__ __forceinline__ float leaky(float v, float alpha) { return fmaxf(v, 0.f) + alpha * fminf(v, 0.f); }
-
+template <bool kSave>
 __global__ void __launch_bounds__(kThreadsFwd, 1)
 mlp_tc_fwd_kernel(const __grid_constant__ TcPlan plan, const uint8_t* __restrict__ packed,
                   const float* __restrict__ xyz_enc, const float* __restrict__ view_enc, int dx, int dv, int64_t M,
@@ -263,12 +195,21 @@ mlp_tc_fwd_kernel(const __grid_constant__ TcPlan plan, const uint8_t* __restrict
       }
       fence_proxy_async();
       mbar_arrive(smem_u32(&bars->act_ready[t]));
+      uint8_t* saved_tile = kSave ? saved + (size_t)tile * kSavedTileBytes : nullptr;
+      uint32_t* saved_mask = reinterpret_cast<uint32_t*>(saved_tile + (size_t)kSavedPanels * kPanelBytes);
+      if (kSave) {
+        named_bar_sync(bar_id, 128);
+        if (gtid == 0) {
+          bulk_s2g(saved_tile, sbase + kSmemInp + t * kPanelBytes, kPanelBytes);
+          bulk_commit();
+        }
+      }
 
       for (int l = 0; l < plan.n_layers; ++l) {
         mbar_wait(smem_u32(&bars->acc_full[t]), acc_cnt & 1u);
         ++acc_cnt;
         tc_fence_after();
-        if (saved) {
+        if (kSave) {
           // the previous layer's bulk stores still read the panels this epilogue overwrites
           if (gtid == 0) bulk_wait_read0();
           named_bar_sync(bar_id, 128);
@@ -281,6 +222,7 @@ mlp_tc_fwd_kernel(const __grid_constant__ TcPlan plan, const uint8_t* __restrict
             tmem_ld32(taddr + c0, acc);
             tmem_ld_wait();
             uint8_t* prow = act + (c0 >> 6) * kPanelBytes + r * 128;
+            uint32_t mword = 0;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + c0 + 8 * j));
@@ -296,16 +238,20 @@ mlp_tc_fwd_kernel(const __grid_constant__ TcPlan plan, const uint8_t* __restrict
               uint4 pk = make_uint4(pack_bf16x2(f0, f1), pack_bf16x2(f2, f3), pack_bf16x2(f4, f5), pack_bf16x2(f6, f7));
               const int chunk16 = ((c0 & 63) >> 3) + j;
               *reinterpret_cast<uint4*>(prow + ((chunk16 ^ (r & 7)) << 4)) = pk;
+              if (kSave)
+                mword |= ((f0 > 0.f) | ((f1 > 0.f) << 1) | ((f2 > 0.f) << 2) | ((f3 > 0.f) << 3) | ((f4 > 0.f) << 4) |
+                        ((f5 > 0.f) << 5) | ((f6 > 0.f) << 6) | ((f7 > 0.f) << 7))
+                       << (8 * j);
             }
+            if (kSave) saved_mask[(l * 8 + (c0 >> 5)) * 128 + r] = mword;
           }
           tc_fence_before();
           fence_proxy_async();
           mbar_arrive(smem_u32(&bars->act_ready[t]));
-          if (saved) {
+          if (kSave) {
             named_bar_sync(bar_id, 128);
             if (gtid == 0) {
-              uint8_t* dst = saved + ((size_t)tile * kSavedPanelsPerTile + (size_t)l * kActPanels) * kPanelBytes;
-              bulk_s2g(dst, act_u32, kActPanels * kPanelBytes);
+              bulk_s2g(saved_tile + (size_t)saved_panel_h(l + 1) * kPanelBytes, act_u32, kActPanels * kPanelBytes);
               bulk_commit();
             }
           }
@@ -327,7 +273,11 @@ mlp_tc_fwd_kernel(const __grid_constant__ TcPlan plan, const uint8_t* __restrict
               gg = fmaf(f[i], w.y, gg);
               bb = fmaf(f[i], w.z, bb);
             }
-            if (saved) {
+            if (kSave) {
+              uint32_t mword = 0;
+#pragma unroll
+              for (int i = 0; i < 32; ++i) mword |= (uint32_t)(f[i] > 0.f) << i;
+              saved_mask[(8 * 8 + (c0 >> 5)) * 128 + r] = mword;
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
                 uint4 pk = make_uint4(pack_bf16x2(f[8 * j], f[8 * j + 1]), pack_bf16x2(f[8 * j + 2], f[8 * j + 3]),
@@ -343,19 +293,18 @@ mlp_tc_fwd_kernel(const __grid_constant__ TcPlan plan, const uint8_t* __restrict
           const float sigma = __uint_as_float(sg[0]) + __ldg(bias + 128);
           if (row_ok) reinterpret_cast<float4*>(out4)[row] = make_float4(rr, gg, bb, sigma);
           tc_fence_before();
-          if (saved) {
+          if (kSave) {
             fence_proxy_async();
             named_bar_sync(bar_id, 128);
             if (gtid == 0) {
-              uint8_t* dst = saved + ((size_t)tile * kSavedPanelsPerTile + (size_t)8 * kActPanels) * kPanelBytes;
-              bulk_s2g(dst, act_u32, 2 * kPanelBytes);
+              bulk_s2g(saved_tile + (size_t)kSavedPanelHL * kPanelBytes, act_u32, 2 * kPanelBytes);
               bulk_commit();
             }
           }
         }
       }
     }
-    if (saved && gtid == 0) bulk_wait0();
+    if (kSave && gtid == 0) bulk_wait0();
   }
   tc_fence_before();
   __syncthreads();
@@ -366,12 +315,15 @@ mlp_tc_fwd_kernel(const __grid_constant__ TcPlan plan, const uint8_t* __restrict
 int64_t mlp_tc_saved_bytes(const NetGeom& g, int64_t m) {
   int64_t tiles = (m + kTileM - 1) / kTileM;
   tiles = (tiles + 1) / 2 * 2;
-  return tiles * (int64_t)kSavedPanelsPerTile * kPanelBytes;
+  return tiles * (int64_t)kSavedTileBytes;
 }
 
 int64_t mlp_tc_workspace_bytes(const NetGeom& g, int64_t m, int backward) {
-  (void)g; (void)m; (void)backward;
-  return 256;
+  (void)g;
+  if (!backward) return 256;
+  int64_t tiles = (m + kTileM - 1) / kTileM;
+  tiles = (tiles + 1) / 2 * 2;
+  return tiles * (int64_t)kDzTileBytes + 1024;
 }
 
 int mlp_tc_fwd(const nerf_net_cfg* cfg, const NetGeom& g, const float* params, const void* packed, const float* xyz_enc,
@@ -384,22 +336,20 @@ int mlp_tc_fwd(const nerf_net_cfg* cfg, const NetGeom& g, const float* params, c
   }
   static bool attr_set = false;
   if (!attr_set) {
-    NERF_CUDA(cudaFuncSetAttribute(mlp_tc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemAlloc));
+    NERF_CUDA(cudaFuncSetAttribute(mlp_tc_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemAlloc));
+    NERF_CUDA(cudaFuncSetAttribute(mlp_tc_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemAlloc));
     attr_set = true;
   }
   int64_t n_pairs = ((m + kTileM - 1) / kTileM + 1) / 2;
   int grid = (int)(n_pairs < kNumSMs ? n_pairs : kNumSMs);
-  mlp_tc_fwd_kernel<<<grid, kThreadsFwd, kSmemAlloc, st>>>(plan, (const uint8_t*)packed, xyz_enc, view_enc, g.dx, g.dv, m,
-                                                          out4, (uint8_t*)saved, cfg->leaky_alpha);
+  if (saved)
+    mlp_tc_fwd_kernel<true><<<grid, kThreadsFwd, kSmemAlloc, st>>>(plan, (const uint8_t*)packed, xyz_enc, view_enc, g.dx,
+                                                                  g.dv, m, out4, (uint8_t*)saved, cfg->leaky_alpha);
+  else
+    mlp_tc_fwd_kernel<false><<<grid, kThreadsFwd, kSmemAlloc, st>>>(plan, (const uint8_t*)packed, xyz_enc, view_enc, g.dx,
+                                                                   g.dv, m, out4, nullptr, cfg->leaky_alpha);
   NERF_CHECK_LAUNCH();
   return NERF_OK;
-}
-
-int mlp_tc_bwd(const nerf_net_cfg* cfg, const NetGeom& g, const float* params, const void* packed, const float* xyz_enc,
-               const float* view_enc, const void* saved, const float* d_out4, int64_t m, float* grads, float* d_xyz_enc,
-               void* workspace, cudaStream_t st) {
-  set_error("BF16 backward not built yet");
-  return NERF_E_UNSUPPORTED;
 }
 
 }  // namespace nerf
@@ -413,7 +363,7 @@ int64_t nerf_packed_bytes(const nerf_net_cfg* cfg) {
   TcPlan plan;
   if (!make_geom(cfg, &g)) { set_error("nerf_packed_bytes: bad net config"); return NERF_E_ARG; }
   if (!make_plan(g, &plan)) { set_error("nerf_packed_bytes: config not supported by NERF_MODE_BF16"); return NERF_E_UNSUPPORTED; }
-  return plan.total_bytes;
+  return (int64_t)((plan.total_bytes + 1023u) & ~1023u) + bwd_pack_bytes();
 }
 
 int nerf_pack_weights(const nerf_net_cfg* cfg, const float* params, void* packed, void* stream) {
@@ -425,7 +375,7 @@ int nerf_pack_weights(const nerf_net_cfg* cfg, const float* params, void* packed
   dim3 grid((256 * 64 + 255) / 256, plan.n_chunks + 1);
   pack_weights_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(plan, g, params, (uint8_t*)packed);
   NERF_CHECK_LAUNCH();
-  return NERF_OK;
+  return bwd_pack_weights(g, params, (uint8_t*)packed + ((plan.total_bytes + 1023u) & ~1023u), (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -1,0 +1,97 @@
+// Shared definitions of the tensor-core MLP kernels (forward: mlp_tc.cu, backward: mlp_tc_bwd.cu).
+#pragma once
+#include <string.h>
+
+#include "common.cuh"
+#include "tc_common.cuh"
+
+namespace nerf {
+
+using namespace tc;
+
+constexpr int kTileM = 128;
+constexpr int kPanelBytes = 128 * 128;            // [128 rows][64 bf16]
+constexpr int kActPanels = 4;                     // 256 features
+constexpr int kStageBytes = 32768;                // one weight chunk: [<=256][64] bf16
+constexpr int kStages = 2;
+constexpr int kInpViewCol = 40;                   // first view-encoding column of the input panel
+constexpr int kMaxChunks = 40;
+constexpr int kThreadsFwd = 320;
+// Saved activations of one 128-row tile (forward -> backward), all bf16 panels in the swizzled smem layout:
+//   panel 0            input panel (xyz | view encodings)
+//   panels 1 + 4(l-1)  h_l, l = 1..8 (4 panels each)
+//   panels 33, 34      last hidden (2 panels)
+//   then uint32 sign masks [9 layers][8 words][128 rows]: bit i of word w = (activation[32 w + i] > 0)
+constexpr int kSavedPanels = 1 + 8 * kActPanels + 2;
+constexpr int kSavedMaskBytes = 9 * 8 * 128 * 4;
+constexpr int kSavedTileBytes = kSavedPanels * kPanelBytes + kSavedMaskBytes;
+__host__ __device__ constexpr int saved_panel_h(int l) { return 1 + (l - 1) * kActPanels; }  // l = 1..8
+constexpr int kSavedPanelHL = 1 + 8 * kActPanels;
+// Backward workspace of one tile (chain kernel -> dW kernel): dZ_1..dZ_8 (4 panels each), dZ_L' (2 panels + the
+// sigma-gradient panel), dOut (1 panel: cols 0..3 = d_out4)
+constexpr int kDzPanels = 8 * kActPanels + 3 + 1;
+constexpr int kDzTileBytes = kDzPanels * kPanelBytes;
+__host__ __device__ constexpr int dz_panel(int l) { return (l - 1) * kActPanels; }            // l = 1..8
+constexpr int kDzPanelL = 8 * kActPanels;
+constexpr int kDzPanelOut = 8 * kActPanels + 3;
+
+// shared memory map (offsets from a 1024-aligned base)
+constexpr int kSmemAct = 0;                                          // [2 tiles][4 panels]
+constexpr int kSmemInp = kSmemAct + 2 * kActPanels * kPanelBytes;    // [2 tiles]
+constexpr int kSmemStage = kSmemInp + 2 * kPanelBytes;               // [kStages]
+constexpr int kSmemBar = kSmemStage + kStages * kStageBytes;
+constexpr int kSmemTotal = kSmemBar + 256;
+constexpr int kSmemAlloc = kSmemTotal + 1024;
+
+struct TcPlan {
+  uint32_t chunk_off[kMaxChunks];    // byte offset of the chunk in the packed buffer
+  uint32_t chunk_bytes[kMaxChunks];
+  int8_t a_src[kMaxChunks];          // 0..3 = activation panel, 4 = input panel
+  int8_t layer_first[12], layer_nchunks[12];
+  int16_t layer_n[12];               // UMMA N of the layer
+  int32_t n_layers, n_chunks;
+  uint32_t bias_off;                 // fp32 [9][256] (layer 8: b8[128], b_sigma, zeros)
+  uint32_t w_rgb_off;                // fp32 float4 [128] = (W9[j][0], W9[j][1], W9[j][2], 0)
+  uint32_t b_rgb_off;                // fp32 [4]
+  uint32_t total_bytes;
+};
+
+inline bool make_plan(const NetGeom& g, TcPlan* p) {
+  if (!g.view || g.hidden != 256 || g.last_hidden != 128 || g.dx > kInpViewCol || g.dv > 64 - kInpViewCol) return false;
+  memset(p, 0, sizeof(*p));
+  int c = 0;
+  uint32_t off = 0;
+  auto add = [&](int layer, int n, int src) {
+    p->chunk_off[c] = off;
+    p->chunk_bytes[c] = (uint32_t)n * 128u;
+    p->a_src[c] = (int8_t)src;
+    off += (uint32_t)n * 128u;
+    if (p->layer_nchunks[layer] == 0) p->layer_first[layer] = (int8_t)c;
+    p->layer_nchunks[layer]++;
+    p->layer_n[layer] = (int16_t)n;
+    ++c;
+  };
+  add(0, 256, 4);
+  for (int l = 1; l <= 3; ++l) for (int k = 0; k < 4; ++k) add(l, 256, k);
+  add(4, 256, 4);
+  for (int k = 0; k < 4; ++k) add(4, 256, k);
+  for (int l = 5; l <= 7; ++l) for (int k = 0; k < 4; ++k) add(l, 256, k);
+  for (int k = 0; k < 4; ++k) add(8, 144, k);
+  add(8, 144, 4);
+  p->n_layers = 9;
+  p->n_chunks = c;
+  p->bias_off = off;        off += 9 * 256 * 4;
+  p->w_rgb_off = off;       off += 128 * 16;
+  p->b_rgb_off = off;       off += 16;
+  p->total_bytes = off;
+  return true;
+}
+
+
+__device__ __forceinline__ float leaky(float v, float alpha) { return fmaxf(v, 0.f) + alpha * fminf(v, 0.f); }
+
+// backward half of the bf16 weight pack (defined in mlp_tc_bwd.cu)
+uint32_t bwd_pack_bytes();
+int bwd_pack_weights(const NetGeom& g, const float* params, uint8_t* packed_bwd, cudaStream_t st);
+
+}  // namespace nerf

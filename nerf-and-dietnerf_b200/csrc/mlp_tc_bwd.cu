@@ -1,0 +1,590 @@
+// K4 in NERF_MODE_BF16: the gradients TF autodiff produces for the NeRF MLP inside NeRF.train_step
+// (src/NeRF.py:149-167), as two tcgen05/TMEM kernels per network:
+//
+//  (1) mlp_tc_bwd_chain_kernel -- dX chain, the mirror image of the forward kernel.  Per 128-row tile the upstream
+//      gradient d_out4 is turned into dZ_L (rgb head transposed on CUDA cores, LeakyReLU' from the saved sign masks),
+//      then dH_l = dZ_{l+1} W_l^T runs layer by layer on the tensor cores with the fp32 accumulator in TMEM; the
+//      epilogue applies the LeakyReLU' mask, rounds to bf16 and writes dZ_l back into the same swizzled panels (next A
+//      operand) and, with one bulk S2G copy, to HBM for the weight-gradient pass.  For the fine network two extra
+//      N=64 steps accumulate d(xyz encoding) = dZ_5 W_4[0:33]^T + dZ_1 W_0^T (the reference does not detach the
+//      importance samples, so this gradient flows on to the coarse network).
+//  (2) mlp_tc_bwd_dw_kernel -- dW_l = A_l^T dZ_{l+1}: the contraction runs over ROWS, so both operands are the
+//      saved [rows][64] panels read as MN-major UMMA operands.  The 148 CTAs are split over (layer, row-range) units;
+//      each CTA keeps its whole 256x256 fp32 accumulator in TMEM (512 columns) across its row range, the idle epilogue
+//      warps sum the bias gradients from the dZ stages in shared memory, and one fp32 atomic drain per CTA lands the
+//      result in the flat gradient vector.  HBM-bound (128 FLOP/B), see DESIGN.md.
+#include "mlp_tc.cuh"
+
+namespace nerf {
+
+constexpr int kBwdMaxChunks = 40;
+constexpr int kBwdMaxSteps = 12;
+enum : int { STEP_MASK = 0, STEP_XSTASH = 1, STEP_XFINAL = 2 };
+
+struct BwdPlan {
+  uint32_t chunk_off[kBwdMaxChunks];
+  uint32_t chunk_bytes[kBwdMaxChunks];
+  int8_t step_first[kBwdMaxSteps], step_nch[kBwdMaxSteps], step_kind[kBwdMaxSteps], step_layer[kBwdMaxSteps];
+  int16_t step_n[kBwdMaxSteps];
+  int32_t n_steps, n_chunks;
+  uint32_t w_sigma_off;  // fp32 [256]: sigma-head kernel rows 0..255
+  uint32_t w_rgb_off;    // fp32 float4 [128]: rgb-head kernel rows
+  uint32_t total_bytes;
+};
+
+static void make_bwd_plan(BwdPlan* p) {
+  memset(p, 0, sizeof(*p));
+  int c = 0, s = 0;
+  uint32_t off = 0;
+  auto step = [&](int kind, int layer, int n, int nch) {
+    p->step_first[s] = (int8_t)c;
+    p->step_nch[s] = (int8_t)nch;
+    p->step_kind[s] = (int8_t)kind;
+    p->step_layer[s] = (int8_t)layer;
+    p->step_n[s] = (int16_t)n;
+    for (int i = 0; i < nch; ++i, ++c) {
+      p->chunk_off[c] = off;
+      p->chunk_bytes[c] = (uint32_t)n * 128u;
+      off += (uint32_t)n * 128u;
+    }
+    ++s;
+  };
+  step(STEP_MASK, 8, 256, 2);                       // dH8 = dZ_L W8[0:256]^T  (+ sigma term in the epilogue)
+  for (int l = 7; l >= 5; --l) step(STEP_MASK, l, 256, 4);
+  step(STEP_XSTASH, 4, 64, 4);                      // d xyz  = dZ5 W4[0:dx]^T
+  step(STEP_MASK, 4, 256, 4);                       // dH4 = dZ5 W4[dx:dx+256]^T
+  for (int l = 3; l >= 1; --l) step(STEP_MASK, l, 256, 4);
+  step(STEP_XFINAL, 0, 64, 4);                      // d xyz += dZ1 W0^T
+  p->n_steps = s;
+  p->n_chunks = c;
+  p->w_sigma_off = off;  off += 256 * 4;
+  p->w_rgb_off = off;    off += 128 * 16;
+  p->total_bytes = off;
+}
+
+uint32_t bwd_pack_bytes() {
+  BwdPlan p;
+  make_bwd_plan(&p);
+  return p.total_bytes;
+}
+
+__global__ void pack_bwd_kernel(const __grid_constant__ BwdPlan plan, NetGeom g, const float* __restrict__ P,
+                                uint8_t* __restrict__ packed) {
+  const int chunk = blockIdx.y;
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (chunk < plan.n_chunks) {
+    int s = 0;
+    while (!(chunk >= plan.step_first[s] && chunk < plan.step_first[s] + plan.step_nch[s])) ++s;
+    const int rows = plan.step_n[s];
+    if (e >= rows * 64) return;
+    const int j = e >> 6, kk = e & 63;
+    const int n = (chunk - plan.step_first[s]) * 64 + kk;   // output unit of the forward layer (contraction index)
+    const int kind = plan.step_kind[s], layer = plan.step_layer[s];
+    float v = 0.f;
+    if (kind == STEP_MASK) {
+      const LayerDesc& L = g.layers[layer];
+      int row = (layer == 4) ? g.dx + j : j;
+      if (n < L.out) v = P[L.w_off + (int64_t)row * L.out + n];
+    } else {
+      const LayerDesc& L = g.layers[kind == STEP_XSTASH ? 4 : 0];
+      if (j < g.dx) v = P[L.w_off + (int64_t)j * L.out + n];
+    }
+    *reinterpret_cast<__nv_bfloat16*>(packed + plan.chunk_off[chunk] + panel_offset(j, kk)) = __float2bfloat16_rn(v);
+  } else {
+    if (e < 256) reinterpret_cast<float*>(packed + plan.w_sigma_off)[e] = P[g.layers[10].w_off + e];
+    if (e < 128) {
+      const LayerDesc& L = g.layers[9];
+      reinterpret_cast<float4*>(packed + plan.w_rgb_off)[e] =
+          make_float4(P[L.w_off + e * 3 + 0], P[L.w_off + e * 3 + 1], P[L.w_off + e * 3 + 2], 0.f);
+    }
+  }
+}
+
+int bwd_pack_weights(const NetGeom& g, const float* params, uint8_t* packed_bwd, cudaStream_t st) {
+  BwdPlan plan;
+  make_bwd_plan(&plan);
+  dim3 grid((256 * 64 + 255) / 256, plan.n_chunks + 1);
+  pack_bwd_kernel<<<grid, 256, 0, st>>>(plan, g, params, packed_bwd);
+  NERF_CHECK_LAUNCH();
+  return NERF_OK;
+}
+
+// =====================================================================================================================
+// (1) dX chain
+// =====================================================================================================================
+constexpr int kSmemCAct = 0;                                          // [2 tiles][4 panels]
+constexpr int kSmemCStage = 2 * kActPanels * kPanelBytes;             // [kStages] x 32 KB
+constexpr int kSmemCBar = kSmemCStage + kStages * kStageBytes;
+constexpr int kSmemCAlloc = kSmemCBar + 256 + 1024;
+
+struct ChainBars {
+  uint64_t full[kStages], empty[kStages], act_ready[2], acc_full[2];
+  uint32_t tmem_base;
+};
+
+__device__ __forceinline__ void store_chunk16(uint8_t* panel_row, int r, int chunk16, uint4 v) {
+  *reinterpret_cast<uint4*>(panel_row + ((chunk16 ^ (r & 7)) << 4)) = v;
+}
+
+__global__ void __launch_bounds__(kThreadsFwd, 1)
+mlp_tc_bwd_chain_kernel(const __grid_constant__ BwdPlan plan, const uint8_t* __restrict__ packed,
+                        const uint8_t* __restrict__ saved, const float* __restrict__ d_out4, int64_t M,
+                        uint8_t* __restrict__ dz_ws, float* __restrict__ d_xyz_enc, int dx, float alpha) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const uint32_t sbase = smem_u32(smem);
+  ChainBars* bars = reinterpret_cast<ChainBars*>(smem + kSmemCBar);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool need_dx = d_xyz_enc != nullptr;
+  const int64_t n_tiles = (M + kTileM - 1) / kTileM;
+  const int64_t n_pairs = (n_tiles + 1) / 2;
+  int last_step = 0;
+  for (int s = 0; s < plan.n_steps; ++s)
+    if (need_dx || plan.step_kind[s] == STEP_MASK) last_step = s;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kStages; ++s) { mbar_init(smem_u32(&bars->full[s]), 1); mbar_init(smem_u32(&bars->empty[s]), 1); }
+    for (int t = 0; t < 2; ++t) { mbar_init(smem_u32(&bars->act_ready[t]), 128); mbar_init(smem_u32(&bars->acc_full[t]), 1); }
+    fence_barrier_init();
+  }
+  if (warp == 9) tmem_alloc(smem_u32(&bars->tmem_base), 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = bars->tmem_base;
+
+  if (warp == 8) {
+    if (lane == 0) {
+      uint32_t g = 0;
+      for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
+        for (int s = 0; s < plan.n_steps; ++s) {
+          if (!need_dx && plan.step_kind[s] != STEP_MASK) continue;
+          for (int ci = 0; ci < plan.step_nch[s]; ++ci, ++g) {
+            const int c = plan.step_first[s] + ci;
+            const uint32_t st = g % kStages, ph = (g / kStages) & 1u;
+            mbar_wait(smem_u32(&bars->empty[st]), ph ^ 1u);
+            mbar_arrive_expect_tx(smem_u32(&bars->full[st]), plan.chunk_bytes[c]);
+            bulk_g2s(sbase + kSmemCStage + st * kStageBytes, packed + plan.chunk_off[c], plan.chunk_bytes[c],
+                     smem_u32(&bars->full[st]));
+          }
+        }
+      }
+    }
+  } else if (warp == 9) {
+    if (lane == 0) {
+      uint32_t g = 0, act_cnt = 0;
+      for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
+        for (int s = 0; s < plan.n_steps; ++s) {
+          if (!need_dx && plan.step_kind[s] != STEP_MASK) continue;
+          const uint32_t idesc = make_idesc(plan.step_n[s]);
+          const int nch = plan.step_nch[s];
+          for (int ci = 0; ci < nch; ++ci, ++g) {
+            const uint32_t st = g % kStages, ph = (g / kStages) & 1u;
+            mbar_wait(smem_u32(&bars->full[st]), ph);
+            const uint32_t b_addr = sbase + kSmemCStage + st * kStageBytes;
+#pragma unroll
+            for (int t = 0; t < 2; ++t) {
+              if (ci == 0) mbar_wait(smem_u32(&bars->act_ready[t]), act_cnt & 1u);
+              tc_fence_after();
+              const uint32_t a_addr = sbase + kSmemCAct + (t * kActPanels + ci) * kPanelBytes;
+              const uint32_t d_tmem = tmem_base + (uint32_t)t * 256u;
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                umma_bf16(d_tmem, make_desc_kmajor(a_addr + k * 32), make_desc_kmajor(b_addr + k * 32), idesc,
+                          (ci > 0 || k > 0) ? 1u : 0u);
+              if (ci == nch - 1) umma_commit(smem_u32(&bars->acc_full[t]));
+            }
+            umma_commit(smem_u32(&bars->empty[st]));
+          }
+          ++act_cnt;
+        }
+      }
+    }
+  } else {
+    const int t = warp >> 2, q = warp & 3;
+    const int r = q * 32 + lane;
+    const int gtid = threadIdx.x & 127;
+    const int bar_id = 1 + t;
+    uint8_t* act = smem + kSmemCAct + t * kActPanels * kPanelBytes;
+    const uint32_t act_u32 = sbase + kSmemCAct + t * kActPanels * kPanelBytes;
+    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)t * 256u;
+    const float* w_sigma = reinterpret_cast<const float*>(packed + plan.w_sigma_off);
+    const float4* w_rgb = reinterpret_cast<const float4*>(packed + plan.w_rgb_off);
+    uint32_t acc_cnt = 0;
+    for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
+      const int64_t tile = pair * 2 + t;
+      const int64_t row = tile * kTileM + r;
+      const bool row_ok = row < M;
+      const uint8_t* saved_tile = saved + (size_t)tile * kSavedTileBytes;
+      const uint32_t* saved_mask = reinterpret_cast<const uint32_t*>(saved_tile + (size_t)kSavedPanels * kPanelBytes);
+      uint8_t* dz_tile = dz_ws + (size_t)tile * kDzTileBytes;
+      // ---- prologue: dZ_L (panels 0,1), sigma-gradient panel (2), d_out panel (3)
+      if (gtid == 0) bulk_wait_read0();
+      named_bar_sync(bar_id, 128);
+      float4 d4 = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (row_ok) d4 = __ldg(reinterpret_cast<const float4*>(d_out4) + row);
+      {
+        uint32_t mw[4];
+#pragma unroll
+        for (int w = 0; w < 4; ++w) mw[w] = __ldg(saved_mask + (8 * 8 + w) * 128 + r);
+#pragma unroll
+        for (int jg = 0; jg < 16; ++jg) {
+          float v[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int j = jg * 8 + i;
+            float4 w = __ldg(w_rgb + j);
+            float dh = d4.x * w.x + d4.y * w.y + d4.z * w.z;
+            v[i] = ((mw[j >> 5] >> (j & 31)) & 1u) ? dh : alpha * dh;
+          }
+          uint4 pk = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]),
+                                pack_bf16x2(v[6], v[7]));
+          store_chunk16(act + (jg >> 3) * kPanelBytes + r * 128, r, jg & 7, pk);
+        }
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          uint4 sg = make_uint4(c == 0 ? pack_bf16x2(d4.w, 0.f) : 0u, 0u, 0u, 0u);
+          uint4 od = make_uint4(c == 0 ? pack_bf16x2(d4.x, d4.y) : 0u, c == 0 ? pack_bf16x2(d4.z, d4.w) : 0u, 0u, 0u);
+          store_chunk16(act + 2 * kPanelBytes + r * 128, r, c, sg);
+          store_chunk16(act + 3 * kPanelBytes + r * 128, r, c, od);
+        }
+      }
+      fence_proxy_async();
+      mbar_arrive(smem_u32(&bars->act_ready[t]));
+      named_bar_sync(bar_id, 128);
+      if (gtid == 0) {
+        bulk_s2g(dz_tile + (size_t)kDzPanelL * kPanelBytes, act_u32, 3 * kPanelBytes);
+        bulk_s2g(dz_tile + (size_t)kDzPanelOut * kPanelBytes, act_u32 + 3 * kPanelBytes, kPanelBytes);
+        bulk_commit();
+      }
+      float xs[40];
+#pragma unroll
+      for (int i = 0; i < 40; ++i) xs[i] = 0.f;
+
+      for (int s = 0; s < plan.n_steps; ++s) {
+        const int kind = plan.step_kind[s];
+        if (!need_dx && kind != STEP_MASK) continue;
+        mbar_wait(smem_u32(&bars->acc_full[t]), acc_cnt & 1u);
+        ++acc_cnt;
+        tc_fence_after();
+        if (kind == STEP_MASK) {
+          const int l = plan.step_layer[s];
+          if (gtid == 0) bulk_wait_read0();
+          named_bar_sync(bar_id, 128);
+          const uint32_t* mk = saved_mask + ((l - 1) * 8) * 128 + r;
+#pragma unroll 1
+          for (int c0 = 0; c0 < 256; c0 += 32) {
+            uint32_t acc[32];
+            tmem_ld32(taddr + c0, acc);
+            tmem_ld_wait();
+            const uint32_t mw = __ldg(mk + (c0 >> 5) * 128);
+            uint8_t* prow = act + (c0 >> 6) * kPanelBytes + r * 128;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              float v[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                float a = __uint_as_float(acc[8 * j + i]);
+                if (l == 8) a = fmaf(d4.w, __ldg(w_sigma + c0 + 8 * j + i), a);
+                v[i] = ((mw >> (8 * j + i)) & 1u) ? a : alpha * a;
+              }
+              uint4 pk = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]),
+                                    pack_bf16x2(v[6], v[7]));
+              store_chunk16(prow, r, ((c0 & 63) >> 3) + j, pk);
+            }
+          }
+          tc_fence_before();
+          fence_proxy_async();
+          if (s != last_step) mbar_arrive(smem_u32(&bars->act_ready[t]));
+          named_bar_sync(bar_id, 128);
+          if (gtid == 0) {
+            bulk_s2g(dz_tile + (size_t)dz_panel(l) * kPanelBytes, act_u32, kActPanels * kPanelBytes);
+            bulk_commit();
+          }
+        } else {
+          uint32_t a0[32], a1[16];
+          tmem_ld32(taddr, a0);
+          tmem_ld16(taddr + 32, a1);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) xs[i] += __uint_as_float(a0[i]);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) xs[32 + i] += __uint_as_float(a1[i]);
+          tc_fence_before();
+          if (kind == STEP_XSTASH) {
+            mbar_arrive(smem_u32(&bars->act_ready[t]));
+          } else if (row_ok) {
+            float* dst = d_xyz_enc + row * dx;
+#pragma unroll
+            for (int i = 0; i < 40; ++i) if (i < dx) dst[i] = xs[i];
+          }
+        }
+      }
+    }
+    if (gtid == 0) bulk_wait0();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 9) tmem_dealloc(tmem_base, 512);
+}
+
+// =====================================================================================================================
+// (2) dW
+// =====================================================================================================================
+enum : int { OUT_MAIN = 0, OUT_D8A = 1, OUT_INP_XYZ = 2, OUT_INP_VIEW = 3, OUT_D9 = 4 };
+
+struct DwUnit {
+  int16_t a_panel, a_panels, b_panel, b_panels, n, m_blocks, out_kind, dense, has_bias, first_cta, n_ctas;
+};
+struct DwPlan {
+  DwUnit u[16];
+  int32_t n_units;
+};
+
+static void make_dw_plan(DwPlan* p, int n_ctas_total) {
+  memset(p, 0, sizeof(*p));
+  int n = 0;
+  auto add = [&](int a_panel, int a_panels, int b_panel, int b_panels, int nn, int out_kind, int dense, int has_bias) {
+    DwUnit& u = p->u[n++];
+    u.a_panel = (int16_t)a_panel; u.a_panels = (int16_t)a_panels; u.b_panel = (int16_t)b_panel;
+    u.b_panels = (int16_t)b_panels; u.n = (int16_t)nn; u.m_blocks = (int16_t)(a_panels == 4 ? 2 : 1);
+    u.out_kind = (int16_t)out_kind; u.dense = (int16_t)dense; u.has_bias = (int16_t)has_bias;
+  };
+  // Dense l (input h_l, or the input panel) with the gradient of its pre-activation output dZ_{l+1}
+  add(0, 1, dz_panel(1), 4, 256, OUT_INP_XYZ, 0, 1);                                  // Dense 0
+  for (int l = 1; l <= 7; ++l) add(saved_panel_h(l), 4, dz_panel(l + 1), 4, 256, OUT_MAIN, l, 1);  // Dense 1..7 (4: h4 rows)
+  add(0, 1, dz_panel(5), 4, 256, OUT_INP_XYZ, 4, 0);                                  // Dense 4, xyz rows
+  add(saved_panel_h(8), 4, kDzPanelL, 3, 144, OUT_D8A, 8, 1);                          // Dense 8 + sigma head, h8 rows
+  add(0, 1, kDzPanelL, 3, 144, OUT_INP_VIEW, 8, 0);                                    // Dense 8 + sigma head, view rows
+  add(kSavedPanelHL, 2, kDzPanelOut, 1, 16, OUT_D9, 9, 1);                             // rgb head
+  p->n_units = n;
+  // CTAs proportional to the bytes a unit streams per tile
+  int bytes[16], total = 0;
+  for (int i = 0; i < n; ++i) { bytes[i] = p->u[i].a_panels + p->u[i].b_panels; total += bytes[i]; }
+  int used = 0;
+  for (int i = 0; i < n; ++i) {
+    int c = (int)((int64_t)n_ctas_total * bytes[i] / total);
+    if (c < 1) c = 1;
+    p->u[i].n_ctas = (int16_t)c;
+    used += c;
+  }
+  for (int i = 0; used < n_ctas_total; i = (i + 1) % n) {   // hand out the remainder to the heaviest units first
+    if (p->u[i].a_panels == 4) { p->u[i].n_ctas++; ++used; }
+  }
+  int first = 0;
+  for (int i = 0; i < n; ++i) { p->u[i].first_cta = (int16_t)first; first += p->u[i].n_ctas; }
+}
+
+constexpr int kDwStages = 3;
+constexpr int kDwHalf = 8192;                    // one panel restricted to 64 rows
+constexpr int kDwStageBytes = 8 * kDwHalf;       // 4 A slots + 4 B slots
+constexpr int kSmemDwBar = kDwStages * kDwStageBytes;
+constexpr int kSmemDwAlloc = kSmemDwBar + 256 + 1024;
+constexpr int kThreadsDw = 192;
+
+struct DwBars {
+  uint64_t full[kDwStages], empty[kDwStages], acc_full;
+  uint32_t tmem_base;
+};
+
+__device__ __forceinline__ float* dw_target(const DwUnit& u, const NetGeom& g, float* G, int k, int n) {
+  switch (u.out_kind) {
+    case OUT_MAIN: {
+      const LayerDesc& L = g.layers[u.dense];
+      int row = (u.dense == 4 ? g.dx : 0) + k;
+      return G + L.w_off + (int64_t)row * L.out + n;
+    }
+    case OUT_D8A:
+      if (n < 128) return G + g.layers[8].w_off + (int64_t)k * 128 + n;
+      if (n == 128) return G + g.layers[10].w_off + k;
+      return nullptr;
+    case OUT_INP_XYZ:
+      if (k < g.dx) return G + g.layers[u.dense].w_off + (int64_t)k * 256 + n;
+      return nullptr;
+    case OUT_INP_VIEW: {
+      if (k < kInpViewCol || k >= kInpViewCol + g.dv) return nullptr;
+      int row = g.hidden + (k - kInpViewCol);
+      if (n < 128) return G + g.layers[8].w_off + (int64_t)row * 128 + n;
+      if (n == 128) return G + g.layers[10].w_off + row;
+      return nullptr;
+    }
+    case OUT_D9:
+      if (n < 3) return G + g.layers[9].w_off + (int64_t)k * 3 + n;
+      return nullptr;
+  }
+  return nullptr;
+}
+
+__device__ __forceinline__ float* db_target(const DwUnit& u, const NetGeom& g, float* G, int n) {
+  switch (u.out_kind) {
+    case OUT_MAIN:
+    case OUT_INP_XYZ: return G + g.layers[u.dense].b_off + n;
+    case OUT_D8A:
+      if (n < 128) return G + g.layers[8].b_off + n;
+      if (n == 128) return G + g.layers[10].b_off;
+      return nullptr;
+    case OUT_D9: return n < 3 ? G + g.layers[9].b_off + n : nullptr;
+  }
+  return nullptr;
+}
+
+__global__ void __launch_bounds__(kThreadsDw, 1)
+mlp_tc_bwd_dw_kernel(const __grid_constant__ DwPlan plan, const __grid_constant__ NetGeom g,
+                     const uint8_t* __restrict__ saved, const uint8_t* __restrict__ dz_ws, int64_t M,
+                     float* __restrict__ G) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const uint32_t sbase = smem_u32(smem);
+  DwBars* bars = reinterpret_cast<DwBars*>(smem + kSmemDwBar);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  int ui = 0;
+  while (ui + 1 < plan.n_units && (int)blockIdx.x >= plan.u[ui].first_cta + plan.u[ui].n_ctas) ++ui;
+  const DwUnit& u = plan.u[ui];
+  const int split = blockIdx.x - u.first_cta;
+  const int64_t n_tiles = (M + kTileM - 1) / kTileM;
+  const int64_t per = (n_tiles + u.n_ctas - 1) / u.n_ctas;
+  const int64_t tb = min(n_tiles, split * per), te = min(n_tiles, (split + 1) * per);
+  if (tb >= te) return;                       // whole CTA leaves together: nothing to do for this split
+  const uint32_t n_stages_total = (uint32_t)(te - tb) * 2u;
+
+  // zero the operand slots once: the unused second A block of the input-panel units must read as zeros
+  for (int i = threadIdx.x; i < kDwStages * kDwStageBytes / 16; i += blockDim.x)
+    reinterpret_cast<uint4*>(smem)[i] = make_uint4(0u, 0u, 0u, 0u);
+  fence_proxy_async();
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kDwStages; ++s) { mbar_init(smem_u32(&bars->full[s]), 1); mbar_init(smem_u32(&bars->empty[s]), 5); }
+    mbar_init(smem_u32(&bars->acc_full), 1);
+    fence_barrier_init();
+  }
+  if (warp == 5) tmem_alloc(smem_u32(&bars->tmem_base), 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = bars->tmem_base;
+  const uint32_t stage_tx = (uint32_t)(u.a_panels + u.b_panels) * kDwHalf;
+
+  if (warp == 4) {
+    if (lane == 0) {
+      uint32_t gi = 0;
+      for (int64_t tile = tb; tile < te; ++tile) {
+        const uint8_t* a_src = saved + (size_t)tile * kSavedTileBytes + (size_t)u.a_panel * kPanelBytes;
+        const uint8_t* b_src = dz_ws + (size_t)tile * kDzTileBytes + (size_t)u.b_panel * kPanelBytes;
+        for (int half = 0; half < 2; ++half, ++gi) {
+          const uint32_t st = gi % kDwStages, ph = (gi / kDwStages) & 1u;
+          mbar_wait(smem_u32(&bars->empty[st]), ph ^ 1u);
+          const uint32_t fb = smem_u32(&bars->full[st]);
+          mbar_arrive_expect_tx(fb, stage_tx);
+          const uint32_t dst = sbase + st * kDwStageBytes;
+          for (int p = 0; p < u.a_panels; ++p)
+            bulk_g2s(dst + p * kDwHalf, a_src + (size_t)p * kPanelBytes + half * kDwHalf, kDwHalf, fb);
+          for (int p = 0; p < u.b_panels; ++p)
+            bulk_g2s(dst + (4 + p) * kDwHalf, b_src + (size_t)p * kPanelBytes + half * kDwHalf, kDwHalf, fb);
+        }
+      }
+    }
+  } else if (warp == 5) {
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc(u.n, 1, 1);
+      for (uint32_t gi = 0; gi < n_stages_total; ++gi) {
+        const uint32_t st = gi % kDwStages, ph = (gi / kDwStages) & 1u;
+        mbar_wait(smem_u32(&bars->full[st]), ph);
+        tc_fence_after();
+        const uint32_t base = sbase + st * kDwStageBytes;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const uint64_t b_desc = make_desc(base + 4 * kDwHalf + k * 2048, kDwHalf, 1024);
+          for (int mb = 0; mb < u.m_blocks; ++mb) {
+            const uint64_t a_desc = make_desc(base + 2 * mb * kDwHalf + k * 2048, kDwHalf, 1024);
+            umma_bf16(tmem_base + (uint32_t)mb * 256u, a_desc, b_desc, idesc, (gi > 0 || k > 0) ? 1u : 0u);
+          }
+        }
+        umma_commit(smem_u32(&bars->empty[st]));
+      }
+      umma_commit(smem_u32(&bars->acc_full));
+    }
+  } else {
+    // warps 0..3: bias-gradient column sums from the dZ stages, then the accumulator drain
+    const int tid = threadIdx.x;                       // 0..127, owns columns 2*tid, 2*tid+1
+    const int c = 2 * tid;
+    const bool col_ok = u.has_bias && c < u.n;
+    float s0 = 0.f, s1 = 0.f;
+    for (uint32_t gi = 0; gi < n_stages_total; ++gi) {
+      const uint32_t st = gi % kDwStages, ph = (gi / kDwStages) & 1u;
+      mbar_wait(smem_u32(&bars->full[st]), ph);
+      if (col_ok) {
+        const uint8_t* pb = smem + st * kDwStageBytes + (4 + (c >> 6)) * kDwHalf;
+        const int cc = c & 63;
+#pragma unroll 8
+        for (int rr = 0; rr < 64; ++rr) {
+          uint32_t wv = *reinterpret_cast<const uint32_t*>(pb + panel_offset(rr, cc));
+          __nv_bfloat162 v2 = *reinterpret_cast<__nv_bfloat162*>(&wv);
+          s0 += __low2float(v2);
+          s1 += __high2float(v2);
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&bars->empty[st]));
+    }
+    if (col_ok) {
+      float* t0 = db_target(u, g, G, c);
+      float* t1 = db_target(u, g, G, c + 1);
+      if (t0) atomicAdd(t0, s0);
+      if (t1 && c + 1 < u.n) atomicAdd(t1, s1);
+    }
+    mbar_wait(smem_u32(&bars->acc_full), 0);
+    tc_fence_after();
+    const int q = warp;  // TMEM lane quarter
+    for (int mb = 0; mb < u.m_blocks; ++mb) {
+      const int k = mb * 128 + q * 32 + lane;
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)mb * 256u;
+      for (int c0 = 0; c0 < u.n; c0 += 16) {
+        uint32_t acc[16];
+        tmem_ld16(taddr + c0, acc);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          float* tgt = dw_target(u, g, G, k, c0 + i);
+          if (tgt) atomicAdd(tgt, __uint_as_float(acc[i]));
+        }
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 5) tmem_dealloc(tmem_base, 512);
+}
+
+// ---- host ---------------------------------------------------------------------------------------------------------------
+int mlp_tc_bwd(const nerf_net_cfg* cfg, const NetGeom& g, const float* params, const void* packed, const float* xyz_enc,
+               const float* view_enc, const void* saved, const float* d_out4, int64_t m, float* grads, float* d_xyz_enc,
+               void* workspace, cudaStream_t st) {
+  (void)params; (void)xyz_enc; (void)view_enc;
+  TcPlan fplan;
+  if (!make_plan(g, &fplan)) {
+    set_error("NERF_MODE_BF16 supports hidden=256, last_hidden=128, n_angles in {1,2}, xyz width <= 40, view width <= 24");
+    return NERF_E_UNSUPPORTED;
+  }
+  static bool attr_set = false;
+  if (!attr_set) {
+    NERF_CUDA(cudaFuncSetAttribute(mlp_tc_bwd_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemCAlloc));
+    NERF_CUDA(cudaFuncSetAttribute(mlp_tc_bwd_dw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemDwAlloc));
+    attr_set = true;
+  }
+  BwdPlan bplan;
+  make_bwd_plan(&bplan);
+  const uint8_t* packed_bwd = (const uint8_t*)packed + ((fplan.total_bytes + 1023u) & ~1023u);
+  uint8_t* dz_ws = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(workspace) + 1023) & ~(uintptr_t)1023);
+  int64_t n_pairs = ((m + kTileM - 1) / kTileM + 1) / 2;
+  int grid = (int)(n_pairs < kNumSMs ? n_pairs : kNumSMs);
+  mlp_tc_bwd_chain_kernel<<<grid, kThreadsFwd, kSmemCAlloc, st>>>(bplan, packed_bwd, (const uint8_t*)saved, d_out4, m,
+                                                                 dz_ws, d_xyz_enc, g.dx, cfg->leaky_alpha);
+  NERF_CHECK_LAUNCH();
+  DwPlan dplan;
+  make_dw_plan(&dplan, kNumSMs);
+  mlp_tc_bwd_dw_kernel<<<kNumSMs, kThreadsDw, kSmemDwAlloc, st>>>(dplan, g, (const uint8_t*)saved, dz_ws, m, grads);
+  NERF_CHECK_LAUNCH();
+  return NERF_OK;
+}
+
+}  // namespace nerf
