@@ -34,11 +34,12 @@ def main():
     ap.add_argument("--rays", type=int, default=4096)
     ap.add_argument("--mode", default="bf16")
     ap.add_argument("--bwd", action="store_true")
+    ap.add_argument("--only", default="all", choices=["all", "mlp", "composite"])
     args = ap.parse_args()
     call, ptr = pkg._lib.call, pkg._lib.ptr
     cfg = pkg.NetCfg(5, 4, 2, 256, 128, 0.05)
     net = pkg.NerfMLP(cfg, mode=args.mode, seed=0)
-    for s in (64, 128, 192):
+    for s in ((64, 128, 192) if args.only != "composite" else ()):
         m = args.rays * s
         xyz = torch.randn(m, 33, device="cuda")
         view = torch.randn(m, 24, device="cuda")
@@ -63,7 +64,7 @@ def main():
             flops = 2 * (512152 + 509056) * m
             print(f"mlp_bwd[{args.mode}]                    M={m:8d}: {med:8.3f} ms  {flops / med / 1e9:8.1f} TFLOP/s")
     # compositing: one 256x256 frame
-    for n, s in ((65536, 192), (65536, 64), (4096 * 16, 128)):
+    for n, s in (((65536, 192), (65536, 64), (4096 * 16, 128)) if args.only != "mlp" else ()):
         raw = torch.randn(n, s, 4, device="cuda")
         z = torch.sort(torch.rand(n, s, device="cuda"), -1).values
         rgb = torch.empty(n, 3, device="cuda"); w = torch.empty(n, s, device="cuda"); T = torch.empty(n, s, device="cuda")
