@@ -104,7 +104,14 @@ int64_t nerf_mlp_workspace_bytes(const nerf_net_cfg* cfg, int64_t m, int32_t mod
 int nerf_mlp_fwd(const nerf_net_cfg* cfg, const float* params, const void* packed_or_null,
                  const float* xyz_enc, const float* view_enc, int64_t m, float* out4, void* saved_or_null,
                  void* workspace, int32_t mode, void* stream);
-/* grads (+= , same layout as params); d_xyz_enc_or_null (M, Dx) is written when non-null. */
+/* Fused K1+K2 (NERF_MODE_BF16 only): render_rays' sample_along_rays -> get_view_directions -> both positional
+ * encodings -> MLP (src/UtilsNeuralRadianceField.py:204-207) in ONE kernel: the encoded samples are written straight
+ * into the shared-memory A operand of the first layer and never reach HBM.  Rows are ordered ray-major: M = N*S. */
+int nerf_mlp_fwd_rays(const nerf_net_cfg* cfg, const void* packed, const float* origs4, const float* dirs4,
+                      const float* z, int64_t n_rays, int32_t n_samples, float* out4, void* saved_or_null,
+                      int32_t mode, void* stream);
+/* grads (+= , same layout as params); d_xyz_enc_or_null (M, Dx) is written when non-null.  xyz_enc / view_enc may be
+ * null in NERF_MODE_BF16 (the forward pass saved its bf16 input panel). */
 int nerf_mlp_bwd(const nerf_net_cfg* cfg, const float* params, const void* packed_or_null,
                  const float* xyz_enc, const float* view_enc, const void* saved, const float* d_out4,
                  int64_t m, float* grads, float* d_xyz_enc_or_null, void* workspace, int32_t mode,

@@ -45,8 +45,9 @@ class _StepWorkspace:
         mc = model.model_coarse
         self.n = n
         self.z_c = f(n, sc)
-        self.xyz_c = f(n * sc, mc.dx)
-        self.view_c = f(n * sc, mc.dv) if mc.dv else None
+        fused = model.mode == "bf16"          # bf16: encodings are computed inside the MLP kernel, never materialised
+        self.xyz_c = None if fused else f(n * sc, mc.dx)
+        self.view_c = f(n * sc, mc.dv) if (mc.dv and not fused) else None
         self.raw_c = f(n, sc, 4)
         self.rgb_c = f(n, 3)
         self.w_c = f(n, sc)
@@ -61,8 +62,8 @@ class _StepWorkspace:
             self.z_f = f(n, sf)
             self.u = f(n, sf)
             self.perm = torch.empty((n, sf), dtype=torch.int32, device=dev)
-            self.xyz_f = f(n * sf, mc.dx)
-            self.view_f = f(n * sf, mc.dv) if mc.dv else None
+            self.xyz_f = None if fused else f(n * sf, mc.dx)
+            self.view_f = f(n * sf, mc.dv) if (mc.dv and not fused) else None
             self.raw_f = f(n, sf, 4)
             self.rgb_f = f(n, 3)
             self.d_rgb_f = f(n, 3)
@@ -166,13 +167,17 @@ class NeRF:
         """Inference-only fast path: fused encode -> MLP -> compositing, no autograd bookkeeping."""
         n, s = z.shape
         dev = z.device
-        xyz = torch.empty((n * s, model.dx), dtype=torch.float32, device=dev)
-        view = torch.empty((n * s, model.dv), dtype=torch.float32, device=dev) if model.dv else None
-        call("nerf_encode_samples", model.cfg_ref, ptr(rays_orig), ptr(rays_dirs), ptr(z), n, s, ptr(xyz), ptr(view))
         raw = torch.empty((n, s, 4), dtype=torch.float32, device=dev)
-        ws = model._buffer("ws_fwd", model.workspace_bytes(n * s, False))
-        call("nerf_mlp_fwd", model.cfg_ref, ptr(model.params), ptr(model.packed_for(model.params)), ptr(xyz), ptr(view),
-             n * s, ptr(raw), None, ptr(ws), model.mode_id)
+        if model.mode == "bf16":
+            call("nerf_mlp_fwd_rays", model.cfg_ref, ptr(model.packed_for(model.params)), ptr(rays_orig), ptr(rays_dirs),
+                 ptr(z), n, s, ptr(raw), None, model.mode_id)
+        else:
+            xyz = torch.empty((n * s, model.dx), dtype=torch.float32, device=dev)
+            view = torch.empty((n * s, model.dv), dtype=torch.float32, device=dev) if model.dv else None
+            call("nerf_encode_samples", model.cfg_ref, ptr(rays_orig), ptr(rays_dirs), ptr(z), n, s, ptr(xyz), ptr(view))
+            ws = model._buffer("ws_fwd", model.workspace_bytes(n * s, False))
+            call("nerf_mlp_fwd", model.cfg_ref, ptr(model.params), ptr(model.packed_for(model.params)), ptr(xyz),
+                 ptr(view), n * s, ptr(raw), None, ptr(ws), model.mode_id)
         with torch.no_grad():
             if lean:
                 return _unrf.ray_marching_lean(raw, z)
@@ -294,9 +299,7 @@ class NeRF:
         # coarse forward
         call("nerf_stratified_z", self.near_boundary, self.far_boundary, n, sc, ptr(jitter), seed, step, ray_offset,
              ptr(w.z_c))
-        call("nerf_encode_samples", mc.cfg_ref, ptr(o), ptr(d), ptr(w.z_c), n, sc, ptr(w.xyz_c), ptr(w.view_c))
-        call("nerf_mlp_fwd", mc.cfg_ref, ptr(mc.params), ptr(mc.packed_for(mc.params)), ptr(w.xyz_c), ptr(w.view_c),
-             n * sc, ptr(w.raw_c), ptr(w.saved_c), ptr(w.ws_fwd), mc.mode_id)
+        self._mlp_fwd_train(mc, o, d, w.z_c, n, sc, w.xyz_c, w.view_c, w.raw_c, w.saved_c, w.ws_fwd)
         call("nerf_composite_fwd", ptr(w.raw_c), ptr(w.z_c), n, sc, ptr(w.rgb_c), ptr(w.w_c), None, None, None, None,
              None)
         call("nerf_mse_fwd_bwd", ptr(w.rgb_c), ptr(y), n, n_total, self.COARSE_LOSS_WEIGHT, ptr(sums[0:1]),
@@ -306,9 +309,7 @@ class NeRF:
             # fine forward on the n_f importance samples only (src/NeRF.py:155-156)
             call("nerf_sample_pdf_fwd", ptr(w.w_c), ptr(w.z_c), n, sc, sf, ptr(u), seed, step, ray_offset, ptr(w.z_f),
                  None, ptr(w.perm), ptr(w.u))
-            call("nerf_encode_samples", mf.cfg_ref, ptr(o), ptr(d), ptr(w.z_f), n, sf, ptr(w.xyz_f), ptr(w.view_f))
-            call("nerf_mlp_fwd", mf.cfg_ref, ptr(mf.params), ptr(mf.packed_for(mf.params)), ptr(w.xyz_f),
-                 ptr(w.view_f), n * sf, ptr(w.raw_f), ptr(w.saved_f), ptr(w.ws_fwd), mf.mode_id)
+            self._mlp_fwd_train(mf, o, d, w.z_f, n, sf, w.xyz_f, w.view_f, w.raw_f, w.saved_f, w.ws_fwd)
             call("nerf_composite_fwd", ptr(w.raw_f), ptr(w.z_f), n, sf, ptr(w.rgb_f), None, None, None, None, None,
                  None)
             call("nerf_mse_fwd_bwd", ptr(w.rgb_f), ptr(y), n, n_total, 1.0, ptr(sums[1:2]), ptr(w.d_rgb_f))
@@ -331,6 +332,16 @@ class NeRF:
         call("nerf_mlp_bwd", mc.cfg_ref, ptr(mc.params), ptr(mc.packed_for(mc.params)), ptr(w.xyz_c), ptr(w.view_c),
              ptr(w.saved_c), ptr(w.d_raw_c), n * sc, ptr(g_c), None, ptr(w.ws_bwd), mc.mode_id)
         return g_c, g_f, sums
+
+    def _mlp_fwd_train(self, net, o, d, z, n, s, xyz, view, raw, saved, ws):
+        """Training-mode MLP forward (activations saved): fused encode+MLP kernel in bf16 mode, two kernels in fp32."""
+        if self.mode == "bf16":
+            call("nerf_mlp_fwd_rays", net.cfg_ref, ptr(net.packed_for(net.params)), ptr(o), ptr(d), ptr(z), n, s,
+                 ptr(raw), ptr(saved), net.mode_id)
+        else:
+            call("nerf_encode_samples", net.cfg_ref, ptr(o), ptr(d), ptr(z), n, s, ptr(xyz), ptr(view))
+            call("nerf_mlp_fwd", net.cfg_ref, ptr(net.params), ptr(net.packed_for(net.params)), ptr(xyz), ptr(view),
+                 n * s, ptr(raw), ptr(saved), ptr(ws), net.mode_id)
 
     def _metrics(self, sums, n_total):
         mse_c = sums[0] / (3.0 * n_total)

@@ -12,6 +12,8 @@ int mlp_tc_fwd(const nerf_net_cfg* cfg, const NetGeom& g, const float* params, c
 int mlp_tc_bwd(const nerf_net_cfg* cfg, const NetGeom& g, const float* params, const void* packed, const float* xyz_enc,
                const float* view_enc, const void* saved, const float* d_out4, int64_t m, float* grads, float* d_xyz_enc,
                void* workspace, cudaStream_t st);
+int mlp_tc_fwd_rays(const nerf_net_cfg* cfg, const NetGeom& g, const void* packed, const float* origs4, const float* dirs4,
+                    const float* z, int64_t n_rays, int n_samples, float* out4, void* saved, cudaStream_t st);
 int64_t mlp_tc_saved_bytes(const NetGeom& g, int64_t m);
 int64_t mlp_tc_workspace_bytes(const NetGeom& g, int64_t m, int backward);
 
@@ -356,12 +358,29 @@ int nerf_mlp_fwd(const nerf_net_cfg* cfg, const float* params, const void* packe
   return NERF_OK;
 }
 
+int nerf_mlp_fwd_rays(const nerf_net_cfg* cfg, const void* packed, const float* origs4, const float* dirs4, const float* z,
+                      int64_t n_rays, int32_t n_samples, float* out4, void* saved_or_null, int32_t mode, void* stream) {
+  NetGeom g;
+  NERF_CHECK_ARG(make_geom(cfg, &g), "bad net config");
+  NERF_CHECK_ARG(packed && origs4 && dirs4 && z && out4, "null pointer");
+  NERF_CHECK_ARG(n_rays >= 0 && n_samples > 0, "bad shape");
+  if (mode != NERF_MODE_BF16) {
+    set_error("nerf_mlp_fwd_rays: only NERF_MODE_BF16 fuses the encodings into the MLP kernel "
+              "(fp32 mode: nerf_encode_samples + nerf_mlp_fwd)");
+    return NERF_E_UNSUPPORTED;
+  }
+  if (n_rays == 0) return NERF_OK;
+  return mlp_tc_fwd_rays(cfg, g, packed, origs4, dirs4, z, n_rays, n_samples, out4, saved_or_null, (cudaStream_t)stream);
+}
+
 int nerf_mlp_bwd(const nerf_net_cfg* cfg, const float* params, const void* packed_or_null, const float* xyz_enc,
                  const float* view_enc, const void* saved, const float* d_out4, int64_t m, float* grads,
                  float* d_xyz_enc_or_null, void* workspace, int32_t mode, void* stream) {
   NetGeom g;
   NERF_CHECK_ARG(make_geom(cfg, &g), "bad net config");
-  NERF_CHECK_ARG(params && xyz_enc && saved && d_out4 && grads && workspace && (view_enc || !g.view), "null pointer");
+  NERF_CHECK_ARG(params && saved && d_out4 && grads && workspace, "null pointer");
+  // the bf16 path reads the bf16 input panel it saved in the forward pass; only the fp32 path needs the encodings again
+  NERF_CHECK_ARG(mode == NERF_MODE_BF16 || (xyz_enc && (view_enc || !g.view)), "null pointer");
   NERF_CHECK_ARG(m >= 0, "negative row count");
   NERF_CHECK_ARG(mode == NERF_MODE_FP32 || mode == NERF_MODE_BF16, "unknown mode");
   if (m == 0) return NERF_OK;

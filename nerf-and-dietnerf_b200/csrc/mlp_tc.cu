@@ -79,18 +79,65 @@ __global__ void pack_weights_kernel(const __grid_constant__ TcPlan plan, NetGeom
 
 // ---- forward kernel --------------------------------------------------------------------------------------------------------
 struct FwdBars {
-  uint64_t full[kStages], empty[kStages], act_ready[2], acc_full[2];
+  uint64_t full[kStages], empty[kStages], act_ready[2], acc_full[2], bias_full[2], bias_empty[2];
   uint32_t tmem_base;
 };
+
+// Where the MLP input comes from: pre-encoded rows (xyz_enc / view_enc, the standalone model_predict entry point) or,
+// when xyz_enc == nullptr, rays + depths: then the sample position o + d z and both sin/cos encodings are computed in
+// the prologue and written straight into the shared-memory input panel (K1 fused into K2; nothing touches HBM).
+struct FwdInput {
+  const float* xyz_enc;
+  const float* view_enc;
+  const float4* origs;
+  const float4* dirs;
+  const float* z;
+  int32_t n_samples, Lx, Lv, ncomp, dx, dv;
+};
+
+__device__ __forceinline__ void sts_bf16(uint32_t panel_row_addr, int r, int col, float v) {
+  const __nv_bfloat16 h = __float2bfloat16_rn(v);
+  const uint32_t addr = panel_row_addr + ((((uint32_t)col >> 3) ^ ((uint32_t)r & 7u)) << 4) + (((uint32_t)col & 7u) << 1);
+  asm volatile("st.shared.b16 [%0], %1;" ::"r"(addr), "h"(*reinterpret_cast<const uint16_t*>(&h)) : "memory");
+}
+
+// Epilogue of one 32-column group: acc + bias (smem) -> LeakyReLU -> bf16 -> swizzled panel row.  Returns the sign mask
+// (bit (15 - k) = element 2k is positive, bit (31 - k) = element 2k+1 is positive, k = 0..15) when kMask.
+template <bool kMask>
+__device__ __forceinline__ uint32_t epi_group32(const uint32_t (&acc)[32], uint32_t bias_addr, float alpha,
+                                                uint32_t prow_addr, int r, int chunk_base) {
+  uint32_t mword = 0;
+  const uint64_t alpha2 = pack_f32x2(alpha, alpha);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float4 b0 = lds128f(bias_addr + 32 * j);
+    const float4 b1 = lds128f(bias_addr + 32 * j + 16);
+    const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+    uint32_t pk[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const uint64_t x = add_f32x2(pack_f32x2(__uint_as_float(acc[8 * j + 2 * i]), __uint_as_float(acc[8 * j + 2 * i + 1])),
+                                   pack_f32x2(bb[2 * i], bb[2 * i + 1]));
+      const uint64_t lo = mul_f32x2(x, alpha2);
+      float x0, x1, l0, l1;
+      unpack_f32x2(x, x0, x1);
+      unpack_f32x2(lo, l0, l1);
+      pk[i] = pack_bf16x2(fmaxf(x0, l0), fmaxf(x1, l1));      // LeakyReLU for 0 <= alpha <= 1
+      if (kMask) mword |= (~pk[i] >> (4 * j + i)) & (0x80008000u >> (4 * j + i));
+    }
+    sts128(prow_addr + (((chunk_base + j) ^ (r & 7)) << 4), make_uint4(pk[0], pk[1], pk[2], pk[3]));
+  }
+  return mword;
+}
 
 template <bool kSave>
 __global__ void __launch_bounds__(kThreadsFwd, 1)
 mlp_tc_fwd_kernel(const __grid_constant__ TcPlan plan, const uint8_t* __restrict__ packed,
-                  const float* __restrict__ xyz_enc, const float* __restrict__ view_enc, int dx, int dv, int64_t M,
-                  float* __restrict__ out4, uint8_t* __restrict__ saved, float alpha) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+                  const __grid_constant__ FwdInput in, int64_t M, float* __restrict__ out4, uint8_t* __restrict__ saved,
+                  float alpha) {
+  extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t sbase = smem_u32(smem);
+  if ((sbase & 1023u) != 0u) __trap();               // swizzled panels need the 1024-byte alignment
   FwdBars* bars = reinterpret_cast<FwdBars*>(smem + kSmemBar);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -99,30 +146,46 @@ mlp_tc_fwd_kernel(const __grid_constant__ TcPlan plan, const uint8_t* __restrict
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kStages; ++s) { mbar_init(smem_u32(&bars->full[s]), 1); mbar_init(smem_u32(&bars->empty[s]), 1); }
-    for (int t = 0; t < 2; ++t) { mbar_init(smem_u32(&bars->act_ready[t]), 128); mbar_init(smem_u32(&bars->acc_full[t]), 1); }
+    for (int t = 0; t < 2; ++t) {
+      mbar_init(smem_u32(&bars->act_ready[t]), kEpiThreadsPerTile);
+      mbar_init(smem_u32(&bars->acc_full[t]), 1);
+      mbar_init(smem_u32(&bars->bias_full[t]), 1);
+      mbar_init(smem_u32(&bars->bias_empty[t]), 2 * kEpiThreadsPerTile);
+    }
     fence_barrier_init();
   }
-  if (warp == 9) tmem_alloc(smem_u32(&bars->tmem_base), 512);
+  if (warp == kWarpMma) tmem_alloc(smem_u32(&bars->tmem_base), 512);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = bars->tmem_base;
 
-  if (warp == 8) {
-    // ===== weight producer =====
+  if (warp == kWarpProducer) {
+    // ===== producer: weight chunks (ring) and the per-layer bias vector (2 slots) =====
     if (lane == 0) {
-      uint32_t g = 0;
+      uint32_t g = 0, lc = 0;
       for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
-        for (int c = 0; c < plan.n_chunks; ++c, ++g) {
-          const uint32_t s = g % kStages, ph = (g / kStages) & 1u;
-          mbar_wait(smem_u32(&bars->empty[s]), ph ^ 1u);
-          mbar_arrive_expect_tx(smem_u32(&bars->full[s]), plan.chunk_bytes[c]);
-          bulk_g2s(sbase + kSmemStage + s * kStageBytes, packed + plan.chunk_off[c], plan.chunk_bytes[c],
-                   smem_u32(&bars->full[s]));
+        // staggered schedule: tile A runs layer l while tile B's previous accumulator is drained, so each layer's
+        // chunks are streamed once per tile (they come from L2)
+        for (int l = 0; l < plan.n_layers; ++l, ++lc) {
+          const uint32_t slot = lc & 1u;
+          mbar_wait(smem_u32(&bars->bias_empty[slot]), ((lc >> 1) & 1u) ^ 1u);
+          mbar_arrive_expect_tx(smem_u32(&bars->bias_full[slot]), 1024);
+          bulk_g2s(sbase + kSmemBias + slot * 1024, packed + plan.bias_off + l * 1024, 1024, smem_u32(&bars->bias_full[slot]));
+          for (int t = 0; t < 2; ++t) {
+            for (int ci = 0; ci < plan.layer_nchunks[l]; ++ci, ++g) {
+              const int c = plan.layer_first[l] + ci;
+              const uint32_t s = g % kStages, ph = (g / kStages) & 1u;
+              mbar_wait(smem_u32(&bars->empty[s]), ph ^ 1u);
+              mbar_arrive_expect_tx(smem_u32(&bars->full[s]), plan.chunk_bytes[c]);
+              bulk_g2s(sbase + kSmemStage + s * kStageBytes, packed + plan.chunk_off[c], plan.chunk_bytes[c],
+                       smem_u32(&bars->full[s]));
+            }
+          }
         }
       }
     }
-  } else if (warp == 9) {
+  } else if (warp == kWarpMma) {
     // ===== MMA issuer =====
     if (lane == 0) {
       uint32_t g = 0, act_cnt = 0;
@@ -130,67 +193,92 @@ mlp_tc_fwd_kernel(const __grid_constant__ TcPlan plan, const uint8_t* __restrict
         for (int l = 0; l < plan.n_layers; ++l) {
           const uint32_t idesc = make_idesc(plan.layer_n[l]);
           const int first = plan.layer_first[l], nch = plan.layer_nchunks[l];
-          for (int ci = 0; ci < nch; ++ci, ++g) {
-            const int c = first + ci;
-            const uint32_t s = g % kStages, ph = (g / kStages) & 1u;
-            mbar_wait(smem_u32(&bars->full[s]), ph);
-            const uint32_t b_addr = sbase + kSmemStage + s * kStageBytes;
-            const int src = plan.a_src[c];
-#pragma unroll
-            for (int t = 0; t < 2; ++t) {
-              if (ci == 0) mbar_wait(smem_u32(&bars->act_ready[t]), act_cnt & 1u);
+          for (int t = 0; t < 2; ++t) {
+            mbar_wait(smem_u32(&bars->act_ready[t]), act_cnt & 1u);
+            const uint32_t d_tmem = tmem_base + (uint32_t)t * 256u;
+            for (int ci = 0; ci < nch; ++ci, ++g) {
+              const int c = first + ci;
+              const uint32_t s = g % kStages, ph = (g / kStages) & 1u;
+              mbar_wait(smem_u32(&bars->full[s]), ph);
               tc_fence_after();
+              const uint32_t b_addr = sbase + kSmemStage + s * kStageBytes;
+              const int src = plan.a_src[c];
               const uint32_t a_addr = (src < 4) ? sbase + kSmemAct + (t * kActPanels + src) * kPanelBytes
                                                 : sbase + kSmemInp + t * kPanelBytes;
-              const uint32_t d_tmem = tmem_base + (uint32_t)t * 256u;
 #pragma unroll
               for (int k = 0; k < 4; ++k)
                 umma_bf16(d_tmem, make_desc_kmajor(a_addr + k * 32), make_desc_kmajor(b_addr + k * 32), idesc,
                           (ci > 0 || k > 0) ? 1u : 0u);
-              if (ci == nch - 1) umma_commit(smem_u32(&bars->acc_full[t]));
+              umma_commit(smem_u32(&bars->empty[s]));
             }
-            umma_commit(smem_u32(&bars->empty[s]));
+            umma_commit(smem_u32(&bars->acc_full[t]));
           }
           ++act_cnt;
         }
       }
     }
   } else {
-    // ===== epilogue warps: tile t = warp / 4, TMEM lane quarter q = warp % 4 =====
-    const int t = warp >> 2, q = warp & 3;
+    // ===== 16 epilogue warps: tile t = warp / 8, TMEM lane quarter q = warp % 4, column half = (warp / 4) % 2 =====
+    const int t = warp >> 3, q = warp & 3, half = (warp >> 2) & 1;
     const int r = q * 32 + lane;                       // row inside the tile == TMEM lane
-    const int gtid = threadIdx.x & 127;                // thread index inside this tile's group
+    const int gtid = threadIdx.x & (kEpiThreadsPerTile - 1);
     const int bar_id = 1 + t;
-    uint8_t* act = smem + kSmemAct + t * kActPanels * kPanelBytes;
-    uint8_t* inp = smem + kSmemInp + t * kPanelBytes;
     const uint32_t act_u32 = sbase + kSmemAct + t * kActPanels * kPanelBytes;
+    const uint32_t inp_u32 = sbase + kSmemInp + t * kPanelBytes;
     const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)t * 256u;
-    const float* bias_all = reinterpret_cast<const float*>(packed + plan.bias_off);
     const float4* w_rgb = reinterpret_cast<const float4*>(packed + plan.w_rgb_off);
     const float* b_rgb = reinterpret_cast<const float*>(packed + plan.b_rgb_off);
-    uint32_t acc_cnt = 0;
+    uint32_t acc_cnt = 0, lc = 0;
     for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
       const int64_t tile = pair * 2 + t;
       const int64_t row = tile * kTileM + r;
       const bool row_ok = row < M;
-      // ---- prologue: build the input panel row (bf16): cols [0,dx) xyz, [40,40+dv) view, zeros elsewhere
+      // ---- prologue: this thread's half of the input panel row: half 0 = xyz columns (16-byte chunks 0..4),
+      //      half 1 = view columns (chunks 5..7).  Zero first, then scatter the encoded values as bf16.
       {
-        float v[64];
-#pragma unroll
-        for (int i = 0; i < 64; ++i) v[i] = 0.f;
+        const uint32_t prow = inp_u32 + r * 128;
+        const int cb = half ? 5 : 0, ce = half ? 8 : 5;
+        for (int j = cb; j < ce; ++j) sts128(prow + ((j ^ (r & 7)) << 4), make_uint4(0u, 0u, 0u, 0u));
         if (row_ok) {
-          const float* xr = xyz_enc + row * dx;
+          if (in.xyz_enc != nullptr) {
+            if (half == 0) {
+              const float* xr = in.xyz_enc + row * in.dx;
+              for (int i = 0; i < in.dx; ++i) sts_bf16(prow, r, i, __ldg(xr + i));
+            } else {
+              const float* vr = in.view_enc + row * in.dv;
+              for (int i = 0; i < in.dv; ++i) sts_bf16(prow, r, kInpViewCol + i, __ldg(vr + i));
+            }
+          } else {
+            const int64_t ray = row / in.n_samples;
+            const float4 d = __ldg(in.dirs + ray);
+            if (half == 0) {
+              const float4 o = __ldg(in.origs + ray);
+              const float zz = __ldg(in.z + row);
+              const int per = 1 + 2 * in.Lx;
 #pragma unroll
-          for (int i = 0; i < kInpViewCol; ++i) if (i < dx) v[i] = __ldg(xr + i);
-          const float* vr = view_enc + row * dv;
-#pragma unroll
-          for (int i = 0; i < 64 - kInpViewCol; ++i) if (i < dv) v[kInpViewCol + i] = __ldg(vr + i);
-        }
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          uint4 pk = make_uint4(pack_bf16x2(v[8 * j], v[8 * j + 1]), pack_bf16x2(v[8 * j + 2], v[8 * j + 3]),
-                                pack_bf16x2(v[8 * j + 4], v[8 * j + 5]), pack_bf16x2(v[8 * j + 6], v[8 * j + 7]));
-          *reinterpret_cast<uint4*>(inp + r * 128 + ((j ^ (r & 7)) << 4)) = pk;
+              for (int c = 0; c < 3; ++c) {
+                const float oc = c == 0 ? o.x : (c == 1 ? o.y : o.z), dc = c == 0 ? d.x : (c == 1 ? d.y : d.z);
+                const float pc = __fadd_rn(oc, __fmul_rn(dc, zz));       // sample_along_rays, src/UtilsCV.py:598
+                sts_bf16(prow, r, c * per, pc);
+                for (int k = 0; k < in.Lx; ++k) {
+                  float sn, cs;
+                  sincospif(ldexpf(pc, k), &sn, &cs);                      // sin/cos(2^k pi p)
+                  sts_bf16(prow, r, c * per + 1 + 2 * k, sn);
+                  sts_bf16(prow, r, c * per + 2 + 2 * k, cs);
+                }
+              }
+            } else {
+              for (int c = 0; c < in.ncomp; ++c) {
+                const float vc = (in.ncomp == 3) ? (c == 0 ? d.x : (c == 1 ? d.y : d.z)) : (c == 0 ? d.x : d.z);
+                for (int k = 0; k < in.Lv; ++k) {
+                  float sn, cs;
+                  sincospif(ldexpf(vc, k), &sn, &cs);
+                  sts_bf16(prow, r, kInpViewCol + c * 2 * in.Lv + 2 * k, sn);
+                  sts_bf16(prow, r, kInpViewCol + c * 2 * in.Lv + 2 * k + 1, cs);
+                }
+              }
+            }
+          }
         }
       }
       fence_proxy_async();
@@ -198,109 +286,107 @@ mlp_tc_fwd_kernel(const __grid_constant__ TcPlan plan, const uint8_t* __restrict
       uint8_t* saved_tile = kSave ? saved + (size_t)tile * kSavedTileBytes : nullptr;
       uint32_t* saved_mask = reinterpret_cast<uint32_t*>(saved_tile + (size_t)kSavedPanels * kPanelBytes);
       if (kSave) {
-        named_bar_sync(bar_id, 128);
+        named_bar_sync(bar_id, kEpiThreadsPerTile);
         if (gtid == 0) {
-          bulk_s2g(saved_tile, sbase + kSmemInp + t * kPanelBytes, kPanelBytes);
+          bulk_s2g(saved_tile, inp_u32, kPanelBytes);
           bulk_commit();
         }
       }
 
-      for (int l = 0; l < plan.n_layers; ++l) {
+      for (int l = 0; l < plan.n_layers; ++l, ++lc) {
+        const uint32_t slot = lc & 1u;
+        const uint32_t bias_u32 = sbase + kSmemBias + slot * 1024;
+        mbar_wait(smem_u32(&bars->bias_full[slot]), (lc >> 1) & 1u);
         mbar_wait(smem_u32(&bars->acc_full[t]), acc_cnt & 1u);
         ++acc_cnt;
         tc_fence_after();
         if (kSave) {
           // the previous layer's bulk stores still read the panels this epilogue overwrites
           if (gtid == 0) bulk_wait_read0();
-          named_bar_sync(bar_id, 128);
+          named_bar_sync(bar_id, kEpiThreadsPerTile);
         }
-        const float* bias = bias_all + l * 256;
         if (l < 8) {
-#pragma unroll 1
-          for (int c0 = 0; c0 < 256; c0 += 32) {
-            uint32_t acc[32];
-            tmem_ld32(taddr + c0, acc);
-            tmem_ld_wait();
-            uint8_t* prow = act + (c0 >> 6) * kPanelBytes + r * 128;
-            uint32_t mword = 0;
+          // TMEM loads are double-buffered: group cc+1 is in flight while group cc is processed
+          uint32_t acc[2][32];
+          tmem_ld32(taddr + half * 128, acc[0]);
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + c0 + 8 * j));
-              float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + c0 + 8 * j + 4));
-              float f0 = leaky(__uint_as_float(acc[8 * j + 0]) + b0.x, alpha);
-              float f1 = leaky(__uint_as_float(acc[8 * j + 1]) + b0.y, alpha);
-              float f2 = leaky(__uint_as_float(acc[8 * j + 2]) + b0.z, alpha);
-              float f3 = leaky(__uint_as_float(acc[8 * j + 3]) + b0.w, alpha);
-              float f4 = leaky(__uint_as_float(acc[8 * j + 4]) + b1.x, alpha);
-              float f5 = leaky(__uint_as_float(acc[8 * j + 5]) + b1.y, alpha);
-              float f6 = leaky(__uint_as_float(acc[8 * j + 6]) + b1.z, alpha);
-              float f7 = leaky(__uint_as_float(acc[8 * j + 7]) + b1.w, alpha);
-              uint4 pk = make_uint4(pack_bf16x2(f0, f1), pack_bf16x2(f2, f3), pack_bf16x2(f4, f5), pack_bf16x2(f6, f7));
-              const int chunk16 = ((c0 & 63) >> 3) + j;
-              *reinterpret_cast<uint4*>(prow + ((chunk16 ^ (r & 7)) << 4)) = pk;
-              if (kSave)
-                mword |= ((f0 > 0.f) | ((f1 > 0.f) << 1) | ((f2 > 0.f) << 2) | ((f3 > 0.f) << 3) | ((f4 > 0.f) << 4) |
-                        ((f5 > 0.f) << 5) | ((f6 > 0.f) << 6) | ((f7 > 0.f) << 7))
-                       << (8 * j);
-            }
+          for (int cc = 0; cc < 4; ++cc) {
+            const int c0 = half * 128 + cc * 32;
+            tmem_ld_wait();
+            if (cc + 1 < 4) tmem_ld32(taddr + c0 + 32, acc[(cc + 1) & 1]);
+            const uint32_t prow = act_u32 + (c0 >> 6) * kPanelBytes + r * 128;
+            const uint32_t mword = epi_group32<kSave>(acc[cc & 1], bias_u32 + c0 * 4, alpha, prow, r, (c0 & 63) >> 3);
             if (kSave) saved_mask[(l * 8 + (c0 >> 5)) * 128 + r] = mword;
           }
+          mbar_arrive(smem_u32(&bars->bias_empty[slot]));
           tc_fence_before();
           fence_proxy_async();
           mbar_arrive(smem_u32(&bars->act_ready[t]));
           if (kSave) {
-            named_bar_sync(bar_id, 128);
+            named_bar_sync(bar_id, kEpiThreadsPerTile);
             if (gtid == 0) {
               bulk_s2g(saved_tile + (size_t)saved_panel_h(l + 1) * kPanelBytes, act_u32, kActPanels * kPanelBytes);
               bulk_commit();
             }
           }
         } else {
-          // last layer: cols 0..127 = last hidden (LeakyReLU), col 128 = sigma (linear); rgb head on CUDA cores
-          float rr = __ldg(b_rgb + 0), gg = __ldg(b_rgb + 1), bb = __ldg(b_rgb + 2);
+          // last layer: cols 0..127 = last hidden (LeakyReLU), col 128 = sigma (linear); rgb head on CUDA cores.
+          // half 0 owns cols 0..63, half 1 owns cols 64..127 and sigma; partial rgb sums meet in the (dead) input panel.
+          float rr = 0.f, gg = 0.f, bb = 0.f;
 #pragma unroll 1
-          for (int c0 = 0; c0 < 128; c0 += 32) {
+          for (int cc = 0; cc < 2; ++cc) {
+            const int c0 = half * 64 + cc * 32;
             uint32_t acc[32];
             tmem_ld32(taddr + c0, acc);
             tmem_ld_wait();
-            uint8_t* prow = act + (c0 >> 6) * kPanelBytes + r * 128;
-            float f[32];
+            const uint32_t prow = act_u32 + (c0 >> 6) * kPanelBytes + r * 128;
+            uint32_t mword = 0;
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              f[i] = leaky(__uint_as_float(acc[i]) + __ldg(bias + c0 + i), alpha);
-              float4 w = __ldg(w_rgb + c0 + i);
-              rr = fmaf(f[i], w.x, rr);
-              gg = fmaf(f[i], w.y, gg);
-              bb = fmaf(f[i], w.z, bb);
-            }
-            if (kSave) {
-              uint32_t mword = 0;
+            for (int j = 0; j < 4; ++j) {
+              const float4 b0 = lds128f(bias_u32 + (c0 + 8 * j) * 4), b1 = lds128f(bias_u32 + (c0 + 8 * j + 4) * 4);
+              const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+              uint32_t pk[4];
 #pragma unroll
-              for (int i = 0; i < 32; ++i) mword |= (uint32_t)(f[i] > 0.f) << i;
-              saved_mask[(8 * 8 + (c0 >> 5)) * 128 + r] = mword;
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                uint4 pk = make_uint4(pack_bf16x2(f[8 * j], f[8 * j + 1]), pack_bf16x2(f[8 * j + 2], f[8 * j + 3]),
-                                      pack_bf16x2(f[8 * j + 4], f[8 * j + 5]), pack_bf16x2(f[8 * j + 6], f[8 * j + 7]));
-                const int chunk16 = ((c0 & 63) >> 3) + j;
-                *reinterpret_cast<uint4*>(prow + ((chunk16 ^ (r & 7)) << 4)) = pk;
+              for (int i = 0; i < 4; ++i) {
+                const int e = 8 * j + 2 * i;
+                float x0 = __uint_as_float(acc[e]) + bv[2 * i];
+                float x1 = __uint_as_float(acc[e + 1]) + bv[2 * i + 1];
+                x0 = fmaxf(x0, alpha * x0);
+                x1 = fmaxf(x1, alpha * x1);
+                const float4 w0 = __ldg(w_rgb + c0 + e), w1 = __ldg(w_rgb + c0 + e + 1);
+                rr = fmaf(x0, w0.x, fmaf(x1, w1.x, rr));
+                gg = fmaf(x0, w0.y, fmaf(x1, w1.y, gg));
+                bb = fmaf(x0, w0.z, fmaf(x1, w1.z, bb));
+                pk[i] = pack_bf16x2(x0, x1);
+                if (kSave) mword |= (~pk[i] >> (4 * j + i)) & (0x80008000u >> (4 * j + i));
               }
+              if (kSave) sts128(prow + (((((c0 & 63) >> 3) + j) ^ (r & 7)) << 4), make_uint4(pk[0], pk[1], pk[2], pk[3]));
             }
+            if (kSave) saved_mask[(8 * 8 + (c0 >> 5)) * 128 + r] = mword;
           }
-          uint32_t sg[16];
-          tmem_ld16(taddr + 128, sg);
-          tmem_ld_wait();
-          const float sigma = __uint_as_float(sg[0]) + __ldg(bias + 128);
-          if (row_ok) reinterpret_cast<float4*>(out4)[row] = make_float4(rr, gg, bb, sigma);
+          const uint32_t xch = inp_u32 + r * 16;                  // input panel is dead after this layer's MMAs
+          if (half == 1) {
+            uint32_t sg[16];
+            tmem_ld16(taddr + 128, sg);
+            tmem_ld_wait();
+            const float sigma = __uint_as_float(sg[0]) + lds32f(bias_u32 + 128 * 4);
+            sts128(xch, make_uint4(__float_as_uint(rr), __float_as_uint(gg), __float_as_uint(bb), __float_as_uint(sigma)));
+          }
+          mbar_arrive(smem_u32(&bars->bias_empty[slot]));
           tc_fence_before();
-          if (kSave) {
-            fence_proxy_async();
-            named_bar_sync(bar_id, 128);
-            if (gtid == 0) {
-              bulk_s2g(saved_tile + (size_t)kSavedPanelHL * kPanelBytes, act_u32, 2 * kPanelBytes);
-              bulk_commit();
-            }
+          if (kSave) fence_proxy_async();
+          named_bar_sync(bar_id, kEpiThreadsPerTile);
+          if (half == 0 && row_ok) {
+            const float4 o = lds128f(xch);
+            reinterpret_cast<float4*>(out4)[row] =
+                make_float4(rr + o.x + __ldg(b_rgb + 0), gg + o.y + __ldg(b_rgb + 1), bb + o.z + __ldg(b_rgb + 2), o.w);
           }
+          if (kSave && gtid == 0) {
+            bulk_s2g(saved_tile + (size_t)kSavedPanelHL * kPanelBytes, act_u32, 2 * kPanelBytes);
+            bulk_commit();
+          }
+          // the next pair's prologue overwrites the input panel: everyone must have read the exchange first
+          named_bar_sync(bar_id, kEpiThreadsPerTile);
         }
       }
     }
@@ -308,7 +394,7 @@ mlp_tc_fwd_kernel(const __grid_constant__ TcPlan plan, const uint8_t* __restrict
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 9) tmem_dealloc(tmem_base, 512);
+  if (warp == kWarpMma) tmem_dealloc(tmem_base, 512);
 }
 
 // ---- host side ----------------------------------------------------------------------------------------------------------------
@@ -326,12 +412,12 @@ int64_t mlp_tc_workspace_bytes(const NetGeom& g, int64_t m, int backward) {
   return tiles * (int64_t)kDzTileBytes + 1024;
 }
 
-int mlp_tc_fwd(const nerf_net_cfg* cfg, const NetGeom& g, const float* params, const void* packed, const float* xyz_enc,
-               const float* view_enc, int64_t m, float* out4, void* saved, void* workspace, cudaStream_t st) {
-  (void)params; (void)workspace;
+static int launch_fwd(const nerf_net_cfg* cfg, const NetGeom& g, const void* packed, const FwdInput& in, int64_t m,
+                      float* out4, void* saved, cudaStream_t st) {
   TcPlan plan;
-  if (!make_plan(g, &plan)) {
-    set_error("NERF_MODE_BF16 supports hidden=256, last_hidden=128, n_angles in {1,2}, xyz width <= 40, view width <= 24");
+  if (!make_plan(g, &plan) || cfg->leaky_alpha < 0.f || cfg->leaky_alpha > 1.f) {
+    set_error("NERF_MODE_BF16 supports hidden=256, last_hidden=128, n_angles in {1,2}, xyz width <= 40, view width <= 24, "
+              "0 <= leaky_relu_alpha <= 1");
     return NERF_E_UNSUPPORTED;
   }
   static bool attr_set = false;
@@ -343,13 +429,30 @@ int mlp_tc_fwd(const nerf_net_cfg* cfg, const NetGeom& g, const float* params, c
   int64_t n_pairs = ((m + kTileM - 1) / kTileM + 1) / 2;
   int grid = (int)(n_pairs < kNumSMs ? n_pairs : kNumSMs);
   if (saved)
-    mlp_tc_fwd_kernel<true><<<grid, kThreadsFwd, kSmemAlloc, st>>>(plan, (const uint8_t*)packed, xyz_enc, view_enc, g.dx,
-                                                                  g.dv, m, out4, (uint8_t*)saved, cfg->leaky_alpha);
+    mlp_tc_fwd_kernel<true><<<grid, kThreadsFwd, kSmemAlloc, st>>>(plan, (const uint8_t*)packed, in, m, out4,
+                                                                  (uint8_t*)saved, cfg->leaky_alpha);
   else
-    mlp_tc_fwd_kernel<false><<<grid, kThreadsFwd, kSmemAlloc, st>>>(plan, (const uint8_t*)packed, xyz_enc, view_enc, g.dx,
-                                                                   g.dv, m, out4, nullptr, cfg->leaky_alpha);
+    mlp_tc_fwd_kernel<false><<<grid, kThreadsFwd, kSmemAlloc, st>>>(plan, (const uint8_t*)packed, in, m, out4, nullptr,
+                                                                   cfg->leaky_alpha);
   NERF_CHECK_LAUNCH();
   return NERF_OK;
+}
+
+int mlp_tc_fwd(const nerf_net_cfg* cfg, const NetGeom& g, const float* params, const void* packed, const float* xyz_enc,
+               const float* view_enc, int64_t m, float* out4, void* saved, void* workspace, cudaStream_t st) {
+  (void)params; (void)workspace;
+  FwdInput in = {};
+  in.xyz_enc = xyz_enc; in.view_enc = view_enc; in.dx = g.dx; in.dv = g.dv;
+  in.Lx = cfg->n_pos_enc_xyz; in.Lv = cfg->n_pos_enc_view; in.ncomp = cfg->n_angles + 1; in.n_samples = 1;
+  return launch_fwd(cfg, g, packed, in, m, out4, saved, st);
+}
+
+int mlp_tc_fwd_rays(const nerf_net_cfg* cfg, const NetGeom& g, const void* packed, const float* origs4, const float* dirs4,
+                    const float* z, int64_t n_rays, int n_samples, float* out4, void* saved, cudaStream_t st) {
+  FwdInput in = {};
+  in.origs = (const float4*)origs4; in.dirs = (const float4*)dirs4; in.z = z; in.n_samples = n_samples;
+  in.dx = g.dx; in.dv = g.dv; in.Lx = cfg->n_pos_enc_xyz; in.Lv = cfg->n_pos_enc_view; in.ncomp = cfg->n_angles + 1;
+  return launch_fwd(cfg, g, packed, in, n_rays * n_samples, out4, saved, st);
 }
 
 }  // namespace nerf

@@ -16,7 +16,10 @@ constexpr int kStageBytes = 32768;                // one weight chunk: [<=256][6
 constexpr int kStages = 2;
 constexpr int kInpViewCol = 40;                   // first view-encoding column of the input panel
 constexpr int kMaxChunks = 40;
-constexpr int kThreadsFwd = 320;
+constexpr int kEpiWarps = 16;                     // 8 per tile: 4 TMEM lane quarters x 2 column halves
+constexpr int kEpiThreadsPerTile = 256;
+constexpr int kWarpProducer = 16, kWarpMma = 17;
+constexpr int kThreadsFwd = 18 * 32;
 // Saved activations of one 128-row tile (forward -> backward), all bf16 panels in the swizzled smem layout:
 //   panel 0            input panel (xyz | view encodings)
 //   panels 1 + 4(l-1)  h_l, l = 1..8 (4 panels each)
@@ -40,8 +43,10 @@ constexpr int kSmemAct = 0;                                          // [2 tiles
 constexpr int kSmemInp = kSmemAct + 2 * kActPanels * kPanelBytes;    // [2 tiles]
 constexpr int kSmemStage = kSmemInp + 2 * kPanelBytes;               // [kStages]
 constexpr int kSmemBar = kSmemStage + kStages * kStageBytes;
-constexpr int kSmemTotal = kSmemBar + 256;
-constexpr int kSmemAlloc = kSmemTotal + 1024;
+constexpr int kSmemBias = kSmemBar + 128;                            // [2 slots][256 fp32]: bias of the current layers
+constexpr int kSmemTotal = kSmemBias + 2 * 1024;
+// no alignment slack: the kernels check that the dynamic shared memory window is 1024-byte aligned and trap otherwise
+constexpr int kSmemAlloc = kSmemTotal;
 
 struct TcPlan {
   uint32_t chunk_off[kMaxChunks];    // byte offset of the chunk in the packed buffer

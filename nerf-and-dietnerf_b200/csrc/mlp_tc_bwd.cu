@@ -115,25 +115,34 @@ int bwd_pack_weights(const NetGeom& g, const float* params, uint8_t* packed_bwd,
 constexpr int kSmemCAct = 0;                                          // [2 tiles][4 panels]
 constexpr int kSmemCStage = 2 * kActPanels * kPanelBytes;             // [kStages] x 32 KB
 constexpr int kSmemCBar = kSmemCStage + kStages * kStageBytes;
-constexpr int kSmemCAlloc = kSmemCBar + 256 + 1024;
+constexpr int kSmemCConst = kSmemCBar + 128;          // fp32 [256] sigma-head kernel, then float4 [128] rgb-head kernel
+constexpr int kSmemCAlloc = kSmemCConst + 1024 + 2048;
 
 struct ChainBars {
   uint64_t full[kStages], empty[kStages], act_ready[2], acc_full[2];
   uint32_t tmem_base;
 };
 
-__device__ __forceinline__ void store_chunk16(uint8_t* panel_row, int r, int chunk16, uint4 v) {
-  *reinterpret_cast<uint4*>(panel_row + ((chunk16 ^ (r & 7)) << 4)) = v;
+// sign-mask layout written by the forward epilogue: element e of a 32-column group -> bit (e odd ? 31 : 15) - e/2
+__device__ __forceinline__ bool mask_bit(uint32_t mw, int e) { return (mw >> (((e & 1) ? 31 : 15) - (e >> 1))) & 1u; }
+
+__device__ __forceinline__ void store_chunk16(uint32_t panel_row_addr, int r, int chunk16, uint4 v) {
+  sts128(panel_row_addr + ((chunk16 ^ (r & 7)) << 4), v);
 }
 
 __global__ void __launch_bounds__(kThreadsFwd, 1)
 mlp_tc_bwd_chain_kernel(const __grid_constant__ BwdPlan plan, const uint8_t* __restrict__ packed,
                         const uint8_t* __restrict__ saved, const float* __restrict__ d_out4, int64_t M,
                         uint8_t* __restrict__ dz_ws, float* __restrict__ d_xyz_enc, int dx, float alpha) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t sbase = smem_u32(smem);
+  if ((sbase & 1023u) != 0u) __trap();
   ChainBars* bars = reinterpret_cast<ChainBars*>(smem + kSmemCBar);
+  // L1 is ~3 KB next to 200 KB of shared memory: the head kernels the epilogue needs live in shared memory
+  for (int i = threadIdx.x; i < 256 + 512; i += blockDim.x)
+    reinterpret_cast<float*>(smem + kSmemCConst)[i] =
+        i < 256 ? reinterpret_cast<const float*>(packed + plan.w_sigma_off)[i]
+                : reinterpret_cast<const float*>(packed + plan.w_rgb_off)[i - 256];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const bool need_dx = d_xyz_enc != nullptr;
   const int64_t n_tiles = (M + kTileM - 1) / kTileM;
@@ -144,33 +153,35 @@ mlp_tc_bwd_chain_kernel(const __grid_constant__ BwdPlan plan, const uint8_t* __r
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kStages; ++s) { mbar_init(smem_u32(&bars->full[s]), 1); mbar_init(smem_u32(&bars->empty[s]), 1); }
-    for (int t = 0; t < 2; ++t) { mbar_init(smem_u32(&bars->act_ready[t]), 128); mbar_init(smem_u32(&bars->acc_full[t]), 1); }
+    for (int t = 0; t < 2; ++t) { mbar_init(smem_u32(&bars->act_ready[t]), kEpiThreadsPerTile); mbar_init(smem_u32(&bars->acc_full[t]), 1); }
     fence_barrier_init();
   }
-  if (warp == 9) tmem_alloc(smem_u32(&bars->tmem_base), 512);
+  if (warp == kWarpMma) tmem_alloc(smem_u32(&bars->tmem_base), 512);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = bars->tmem_base;
 
-  if (warp == 8) {
+  if (warp == kWarpProducer) {
     if (lane == 0) {
       uint32_t g = 0;
       for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
         for (int s = 0; s < plan.n_steps; ++s) {
           if (!need_dx && plan.step_kind[s] != STEP_MASK) continue;
-          for (int ci = 0; ci < plan.step_nch[s]; ++ci, ++g) {
-            const int c = plan.step_first[s] + ci;
-            const uint32_t st = g % kStages, ph = (g / kStages) & 1u;
-            mbar_wait(smem_u32(&bars->empty[st]), ph ^ 1u);
-            mbar_arrive_expect_tx(smem_u32(&bars->full[st]), plan.chunk_bytes[c]);
-            bulk_g2s(sbase + kSmemCStage + st * kStageBytes, packed + plan.chunk_off[c], plan.chunk_bytes[c],
-                     smem_u32(&bars->full[st]));
+          for (int t = 0; t < 2; ++t) {      // staggered: every step's chunks are streamed once per tile
+            for (int ci = 0; ci < plan.step_nch[s]; ++ci, ++g) {
+              const int c = plan.step_first[s] + ci;
+              const uint32_t st = g % kStages, ph = (g / kStages) & 1u;
+              mbar_wait(smem_u32(&bars->empty[st]), ph ^ 1u);
+              mbar_arrive_expect_tx(smem_u32(&bars->full[st]), plan.chunk_bytes[c]);
+              bulk_g2s(sbase + kSmemCStage + st * kStageBytes, packed + plan.chunk_off[c], plan.chunk_bytes[c],
+                       smem_u32(&bars->full[st]));
+            }
           }
         }
       }
     }
-  } else if (warp == 9) {
+  } else if (warp == kWarpMma) {
     if (lane == 0) {
       uint32_t g = 0, act_cnt = 0;
       for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
@@ -178,38 +189,36 @@ mlp_tc_bwd_chain_kernel(const __grid_constant__ BwdPlan plan, const uint8_t* __r
           if (!need_dx && plan.step_kind[s] != STEP_MASK) continue;
           const uint32_t idesc = make_idesc(plan.step_n[s]);
           const int nch = plan.step_nch[s];
-          for (int ci = 0; ci < nch; ++ci, ++g) {
-            const uint32_t st = g % kStages, ph = (g / kStages) & 1u;
-            mbar_wait(smem_u32(&bars->full[st]), ph);
-            const uint32_t b_addr = sbase + kSmemCStage + st * kStageBytes;
-#pragma unroll
-            for (int t = 0; t < 2; ++t) {
-              if (ci == 0) mbar_wait(smem_u32(&bars->act_ready[t]), act_cnt & 1u);
+          for (int t = 0; t < 2; ++t) {
+            mbar_wait(smem_u32(&bars->act_ready[t]), act_cnt & 1u);
+            const uint32_t d_tmem = tmem_base + (uint32_t)t * 256u;
+            for (int ci = 0; ci < nch; ++ci, ++g) {
+              const uint32_t st = g % kStages, ph = (g / kStages) & 1u;
+              mbar_wait(smem_u32(&bars->full[st]), ph);
               tc_fence_after();
+              const uint32_t b_addr = sbase + kSmemCStage + st * kStageBytes;
               const uint32_t a_addr = sbase + kSmemCAct + (t * kActPanels + ci) * kPanelBytes;
-              const uint32_t d_tmem = tmem_base + (uint32_t)t * 256u;
 #pragma unroll
               for (int k = 0; k < 4; ++k)
                 umma_bf16(d_tmem, make_desc_kmajor(a_addr + k * 32), make_desc_kmajor(b_addr + k * 32), idesc,
                           (ci > 0 || k > 0) ? 1u : 0u);
-              if (ci == nch - 1) umma_commit(smem_u32(&bars->acc_full[t]));
+              umma_commit(smem_u32(&bars->empty[st]));
             }
-            umma_commit(smem_u32(&bars->empty[st]));
+            umma_commit(smem_u32(&bars->acc_full[t]));
           }
           ++act_cnt;
         }
       }
     }
   } else {
-    const int t = warp >> 2, q = warp & 3;
+    // 16 epilogue warps: tile t = warp / 8, TMEM lane quarter q = warp % 4, column half = (warp / 4) % 2
+    const int t = warp >> 3, q = warp & 3, half = (warp >> 2) & 1;
     const int r = q * 32 + lane;
-    const int gtid = threadIdx.x & 127;
+    const int gtid = threadIdx.x & (kEpiThreadsPerTile - 1);
     const int bar_id = 1 + t;
-    uint8_t* act = smem + kSmemCAct + t * kActPanels * kPanelBytes;
     const uint32_t act_u32 = sbase + kSmemCAct + t * kActPanels * kPanelBytes;
     const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)t * 256u;
-    const float* w_sigma = reinterpret_cast<const float*>(packed + plan.w_sigma_off);
-    const float4* w_rgb = reinterpret_cast<const float4*>(packed + plan.w_rgb_off);
+    const uint32_t w_sigma_u32 = sbase + kSmemCConst, w_rgb_u32 = sbase + kSmemCConst + 1024;
     uint32_t acc_cnt = 0;
     for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
       const int64_t tile = pair * 2 + t;
@@ -218,75 +227,83 @@ mlp_tc_bwd_chain_kernel(const __grid_constant__ BwdPlan plan, const uint8_t* __r
       const uint8_t* saved_tile = saved + (size_t)tile * kSavedTileBytes;
       const uint32_t* saved_mask = reinterpret_cast<const uint32_t*>(saved_tile + (size_t)kSavedPanels * kPanelBytes);
       uint8_t* dz_tile = dz_ws + (size_t)tile * kDzTileBytes;
-      // ---- prologue: dZ_L (panels 0,1), sigma-gradient panel (2), d_out panel (3)
-      if (gtid == 0) bulk_wait_read0();
-      named_bar_sync(bar_id, 128);
+      // ---- prologue: half 0 -> dZ_L cols 0..63 (panel 0) + sigma-gradient panel (2);
+      //                half 1 -> dZ_L cols 64..127 (panel 1) + d_out panel (3)
       float4 d4 = make_float4(0.f, 0.f, 0.f, 0.f);
       if (row_ok) d4 = __ldg(reinterpret_cast<const float4*>(d_out4) + row);
+      uint32_t mwl[2];
+#pragma unroll
+      for (int w = 0; w < 2; ++w) mwl[w] = __ldg(saved_mask + (8 * 8 + half * 2 + w) * 128 + r);
+      if (gtid == 0) bulk_wait_read0();
+      named_bar_sync(bar_id, kEpiThreadsPerTile);
       {
-        uint32_t mw[4];
 #pragma unroll
-        for (int w = 0; w < 4; ++w) mw[w] = __ldg(saved_mask + (8 * 8 + w) * 128 + r);
-#pragma unroll
-        for (int jg = 0; jg < 16; ++jg) {
+        for (int jg = 0; jg < 8; ++jg) {
           float v[8];
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
-            const int j = jg * 8 + i;
-            float4 w = __ldg(w_rgb + j);
+            const int jl = jg * 8 + i;                   // column inside this half
+            const float4 w = lds128f(w_rgb_u32 + (half * 64 + jl) * 16);
             float dh = d4.x * w.x + d4.y * w.y + d4.z * w.z;
-            v[i] = ((mw[j >> 5] >> (j & 31)) & 1u) ? dh : alpha * dh;
+            v[i] = mask_bit(mwl[jl >> 5], jl & 31) ? dh : alpha * dh;
           }
           uint4 pk = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]),
                                 pack_bf16x2(v[6], v[7]));
-          store_chunk16(act + (jg >> 3) * kPanelBytes + r * 128, r, jg & 7, pk);
+          store_chunk16(act_u32 + half * kPanelBytes + r * 128, r, jg, pk);
         }
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
-          uint4 sg = make_uint4(c == 0 ? pack_bf16x2(d4.w, 0.f) : 0u, 0u, 0u, 0u);
-          uint4 od = make_uint4(c == 0 ? pack_bf16x2(d4.x, d4.y) : 0u, c == 0 ? pack_bf16x2(d4.z, d4.w) : 0u, 0u, 0u);
-          store_chunk16(act + 2 * kPanelBytes + r * 128, r, c, sg);
-          store_chunk16(act + 3 * kPanelBytes + r * 128, r, c, od);
+          uint4 v;
+          if (half == 0) v = make_uint4(c == 0 ? pack_bf16x2(d4.w, 0.f) : 0u, 0u, 0u, 0u);
+          else v = make_uint4(c == 0 ? pack_bf16x2(d4.x, d4.y) : 0u, c == 0 ? pack_bf16x2(d4.z, d4.w) : 0u, 0u, 0u);
+          store_chunk16(act_u32 + (2 + half) * kPanelBytes + r * 128, r, c, v);
         }
       }
       fence_proxy_async();
       mbar_arrive(smem_u32(&bars->act_ready[t]));
-      named_bar_sync(bar_id, 128);
+      named_bar_sync(bar_id, kEpiThreadsPerTile);
       if (gtid == 0) {
         bulk_s2g(dz_tile + (size_t)kDzPanelL * kPanelBytes, act_u32, 3 * kPanelBytes);
         bulk_s2g(dz_tile + (size_t)kDzPanelOut * kPanelBytes, act_u32 + 3 * kPanelBytes, kPanelBytes);
         bulk_commit();
       }
-      float xs[40];
+      float xs[32];                                      // d(xyz encoding): half 0 -> cols 0..31, half 1 -> cols 32..39
 #pragma unroll
-      for (int i = 0; i < 40; ++i) xs[i] = 0.f;
+      for (int i = 0; i < 32; ++i) xs[i] = 0.f;
 
       for (int s = 0; s < plan.n_steps; ++s) {
         const int kind = plan.step_kind[s];
         if (!need_dx && kind != STEP_MASK) continue;
+        const int l = plan.step_layer[s];
+        // the LeakyReLU' masks do not depend on the accumulator: fetch them (L2 latency) before waiting for the MMAs
+        uint32_t mw4[4] = {0u, 0u, 0u, 0u};
+        if (kind == STEP_MASK) {
+#pragma unroll
+          for (int cc = 0; cc < 4; ++cc) mw4[cc] = __ldg(saved_mask + ((l - 1) * 8 + half * 4 + cc) * 128 + r);
+        }
         mbar_wait(smem_u32(&bars->acc_full[t]), acc_cnt & 1u);
         ++acc_cnt;
         tc_fence_after();
         if (kind == STEP_MASK) {
-          const int l = plan.step_layer[s];
           if (gtid == 0) bulk_wait_read0();
-          named_bar_sync(bar_id, 128);
-          const uint32_t* mk = saved_mask + ((l - 1) * 8) * 128 + r;
-#pragma unroll 1
-          for (int c0 = 0; c0 < 256; c0 += 32) {
-            uint32_t acc[32];
-            tmem_ld32(taddr + c0, acc);
+          named_bar_sync(bar_id, kEpiThreadsPerTile);
+          uint32_t acc[2][32];
+          tmem_ld32(taddr + half * 128, acc[0]);
+#pragma unroll
+          for (int cc = 0; cc < 4; ++cc) {
+            const int c0 = half * 128 + cc * 32;
             tmem_ld_wait();
-            const uint32_t mw = __ldg(mk + (c0 >> 5) * 128);
-            uint8_t* prow = act + (c0 >> 6) * kPanelBytes + r * 128;
+            if (cc + 1 < 4) tmem_ld32(taddr + c0 + 32, acc[(cc + 1) & 1]);
+            const uint32_t mw = mw4[cc];
+            const uint32_t prow = act_u32 + (c0 >> 6) * kPanelBytes + r * 128;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               float v[8];
 #pragma unroll
               for (int i = 0; i < 8; ++i) {
-                float a = __uint_as_float(acc[8 * j + i]);
-                if (l == 8) a = fmaf(d4.w, __ldg(w_sigma + c0 + 8 * j + i), a);
-                v[i] = ((mw >> (8 * j + i)) & 1u) ? a : alpha * a;
+                float a = __uint_as_float(acc[cc & 1][8 * j + i]);
+                if (l == 8) a = fmaf(d4.w, lds32f(w_sigma_u32 + (c0 + 8 * j + i) * 4), a);
+                v[i] = mask_bit(mw, 8 * j + i) ? a : alpha * a;
               }
               uint4 pk = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]),
                                     pack_bf16x2(v[6], v[7]));
@@ -296,27 +313,33 @@ mlp_tc_bwd_chain_kernel(const __grid_constant__ BwdPlan plan, const uint8_t* __r
           tc_fence_before();
           fence_proxy_async();
           if (s != last_step) mbar_arrive(smem_u32(&bars->act_ready[t]));
-          named_bar_sync(bar_id, 128);
+          named_bar_sync(bar_id, kEpiThreadsPerTile);
           if (gtid == 0) {
             bulk_s2g(dz_tile + (size_t)dz_panel(l) * kPanelBytes, act_u32, kActPanels * kPanelBytes);
             bulk_commit();
           }
         } else {
-          uint32_t a0[32], a1[16];
-          tmem_ld32(taddr, a0);
-          tmem_ld16(taddr + 32, a1);
-          tmem_ld_wait();
+          if (half == 0) {
+            uint32_t a0[32];
+            tmem_ld32(taddr, a0);
+            tmem_ld_wait();
 #pragma unroll
-          for (int i = 0; i < 32; ++i) xs[i] += __uint_as_float(a0[i]);
+            for (int i = 0; i < 32; ++i) xs[i] += __uint_as_float(a0[i]);
+          } else {
+            uint32_t a1[16];
+            tmem_ld16(taddr + 32, a1);
+            tmem_ld_wait();
 #pragma unroll
-          for (int i = 0; i < 8; ++i) xs[32 + i] += __uint_as_float(a1[i]);
+            for (int i = 0; i < 8; ++i) xs[i] += __uint_as_float(a1[i]);
+          }
           tc_fence_before();
           if (kind == STEP_XSTASH) {
             mbar_arrive(smem_u32(&bars->act_ready[t]));
           } else if (row_ok) {
-            float* dst = d_xyz_enc + row * dx;
+            float* dst = d_xyz_enc + row * dx + half * 32;
+            const int lim = dx - half * 32;
 #pragma unroll
-            for (int i = 0; i < 40; ++i) if (i < dx) dst[i] = xs[i];
+            for (int i = 0; i < 32; ++i) if (i < lim && (half == 0 || i < 8)) dst[i] = xs[i];
           }
         }
       }
@@ -325,7 +348,7 @@ mlp_tc_bwd_chain_kernel(const __grid_constant__ BwdPlan plan, const uint8_t* __r
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 9) tmem_dealloc(tmem_base, 512);
+  if (warp == kWarpMma) tmem_dealloc(tmem_base, 512);
 }
 
 // =====================================================================================================================
