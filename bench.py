@@ -84,7 +84,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                          "--format=csv,noheader,nounits", "-lms", "20"], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except OSError:
@@ -256,7 +256,7 @@ def main():
 
     @contextlib.contextmanager
     def hook(name):
-        if name in ("nerf_mlp_fwd", "nerf_mlp_bwd", "nerf_composite_fwd", "nerf_composite_bwd"):
+        if name in ("nerf_mlp_fwd", "nerf_mlp_fwd_rays", "nerf_mlp_bwd", "nerf_composite_fwd", "nerf_composite_bwd"):
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record()
             yield
@@ -303,7 +303,7 @@ def main():
                     "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf, "traffic": None,
                     "peak_source": peak_src,
                     "fwd_kernel": {"kernel": "mlp_tc_fwd_kernel<save>",
-                                   "achieved": fwd_flops / (call_ms.get("nerf_mlp_fwd", float("nan")) * 1e-3) / 1e12},
+                                   "achieved": fwd_flops / (call_ms.get("nerf_mlp_fwd_rays", call_ms.get("nerf_mlp_fwd", float("nan"))) * 1e-3) / 1e12},
                     "step_tensor_frac": FLOP_PER_RAY_TRAIN * value / 1e12 / peak_tf,
                     "avg_call_ms": call_ms, "calls_per_step": call_n}
         if args.mode != "bf16":

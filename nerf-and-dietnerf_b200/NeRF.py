@@ -20,6 +20,7 @@ from .ConfigurationKeys import (HIDDEN_LAYER_DIM, LAST_HIDDEN_LAYER_DIM, LEAKY_R
                                 N_RENDER_SAMPLES_COARSE, N_RENDER_SAMPLES_FINE)
 from .network import NerfMLP
 from .optimizers import Adam
+from .parallel import allreduce_sum_, shard_bounds
 from .UtilsCV import get_rays_directions, get_z_vals_from_prob_dist_func, get_z_values, rng
 from .UtilsNeuralRadianceField import get_psnr, split_to_batches
 from . import UtilsNeuralRadianceField as _unrf
@@ -363,10 +364,7 @@ class NeRF:
         """
         rays_orig, rays_dirs, real_rgb = data
         n_total = rays_orig.shape[0]
-        lo, hi = 0, n_total
-        if self.world_size > 1:
-            per = (n_total + self.world_size - 1) // self.world_size
-            lo, hi = min(n_total, self.rank * per), min(n_total, (self.rank + 1) * per)
+        lo, hi = shard_bounds(n_total, self.world_size, self.rank)
         to_dev = lambda t: t[lo:hi].to(device=self.device, dtype=torch.float32, non_blocking=True).contiguous()
         return self.train_step_local(to_dev(rays_orig), to_dev(rays_dirs), to_dev(real_rgb), n_total, lo)
 
@@ -381,8 +379,7 @@ class NeRF:
         self.forward_backward(rays_orig, rays_dirs, real_rgb, n_total_rays=n_total_rays, ray_offset=ray_offset)
         g = self._grad_buffer()
         if self.world_size > 1:
-            import torch.distributed as dist
-            dist.all_reduce(g, op=dist.ReduceOp.SUM, group=self._process_group)
+            allreduce_sum_(g, self._process_group)
         self.apply_gradients(g)
         self.step_counter += 1
         return self._metrics(g[-2:], n_total_rays)

@@ -1,0 +1,83 @@
+"""World-size-2 gloo test of the N>1 path's host logic (no GPU): contiguous ray shards, loss normalised by the GLOBAL
+ray count, one all-reduce(sum) of the flat gradient buffer == the single-process gradient; and the Philox stream keyed
+by the global ray index gives every rank the draws the single-process run uses."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from conftest import ROOT
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, n, out_dir):
+    import importlib
+    import sys
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.set_num_threads(2)
+    from helpers import FAR, NEAR, make_params, oracle_cfg, random_rays
+    from oracle import nerf_oracle as O
+    parallel = importlib.import_module("nerf-and-dietnerf_b200.parallel")
+    cfg = oracle_cfg()
+    pc, pf = make_params(cfg, 1, 4.0), make_params(cfg, 2, 4.0)
+    o, d = random_rays(n, 0)
+    y = torch.rand(n, 3, generator=torch.Generator().manual_seed(0))
+    lo, hi = parallel.shard_bounds(n, world, rank)
+    jit = O.stratified_jitter(3, 0, hi - lo, 16, ray_offset=lo)
+    u = O.importance_uniforms(3, 0, hi - lo, 16, ray_offset=lo)
+    pcs, pfs = pc.clone().requires_grad_(True), pf.clone().requires_grad_(True)
+    out = O.train_losses(pcs, pfs, cfg, NEAR, FAR, o[lo:hi], d[lo:hi], y[lo:hi], 16, 16, jit, u)
+    # what NeRF.train_step_local does: squared errors summed over the shard, divided by the GLOBAL element count
+    sq_c = ((out["rgb_c"] - y[lo:hi]) ** 2).sum()
+    sq_f = ((out["rgb_f"] - y[lo:hi]) ** 2).sum()
+    ((sq_c + sq_f) / (3.0 * n)).backward()
+    flat = torch.cat([pcs.grad, pfs.grad, sq_c.detach().reshape(1), sq_f.detach().reshape(1)])
+    parallel.allreduce_sum_(flat)
+    if rank == 0:
+        np.save(os.path.join(out_dir, "flat.npy"), flat.numpy())
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_two_rank_gradient_equals_single_process(tmp_path):
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from helpers import FAR, NEAR, make_params, oracle_cfg, random_rays
+    from oracle import nerf_oracle as O
+    n = 24                                    # 2 ranks x 12 rays
+    mp.spawn(_worker, args=(2, _free_port(), n, str(tmp_path)), nprocs=2, join=True)
+    flat = torch.from_numpy(np.load(tmp_path / "flat.npy"))
+    cfg = oracle_cfg()
+    pc, pf = make_params(cfg, 1, 4.0), make_params(cfg, 2, 4.0)
+    o, d = random_rays(n, 0)
+    y = torch.rand(n, 3, generator=torch.Generator().manual_seed(0))
+    jit, u = O.stratified_jitter(3, 0, n, 16), O.importance_uniforms(3, 0, n, 16)
+    metrics, gc, gf, out = O.train_step(pc, pf, cfg, NEAR, FAR, o, d, y, 16, 16, jit, u)
+    np_ = cfg.n_params
+    assert ((flat[:np_] - gc).norm() / gc.norm()).item() < 1e-5
+    assert ((flat[np_:2 * np_] - gf).norm() / gf.norm()).item() < 1e-5
+    loss = (flat[-2] + flat[-1]) / (3.0 * n)
+    assert abs(loss.item() - metrics["loss"].item()) < 1e-6
+
+
+def test_shard_bounds():
+    import importlib
+    parallel = importlib.import_module("nerf-and-dietnerf_b200.parallel")
+    assert [parallel.shard_bounds(4096, 8, r) for r in (0, 7)] == [(0, 512), (3584, 4096)]
+    spans = [parallel.shard_bounds(10, 4, r) for r in range(4)]
+    assert spans == [(0, 3), (3, 6), (6, 9), (9, 10)]
+    assert [parallel.shard_bounds(2, 4, r) for r in range(4)] == [(0, 1), (1, 2), (2, 2), (2, 2)]   # empty shards
+    assert parallel.shard_bounds(7, 1, 0) == (0, 7)
