@@ -173,13 +173,17 @@ mlp_tc_fwd_kernel(const __grid_constant__ TcPlan plan, const uint8_t* __restrict
           mbar_arrive_expect_tx(smem_u32(&bars->bias_full[slot]), 1024);
           bulk_g2s(sbase + kSmemBias + slot * 1024, packed + plan.bias_off + l * 1024, 1024, smem_u32(&bars->bias_full[slot]));
           for (int t = 0; t < 2; ++t) {
-            for (int ci = 0; ci < plan.layer_nchunks[l]; ++ci, ++g) {
+            for (int ci = 0; ci < plan.layer_nchunks[l]; ++ci) {
               const int c = plan.layer_first[l] + ci;
-              const uint32_t s = g % kStages, ph = (g / kStages) & 1u;
-              mbar_wait(smem_u32(&bars->empty[s]), ph ^ 1u);
-              mbar_arrive_expect_tx(smem_u32(&bars->full[s]), plan.chunk_bytes[c]);
-              bulk_g2s(sbase + kSmemStage + s * kStageBytes, packed + plan.chunk_off[c], plan.chunk_bytes[c],
-                       smem_u32(&bars->full[s]));
+              // a chunk [N][64] travels as row halves of <= 128 rows (16 KB): finer ring, more loads in flight
+              for (uint32_t off = 0; off < plan.chunk_bytes[c]; off += kStageBytes, ++g) {
+                const uint32_t bytes = min(plan.chunk_bytes[c] - off, (uint32_t)kStageBytes);
+                const uint32_t s = g % kStages, ph = (g / kStages) & 1u;
+                mbar_wait(smem_u32(&bars->empty[s]), ph ^ 1u);
+                mbar_arrive_expect_tx(smem_u32(&bars->full[s]), bytes);
+                bulk_g2s(sbase + kSmemStage + s * kStageBytes, packed + plan.chunk_off[c] + off, bytes,
+                         smem_u32(&bars->full[s]));
+              }
             }
           }
         }
@@ -191,25 +195,27 @@ mlp_tc_fwd_kernel(const __grid_constant__ TcPlan plan, const uint8_t* __restrict
       uint32_t g = 0, act_cnt = 0;
       for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
         for (int l = 0; l < plan.n_layers; ++l) {
-          const uint32_t idesc = make_idesc(plan.layer_n[l]);
-          const int first = plan.layer_first[l], nch = plan.layer_nchunks[l];
+          const int first = plan.layer_first[l], nch = plan.layer_nchunks[l], n_total = plan.layer_n[l];
           for (int t = 0; t < 2; ++t) {
             mbar_wait(smem_u32(&bars->act_ready[t]), act_cnt & 1u);
             const uint32_t d_tmem = tmem_base + (uint32_t)t * 256u;
-            for (int ci = 0; ci < nch; ++ci, ++g) {
+            for (int ci = 0; ci < nch; ++ci) {
               const int c = first + ci;
-              const uint32_t s = g % kStages, ph = (g / kStages) & 1u;
-              mbar_wait(smem_u32(&bars->full[s]), ph);
-              tc_fence_after();
-              const uint32_t b_addr = sbase + kSmemStage + s * kStageBytes;
               const int src = plan.a_src[c];
               const uint32_t a_addr = (src < 4) ? sbase + kSmemAct + (t * kActPanels + src) * kPanelBytes
                                                 : sbase + kSmemInp + t * kPanelBytes;
+              for (int n0 = 0; n0 < n_total; n0 += kStageRows, ++g) {          // row halves of the chunk: N = 128 (or the rest)
+                const uint32_t idesc = make_idesc(min(kStageRows, n_total - n0));
+                const uint32_t s = g % kStages, ph = (g / kStages) & 1u;
+                mbar_wait(smem_u32(&bars->full[s]), ph);
+                tc_fence_after();
+                const uint32_t b_addr = sbase + kSmemStage + s * kStageBytes;
 #pragma unroll
-              for (int k = 0; k < 4; ++k)
-                umma_bf16(d_tmem, make_desc_kmajor(a_addr + k * 32), make_desc_kmajor(b_addr + k * 32), idesc,
-                          (ci > 0 || k > 0) ? 1u : 0u);
-              umma_commit(smem_u32(&bars->empty[s]));
+                for (int k = 0; k < 4; ++k)
+                  umma_bf16(d_tmem + (uint32_t)n0, make_desc_kmajor(a_addr + k * 32), make_desc_kmajor(b_addr + k * 32),
+                            idesc, (ci > 0 || k > 0) ? 1u : 0u);
+                umma_commit(smem_u32(&bars->empty[s]));
+              }
             }
             umma_commit(smem_u32(&bars->acc_full[t]));
           }

@@ -114,12 +114,13 @@ int bwd_pack_weights(const NetGeom& g, const float* params, uint8_t* packed_bwd,
 // =====================================================================================================================
 constexpr int kSmemCAct = 0;                                          // [2 tiles][4 panels]
 constexpr int kSmemCStage = 2 * kActPanels * kPanelBytes;             // [kStages] x 32 KB
-constexpr int kSmemCBar = kSmemCStage + kStages * kStageBytes;
-constexpr int kSmemCConst = kSmemCBar + 128;          // fp32 [256] sigma-head kernel, then float4 [128] rgb-head kernel
-constexpr int kSmemCAlloc = kSmemCConst + 1024 + 2048;
+constexpr int kSmemCBar = kSmemCStage + kChainStages * kStageBytes;
+constexpr int kSmemCConst = kSmemCBar + 256;          // fp32 [256] sigma-head kernel, then fp32 [128][3] rgb-head kernel
+constexpr int kSmemCAlloc = kSmemCConst + 1024 + 1536;
+static_assert(kSmemCAlloc <= 232448, "chain kernel exceeds the 227 KB shared-memory limit");
 
 struct ChainBars {
-  uint64_t full[kStages], empty[kStages], act_ready[2], acc_full[2];
+  uint64_t full[kChainStages], empty[kChainStages], act_ready[2], acc_full[2];
   uint32_t tmem_base;
 };
 
@@ -139,10 +140,12 @@ mlp_tc_bwd_chain_kernel(const __grid_constant__ BwdPlan plan, const uint8_t* __r
   if ((sbase & 1023u) != 0u) __trap();
   ChainBars* bars = reinterpret_cast<ChainBars*>(smem + kSmemCBar);
   // L1 is ~3 KB next to 200 KB of shared memory: the head kernels the epilogue needs live in shared memory
-  for (int i = threadIdx.x; i < 256 + 512; i += blockDim.x)
+  for (int i = threadIdx.x; i < 256 + 384; i += blockDim.x) {
+    const int j = i - 256;                              // rgb-head kernel is packed as float4 (w_r, w_g, w_b, 0) per unit
     reinterpret_cast<float*>(smem + kSmemCConst)[i] =
         i < 256 ? reinterpret_cast<const float*>(packed + plan.w_sigma_off)[i]
-                : reinterpret_cast<const float*>(packed + plan.w_rgb_off)[i - 256];
+                : reinterpret_cast<const float*>(packed + plan.w_rgb_off)[(j / 3) * 4 + (j % 3)];
+  }
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const bool need_dx = d_xyz_enc != nullptr;
   const int64_t n_tiles = (M + kTileM - 1) / kTileM;
@@ -152,7 +155,7 @@ mlp_tc_bwd_chain_kernel(const __grid_constant__ BwdPlan plan, const uint8_t* __r
     if (need_dx || plan.step_kind[s] == STEP_MASK) last_step = s;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kStages; ++s) { mbar_init(smem_u32(&bars->full[s]), 1); mbar_init(smem_u32(&bars->empty[s]), 1); }
+    for (int s = 0; s < kChainStages; ++s) { mbar_init(smem_u32(&bars->full[s]), 1); mbar_init(smem_u32(&bars->empty[s]), 1); }
     for (int t = 0; t < 2; ++t) { mbar_init(smem_u32(&bars->act_ready[t]), kEpiThreadsPerTile); mbar_init(smem_u32(&bars->acc_full[t]), 1); }
     fence_barrier_init();
   }
@@ -169,13 +172,16 @@ mlp_tc_bwd_chain_kernel(const __grid_constant__ BwdPlan plan, const uint8_t* __r
         for (int s = 0; s < plan.n_steps; ++s) {
           if (!need_dx && plan.step_kind[s] != STEP_MASK) continue;
           for (int t = 0; t < 2; ++t) {      // staggered: every step's chunks are streamed once per tile
-            for (int ci = 0; ci < plan.step_nch[s]; ++ci, ++g) {
+            for (int ci = 0; ci < plan.step_nch[s]; ++ci) {
               const int c = plan.step_first[s] + ci;
-              const uint32_t st = g % kStages, ph = (g / kStages) & 1u;
-              mbar_wait(smem_u32(&bars->empty[st]), ph ^ 1u);
-              mbar_arrive_expect_tx(smem_u32(&bars->full[st]), plan.chunk_bytes[c]);
-              bulk_g2s(sbase + kSmemCStage + st * kStageBytes, packed + plan.chunk_off[c], plan.chunk_bytes[c],
-                       smem_u32(&bars->full[st]));
+              for (uint32_t off = 0; off < plan.chunk_bytes[c]; off += kStageBytes, ++g) {   // row halves (<= 128 rows)
+                const uint32_t bytes = min(plan.chunk_bytes[c] - off, (uint32_t)kStageBytes);
+                const uint32_t st = g % kChainStages, ph = (g / kChainStages) & 1u;
+                mbar_wait(smem_u32(&bars->empty[st]), ph ^ 1u);
+                mbar_arrive_expect_tx(smem_u32(&bars->full[st]), bytes);
+                bulk_g2s(sbase + kSmemCStage + st * kStageBytes, packed + plan.chunk_off[c] + off, bytes,
+                         smem_u32(&bars->full[st]));
+              }
             }
           }
         }
@@ -187,22 +193,24 @@ mlp_tc_bwd_chain_kernel(const __grid_constant__ BwdPlan plan, const uint8_t* __r
       for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
         for (int s = 0; s < plan.n_steps; ++s) {
           if (!need_dx && plan.step_kind[s] != STEP_MASK) continue;
-          const uint32_t idesc = make_idesc(plan.step_n[s]);
-          const int nch = plan.step_nch[s];
+          const int nch = plan.step_nch[s], n_total = plan.step_n[s];
           for (int t = 0; t < 2; ++t) {
             mbar_wait(smem_u32(&bars->act_ready[t]), act_cnt & 1u);
             const uint32_t d_tmem = tmem_base + (uint32_t)t * 256u;
-            for (int ci = 0; ci < nch; ++ci, ++g) {
-              const uint32_t st = g % kStages, ph = (g / kStages) & 1u;
-              mbar_wait(smem_u32(&bars->full[st]), ph);
-              tc_fence_after();
-              const uint32_t b_addr = sbase + kSmemCStage + st * kStageBytes;
+            for (int ci = 0; ci < nch; ++ci) {
               const uint32_t a_addr = sbase + kSmemCAct + (t * kActPanels + ci) * kPanelBytes;
+              for (int n0 = 0; n0 < n_total; n0 += kStageRows, ++g) {
+                const uint32_t idesc = make_idesc(min(kStageRows, n_total - n0));
+                const uint32_t st = g % kChainStages, ph = (g / kChainStages) & 1u;
+                mbar_wait(smem_u32(&bars->full[st]), ph);
+                tc_fence_after();
+                const uint32_t b_addr = sbase + kSmemCStage + st * kStageBytes;
 #pragma unroll
-              for (int k = 0; k < 4; ++k)
-                umma_bf16(d_tmem, make_desc_kmajor(a_addr + k * 32), make_desc_kmajor(b_addr + k * 32), idesc,
-                          (ci > 0 || k > 0) ? 1u : 0u);
-              umma_commit(smem_u32(&bars->empty[st]));
+                for (int k = 0; k < 4; ++k)
+                  umma_bf16(d_tmem + (uint32_t)n0, make_desc_kmajor(a_addr + k * 32), make_desc_kmajor(b_addr + k * 32),
+                            idesc, (ci > 0 || k > 0) ? 1u : 0u);
+                umma_commit(smem_u32(&bars->empty[st]));
+              }
             }
             umma_commit(smem_u32(&bars->acc_full[t]));
           }
@@ -243,8 +251,8 @@ mlp_tc_bwd_chain_kernel(const __grid_constant__ BwdPlan plan, const uint8_t* __r
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             const int jl = jg * 8 + i;                   // column inside this half
-            const float4 w = lds128f(w_rgb_u32 + (half * 64 + jl) * 16);
-            float dh = d4.x * w.x + d4.y * w.y + d4.z * w.z;
+            const uint32_t wa = w_rgb_u32 + (half * 64 + jl) * 12;
+            float dh = d4.x * lds32f(wa) + d4.y * lds32f(wa + 4) + d4.z * lds32f(wa + 8);
             v[i] = mask_bit(mwl[jl >> 5], jl & 31) ? dh : alpha * dh;
           }
           uint4 pk = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]),
@@ -402,7 +410,8 @@ constexpr int kDwStages = 3;
 constexpr int kDwHalf = 8192;                    // one panel restricted to 64 rows
 constexpr int kDwStageBytes = 8 * kDwHalf;       // 4 A slots + 4 B slots
 constexpr int kSmemDwBar = kDwStages * kDwStageBytes;
-constexpr int kSmemDwAlloc = kSmemDwBar + 256 + 1024;
+constexpr int kSmemDwAlloc = kSmemDwBar + 256;
+static_assert(kSmemDwAlloc <= 232448, "dW kernel exceeds the 227 KB shared-memory limit");
 constexpr int kThreadsDw = 192;
 
 struct DwBars {
@@ -455,9 +464,9 @@ __global__ void __launch_bounds__(kThreadsDw, 1)
 mlp_tc_bwd_dw_kernel(const __grid_constant__ DwPlan plan, const __grid_constant__ NetGeom g,
                      const uint8_t* __restrict__ saved, const uint8_t* __restrict__ dz_ws, int64_t M,
                      float* __restrict__ G) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t sbase = smem_u32(smem);
+  if ((sbase & 1023u) != 0u) __trap();
   DwBars* bars = reinterpret_cast<DwBars*>(smem + kSmemDwBar);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -536,15 +545,24 @@ mlp_tc_bwd_dw_kernel(const __grid_constant__ DwPlan plan, const __grid_constant_
       const uint32_t st = gi % kDwStages, ph = (gi / kDwStages) & 1u;
       mbar_wait(smem_u32(&bars->full[st]), ph);
       if (col_ok) {
-        const uint8_t* pb = smem + st * kDwStageBytes + (4 + (c >> 6)) * kDwHalf;
-        const int cc = c & 63;
-#pragma unroll 8
-        for (int rr = 0; rr < 64; ++rr) {
-          uint32_t wv = *reinterpret_cast<const uint32_t*>(pb + panel_offset(rr, cc));
-          __nv_bfloat162 v2 = *reinterpret_cast<__nv_bfloat162*>(&wv);
-          s0 += __low2float(v2);
-          s1 += __high2float(v2);
+        // columns (c, c+1) of the dZ stage: one 32-bit word per row; (row & 7) selects the swizzled 16-byte chunk
+        const uint32_t pb = sbase + st * kDwStageBytes + (4 + (c >> 6)) * kDwHalf + ((c & 7) << 1);
+        const uint32_t ch = (uint32_t)(c & 63) >> 3;
+        float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f;
+#pragma unroll
+        for (int r8 = 0; r8 < 8; ++r8) {
+#pragma unroll
+          for (int j = 0; j < 8; j += 2) {
+            const uint32_t w0 = lds32u(pb + (r8 * 8 + j) * 128 + ((ch ^ (uint32_t)j) << 4));
+            const uint32_t w1 = lds32u(pb + (r8 * 8 + j + 1) * 128 + ((ch ^ (uint32_t)(j + 1)) << 4));
+            a0 += __uint_as_float(w0 << 16);
+            a1 += __uint_as_float(w0 & 0xffff0000u);
+            b0 += __uint_as_float(w1 << 16);
+            b1 += __uint_as_float(w1 & 0xffff0000u);
+          }
         }
+        s0 += a0 + b0;
+        s1 += a1 + b1;
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_u32(&bars->empty[st]));
