@@ -122,8 +122,8 @@ def cpu_reference_rate(cfg_name, n_rays, reps, threads=None):
     import torch
     from oracle import nerf_oracle as O
     batch, near, far, fov = CONFIGS[cfg_name]
-    if threads:
-        torch.set_num_threads(threads)
+    # all host threads, also under torchrun (which exports OMP_NUM_THREADS=1)
+    torch.set_num_threads(threads or os.cpu_count() or 1)
     ocfg = O.NetCfg()
     pc, pf = O.glorot_params(ocfg.shapes, 0), O.glorot_params(ocfg.shapes, 1)
     o, d, y = synthetic_batch(n_rays, fov, 0, O.rays_for_image)

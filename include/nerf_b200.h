@@ -34,6 +34,10 @@ extern "C" {
  * chain, bf16 operands, fp32 accumulate (1e-3 parity mode). */
 #define NERF_MODE_FP32 0
 #define NERF_MODE_BF16 1
+/* FP16: the same tensor-core forward chain with fp16 operands (8x finer operand rounding than bf16, same throughput);
+ * forward only -- the render mode that meets the 1e-3 bound on sharp networks (the reference itself renders in
+ * float16).  Needs nerf_pack_weights_fp16. */
+#define NERF_MODE_FP16 2
 
 /* Network hyper-parameters: the `neural_net:` block of the reference YAML (src/NeRF.py:35-53,
  * src/ConfigurationKeys.py). */
@@ -119,6 +123,8 @@ int nerf_mlp_bwd(const nerf_net_cfg* cfg, const float* params, const void* packe
 /* bf16 weight pack for the tensor-core path (re-run after every optimizer step). */
 int64_t nerf_packed_bytes(const nerf_net_cfg* cfg);
 int nerf_pack_weights(const nerf_net_cfg* cfg, const float* params, void* packed, void* stream);
+/* fills the fp16 region of the same packed buffer (only needed before NERF_MODE_FP16 calls). */
+int nerf_pack_weights_fp16(const nerf_net_cfg* cfg, const float* params, void* packed, void* stream);
 
 /* ---- alpha compositing (ray_marching, src/UtilsNeuralRadianceField.py:88-115) ------------------------- */
 /* raw4 (N,S,4), z (N,S).  Outputs (any may be null): rgb (N,3), weights/cumprod/alpha (N,S),

@@ -46,7 +46,7 @@ class _StepWorkspace:
         mc = model.model_coarse
         self.n = n
         self.z_c = f(n, sc)
-        fused = model.mode == "bf16"          # bf16: encodings are computed inside the MLP kernel, never materialised
+        fused = mc.tensor_core                # tensor-core modes: encodings are computed inside the MLP kernel
         self.xyz_c = None if fused else f(n * sc, mc.dx)
         self.view_c = f(n * sc, mc.dv) if (mc.dv and not fused) else None
         self.raw_c = f(n, sc, 4)
@@ -86,7 +86,8 @@ class NeRF:
         """
         :param net_config:      ``neural_net`` block of the config file.
         :param render_config:   ``render`` block of the config file.
-        :param mode:            (extension) "bf16" tensor-core path or "fp32" parity path.
+        :param mode:            (extension) "bf16": tensor-core path (train + render); "fp16": train in bf16, render with
+                                fp16 operands (8x finer rounding, same speed); "fp32": SIMT parity path.
         :param stop_grad_z:     (extension, default False = reference behaviour) detach the importance samples.
         """
         self.device = device or torch.device("cuda", torch.cuda.current_device())
@@ -169,9 +170,10 @@ class NeRF:
         n, s = z.shape
         dev = z.device
         raw = torch.empty((n, s, 4), dtype=torch.float32, device=dev)
-        if model.mode == "bf16":
-            call("nerf_mlp_fwd_rays", model.cfg_ref, ptr(model.packed_for(model.params)), ptr(rays_orig), ptr(rays_dirs),
-                 ptr(z), n, s, ptr(raw), None, model.mode_id)
+        if model.tensor_core:
+            half = model.infer_mode_id == _lib.MODE_FP16
+            call("nerf_mlp_fwd_rays", model.cfg_ref, ptr(model.packed_for(model.params, half=half)), ptr(rays_orig),
+                 ptr(rays_dirs), ptr(z), n, s, ptr(raw), None, model.infer_mode_id)
         else:
             xyz = torch.empty((n * s, model.dx), dtype=torch.float32, device=dev)
             view = torch.empty((n * s, model.dv), dtype=torch.float32, device=dev) if model.dv else None
@@ -336,7 +338,7 @@ class NeRF:
 
     def _mlp_fwd_train(self, net, o, d, z, n, s, xyz, view, raw, saved, ws):
         """Training-mode MLP forward (activations saved): fused encode+MLP kernel in bf16 mode, two kernels in fp32."""
-        if self.mode == "bf16":
+        if net.tensor_core:
             call("nerf_mlp_fwd_rays", net.cfg_ref, ptr(net.packed_for(net.params)), ptr(o), ptr(d), ptr(z), n, s,
                  ptr(raw), ptr(saved), net.mode_id)
         else:

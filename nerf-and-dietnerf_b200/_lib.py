@@ -15,6 +15,7 @@ LIB_PATH = os.path.join(_HERE, "libnerf_b200.so")
 
 MODE_FP32 = 0
 MODE_BF16 = 1
+MODE_FP16 = 2
 
 
 class NetCfg(Structure):
@@ -53,6 +54,7 @@ SIGNATURES = {
     "nerf_mlp_bwd": (c_int32, [_CFG, _P, _P, _P, _P, _P, _P, c_int64, _P, _P, _P, c_int32, _P]),
     "nerf_packed_bytes": (c_int64, [_CFG]),
     "nerf_pack_weights": (c_int32, [_CFG, _P, _P, _P]),
+    "nerf_pack_weights_fp16": (c_int32, [_CFG, _P, _P, _P]),
     "nerf_composite_fwd": (c_int32, [_P, _P, c_int64, c_int32, _P, _P, _P, _P, _P, _P, _P, _P]),
     "nerf_composite_bwd": (c_int32, [_P, _P, _P, _P, c_int64, c_int32, _P, _P, _P]),
     "nerf_sample_pdf_fwd": (c_int32, [_P, _P, c_int64, c_int32, c_int32, _P, c_uint64, c_uint32, c_uint64, _P, _P, _P,

@@ -8,12 +8,12 @@ namespace nerf {
 
 // provided by mlp_tc.cu
 int mlp_tc_fwd(const nerf_net_cfg* cfg, const NetGeom& g, const float* params, const void* packed, const float* xyz_enc,
-               const float* view_enc, int64_t m, float* out4, void* saved, void* workspace, cudaStream_t st);
+               const float* view_enc, int64_t m, float* out4, void* saved, void* workspace, cudaStream_t st, bool half);
 int mlp_tc_bwd(const nerf_net_cfg* cfg, const NetGeom& g, const float* params, const void* packed, const float* xyz_enc,
                const float* view_enc, const void* saved, const float* d_out4, int64_t m, float* grads, float* d_xyz_enc,
                void* workspace, cudaStream_t st);
 int mlp_tc_fwd_rays(const nerf_net_cfg* cfg, const NetGeom& g, const void* packed, const float* origs4, const float* dirs4,
-                    const float* z, int64_t n_rays, int n_samples, float* out4, void* saved, cudaStream_t st);
+                    const float* z, int64_t n_rays, int n_samples, float* out4, void* saved, cudaStream_t st, bool half);
 int64_t mlp_tc_saved_bytes(const NetGeom& g, int64_t m);
 int64_t mlp_tc_workspace_bytes(const NetGeom& g, int64_t m, int backward);
 
@@ -345,12 +345,12 @@ int nerf_mlp_fwd(const nerf_net_cfg* cfg, const float* params, const void* packe
   NERF_CHECK_ARG(make_geom(cfg, &g), "bad net config");
   NERF_CHECK_ARG(params && xyz_enc && out4 && (view_enc || !g.view), "null pointer");
   NERF_CHECK_ARG(m >= 0, "negative row count");
-  NERF_CHECK_ARG(mode == NERF_MODE_FP32 || mode == NERF_MODE_BF16, "unknown mode");
+  NERF_CHECK_ARG(mode == NERF_MODE_FP32 || mode == NERF_MODE_BF16 || mode == NERF_MODE_FP16, "unknown mode");
   if (m == 0) return NERF_OK;
-  if (mode == NERF_MODE_BF16) {
-    NERF_CHECK_ARG(packed_or_null, "NERF_MODE_BF16 needs the packed weights (nerf_pack_weights)");
+  if (mode != NERF_MODE_FP32) {
+    NERF_CHECK_ARG(packed_or_null, "the tensor-core modes need the packed weights (nerf_pack_weights[_fp16])");
     return mlp_tc_fwd(cfg, g, params, packed_or_null, xyz_enc, view_enc, m, out4, saved_or_null, workspace,
-                      (cudaStream_t)stream);
+                      (cudaStream_t)stream, mode == NERF_MODE_FP16);
   }
   NERF_CHECK_ARG(saved_or_null || workspace, "inference needs a workspace (nerf_mlp_workspace_bytes)");
   fp32_fwd(cfg, g, params, xyz_enc, view_enc, m, out4, (float*)saved_or_null, (float*)workspace, (cudaStream_t)stream);
@@ -364,13 +364,14 @@ int nerf_mlp_fwd_rays(const nerf_net_cfg* cfg, const void* packed, const float* 
   NERF_CHECK_ARG(make_geom(cfg, &g), "bad net config");
   NERF_CHECK_ARG(packed && origs4 && dirs4 && z && out4, "null pointer");
   NERF_CHECK_ARG(n_rays >= 0 && n_samples > 0, "bad shape");
-  if (mode != NERF_MODE_BF16) {
-    set_error("nerf_mlp_fwd_rays: only NERF_MODE_BF16 fuses the encodings into the MLP kernel "
+  if (mode != NERF_MODE_BF16 && mode != NERF_MODE_FP16) {
+    set_error("nerf_mlp_fwd_rays: only the tensor-core modes fuse the encodings into the MLP kernel "
               "(fp32 mode: nerf_encode_samples + nerf_mlp_fwd)");
     return NERF_E_UNSUPPORTED;
   }
   if (n_rays == 0) return NERF_OK;
-  return mlp_tc_fwd_rays(cfg, g, packed, origs4, dirs4, z, n_rays, n_samples, out4, saved_or_null, (cudaStream_t)stream);
+  return mlp_tc_fwd_rays(cfg, g, packed, origs4, dirs4, z, n_rays, n_samples, out4, saved_or_null, (cudaStream_t)stream,
+                         mode == NERF_MODE_FP16);
 }
 
 int nerf_mlp_bwd(const nerf_net_cfg* cfg, const float* params, const void* packed_or_null, const float* xyz_enc,

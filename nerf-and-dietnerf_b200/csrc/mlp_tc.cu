@@ -22,7 +22,7 @@ namespace nerf {
 // ---- weight packing -----------------------------------------------------------------------------------------------------
 // One thread per bf16 element of every chunk, plus the fp32 tail (biases, rgb head).
 __global__ void pack_weights_kernel(const __grid_constant__ TcPlan plan, NetGeom g, const float* __restrict__ P,
-                                    uint8_t* __restrict__ packed) {
+                                    uint8_t* __restrict__ packed, int as_half) {
   const int chunk = blockIdx.y;
   if (chunk < plan.n_chunks) {
     // find the layer of this chunk
@@ -55,7 +55,10 @@ __global__ void pack_weights_kernel(const __grid_constant__ TcPlan plan, NetGeom
       const LayerDesc& L = g.layers[dense];
       v = P[L.w_off + (int64_t)row * L.out + col];
     }
-    *reinterpret_cast<__nv_bfloat16*>(packed + plan.chunk_off[chunk] + panel_offset(n, k)) = __float2bfloat16_rn(v);
+    if (as_half)
+      *reinterpret_cast<__half*>(packed + plan.chunk_off[chunk] + panel_offset(n, k)) = __float2half_rn(v);
+    else
+      *reinterpret_cast<__nv_bfloat16*>(packed + plan.chunk_off[chunk] + panel_offset(n, k)) = __float2bfloat16_rn(v);
   } else {
     // fp32 tail
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
@@ -95,15 +98,16 @@ struct FwdInput {
   int32_t n_samples, Lx, Lv, ncomp, dx, dv;
 };
 
-__device__ __forceinline__ void sts_bf16(uint32_t panel_row_addr, int r, int col, float v) {
-  const __nv_bfloat16 h = __float2bfloat16_rn(v);
+template <bool kHalf>
+__device__ __forceinline__ void sts_16(uint32_t panel_row_addr, int r, int col, float v) {
+  const uint32_t both = pack_16x2<kHalf>(v, 0.f);
   const uint32_t addr = panel_row_addr + ((((uint32_t)col >> 3) ^ ((uint32_t)r & 7u)) << 4) + (((uint32_t)col & 7u) << 1);
-  asm volatile("st.shared.b16 [%0], %1;" ::"r"(addr), "h"(*reinterpret_cast<const uint16_t*>(&h)) : "memory");
+  asm volatile("st.shared.b16 [%0], %1;" ::"r"(addr), "h"((uint16_t)(both & 0xffffu)) : "memory");
 }
 
 // Epilogue of one 32-column group: acc + bias (smem) -> LeakyReLU -> bf16 -> swizzled panel row.  Returns the sign mask
 // (bit (15 - k) = element 2k is positive, bit (31 - k) = element 2k+1 is positive, k = 0..15) when kMask.
-template <bool kMask>
+template <bool kMask, bool kHalf>
 __device__ __forceinline__ uint32_t epi_group32(const uint32_t (&acc)[32], uint32_t bias_addr, float alpha,
                                                 uint32_t prow_addr, int r, int chunk_base) {
   uint32_t mword = 0;
@@ -122,7 +126,7 @@ __device__ __forceinline__ uint32_t epi_group32(const uint32_t (&acc)[32], uint3
       float x0, x1, l0, l1;
       unpack_f32x2(x, x0, x1);
       unpack_f32x2(lo, l0, l1);
-      pk[i] = pack_bf16x2(fmaxf(x0, l0), fmaxf(x1, l1));      // LeakyReLU for 0 <= alpha <= 1
+      pk[i] = pack_16x2<kHalf>(fmaxf(x0, l0), fmaxf(x1, l1)); // LeakyReLU for 0 <= alpha <= 1
       if (kMask) mword |= (~pk[i] >> (4 * j + i)) & (0x80008000u >> (4 * j + i));
     }
     sts128(prow_addr + (((chunk_base + j) ^ (r & 7)) << 4), make_uint4(pk[0], pk[1], pk[2], pk[3]));
@@ -130,7 +134,7 @@ __device__ __forceinline__ uint32_t epi_group32(const uint32_t (&acc)[32], uint3
   return mword;
 }
 
-template <bool kSave>
+template <bool kSave, bool kHalf>
 __global__ void __launch_bounds__(kThreadsFwd, 1)
 mlp_tc_fwd_kernel(const __grid_constant__ TcPlan plan, const uint8_t* __restrict__ packed,
                   const __grid_constant__ FwdInput in, int64_t M, float* __restrict__ out4, uint8_t* __restrict__ saved,
@@ -205,7 +209,7 @@ mlp_tc_fwd_kernel(const __grid_constant__ TcPlan plan, const uint8_t* __restrict
               const uint32_t a_addr = (src < 4) ? sbase + kSmemAct + (t * kActPanels + src) * kPanelBytes
                                                 : sbase + kSmemInp + t * kPanelBytes;
               for (int n0 = 0; n0 < n_total; n0 += kStageRows, ++g) {          // row halves of the chunk: N = 128 (or the rest)
-                const uint32_t idesc = make_idesc(min(kStageRows, n_total - n0));
+                const uint32_t idesc = make_idesc(min(kStageRows, n_total - n0), 0, 0, kHalf ? 0 : 1);
                 const uint32_t s = g % kStages, ph = (g / kStages) & 1u;
                 mbar_wait(smem_u32(&bars->full[s]), ph);
                 tc_fence_after();
@@ -249,10 +253,10 @@ mlp_tc_fwd_kernel(const __grid_constant__ TcPlan plan, const uint8_t* __restrict
           if (in.xyz_enc != nullptr) {
             if (half == 0) {
               const float* xr = in.xyz_enc + row * in.dx;
-              for (int i = 0; i < in.dx; ++i) sts_bf16(prow, r, i, __ldg(xr + i));
+              for (int i = 0; i < in.dx; ++i) sts_16<kHalf>(prow, r, i, __ldg(xr + i));
             } else {
               const float* vr = in.view_enc + row * in.dv;
-              for (int i = 0; i < in.dv; ++i) sts_bf16(prow, r, kInpViewCol + i, __ldg(vr + i));
+              for (int i = 0; i < in.dv; ++i) sts_16<kHalf>(prow, r, kInpViewCol + i, __ldg(vr + i));
             }
           } else {
             const int64_t ray = row / in.n_samples;
@@ -265,12 +269,12 @@ mlp_tc_fwd_kernel(const __grid_constant__ TcPlan plan, const uint8_t* __restrict
               for (int c = 0; c < 3; ++c) {
                 const float oc = c == 0 ? o.x : (c == 1 ? o.y : o.z), dc = c == 0 ? d.x : (c == 1 ? d.y : d.z);
                 const float pc = __fadd_rn(oc, __fmul_rn(dc, zz));       // sample_along_rays, src/UtilsCV.py:598
-                sts_bf16(prow, r, c * per, pc);
+                sts_16<kHalf>(prow, r, c * per, pc);
                 for (int k = 0; k < in.Lx; ++k) {
                   float sn, cs;
                   sincospif(ldexpf(pc, k), &sn, &cs);                      // sin/cos(2^k pi p)
-                  sts_bf16(prow, r, c * per + 1 + 2 * k, sn);
-                  sts_bf16(prow, r, c * per + 2 + 2 * k, cs);
+                  sts_16<kHalf>(prow, r, c * per + 1 + 2 * k, sn);
+                  sts_16<kHalf>(prow, r, c * per + 2 + 2 * k, cs);
                 }
               }
             } else {
@@ -279,8 +283,8 @@ mlp_tc_fwd_kernel(const __grid_constant__ TcPlan plan, const uint8_t* __restrict
                 for (int k = 0; k < in.Lv; ++k) {
                   float sn, cs;
                   sincospif(ldexpf(vc, k), &sn, &cs);
-                  sts_bf16(prow, r, kInpViewCol + c * 2 * in.Lv + 2 * k, sn);
-                  sts_bf16(prow, r, kInpViewCol + c * 2 * in.Lv + 2 * k + 1, cs);
+                  sts_16<kHalf>(prow, r, kInpViewCol + c * 2 * in.Lv + 2 * k, sn);
+                  sts_16<kHalf>(prow, r, kInpViewCol + c * 2 * in.Lv + 2 * k + 1, cs);
                 }
               }
             }
@@ -321,7 +325,7 @@ mlp_tc_fwd_kernel(const __grid_constant__ TcPlan plan, const uint8_t* __restrict
             tmem_ld_wait();
             if (cc + 1 < 4) tmem_ld32(taddr + c0 + 32, acc[(cc + 1) & 1]);
             const uint32_t prow = act_u32 + (c0 >> 6) * kPanelBytes + r * 128;
-            const uint32_t mword = epi_group32<kSave>(acc[cc & 1], bias_u32 + c0 * 4, alpha, prow, r, (c0 & 63) >> 3);
+            const uint32_t mword = epi_group32<kSave, kHalf>(acc[cc & 1], bias_u32 + c0 * 4, alpha, prow, r, (c0 & 63) >> 3);
             if (kSave) saved_mask[(l * 8 + (c0 >> 5)) * 128 + r] = mword;
           }
           mbar_arrive(smem_u32(&bars->bias_empty[slot]));
@@ -363,7 +367,7 @@ mlp_tc_fwd_kernel(const __grid_constant__ TcPlan plan, const uint8_t* __restrict
                 rr = fmaf(x0, w0.x, fmaf(x1, w1.x, rr));
                 gg = fmaf(x0, w0.y, fmaf(x1, w1.y, gg));
                 bb = fmaf(x0, w0.z, fmaf(x1, w1.z, bb));
-                pk[i] = pack_bf16x2(x0, x1);
+                pk[i] = pack_16x2<kHalf>(x0, x1);
                 if (kSave) mword |= (~pk[i] >> (4 * j + i)) & (0x80008000u >> (4 * j + i));
               }
               if (kSave) sts128(prow + (((((c0 & 63) >> 3) + j) ^ (r & 7)) << 4), make_uint4(pk[0], pk[1], pk[2], pk[3]));
@@ -418,8 +422,13 @@ int64_t mlp_tc_workspace_bytes(const NetGeom& g, int64_t m, int backward) {
   return tiles * (int64_t)kDzTileBytes + 1024;
 }
 
+// byte offset of the fp16 copy of the forward weight pack inside the packed buffer: [bf16 fwd | bf16 bwd | fp16 fwd]
+static uint32_t half_region_offset(const TcPlan& plan) {
+  return ((plan.total_bytes + 1023u) & ~1023u) + ((bwd_pack_bytes() + 1023u) & ~1023u);
+}
+
 static int launch_fwd(const nerf_net_cfg* cfg, const NetGeom& g, const void* packed, const FwdInput& in, int64_t m,
-                      float* out4, void* saved, cudaStream_t st) {
+                      float* out4, void* saved, cudaStream_t st, bool half = false) {
   TcPlan plan;
   if (!make_plan(g, &plan) || cfg->leaky_alpha < 0.f || cfg->leaky_alpha > 1.f) {
     set_error("NERF_MODE_BF16 supports hidden=256, last_hidden=128, n_angles in {1,2}, xyz width <= 40, view width <= 24, "
@@ -428,37 +437,43 @@ static int launch_fwd(const nerf_net_cfg* cfg, const NetGeom& g, const void* pac
   }
   static bool attr_set = false;
   if (!attr_set) {
-    NERF_CUDA(cudaFuncSetAttribute(mlp_tc_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemAlloc));
-    NERF_CUDA(cudaFuncSetAttribute(mlp_tc_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemAlloc));
+    NERF_CUDA(cudaFuncSetAttribute(mlp_tc_fwd_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemAlloc));
+    NERF_CUDA(cudaFuncSetAttribute(mlp_tc_fwd_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemAlloc));
+    NERF_CUDA(cudaFuncSetAttribute(mlp_tc_fwd_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemAlloc));
     attr_set = true;
   }
   int64_t n_pairs = ((m + kTileM - 1) / kTileM + 1) / 2;
   int grid = (int)(n_pairs < kNumSMs ? n_pairs : kNumSMs);
-  if (saved)
-    mlp_tc_fwd_kernel<true><<<grid, kThreadsFwd, kSmemAlloc, st>>>(plan, (const uint8_t*)packed, in, m, out4,
-                                                                  (uint8_t*)saved, cfg->leaky_alpha);
-  else
-    mlp_tc_fwd_kernel<false><<<grid, kThreadsFwd, kSmemAlloc, st>>>(plan, (const uint8_t*)packed, in, m, out4, nullptr,
-                                                                   cfg->leaky_alpha);
+  if (half) {
+    if (saved) { set_error("NERF_MODE_FP16 is a forward-only (render) mode: train in NERF_MODE_BF16"); return NERF_E_UNSUPPORTED; }
+    mlp_tc_fwd_kernel<false, true><<<grid, kThreadsFwd, kSmemAlloc, st>>>(
+        plan, (const uint8_t*)packed + half_region_offset(plan), in, m, out4, nullptr, cfg->leaky_alpha);
+  } else if (saved) {
+    mlp_tc_fwd_kernel<true, false><<<grid, kThreadsFwd, kSmemAlloc, st>>>(plan, (const uint8_t*)packed, in, m, out4,
+                                                                         (uint8_t*)saved, cfg->leaky_alpha);
+  } else {
+    mlp_tc_fwd_kernel<false, false><<<grid, kThreadsFwd, kSmemAlloc, st>>>(plan, (const uint8_t*)packed, in, m, out4, nullptr,
+                                                                          cfg->leaky_alpha);
+  }
   NERF_CHECK_LAUNCH();
   return NERF_OK;
 }
 
 int mlp_tc_fwd(const nerf_net_cfg* cfg, const NetGeom& g, const float* params, const void* packed, const float* xyz_enc,
-               const float* view_enc, int64_t m, float* out4, void* saved, void* workspace, cudaStream_t st) {
+               const float* view_enc, int64_t m, float* out4, void* saved, void* workspace, cudaStream_t st, bool half) {
   (void)params; (void)workspace;
   FwdInput in = {};
   in.xyz_enc = xyz_enc; in.view_enc = view_enc; in.dx = g.dx; in.dv = g.dv;
   in.Lx = cfg->n_pos_enc_xyz; in.Lv = cfg->n_pos_enc_view; in.ncomp = cfg->n_angles + 1; in.n_samples = 1;
-  return launch_fwd(cfg, g, packed, in, m, out4, saved, st);
+  return launch_fwd(cfg, g, packed, in, m, out4, saved, st, half);
 }
 
 int mlp_tc_fwd_rays(const nerf_net_cfg* cfg, const NetGeom& g, const void* packed, const float* origs4, const float* dirs4,
-                    const float* z, int64_t n_rays, int n_samples, float* out4, void* saved, cudaStream_t st) {
+                    const float* z, int64_t n_rays, int n_samples, float* out4, void* saved, cudaStream_t st, bool half) {
   FwdInput in = {};
   in.origs = (const float4*)origs4; in.dirs = (const float4*)dirs4; in.z = z; in.n_samples = n_samples;
   in.dx = g.dx; in.dv = g.dv; in.Lx = cfg->n_pos_enc_xyz; in.Lv = cfg->n_pos_enc_view; in.ncomp = cfg->n_angles + 1;
-  return launch_fwd(cfg, g, packed, in, n_rays * n_samples, out4, saved, st);
+  return launch_fwd(cfg, g, packed, in, n_rays * n_samples, out4, saved, st, half);
 }
 
 }  // namespace nerf
@@ -472,7 +487,7 @@ int64_t nerf_packed_bytes(const nerf_net_cfg* cfg) {
   TcPlan plan;
   if (!make_geom(cfg, &g)) { set_error("nerf_packed_bytes: bad net config"); return NERF_E_ARG; }
   if (!make_plan(g, &plan)) { set_error("nerf_packed_bytes: config not supported by NERF_MODE_BF16"); return NERF_E_UNSUPPORTED; }
-  return (int64_t)((plan.total_bytes + 1023u) & ~1023u) + bwd_pack_bytes();
+  return (int64_t)half_region_offset(plan) + plan.total_bytes;
 }
 
 int nerf_pack_weights(const nerf_net_cfg* cfg, const float* params, void* packed, void* stream) {
@@ -482,9 +497,21 @@ int nerf_pack_weights(const nerf_net_cfg* cfg, const float* params, void* packed
   NERF_CHECK_ARG(params && packed, "null pointer");
   if (!make_plan(g, &plan)) { set_error("nerf_pack_weights: config not supported by NERF_MODE_BF16"); return NERF_E_UNSUPPORTED; }
   dim3 grid((256 * 64 + 255) / 256, plan.n_chunks + 1);
-  pack_weights_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(plan, g, params, (uint8_t*)packed);
+  pack_weights_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(plan, g, params, (uint8_t*)packed, 0);
   NERF_CHECK_LAUNCH();
   return bwd_pack_weights(g, params, (uint8_t*)packed + ((plan.total_bytes + 1023u) & ~1023u), (cudaStream_t)stream);
+}
+
+int nerf_pack_weights_fp16(const nerf_net_cfg* cfg, const float* params, void* packed, void* stream) {
+  NetGeom g;
+  TcPlan plan;
+  NERF_CHECK_ARG(make_geom(cfg, &g), "bad net config");
+  NERF_CHECK_ARG(params && packed, "null pointer");
+  if (!make_plan(g, &plan)) { set_error("nerf_pack_weights_fp16: config not supported by the tensor-core path"); return NERF_E_UNSUPPORTED; }
+  dim3 grid((256 * 64 + 255) / 256, plan.n_chunks + 1);
+  pack_weights_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(plan, g, params, (uint8_t*)packed + half_region_offset(plan), 1);
+  NERF_CHECK_LAUNCH();
+  return NERF_OK;
 }
 
 }  // extern "C"

@@ -2,6 +2,7 @@
 // tcgen05 (alloc / mma / commit / ld / fences) and UMMA descriptors.  Inline PTX only; no CUTLASS dependency.
 #pragma once
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 
 namespace nerf {
@@ -148,9 +149,10 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t lbo_b
 __device__ __forceinline__ uint64_t make_desc_kmajor(uint32_t smem_addr) { return make_desc(smem_addr, 16, 1024); }
 
 // Instruction descriptor for kind::f16: bf16 x bf16 -> fp32, M = 128, N = n.  a_major/b_major: 0 = K-major, 1 = MN-major.
-__host__ __device__ constexpr uint32_t make_idesc(int n, int a_mn_major = 0, int b_mn_major = 0) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
-         ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+// operand_fmt: 1 = bf16 (default), 0 = fp16.
+__host__ __device__ constexpr uint32_t make_idesc(int n, int a_mn_major = 0, int b_mn_major = 0, int operand_fmt = 1) {
+  return (1u << 4) | ((uint32_t)operand_fmt << 7) | ((uint32_t)operand_fmt << 10) | ((uint32_t)a_mn_major << 15) |
+         ((uint32_t)b_mn_major << 16) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 }
 
 // byte offset of element (row, col) inside a [rows][64] bf16 panel stored with the 128-byte swizzle
@@ -176,6 +178,17 @@ __device__ __forceinline__ uint64_t mul_f32x2(uint64_t a, uint64_t b) {
   uint64_t r;
   asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
   return r;
+}
+
+// two floats -> packed 16-bit pair (lo in bits 0..15): fp16 when kHalf, else bf16
+template <bool kHalf>
+__device__ __forceinline__ uint32_t pack_16x2(float lo, float hi) {
+  if (kHalf) {
+    __half2 v = __floats2half2_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&v);
+  }
+  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
 }
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {

@@ -11,9 +11,10 @@ import math
 import torch
 
 from . import _lib
-from ._lib import MODE_BF16, MODE_FP32, NetCfg, call, load, ptr
+from ._lib import MODE_BF16, MODE_FP16, MODE_FP32, NetCfg, call, load, ptr
 
-_MODES = {"fp32": MODE_FP32, "bf16": MODE_BF16}
+# mode -> (arithmetic of training / differentiable calls, arithmetic of inference-only calls)
+_MODES = {"fp32": (MODE_FP32, MODE_FP32), "bf16": (MODE_BF16, MODE_BF16), "fp16": (MODE_BF16, MODE_FP16)}
 
 
 def layer_shapes(cfg: NetCfg):
@@ -32,11 +33,12 @@ class _MlpFn(torch.autograd.Function):
         m = xyz_enc.shape[0]
         out = torch.empty((m, 4), dtype=torch.float32, device=xyz_enc.device)
         need_grad = bool(ctx.needs_input_grad[0] or ctx.needs_input_grad[1])
+        mode_id = model.mode_id if need_grad else model.infer_mode_id
         saved = (torch.empty(max(model.saved_bytes(m), 16), dtype=torch.uint8, device=xyz_enc.device)
                  if need_grad else None)
         ws = model._buffer("ws_fwd", model.workspace_bytes(m, False))
-        call("nerf_mlp_fwd", model.cfg_ref, ptr(params), ptr(model.packed_for(params)), ptr(xyz_enc), ptr(view_enc), m,
-             ptr(out), ptr(saved), ptr(ws), model.mode_id)
+        call("nerf_mlp_fwd", model.cfg_ref, ptr(params), ptr(model.packed_for(params, half=mode_id == MODE_FP16)),
+             ptr(xyz_enc), ptr(view_enc), m, ptr(out), ptr(saved), ptr(ws), mode_id)
         ctx.model = model
         ctx.save_for_backward(params, xyz_enc, view_enc if view_enc is not None else torch.empty(0), saved
                               if saved is not None else torch.empty(0))
@@ -62,25 +64,27 @@ class NerfMLP:
 
     def __init__(self, cfg: NetCfg, mode: str = "bf16", device=None, seed=None):
         if mode not in _MODES:
-            raise ValueError("mode must be 'fp32' or 'bf16'")
+            raise ValueError("mode must be 'fp32', 'bf16' or 'fp16'")
         load()
         self.cfg = cfg
         self.cfg_ref = _lib.ctypes.byref(cfg)
         self.mode = mode
-        self.mode_id = _MODES[mode]
+        self.mode_id, self.infer_mode_id = _MODES[mode]
+        self.tensor_core = self.mode_id != MODE_FP32
         self.device = device or torch.device("cuda", torch.cuda.current_device())
         self.shapes = layer_shapes(cfg)
         self.n_params = int(load().nerf_param_count(self.cfg_ref))
         assert self.n_params == sum(i * o + o for i, o in self.shapes)
         self.dx = int(load().nerf_xyz_enc_dim(self.cfg_ref))
         self.dv = int(load().nerf_view_enc_dim(self.cfg_ref))
-        if self.mode_id == MODE_BF16 and int(load().nerf_packed_bytes(self.cfg_ref)) < 0:
-            raise _lib.NerfLibraryError("mode='bf16' does not support this network: "
+        if self.tensor_core and int(load().nerf_packed_bytes(self.cfg_ref)) < 0:
+            raise _lib.NerfLibraryError("mode='bf16'/'fp16' does not support this network: "
                                         + load().nerf_last_error().decode() + " (use mode='fp32')")
         self.params = self._glorot_init(seed).to(self.device)
         self._buffers = {}
         self._packed = None
         self._packed_version = None
+        self._packed_half_version = None
 
     # -- parameters -------------------------------------------------------------------------------------------
     def _glorot_init(self, seed):
@@ -110,11 +114,11 @@ class NerfMLP:
         if flat.numel() != self.n_params:
             raise ValueError(f"expected {self.n_params} parameters, got {flat.numel()}")
         self.params = flat.to(self.device).contiguous().clone()
-        self._packed_version = None
+        self._packed_version = self._packed_half_version = None
 
     def mark_updated(self):
         """Call after an in-place parameter update so the bf16 weight pack is refreshed."""
-        self._packed_version = None
+        self._packed_version = self._packed_half_version = None
 
     # -- workspaces ------------------------------------------------------------------------------------------
     def saved_bytes(self, m):
@@ -131,14 +135,19 @@ class NerfMLP:
             self._buffers[name] = buf
         return buf
 
-    def packed_for(self, params):
-        if self.mode_id != MODE_BF16:
+    def packed_for(self, params, half=False):
+        """The packed 16-bit weight buffer, refreshed when the parameters changed (bf16 regions; fp16 region if half)."""
+        if not self.tensor_core:
             return None
         key = (params.data_ptr(), params._version)
         if self._packed is None:
             self._packed = torch.empty(int(load().nerf_packed_bytes(self.cfg_ref)), dtype=torch.uint8,
                                        device=self.device)
-        if self._packed_version != key:
+        if half:
+            if self._packed_half_version != key:
+                call("nerf_pack_weights_fp16", self.cfg_ref, ptr(params), ptr(self._packed))
+                self._packed_half_version = key
+        elif self._packed_version != key:
             call("nerf_pack_weights", self.cfg_ref, ptr(params), ptr(self._packed))
             self._packed_version = key
         return self._packed

@@ -337,11 +337,12 @@ def _model(pkg, mode, n_angles=2, l_view=4, n_c=64, n_f=128, cls=None, sigma_gai
 # bf16 rows: `gain` scales the sigma head of the synthetic networks.  gain 30 makes densities of +-30 per unit length
 # (opaque surfaces, saturated alphas): there the 2^-9 relative rounding of bf16 operands moves rendered colours by up
 # to ~1e-2, which no bf16 pipeline can avoid; gain 4 is the regime of north_star's 1e-3 bound.
-@pytest.mark.parametrize("mode,tol,gain", [("fp32", FP32_TOL, 30.0), ("bf16", 2e-2, 30.0), ("bf16", 4e-3, 4.0)])
+@pytest.mark.parametrize("mode,tol,gain", [("fp32", FP32_TOL, 30.0), ("bf16", 2e-2, 30.0), ("bf16", 4e-3, 4.0),
+                                           ("fp16", BF16_TOL, 4.0), ("fp16", 4e-3, 30.0)])
 @pytest.mark.parametrize("n_angles,n_c,n_f,n", [(2, 64, 128, 500), (0, 64, 128, 130), (1, 64, 64, 77), (2, 64, 0, 100)])
 def test_render(pkg, mode, tol, gain, n_angles, n_c, n_f, n):
-    if mode == "bf16" and n_angles == 0:
-        pytest.skip("xyz-only network: fp32 mode only (documented gap of the bf16 path)")
+    if mode != "fp32" and n_angles == 0:
+        pytest.skip("xyz-only network: fp32 mode only (documented gap of the tensor-core path)")
     model, ocfg, pc, pf = _model(pkg, mode, n_angles, 4, n_c, n_f, sigma_gain=gain)
     o, d = random_rays(n, 3)
     jit = O.stratified_jitter(7, 2, n, n_c, ray_offset=40)
@@ -469,7 +470,7 @@ def test_trained_reference_weights(pkg):
     img = torch.from_numpy(pin["test_image"])
     golden = torch.from_numpy(pin["test_rgb_oracle"])
     psnr = {}
-    for mode in ("fp32", "bf16"):
+    for mode in ("fp32", "bf16", "fp16"):
         model = pkg.NeRFModel(net_config(batch_render=4096), render_config(), float(pin["near"]), float(pin["far"]),
                               mode=mode)
         model.model_coarse.set_params(pin["params_coarse"])
@@ -484,10 +485,12 @@ def test_trained_reference_weights(pkg):
               f"{float(pin['psnr_reference_test'][-1]):.3f})")
         if mode == "fp32":
             assert err < 2e-5 and depth_err < 2e-4
+        elif mode == "fp16":
+            assert err < 1e-3, "north_star: rendered rgb within 1e-3 under 16-bit tensor-core math"
         else:
             assert err < 2e-2
     assert abs(psnr["fp32"] - float(pin["test_psnr_oracle"])) < 0.005
-    assert abs(psnr["bf16"] - psnr["fp32"]) < 0.05
+    assert abs(psnr["bf16"] - psnr["fp32"]) < 0.05 and abs(psnr["fp16"] - psnr["fp32"]) < 0.05
     assert abs(psnr["bf16"] - float(pin["psnr_reference_test"][-1])) < 0.15
 
 
