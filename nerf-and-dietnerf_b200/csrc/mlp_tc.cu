@@ -13,8 +13,11 @@
 //     that feeds layer 0, the skip connection of layer 4 and the view branch of layer 8 (zero weight rows elsewhere);
 //   * layer 8 is N = 144: 128 last-hidden units + the sigma head (column 128); the 128->3 rgb head is evaluated on
 //     CUDA cores from the fp32 registers of the last epilogue;
-//   * training mode stores each layer's bf16 activation tile to HBM with bulk S2G copies in the swizzled tile-panel
-//     format the backward kernels load back verbatim.
+//   * training mode also stores each layer's bf16 activations to HBM straight from the epilogue registers (coalesced
+//     512-byte warp stores) in the row-block chunk-major layout (mlp_tc.cuh) the dW kernel bulk-loads as an un-swizzled
+//     MN-major operand; only the input panel travels as a bulk S2G copy, once per tile.
+#include <stdlib.h>
+
 #include "mlp_tc.cuh"
 
 namespace nerf {
@@ -107,9 +110,10 @@ __device__ __forceinline__ void sts_16(uint32_t panel_row_addr, int r, int col, 
 
 // Epilogue of one 32-column group: acc + bias (smem) -> LeakyReLU -> bf16 -> swizzled panel row.  Returns the sign mask
 // (bit (15 - k) = element 2k is positive, bit (31 - k) = element 2k+1 is positive, k = 0..15) when kMask.
+// kMask also stores the four packed 16-byte chunks to gsave + j * 1024 (RBCM block, mlp_tc.cuh) unless gsave is null.
 template <bool kMask, bool kHalf>
 __device__ __forceinline__ uint32_t epi_group32(const uint32_t (&acc)[32], uint32_t bias_addr, float alpha,
-                                                uint32_t prow_addr, int r, int chunk_base) {
+                                                uint32_t prow_addr, int r, int chunk_base, uint8_t* gsave) {
   uint32_t mword = 0;
   const uint64_t alpha2 = pack_f32x2(alpha, alpha);
 #pragma unroll
@@ -130,6 +134,7 @@ __device__ __forceinline__ uint32_t epi_group32(const uint32_t (&acc)[32], uint3
       if (kMask) mword |= (~pk[i] >> (4 * j + i)) & (0x80008000u >> (4 * j + i));
     }
     sts128(prow_addr + (((chunk_base + j) ^ (r & 7)) << 4), make_uint4(pk[0], pk[1], pk[2], pk[3]));
+    if (kMask && gsave) stg128(gsave + j * 1024, make_uint4(pk[0], pk[1], pk[2], pk[3]));
   }
   return mword;
 }
@@ -138,7 +143,7 @@ template <bool kSave, bool kHalf>
 __global__ void __launch_bounds__(kThreadsFwd, 1)
 mlp_tc_fwd_kernel(const __grid_constant__ TcPlan plan, const uint8_t* __restrict__ packed,
                   const __grid_constant__ FwdInput in, int64_t M, float* __restrict__ out4, uint8_t* __restrict__ saved,
-                  float alpha) {
+                  float alpha, uint32_t dbg) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t sbase = smem_u32(smem);
   if ((sbase & 1023u) != 0u) __trap();               // swizzled panels need the 1024-byte alignment
@@ -184,6 +189,7 @@ mlp_tc_fwd_kernel(const __grid_constant__ TcPlan plan, const uint8_t* __restrict
                 const uint32_t bytes = min(plan.chunk_bytes[c] - off, (uint32_t)kStageBytes);
                 const uint32_t s = g % kStages, ph = (g / kStages) & 1u;
                 mbar_wait(smem_u32(&bars->empty[s]), ph ^ 1u);
+                if (dbg & kDbgNoWeightCopy) { mbar_arrive(smem_u32(&bars->full[s])); continue; }
                 mbar_arrive_expect_tx(smem_u32(&bars->full[s]), bytes);
                 bulk_g2s(sbase + kSmemStage + s * kStageBytes, packed + plan.chunk_off[c] + off, bytes,
                          smem_u32(&bars->full[s]));
@@ -214,10 +220,12 @@ mlp_tc_fwd_kernel(const __grid_constant__ TcPlan plan, const uint8_t* __restrict
                 mbar_wait(smem_u32(&bars->full[s]), ph);
                 tc_fence_after();
                 const uint32_t b_addr = sbase + kSmemStage + s * kStageBytes;
+                if (!(dbg & kDbgNoMma)) {
 #pragma unroll
-                for (int k = 0; k < 4; ++k)
-                  umma_bf16(d_tmem + (uint32_t)n0, make_desc_kmajor(a_addr + k * 32), make_desc_kmajor(b_addr + k * 32),
-                            idesc, (ci > 0 || k > 0) ? 1u : 0u);
+                  for (int k = 0; k < 4; ++k)
+                    umma_bf16(d_tmem + (uint32_t)n0, make_desc_kmajor(a_addr + k * 32), make_desc_kmajor(b_addr + k * 32),
+                              idesc, (ci > 0 || k > 0) ? 1u : 0u);
+                }
                 umma_commit(smem_u32(&bars->empty[s]));
               }
             }
@@ -295,9 +303,10 @@ mlp_tc_fwd_kernel(const __grid_constant__ TcPlan plan, const uint8_t* __restrict
       mbar_arrive(smem_u32(&bars->act_ready[t]));
       uint8_t* saved_tile = kSave ? saved + (size_t)tile * kSavedTileBytes : nullptr;
       uint32_t* saved_mask = reinterpret_cast<uint32_t*>(saved_tile + (size_t)kSavedPanels * kPanelBytes);
+      const bool do_store = kSave && !(dbg & kDbgNoStore);
       if (kSave) {
         named_bar_sync(bar_id, kEpiThreadsPerTile);
-        if (gtid == 0) {
+        if (gtid == 0 && do_store) {
           bulk_s2g(saved_tile, inp_u32, kPanelBytes);
           bulk_commit();
         }
@@ -310,46 +319,38 @@ mlp_tc_fwd_kernel(const __grid_constant__ TcPlan plan, const uint8_t* __restrict
         mbar_wait(smem_u32(&bars->acc_full[t]), acc_cnt & 1u);
         ++acc_cnt;
         tc_fence_after();
-        if (kSave) {
-          // the previous layer's bulk stores still read the panels this epilogue overwrites
-          if (gtid == 0) bulk_wait_read0();
-          named_bar_sync(bar_id, kEpiThreadsPerTile);
-        }
         if (l < 8) {
           // TMEM loads are double-buffered: group cc+1 is in flight while group cc is processed
           uint32_t acc[2][32];
-          tmem_ld32(taddr + half * 128, acc[0]);
+          // this thread's row inside the RBCM block of h_{l+1}; the chunk index adds j * 1024
+          uint8_t* grow = do_store ? saved_tile + (size_t)saved_panel_h(l + 1) * kPanelBytes + rbcm_offset(r, 0, 32) : nullptr;
+          if (!(dbg & kDbgNoEpi)) tmem_ld32(taddr + half * 128, acc[0]);
 #pragma unroll
           for (int cc = 0; cc < 4; ++cc) {
+            if (dbg & kDbgNoEpi) break;
             const int c0 = half * 128 + cc * 32;
             tmem_ld_wait();
             if (cc + 1 < 4) tmem_ld32(taddr + c0 + 32, acc[(cc + 1) & 1]);
             const uint32_t prow = act_u32 + (c0 >> 6) * kPanelBytes + r * 128;
-            const uint32_t mword = epi_group32<kSave, kHalf>(acc[cc & 1], bias_u32 + c0 * 4, alpha, prow, r, (c0 & 63) >> 3);
-            if (kSave) saved_mask[(l * 8 + (c0 >> 5)) * 128 + r] = mword;
+            const uint32_t mword = epi_group32<kSave, kHalf>(acc[cc & 1], bias_u32 + c0 * 4, alpha, prow, r, (c0 & 63) >> 3,
+                                                             grow ? grow + (c0 >> 3) * 1024 : nullptr);
+            if (do_store) saved_mask[(l * 8 + (c0 >> 5)) * 128 + r] = mword;
           }
           mbar_arrive(smem_u32(&bars->bias_empty[slot]));
           tc_fence_before();
           fence_proxy_async();
           mbar_arrive(smem_u32(&bars->act_ready[t]));
-          if (kSave) {
-            named_bar_sync(bar_id, kEpiThreadsPerTile);
-            if (gtid == 0) {
-              bulk_s2g(saved_tile + (size_t)saved_panel_h(l + 1) * kPanelBytes, act_u32, kActPanels * kPanelBytes);
-              bulk_commit();
-            }
-          }
         } else {
           // last layer: cols 0..127 = last hidden (LeakyReLU), col 128 = sigma (linear); rgb head on CUDA cores.
           // half 0 owns cols 0..63, half 1 owns cols 64..127 and sigma; partial rgb sums meet in the (dead) input panel.
           float rr = 0.f, gg = 0.f, bb = 0.f;
+          uint8_t* grow = do_store ? saved_tile + (size_t)kSavedPanelHL * kPanelBytes + rbcm_offset(r, 0, 16) : nullptr;
 #pragma unroll 1
           for (int cc = 0; cc < 2; ++cc) {
             const int c0 = half * 64 + cc * 32;
             uint32_t acc[32];
             tmem_ld32(taddr + c0, acc);
             tmem_ld_wait();
-            const uint32_t prow = act_u32 + (c0 >> 6) * kPanelBytes + r * 128;
             uint32_t mword = 0;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -370,11 +371,11 @@ mlp_tc_fwd_kernel(const __grid_constant__ TcPlan plan, const uint8_t* __restrict
                 pk[i] = pack_16x2<kHalf>(x0, x1);
                 if (kSave) mword |= (~pk[i] >> (4 * j + i)) & (0x80008000u >> (4 * j + i));
               }
-              if (kSave) sts128(prow + (((((c0 & 63) >> 3) + j) ^ (r & 7)) << 4), make_uint4(pk[0], pk[1], pk[2], pk[3]));
+              if (kSave && grow) stg128(grow + ((c0 >> 3) + j) * 1024, make_uint4(pk[0], pk[1], pk[2], pk[3]));
             }
-            if (kSave) saved_mask[(8 * 8 + (c0 >> 5)) * 128 + r] = mword;
+            if (do_store) saved_mask[(8 * 8 + (c0 >> 5)) * 128 + r] = mword;
           }
-          const uint32_t xch = inp_u32 + r * 16;                  // input panel is dead after this layer's MMAs
+          const uint32_t xch = act_u32 + r * 16;                  // activation panels are dead after this layer's MMAs
           if (half == 1) {
             uint32_t sg[16];
             tmem_ld16(taddr + 128, sg);
@@ -384,18 +385,15 @@ mlp_tc_fwd_kernel(const __grid_constant__ TcPlan plan, const uint8_t* __restrict
           }
           mbar_arrive(smem_u32(&bars->bias_empty[slot]));
           tc_fence_before();
-          if (kSave) fence_proxy_async();
           named_bar_sync(bar_id, kEpiThreadsPerTile);
           if (half == 0 && row_ok) {
             const float4 o = lds128f(xch);
             reinterpret_cast<float4*>(out4)[row] =
                 make_float4(rr + o.x + __ldg(b_rgb + 0), gg + o.y + __ldg(b_rgb + 1), bb + o.z + __ldg(b_rgb + 2), o.w);
           }
-          if (kSave && gtid == 0) {
-            bulk_s2g(saved_tile + (size_t)kSavedPanelHL * kPanelBytes, act_u32, 2 * kPanelBytes);
-            bulk_commit();
-          }
-          // the next pair's prologue overwrites the input panel: everyone must have read the exchange first
+          // the next pair's first epilogue overwrites the exchange rows, its prologue the input panel (whose saved copy,
+          // a bulk S2G issued after this pair's prologue, must have been read out by now)
+          if (kSave && gtid == 0) bulk_wait_read0();
           named_bar_sync(bar_id, kEpiThreadsPerTile);
         }
       }
@@ -408,6 +406,14 @@ mlp_tc_fwd_kernel(const __grid_constant__ TcPlan plan, const uint8_t* __restrict
 }
 
 // ---- host side ----------------------------------------------------------------------------------------------------------------
+uint32_t tc_debug_flags() {
+  static const uint32_t flags = [] {
+    const char* e = getenv("NERF_TC_DEBUG");
+    return e ? (uint32_t)strtoul(e, nullptr, 0) : 0u;
+  }();
+  return flags;
+}
+
 int64_t mlp_tc_saved_bytes(const NetGeom& g, int64_t m) {
   int64_t tiles = (m + kTileM - 1) / kTileM;
   tiles = (tiles + 1) / 2 * 2;
@@ -447,13 +453,13 @@ static int launch_fwd(const nerf_net_cfg* cfg, const NetGeom& g, const void* pac
   if (half) {
     if (saved) { set_error("NERF_MODE_FP16 is a forward-only (render) mode: train in NERF_MODE_BF16"); return NERF_E_UNSUPPORTED; }
     mlp_tc_fwd_kernel<false, true><<<grid, kThreadsFwd, kSmemAlloc, st>>>(
-        plan, (const uint8_t*)packed + half_region_offset(plan), in, m, out4, nullptr, cfg->leaky_alpha);
+        plan, (const uint8_t*)packed + half_region_offset(plan), in, m, out4, nullptr, cfg->leaky_alpha, tc_debug_flags());
   } else if (saved) {
     mlp_tc_fwd_kernel<true, false><<<grid, kThreadsFwd, kSmemAlloc, st>>>(plan, (const uint8_t*)packed, in, m, out4,
-                                                                         (uint8_t*)saved, cfg->leaky_alpha);
+                                                                         (uint8_t*)saved, cfg->leaky_alpha, tc_debug_flags());
   } else {
     mlp_tc_fwd_kernel<false, false><<<grid, kThreadsFwd, kSmemAlloc, st>>>(plan, (const uint8_t*)packed, in, m, out4, nullptr,
-                                                                          cfg->leaky_alpha);
+                                                                          cfg->leaky_alpha, tc_debug_flags());
   }
   NERF_CHECK_LAUNCH();
   return NERF_OK;

@@ -23,23 +23,32 @@ constexpr int kEpiWarps = 16;                     // 8 per tile: 4 TMEM lane qua
 constexpr int kEpiThreadsPerTile = 256;
 constexpr int kWarpProducer = 16, kWarpMma = 17;
 constexpr int kThreadsFwd = 18 * 32;
-// Saved activations of one 128-row tile (forward -> backward), all bf16 panels in the swizzled smem layout:
-//   panel 0            input panel (xyz | view encodings)
-//   panels 1 + 4(l-1)  h_l, l = 1..8 (4 panels each)
-//   panels 33, 34      last hidden (2 panels)
+// Saved activations of one 128-row tile (forward -> backward), bf16:
+//   block 0            input panel (xyz | view encodings), [128 rows][64 cols] in the 128-byte-swizzled smem layout (16 KB)
+//   blocks h_1 .. h_8  64 KB each, "row-block chunk-major" (RBCM): [row half 0/1][16-byte column chunk j][row 0..63][8 cols].
+//                      An epilogue warp (32 consecutive rows, one chunk) stores 512 contiguous bytes straight from its
+//                      registers, and a 64-row K-slab of the block is ONE contiguous 32 KB bulk copy that lands in shared
+//                      memory as the canonical un-swizzled MN-major UMMA operand of the dW kernel (core matrix = 8 rows x
+//                      16 B, SBO = 1024 B between column chunks, LBO = 128 B between 8-row groups)
+//   block h_L          last hidden (128 cols), RBCM with 16 chunks (32 KB)
 //   then uint32 sign masks [9 layers][8 words][128 rows]: bit i of word w = (activation[32 w + i] > 0)
 constexpr int kSavedPanels = 1 + 8 * kActPanels + 2;
 constexpr int kSavedMaskBytes = 9 * 8 * 128 * 4;
 constexpr int kSavedTileBytes = kSavedPanels * kPanelBytes + kSavedMaskBytes;
 __host__ __device__ constexpr int saved_panel_h(int l) { return 1 + (l - 1) * kActPanels; }  // l = 1..8
 constexpr int kSavedPanelHL = 1 + 8 * kActPanels;
-// Backward workspace of one tile (chain kernel -> dW kernel): dZ_1..dZ_8 (4 panels each), dZ_L' (2 panels + the
-// sigma-gradient panel), dOut (1 panel: cols 0..3 = d_out4)
+// byte offset of (row r, 16-byte chunk j) inside an RBCM block with n_chunks column chunks
+__host__ __device__ constexpr uint32_t rbcm_offset(int r, int j, int n_chunks) {
+  return (uint32_t)(r >> 6) * (uint32_t)(n_chunks * 1024) + (uint32_t)j * 1024u + (uint32_t)(r & 63) * 16u;
+}
+// Backward workspace of one tile (chain kernel -> dW kernel), RBCM blocks: dZ_1..dZ_8 (32 chunks each), dZ_L' (24
+// chunks: 0..15 = dZ_L, chunk 16 = [d sigma, 0 ...], 17 zero, 18..23 unused), dOut (8 chunks: chunk 0 = d_out4, 1 zero)
 constexpr int kDzPanels = 8 * kActPanels + 3 + 1;
 constexpr int kDzTileBytes = kDzPanels * kPanelBytes;
 __host__ __device__ constexpr int dz_panel(int l) { return (l - 1) * kActPanels; }            // l = 1..8
 constexpr int kDzPanelL = 8 * kActPanels;
 constexpr int kDzPanelOut = 8 * kActPanels + 3;
+constexpr int kDzChunksL = 24, kDzChunksOut = 8;
 
 // shared memory map (offsets from a 1024-aligned base)
 constexpr int kSmemAct = 0;                                          // [2 tiles][4 panels]
@@ -98,6 +107,20 @@ inline bool make_plan(const NetGeom& g, TcPlan* p) {
 
 
 __device__ __forceinline__ float leaky(float v, float alpha) { return fmaxf(v, 0.f) + alpha * fminf(v, 0.f); }
+
+// Bottleneck-decomposition switches (env NERF_TC_DEBUG, profiling only; results are WRONG when any is set):
+enum : uint32_t {
+  kDbgNoStore = 1u,        // forward / chain: no activation, mask or dZ stores to HBM
+  kDbgNoMma = 2u,          // forward / chain / dW: the MMA issuer only commits
+  kDbgNoWeightCopy = 4u,   // forward / chain: the producer arrives without copying
+  kDbgNoEpi = 8u,          // forward / chain: hidden-layer epilogues skip the TMEM loads, math and stores
+  kDbgNoDrain = 16u,       // dW: no accumulator drain
+  kDbgNoBiasSum = 32u,     // dW: no bias-gradient column sums
+  kDbgNoChain = 64u,       // backward: skip the dX chain launch
+  kDbgNoDw = 128u,         // backward: skip the dW launch
+  kDbgTiming = 256u,       // dW: every CTA prints its cycle count
+};
+uint32_t tc_debug_flags();
 
 // backward half of the bf16 weight pack (defined in mlp_tc_bwd.cu)
 uint32_t bwd_pack_bytes();

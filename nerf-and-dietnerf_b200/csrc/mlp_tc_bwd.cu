@@ -5,11 +5,13 @@
 //      gradient d_out4 is turned into dZ_L (rgb head transposed on CUDA cores, LeakyReLU' from the saved sign masks),
 //      then dH_l = dZ_{l+1} W_l^T runs layer by layer on the tensor cores with the fp32 accumulator in TMEM; the
 //      epilogue applies the LeakyReLU' mask, rounds to bf16 and writes dZ_l back into the same swizzled panels (next A
-//      operand) and, with one bulk S2G copy, to HBM for the weight-gradient pass.  For the fine network two extra
+//      operand) and, straight from its registers with coalesced 512-byte warp stores, to HBM in the row-block
+//      chunk-major layout (mlp_tc.cuh) for the weight-gradient pass.  For the fine network two extra
 //      N=64 steps accumulate d(xyz encoding) = dZ_5 W_4[0:33]^T + dZ_1 W_0^T (the reference does not detach the
 //      importance samples, so this gradient flows on to the coarse network).
-//  (2) mlp_tc_bwd_dw_kernel -- dW_l = A_l^T dZ_{l+1}: the contraction runs over ROWS, so both operands are the
-//      saved [rows][64] panels read as MN-major UMMA operands.  The 148 CTAs are split over (layer, row-range) units;
+//  (2) mlp_tc_bwd_dw_kernel -- dW_l = A_l^T dZ_{l+1}: the contraction runs over ROWS, so both operands are read as
+//      MN-major UMMA operands: a 64-row slab of a saved RBCM block is one contiguous bulk copy and IS the un-swizzled
+//      MN-major operand (the saved input panel keeps the 128-byte-swizzled form).  The 148 CTAs are split over (layer, row-range) units;
 //      each CTA keeps its whole 256x256 fp32 accumulator in TMEM (512 columns) across its row range, the idle epilogue
 //      warps sum the bias gradients from the dZ stages in shared memory, and one fp32 atomic drain per CTA lands the
 //      result in the flat gradient vector.  HBM-bound (128 FLOP/B), see DESIGN.md.
@@ -134,7 +136,7 @@ __device__ __forceinline__ void store_chunk16(uint32_t panel_row_addr, int r, in
 __global__ void __launch_bounds__(kThreadsFwd, 1)
 mlp_tc_bwd_chain_kernel(const __grid_constant__ BwdPlan plan, const uint8_t* __restrict__ packed,
                         const uint8_t* __restrict__ saved, const float* __restrict__ d_out4, int64_t M,
-                        uint8_t* __restrict__ dz_ws, float* __restrict__ d_xyz_enc, int dx, float alpha) {
+                        uint8_t* __restrict__ dz_ws, float* __restrict__ d_xyz_enc, int dx, float alpha, uint32_t dbg) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t sbase = smem_u32(smem);
   if ((sbase & 1023u) != 0u) __trap();
@@ -178,6 +180,7 @@ mlp_tc_bwd_chain_kernel(const __grid_constant__ BwdPlan plan, const uint8_t* __r
                 const uint32_t bytes = min(plan.chunk_bytes[c] - off, (uint32_t)kStageBytes);
                 const uint32_t st = g % kChainStages, ph = (g / kChainStages) & 1u;
                 mbar_wait(smem_u32(&bars->empty[st]), ph ^ 1u);
+                if (dbg & kDbgNoWeightCopy) { mbar_arrive(smem_u32(&bars->full[st])); continue; }
                 mbar_arrive_expect_tx(smem_u32(&bars->full[st]), bytes);
                 bulk_g2s(sbase + kSmemCStage + st * kStageBytes, packed + plan.chunk_off[c] + off, bytes,
                          smem_u32(&bars->full[st]));
@@ -205,10 +208,12 @@ mlp_tc_bwd_chain_kernel(const __grid_constant__ BwdPlan plan, const uint8_t* __r
                 mbar_wait(smem_u32(&bars->full[st]), ph);
                 tc_fence_after();
                 const uint32_t b_addr = sbase + kSmemCStage + st * kStageBytes;
+                if (!(dbg & kDbgNoMma)) {
 #pragma unroll
-                for (int k = 0; k < 4; ++k)
-                  umma_bf16(d_tmem + (uint32_t)n0, make_desc_kmajor(a_addr + k * 32), make_desc_kmajor(b_addr + k * 32),
-                            idesc, (ci > 0 || k > 0) ? 1u : 0u);
+                  for (int k = 0; k < 4; ++k)
+                    umma_bf16(d_tmem + (uint32_t)n0, make_desc_kmajor(a_addr + k * 32), make_desc_kmajor(b_addr + k * 32),
+                              idesc, (ci > 0 || k > 0) ? 1u : 0u);
+                }
                 umma_commit(smem_u32(&bars->empty[st]));
               }
             }
@@ -242,9 +247,11 @@ mlp_tc_bwd_chain_kernel(const __grid_constant__ BwdPlan plan, const uint8_t* __r
       uint32_t mwl[2];
 #pragma unroll
       for (int w = 0; w < 2; ++w) mwl[w] = __ldg(saved_mask + (8 * 8 + half * 2 + w) * 128 + r);
-      if (gtid == 0) bulk_wait_read0();
+      // the previous tile's last epilogue wrote these panel rows from other threads
       named_bar_sync(bar_id, kEpiThreadsPerTile);
+      const bool do_store = !(dbg & kDbgNoStore);
       {
+        uint8_t* gL = dz_tile + (size_t)kDzPanelL * kPanelBytes;
 #pragma unroll
         for (int jg = 0; jg < 8; ++jg) {
           float v[8];
@@ -258,6 +265,7 @@ mlp_tc_bwd_chain_kernel(const __grid_constant__ BwdPlan plan, const uint8_t* __r
           uint4 pk = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]),
                                 pack_bf16x2(v[6], v[7]));
           store_chunk16(act_u32 + half * kPanelBytes + r * 128, r, jg, pk);
+          if (do_store) stg128(gL + rbcm_offset(r, half * 8 + jg, kDzChunksL), pk);
         }
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
@@ -265,16 +273,14 @@ mlp_tc_bwd_chain_kernel(const __grid_constant__ BwdPlan plan, const uint8_t* __r
           if (half == 0) v = make_uint4(c == 0 ? pack_bf16x2(d4.w, 0.f) : 0u, 0u, 0u, 0u);
           else v = make_uint4(c == 0 ? pack_bf16x2(d4.x, d4.y) : 0u, c == 0 ? pack_bf16x2(d4.z, d4.w) : 0u, 0u, 0u);
           store_chunk16(act_u32 + (2 + half) * kPanelBytes + r * 128, r, c, v);
+          if (do_store && c < 2) {                       // the dW pass reads chunks 16, 17 of dZ_L' and 0, 1 of dOut
+            if (half == 0) stg128(gL + rbcm_offset(r, 16 + c, kDzChunksL), v);
+            else stg128(dz_tile + (size_t)kDzPanelOut * kPanelBytes + rbcm_offset(r, c, kDzChunksOut), v);
+          }
         }
       }
       fence_proxy_async();
       mbar_arrive(smem_u32(&bars->act_ready[t]));
-      named_bar_sync(bar_id, kEpiThreadsPerTile);
-      if (gtid == 0) {
-        bulk_s2g(dz_tile + (size_t)kDzPanelL * kPanelBytes, act_u32, 3 * kPanelBytes);
-        bulk_s2g(dz_tile + (size_t)kDzPanelOut * kPanelBytes, act_u32 + 3 * kPanelBytes, kPanelBytes);
-        bulk_commit();
-      }
       float xs[32];                                      // d(xyz encoding): half 0 -> cols 0..31, half 1 -> cols 32..39
 #pragma unroll
       for (int i = 0; i < 32; ++i) xs[i] = 0.f;
@@ -293,12 +299,12 @@ mlp_tc_bwd_chain_kernel(const __grid_constant__ BwdPlan plan, const uint8_t* __r
         ++acc_cnt;
         tc_fence_after();
         if (kind == STEP_MASK) {
-          if (gtid == 0) bulk_wait_read0();
-          named_bar_sync(bar_id, kEpiThreadsPerTile);
           uint32_t acc[2][32];
-          tmem_ld32(taddr + half * 128, acc[0]);
+          uint8_t* grow = dz_tile + (size_t)dz_panel(l) * kPanelBytes + rbcm_offset(r, 0, 32);
+          if (!(dbg & kDbgNoEpi)) tmem_ld32(taddr + half * 128, acc[0]);
 #pragma unroll
           for (int cc = 0; cc < 4; ++cc) {
+            if (dbg & kDbgNoEpi) break;
             const int c0 = half * 128 + cc * 32;
             tmem_ld_wait();
             if (cc + 1 < 4) tmem_ld32(taddr + c0 + 32, acc[(cc + 1) & 1]);
@@ -316,16 +322,12 @@ mlp_tc_bwd_chain_kernel(const __grid_constant__ BwdPlan plan, const uint8_t* __r
               uint4 pk = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]),
                                     pack_bf16x2(v[6], v[7]));
               store_chunk16(prow, r, ((c0 & 63) >> 3) + j, pk);
+              if (do_store) stg128(grow + ((c0 >> 3) + j) * 1024, pk);
             }
           }
           tc_fence_before();
           fence_proxy_async();
           if (s != last_step) mbar_arrive(smem_u32(&bars->act_ready[t]));
-          named_bar_sync(bar_id, kEpiThreadsPerTile);
-          if (gtid == 0) {
-            bulk_s2g(dz_tile + (size_t)dz_panel(l) * kPanelBytes, act_u32, kActPanels * kPanelBytes);
-            bulk_commit();
-          }
         } else {
           if (half == 0) {
             uint32_t a0[32];
@@ -352,7 +354,6 @@ mlp_tc_bwd_chain_kernel(const __grid_constant__ BwdPlan plan, const uint8_t* __r
         }
       }
     }
-    if (gtid == 0) bulk_wait0();
   }
   tc_fence_before();
   __syncthreads();
@@ -364,8 +365,22 @@ mlp_tc_bwd_chain_kernel(const __grid_constant__ BwdPlan plan, const uint8_t* __r
 // =====================================================================================================================
 enum : int { OUT_MAIN = 0, OUT_D8A = 1, OUT_INP_XYZ = 2, OUT_INP_VIEW = 3, OUT_D9 = 4 };
 
+constexpr int kDwMaxStages = 10;
+constexpr int kDwRingBytes = 196608;
+constexpr int kDwOperandBytes = 32768;           // 64 rows x 256 columns bf16: the largest operand slab
+constexpr int kDwHalf = 8192;                    // 64 rows of the swizzled input panel
 struct DwUnit {
-  int16_t a_panel, a_panels, b_panel, b_panels, n, m_blocks, out_kind, dense, has_bias, first_cta, n_ctas;
+  int32_t a_off;          // byte offset of the A block inside a saved tile
+  int32_t b_off;          // byte offset of the B block inside a dZ-workspace tile
+  int16_t a_inp;          // 1: A = saved input panel (128-byte-swizzled [128][64]); 0: RBCM block
+  int16_t a_chunks;       // column chunks of the A block (RBCM): 32 (h_l) or 16 (h_L)
+  int16_t b_chunks;       // column chunks of the B block (its half stride)
+  int16_t b_load;         // chunks actually loaded = ceil(n / 8)
+  int16_t n, m_blocks, out_kind, dense, has_bias, first_cta, n_ctas;
+  int16_t stages;         // ring depth: as many (A slab | B slab) stages as fit in the 192 KB ring, at most kDwMaxStages
+  int32_t a_region;       // bytes reserved for the A slab inside a stage (the B slab follows)
+  int32_t stage_bytes;
+  float cost;             // modelled time per 64-row stage, the unit of the CTA allocation
 };
 struct DwPlan {
   DwUnit u[16];
@@ -375,47 +390,63 @@ struct DwPlan {
 static void make_dw_plan(DwPlan* p, int n_ctas_total) {
   memset(p, 0, sizeof(*p));
   int n = 0;
-  auto add = [&](int a_panel, int a_panels, int b_panel, int b_panels, int nn, int out_kind, int dense, int has_bias) {
+  auto add = [&](int a_panel, int a_chunks, int b_panel, int b_chunks, int nn, int out_kind, int dense, int has_bias) {
     DwUnit& u = p->u[n++];
-    u.a_panel = (int16_t)a_panel; u.a_panels = (int16_t)a_panels; u.b_panel = (int16_t)b_panel;
-    u.b_panels = (int16_t)b_panels; u.n = (int16_t)nn; u.m_blocks = (int16_t)(a_panels == 4 ? 2 : 1);
+    u.a_off = a_panel * kPanelBytes; u.a_inp = (int16_t)(a_chunks == 0); u.a_chunks = (int16_t)a_chunks;
+    u.b_off = b_panel * kPanelBytes; u.b_chunks = (int16_t)b_chunks; u.n = (int16_t)nn; u.b_load = (int16_t)((nn + 7) / 8);
+    u.m_blocks = (int16_t)(a_chunks == 32 ? 2 : 1);
     u.out_kind = (int16_t)out_kind; u.dense = (int16_t)dense; u.has_bias = (int16_t)has_bias;
+    // input-panel units: 8 KB of data + 8 KB that stay zero (the second 64-column MN block of the M = 128 operand)
+    u.a_region = a_chunks == 0 ? 2 * kDwHalf : a_chunks * 1024;
+    u.stage_bytes = u.a_region + u.b_load * 1024;
+    int st = kDwRingBytes / u.stage_bytes;
+    u.stages = (int16_t)(st > kDwMaxStages ? kDwMaxStages : st);
+    // measured per-CTA cycle counts (NERF_TC_DEBUG=320, all 148 CTAs streaming): a 64-row stage costs ~26 cycles per KB
+    // plus ~700 cycles that do not shrink with the ring depth -> a 27 KB-equivalent overhead per stage
+    u.cost = (float)((a_chunks == 0 ? 8 : a_chunks) + u.b_load) + 27.f;
   };
   // Dense l (input h_l, or the input panel) with the gradient of its pre-activation output dZ_{l+1}
-  add(0, 1, dz_panel(1), 4, 256, OUT_INP_XYZ, 0, 1);                                  // Dense 0
-  for (int l = 1; l <= 7; ++l) add(saved_panel_h(l), 4, dz_panel(l + 1), 4, 256, OUT_MAIN, l, 1);  // Dense 1..7 (4: h4 rows)
-  add(0, 1, dz_panel(5), 4, 256, OUT_INP_XYZ, 4, 0);                                  // Dense 4, xyz rows
-  add(saved_panel_h(8), 4, kDzPanelL, 3, 144, OUT_D8A, 8, 1);                          // Dense 8 + sigma head, h8 rows
-  add(0, 1, kDzPanelL, 3, 144, OUT_INP_VIEW, 8, 0);                                    // Dense 8 + sigma head, view rows
-  add(kSavedPanelHL, 2, kDzPanelOut, 1, 16, OUT_D9, 9, 1);                             // rgb head
+  add(0, 0, dz_panel(1), 32, 256, OUT_INP_XYZ, 0, 1);                                  // Dense 0
+  for (int l = 1; l <= 7; ++l) add(saved_panel_h(l), 32, dz_panel(l + 1), 32, 256, OUT_MAIN, l, 1);  // Dense 1..7 (4: h4 rows)
+  add(0, 0, dz_panel(5), 32, 256, OUT_INP_XYZ, 4, 0);                                  // Dense 4, xyz rows
+  add(saved_panel_h(8), 32, kDzPanelL, kDzChunksL, 144, OUT_D8A, 8, 1);                // Dense 8 + sigma head, h8 rows
+  add(0, 0, kDzPanelL, kDzChunksL, 144, OUT_INP_VIEW, 8, 0);                           // Dense 8 + sigma head, view rows
+  add(kSavedPanelHL, 16, kDzPanelOut, kDzChunksOut, 16, OUT_D9, 9, 1);                 // rgb head
   p->n_units = n;
-  // CTAs proportional to the bytes a unit streams per tile
-  int bytes[16], total = 0;
-  for (int i = 0; i < n; ++i) { bytes[i] = p->u[i].a_panels + p->u[i].b_panels; total += bytes[i]; }
+  // CTAs in proportion to the modelled cost (largest-remainder rounding, at least one each)
+  float total = 0.f;
+  for (int i = 0; i < n; ++i) total += p->u[i].cost;
   int used = 0;
+  float frac[16];
   for (int i = 0; i < n; ++i) {
-    int c = (int)((int64_t)n_ctas_total * bytes[i] / total);
+    const float share = (float)n_ctas_total * p->u[i].cost / total;
+    int c = (int)share;
     if (c < 1) c = 1;
+    frac[i] = share - (float)c;
     p->u[i].n_ctas = (int16_t)c;
     used += c;
   }
-  for (int i = 0; used < n_ctas_total; i = (i + 1) % n) {   // hand out the remainder to the heaviest units first
-    if (p->u[i].a_panels == 4) { p->u[i].n_ctas++; ++used; }
+  while (used < n_ctas_total) {
+    int best = 0;
+    for (int i = 1; i < n; ++i) if (frac[i] > frac[best]) best = i;
+    p->u[best].n_ctas++; frac[best] -= 1.f; ++used;
+  }
+  while (used > n_ctas_total) {
+    int best = -1;
+    for (int i = 0; i < n; ++i) if (p->u[i].n_ctas > 1 && (best < 0 || frac[i] < frac[best])) best = i;
+    p->u[best].n_ctas--; frac[best] += 1.f; --used;
   }
   int first = 0;
   for (int i = 0; i < n; ++i) { p->u[i].first_cta = (int16_t)first; first += p->u[i].n_ctas; }
 }
 
-constexpr int kDwStages = 3;
-constexpr int kDwHalf = 8192;                    // one panel restricted to 64 rows
-constexpr int kDwStageBytes = 8 * kDwHalf;       // 4 A slots + 4 B slots
-constexpr int kSmemDwBar = kDwStages * kDwStageBytes;
+constexpr int kSmemDwBar = kDwRingBytes;
 constexpr int kSmemDwAlloc = kSmemDwBar + 256;
 static_assert(kSmemDwAlloc <= 232448, "dW kernel exceeds the 227 KB shared-memory limit");
 constexpr int kThreadsDw = 192;
 
 struct DwBars {
-  uint64_t full[kDwStages], empty[kDwStages], acc_full;
+  uint64_t full[kDwMaxStages], empty[kDwMaxStages], acc_full;
   uint32_t tmem_base;
 };
 
@@ -463,7 +494,7 @@ __device__ __forceinline__ float* db_target(const DwUnit& u, const NetGeom& g, f
 __global__ void __launch_bounds__(kThreadsDw, 1)
 mlp_tc_bwd_dw_kernel(const __grid_constant__ DwPlan plan, const __grid_constant__ NetGeom g,
                      const uint8_t* __restrict__ saved, const uint8_t* __restrict__ dz_ws, int64_t M,
-                     float* __restrict__ G) {
+                     float* __restrict__ G, uint32_t dbg) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t sbase = smem_u32(smem);
   if ((sbase & 1023u) != 0u) __trap();
@@ -479,13 +510,14 @@ mlp_tc_bwd_dw_kernel(const __grid_constant__ DwPlan plan, const __grid_constant_
   const int64_t tb = min(n_tiles, split * per), te = min(n_tiles, (split + 1) * per);
   if (tb >= te) return;                       // whole CTA leaves together: nothing to do for this split
   const uint32_t n_stages_total = (uint32_t)(te - tb) * 2u;
+  const long long t_start = clock64();
 
   // zero the operand slots once: the unused second A block of the input-panel units must read as zeros
-  for (int i = threadIdx.x; i < kDwStages * kDwStageBytes / 16; i += blockDim.x)
+  for (int i = threadIdx.x; i < kDwRingBytes / 16; i += blockDim.x)
     reinterpret_cast<uint4*>(smem)[i] = make_uint4(0u, 0u, 0u, 0u);
   fence_proxy_async();
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kDwStages; ++s) { mbar_init(smem_u32(&bars->full[s]), 1); mbar_init(smem_u32(&bars->empty[s]), 5); }
+    for (int s = 0; s < kDwMaxStages; ++s) { mbar_init(smem_u32(&bars->full[s]), 1); mbar_init(smem_u32(&bars->empty[s]), 5); }
     mbar_init(smem_u32(&bars->acc_full), 1);
     fence_barrier_init();
   }
@@ -494,24 +526,24 @@ mlp_tc_bwd_dw_kernel(const __grid_constant__ DwPlan plan, const __grid_constant_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = bars->tmem_base;
-  const uint32_t stage_tx = (uint32_t)(u.a_panels + u.b_panels) * kDwHalf;
+  const uint32_t a_bytes = u.a_inp ? (uint32_t)kDwHalf : (uint32_t)u.a_chunks * 1024u;   // per 64-row slab
+  const uint32_t b_bytes = (uint32_t)u.b_load * 1024u, b_half_stride = (uint32_t)u.b_chunks * 1024u;
+  const uint32_t n_ring = (uint32_t)u.stages, stage_bytes = (uint32_t)u.stage_bytes, a_region = (uint32_t)u.a_region;
 
   if (warp == 4) {
     if (lane == 0) {
       uint32_t gi = 0;
       for (int64_t tile = tb; tile < te; ++tile) {
-        const uint8_t* a_src = saved + (size_t)tile * kSavedTileBytes + (size_t)u.a_panel * kPanelBytes;
-        const uint8_t* b_src = dz_ws + (size_t)tile * kDzTileBytes + (size_t)u.b_panel * kPanelBytes;
+        const uint8_t* a_src = saved + (size_t)tile * kSavedTileBytes + (size_t)u.a_off;
+        const uint8_t* b_src = dz_ws + (size_t)tile * kDzTileBytes + (size_t)u.b_off;
         for (int half = 0; half < 2; ++half, ++gi) {
-          const uint32_t st = gi % kDwStages, ph = (gi / kDwStages) & 1u;
+          const uint32_t st = gi % n_ring, ph = (gi / n_ring) & 1u;
           mbar_wait(smem_u32(&bars->empty[st]), ph ^ 1u);
           const uint32_t fb = smem_u32(&bars->full[st]);
-          mbar_arrive_expect_tx(fb, stage_tx);
-          const uint32_t dst = sbase + st * kDwStageBytes;
-          for (int p = 0; p < u.a_panels; ++p)
-            bulk_g2s(dst + p * kDwHalf, a_src + (size_t)p * kPanelBytes + half * kDwHalf, kDwHalf, fb);
-          for (int p = 0; p < u.b_panels; ++p)
-            bulk_g2s(dst + (4 + p) * kDwHalf, b_src + (size_t)p * kPanelBytes + half * kDwHalf, kDwHalf, fb);
+          mbar_arrive_expect_tx(fb, a_bytes + b_bytes);
+          const uint32_t dst = sbase + st * stage_bytes;
+          bulk_g2s(dst, a_src + (size_t)half * a_bytes, a_bytes, fb);
+          bulk_g2s(dst + a_region, b_src + (size_t)half * b_half_stride, b_bytes, fb);
         }
       }
     }
@@ -519,15 +551,17 @@ mlp_tc_bwd_dw_kernel(const __grid_constant__ DwPlan plan, const __grid_constant_
     if (lane == 0) {
       const uint32_t idesc = make_idesc(u.n, 1, 1);
       for (uint32_t gi = 0; gi < n_stages_total; ++gi) {
-        const uint32_t st = gi % kDwStages, ph = (gi / kDwStages) & 1u;
+        const uint32_t st = gi % n_ring, ph = (gi / n_ring) & 1u;
         mbar_wait(smem_u32(&bars->full[st]), ph);
         tc_fence_after();
-        const uint32_t base = sbase + st * kDwStageBytes;
+        const uint32_t base = sbase + st * stage_bytes;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const uint64_t b_desc = make_desc(base + 4 * kDwHalf + k * 2048, kDwHalf, 1024);
+        for (int k = 0; k < 4; ++k) {                       // K = 16 rows per MMA
+          if (dbg & kDbgNoMma) break;
+          const uint64_t b_desc = make_desc_mn_nosw(base + a_region + k * 256, 128, 1024);
           for (int mb = 0; mb < u.m_blocks; ++mb) {
-            const uint64_t a_desc = make_desc(base + 2 * mb * kDwHalf + k * 2048, kDwHalf, 1024);
+            const uint64_t a_desc = u.a_inp ? make_desc(base + k * 2048, kDwHalf, 1024)
+                                            : make_desc_mn_nosw(base + mb * 16 * 1024 + k * 256, 128, 1024);
             umma_bf16(tmem_base + (uint32_t)mb * 256u, a_desc, b_desc, idesc, (gi > 0 || k > 0) ? 1u : 0u);
           }
         }
@@ -536,30 +570,28 @@ mlp_tc_bwd_dw_kernel(const __grid_constant__ DwPlan plan, const __grid_constant_
       umma_commit(smem_u32(&bars->acc_full));
     }
   } else {
-    // warps 0..3: bias-gradient column sums from the dZ stages, then the accumulator drain
-    const int tid = threadIdx.x;                       // 0..127, owns columns 2*tid, 2*tid+1
+    // warps 0..3: bias-gradient column sums from the dZ slabs, then the accumulator drain
+    const int tid = threadIdx.x;                       // 0..127, owns columns 2*tid, 2*tid+1 = chunk tid/4, word tid%4
     const int c = 2 * tid;
     const bool col_ok = u.has_bias && c < u.n;
     float s0 = 0.f, s1 = 0.f;
     for (uint32_t gi = 0; gi < n_stages_total; ++gi) {
-      const uint32_t st = gi % kDwStages, ph = (gi / kDwStages) & 1u;
+      const uint32_t st = gi % n_ring, ph = (gi / n_ring) & 1u;
       mbar_wait(smem_u32(&bars->full[st]), ph);
-      if (col_ok) {
-        // columns (c, c+1) of the dZ stage: one 32-bit word per row; (row & 7) selects the swizzled 16-byte chunk
-        const uint32_t pb = sbase + st * kDwStageBytes + (4 + (c >> 6)) * kDwHalf + ((c & 7) << 1);
-        const uint32_t ch = (uint32_t)(c & 63) >> 3;
+      if (col_ok && !(dbg & kDbgNoBiasSum)) {
+        // slab layout [chunk][row][16 B]: rows are visited rotated by (chunk & 7) so that the 8 chunks of a warp hit
+        // 8 different bank groups
+        const uint32_t pb = sbase + st * stage_bytes + a_region + (uint32_t)(tid >> 2) * 1024u + (uint32_t)(tid & 3) * 4u;
+        const uint32_t rot = (uint32_t)(tid >> 2) & 7u;
         float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f;
-#pragma unroll
-        for (int r8 = 0; r8 < 8; ++r8) {
-#pragma unroll
-          for (int j = 0; j < 8; j += 2) {
-            const uint32_t w0 = lds32u(pb + (r8 * 8 + j) * 128 + ((ch ^ (uint32_t)j) << 4));
-            const uint32_t w1 = lds32u(pb + (r8 * 8 + j + 1) * 128 + ((ch ^ (uint32_t)(j + 1)) << 4));
-            a0 += __uint_as_float(w0 << 16);
-            a1 += __uint_as_float(w0 & 0xffff0000u);
-            b0 += __uint_as_float(w1 << 16);
-            b1 += __uint_as_float(w1 & 0xffff0000u);
-          }
+#pragma unroll 8
+        for (uint32_t i = 0; i < 64; i += 2) {
+          const uint32_t w0 = lds32u(pb + (((i + rot) & 63u) << 4));
+          const uint32_t w1 = lds32u(pb + (((i + 1 + rot) & 63u) << 4));
+          a0 += __uint_as_float(w0 << 16);
+          a1 += __uint_as_float(w0 & 0xffff0000u);
+          b0 += __uint_as_float(w1 << 16);
+          b1 += __uint_as_float(w1 & 0xffff0000u);
         }
         s0 += a0 + b0;
         s1 += a1 + b1;
@@ -577,6 +609,7 @@ mlp_tc_bwd_dw_kernel(const __grid_constant__ DwPlan plan, const __grid_constant_
     tc_fence_after();
     const int q = warp;  // TMEM lane quarter
     for (int mb = 0; mb < u.m_blocks; ++mb) {
+      if (dbg & kDbgNoDrain) break;
       const int k = mb * 128 + q * 32 + lane;
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)mb * 256u;
       for (int c0 = 0; c0 < u.n; c0 += 16) {
@@ -591,6 +624,11 @@ mlp_tc_bwd_dw_kernel(const __grid_constant__ DwPlan plan, const __grid_constant_
       }
     }
     tc_fence_before();
+    if ((dbg & kDbgTiming) && threadIdx.x == 0) {
+      const long long t_acc = clock64();
+      printf("dw cta %3d unit %2d (dense %d kind %d) tiles %4d  cycles %8lld\n", blockIdx.x, ui, u.dense, u.out_kind, (int)(te - tb),
+             t_acc - t_start);
+    }
   }
   __syncthreads();
   if (warp == 5) tmem_dealloc(tmem_base, 512);
@@ -618,13 +656,18 @@ int mlp_tc_bwd(const nerf_net_cfg* cfg, const NetGeom& g, const float* params, c
   uint8_t* dz_ws = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(workspace) + 1023) & ~(uintptr_t)1023);
   int64_t n_pairs = ((m + kTileM - 1) / kTileM + 1) / 2;
   int grid = (int)(n_pairs < kNumSMs ? n_pairs : kNumSMs);
-  mlp_tc_bwd_chain_kernel<<<grid, kThreadsFwd, kSmemCAlloc, st>>>(bplan, packed_bwd, (const uint8_t*)saved, d_out4, m,
-                                                                 dz_ws, d_xyz_enc, g.dx, cfg->leaky_alpha);
-  NERF_CHECK_LAUNCH();
+  const uint32_t dbg = tc_debug_flags();
+  if (!(dbg & kDbgNoChain)) {
+    mlp_tc_bwd_chain_kernel<<<grid, kThreadsFwd, kSmemCAlloc, st>>>(bplan, packed_bwd, (const uint8_t*)saved, d_out4, m,
+                                                                   dz_ws, d_xyz_enc, g.dx, cfg->leaky_alpha, dbg);
+    NERF_CHECK_LAUNCH();
+  }
   DwPlan dplan;
   make_dw_plan(&dplan, kNumSMs);
-  mlp_tc_bwd_dw_kernel<<<kNumSMs, kThreadsDw, kSmemDwAlloc, st>>>(dplan, g, (const uint8_t*)saved, dz_ws, m, grads);
-  NERF_CHECK_LAUNCH();
+  if (!(dbg & kDbgNoDw)) {
+    mlp_tc_bwd_dw_kernel<<<kNumSMs, kThreadsDw, kSmemDwAlloc, st>>>(dplan, g, (const uint8_t*)saved, dz_ws, m, grads, dbg);
+    NERF_CHECK_LAUNCH();
+  }
   return NERF_OK;
 }
 

@@ -147,6 +147,19 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t lbo_b
   return d;
 }
 __device__ __forceinline__ uint64_t make_desc_kmajor(uint32_t smem_addr) { return make_desc(smem_addr, 16, 1024); }
+// Un-swizzled (INTERLEAVE) MN-major operand: core matrices of 8 k-rows x 16 B (8 MN elements) stored contiguously;
+// SBO = byte stride between 8-element MN blocks, LBO = byte stride between 8-row k groups.
+__device__ __forceinline__ uint64_t make_desc_mn_nosw(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;                              // descriptor version 1 (Blackwell); layout type 0 = no swizzle
+  return d;
+}
+__device__ __forceinline__ void stg128(void* p, uint4 v) {
+  asm volatile("st.global.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
 
 // Instruction descriptor for kind::f16: bf16 x bf16 -> fp32, M = 128, N = n.  a_major/b_major: 0 = K-major, 1 = MN-major.
 // operand_fmt: 1 = bf16 (default), 0 = fp16.
