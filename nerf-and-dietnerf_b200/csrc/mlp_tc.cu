@@ -24,8 +24,35 @@ namespace nerf {
 
 // ---- weight packing -----------------------------------------------------------------------------------------------------
 // One thread per bf16 element of every chunk, plus the fp32 tail (biases, rgb head).
+// hi/lo split of an fp32 bias into two 16-bit values (bf16 or fp16) whose sum carries ~16 mantissa bits
+template <typename T16>
+__device__ __forceinline__ void split_bias(float b, T16* hi, T16* lo);
+template <>
+__device__ __forceinline__ void split_bias<__nv_bfloat16>(float b, __nv_bfloat16* hi, __nv_bfloat16* lo) {
+  *hi = __float2bfloat16_rn(b);
+  *lo = __float2bfloat16_rn(b - __bfloat162float(*hi));
+}
+template <>
+__device__ __forceinline__ void split_bias<__half>(float b, __half* hi, __half* lo) {
+  *hi = __float2half_rn(b);
+  *lo = __float2half_rn(b - __half2float(*hi));
+}
+
+__device__ __forceinline__ float layer_bias(const NetGeom& g, const float* P, int layer, int n) {
+  if (layer < 8) return P[g.layers[layer].b_off + n];
+  if (n < 128) return P[g.layers[8].b_off + n];
+  if (n == 128) return P[g.layers[10].b_off];       // sigma head shares the [h8 ; view] input
+  return 0.f;
+}
+
+template <typename T16>
+__device__ __forceinline__ T16 to16(float v);
+template <> __device__ __forceinline__ __nv_bfloat16 to16<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+template <> __device__ __forceinline__ __half to16<__half>(float v) { return __float2half_rn(v); }
+
+template <typename T16>
 __global__ void pack_weights_kernel(const __grid_constant__ TcPlan plan, NetGeom g, const float* __restrict__ P,
-                                    uint8_t* __restrict__ packed, int as_half) {
+                                    uint8_t* __restrict__ packed) {
   const int chunk = blockIdx.y;
   if (chunk < plan.n_chunks) {
     // find the layer of this chunk
@@ -33,9 +60,19 @@ __global__ void pack_weights_kernel(const __grid_constant__ TcPlan plan, NetGeom
     while (!(chunk >= plan.layer_first[layer] && chunk < plan.layer_first[layer] + plan.layer_nchunks[layer])) ++layer;
     const int n_rows = plan.layer_n[layer];
     const int e = blockIdx.x * blockDim.x + threadIdx.x;  // element index within [n_rows][64]
+    const int src = plan.a_src[chunk];
+    if (src == 5) {
+      // bias slab [256][16], un-swizzled K-major: core matrices of 8 rows x 16 B; k = input-panel column - 32
+      if (e >= 256 * 16) return;
+      const int n = e >> 4, k = e & 15;
+      T16 hi, lo;
+      split_bias<T16>(n < n_rows ? layer_bias(g, P, layer, n) : 0.f, &hi, &lo);
+      const T16 v = (k == kInpOneCol - 32) ? hi : (k == kInpOneCol + 1 - 32) ? lo : to16<T16>(0.f);
+      *reinterpret_cast<T16*>(packed + plan.chunk_off[chunk] + (n >> 3) * 256 + (k >> 3) * 128 + (n & 7) * 16 + (k & 7) * 2) = v;
+      return;
+    }
     if (e >= n_rows * 64) return;
     const int n = e >> 6, k = e & 63;
-    const int src = plan.a_src[chunk];
     // source Dense layer and output column
     int dense = layer, col = n;
     bool valid = true;
@@ -53,39 +90,37 @@ __global__ void pack_weights_kernel(const __grid_constant__ TcPlan plan, NetGeom
       if (layer == 0 || layer == 4) { if (k < g.dx) row = k; }                       // xyz columns
       else if (layer == 8) { if (k >= kInpViewCol && k < kInpViewCol + g.dv) row = g.hidden + (k - kInpViewCol); }
     }
-    float v = 0.f;
+    T16 v = to16<T16>(0.f);
     if (valid && row >= 0) {
       const LayerDesc& L = g.layers[dense];
-      v = P[L.w_off + (int64_t)row * L.out + col];
+      v = to16<T16>(P[L.w_off + (int64_t)row * L.out + col]);
     }
-    if (as_half)
-      *reinterpret_cast<__half*>(packed + plan.chunk_off[chunk] + panel_offset(n, k)) = __float2half_rn(v);
-    else
-      *reinterpret_cast<__nv_bfloat16*>(packed + plan.chunk_off[chunk] + panel_offset(n, k)) = __float2bfloat16_rn(v);
+    if (src == 4 && (k == kInpOneCol || k == kInpOneCol + 1)) {   // the constant-1 columns meet the bias
+      T16 hi, lo;
+      split_bias<T16>(layer_bias(g, P, layer, n), &hi, &lo);
+      v = (k == kInpOneCol) ? hi : lo;
+    }
+    *reinterpret_cast<T16*>(packed + plan.chunk_off[chunk] + panel_offset(n, k)) = v;
   } else {
-    // fp32 tail
+    // fp32 tail: rgb head
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
-    float* bias = reinterpret_cast<float*>(packed + plan.bias_off);
-    if (e < 9 * 256) {
-      int l = e >> 8, n = e & 255;
-      float v = 0.f;
-      if (l < 8) v = P[g.layers[l].b_off + n];
-      else if (n < 128) v = P[g.layers[8].b_off + n];
-      else if (n == 128) v = P[g.layers[10].b_off];
-      bias[e] = v;
-    }
-    if (e < 128) {
-      const LayerDesc& L = g.layers[9];
+    const LayerDesc& L = g.layers[9];
+    if (e < 128)
       reinterpret_cast<float4*>(packed + plan.w_rgb_off)[e] =
           make_float4(P[L.w_off + e * 3 + 0], P[L.w_off + e * 3 + 1], P[L.w_off + e * 3 + 2], 0.f);
-    }
-    if (e < 4) reinterpret_cast<float*>(packed + plan.b_rgb_off)[e] = e < 3 ? P[g.layers[9].b_off + e] : 0.f;
+    if (e == 128) reinterpret_cast<float4*>(packed + plan.w_rgb_off)[128] = make_float4(P[L.b_off], P[L.b_off + 1], P[L.b_off + 2], 0.f);
   }
 }
 
 // ---- forward kernel --------------------------------------------------------------------------------------------------------
+// NERF_TC_DEBUG & kDbgTiming: CTA 0 records the clock of its first handshake events and prints the timeline at exit
+__device__ long long g_trace[3][160];
+__device__ __forceinline__ void trace(bool on, int who, int& n, int code) {
+  if (on && n < 160) { g_trace[who][n] = (clock64() << 8) | (long long)(code & 255); ++n; }
+}
+
 struct FwdBars {
-  uint64_t full[kStages], empty[kStages], act_ready[2], acc_full[2], bias_full[2], bias_empty[2];
+  uint64_t full[kStages], empty[kStages], act_ready[2], acc_full[2];
   uint32_t tmem_base;
 };
 
@@ -108,35 +143,41 @@ __device__ __forceinline__ void sts_16(uint32_t panel_row_addr, int r, int col, 
   asm volatile("st.shared.b16 [%0], %1;" ::"r"(addr), "h"((uint16_t)(both & 0xffffu)) : "memory");
 }
 
-// Epilogue of one 32-column group: acc + bias (smem) -> LeakyReLU -> bf16 -> swizzled panel row.  Returns the sign mask
-// (bit (15 - k) = element 2k is positive, bit (31 - k) = element 2k+1 is positive, k = 0..15) when kMask.
-// kMask also stores the four packed 16-byte chunks to gsave + j * 1024 (RBCM block, mlp_tc.cuh) unless gsave is null.
+// Sign bits of 32 packed 16-bit values (8 words u[k] = high bytes of elements 4k..4k+3, from PRMT):
+// element e lands in bit 8 (e & 3) + 7 - (e >> 2); a SET bit means NEGATIVE (LeakyReLU' = alpha).
+__device__ __forceinline__ uint32_t hi_bytes(uint32_t a, uint32_t b) { return __byte_perm(a, b, 0x7531); }
+__device__ __forceinline__ uint32_t neg_mask32(const uint32_t (&u)[8]) {
+  uint32_t m = u[0] & 0x80808080u;
+#pragma unroll
+  for (int k = 1; k < 8; ++k) m |= (u[k] & 0x80808080u) >> k;
+  return m;
+}
+
+// Epilogue of one 32-column group: acc (bias already inside, it rode in the MMA) -> LeakyReLU -> 16-bit -> swizzled
+// panel row.  kMask: returns the negative-sign mask and also stores the four packed 16-byte chunks to
+// gsave + j * 1024 (RBCM block, mlp_tc.cuh) unless gsave is null.
 template <bool kMask, bool kHalf>
-__device__ __forceinline__ uint32_t epi_group32(const uint32_t (&acc)[32], uint32_t bias_addr, float alpha,
-                                                uint32_t prow_addr, int r, int chunk_base, uint8_t* gsave) {
-  uint32_t mword = 0;
+__device__ __forceinline__ uint32_t epi_group32(const uint32_t (&acc)[32], float alpha, uint32_t prow_addr, int r,
+                                                int chunk_base, uint8_t* gsave) {
+  uint32_t u[8];
   const uint64_t alpha2 = pack_f32x2(alpha, alpha);
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
-    const float4 b0 = lds128f(bias_addr + 32 * j);
-    const float4 b1 = lds128f(bias_addr + 32 * j + 16);
-    const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
     uint32_t pk[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      const uint64_t x = add_f32x2(pack_f32x2(__uint_as_float(acc[8 * j + 2 * i]), __uint_as_float(acc[8 * j + 2 * i + 1])),
-                                   pack_f32x2(bb[2 * i], bb[2 * i + 1]));
+      const uint64_t x = pack_f32x2(__uint_as_float(acc[8 * j + 2 * i]), __uint_as_float(acc[8 * j + 2 * i + 1]));
       const uint64_t lo = mul_f32x2(x, alpha2);
       float x0, x1, l0, l1;
       unpack_f32x2(x, x0, x1);
       unpack_f32x2(lo, l0, l1);
       pk[i] = pack_16x2<kHalf>(fmaxf(x0, l0), fmaxf(x1, l1)); // LeakyReLU for 0 <= alpha <= 1
-      if (kMask) mword |= (~pk[i] >> (4 * j + i)) & (0x80008000u >> (4 * j + i));
     }
+    if (kMask) { u[2 * j] = hi_bytes(pk[0], pk[1]); u[2 * j + 1] = hi_bytes(pk[2], pk[3]); }
     sts128(prow_addr + (((chunk_base + j) ^ (r & 7)) << 4), make_uint4(pk[0], pk[1], pk[2], pk[3]));
     if (kMask && gsave) stg128(gsave + j * 1024, make_uint4(pk[0], pk[1], pk[2], pk[3]));
   }
-  return mword;
+  return kMask ? neg_mask32(u) : 0u;
 }
 
 template <bool kSave, bool kHalf>
@@ -158,42 +199,36 @@ mlp_tc_fwd_kernel(const __grid_constant__ TcPlan plan, const uint8_t* __restrict
     for (int t = 0; t < 2; ++t) {
       mbar_init(smem_u32(&bars->act_ready[t]), kEpiThreadsPerTile);
       mbar_init(smem_u32(&bars->acc_full[t]), 1);
-      mbar_init(smem_u32(&bars->bias_full[t]), 1);
-      mbar_init(smem_u32(&bars->bias_empty[t]), 2 * kEpiThreadsPerTile);
     }
     fence_barrier_init();
   }
   if (warp == kWarpMma) tmem_alloc(smem_u32(&bars->tmem_base), 512);
+  // L1 is ~3 KB next to 225 KB of shared memory: the fp32 rgb head lives in shared memory
+  for (int i = threadIdx.x; i < 129; i += blockDim.x)
+    reinterpret_cast<float4*>(smem + kSmemWrgb)[i] = __ldg(reinterpret_cast<const float4*>(packed + plan.w_rgb_off) + i);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = bars->tmem_base;
 
   if (warp == kWarpProducer) {
-    // ===== producer: weight chunks (ring) and the per-layer bias vector (2 slots) =====
+    // ===== producer: weight chunks (ring) =====
     if (lane == 0) {
-      uint32_t g = 0, lc = 0;
+      uint32_t g = 0;
       for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
         // staggered schedule: tile A runs layer l while tile B's previous accumulator is drained, so each layer's
         // chunks are streamed once per tile (they come from L2)
-        for (int l = 0; l < plan.n_layers; ++l, ++lc) {
-          const uint32_t slot = lc & 1u;
-          mbar_wait(smem_u32(&bars->bias_empty[slot]), ((lc >> 1) & 1u) ^ 1u);
-          mbar_arrive_expect_tx(smem_u32(&bars->bias_full[slot]), 1024);
-          bulk_g2s(sbase + kSmemBias + slot * 1024, packed + plan.bias_off + l * 1024, 1024, smem_u32(&bars->bias_full[slot]));
+        for (int l = 0; l < plan.n_layers; ++l) {
           for (int t = 0; t < 2; ++t) {
             for (int ci = 0; ci < plan.layer_nchunks[l]; ++ci) {
               const int c = plan.layer_first[l] + ci;
-              // a chunk [N][64] travels as row halves of <= 128 rows (16 KB): finer ring, more loads in flight
-              for (uint32_t off = 0; off < plan.chunk_bytes[c]; off += kStageBytes, ++g) {
-                const uint32_t bytes = min(plan.chunk_bytes[c] - off, (uint32_t)kStageBytes);
-                const uint32_t s = g % kStages, ph = (g / kStages) & 1u;
-                mbar_wait(smem_u32(&bars->empty[s]), ph ^ 1u);
-                if (dbg & kDbgNoWeightCopy) { mbar_arrive(smem_u32(&bars->full[s])); continue; }
-                mbar_arrive_expect_tx(smem_u32(&bars->full[s]), bytes);
-                bulk_g2s(sbase + kSmemStage + s * kStageBytes, packed + plan.chunk_off[c] + off, bytes,
-                         smem_u32(&bars->full[s]));
-              }
+              const uint32_t bytes = plan.chunk_bytes[c];
+              const uint32_t s = g % kStages, ph = (g / kStages) & 1u;
+              ++g;
+              mbar_wait(smem_u32(&bars->empty[s]), ph ^ 1u);
+              if (dbg & kDbgNoWeightCopy) { mbar_arrive(smem_u32(&bars->full[s])); continue; }
+              mbar_arrive_expect_tx(smem_u32(&bars->full[s]), bytes);
+              bulk_g2s(sbase + kSmemStage + s * kStageBytes, packed + plan.chunk_off[c], bytes, smem_u32(&bars->full[s]));
             }
           }
         }
@@ -203,36 +238,55 @@ mlp_tc_fwd_kernel(const __grid_constant__ TcPlan plan, const uint8_t* __restrict
     // ===== MMA issuer =====
     if (lane == 0) {
       uint32_t g = 0, act_cnt = 0;
+      const bool timing = (dbg & kDbgTiming) && blockIdx.x == 0;
+      long long t_begin = clock64(), t_act = 0, t_full = 0;
+      int n_tr = 0;
       for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
         for (int l = 0; l < plan.n_layers; ++l) {
           const int first = plan.layer_first[l], nch = plan.layer_nchunks[l], n_total = plan.layer_n[l];
           for (int t = 0; t < 2; ++t) {
+            long long tw = timing ? clock64() : 0;
             mbar_wait(smem_u32(&bars->act_ready[t]), act_cnt & 1u);
+            if (timing) t_act += clock64() - tw;
+            trace(timing, 2, n_tr, l * 4 + t * 2);
             const uint32_t d_tmem = tmem_base + (uint32_t)t * 256u;
             for (int ci = 0; ci < nch; ++ci) {
               const int c = first + ci;
               const int src = plan.a_src[c];
               const uint32_t a_addr = (src < 4) ? sbase + kSmemAct + (t * kActPanels + src) * kPanelBytes
                                                 : sbase + kSmemInp + t * kPanelBytes;
-              for (int n0 = 0; n0 < n_total; n0 += kStageRows, ++g) {          // row halves of the chunk: N = 128 (or the rest)
-                const uint32_t idesc = make_idesc(min(kStageRows, n_total - n0), 0, 0, kHalf ? 0 : 1);
-                const uint32_t s = g % kStages, ph = (g / kStages) & 1u;
-                mbar_wait(smem_u32(&bars->full[s]), ph);
-                tc_fence_after();
-                const uint32_t b_addr = sbase + kSmemStage + s * kStageBytes;
-                if (!(dbg & kDbgNoMma)) {
+              const uint32_t idesc = make_idesc(n_total, 0, 0, kHalf ? 0 : 1);
+              const uint32_t s = g % kStages, ph = (g / kStages) & 1u;
+              ++g;
+              tw = timing ? clock64() : 0;
+              mbar_wait(smem_u32(&bars->full[s]), ph);
+              if (timing) t_full += clock64() - tw;
+              tc_fence_after();
+              const uint32_t b_addr = sbase + kSmemStage + s * kStageBytes;
+              if (!(dbg & kDbgNoMma)) {
+                if (src == 5) {
+                  // bias slab: ONE K = 16 step over input-panel columns 32..47 (the constant-1 columns 38, 39)
+                  umma_bf16(d_tmem, make_desc_kmajor(a_addr + 2 * 32), make_desc_k_nosw(b_addr, 128, 256), idesc, 1u);
+                } else {
 #pragma unroll
                   for (int k = 0; k < 4; ++k)
-                    umma_bf16(d_tmem + (uint32_t)n0, make_desc_kmajor(a_addr + k * 32), make_desc_kmajor(b_addr + k * 32),
-                              idesc, (ci > 0 || k > 0) ? 1u : 0u);
+                    umma_bf16(d_tmem, make_desc_kmajor(a_addr + k * 32), make_desc_kmajor(b_addr + k * 32), idesc,
+                              (ci > 0 || k > 0) ? 1u : 0u);
                 }
-                umma_commit(smem_u32(&bars->empty[s]));
               }
+              umma_commit(smem_u32(&bars->empty[s]));
             }
             umma_commit(smem_u32(&bars->acc_full[t]));
+            trace(timing, 2, n_tr, l * 4 + t * 2 + 1);
           }
           ++act_cnt;
         }
+      }
+      if (timing) {
+        printf("fwd MMA thread: total %lld  wait act_ready %lld  wait full %lld (cycles)\n", clock64() - t_begin, t_act, t_full);
+        for (int i = 0; i < n_tr; ++i)
+          printf("TRACE mma %lld l%d t%d %s\n", (g_trace[2][i] >> 8) - t_begin, (int)(g_trace[2][i] & 255) >> 2,
+                 (int)(g_trace[2][i] & 2) >> 1, (g_trace[2][i] & 1) ? "issued" : "act_ready");
       }
     }
   } else {
@@ -244,19 +298,26 @@ mlp_tc_fwd_kernel(const __grid_constant__ TcPlan plan, const uint8_t* __restrict
     const uint32_t act_u32 = sbase + kSmemAct + t * kActPanels * kPanelBytes;
     const uint32_t inp_u32 = sbase + kSmemInp + t * kPanelBytes;
     const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)t * 256u;
-    const float4* w_rgb = reinterpret_cast<const float4*>(packed + plan.w_rgb_off);
-    const float* b_rgb = reinterpret_cast<const float*>(packed + plan.b_rgb_off);
-    uint32_t acc_cnt = 0, lc = 0;
+    const uint32_t wrgb_u32 = sbase + kSmemWrgb;
+    uint32_t acc_cnt = 0;
+    const bool timing = (dbg & kDbgTiming) && blockIdx.x == 0 && gtid == 0;
+    long long t_begin = clock64(), t_pro = 0, t_acc = 0, t_epi = 0, t_last = 0;
+    int n_tr = 0;
     for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
       const int64_t tile = pair * 2 + t;
       const int64_t row = tile * kTileM + r;
       const bool row_ok = row < M;
+      long long tw = timing ? clock64() : 0;
       // ---- prologue: this thread's half of the input panel row: half 0 = xyz columns (16-byte chunks 0..4),
       //      half 1 = view columns (chunks 5..7).  Zero first, then scatter the encoded values as bf16.
       {
         const uint32_t prow = inp_u32 + r * 128;
         const int cb = half ? 5 : 0, ce = half ? 8 : 5;
         for (int j = cb; j < ce; ++j) sts128(prow + ((j ^ (r & 7)) << 4), make_uint4(0u, 0u, 0u, 0u));
+        if (half == 0) {                                  // the constant-1 columns the bias rows / slabs multiply
+          sts_16<kHalf>(prow, r, kInpOneCol, 1.f);
+          sts_16<kHalf>(prow, r, kInpOneCol + 1, 1.f);
+        }
         if (row_ok) {
           if (in.xyz_enc != nullptr) {
             if (half == 0) {
@@ -301,6 +362,7 @@ mlp_tc_fwd_kernel(const __grid_constant__ TcPlan plan, const uint8_t* __restrict
       }
       fence_proxy_async();
       mbar_arrive(smem_u32(&bars->act_ready[t]));
+      if (timing) t_pro += clock64() - tw;
       uint8_t* saved_tile = kSave ? saved + (size_t)tile * kSavedTileBytes : nullptr;
       uint32_t* saved_mask = reinterpret_cast<uint32_t*>(saved_tile + (size_t)kSavedPanels * kPanelBytes);
       const bool do_store = kSave && !(dbg & kDbgNoStore);
@@ -312,13 +374,13 @@ mlp_tc_fwd_kernel(const __grid_constant__ TcPlan plan, const uint8_t* __restrict
         }
       }
 
-      for (int l = 0; l < plan.n_layers; ++l, ++lc) {
-        const uint32_t slot = lc & 1u;
-        const uint32_t bias_u32 = sbase + kSmemBias + slot * 1024;
-        mbar_wait(smem_u32(&bars->bias_full[slot]), (lc >> 1) & 1u);
+      for (int l = 0; l < plan.n_layers; ++l) {
+        tw = timing ? clock64() : 0;
         mbar_wait(smem_u32(&bars->acc_full[t]), acc_cnt & 1u);
         ++acc_cnt;
         tc_fence_after();
+        if (timing) { const long long now = clock64(); t_acc += now - tw; tw = now; }
+        trace(timing, t, n_tr, l * 2);
         if (l < 8) {
           // TMEM loads are double-buffered: group cc+1 is in flight while group cc is processed
           uint32_t acc[2][32];
@@ -332,14 +394,15 @@ mlp_tc_fwd_kernel(const __grid_constant__ TcPlan plan, const uint8_t* __restrict
             tmem_ld_wait();
             if (cc + 1 < 4) tmem_ld32(taddr + c0 + 32, acc[(cc + 1) & 1]);
             const uint32_t prow = act_u32 + (c0 >> 6) * kPanelBytes + r * 128;
-            const uint32_t mword = epi_group32<kSave, kHalf>(acc[cc & 1], bias_u32 + c0 * 4, alpha, prow, r, (c0 & 63) >> 3,
+            const uint32_t mword = epi_group32<kSave, kHalf>(acc[cc & 1], alpha, prow, r, (c0 & 63) >> 3,
                                                              grow ? grow + (c0 >> 3) * 1024 : nullptr);
             if (do_store) saved_mask[(l * 8 + (c0 >> 5)) * 128 + r] = mword;
           }
-          mbar_arrive(smem_u32(&bars->bias_empty[slot]));
           tc_fence_before();
           fence_proxy_async();
           mbar_arrive(smem_u32(&bars->act_ready[t]));
+          if (timing) t_epi += clock64() - tw;
+          trace(timing, t, n_tr, l * 2 + 1);
         } else {
           // last layer: cols 0..127 = last hidden (LeakyReLU), col 128 = sigma (linear); rgb head on CUDA cores.
           // half 0 owns cols 0..63, half 1 owns cols 64..127 and sigma; partial rgb sums meet in the (dead) input panel.
@@ -351,53 +414,57 @@ mlp_tc_fwd_kernel(const __grid_constant__ TcPlan plan, const uint8_t* __restrict
             uint32_t acc[32];
             tmem_ld32(taddr + c0, acc);
             tmem_ld_wait();
-            uint32_t mword = 0;
+            uint32_t u[8];
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-              const float4 b0 = lds128f(bias_u32 + (c0 + 8 * j) * 4), b1 = lds128f(bias_u32 + (c0 + 8 * j + 4) * 4);
-              const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
               uint32_t pk[4];
 #pragma unroll
               for (int i = 0; i < 4; ++i) {
                 const int e = 8 * j + 2 * i;
-                float x0 = __uint_as_float(acc[e]) + bv[2 * i];
-                float x1 = __uint_as_float(acc[e + 1]) + bv[2 * i + 1];
+                float x0 = __uint_as_float(acc[e]), x1 = __uint_as_float(acc[e + 1]);     // bias rode in the MMA
                 x0 = fmaxf(x0, alpha * x0);
                 x1 = fmaxf(x1, alpha * x1);
-                const float4 w0 = __ldg(w_rgb + c0 + e), w1 = __ldg(w_rgb + c0 + e + 1);
+                const float4 w0 = lds128f(wrgb_u32 + (c0 + e) * 16), w1 = lds128f(wrgb_u32 + (c0 + e + 1) * 16);
                 rr = fmaf(x0, w0.x, fmaf(x1, w1.x, rr));
                 gg = fmaf(x0, w0.y, fmaf(x1, w1.y, gg));
                 bb = fmaf(x0, w0.z, fmaf(x1, w1.z, bb));
                 pk[i] = pack_16x2<kHalf>(x0, x1);
-                if (kSave) mword |= (~pk[i] >> (4 * j + i)) & (0x80008000u >> (4 * j + i));
               }
+              if (kSave) { u[2 * j] = hi_bytes(pk[0], pk[1]); u[2 * j + 1] = hi_bytes(pk[2], pk[3]); }
               if (kSave && grow) stg128(grow + ((c0 >> 3) + j) * 1024, make_uint4(pk[0], pk[1], pk[2], pk[3]));
             }
-            if (do_store) saved_mask[(8 * 8 + (c0 >> 5)) * 128 + r] = mword;
+            if (do_store) saved_mask[(8 * 8 + (c0 >> 5)) * 128 + r] = neg_mask32(u);
           }
           const uint32_t xch = act_u32 + r * 16;                  // activation panels are dead after this layer's MMAs
           if (half == 1) {
             uint32_t sg[16];
             tmem_ld16(taddr + 128, sg);
             tmem_ld_wait();
-            const float sigma = __uint_as_float(sg[0]) + lds32f(bias_u32 + 128 * 4);
+            const float sigma = __uint_as_float(sg[0]);
             sts128(xch, make_uint4(__float_as_uint(rr), __float_as_uint(gg), __float_as_uint(bb), __float_as_uint(sigma)));
           }
-          mbar_arrive(smem_u32(&bars->bias_empty[slot]));
           tc_fence_before();
           named_bar_sync(bar_id, kEpiThreadsPerTile);
           if (half == 0 && row_ok) {
-            const float4 o = lds128f(xch);
-            reinterpret_cast<float4*>(out4)[row] =
-                make_float4(rr + o.x + __ldg(b_rgb + 0), gg + o.y + __ldg(b_rgb + 1), bb + o.z + __ldg(b_rgb + 2), o.w);
+            const float4 o = lds128f(xch), br = lds128f(wrgb_u32 + 128 * 16);
+            reinterpret_cast<float4*>(out4)[row] = make_float4(rr + o.x + br.x, gg + o.y + br.y, bb + o.z + br.z, o.w);
           }
           // the next pair's first epilogue overwrites the exchange rows, its prologue the input panel (whose saved copy,
           // a bulk S2G issued after this pair's prologue, must have been read out by now)
           if (kSave && gtid == 0) bulk_wait_read0();
           named_bar_sync(bar_id, kEpiThreadsPerTile);
+          if (timing) t_last += clock64() - tw;
+          trace(timing, t, n_tr, l * 2 + 1);
         }
       }
     }
+    if (timing)
+      for (int i = 0; i < n_tr; ++i)
+        printf("TRACE epi%d %lld l%d %s\n", t, (g_trace[t][i] >> 8) - t_begin, (int)(g_trace[t][i] & 255) >> 1,
+               (g_trace[t][i] & 1) ? "done" : "acc_full");
+    if (timing)
+      printf("fwd epilogue tile %d: total %lld  prologue %lld  wait acc_full %lld  hidden epilogues %lld  last layer %lld (cycles)\n", t,
+             clock64() - t_begin, t_pro, t_acc, t_epi, t_last);
     if (kSave && gtid == 0) bulk_wait0();
   }
   tc_fence_before();
@@ -503,7 +570,7 @@ int nerf_pack_weights(const nerf_net_cfg* cfg, const float* params, void* packed
   NERF_CHECK_ARG(params && packed, "null pointer");
   if (!make_plan(g, &plan)) { set_error("nerf_pack_weights: config not supported by NERF_MODE_BF16"); return NERF_E_UNSUPPORTED; }
   dim3 grid((256 * 64 + 255) / 256, plan.n_chunks + 1);
-  pack_weights_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(plan, g, params, (uint8_t*)packed, 0);
+  pack_weights_kernel<__nv_bfloat16><<<grid, 256, 0, (cudaStream_t)stream>>>(plan, g, params, (uint8_t*)packed);
   NERF_CHECK_LAUNCH();
   return bwd_pack_weights(g, params, (uint8_t*)packed + ((plan.total_bytes + 1023u) & ~1023u), (cudaStream_t)stream);
 }
@@ -515,7 +582,7 @@ int nerf_pack_weights_fp16(const nerf_net_cfg* cfg, const float* params, void* p
   NERF_CHECK_ARG(params && packed, "null pointer");
   if (!make_plan(g, &plan)) { set_error("nerf_pack_weights_fp16: config not supported by the tensor-core path"); return NERF_E_UNSUPPORTED; }
   dim3 grid((256 * 64 + 255) / 256, plan.n_chunks + 1);
-  pack_weights_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(plan, g, params, (uint8_t*)packed + half_region_offset(plan), 1);
+  pack_weights_kernel<__half><<<grid, 256, 0, (cudaStream_t)stream>>>(plan, g, params, (uint8_t*)packed + half_region_offset(plan));
   NERF_CHECK_LAUNCH();
   return NERF_OK;
 }

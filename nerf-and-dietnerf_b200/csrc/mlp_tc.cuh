@@ -17,7 +17,11 @@ constexpr int kStageBytes = 32768;                // one weight chunk: [<=256][6
 constexpr int kStageRows = kStageBytes / 128;
 constexpr int kStages = 2;                        // forward ring; the chain kernel has room for kChainStages
 constexpr int kInpViewCol = 40;                   // first view-encoding column of the input panel
-constexpr int kMaxChunks = 40;
+constexpr int kInpOneCol = 38;                    // input-panel columns 38, 39 hold the constant 1: the weight rows they
+                                                  // meet carry bf16(b) and bf16(b - bf16(b)), so the bias rides in the MMA
+constexpr int kBiasSlabBytes = 256 * 32;          // [256][16] bf16, un-swizzled K-major: the K = 16 slice (input-panel
+                                                  // columns 32..47) that adds the bias of a layer without input-panel chunk
+constexpr int kMaxChunks = 48;
 constexpr int kChainStages = 3;
 constexpr int kEpiWarps = 16;                     // 8 per tile: 4 TMEM lane quarters x 2 column halves
 constexpr int kEpiThreadsPerTile = 256;
@@ -55,8 +59,8 @@ constexpr int kSmemAct = 0;                                          // [2 tiles
 constexpr int kSmemInp = kSmemAct + 2 * kActPanels * kPanelBytes;    // [2 tiles]
 constexpr int kSmemStage = kSmemInp + 2 * kPanelBytes;               // [kStages]
 constexpr int kSmemBar = kSmemStage + kStages * kStageBytes;
-constexpr int kSmemBias = kSmemBar + 128;                            // [2 slots][256 fp32]: bias of the current layers
-constexpr int kSmemTotal = kSmemBias + 2 * 1024;
+constexpr int kSmemWrgb = kSmemBar + 128;                            // float4 [128] rgb-head kernel rows + float4 rgb bias
+constexpr int kSmemTotal = kSmemWrgb + 129 * 16;
 // no alignment slack: the kernels check that the dynamic shared memory window is 1024-byte aligned and trap otherwise
 constexpr int kSmemAlloc = kSmemTotal;
 static_assert(kSmemAlloc <= 232448, "forward kernel exceeds the 227 KB shared-memory limit");
@@ -64,43 +68,41 @@ static_assert(kSmemAlloc <= 232448, "forward kernel exceeds the 227 KB shared-me
 struct TcPlan {
   uint32_t chunk_off[kMaxChunks];    // byte offset of the chunk in the packed buffer
   uint32_t chunk_bytes[kMaxChunks];
-  int8_t a_src[kMaxChunks];          // 0..3 = activation panel, 4 = input panel
+  int8_t a_src[kMaxChunks];          // 0..3 = activation panel, 4 = input panel, 5 = bias slab (input-panel K slice 32..47)
   int8_t layer_first[12], layer_nchunks[12];
   int16_t layer_n[12];               // UMMA N of the layer
   int32_t n_layers, n_chunks;
-  uint32_t bias_off;                 // fp32 [9][256] (layer 8: b8[128], b_sigma, zeros)
-  uint32_t w_rgb_off;                // fp32 float4 [128] = (W9[j][0], W9[j][1], W9[j][2], 0)
-  uint32_t b_rgb_off;                // fp32 [4]
+  uint32_t w_rgb_off;                // fp32 float4 [128] = (W9[j][0], W9[j][1], W9[j][2], 0), then float4 (b9, 0)
   uint32_t total_bytes;
 };
 
 inline bool make_plan(const NetGeom& g, TcPlan* p) {
-  if (!g.view || g.hidden != 256 || g.last_hidden != 128 || g.dx > kInpViewCol || g.dv > 64 - kInpViewCol) return false;
+  if (!g.view || g.hidden != 256 || g.last_hidden != 128 || g.dx > kInpOneCol || g.dv > 64 - kInpViewCol) return false;
   memset(p, 0, sizeof(*p));
   int c = 0;
   uint32_t off = 0;
   auto add = [&](int layer, int n, int src) {
+    const uint32_t bytes = src == 5 ? (uint32_t)kBiasSlabBytes : (uint32_t)n * 128u;
     p->chunk_off[c] = off;
-    p->chunk_bytes[c] = (uint32_t)n * 128u;
+    p->chunk_bytes[c] = bytes;
     p->a_src[c] = (int8_t)src;
-    off += (uint32_t)n * 128u;
+    off += bytes;
     if (p->layer_nchunks[layer] == 0) p->layer_first[layer] = (int8_t)c;
     p->layer_nchunks[layer]++;
     p->layer_n[layer] = (int16_t)n;
     ++c;
   };
+  // every layer ends with the chunk that carries its bias: the input-panel chunk (layers 0, 4, 8) or the bias slab
   add(0, 256, 4);
-  for (int l = 1; l <= 3; ++l) for (int k = 0; k < 4; ++k) add(l, 256, k);
-  add(4, 256, 4);
+  for (int l = 1; l <= 3; ++l) { for (int k = 0; k < 4; ++k) add(l, 256, k); add(l, 256, 5); }
   for (int k = 0; k < 4; ++k) add(4, 256, k);
-  for (int l = 5; l <= 7; ++l) for (int k = 0; k < 4; ++k) add(l, 256, k);
+  add(4, 256, 4);
+  for (int l = 5; l <= 7; ++l) { for (int k = 0; k < 4; ++k) add(l, 256, k); add(l, 256, 5); }
   for (int k = 0; k < 4; ++k) add(8, 144, k);
   add(8, 144, 4);
   p->n_layers = 9;
   p->n_chunks = c;
-  p->bias_off = off;        off += 9 * 256 * 4;
-  p->w_rgb_off = off;       off += 128 * 16;
-  p->b_rgb_off = off;       off += 16;
+  p->w_rgb_off = off;       off += 129 * 16;
   p->total_bytes = off;
   return true;
 }

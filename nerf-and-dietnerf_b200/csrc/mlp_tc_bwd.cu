@@ -126,8 +126,9 @@ struct ChainBars {
   uint32_t tmem_base;
 };
 
-// sign-mask layout written by the forward epilogue: element e of a 32-column group -> bit (e odd ? 31 : 15) - e/2
-__device__ __forceinline__ bool mask_bit(uint32_t mw, int e) { return (mw >> (((e & 1) ? 31 : 15) - (e >> 1))) & 1u; }
+// sign-mask layout written by the forward epilogue (neg_mask32, mlp_tc.cu): element e of a 32-column group -> bit
+// 8 (e & 3) + 7 - (e >> 2), SET when the activation is negative; mask_bit() is true for the positive side
+__device__ __forceinline__ bool mask_bit(uint32_t mw, int e) { return !((mw >> (8 * (e & 3) + 7 - (e >> 2))) & 1u); }
 
 __device__ __forceinline__ void store_chunk16(uint32_t panel_row_addr, int r, int chunk16, uint4 v) {
   sts128(panel_row_addr + ((chunk16 ^ (r & 7)) << 4), v);

@@ -157,6 +157,11 @@ __device__ __forceinline__ uint64_t make_desc_mn_nosw(uint32_t smem_addr, uint32
   d |= (uint64_t)1 << 46;                              // descriptor version 1 (Blackwell); layout type 0 = no swizzle
   return d;
 }
+// Un-swizzled K-major operand: core matrices of 8 rows x 16 B (8 K elements); LBO = byte stride between the K core
+// matrices of one MMA (K = 16 -> two), SBO = byte stride between 8-row groups.
+__device__ __forceinline__ uint64_t make_desc_k_nosw(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  return make_desc_mn_nosw(smem_addr, lbo_bytes, sbo_bytes);
+}
 __device__ __forceinline__ void stg128(void* p, uint4 v) {
   asm volatile("st.global.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }

@@ -75,7 +75,7 @@ struct ProbeOut { long long mma_cycles, fill_cycles, fill_bytes; };
 
 template <int kCta>
 __global__ void __launch_bounds__(320, 1)
-mma_kernel(int n_mma, int N, int fill, int n_fill, int n_store_warps, const uint8_t* __restrict__ wsrc, uint32_t wbytes, ProbeOut* out) {
+mma_kernel(int n_mma, int N, int fill, int n_fill, int n_store_warps, int n_ld_warps, const uint8_t* __restrict__ wsrc, uint32_t wbytes, ProbeOut* out) {
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ uint64_t bar_done, bar_fill[2];
   __shared__ uint32_t tmem_base_s;
@@ -137,6 +137,21 @@ mma_kernel(int n_mma, int N, int fill, int n_fill, int n_store_warps, const uint
     if (g >= 1) mbar_wait(smem_u32(&bar_fill[(g - 1) & 1u]), ((g - 1) >> 1) & 1u);   // the copy still in flight
     long long t1 = clock64();
     if (blockIdx.x == 0) { out->fill_cycles = t1 - t0; out->fill_bytes = total; }
+  } else if (warp >= 2 && warp < 2 + n_ld_warps) {
+    // epilogue-like readers: tcgen05.ld of the accumulator the MMA stream is NOT writing would need exact phase
+    // knowledge; read columns 256..511 lanes (warp % 4) while the MMAs alternate over both halves
+    const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + 256u + (uint32_t)(((warp - 2) >> 2) & 1) * 128u;
+    uint32_t x = 0;
+    while (!stop_flag) {
+      uint32_t a[32];
+      tmem_ld32(taddr, a);
+      tmem_ld32(taddr + 32, a);
+      tmem_ld32(taddr + 64, a);
+      tmem_ld32(taddr + 96, a);
+      tmem_ld_wait();
+      x ^= a[0];
+    }
+    if (x == 0x12345u) out->fill_bytes = x;
   } else if (warp >= 2 && warp < 2 + n_store_warps) {
     // epilogue-like writers: st.shared.v4 into the scratch region, 512 B per warp-instruction
     const uint32_t base = sbase + 131072 + (uint32_t)((warp - 2) & 7) * 4096 + lane * 16;
@@ -199,6 +214,21 @@ __global__ void __launch_bounds__(128, 1) major_kernel(int n_mma, int a_mode, in
 }
 
 int main(int argc, char** argv) {
+  if (argc > 1 && argv[1][0] == 't') {
+    // MMA stream (N = 256, alternating accumulators) with 0 / 4 / 8 warps hammering tcgen05.ld
+    ProbeOut* po; cudaMalloc(&po, sizeof(ProbeOut));
+    uint8_t* w; cudaMalloc(&w, 2u << 20); cudaMemset(w, 0, 2u << 20);
+    const int smem = 164 * 1024;
+    cudaFuncSetAttribute(mma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    for (int nld : {0, 4, 8}) for (int fill : {0, 1}) {
+      ProbeOut h = {};
+      for (int rep = 0; rep < 2; ++rep) mma_kernel<1><<<148, 320, smem>>>(8192, 256, fill, 0, 0, nld, w, 2u << 20, po);
+      cudaError_t err = cudaDeviceSynchronize();
+      cudaMemcpy(&h, po, sizeof(h), cudaMemcpyDeviceToHost);
+      printf("MMA N=256 with %d tcgen05.ld warps, fill %d: %6.1f cycles/MMA %s\n", nld, fill, (double)h.mma_cycles / 8192, cudaGetErrorString(err));
+    }
+    return 0;
+  }
   if (argc > 1 && argv[1][0] == 'm') {
     long long* d; cudaMalloc(&d, 64);
     const int smem = 132 * 1024;
@@ -240,14 +270,14 @@ int main(int argc, char** argv) {
     cudaMemset(po, 0, sizeof(ProbeOut));
     for (int rep = 0; rep < 2; ++rep) {
       if (cta == 1) {
-        mma_kernel<1><<<148, 320, smem>>>(n_mma, N, fill, 0, nsw, w, wbytes, po);
+        mma_kernel<1><<<148, 320, smem>>>(n_mma, N, fill, 0, nsw, 0, w, wbytes, po);
       } else {
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(148); cfg.blockDim = dim3(320); cfg.dynamicSmemBytes = smem;
         cudaLaunchAttribute at[1];
         at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
         cfg.attrs = at; cfg.numAttrs = 1;
-        cudaLaunchKernelEx(&cfg, mma_kernel<2>, n_mma, N, fill, 0, nsw, (const uint8_t*)w, wbytes, po);
+        cudaLaunchKernelEx(&cfg, mma_kernel<2>, n_mma, N, fill, 0, nsw, 0, (const uint8_t*)w, wbytes, po);
       }
     }
     cudaError_t err = cudaDeviceSynchronize();
@@ -261,9 +291,9 @@ int main(int argc, char** argv) {
   for (int cta : {1}) for (int N : {256, 128}) {
     ProbeOut h = {};
     cudaMemset(po, 0, sizeof(ProbeOut));
-    mma_kernel<1><<<148, 320, smem>>>(0, N, 1, 64, 0, w, wbytes, po);
+    mma_kernel<1><<<148, 320, smem>>>(0, N, 1, 64, 0, 0, w, wbytes, po);
     cudaMemset(po, 0, sizeof(ProbeOut));
-    mma_kernel<1><<<148, 320, smem>>>(0, N, 1, 4096, 0, w, wbytes, po);
+    mma_kernel<1><<<148, 320, smem>>>(0, N, 1, 4096, 0, 0, w, wbytes, po);
     cudaError_t err = cudaDeviceSynchronize();
     cudaMemcpy(&h, po, sizeof(h), cudaMemcpyDeviceToHost);
     printf("bulk G2S from L2, %5d-byte copies, 2 in flight, 148 SMs: %.1f B/clk/SM %s\n", N * 128,
