@@ -2,10 +2,12 @@
 // src/UtilsNeuralRadianceField.py:214-234) as ONE persistent tcgen05/TMEM kernel per call.
 //
 // Design (DESIGN.md "K2"):
-//   * one CTA per SM, 320 threads: warps 0-3 = epilogue of row-tile A, warps 4-7 = epilogue of row-tile B,
-//     warp 8 = weight producer (1-D bulk async copies, TMA engine), warp 9 = tcgen05.mma issuer (one elected lane);
-//   * a CTA owns TWO 128-sample tiles at a time; both consume the same streamed weight chunk (32 KB, [N][64] bf16,
-//     128-byte swizzle, pre-swizzled in HBM by nerf_pack_weights) so every weight byte fetched from L2 feeds 256 rows;
+//   * CTA pairs (cluster of 2 on one TPC, tcgen05 cta_group::2), one CTA per SM, 576 threads: warps 0-7 = epilogue of
+//     row-tile A, warps 8-15 = epilogue of row-tile B, warp 16 = weight producer (1-D bulk async copies, TMA engine),
+//     warp 17 = tcgen05.mma issuer in the leader CTA (one elected lane) / weight-arrival relay in the peer CTA;
+//   * a pair owns TWO 256-sample super-tiles at a time (128 rows of each per CTA).  One MMA (M = 256, N = 256, K = 16)
+//     covers a whole super-tile; each CTA streams only its half of every weight chunk ([N/2][64] bf16 = 16 KB,
+//     128-byte swizzle, pre-swizzled in HBM by nerf_pack_weights) through a 4-stage ring;
 //   * activations never leave the SM: the fp32 accumulator (128 x 256) of each tile lives in TMEM (2 x 256 columns),
 //     the epilogue warps read it with tcgen05.ld, add bias, apply LeakyReLU, round to bf16 and write the next layer's
 //     A operand back into the SAME swizzled shared-memory panels (all MMAs of the layer have completed by then);
@@ -181,7 +183,7 @@ __device__ __forceinline__ uint32_t epi_group32(const uint32_t (&acc)[32], float
 }
 
 template <bool kSave, bool kHalf>
-__global__ void __launch_bounds__(kThreadsFwd, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreadsFwd, 1)
 mlp_tc_fwd_kernel(const __grid_constant__ TcPlan plan, const uint8_t* __restrict__ packed,
                   const __grid_constant__ FwdInput in, int64_t M, float* __restrict__ out4, uint8_t* __restrict__ saved,
                   float alpha, uint32_t dbg) {
@@ -191,99 +193,156 @@ mlp_tc_fwd_kernel(const __grid_constant__ TcPlan plan, const uint8_t* __restrict
   FwdBars* bars = reinterpret_cast<FwdBars*>(smem + kSmemBar);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
+  // a "quad" = the four 128-row tiles a CTA pair works on at a time: tile = 4 quad + 2 t + rank (t = super-tile 0/1)
+  const uint32_t rank = cluster_ctarank();
   const int64_t n_tiles = (M + kTileM - 1) / kTileM;
-  const int64_t n_pairs = (n_tiles + 1) / 2;
+  const int64_t n_quads = (n_tiles + 3) / 4;
+  const int64_t quad0 = cluster_id_x(), quad_step = num_clusters_x();
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kStages; ++s) { mbar_init(smem_u32(&bars->full[s]), 1); mbar_init(smem_u32(&bars->empty[s]), 1); }
+    // full[s] of the LEADER also counts the peer's relay arrive: both halves of the chunk have landed
+    for (int s = 0; s < kStages; ++s) { mbar_init(smem_u32(&bars->full[s]), (rank == 0 && !(dbg & kDbgNoRelay)) ? 2 : 1); mbar_init(smem_u32(&bars->empty[s]), 1); }
     for (int t = 0; t < 2; ++t) {
-      mbar_init(smem_u32(&bars->act_ready[t]), kEpiThreadsPerTile);
+      mbar_init(smem_u32(&bars->act_ready[t]), 2 * 8);   // leader's copy: one arrive per epilogue warp of BOTH CTAs
       mbar_init(smem_u32(&bars->acc_full[t]), 1);
     }
     fence_barrier_init();
   }
-  if (warp == kWarpMma) tmem_alloc(smem_u32(&bars->tmem_base), 512);
+  cluster_sync_all();                                  // barriers of both CTAs exist before any remote arrive
+  if (warp == kWarpMma) tmem_alloc_pair(smem_u32(&bars->tmem_base), 512);
   // L1 is ~3 KB next to 225 KB of shared memory: the fp32 rgb head lives in shared memory
   for (int i = threadIdx.x; i < 129; i += blockDim.x)
     reinterpret_cast<float4*>(smem + kSmemWrgb)[i] = __ldg(reinterpret_cast<const float4*>(packed + plan.w_rgb_off) + i);
   tc_fence_before();
   __syncthreads();
+  cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = bars->tmem_base;
 
   if (warp == kWarpProducer) {
     // ===== producer: weight chunks (ring) =====
     if (lane == 0) {
-      uint32_t g = 0;
-      for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
-        // staggered schedule: tile A runs layer l while tile B's previous accumulator is drained, so each layer's
-        // chunks are streamed once per tile (they come from L2)
-        for (int l = 0; l < plan.n_layers; ++l) {
+      // Static walk over the packed weights (the chunk order of make_plan): no table look-ups, no divisions -- this
+      // thread's own instruction latency sits on the path from "stage released" to "stage full".
+      const bool timing = (dbg & kDbgTiming) && blockIdx.x == 0;
+      long long t_begin = clock64(), t_rel = 0;
+      const uint32_t full0 = smem_u32(&bars->full[0]), empty0 = smem_u32(&bars->empty[0]);
+      const bool no_copy = (dbg & kDbgNoWeightCopy) != 0;
+      uint32_t s = 0, ph = 1;                            // ring stage, parity of the "stage is free" phase
+      // this CTA's half of a chunk: rows [rank N/2, (rank + 1) N/2) of [N][64] (or of the [256][16] bias slab)
+      auto load = [&](const uint8_t* src, uint32_t half_bytes) {
+        long long tw = timing ? clock64() : 0;
+        mbar_wait_spin(empty0 + 8u * s, ph);
+        if (timing) t_rel += clock64() - tw;
+        if (no_copy) {
+          mbar_arrive(full0 + 8u * s);
+        } else {
+          mbar_arrive_expect_tx(full0 + 8u * s, half_bytes);
+          bulk_g2s(sbase + kSmemStage + s * kStageBytes, src + rank * half_bytes, half_bytes, full0 + 8u * s);
+        }
+        if (++s == kStages) { s = 0; ph ^= 1u; }
+      };
+      for (int64_t quad = quad0; quad < n_quads; quad += quad_step) {
+        // staggered schedule: super-tile A runs layer l while super-tile B's previous accumulator is drained, so each
+        // layer's chunks are streamed once per super-tile (they come from L2)
+        const uint8_t* layer_base = packed;
+#pragma unroll 1
+        for (int l = 0; l < 9; ++l) {
+          const uint32_t chunk_bytes = (l == 8 ? 144u : 256u) * 128u;
+          const bool slab = !(l == 0 || l == 4 || l == 8);
+#pragma unroll
           for (int t = 0; t < 2; ++t) {
-            for (int ci = 0; ci < plan.layer_nchunks[l]; ++ci) {
-              const int c = plan.layer_first[l] + ci;
-              const uint32_t bytes = plan.chunk_bytes[c];
-              const uint32_t s = g % kStages, ph = (g / kStages) & 1u;
-              ++g;
-              mbar_wait(smem_u32(&bars->empty[s]), ph ^ 1u);
-              if (dbg & kDbgNoWeightCopy) { mbar_arrive(smem_u32(&bars->full[s])); continue; }
-              mbar_arrive_expect_tx(smem_u32(&bars->full[s]), bytes);
-              bulk_g2s(sbase + kSmemStage + s * kStageBytes, packed + plan.chunk_off[c], bytes, smem_u32(&bars->full[s]));
+            const uint8_t* p = layer_base;
+            if (l > 0) {
+#pragma unroll
+              for (int ci = 0; ci < 4; ++ci, p += chunk_bytes) load(p, chunk_bytes >> 1);
             }
+            load(p, slab ? (uint32_t)(kBiasSlabBytes >> 1) : (chunk_bytes >> 1));
           }
+          layer_base += (l == 0 ? chunk_bytes : 4u * chunk_bytes + (slab ? (uint32_t)kBiasSlabBytes : chunk_bytes));
         }
       }
+      if (timing) printf("fwd producer: total %lld  wait stage release %lld (cycles)\n", clock64() - t_begin, t_rel);
     }
   } else if (warp == kWarpMma) {
-    // ===== MMA issuer =====
-    if (lane == 0) {
-      uint32_t g = 0, act_cnt = 0;
+    // ===== MMA issuer (leader CTA) / weight-arrival relay (peer CTA) =====
+    if (lane == 0 && rank != 0 && (dbg & kDbgNoRelay)) {
+    } else if (lane == 0 && rank != 0) {
+      // peer CTA: forward "my half of the chunk has landed" to the leader's full barrier
+      const uint32_t full0 = smem_u32(&bars->full[0]), full0_leader = mapa_shared(full0, 0);
+      uint32_t s = 0, ph = 0;
+      for (int64_t quad = quad0; quad < n_quads; quad += quad_step)
+        for (int i = 0; i < 2 * plan.n_chunks; ++i) {
+          mbar_wait_spin(full0 + 8u * s, ph);
+          mbar_arrive_cluster(full0_leader + 8u * s);
+          if (++s == kStages) { s = 0; ph ^= 1u; }
+        }
+    } else if (lane == 0) {
+      // The issuing thread is latency-bound, not the tensor pipe: a generic loop (plan look-ups, descriptor rebuilds,
+      // modulo ring indices) cost ~750 cycles per 4-MMA chunk (tools/sm_probe.cu "p"), 1.5x the 512 cycles the MMAs take.
+      // So the schedule is spelled out statically (the chunk order of make_plan) and every descriptor is a register add.
       const bool timing = (dbg & kDbgTiming) && blockIdx.x == 0;
-      long long t_begin = clock64(), t_act = 0, t_full = 0;
+      long long t_begin = clock64(), t_act = 0, t_full = 0, t_issue = 0;
       int n_tr = 0;
-      for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
-        for (int l = 0; l < plan.n_layers; ++l) {
-          const int first = plan.layer_first[l], nch = plan.layer_nchunks[l], n_total = plan.layer_n[l];
+      const uint32_t fmt = kHalf ? 0 : 1;
+      const uint32_t idesc256 = make_idesc(256, 0, 0, fmt, 256), idesc144 = make_idesc(144, 0, 0, fmt, 256);
+      const uint64_t b_sw = make_desc_kmajor(sbase + kSmemStage), b_slab = make_desc_k_nosw(sbase + kSmemStage, 128, 256);
+      const uint32_t full0 = smem_u32(&bars->full[0]), empty0 = smem_u32(&bars->empty[0]);
+      const bool no_mma = (dbg & kDbgNoMma) != 0;
+      uint32_t s = 0, ph = 0, act_ph = 0;               // ring stage / phase, act_ready phase
+      // one weight chunk: wait for both halves, 4 MMAs of K = 16 (or the single bias-slab MMA), release the stage
+      auto chunk = [&](uint32_t d_tmem, uint64_t a_desc, bool slab, uint32_t idesc, uint32_t first_acc) {
+        long long tw = timing ? clock64() : 0;
+        mbar_wait_spin(full0 + 8u * s, ph);
+        if (timing) { const long long now = clock64(); t_full += now - tw; tw = now; }
+        tc_fence_after();
+        const uint64_t soff = (uint64_t)(s * (uint32_t)(kStageBytes >> 4));
+        if (!no_mma) {
+          if (slab) {
+            umma_pair(d_tmem, a_desc + 4, b_slab + soff, idesc, 1u);   // input-panel columns 32..47
+          } else {
+            const uint64_t b = b_sw + soff;
+            umma_pair(d_tmem, a_desc, b, idesc, first_acc);
+            umma_pair(d_tmem, a_desc + 2, b + 2, idesc, 1u);
+            umma_pair(d_tmem, a_desc + 4, b + 4, idesc, 1u);
+            umma_pair(d_tmem, a_desc + 6, b + 6, idesc, 1u);
+          }
+        }
+        umma_commit_pair(empty0 + 8u * s);             // releases this stage in both CTAs
+        if (timing) t_issue += clock64() - tw;
+        if (++s == kStages) { s = 0; ph ^= 1u; }
+      };
+      for (int64_t quad = quad0; quad < n_quads; quad += quad_step) {
+#pragma unroll 1
+        for (int l = 0; l < 9; ++l) {
+#pragma unroll
           for (int t = 0; t < 2; ++t) {
             long long tw = timing ? clock64() : 0;
-            mbar_wait(smem_u32(&bars->act_ready[t]), act_cnt & 1u);
+            mbar_wait_spin(smem_u32(&bars->act_ready[t]), act_ph);
             if (timing) t_act += clock64() - tw;
             trace(timing, 2, n_tr, l * 4 + t * 2);
             const uint32_t d_tmem = tmem_base + (uint32_t)t * 256u;
-            for (int ci = 0; ci < nch; ++ci) {
-              const int c = first + ci;
-              const int src = plan.a_src[c];
-              const uint32_t a_addr = (src < 4) ? sbase + kSmemAct + (t * kActPanels + src) * kPanelBytes
-                                                : sbase + kSmemInp + t * kPanelBytes;
-              const uint32_t idesc = make_idesc(n_total, 0, 0, kHalf ? 0 : 1);
-              const uint32_t s = g % kStages, ph = (g / kStages) & 1u;
-              ++g;
-              tw = timing ? clock64() : 0;
-              mbar_wait(smem_u32(&bars->full[s]), ph);
-              if (timing) t_full += clock64() - tw;
-              tc_fence_after();
-              const uint32_t b_addr = sbase + kSmemStage + s * kStageBytes;
-              if (!(dbg & kDbgNoMma)) {
-                if (src == 5) {
-                  // bias slab: ONE K = 16 step over input-panel columns 32..47 (the constant-1 columns 38, 39)
-                  umma_bf16(d_tmem, make_desc_kmajor(a_addr + 2 * 32), make_desc_k_nosw(b_addr, 128, 256), idesc, 1u);
-                } else {
-#pragma unroll
-                  for (int k = 0; k < 4; ++k)
-                    umma_bf16(d_tmem, make_desc_kmajor(a_addr + k * 32), make_desc_kmajor(b_addr + k * 32), idesc,
-                              (ci > 0 || k > 0) ? 1u : 0u);
-                }
-              }
-              umma_commit(smem_u32(&bars->empty[s]));
+            const uint64_t a_act = make_desc_kmajor(sbase + kSmemAct + t * kActPanels * kPanelBytes);
+            const uint64_t a_inp = make_desc_kmajor(sbase + kSmemInp + t * kPanelBytes);
+            if (l == 0) {
+              chunk(d_tmem, a_inp, false, idesc256, 0u);
+            } else {
+              const uint32_t idesc = l == 8 ? idesc144 : idesc256;
+              chunk(d_tmem, a_act, false, idesc, 0u);
+              chunk(d_tmem, a_act + 1 * (kPanelBytes >> 4), false, idesc, 1u);
+              chunk(d_tmem, a_act + 2 * (kPanelBytes >> 4), false, idesc, 1u);
+              chunk(d_tmem, a_act + 3 * (kPanelBytes >> 4), false, idesc, 1u);
+              chunk(d_tmem, a_inp, !(l == 4 || l == 8), idesc, 1u);   // input-panel chunk (layers 4, 8) or bias slab
             }
-            umma_commit(smem_u32(&bars->acc_full[t]));
+            umma_commit_pair(smem_u32(&bars->acc_full[t]));
             trace(timing, 2, n_tr, l * 4 + t * 2 + 1);
           }
-          ++act_cnt;
+          act_ph ^= 1u;
         }
       }
       if (timing) {
-        printf("fwd MMA thread: total %lld  wait act_ready %lld  wait full %lld (cycles)\n", clock64() - t_begin, t_act, t_full);
+        printf("fwd MMA thread: total %lld  wait act_ready %lld  wait full %lld  issue %lld (cycles)\n", clock64() - t_begin, t_act,
+               t_full, t_issue);
         for (int i = 0; i < n_tr; ++i)
           printf("TRACE mma %lld l%d t%d %s\n", (g_trace[2][i] >> 8) - t_begin, (int)(g_trace[2][i] & 255) >> 2,
                  (int)(g_trace[2][i] & 2) >> 1, (g_trace[2][i] & 1) ? "issued" : "act_ready");
@@ -303,8 +362,9 @@ mlp_tc_fwd_kernel(const __grid_constant__ TcPlan plan, const uint8_t* __restrict
     const bool timing = (dbg & kDbgTiming) && blockIdx.x == 0 && gtid == 0;
     long long t_begin = clock64(), t_pro = 0, t_acc = 0, t_epi = 0, t_last = 0;
     int n_tr = 0;
-    for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
-      const int64_t tile = pair * 2 + t;
+    const uint32_t act_ready_leader = mapa_shared(smem_u32(&bars->act_ready[t]), 0);
+    for (int64_t quad = quad0; quad < n_quads; quad += quad_step) {
+      const int64_t tile = quad * 4 + t * 2 + rank;
       const int64_t row = tile * kTileM + r;
       const bool row_ok = row < M;
       long long tw = timing ? clock64() : 0;
@@ -361,7 +421,8 @@ mlp_tc_fwd_kernel(const __grid_constant__ TcPlan plan, const uint8_t* __restrict
         }
       }
       fence_proxy_async();
-      mbar_arrive(smem_u32(&bars->act_ready[t]));
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(act_ready_leader);
       if (timing) t_pro += clock64() - tw;
       uint8_t* saved_tile = kSave ? saved + (size_t)tile * kSavedTileBytes : nullptr;
       uint32_t* saved_mask = reinterpret_cast<uint32_t*>(saved_tile + (size_t)kSavedPanels * kPanelBytes);
@@ -400,7 +461,8 @@ mlp_tc_fwd_kernel(const __grid_constant__ TcPlan plan, const uint8_t* __restrict
           }
           tc_fence_before();
           fence_proxy_async();
-          mbar_arrive(smem_u32(&bars->act_ready[t]));
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster(act_ready_leader);
           if (timing) t_epi += clock64() - tw;
           trace(timing, t, n_tr, l * 2 + 1);
         } else {
@@ -449,7 +511,7 @@ mlp_tc_fwd_kernel(const __grid_constant__ TcPlan plan, const uint8_t* __restrict
             const float4 o = lds128f(xch), br = lds128f(wrgb_u32 + 128 * 16);
             reinterpret_cast<float4*>(out4)[row] = make_float4(rr + o.x + br.x, gg + o.y + br.y, bb + o.z + br.z, o.w);
           }
-          // the next pair's first epilogue overwrites the exchange rows, its prologue the input panel (whose saved copy,
+          // the next quad's first epilogue overwrites the exchange rows, its prologue the input panel (whose saved copy,
           // a bulk S2G issued after this pair's prologue, must have been read out by now)
           if (kSave && gtid == 0) bulk_wait_read0();
           named_bar_sync(bar_id, kEpiThreadsPerTile);
@@ -469,7 +531,8 @@ mlp_tc_fwd_kernel(const __grid_constant__ TcPlan plan, const uint8_t* __restrict
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == kWarpMma) tmem_dealloc(tmem_base, 512);
+  cluster_sync_all();                                  // the peer's shared memory / TMEM stay valid until both are done
+  if (warp == kWarpMma) tmem_dealloc_pair(tmem_base, 512);
 }
 
 // ---- host side ----------------------------------------------------------------------------------------------------------------
@@ -483,7 +546,7 @@ uint32_t tc_debug_flags() {
 
 int64_t mlp_tc_saved_bytes(const NetGeom& g, int64_t m) {
   int64_t tiles = (m + kTileM - 1) / kTileM;
-  tiles = (tiles + 1) / 2 * 2;
+  tiles = (tiles + 3) / 4 * 4;
   return tiles * (int64_t)kSavedTileBytes;
 }
 
@@ -491,7 +554,7 @@ int64_t mlp_tc_workspace_bytes(const NetGeom& g, int64_t m, int backward) {
   (void)g;
   if (!backward) return 256;
   int64_t tiles = (m + kTileM - 1) / kTileM;
-  tiles = (tiles + 1) / 2 * 2;
+  tiles = (tiles + 3) / 4 * 4;
   return tiles * (int64_t)kDzTileBytes + 1024;
 }
 
@@ -515,8 +578,8 @@ static int launch_fwd(const nerf_net_cfg* cfg, const NetGeom& g, const void* pac
     NERF_CUDA(cudaFuncSetAttribute(mlp_tc_fwd_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemAlloc));
     attr_set = true;
   }
-  int64_t n_pairs = ((m + kTileM - 1) / kTileM + 1) / 2;
-  int grid = (int)(n_pairs < kNumSMs ? n_pairs : kNumSMs);
+  int64_t n_quads = ((m + kTileM - 1) / kTileM + 3) / 4;
+  int grid = 2 * (int)(n_quads < kNumSMs / 2 ? n_quads : kNumSMs / 2);     // CTA pairs
   if (half) {
     if (saved) { set_error("NERF_MODE_FP16 is a forward-only (render) mode: train in NERF_MODE_BF16"); return NERF_E_UNSUPPORTED; }
     mlp_tc_fwd_kernel<false, true><<<grid, kThreadsFwd, kSmemAlloc, st>>>(

@@ -12,17 +12,18 @@ using namespace tc;
 constexpr int kTileM = 128;
 constexpr int kPanelBytes = 128 * 128;            // [128 rows][64 bf16]
 constexpr int kActPanels = 4;                     // 256 features
-constexpr int kStageBytes = 32768;                // one weight chunk: [<=256][64] bf16 (N = 256 per MMA; N = 128 MMAs
-                                                  // measured 30 % slower end to end)
-constexpr int kStageRows = kStageBytes / 128;
-constexpr int kStages = 2;                        // forward ring; the chain kernel has room for kChainStages
+// The forward kernel runs on CTA PAIRS (cluster of 2, tcgen05 cta_group::2): one MMA covers 256 rows (128 per CTA) and each
+// CTA streams only ITS half of every weight chunk ([<=128][64] bf16 = 16 KB): half the L2 traffic, half the B-operand
+// shared-memory reads, and a 4-deep ring.  Measured motivation (NERF_TC_DEBUG=256 trace, tools/sm_probe.cu): with a
+// 2 x 32 KB single-CTA ring every 512-cycle chunk of MMAs waited ~300 cycles for its weights (L2 latency ~700 cycles).
+constexpr int kStageBytes = 16384;                // this CTA's half of one weight chunk
+constexpr int kStages = 4;                        // forward ring
 constexpr int kInpViewCol = 40;                   // first view-encoding column of the input panel
 constexpr int kInpOneCol = 38;                    // input-panel columns 38, 39 hold the constant 1: the weight rows they
                                                   // meet carry bf16(b) and bf16(b - bf16(b)), so the bias rides in the MMA
 constexpr int kBiasSlabBytes = 256 * 32;          // [256][16] bf16, un-swizzled K-major: the K = 16 slice (input-panel
                                                   // columns 32..47) that adds the bias of a layer without input-panel chunk
 constexpr int kMaxChunks = 48;
-constexpr int kChainStages = 3;
 constexpr int kEpiWarps = 16;                     // 8 per tile: 4 TMEM lane quarters x 2 column halves
 constexpr int kEpiThreadsPerTile = 256;
 constexpr int kWarpProducer = 16, kWarpMma = 17;
@@ -120,6 +121,7 @@ enum : uint32_t {
   kDbgNoBiasSum = 32u,     // dW: no bias-gradient column sums
   kDbgNoChain = 64u,       // backward: skip the dX chain launch
   kDbgNoDw = 128u,         // backward: skip the dW launch
+  kDbgNoRelay = 512u,      // forward (pair mode): the leader does not wait for the peer's weight halves (racy)
   kDbgTiming = 256u,       // dW: every CTA prints its cycle count
 };
 uint32_t tc_debug_flags();

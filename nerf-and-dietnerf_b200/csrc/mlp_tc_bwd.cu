@@ -114,15 +114,16 @@ int bwd_pack_weights(const NetGeom& g, const float* params, uint8_t* packed_bwd,
 // =====================================================================================================================
 // (1) dX chain
 // =====================================================================================================================
+constexpr int kCStageBytes = 32768, kCStageRows = 256, kCStages = 3;   // single-CTA chain ring
 constexpr int kSmemCAct = 0;                                          // [2 tiles][4 panels]
 constexpr int kSmemCStage = 2 * kActPanels * kPanelBytes;             // [kStages] x 32 KB
-constexpr int kSmemCBar = kSmemCStage + kChainStages * kStageBytes;
+constexpr int kSmemCBar = kSmemCStage + kCStages * kCStageBytes;
 constexpr int kSmemCConst = kSmemCBar + 256;          // fp32 [256] sigma-head kernel, then fp32 [128][3] rgb-head kernel
 constexpr int kSmemCAlloc = kSmemCConst + 1024 + 1536;
 static_assert(kSmemCAlloc <= 232448, "chain kernel exceeds the 227 KB shared-memory limit");
 
 struct ChainBars {
-  uint64_t full[kChainStages], empty[kChainStages], act_ready[2], acc_full[2];
+  uint64_t full[kCStages], empty[kCStages], act_ready[2], acc_full[2];
   uint32_t tmem_base;
 };
 
@@ -158,7 +159,7 @@ mlp_tc_bwd_chain_kernel(const __grid_constant__ BwdPlan plan, const uint8_t* __r
     if (need_dx || plan.step_kind[s] == STEP_MASK) last_step = s;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kChainStages; ++s) { mbar_init(smem_u32(&bars->full[s]), 1); mbar_init(smem_u32(&bars->empty[s]), 1); }
+    for (int s = 0; s < kCStages; ++s) { mbar_init(smem_u32(&bars->full[s]), 1); mbar_init(smem_u32(&bars->empty[s]), 1); }
     for (int t = 0; t < 2; ++t) { mbar_init(smem_u32(&bars->act_ready[t]), kEpiThreadsPerTile); mbar_init(smem_u32(&bars->acc_full[t]), 1); }
     fence_barrier_init();
   }
@@ -177,13 +178,13 @@ mlp_tc_bwd_chain_kernel(const __grid_constant__ BwdPlan plan, const uint8_t* __r
           for (int t = 0; t < 2; ++t) {      // staggered: every step's chunks are streamed once per tile
             for (int ci = 0; ci < plan.step_nch[s]; ++ci) {
               const int c = plan.step_first[s] + ci;
-              for (uint32_t off = 0; off < plan.chunk_bytes[c]; off += kStageBytes, ++g) {   // row halves (<= 128 rows)
-                const uint32_t bytes = min(plan.chunk_bytes[c] - off, (uint32_t)kStageBytes);
-                const uint32_t st = g % kChainStages, ph = (g / kChainStages) & 1u;
+              for (uint32_t off = 0; off < plan.chunk_bytes[c]; off += kCStageBytes, ++g) {   // row halves (<= 128 rows)
+                const uint32_t bytes = min(plan.chunk_bytes[c] - off, (uint32_t)kCStageBytes);
+                const uint32_t st = g % kCStages, ph = (g / kCStages) & 1u;
                 mbar_wait(smem_u32(&bars->empty[st]), ph ^ 1u);
                 if (dbg & kDbgNoWeightCopy) { mbar_arrive(smem_u32(&bars->full[st])); continue; }
                 mbar_arrive_expect_tx(smem_u32(&bars->full[st]), bytes);
-                bulk_g2s(sbase + kSmemCStage + st * kStageBytes, packed + plan.chunk_off[c] + off, bytes,
+                bulk_g2s(sbase + kSmemCStage + st * kCStageBytes, packed + plan.chunk_off[c] + off, bytes,
                          smem_u32(&bars->full[st]));
               }
             }
@@ -203,12 +204,12 @@ mlp_tc_bwd_chain_kernel(const __grid_constant__ BwdPlan plan, const uint8_t* __r
             const uint32_t d_tmem = tmem_base + (uint32_t)t * 256u;
             for (int ci = 0; ci < nch; ++ci) {
               const uint32_t a_addr = sbase + kSmemCAct + (t * kActPanels + ci) * kPanelBytes;
-              for (int n0 = 0; n0 < n_total; n0 += kStageRows, ++g) {
-                const uint32_t idesc = make_idesc(min(kStageRows, n_total - n0));
-                const uint32_t st = g % kChainStages, ph = (g / kChainStages) & 1u;
+              for (int n0 = 0; n0 < n_total; n0 += kCStageRows, ++g) {
+                const uint32_t idesc = make_idesc(min(kCStageRows, n_total - n0));
+                const uint32_t st = g % kCStages, ph = (g / kCStages) & 1u;
                 mbar_wait(smem_u32(&bars->full[st]), ph);
                 tc_fence_after();
-                const uint32_t b_addr = sbase + kSmemCStage + st * kStageBytes;
+                const uint32_t b_addr = sbase + kSmemCStage + st * kCStageBytes;
                 if (!(dbg & kDbgNoMma)) {
 #pragma unroll
                   for (int k = 0; k < 4; ++k)

@@ -11,11 +11,6 @@
 #include "../nerf-and-dietnerf_b200/csrc/tc_common.cuh"
 using namespace nerf::tc;
 
-__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
 __device__ __forceinline__ void tmem_alloc2(uint32_t dst_smem, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
   asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
@@ -83,6 +78,16 @@ mma_kernel(int n_mma, int N, int fill, int n_fill, int n_store_warps, int n_ld_w
   const uint32_t sbase = smem_u32(smem);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (int i = threadIdx.x; i < (160 * 1024) / 16; i += blockDim.x) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+  if (fill & 16) {
+    // random bf16 operands in [-2, 2): tensor-core power depends on the data
+    uint32_t x = 0x9E3779B9u * (threadIdx.x + 1) + blockIdx.x;
+    for (int i = threadIdx.x; i < (160 * 1024) / 4; i += blockDim.x) {
+      x = x * 1664525u + 1013904223u;
+      const uint32_t lo = 0x3F00u | ((x >> 8) & 0x80FFu), hi = 0x3F00u | ((x >> 16) & 0x80FFu);
+      reinterpret_cast<uint32_t*>(smem)[i] = lo | (hi << 16);
+    }
+  }
+  fill &= 15;
   fence_proxy_async();
   if (threadIdx.x == 0) {
     mbar_init(smem_u32(&bar_done), 1);
@@ -213,7 +218,198 @@ __global__ void __launch_bounds__(128, 1) major_kernel(int n_mma, int a_mode, in
   if (threadIdx.x < 32) tmem_dealloc(tmem_base, 512);
 }
 
+// ---- (5) the weight pipeline alone: producer (bulk G2S ring) -> MMA issuer (4 MMAs per stage, commit frees the stage) ------
+__global__ void __launch_bounds__(128, 1)
+pipe_kernel(int n_chunks, int n_stages, int stage_bytes, int N, int spin, int var, const uint8_t* __restrict__ wsrc, uint32_t wbytes, long long* out) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint64_t full[8], empty[8], done;
+  __shared__ uint32_t tmem_base_s;
+  const uint32_t sbase = smem_u32(smem);
+  for (int i = threadIdx.x; i < (64 * 1024) / 16; i += blockDim.x) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+  fence_proxy_async();
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < 8; ++s) { mbar_init(smem_u32(&full[s]), 1); mbar_init(smem_u32(&empty[s]), 1); }
+    mbar_init(smem_u32(&done), 1);
+    fence_barrier_init();
+  }
+  if (threadIdx.x < 32) tmem_alloc(smem_u32(&tmem_base_s), 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+  const uint32_t ring = sbase + 65536;
+  if (threadIdx.x == 32) {           // producer
+    uint32_t off = (blockIdx.x * 40960u) % wbytes;
+    for (int g = 0; g < n_chunks; ++g) {
+      const uint32_t s = g % n_stages, ph = (g / n_stages) & 1u;
+      if (spin) mbar_wait_spin(smem_u32(&empty[s]), ph ^ 1u); else mbar_wait(smem_u32(&empty[s]), ph ^ 1u);
+      if (var & 1) { mbar_arrive(smem_u32(&full[s])); continue; }
+      mbar_arrive_expect_tx(smem_u32(&full[s]), stage_bytes);
+      bulk_g2s(ring + s * stage_bytes, wsrc + off, stage_bytes, smem_u32(&full[s]));
+      off += stage_bytes; if (off + stage_bytes > wbytes) off = 0;
+    }
+  } else if ((threadIdx.x >> 5) == 2 && (var & 32)) {
+    // converged issuer warp (CUTLASS style): all 32 lanes run the loop and the waits, one elected lane issues
+    const uint32_t idesc = make_idesc(N);
+    long long t0 = clock64();
+    const bool leader_lane = (threadIdx.x & 31) == 0;
+    for (int g = 0; g < n_chunks; ++g) {
+      const uint32_t s = g % n_stages, ph = (g / n_stages) & 1u;
+      mbar_wait(smem_u32(&full[s]), ph);
+      tc_fence_after();
+      if (leader_lane) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_bf16(tmem_base + (uint32_t)((g >> 2) & 1) * 256u, make_desc_kmajor(sbase + ((g & 3) * 16384) + k * 32),
+                    make_desc_kmajor(ring + s * stage_bytes + k * 32), idesc, 1u);
+        umma_commit(smem_u32(&empty[s]));
+      }
+      __syncwarp();
+    }
+    if (leader_lane) {
+      umma_commit(smem_u32(&done));
+      mbar_wait(smem_u32(&done), 0);
+      if (blockIdx.x == 0) out[0] = clock64() - t0;
+    }
+  } else if (threadIdx.x == 64 && !(var & 16)) {    // MMA issuer
+    const uint32_t idesc = make_idesc(N);
+    long long t0 = clock64();
+    if (var & 8) {
+      // software-pipelined: the wait for stage g+1 sits between the MMAs of stage g, the commit after its last MMA
+      mbar_wait(smem_u32(&full[0]), 0);
+      for (int g = 0; g < n_chunks; ++g) {
+        const uint32_t s = g % n_stages;
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          umma_bf16(tmem_base + (uint32_t)((g >> 2) & 1) * 256u, make_desc_kmajor(sbase + ((g & 3) * 16384) + k * 32),
+                    make_desc_kmajor(ring + s * stage_bytes + k * 32), idesc, 1u);
+          if (k == 1 && g + 1 < n_chunks) mbar_wait(smem_u32(&full[(g + 1) % n_stages]), ((g + 1) / n_stages) & 1u);
+        }
+        umma_commit(smem_u32(&empty[s]));
+      }
+    } else {
+      long long tw = 0, tm = 0, tc = 0;
+      for (int g = 0; g < n_chunks; ++g) {
+        const uint32_t s = g % n_stages, ph = (g / n_stages) & 1u;
+        long long a = clock64();
+        if (!(var & 2)) { if (spin) mbar_wait_spin(smem_u32(&full[s]), ph); else mbar_wait(smem_u32(&full[s]), ph); }
+        tc_fence_after();
+        long long b = clock64();
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_bf16(tmem_base + (uint32_t)((g >> 2) & 1) * 256u, make_desc_kmajor(sbase + ((g & 3) * 16384) + k * 32),
+                    make_desc_kmajor(ring + s * stage_bytes + k * 32), idesc, 1u);
+        long long c = clock64();
+        umma_commit(smem_u32(&empty[s]));
+        long long d = clock64();
+        tw += b - a; tm += c - b; tc += d - c;
+      }
+      if (blockIdx.x == 0 && (var & 64))
+        printf("   MMA thread per stage: wait full %lld, issue 4 MMAs %lld, commit %lld cycles\n", tw / n_chunks, tm / n_chunks, tc / n_chunks);
+    }
+    umma_commit(smem_u32(&done));
+    mbar_wait(smem_u32(&done), 0);
+    if (blockIdx.x == 0) out[0] = clock64() - t0;
+  } else if ((threadIdx.x == 64 || threadIdx.x == 96) && (var & 16)) {
+    // two issuer threads (different warps): even / odd stages, each with its own accumulator
+    const int me = threadIdx.x == 96;
+    const uint32_t idesc = make_idesc(N);
+    long long t0 = clock64();
+    for (int g = me; g < n_chunks; g += 2) {
+      const uint32_t s = g % n_stages, ph = (g / n_stages) & 1u;
+      mbar_wait(smem_u32(&full[s]), ph);
+      tc_fence_after();
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        umma_bf16(tmem_base + (uint32_t)me * 256u, make_desc_kmajor(sbase + ((g & 3) * 16384) + k * 32),
+                  make_desc_kmajor(ring + s * stage_bytes + k * 32), idesc, 1u);
+      umma_commit(smem_u32(&empty[s]));
+    }
+    if (me == 0) {
+      // the other thread's MMAs are not covered by this commit: give it time, then commit + wait
+      umma_commit(smem_u32(&done));
+      mbar_wait(smem_u32(&done), 0);
+      if (blockIdx.x == 0) out[0] = clock64() - t0;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (threadIdx.x < 32) tmem_dealloc(tmem_base, 512);
+}
+
+// ---- (6) issue loop: what does a per-stage tcgen05.commit / tcgen05.fence cost? -------------------------------------------
+__global__ void __launch_bounds__(128, 1) issue_kernel(int n_iter, int N, int mmas_per_iter, int do_fence, int do_commit, long long* out) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint64_t dummy[4], done;
+  __shared__ uint32_t tmem_base_s;
+  const uint32_t sbase = smem_u32(smem);
+  for (int i = threadIdx.x; i < (128 * 1024) / 16; i += blockDim.x) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+  fence_proxy_async();
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < 4; ++s) mbar_init(smem_u32(&dummy[s]), 1);
+    mbar_init(smem_u32(&done), 1);
+    fence_barrier_init();
+  }
+  if (threadIdx.x < 32) tmem_alloc(smem_u32(&tmem_base_s), 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+  if (threadIdx.x == 64) {
+    const uint32_t idesc = make_idesc(N);
+    long long t0 = clock64();
+    for (int g = 0; g < n_iter; ++g) {
+      if (do_fence) tc_fence_after();
+      for (int k = 0; k < mmas_per_iter; ++k)
+        umma_bf16(tmem_base + (uint32_t)((g >> 2) & 1) * 256u, make_desc_kmajor(sbase + ((g & 3) * 16384) + (k & 3) * 32),
+                  make_desc_kmajor(sbase + 65536 + (g & 1) * 32768 + (k & 3) * 32), idesc, 1u);
+      if (do_commit) umma_commit(smem_u32(&dummy[g & 3]));
+    }
+    umma_commit(smem_u32(&done));
+    mbar_wait(smem_u32(&done), 0);
+    if (blockIdx.x == 0) out[0] = clock64() - t0;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (threadIdx.x < 32) tmem_dealloc(tmem_base, 512);
+}
+
 int main(int argc, char** argv) {
+  if (argc > 1 && argv[1][0] == 'i') {
+    long long* d; cudaMalloc(&d, 64);
+    const int smem = 132 * 1024;
+    cudaFuncSetAttribute(issue_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    for (int N : {256, 128}) for (int per : {4, 8, 16}) for (int fence : {0, 1}) for (int commit : {0, 1}) {
+      const int n_iter = 4096;
+      issue_kernel<<<148, 128, smem>>>(n_iter, N, per, fence, commit, d);
+      issue_kernel<<<148, 128, smem>>>(n_iter, N, per, fence, commit, d);
+      cudaError_t err = cudaDeviceSynchronize();
+      long long cyc; cudaMemcpy(&cyc, d, 8, cudaMemcpyDeviceToHost);
+      printf("N=%3d %2d MMAs/iter fence %d commit %d: %7.1f cycles/iter = %6.1f cycles/MMA %s\n", N, per, fence, commit,
+             (double)cyc / n_iter, (double)cyc / n_iter / per, cudaGetErrorString(err));
+    }
+    return 0;
+  }
+  if (argc > 1 && argv[1][0] == 'p') {
+    long long* d; cudaMalloc(&d, 64);
+    uint8_t* w; cudaMalloc(&w, 2u << 20); cudaMemset(w, 0, 2u << 20);
+    const int smem = 196 * 1024;
+    cudaFuncSetAttribute(pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    const int cfgs[][3] = {{2, 32768, 256}, {4, 32768, 256}, {4, 16384, 128}};
+    // var: 1 = producer arrives without copying, 2 = MMA thread does not wait for full, 8 = software-pipelined waits,
+    // 16 = two issuer threads
+    for (auto& c : cfgs) for (int var : {64, 65, 66}) for (int grid : {148}) {
+      const int n_chunks = 4096, spin = 0;
+      pipe_kernel<<<grid, 128, smem>>>(n_chunks, c[0], c[1], c[2], spin, var, w, 2u << 20, d);
+      pipe_kernel<<<grid, 128, smem>>>(n_chunks, c[0], c[1], c[2], spin, var, w, 2u << 20, d);
+      cudaError_t err = cudaDeviceSynchronize();
+      long long cyc; cudaMemcpy(&cyc, d, 8, cudaMemcpyDeviceToHost);
+      printf("grid %3d ring %d x %5d B, N=%3d, var %d: %6.1f cycles per 4-MMA stage (ideal %d) %s\n", grid, c[0], c[1], c[2], var,
+             (double)cyc / n_chunks, c[2] == 256 ? 512 : 267, cudaGetErrorString(err));
+    }
+    return 0;
+  }
   if (argc > 1 && argv[1][0] == 't') {
     // MMA stream (N = 256, alternating accumulators) with 0 / 4 / 8 warps hammering tcgen05.ld
     ProbeOut* po; cudaMalloc(&po, sizeof(ProbeOut));
@@ -226,6 +422,28 @@ int main(int argc, char** argv) {
       cudaError_t err = cudaDeviceSynchronize();
       cudaMemcpy(&h, po, sizeof(h), cudaMemcpyDeviceToHost);
       printf("MMA N=256 with %d tcgen05.ld warps, fill %d: %6.1f cycles/MMA %s\n", nld, fill, (double)h.mma_cycles / 8192, cudaGetErrorString(err));
+    }
+    return 0;
+  }
+  if (argc > 1 && argv[1][0] == 'r') {
+    // zeros vs random operands: cycles per MMA and wall-clock rate (power throttling shows up in the clock)
+    ProbeOut* po; cudaMalloc(&po, sizeof(ProbeOut));
+    uint8_t* w; cudaMalloc(&w, 2u << 20); cudaMemset(w, 0, 2u << 20);
+    const int smem = 164 * 1024;
+    cudaFuncSetAttribute(mma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    for (int rnd : {0, 16, 0, 16}) {
+      ProbeOut h = {};
+      const int n_mma = 1 << 18;
+      cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+      mma_kernel<1><<<148, 320, smem>>>(n_mma, 256, rnd, 0, 0, 0, w, 2u << 20, po);
+      cudaEventRecord(e0);
+      mma_kernel<1><<<148, 320, smem>>>(n_mma, 256, rnd, 0, 0, 0, w, 2u << 20, po);
+      cudaEventRecord(e1);
+      cudaError_t err = cudaDeviceSynchronize();
+      float ms; cudaEventElapsedTime(&ms, e0, e1);
+      cudaMemcpy(&h, po, sizeof(h), cudaMemcpyDeviceToHost);
+      printf("%s operands: %6.1f cycles/MMA, %.2f ms -> %.0f TFLOP/s, SM clock %.2f GHz %s\n", rnd ? "random" : "zero  ",
+             (double)h.mma_cycles / n_mma, ms, 2.0 * 128 * 256 * 16 * (double)n_mma * 148 / ms / 1e9, h.mma_cycles / (ms * 1e6), cudaGetErrorString(err));
     }
     return 0;
   }
