@@ -114,9 +114,10 @@ int bwd_pack_weights(const NetGeom& g, const float* params, uint8_t* packed_bwd,
 // =====================================================================================================================
 // (1) dX chain
 // =====================================================================================================================
-constexpr int kCStageBytes = 32768, kCStageRows = 256, kCStages = 3;   // single-CTA chain ring
+// CTA pairs like the forward kernel (mlp_tc.cu): this CTA's half of a weight chunk is <= 16 KB, six stages fit
+constexpr int kCStageBytes = 16384, kCStages = 6;
 constexpr int kSmemCAct = 0;                                          // [2 tiles][4 panels]
-constexpr int kSmemCStage = 2 * kActPanels * kPanelBytes;             // [kStages] x 32 KB
+constexpr int kSmemCStage = 2 * kActPanels * kPanelBytes;             // [kCStages] x 16 KB
 constexpr int kSmemCBar = kSmemCStage + kCStages * kCStageBytes;
 constexpr int kSmemCConst = kSmemCBar + 256;          // fp32 [256] sigma-head kernel, then fp32 [128][3] rgb-head kernel
 constexpr int kSmemCAlloc = kSmemCConst + 1024 + 1536;
@@ -135,7 +136,7 @@ __device__ __forceinline__ void store_chunk16(uint32_t panel_row_addr, int r, in
   sts128(panel_row_addr + ((chunk16 ^ (r & 7)) << 4), v);
 }
 
-__global__ void __launch_bounds__(kThreadsFwd, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreadsFwd, 1)
 mlp_tc_bwd_chain_kernel(const __grid_constant__ BwdPlan plan, const uint8_t* __restrict__ packed,
                         const uint8_t* __restrict__ saved, const float* __restrict__ d_out4, int64_t M,
                         uint8_t* __restrict__ dz_ws, float* __restrict__ d_xyz_enc, int dx, float alpha, uint32_t dbg) {
@@ -152,76 +153,105 @@ mlp_tc_bwd_chain_kernel(const __grid_constant__ BwdPlan plan, const uint8_t* __r
   }
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const bool need_dx = d_xyz_enc != nullptr;
+  // a "quad" = the four 128-row tiles a CTA pair works on at a time: tile = 4 quad + 2 t + rank (t = super-tile 0/1)
+  const uint32_t rank = cluster_ctarank();
   const int64_t n_tiles = (M + kTileM - 1) / kTileM;
-  const int64_t n_pairs = (n_tiles + 1) / 2;
+  const int64_t n_quads = (n_tiles + 3) / 4;
+  const int64_t quad0 = cluster_id_x(), quad_step = num_clusters_x();
   int last_step = 0;
   for (int s = 0; s < plan.n_steps; ++s)
     if (need_dx || plan.step_kind[s] == STEP_MASK) last_step = s;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kCStages; ++s) { mbar_init(smem_u32(&bars->full[s]), 1); mbar_init(smem_u32(&bars->empty[s]), 1); }
-    for (int t = 0; t < 2; ++t) { mbar_init(smem_u32(&bars->act_ready[t]), kEpiThreadsPerTile); mbar_init(smem_u32(&bars->acc_full[t]), 1); }
+    // full[s] of the LEADER also counts the peer's relay arrive: both halves of the chunk have landed
+    for (int s = 0; s < kCStages; ++s) { mbar_init(smem_u32(&bars->full[s]), rank == 0 ? 2 : 1); mbar_init(smem_u32(&bars->empty[s]), 1); }
+    for (int t = 0; t < 2; ++t) {
+      mbar_init(smem_u32(&bars->act_ready[t]), 2 * 8);    // leader's copy: one arrive per epilogue warp of BOTH CTAs
+      mbar_init(smem_u32(&bars->acc_full[t]), 1);
+    }
     fence_barrier_init();
   }
-  if (warp == kWarpMma) tmem_alloc(smem_u32(&bars->tmem_base), 512);
+  cluster_sync_all();
+  if (warp == kWarpMma) tmem_alloc_pair(smem_u32(&bars->tmem_base), 512);
   tc_fence_before();
   __syncthreads();
+  cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = bars->tmem_base;
 
   if (warp == kWarpProducer) {
     if (lane == 0) {
-      uint32_t g = 0;
-      for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
+      const uint32_t full0 = smem_u32(&bars->full[0]), empty0 = smem_u32(&bars->empty[0]);
+      const bool no_copy = (dbg & kDbgNoWeightCopy) != 0;
+      uint32_t st = 0, ph = 1;                           // ring stage, parity of the "stage is free" phase
+      for (int64_t quad = quad0; quad < n_quads; quad += quad_step) {
         for (int s = 0; s < plan.n_steps; ++s) {
           if (!need_dx && plan.step_kind[s] != STEP_MASK) continue;
-          for (int t = 0; t < 2; ++t) {      // staggered: every step's chunks are streamed once per tile
-            for (int ci = 0; ci < plan.step_nch[s]; ++ci) {
-              const int c = plan.step_first[s] + ci;
-              for (uint32_t off = 0; off < plan.chunk_bytes[c]; off += kCStageBytes, ++g) {   // row halves (<= 128 rows)
-                const uint32_t bytes = min(plan.chunk_bytes[c] - off, (uint32_t)kCStageBytes);
-                const uint32_t st = g % kCStages, ph = (g / kCStages) & 1u;
-                mbar_wait(smem_u32(&bars->empty[st]), ph ^ 1u);
-                if (dbg & kDbgNoWeightCopy) { mbar_arrive(smem_u32(&bars->full[st])); continue; }
-                mbar_arrive_expect_tx(smem_u32(&bars->full[st]), bytes);
-                bulk_g2s(sbase + kSmemCStage + st * kCStageBytes, packed + plan.chunk_off[c] + off, bytes,
-                         smem_u32(&bars->full[st]));
+          const int first = plan.step_first[s], nch = plan.step_nch[s];
+          const uint32_t half_bytes = plan.chunk_bytes[first] >> 1;     // rows [rank N/2, (rank + 1) N/2) of [N][64]
+          const uint8_t* src = packed + plan.chunk_off[first] + rank * half_bytes;
+          for (int t = 0; t < 2; ++t) {      // staggered: every step's chunks are streamed once per super-tile
+            for (int ci = 0; ci < nch; ++ci) {
+              mbar_wait_spin(empty0 + 8u * st, ph);
+              if (no_copy) {
+                mbar_arrive(full0 + 8u * st);
+              } else {
+                mbar_arrive_expect_tx(full0 + 8u * st, half_bytes);
+                bulk_g2s(sbase + kSmemCStage + st * kCStageBytes, src + (size_t)ci * 2u * half_bytes, half_bytes, full0 + 8u * st);
               }
+              if (++st == kCStages) { st = 0; ph ^= 1u; }
             }
           }
         }
       }
     }
   } else if (warp == kWarpMma) {
-    if (lane == 0) {
-      uint32_t g = 0, act_cnt = 0;
-      for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
+    if (lane == 0 && rank != 0) {
+      // peer CTA: forward "my half of the chunk has landed" to the leader's full barrier
+      const uint32_t full0 = smem_u32(&bars->full[0]), full0_leader = mapa_shared(full0, 0);
+      int per_quad = 0;
+      for (int s = 0; s < plan.n_steps; ++s)
+        if (need_dx || plan.step_kind[s] == STEP_MASK) per_quad += 2 * plan.step_nch[s];
+      uint32_t st = 0, ph = 0;
+      for (int64_t quad = quad0; quad < n_quads; quad += quad_step)
+        for (int i = 0; i < per_quad; ++i) {
+          mbar_wait_spin(full0 + 8u * st, ph);
+          mbar_arrive_cluster(full0_leader + 8u * st);
+          if (++st == kCStages) { st = 0; ph ^= 1u; }
+        }
+    } else if (lane == 0) {
+      // leader: one thread issues every MMA of the pair; descriptors are register adds (see mlp_tc.cu)
+      const uint32_t full0 = smem_u32(&bars->full[0]), empty0 = smem_u32(&bars->empty[0]);
+      const uint64_t b0 = make_desc_kmajor(sbase + kSmemCStage);
+      const bool no_mma = (dbg & kDbgNoMma) != 0;
+      uint32_t st = 0, ph = 0, act_ph = 0;
+      for (int64_t quad = quad0; quad < n_quads; quad += quad_step) {
+#pragma unroll 1
         for (int s = 0; s < plan.n_steps; ++s) {
           if (!need_dx && plan.step_kind[s] != STEP_MASK) continue;
-          const int nch = plan.step_nch[s], n_total = plan.step_n[s];
-          for (int t = 0; t < 2; ++t) {
-            mbar_wait(smem_u32(&bars->act_ready[t]), act_cnt & 1u);
-            const uint32_t d_tmem = tmem_base + (uint32_t)t * 256u;
-            for (int ci = 0; ci < nch; ++ci) {
-              const uint32_t a_addr = sbase + kSmemCAct + (t * kActPanels + ci) * kPanelBytes;
-              for (int n0 = 0; n0 < n_total; n0 += kCStageRows, ++g) {
-                const uint32_t idesc = make_idesc(min(kCStageRows, n_total - n0));
-                const uint32_t st = g % kCStages, ph = (g / kCStages) & 1u;
-                mbar_wait(smem_u32(&bars->full[st]), ph);
-                tc_fence_after();
-                const uint32_t b_addr = sbase + kSmemCStage + st * kCStageBytes;
-                if (!(dbg & kDbgNoMma)) {
+          const int nch = plan.step_nch[s];
+          const uint32_t idesc = make_idesc(plan.step_n[s], 0, 0, 1, 256);
 #pragma unroll
-                  for (int k = 0; k < 4; ++k)
-                    umma_bf16(d_tmem + (uint32_t)n0, make_desc_kmajor(a_addr + k * 32), make_desc_kmajor(b_addr + k * 32),
-                              idesc, (ci > 0 || k > 0) ? 1u : 0u);
-                }
-                umma_commit(smem_u32(&bars->empty[st]));
+          for (int t = 0; t < 2; ++t) {
+            mbar_wait_spin(smem_u32(&bars->act_ready[t]), act_ph);
+            const uint32_t d_tmem = tmem_base + (uint32_t)t * 256u;
+            uint64_t a = make_desc_kmajor(sbase + kSmemCAct + t * kActPanels * kPanelBytes);
+            for (int ci = 0; ci < nch; ++ci, a += (kPanelBytes >> 4)) {
+              mbar_wait_spin(full0 + 8u * st, ph);
+              tc_fence_after();
+              const uint64_t b = b0 + (uint64_t)(st * (uint32_t)(kCStageBytes >> 4));
+              if (!no_mma) {
+                umma_pair(d_tmem, a, b, idesc, ci > 0 ? 1u : 0u);
+                umma_pair(d_tmem, a + 2, b + 2, idesc, 1u);
+                umma_pair(d_tmem, a + 4, b + 4, idesc, 1u);
+                umma_pair(d_tmem, a + 6, b + 6, idesc, 1u);
               }
+              umma_commit_pair(empty0 + 8u * st);          // releases this stage in both CTAs
+              if (++st == kCStages) { st = 0; ph ^= 1u; }
             }
-            umma_commit(smem_u32(&bars->acc_full[t]));
+            umma_commit_pair(smem_u32(&bars->acc_full[t]));
           }
-          ++act_cnt;
+          act_ph ^= 1u;
         }
       }
     }
@@ -235,8 +265,9 @@ mlp_tc_bwd_chain_kernel(const __grid_constant__ BwdPlan plan, const uint8_t* __r
     const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)t * 256u;
     const uint32_t w_sigma_u32 = sbase + kSmemCConst, w_rgb_u32 = sbase + kSmemCConst + 1024;
     uint32_t acc_cnt = 0;
-    for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
-      const int64_t tile = pair * 2 + t;
+    const uint32_t act_ready_leader = mapa_shared(smem_u32(&bars->act_ready[t]), 0);
+    for (int64_t quad = quad0; quad < n_quads; quad += quad_step) {
+      const int64_t tile = quad * 4 + t * 2 + rank;
       const int64_t row = tile * kTileM + r;
       const bool row_ok = row < M;
       const uint8_t* saved_tile = saved + (size_t)tile * kSavedTileBytes;
@@ -282,7 +313,8 @@ mlp_tc_bwd_chain_kernel(const __grid_constant__ BwdPlan plan, const uint8_t* __r
         }
       }
       fence_proxy_async();
-      mbar_arrive(smem_u32(&bars->act_ready[t]));
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(act_ready_leader);
       float xs[32];                                      // d(xyz encoding): half 0 -> cols 0..31, half 1 -> cols 32..39
 #pragma unroll
       for (int i = 0; i < 32; ++i) xs[i] = 0.f;
@@ -329,7 +361,8 @@ mlp_tc_bwd_chain_kernel(const __grid_constant__ BwdPlan plan, const uint8_t* __r
           }
           tc_fence_before();
           fence_proxy_async();
-          if (s != last_step) mbar_arrive(smem_u32(&bars->act_ready[t]));
+          __syncwarp();
+          if (s != last_step && lane == 0) mbar_arrive_cluster(act_ready_leader);
         } else {
           if (half == 0) {
             uint32_t a0[32];
@@ -346,7 +379,8 @@ mlp_tc_bwd_chain_kernel(const __grid_constant__ BwdPlan plan, const uint8_t* __r
           }
           tc_fence_before();
           if (kind == STEP_XSTASH) {
-            mbar_arrive(smem_u32(&bars->act_ready[t]));
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(act_ready_leader);
           } else if (row_ok) {
             float* dst = d_xyz_enc + row * dx + half * 32;
             const int lim = dx - half * 32;
@@ -359,7 +393,8 @@ mlp_tc_bwd_chain_kernel(const __grid_constant__ BwdPlan plan, const uint8_t* __r
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == kWarpMma) tmem_dealloc(tmem_base, 512);
+  cluster_sync_all();                                  // the peer's shared memory / TMEM stay valid until both are done
+  if (warp == kWarpMma) tmem_dealloc_pair(tmem_base, 512);
 }
 
 // =====================================================================================================================
@@ -656,8 +691,8 @@ int mlp_tc_bwd(const nerf_net_cfg* cfg, const NetGeom& g, const float* params, c
   make_bwd_plan(&bplan);
   const uint8_t* packed_bwd = (const uint8_t*)packed + ((fplan.total_bytes + 1023u) & ~1023u);
   uint8_t* dz_ws = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(workspace) + 1023) & ~(uintptr_t)1023);
-  int64_t n_pairs = ((m + kTileM - 1) / kTileM + 1) / 2;
-  int grid = (int)(n_pairs < kNumSMs ? n_pairs : kNumSMs);
+  int64_t n_quads = ((m + kTileM - 1) / kTileM + 3) / 4;
+  int grid = 2 * (int)(n_quads < kNumSMs / 2 ? n_quads : kNumSMs / 2);     // CTA pairs
   const uint32_t dbg = tc_debug_flags();
   if (!(dbg & kDbgNoChain)) {
     mlp_tc_bwd_chain_kernel<<<grid, kThreadsFwd, kSmemCAlloc, st>>>(bplan, packed_bwd, (const uint8_t*)saved, d_out4, m,

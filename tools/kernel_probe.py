@@ -53,6 +53,15 @@ def main():
             med, best = timeit(f)
             print(f"mlp_fwd[{args.mode}] {label:18s} M={m:8d}: {med:8.3f} ms  {2 * MAC_FWD * m / med / 1e9:8.1f} TFLOP/s "
                   f"(best {2 * MAC_FWD * m / best / 1e9:.1f})")
+        # the fused entry point NeRF.render / train_step use: rays + depths in, encodings computed in the prologue
+        o4 = torch.randn(args.rays, 4, device="cuda"); d4 = torch.randn(args.rays, 4, device="cuda")
+        zz = torch.sort(torch.rand(args.rays, s, device="cuda") * 2 + 0.5, -1).values.contiguous()
+        for label, sv in (("rays infer", None), ("rays train", saved)):
+            f = lambda: call("nerf_mlp_fwd_rays", net.cfg_ref, ptr(packed), ptr(o4), ptr(d4), ptr(zz), args.rays, s, ptr(out),
+                             ptr(sv), net.mode_id)
+            med, best = timeit(f)
+            print(f"mlp_fwd[{args.mode}] {label:18s} M={m:8d}: {med:8.3f} ms  {2 * MAC_FWD * m / med / 1e9:8.1f} TFLOP/s "
+                  f"(best {2 * MAC_FWD * m / best / 1e9:.1f})")
         if args.bwd:
             d_out = torch.randn(m, 4, device="cuda")
             grads = torch.zeros(net.n_params, device="cuda")
