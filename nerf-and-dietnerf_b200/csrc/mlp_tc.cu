@@ -156,11 +156,10 @@ __device__ __forceinline__ uint32_t neg_mask32(const uint32_t (&u)[8]) {
 }
 
 // Epilogue of one 32-column group: acc (bias already inside, it rode in the MMA) -> LeakyReLU -> 16-bit -> swizzled
-// panel row.  kMask: returns the negative-sign mask and also stores the four packed 16-byte chunks to
-// gsave + j * 1024 (RBCM block, mlp_tc.cuh) unless gsave is null.
+// panel row.  kMask: returns the negative-sign mask of the 32 values.
 template <bool kMask, bool kHalf>
 __device__ __forceinline__ uint32_t epi_group32(const uint32_t (&acc)[32], float alpha, uint32_t prow_addr, int r,
-                                                int chunk_base, uint8_t* gsave) {
+                                                int chunk_base) {
   uint32_t u[8];
   const uint64_t alpha2 = pack_f32x2(alpha, alpha);
 #pragma unroll
@@ -177,7 +176,6 @@ __device__ __forceinline__ uint32_t epi_group32(const uint32_t (&acc)[32], float
     }
     if (kMask) { u[2 * j] = hi_bytes(pk[0], pk[1]); u[2 * j + 1] = hi_bytes(pk[2], pk[3]); }
     sts128(prow_addr + (((chunk_base + j) ^ (r & 7)) << 4), make_uint4(pk[0], pk[1], pk[2], pk[3]));
-    if (kMask && gsave) stg128(gsave + j * 1024, make_uint4(pk[0], pk[1], pk[2], pk[3]));
   }
   return kMask ? neg_mask32(u) : 0u;
 }
@@ -224,7 +222,7 @@ mlp_tc_fwd_kernel(const __grid_constant__ TcPlan plan, const uint8_t* __restrict
     if (lane == 0) {
       // Static walk over the packed weights (the chunk order of make_plan): no table look-ups, no divisions -- this
       // thread's own instruction latency sits on the path from "stage released" to "stage full".
-      const bool timing = (dbg & kDbgTiming) && blockIdx.x == 0;
+      const bool timing = kTcTrace && (dbg & kDbgTiming) && blockIdx.x == 0;
       long long t_begin = clock64(), t_rel = 0;
       const uint32_t full0 = smem_u32(&bars->full[0]), empty0 = smem_u32(&bars->empty[0]);
       const bool no_copy = (dbg & kDbgNoWeightCopy) != 0;
@@ -281,7 +279,7 @@ mlp_tc_fwd_kernel(const __grid_constant__ TcPlan plan, const uint8_t* __restrict
       // The issuing thread is latency-bound, not the tensor pipe: a generic loop (plan look-ups, descriptor rebuilds,
       // modulo ring indices) cost ~750 cycles per 4-MMA chunk (tools/sm_probe.cu "p"), 1.5x the 512 cycles the MMAs take.
       // So the schedule is spelled out statically (the chunk order of make_plan) and every descriptor is a register add.
-      const bool timing = (dbg & kDbgTiming) && blockIdx.x == 0;
+      const bool timing = kTcTrace && (dbg & kDbgTiming) && blockIdx.x == 0;
       long long t_begin = clock64(), t_act = 0, t_full = 0, t_issue = 0;
       int n_tr = 0;
       const uint32_t fmt = kHalf ? 0 : 1;
@@ -359,7 +357,7 @@ mlp_tc_fwd_kernel(const __grid_constant__ TcPlan plan, const uint8_t* __restrict
     const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)t * 256u;
     const uint32_t wrgb_u32 = sbase + kSmemWrgb;
     uint32_t acc_cnt = 0;
-    const bool timing = (dbg & kDbgTiming) && blockIdx.x == 0 && gtid == 0;
+    const bool timing = kTcTrace && (dbg & kDbgTiming) && blockIdx.x == 0 && gtid == 0;
     long long t_begin = clock64(), t_pro = 0, t_acc = 0, t_epi = 0, t_last = 0;
     int n_tr = 0;
     const uint32_t act_ready_leader = mapa_shared(smem_u32(&bars->act_ready[t]), 0);
@@ -444,20 +442,18 @@ mlp_tc_fwd_kernel(const __grid_constant__ TcPlan plan, const uint8_t* __restrict
         trace(timing, t, n_tr, l * 2);
         if (l < 8) {
           // TMEM loads are double-buffered: group cc+1 is in flight while group cc is processed
-          uint32_t acc[2][32];
-          // this thread's row inside the RBCM block of h_{l+1}; the chunk index adds j * 1024
-          uint8_t* grow = do_store ? saved_tile + (size_t)saved_panel_h(l + 1) * kPanelBytes + rbcm_offset(r, 0, 32) : nullptr;
-          if (!(dbg & kDbgNoEpi)) tmem_ld32(taddr + half * 128, acc[0]);
+          uint32_t acc[kTmemBuffers][32];
+          uint32_t mw[4] = {0u, 0u, 0u, 0u};
+          if (kTmemBuffers == 2 && !(dbg & kDbgNoEpi)) tmem_ld32(taddr + half * 128, acc[0]);
 #pragma unroll
           for (int cc = 0; cc < 4; ++cc) {
             if (dbg & kDbgNoEpi) break;
             const int c0 = half * 128 + cc * 32;
+            if (kTmemBuffers == 1) tmem_ld32(taddr + c0, acc[0]);
             tmem_ld_wait();
-            if (cc + 1 < 4) tmem_ld32(taddr + c0 + 32, acc[(cc + 1) & 1]);
+            if (kTmemBuffers == 2 && cc + 1 < 4) tmem_ld32(taddr + c0 + 32, acc[(cc + 1) & 1]);
             const uint32_t prow = act_u32 + (c0 >> 6) * kPanelBytes + r * 128;
-            const uint32_t mword = epi_group32<kSave, kHalf>(acc[cc & 1], alpha, prow, r, (c0 & 63) >> 3,
-                                                             grow ? grow + (c0 >> 3) * 1024 : nullptr);
-            if (do_store) saved_mask[(l * 8 + (c0 >> 5)) * 128 + r] = mword;
+            mw[cc] = epi_group32<kSave, kHalf>(acc[cc & (kTmemBuffers - 1)], alpha, prow, r, (c0 & 63) >> 3);
           }
           tc_fence_before();
           fence_proxy_async();
@@ -465,6 +461,21 @@ mlp_tc_fwd_kernel(const __grid_constant__ TcPlan plan, const uint8_t* __restrict
           if (lane == 0) mbar_arrive_cluster(act_ready_leader);
           if (timing) t_epi += clock64() - tw;
           trace(timing, t, n_tr, l * 2 + 1);
+          if (do_store && !(dbg & kDbgNoEpi)) {
+            // The saved copy leaves AFTER the MMAs were released: global stores stall the issuing warp (measured: +0.19 ms
+            // per 524k rows when they sat before the arrive).  Re-read this thread's own row of the panels (the next
+            // layer's MMAs only read them; this thread itself is the next writer) and store it coalesced: a warp = 32
+            // consecutive rows of one 16-byte column chunk = 512 contiguous bytes of the RBCM block of h_{l+1}.
+            uint8_t* grow = saved_tile + (size_t)saved_panel_h(l + 1) * kPanelBytes + rbcm_offset(r, half * 16, 32);
+            const uint32_t prow0 = act_u32 + (half * 2) * kPanelBytes + r * 128;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const float4 v = lds128f(prow0 + (j >> 3) * kPanelBytes + (((j & 7) ^ (r & 7)) << 4));
+              stg128(grow + j * 1024, make_uint4(__float_as_uint(v.x), __float_as_uint(v.y), __float_as_uint(v.z), __float_as_uint(v.w)));
+            }
+#pragma unroll
+            for (int cc = 0; cc < 4; ++cc) saved_mask[(l * 8 + half * 4 + cc) * 128 + r] = mw[cc];
+          }
         } else {
           // last layer: cols 0..127 = last hidden (LeakyReLU), col 128 = sigma (linear); rgb head on CUDA cores.
           // half 0 owns cols 0..63, half 1 owns cols 64..127 and sigma; partial rgb sums meet in the (dead) input panel.

@@ -24,6 +24,16 @@ constexpr int kInpOneCol = 38;                    // input-panel columns 38, 39 
 constexpr int kBiasSlabBytes = 256 * 32;          // [256][16] bf16, un-swizzled K-major: the K = 16 slice (input-panel
                                                   // columns 32..47) that adds the bias of a layer without input-panel chunk
 constexpr int kMaxChunks = 48;
+// -DNERF_TC_TRACE=1 compiles the in-kernel handshake timing / event trace in (NERF_TC_DEBUG=256 then prints it); off by
+// default because its 64-bit counters cost registers in kernels that run at the 96-register limit
+#ifndef NERF_TC_TRACE
+#define NERF_TC_TRACE 0
+#endif
+constexpr bool kTcTrace = NERF_TC_TRACE != 0;
+#ifndef NERF_TMEM_BUFFERS
+#define NERF_TMEM_BUFFERS 1
+#endif
+constexpr int kTmemBuffers = NERF_TMEM_BUFFERS;   // 2: tcgen05.ld of column group cc+1 in flight while cc is processed
 constexpr int kEpiWarps = 16;                     // 8 per tile: 4 TMEM lane quarters x 2 column halves
 constexpr int kEpiThreadsPerTile = 256;
 constexpr int kWarpProducer = 16, kWarpMma = 17;

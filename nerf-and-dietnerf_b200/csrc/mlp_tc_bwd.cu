@@ -333,15 +333,15 @@ mlp_tc_bwd_chain_kernel(const __grid_constant__ BwdPlan plan, const uint8_t* __r
         ++acc_cnt;
         tc_fence_after();
         if (kind == STEP_MASK) {
-          uint32_t acc[2][32];
-          uint8_t* grow = dz_tile + (size_t)dz_panel(l) * kPanelBytes + rbcm_offset(r, 0, 32);
-          if (!(dbg & kDbgNoEpi)) tmem_ld32(taddr + half * 128, acc[0]);
+          uint32_t acc[kTmemBuffers][32];
+          if (kTmemBuffers == 2 && !(dbg & kDbgNoEpi)) tmem_ld32(taddr + half * 128, acc[0]);
 #pragma unroll
           for (int cc = 0; cc < 4; ++cc) {
             if (dbg & kDbgNoEpi) break;
             const int c0 = half * 128 + cc * 32;
+            if (kTmemBuffers == 1) tmem_ld32(taddr + c0, acc[0]);
             tmem_ld_wait();
-            if (cc + 1 < 4) tmem_ld32(taddr + c0 + 32, acc[(cc + 1) & 1]);
+            if (kTmemBuffers == 2 && cc + 1 < 4) tmem_ld32(taddr + c0 + 32, acc[(cc + 1) & 1]);
             const uint32_t mw = mw4[cc];
             const uint32_t prow = act_u32 + (c0 >> 6) * kPanelBytes + r * 128;
 #pragma unroll
@@ -349,20 +349,30 @@ mlp_tc_bwd_chain_kernel(const __grid_constant__ BwdPlan plan, const uint8_t* __r
               float v[8];
 #pragma unroll
               for (int i = 0; i < 8; ++i) {
-                float a = __uint_as_float(acc[cc & 1][8 * j + i]);
+                float a = __uint_as_float(acc[cc & (kTmemBuffers - 1)][8 * j + i]);
                 if (l == 8) a = fmaf(d4.w, lds32f(w_sigma_u32 + (c0 + 8 * j + i) * 4), a);
                 v[i] = mask_bit(mw, 8 * j + i) ? a : alpha * a;
               }
               uint4 pk = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]),
                                     pack_bf16x2(v[6], v[7]));
               store_chunk16(prow, r, ((c0 & 63) >> 3) + j, pk);
-              if (do_store) stg128(grow + ((c0 >> 3) + j) * 1024, pk);
             }
           }
           tc_fence_before();
           fence_proxy_async();
           __syncwarp();
           if (s != last_step && lane == 0) mbar_arrive_cluster(act_ready_leader);
+          if (do_store && !(dbg & kDbgNoEpi)) {
+            // dZ_l leaves for HBM AFTER the next MMAs were released (global stores stall the issuing warp): re-read this
+            // thread's own row of the panels and store it coalesced into the RBCM block (see the forward kernel)
+            uint8_t* grow = dz_tile + (size_t)dz_panel(l) * kPanelBytes + rbcm_offset(r, half * 16, 32);
+            const uint32_t prow0 = act_u32 + (half * 2) * kPanelBytes + r * 128;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const float4 v = lds128f(prow0 + (j >> 3) * kPanelBytes + (((j & 7) ^ (r & 7)) << 4));
+              stg128(grow + j * 1024, make_uint4(__float_as_uint(v.x), __float_as_uint(v.y), __float_as_uint(v.z), __float_as_uint(v.w)));
+            }
+          }
         } else {
           if (half == 0) {
             uint32_t a0[32];

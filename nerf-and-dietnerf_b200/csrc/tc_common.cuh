@@ -68,13 +68,15 @@ __device__ __forceinline__ uint32_t mapa_shared(uint32_t addr, uint32_t rank) {
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
   return r;
 }
-// Arrive on an mbarrier that may live in the peer CTA (address from mapa_shared).  RELAXED on purpose: a
-// release.cluster arrive compiles to MEMBAR.ALL.GPU + ERRBAR + CGAERRBAR (~1000 cycles, measured: the per-chunk relay
-// capped the whole forward kernel at one chunk per ~1180 cycles).  What the signal orders lives in the ARRIVING CTA's
-// own shared memory and is read by that CTA's own tensor core (cta_group::2 operands are CTA-local), so a CTA-scope
-// fence before the arrive is all the ordering the data needs.
+// Arrive on an mbarrier that may live in the peer CTA (address from mapa_shared).  RELAXED and fence-free on purpose:
+//  * a release.cluster arrive compiles to MEMBAR.ALL.GPU + ERRBAR + CGAERRBAR (~1000 cycles; as the per-chunk relay it
+//    capped the forward kernel at one chunk per ~1180 cycles);
+//  * even a CTA-scope fence (MEMBAR.ALL.CTA) waits for the thread's outstanding GLOBAL stores -- the training epilogue's
+//    activation stores -- and put their latency on the epilogue -> MMA critical path (ncu: 4.5 % of all samples).
+// What the signal orders lives in the ARRIVING CTA's own shared memory and is consumed by that CTA's own tensor core
+// (cta_group::2 operands are CTA-local): callers run fence.proxy.async (+ __syncwarp for a warp-aggregated arrive) first,
+// which completes their shared-memory writes before this instruction issues.
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("fence.acq_rel.cta;" ::: "memory");
   asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 __device__ __forceinline__ bool mbar_try_wait_cluster(uint32_t bar, uint32_t parity) {
