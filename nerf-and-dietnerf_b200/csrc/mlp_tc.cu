@@ -180,6 +180,23 @@ __device__ __forceinline__ uint32_t epi_group32(const uint32_t (&acc)[32], float
   return kMask ? neg_mask32(u) : 0u;
 }
 
+// sin / cos (pi t) for the fused prologue: exact range reduction r = t - 2 rint(t / 2) in [-1, 1] (exact in fp32), then
+// the SFU on pi r in [-pi, pi] (absolute error ~1e-6, far below the 2^-9 / 2^-12 rounding of the bf16 / fp16 operand it
+// becomes).  ~6 instructions instead of the ~50 of sincospif: the prologue sits on the tile boundary, where the tensor
+// pipe has nothing else to do.
+__device__ __forceinline__ void fast_sincospi(float t, float* sn, float* cs) {
+  const float q = rintf(0.5f * t);
+  const float a = fmaf(-2.f, q, t) * 3.14159265358979f;
+  *sn = __sinf(a);
+  *cs = __cosf(a);
+}
+
+template <bool kHalf>
+__device__ __forceinline__ uint4 pack8_16(const float* v) {
+  return make_uint4(pack_16x2<kHalf>(v[0], v[1]), pack_16x2<kHalf>(v[2], v[3]), pack_16x2<kHalf>(v[4], v[5]),
+                    pack_16x2<kHalf>(v[6], v[7]));
+}
+
 template <bool kSave, bool kHalf>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreadsFwd, 1)
 mlp_tc_fwd_kernel(const __grid_constant__ TcPlan plan, const uint8_t* __restrict__ packed,
@@ -368,7 +385,47 @@ mlp_tc_fwd_kernel(const __grid_constant__ TcPlan plan, const uint8_t* __restrict
       long long tw = timing ? clock64() : 0;
       // ---- prologue: this thread's half of the input panel row: half 0 = xyz columns (16-byte chunks 0..4),
       //      half 1 = view columns (chunks 5..7).  Zero first, then scatter the encoded values as bf16.
-      {
+      if (in.xyz_enc == nullptr && in.Lx == 5 && in.Lv == 4) {
+        // fast path of the reference's network (46 of its 47 configs): the row is assembled in registers with compile-time
+        // column indices and leaves as 16-byte chunks
+        const uint32_t prow = inp_u32 + r * 128;
+        const int64_t ray = row_ok ? row / in.n_samples : 0;
+        const float4 d = row_ok ? __ldg(in.dirs + ray) : make_float4(0.f, 0.f, 0.f, 0.f);
+        if (half == 0) {
+          const float4 o = row_ok ? __ldg(in.origs + ray) : make_float4(0.f, 0.f, 0.f, 0.f);
+          const float zz = row_ok ? __ldg(in.z + row) : 0.f;
+          float v[40];
+#pragma unroll
+          for (int c = 0; c < 3; ++c) {
+            const float oc = c == 0 ? o.x : (c == 1 ? o.y : o.z), dc = c == 0 ? d.x : (c == 1 ? d.y : d.z);
+            const float pc = __fadd_rn(oc, __fmul_rn(dc, zz));         // sample_along_rays, src/UtilsCV.py:598
+            v[c * 11] = pc;
+            float t = pc;
+#pragma unroll
+            for (int k = 0; k < 5; ++k, t *= 2.f) fast_sincospi(t, &v[c * 11 + 1 + 2 * k], &v[c * 11 + 2 + 2 * k]);
+          }
+#pragma unroll
+          for (int i = 33; i < 40; ++i) v[i] = (i >= kInpOneCol) ? 1.f : 0.f;   // the constant-1 columns (bias rows / slabs)
+#pragma unroll
+          for (int j = 0; j < 5; ++j) sts128(prow + ((j ^ (r & 7)) << 4), pack8_16<kHalf>(v + 8 * j));
+        } else {
+          float v[24];
+#pragma unroll
+          for (int c = 0; c < 3; ++c) {
+            const float vc = (in.ncomp == 3) ? (c == 0 ? d.x : (c == 1 ? d.y : d.z)) : (c == 0 ? d.x : d.z);
+            float t = vc;
+#pragma unroll
+            for (int k = 0; k < 4; ++k, t *= 2.f) {
+              float sn, cs;
+              fast_sincospi(t, &sn, &cs);
+              v[c * 8 + 2 * k] = (c < in.ncomp && row_ok) ? sn : 0.f;
+              v[c * 8 + 2 * k + 1] = (c < in.ncomp && row_ok) ? cs : 0.f;
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < 3; ++j) sts128(prow + (((5 + j) ^ (r & 7)) << 4), pack8_16<kHalf>(v + 8 * j));
+        }
+      } else {
         const uint32_t prow = inp_u32 + r * 128;
         const int cb = half ? 5 : 0, ce = half ? 8 : 5;
         for (int j = cb; j < ce; ++j) sts128(prow + ((j ^ (r & 7)) << 4), make_uint4(0u, 0u, 0u, 0u));
