@@ -157,9 +157,9 @@ __device__ __forceinline__ uint32_t neg_mask32(const uint32_t (&u)[8]) {
 
 // Epilogue of one 32-column group: acc (bias already inside, it rode in the MMA) -> LeakyReLU -> 16-bit -> swizzled
 // panel row.  kMask: returns the negative-sign mask of the 32 values.
+// pbx = (panel row address) | ((row & 7) << 4): a 16-byte chunk address is one XOR with an immediate.
 template <bool kMask, bool kHalf>
-__device__ __forceinline__ uint32_t epi_group32(const uint32_t (&acc)[32], float alpha, uint32_t prow_addr, int r,
-                                                int chunk_base) {
+__device__ __forceinline__ uint32_t epi_group32(const uint32_t (&acc)[32], float alpha, uint32_t pbx, int chunk_base) {
   uint32_t u[8];
   const uint64_t alpha2 = pack_f32x2(alpha, alpha);
 #pragma unroll
@@ -175,7 +175,7 @@ __device__ __forceinline__ uint32_t epi_group32(const uint32_t (&acc)[32], float
       pk[i] = pack_16x2<kHalf>(fmaxf(x0, l0), fmaxf(x1, l1)); // LeakyReLU for 0 <= alpha <= 1
     }
     if (kMask) { u[2 * j] = hi_bytes(pk[0], pk[1]); u[2 * j + 1] = hi_bytes(pk[2], pk[3]); }
-    sts128(prow_addr + (((chunk_base + j) ^ (r & 7)) << 4), make_uint4(pk[0], pk[1], pk[2], pk[3]));
+    sts128(pbx ^ (uint32_t)((chunk_base + j) << 4), make_uint4(pk[0], pk[1], pk[2], pk[3]));
   }
   return kMask ? neg_mask32(u) : 0u;
 }
@@ -509,8 +509,8 @@ mlp_tc_fwd_kernel(const __grid_constant__ TcPlan plan, const uint8_t* __restrict
             if (kTmemBuffers == 1) tmem_ld32(taddr + c0, acc[0]);
             tmem_ld_wait();
             if (kTmemBuffers == 2 && cc + 1 < 4) tmem_ld32(taddr + c0 + 32, acc[(cc + 1) & 1]);
-            const uint32_t prow = act_u32 + (c0 >> 6) * kPanelBytes + r * 128;
-            mw[cc] = epi_group32<kSave, kHalf>(acc[cc & (kTmemBuffers - 1)], alpha, prow, r, (c0 & 63) >> 3);
+            const uint32_t pbx = (act_u32 + (c0 >> 6) * kPanelBytes + r * 128) | ((uint32_t)(r & 7) << 4);
+            mw[cc] = epi_group32<kSave, kHalf>(acc[cc & (kTmemBuffers - 1)], alpha, pbx, (c0 & 63) >> 3);
           }
           tc_fence_before();
           fence_proxy_async();
@@ -524,10 +524,10 @@ mlp_tc_fwd_kernel(const __grid_constant__ TcPlan plan, const uint8_t* __restrict
             // layer's MMAs only read them; this thread itself is the next writer) and store it coalesced: a warp = 32
             // consecutive rows of one 16-byte column chunk = 512 contiguous bytes of the RBCM block of h_{l+1}.
             uint8_t* grow = saved_tile + (size_t)saved_panel_h(l + 1) * kPanelBytes + rbcm_offset(r, half * 16, 32);
-            const uint32_t prow0 = act_u32 + (half * 2) * kPanelBytes + r * 128;
+            const uint32_t pbx = (act_u32 + (half * 2) * kPanelBytes + r * 128) | ((uint32_t)(r & 7) << 4);
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
-              const float4 v = lds128f(prow0 + (j >> 3) * kPanelBytes + (((j & 7) ^ (r & 7)) << 4));
+              const float4 v = lds128f((pbx + (j >> 3) * kPanelBytes) ^ (uint32_t)((j & 7) << 4));
               stg128(grow + j * 1024, make_uint4(__float_as_uint(v.x), __float_as_uint(v.y), __float_as_uint(v.z), __float_as_uint(v.w)));
             }
 #pragma unroll

@@ -136,6 +136,39 @@ __device__ __forceinline__ void store_chunk16(uint32_t panel_row_addr, int r, in
   sts128(panel_row_addr + ((chunk16 ^ (r & 7)) << 4), v);
 }
 
+// Epilogue of one dX step for this thread's 128 columns: accumulator (+ the sigma-head rank-1 term of the first step)
+// -> LeakyReLU' from the sign mask -> bf16 -> swizzled panel row.  pbx = (panel row address) | ((row & 7) << 4) of the
+// first of the thread's two panels, so a 16-byte chunk address is one XOR with an immediate.
+template <bool kSigma>
+__device__ __forceinline__ void chain_mask_epilogue(uint32_t taddr_half, const uint32_t (&mw4)[4], uint32_t pbx, float alpha,
+                                                    float dsig, uint32_t w_sigma_half_u32) {
+#pragma unroll
+  for (int cc = 0; cc < 4; ++cc) {
+    uint32_t acc[32];
+    tmem_ld32(taddr_half + cc * 32, acc);
+    tmem_ld_wait();
+    const uint32_t mw = mw4[cc];
+    const uint32_t pb = pbx + (cc >> 1) * kPanelBytes;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float w[8];
+      if (kSigma) {
+        const float4 w0 = lds128f(w_sigma_half_u32 + (cc * 32 + 8 * j) * 4), w1 = lds128f(w_sigma_half_u32 + (cc * 32 + 8 * j + 4) * 4);
+        w[0] = w0.x; w[1] = w0.y; w[2] = w0.z; w[3] = w0.w; w[4] = w1.x; w[5] = w1.y; w[6] = w1.z; w[7] = w1.w;
+      }
+      float v[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        float a = __uint_as_float(acc[8 * j + i]);
+        if (kSigma) a = fmaf(dsig, w[i], a);
+        v[i] = mask_bit(mw, 8 * j + i) ? a : alpha * a;
+      }
+      sts128(pb ^ (uint32_t)((((cc & 1) * 4 + j)) << 4),
+             make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7])));
+    }
+  }
+}
+
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreadsFwd, 1)
 mlp_tc_bwd_chain_kernel(const __grid_constant__ BwdPlan plan, const uint8_t* __restrict__ packed,
                         const uint8_t* __restrict__ saved, const float* __restrict__ d_out4, int64_t M,
@@ -315,10 +348,10 @@ mlp_tc_bwd_chain_kernel(const __grid_constant__ BwdPlan plan, const uint8_t* __r
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(act_ready_leader);
+
       float xs[32];                                      // d(xyz encoding): half 0 -> cols 0..31, half 1 -> cols 32..39
 #pragma unroll
       for (int i = 0; i < 32; ++i) xs[i] = 0.f;
-
       for (int s = 0; s < plan.n_steps; ++s) {
         const int kind = plan.step_kind[s];
         if (!need_dx && kind != STEP_MASK) continue;
@@ -333,30 +366,10 @@ mlp_tc_bwd_chain_kernel(const __grid_constant__ BwdPlan plan, const uint8_t* __r
         ++acc_cnt;
         tc_fence_after();
         if (kind == STEP_MASK) {
-          uint32_t acc[kTmemBuffers][32];
-          if (kTmemBuffers == 2 && !(dbg & kDbgNoEpi)) tmem_ld32(taddr + half * 128, acc[0]);
-#pragma unroll
-          for (int cc = 0; cc < 4; ++cc) {
-            if (dbg & kDbgNoEpi) break;
-            const int c0 = half * 128 + cc * 32;
-            if (kTmemBuffers == 1) tmem_ld32(taddr + c0, acc[0]);
-            tmem_ld_wait();
-            if (kTmemBuffers == 2 && cc + 1 < 4) tmem_ld32(taddr + c0 + 32, acc[(cc + 1) & 1]);
-            const uint32_t mw = mw4[cc];
-            const uint32_t prow = act_u32 + (c0 >> 6) * kPanelBytes + r * 128;
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              float v[8];
-#pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                float a = __uint_as_float(acc[cc & (kTmemBuffers - 1)][8 * j + i]);
-                if (l == 8) a = fmaf(d4.w, lds32f(w_sigma_u32 + (c0 + 8 * j + i) * 4), a);
-                v[i] = mask_bit(mw, 8 * j + i) ? a : alpha * a;
-              }
-              uint4 pk = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]),
-                                    pack_bf16x2(v[6], v[7]));
-              store_chunk16(prow, r, ((c0 & 63) >> 3) + j, pk);
-            }
+          if (!(dbg & kDbgNoEpi)) {
+            const uint32_t pbx = (act_u32 + (half * 2) * kPanelBytes + r * 128) | ((uint32_t)(r & 7) << 4);
+            if (l == 8) chain_mask_epilogue<true>(taddr + half * 128, mw4, pbx, alpha, d4.w, w_sigma_u32 + half * 512);
+            else chain_mask_epilogue<false>(taddr + half * 128, mw4, pbx, alpha, 0.f, 0u);
           }
           tc_fence_before();
           fence_proxy_async();
@@ -366,10 +379,10 @@ mlp_tc_bwd_chain_kernel(const __grid_constant__ BwdPlan plan, const uint8_t* __r
             // dZ_l leaves for HBM AFTER the next MMAs were released (global stores stall the issuing warp): re-read this
             // thread's own row of the panels and store it coalesced into the RBCM block (see the forward kernel)
             uint8_t* grow = dz_tile + (size_t)dz_panel(l) * kPanelBytes + rbcm_offset(r, half * 16, 32);
-            const uint32_t prow0 = act_u32 + (half * 2) * kPanelBytes + r * 128;
+            const uint32_t pbx = (act_u32 + (half * 2) * kPanelBytes + r * 128) | ((uint32_t)(r & 7) << 4);
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
-              const float4 v = lds128f(prow0 + (j >> 3) * kPanelBytes + (((j & 7) ^ (r & 7)) << 4));
+              const float4 v = lds128f((pbx + (j >> 3) * kPanelBytes) ^ (uint32_t)((j & 7) << 4));
               stg128(grow + j * 1024, make_uint4(__float_as_uint(v.x), __float_as_uint(v.y), __float_as_uint(v.z), __float_as_uint(v.w)));
             }
           }
