@@ -623,7 +623,7 @@ int64_t mlp_tc_workspace_bytes(const NetGeom& g, int64_t m, int backward) {
   if (!backward) return 256;
   int64_t tiles = (m + kTileM - 1) / kTileM;
   tiles = (tiles + 3) / 4 * 4;
-  return tiles * (int64_t)kDzTileBytes + 1024;
+  return tiles * (int64_t)kDzTileBytes + 1024 + kDwScratchBytes;
 }
 
 // byte offset of the fp16 copy of the forward weight pack inside the packed buffer: [bf16 fwd | bf16 bwd | fp16 fwd]

@@ -136,6 +136,10 @@ enum : uint32_t {
 };
 uint32_t tc_debug_flags();
 
+// dW split-K partials (backward workspace, after the dZ tiles): one 256 x 256 fp32 block + 256 bias sums per dW CTA
+constexpr int64_t kDwPartialFloats = 256 * 256 + 256;
+constexpr int64_t kDwScratchBytes = (int64_t)148 * kDwPartialFloats * 4;
+
 // backward half of the bf16 weight pack (defined in mlp_tc_bwd.cu)
 uint32_t bwd_pack_bytes();
 int bwd_pack_weights(const NetGeom& g, const float* params, uint8_t* packed_bwd, cudaStream_t st);

@@ -322,6 +322,26 @@ def test_mlp_backward(pkg, mode, tol, n_angles, l_view, m):
         assert rel_p32 < 0.15 and rel_x32 < 0.2
 
 
+def test_mlp_backward_bf16_is_deterministic(pkg):
+    """The weight gradients are reduced from per-CTA split-K partials in a fixed order (no atomics): two backward passes
+    over the same tile-spanning input give bit-identical gradients, weights and input gradients alike."""
+    ocfg = oracle_cfg(2, 4)
+    p = O.glorot_params(ocfg.shapes, 8, bias_scale=0.1)
+    m = 128 * 37 + 19                                  # many tiles per dW CTA split, ragged last tile
+    xyz, view = _mlp_inputs(ocfg, m, 9)
+    g = torch.randn(m, 4, generator=torch.Generator().manual_seed(10))
+    grads = []
+    for _ in range(2):
+        net = pkg.NerfMLP(pkg.NetCfg(5, 4, 2, 256, 128, 0.05), mode="bf16")
+        net.set_params(p)
+        pg = net.params.requires_grad_(True)
+        xg = dev(xyz).requires_grad_(True)
+        net(xg, dev(view)).backward(dev(g))
+        grads.append((pg.grad.clone(), xg.grad.clone()))
+    assert torch.equal(grads[0][0], grads[1][0])
+    assert torch.equal(grads[0][1], grads[1][1])
+
+
 # ---- render / train step -------------------------------------------------------------------------------------------------
 def _model(pkg, mode, n_angles=2, l_view=4, n_c=64, n_f=128, cls=None, sigma_gain=30.0, **kw):
     ocfg = oracle_cfg(n_angles, l_view)

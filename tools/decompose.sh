@@ -4,5 +4,5 @@
 #   64 no chain launch   128 no dW launch
 for f in ${FLAGS:-0 1 2 4 8 5 6 12 64 128 80 112 114}; do
   echo "== NERF_TC_DEBUG=$f"
-  NERF_TC_DEBUG=$f timeout 120 python tools/kernel_probe.py --rays 4096 --bwd --only mlp 2>&1 | grep -E "M=  524288|rror|rap"
+  NERF_TC_DEBUG=$f timeout 120 python tools/kernel_probe.py --rays ${RAYS:-4096} --bwd --only mlp 2>&1 | grep -E "${ROWS:-M=  524288}|rror|rap"
 done
