@@ -256,7 +256,8 @@ def main():
 
     @contextlib.contextmanager
     def hook(name):
-        if name in ("nerf_mlp_fwd", "nerf_mlp_fwd_rays", "nerf_mlp_bwd", "nerf_composite_fwd", "nerf_composite_bwd"):
+        if name in ("nerf_mlp_fwd", "nerf_mlp_fwd_rays", "nerf_mlp_bwd", "nerf_mlp_bwd_dx", "nerf_mlp_bwd_dw",
+                    "nerf_composite_fwd", "nerf_composite_bwd"):
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record()
             yield
@@ -293,21 +294,40 @@ def main():
         peak_tf = peaks.get("bf16_tflops_sustained", 1400.0)
         peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained" if "bf16_tflops_sustained" in peaks else \
             "fallback (B200_PROFILING.md: ~1.4 PFLOP/s sustained)"
-        # dominant kernel group by time: the two MLP-backward kernels of one nerf_mlp_bwd call (dX chain + dW);
-        # algorithmic FLOPs per call, averaged over the coarse (64 samples) and fine (128 samples) calls of a step
-        bwd_flops = 2 * batch * (N_C * (MAC_FWD + MAC_DX_COARSE) + N_F * (MAC_FWD + MAC_DX_FINE)) / 2
+        # Dominant kernel by time (profiles/r01_e_launches_summary.txt: 34 % of the step): mlp_tc_bwd_dw_kernel, the weight
+        # gradients.  Its arithmetic intensity is fixed by the 256x256 output it keeps in TMEM (128 FLOP/B), so its
+        # roofline is HBM: it streams every saved activation and every dZ once.  Algorithmic bytes per sample (DESIGN.md
+        # 4): bf16 saved activations (64 + 8*256 + 128 columns) + bf16 dZ (8*256 + 144 + 16 columns) = 8896 B.  The
+        # launch time is the nerf_mlp_bwd_dw call (dW kernel + its 15 us fixed-order reduce), averaged over the coarse
+        # (64 samples/ray) and fine (128) calls of a step; `traffic` is dram read+write of the same two launches from
+        # the ncu --set full capture (profiles/r01_e_mlp_full_summary.txt: 9806 B/sample).
+        samples_per_launch = batch * (N_C + N_F) / 2
+        dw_ms = call_ms.get("nerf_mlp_bwd_dw", float("nan"))
+        dx_ms = call_ms.get("nerf_mlp_bwd_dx", float("nan"))
+        fwd_ms = call_ms.get("nerf_mlp_fwd_rays", call_ms.get("nerf_mlp_fwd", float("nan")))
+        peak_hbm = peaks.get("hbm_gbs", 6500.0)
         fwd_flops = 2 * batch * (N_C + N_F) * MAC_FWD / 2
-        roof_name = "nerf_mlp_bwd"
-        ach = bwd_flops / (call_ms.get("nerf_mlp_bwd", float("nan")) * 1e-3) / 1e12
-        roofline = {"bound": "tensor", "kernel": "mlp_tc_bwd_chain_kernel + mlp_tc_bwd_dw_kernel (one nerf_mlp_bwd call)",
-                    "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf, "traffic": None,
-                    "peak_source": peak_src,
-                    "fwd_kernel": {"kernel": "mlp_tc_fwd_kernel<save>",
-                                   "achieved": fwd_flops / (call_ms.get("nerf_mlp_fwd_rays", call_ms.get("nerf_mlp_fwd", float("nan"))) * 1e-3) / 1e12},
-                    "step_tensor_frac": FLOP_PER_RAY_TRAIN * value / 1e12 / peak_tf,
+        dx_flops = 2 * batch * (N_C * MAC_DX_COARSE + N_F * MAC_DX_FINE) / 2
+        dw_flops = fwd_flops
+        ach = 8896 * samples_per_launch / (dw_ms * 1e-3) / 1e9
+        tensor = {
+            "peak": peak_tf, "peak_source": peak_src, "unit": "TFLOP/s",
+            "mlp_tc_fwd_kernel<save>": {"achieved": fwd_flops / (fwd_ms * 1e-3) / 1e12, "ms": fwd_ms},
+            "mlp_tc_bwd_chain_kernel": {"achieved": dx_flops / (dx_ms * 1e-3) / 1e12, "ms": dx_ms},
+            "mlp_tc_bwd_dw_kernel": {"achieved": dw_flops / (dw_ms * 1e-3) / 1e12, "ms": dw_ms},
+            "step_tensor_frac": FLOP_PER_RAY_TRAIN * value / 1e12 / peak_tf,
+        }
+        for k in ("mlp_tc_fwd_kernel<save>", "mlp_tc_bwd_chain_kernel", "mlp_tc_bwd_dw_kernel"):
+            tensor[k]["frac"] = tensor[k]["achieved"] / peak_tf
+        roofline = {"bound": "hbm", "kernel": "mlp_tc_bwd_dw_kernel (nerf_mlp_bwd_dw call)",
+                    "achieved": ach, "peak": peak_hbm, "unit": "GB/s", "frac": ach / peak_hbm,
+                    "traffic": 9806 * samples_per_launch,
+                    "peak_source": "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6.5 TB/s",
+                    "algorithmic_bytes_per_launch": 8896 * samples_per_launch,
+                    "tensor_kernels": tensor,
                     "avg_call_ms": call_ms, "calls_per_step": call_n}
         if args.mode != "bf16":
-            roofline["bound"] = "tensor (fp32 SIMT parity mode: not a tensor-core number)"
+            roofline["bound"] = "fp32 SIMT parity mode: the bf16 rooflines above do not apply"
         cpu = None
         if not args.no_cpu_baseline:
             rate, cores = cpu_reference_rate(args.config, 128, 3)

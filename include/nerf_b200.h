@@ -120,6 +120,18 @@ int nerf_mlp_bwd(const nerf_net_cfg* cfg, const float* params, const void* packe
                  const float* xyz_enc, const float* view_enc, const void* saved, const float* d_out4,
                  int64_t m, float* grads, float* d_xyz_enc_or_null, void* workspace, int32_t mode,
                  void* stream);
+/* The two halves of nerf_mlp_bwd in NERF_MODE_BF16 (same arguments), for callers that time or overlap them:
+ * _dx = the input-gradient chain (writes dZ of every layer into the workspace and d_xyz_enc), _dw = the weight
+ * gradients from the saved activations and that workspace (deterministic split-K reduction).  _dw must follow _dx on
+ * the same workspace.  TF autodiff of the Keras models in NeRF.train_step (src/NeRF.py:149-167) is what both replace. */
+int nerf_mlp_bwd_dx(const nerf_net_cfg* cfg, const float* params, const void* packed_or_null,
+                    const float* xyz_enc, const float* view_enc, const void* saved, const float* d_out4,
+                    int64_t m, float* grads, float* d_xyz_enc_or_null, void* workspace, int32_t mode,
+                    void* stream);
+int nerf_mlp_bwd_dw(const nerf_net_cfg* cfg, const float* params, const void* packed_or_null,
+                    const float* xyz_enc, const float* view_enc, const void* saved, const float* d_out4,
+                    int64_t m, float* grads, float* d_xyz_enc_or_null, void* workspace, int32_t mode,
+                    void* stream);
 /* bf16 weight pack for the tensor-core path (re-run after every optimizer step). */
 int64_t nerf_packed_bytes(const nerf_net_cfg* cfg);
 int nerf_pack_weights(const nerf_net_cfg* cfg, const float* params, void* packed, void* stream);

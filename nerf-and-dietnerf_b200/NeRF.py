@@ -14,7 +14,7 @@ from typing import Dict
 import torch
 
 from . import _lib
-from ._lib import NetCfg, call, f32c, ptr
+from ._lib import MODE_BF16, NetCfg, call, f32c, ptr
 from .ConfigurationKeys import (HIDDEN_LAYER_DIM, LAST_HIDDEN_LAYER_DIM, LEAKY_RELU_ALPHA, N_ANGLES_FOR_MODEL,
                                 N_POS_ENC_DIM_XYZ, N_POS_ENC_VIEW_DIR, N_RAYS_IN_BATCH_RENDER, N_RAYS_IN_BATCH_TRAIN,
                                 N_RENDER_SAMPLES_COARSE, N_RENDER_SAMPLES_FINE)
@@ -320,9 +320,8 @@ class NeRF:
             through_z = not self.stop_grad_z
             call("nerf_composite_bwd", ptr(w.raw_f), ptr(w.z_f), ptr(w.d_rgb_f), None, n, sf, ptr(w.d_raw_f),
                  ptr(w.d_z_f) if through_z else None)
-            call("nerf_mlp_bwd", mf.cfg_ref, ptr(mf.params), ptr(mf.packed_for(mf.params)), ptr(w.xyz_f),
-                 ptr(w.view_f), ptr(w.saved_f), ptr(w.d_raw_f), n * sf, ptr(g_f), ptr(w.d_xyz_f) if through_z else None,
-                 ptr(w.ws_bwd), mf.mode_id)
+            self._mlp_bwd(mf, w.xyz_f, w.view_f, w.saved_f, w.d_raw_f, n * sf, g_f, w.d_xyz_f if through_z else None,
+                          w.ws_bwd)
             if through_z:
                 # z_f -> xyz -> PE -> fine net, and z_f -> delta in the fine compositing, reach the coarse weights
                 call("nerf_encode_samples_bwd_z", mf.cfg_ref, ptr(o), ptr(d), ptr(w.z_f), ptr(w.d_xyz_f), n, sf,
@@ -332,9 +331,20 @@ class NeRF:
                 d_w_c = w.d_w_c
         # coarse backward
         call("nerf_composite_bwd", ptr(w.raw_c), ptr(w.z_c), ptr(w.d_rgb_c), ptr(d_w_c), n, sc, ptr(w.d_raw_c), None)
-        call("nerf_mlp_bwd", mc.cfg_ref, ptr(mc.params), ptr(mc.packed_for(mc.params)), ptr(w.xyz_c), ptr(w.view_c),
-             ptr(w.saved_c), ptr(w.d_raw_c), n * sc, ptr(g_c), None, ptr(w.ws_bwd), mc.mode_id)
+        self._mlp_bwd(mc, w.xyz_c, w.view_c, w.saved_c, w.d_raw_c, n * sc, g_c, None, w.ws_bwd)
         return g_c, g_f, sums
+
+    @staticmethod
+    def _mlp_bwd(net, xyz, view, saved, d_raw, m, grads, d_xyz, ws):
+        """TF autodiff of one Keras model (src/NeRF.py:149-167).  The tensor-core path runs its two halves as separate
+        C-ABI calls (input-gradient chain, then weight gradients) so that they can be timed / overlapped separately."""
+        args = (net.cfg_ref, ptr(net.params), ptr(net.packed_for(net.params)), ptr(xyz), ptr(view), ptr(saved), ptr(d_raw), m,
+                ptr(grads), ptr(d_xyz), ptr(ws), net.mode_id)
+        if net.mode_id == MODE_BF16:
+            call("nerf_mlp_bwd_dx", *args)
+            call("nerf_mlp_bwd_dw", *args)
+        else:
+            call("nerf_mlp_bwd", *args)
 
     def _mlp_fwd_train(self, net, o, d, z, n, s, xyz, view, raw, saved, ws):
         """Training-mode MLP forward (activations saved): fused encode+MLP kernel in bf16 mode, two kernels in fp32."""

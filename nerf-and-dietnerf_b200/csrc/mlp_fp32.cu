@@ -11,7 +11,7 @@ int mlp_tc_fwd(const nerf_net_cfg* cfg, const NetGeom& g, const float* params, c
                const float* view_enc, int64_t m, float* out4, void* saved, void* workspace, cudaStream_t st, bool half);
 int mlp_tc_bwd(const nerf_net_cfg* cfg, const NetGeom& g, const float* params, const void* packed, const float* xyz_enc,
                const float* view_enc, const void* saved, const float* d_out4, int64_t m, float* grads, float* d_xyz_enc,
-               void* workspace, cudaStream_t st);
+               void* workspace, cudaStream_t st, int parts);
 int mlp_tc_fwd_rays(const nerf_net_cfg* cfg, const NetGeom& g, const void* packed, const float* origs4, const float* dirs4,
                     const float* z, int64_t n_rays, int n_samples, float* out4, void* saved, cudaStream_t st, bool half);
 int64_t mlp_tc_saved_bytes(const NetGeom& g, int64_t m);
@@ -374,9 +374,11 @@ int nerf_mlp_fwd_rays(const nerf_net_cfg* cfg, const void* packed, const float* 
                          mode == NERF_MODE_FP16);
 }
 
-int nerf_mlp_bwd(const nerf_net_cfg* cfg, const float* params, const void* packed_or_null, const float* xyz_enc,
-                 const float* view_enc, const void* saved, const float* d_out4, int64_t m, float* grads,
-                 float* d_xyz_enc_or_null, void* workspace, int32_t mode, void* stream) {
+// parts: bit 0 = input-gradient chain (dZ of every layer, d_xyz_enc), bit 1 = weight gradients from the saved activations
+// and the dZ workspace.  The fp32 path computes both in one pass (parts must be 3).
+static int mlp_bwd_parts(const nerf_net_cfg* cfg, const float* params, const void* packed_or_null, const float* xyz_enc,
+                         const float* view_enc, const void* saved, const float* d_out4, int64_t m, float* grads,
+                         float* d_xyz_enc_or_null, void* workspace, int32_t mode, void* stream, int parts) {
   NetGeom g;
   NERF_CHECK_ARG(make_geom(cfg, &g), "bad net config");
   NERF_CHECK_ARG(params && saved && d_out4 && grads && workspace, "null pointer");
@@ -384,16 +386,38 @@ int nerf_mlp_bwd(const nerf_net_cfg* cfg, const float* params, const void* packe
   NERF_CHECK_ARG(mode == NERF_MODE_BF16 || (xyz_enc && (view_enc || !g.view)), "null pointer");
   NERF_CHECK_ARG(m >= 0, "negative row count");
   NERF_CHECK_ARG(mode == NERF_MODE_FP32 || mode == NERF_MODE_BF16, "unknown mode");
+  NERF_CHECK_ARG(mode == NERF_MODE_BF16 || parts == 3, "NERF_MODE_FP32 computes both halves of the backward in one pass");
   if (m == 0) return NERF_OK;
   if (mode == NERF_MODE_BF16) {
     NERF_CHECK_ARG(packed_or_null, "NERF_MODE_BF16 needs the packed weights (nerf_pack_weights)");
     return mlp_tc_bwd(cfg, g, params, packed_or_null, xyz_enc, view_enc, saved, d_out4, m, grads, d_xyz_enc_or_null,
-                      workspace, (cudaStream_t)stream);
+                      workspace, (cudaStream_t)stream, parts);
   }
   fp32_bwd(cfg, g, params, xyz_enc, view_enc, (const float*)saved, d_out4, m, grads, d_xyz_enc_or_null,
            (float*)workspace, (cudaStream_t)stream);
   NERF_CHECK_LAUNCH();
   return NERF_OK;
+}
+
+int nerf_mlp_bwd(const nerf_net_cfg* cfg, const float* params, const void* packed_or_null, const float* xyz_enc,
+                 const float* view_enc, const void* saved, const float* d_out4, int64_t m, float* grads,
+                 float* d_xyz_enc_or_null, void* workspace, int32_t mode, void* stream) {
+  return mlp_bwd_parts(cfg, params, packed_or_null, xyz_enc, view_enc, saved, d_out4, m, grads, d_xyz_enc_or_null, workspace,
+                       mode, stream, 3);
+}
+
+int nerf_mlp_bwd_dx(const nerf_net_cfg* cfg, const float* params, const void* packed_or_null, const float* xyz_enc,
+                    const float* view_enc, const void* saved, const float* d_out4, int64_t m, float* grads,
+                    float* d_xyz_enc_or_null, void* workspace, int32_t mode, void* stream) {
+  return mlp_bwd_parts(cfg, params, packed_or_null, xyz_enc, view_enc, saved, d_out4, m, grads, d_xyz_enc_or_null, workspace,
+                       mode, stream, 1);
+}
+
+int nerf_mlp_bwd_dw(const nerf_net_cfg* cfg, const float* params, const void* packed_or_null, const float* xyz_enc,
+                    const float* view_enc, const void* saved, const float* d_out4, int64_t m, float* grads,
+                    float* d_xyz_enc_or_null, void* workspace, int32_t mode, void* stream) {
+  return mlp_bwd_parts(cfg, params, packed_or_null, xyz_enc, view_enc, saved, d_out4, m, grads, d_xyz_enc_or_null, workspace,
+                       mode, stream, 2);
 }
 
 }  // extern "C"

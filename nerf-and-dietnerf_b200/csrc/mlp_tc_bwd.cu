@@ -728,7 +728,7 @@ mlp_tc_bwd_dw_reduce_kernel(const __grid_constant__ DwPlan plan, const __grid_co
 // ---- host ---------------------------------------------------------------------------------------------------------------
 int mlp_tc_bwd(const nerf_net_cfg* cfg, const NetGeom& g, const float* params, const void* packed, const float* xyz_enc,
                const float* view_enc, const void* saved, const float* d_out4, int64_t m, float* grads, float* d_xyz_enc,
-               void* workspace, cudaStream_t st) {
+               void* workspace, cudaStream_t st, int parts) {
   (void)params; (void)xyz_enc; (void)view_enc;
   TcPlan fplan;
   if (!make_plan(g, &fplan)) {
@@ -748,14 +748,14 @@ int mlp_tc_bwd(const nerf_net_cfg* cfg, const NetGeom& g, const float* params, c
   int64_t n_quads = ((m + kTileM - 1) / kTileM + 3) / 4;
   int grid = 2 * (int)(n_quads < kNumSMs / 2 ? n_quads : kNumSMs / 2);     // CTA pairs
   const uint32_t dbg = tc_debug_flags();
-  if (!(dbg & kDbgNoChain)) {
+  if (!(dbg & kDbgNoChain) && (parts & 1)) {
     mlp_tc_bwd_chain_kernel<<<grid, kThreadsFwd, kSmemCAlloc, st>>>(bplan, packed_bwd, (const uint8_t*)saved, d_out4, m,
                                                                    dz_ws, d_xyz_enc, g.dx, cfg->leaky_alpha, dbg);
     NERF_CHECK_LAUNCH();
   }
   DwPlan dplan;
   make_dw_plan(&dplan, kNumSMs);
-  if (!(dbg & kDbgNoDw)) {
+  if (!(dbg & kDbgNoDw) && (parts & 2)) {
     int64_t tiles4 = ((m + kTileM - 1) / kTileM + 3) / 4 * 4;
     float* scratch = reinterpret_cast<float*>(dz_ws + tiles4 * (int64_t)kDzTileBytes);
     mlp_tc_bwd_dw_kernel<<<kNumSMs, kThreadsDw, kSmemDwAlloc, st>>>(dplan, g, (const uint8_t*)saved, dz_ws, m, scratch, dbg);
