@@ -123,8 +123,10 @@ __device__ __forceinline__ void trace(bool on, int who, int& n, int code) {
 
 struct FwdBars {
   uint64_t full[kStages], empty[kStages], act_ready[2], acc_full[2];
+  uint64_t panel_full[2], panel_free[2];   // train mode: epilogue warps <-> the tile's store warp
   uint32_t tmem_base;
 };
+static_assert(sizeof(FwdBars) <= 192, "barrier block overflows its shared-memory slot");
 
 // Where the MLP input comes from: pre-encoded rows (xyz_enc / view_enc, the standalone model_predict entry point) or,
 // when xyz_enc == nullptr, rays + depths: then the sample position o + d z and both sin/cos encodings are computed in
@@ -220,6 +222,8 @@ mlp_tc_fwd_kernel(const __grid_constant__ TcPlan plan, const uint8_t* __restrict
     for (int t = 0; t < 2; ++t) {
       mbar_init(smem_u32(&bars->act_ready[t]), 2 * 8);   // leader's copy: one arrive per epilogue warp of BOTH CTAs
       mbar_init(smem_u32(&bars->acc_full[t]), 1);
+      mbar_init(smem_u32(&bars->panel_full[t]), 8);      // one arrive per epilogue warp of the tile
+      mbar_init(smem_u32(&bars->panel_free[t]), 2);      // both store warps
     }
     fence_barrier_init();
   }
@@ -363,6 +367,41 @@ mlp_tc_fwd_kernel(const __grid_constant__ TcPlan plan, const uint8_t* __restrict
                  (int)(g_trace[2][i] & 2) >> 1, (g_trace[2][i] & 1) ? "issued" : "act_ready");
       }
     }
+  } else if (warp >= kWarpStore) {
+    // ===== store warps (train mode): tile t's freshly written activation panels -> HBM, row-block chunk-major =====
+    // Global stores stall the issuing warp whenever the 32 B/clk SM->L2 port is busy (64 KB per tile-layer = 2048
+    // cycles, as long as the MMAs of that tile-layer).  Issued from the epilogue warps they delayed the next epilogue;
+    // a dedicated warp per tile absorbs the stalls while the epilogue warps go back to waiting for accumulators.
+    // Both store warps work on EVERY copy (one half of the column chunks each): the two tiles' copies alternate in
+    // time, and one warp alone does not saturate the port.
+    if (kSave) {
+      const int hw = warp - kWarpStore;                  // which half of the 32 column chunks
+      const bool do_store = !(dbg & kDbgNoStore);
+      uint32_t ph = 0;
+      for (int64_t quad = quad0; quad < n_quads; quad += quad_step) {
+        for (int l = 0; l < 8; ++l, ph ^= 1u) {
+#pragma unroll
+          for (int t = 0; t < 2; ++t) {
+            const uint32_t act_u32 = sbase + kSmemAct + t * kActPanels * kPanelBytes;
+            const int64_t tile = quad * 4 + t * 2 + rank;
+            const int64_t tile_dst = (dbg & kDbgStoreL2) ? (tile & 63) : tile;
+            uint8_t* gblock = saved + (size_t)tile_dst * kSavedTileBytes + (size_t)saved_panel_h(l + 1) * kPanelBytes;
+            mbar_wait(smem_u32(&bars->panel_full[t]), ph);
+            if (do_store) {
+#pragma unroll 8
+              for (int it = 0; it < 64; ++it) {
+                const int j = hw * 16 + (it >> 2), r = (it & 3) * 32 + lane;     // 16-byte column chunk, row
+                const float4 v = lds128f(act_u32 + (j >> 3) * kPanelBytes + r * 128 + (((j & 7) ^ (r & 7)) << 4));
+                stg128(gblock + rbcm_offset(r, j, 32),
+                       make_uint4(__float_as_uint(v.x), __float_as_uint(v.y), __float_as_uint(v.z), __float_as_uint(v.w)));
+              }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&bars->panel_free[t]));
+          }
+        }
+      }
+    }
   } else {
     // ===== 16 epilogue warps: tile t = warp / 8, TMEM lane quarter q = warp % 4, column half = (warp / 4) % 2 =====
     const int t = warp >> 3, q = warp & 3, half = (warp >> 2) & 1;
@@ -373,7 +412,8 @@ mlp_tc_fwd_kernel(const __grid_constant__ TcPlan plan, const uint8_t* __restrict
     const uint32_t inp_u32 = sbase + kSmemInp + t * kPanelBytes;
     const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)t * 256u;
     const uint32_t wrgb_u32 = sbase + kSmemWrgb;
-    uint32_t acc_cnt = 0;
+    uint32_t acc_cnt = 0, copy_ph = 0;
+    bool copy_pending = false;
     const bool timing = kTcTrace && (dbg & kDbgTiming) && blockIdx.x == 0 && gtid == 0;
     long long t_begin = clock64(), t_pro = 0, t_acc = 0, t_epi = 0, t_last = 0;
     int n_tr = 0;
@@ -497,6 +537,12 @@ mlp_tc_fwd_kernel(const __grid_constant__ TcPlan plan, const uint8_t* __restrict
         tc_fence_after();
         if (timing) { const long long now = clock64(); t_acc += now - tw; tw = now; }
         trace(timing, t, n_tr, l * 2);
+        if (kSave && copy_pending) {
+          // the store warp must have read the panels this epilogue overwrites
+          mbar_wait(smem_u32(&bars->panel_free[t]), copy_ph);
+          copy_ph ^= 1u;
+          copy_pending = false;
+        }
         if (l < 8) {
           // TMEM loads are double-buffered: group cc+1 is in flight while group cc is processed
           uint32_t acc[kTmemBuffers][32];
@@ -518,20 +564,14 @@ mlp_tc_fwd_kernel(const __grid_constant__ TcPlan plan, const uint8_t* __restrict
           if (lane == 0) mbar_arrive_cluster(act_ready_leader);
           if (timing) t_epi += clock64() - tw;
           trace(timing, t, n_tr, l * 2 + 1);
-          if (do_store && !(dbg & kDbgNoEpi)) {
-            // The saved copy leaves AFTER the MMAs were released: global stores stall the issuing warp (measured: +0.19 ms
-            // per 524k rows when they sat before the arrive).  Re-read this thread's own row of the panels (the next
-            // layer's MMAs only read them; this thread itself is the next writer) and store it coalesced: a warp = 32
-            // consecutive rows of one 16-byte column chunk = 512 contiguous bytes of the RBCM block of h_{l+1}.
-            uint8_t* grow = saved_tile + (size_t)saved_panel_h(l + 1) * kPanelBytes + rbcm_offset(r, half * 16, 32);
-            const uint32_t pbx = (act_u32 + (half * 2) * kPanelBytes + r * 128) | ((uint32_t)(r & 7) << 4);
+          if (kSave) {
+            // hand the panels to the tile's store warp; the masks (4 words) leave from here
+            if (lane == 0) mbar_arrive(smem_u32(&bars->panel_full[t]));
+            copy_pending = true;
+            if (do_store && !(dbg & kDbgNoEpi)) {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              const float4 v = lds128f((pbx + (j >> 3) * kPanelBytes) ^ (uint32_t)((j & 7) << 4));
-              stg128(grow + j * 1024, make_uint4(__float_as_uint(v.x), __float_as_uint(v.y), __float_as_uint(v.z), __float_as_uint(v.w)));
+              for (int cc = 0; cc < 4; ++cc) saved_mask[(l * 8 + half * 4 + cc) * 128 + r] = mw[cc];
             }
-#pragma unroll
-            for (int cc = 0; cc < 4; ++cc) saved_mask[(l * 8 + half * 4 + cc) * 128 + r] = mw[cc];
           }
         } else {
           // last layer: cols 0..127 = last hidden (LeakyReLU), col 128 = sigma (linear); rgb head on CUDA cores.

@@ -37,7 +37,8 @@ constexpr int kTmemBuffers = NERF_TMEM_BUFFERS;   // 2: tcgen05.ld of column gro
 constexpr int kEpiWarps = 16;                     // 8 per tile: 4 TMEM lane quarters x 2 column halves
 constexpr int kEpiThreadsPerTile = 256;
 constexpr int kWarpProducer = 16, kWarpMma = 17;
-constexpr int kThreadsFwd = 18 * 32;
+constexpr int kWarpStore = 18;                    // warps 18, 19: train-mode copy of tile 0 / 1's panels to HBM (RBCM)
+constexpr int kThreadsFwd = 20 * 32;              // 5 warps per SM sub-partition: the register cap stays at 96
 // Saved activations of one 128-row tile (forward -> backward), bf16:
 //   block 0            input panel (xyz | view encodings), [128 rows][64 cols] in the 128-byte-swizzled smem layout (16 KB)
 //   blocks h_1 .. h_8  64 KB each, "row-block chunk-major" (RBCM): [row half 0/1][16-byte column chunk j][row 0..63][8 cols].
@@ -70,7 +71,7 @@ constexpr int kSmemAct = 0;                                          // [2 tiles
 constexpr int kSmemInp = kSmemAct + 2 * kActPanels * kPanelBytes;    // [2 tiles]
 constexpr int kSmemStage = kSmemInp + 2 * kPanelBytes;               // [kStages]
 constexpr int kSmemBar = kSmemStage + kStages * kStageBytes;
-constexpr int kSmemWrgb = kSmemBar + 128;                            // float4 [128] rgb-head kernel rows + float4 rgb bias
+constexpr int kSmemWrgb = kSmemBar + 192;                            // float4 [128] rgb-head kernel rows + float4 rgb bias
 constexpr int kSmemTotal = kSmemWrgb + 129 * 16;
 // no alignment slack: the kernels check that the dynamic shared memory window is 1024-byte aligned and trap otherwise
 constexpr int kSmemAlloc = kSmemTotal;
@@ -132,6 +133,7 @@ enum : uint32_t {
   kDbgNoChain = 64u,       // backward: skip the dX chain launch
   kDbgNoDw = 128u,         // backward: skip the dW launch
   kDbgNoRelay = 512u,      // forward (pair mode): the leader does not wait for the peer's weight halves (racy)
+  kDbgStoreL2 = 1024u,     // forward: the activation copies land in a 64-tile window (L2-resident): isolates HBM from the SM store port
   kDbgTiming = 256u,       // dW: every CTA prints its cycle count
 };
 uint32_t tc_debug_flags();

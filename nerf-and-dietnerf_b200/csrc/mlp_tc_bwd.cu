@@ -126,6 +126,7 @@ static_assert(kSmemCAlloc <= 232448, "chain kernel exceeds the 227 KB shared-mem
 
 struct ChainBars {
   uint64_t full[kCStages], empty[kCStages], act_ready[2], acc_full[2];
+  uint64_t panel_full[2], panel_free[2];   // epilogue warps <-> the tile's store warp (see the forward kernel)
   uint32_t tmem_base;
 };
 
@@ -202,6 +203,8 @@ mlp_tc_bwd_chain_kernel(const __grid_constant__ BwdPlan plan, const uint8_t* __r
     for (int t = 0; t < 2; ++t) {
       mbar_init(smem_u32(&bars->act_ready[t]), 2 * 8);    // leader's copy: one arrive per epilogue warp of BOTH CTAs
       mbar_init(smem_u32(&bars->acc_full[t]), 1);
+      mbar_init(smem_u32(&bars->panel_full[t]), 8);
+      mbar_init(smem_u32(&bars->panel_free[t]), 2);       // both store warps
     }
     fence_barrier_init();
   }
@@ -289,6 +292,34 @@ mlp_tc_bwd_chain_kernel(const __grid_constant__ BwdPlan plan, const uint8_t* __r
         }
       }
     }
+  } else if (warp >= kWarpStore) {
+    // store warps: tile t's freshly written dZ_l panels -> HBM (RBCM block of the dZ workspace); see mlp_tc.cu
+    // both store warps work on every copy (one half of the column chunks each), in the order the epilogues finish
+    const int hw = warp - kWarpStore;
+    const bool do_store = !(dbg & kDbgNoStore);
+    uint32_t ph = 0;
+    for (int64_t quad = quad0; quad < n_quads; quad += quad_step) {
+      for (int l = 8; l >= 1; --l, ph ^= 1u) {
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+          const uint32_t act_u32 = sbase + kSmemCAct + t * kActPanels * kPanelBytes;
+          const int64_t tile = quad * 4 + t * 2 + rank;
+          uint8_t* gblock = dz_ws + (size_t)tile * kDzTileBytes + (size_t)dz_panel(l) * kPanelBytes;
+          mbar_wait(smem_u32(&bars->panel_full[t]), ph);
+          if (do_store) {
+#pragma unroll 8
+            for (int it = 0; it < 64; ++it) {
+              const int j = hw * 16 + (it >> 2), r = (it & 3) * 32 + lane;     // 16-byte column chunk, row
+              const float4 v = lds128f(act_u32 + (j >> 3) * kPanelBytes + r * 128 + (((j & 7) ^ (r & 7)) << 4));
+              stg128(gblock + rbcm_offset(r, j, 32),
+                     make_uint4(__float_as_uint(v.x), __float_as_uint(v.y), __float_as_uint(v.z), __float_as_uint(v.w)));
+            }
+          }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(smem_u32(&bars->panel_free[t]));
+        }
+      }
+    }
   } else {
     // 16 epilogue warps: tile t = warp / 8, TMEM lane quarter q = warp % 4, column half = (warp / 4) % 2
     const int t = warp >> 3, q = warp & 3, half = (warp >> 2) & 1;
@@ -298,7 +329,8 @@ mlp_tc_bwd_chain_kernel(const __grid_constant__ BwdPlan plan, const uint8_t* __r
     const uint32_t act_u32 = sbase + kSmemCAct + t * kActPanels * kPanelBytes;
     const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)t * 256u;
     const uint32_t w_sigma_u32 = sbase + kSmemCConst, w_rgb_u32 = sbase + kSmemCConst + 1024;
-    uint32_t acc_cnt = 0;
+    uint32_t acc_cnt = 0, copy_ph = 0;
+    bool copy_pending = false;
     const uint32_t act_ready_leader = mapa_shared(smem_u32(&bars->act_ready[t]), 0);
     for (int64_t quad = quad0; quad < n_quads; quad += quad_step) {
       const int64_t tile = quad * 4 + t * 2 + rank;
@@ -314,7 +346,12 @@ mlp_tc_bwd_chain_kernel(const __grid_constant__ BwdPlan plan, const uint8_t* __r
       uint32_t mwl[2];
 #pragma unroll
       for (int w = 0; w < 2; ++w) mwl[w] = __ldg(saved_mask + (8 * 8 + half * 2 + w) * 128 + r);
-      // the previous tile's last epilogue wrote these panel rows from other threads
+      // the previous tile's last epilogue wrote these panel rows from other threads, and its store warp may still read them
+      if (copy_pending) {
+        mbar_wait(smem_u32(&bars->panel_free[t]), copy_ph);
+        copy_ph ^= 1u;
+        copy_pending = false;
+      }
       named_bar_sync(bar_id, kEpiThreadsPerTile);
       const bool do_store = !(dbg & kDbgNoStore);
       {
@@ -367,6 +404,11 @@ mlp_tc_bwd_chain_kernel(const __grid_constant__ BwdPlan plan, const uint8_t* __r
         ++acc_cnt;
         tc_fence_after();
         if (kind == STEP_MASK) {
+          if (copy_pending) {                            // the store warp must have read the panels this epilogue overwrites
+            mbar_wait(smem_u32(&bars->panel_free[t]), copy_ph);
+            copy_ph ^= 1u;
+            copy_pending = false;
+          }
           if (!(dbg & kDbgNoEpi)) {
             const uint32_t pbx = (act_u32 + (half * 2) * kPanelBytes + r * 128) | ((uint32_t)(r & 7) << 4);
             if (l == 8) chain_mask_epilogue<true>(taddr + half * 128, mw4, pbx, alpha, d4.w, w_sigma_u32 + half * 512);
@@ -376,17 +418,8 @@ mlp_tc_bwd_chain_kernel(const __grid_constant__ BwdPlan plan, const uint8_t* __r
           fence_proxy_async();
           __syncwarp();
           if (s != last_step && lane == 0) mbar_arrive_cluster(act_ready_leader);
-          if (do_store && !(dbg & kDbgNoEpi)) {
-            // dZ_l leaves for HBM AFTER the next MMAs were released (global stores stall the issuing warp): re-read this
-            // thread's own row of the panels and store it coalesced into the RBCM block (see the forward kernel)
-            uint8_t* grow = dz_tile + (size_t)dz_panel(l) * kPanelBytes + rbcm_offset(r, half * 16, 32);
-            const uint32_t pbx = (act_u32 + (half * 2) * kPanelBytes + r * 128) | ((uint32_t)(r & 7) << 4);
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              const float4 v = lds128f((pbx + (j >> 3) * kPanelBytes) ^ (uint32_t)((j & 7) << 4));
-              stg128(grow + j * 1024, make_uint4(__float_as_uint(v.x), __float_as_uint(v.y), __float_as_uint(v.z), __float_as_uint(v.w)));
-            }
-          }
+          if (lane == 0) mbar_arrive(smem_u32(&bars->panel_full[t]));   // hand dZ_l to the tile's store warp
+          copy_pending = true;
         } else {
           if (half == 0) {
             uint32_t a0[32];
