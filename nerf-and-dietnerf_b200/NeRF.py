@@ -117,6 +117,8 @@ class NeRF:
         self.step_counter = 0           # Philox `step` of the next train step
         self._ws = {}
         self._grads = None
+        self._overlap_allreduce = False
+        self._fine_allreduce = None
         # data-parallel state (set by distribute())
         self.world_size, self.rank, self._process_group = 1, 0, None
 
@@ -273,10 +275,19 @@ class NeRF:
         return ws
 
     def _grad_buffer(self):
+        """Flat gradient buffer [sq_err_coarse, sq_err_fine, 0, 0 | grads_coarse | grads_fine].  The two squared-error sums
+        ride in FRONT of the coarse gradients so that the buffer splits into the two all-reduces of a step: the fine
+        gradients (final before the coarse backward starts, overlapped with it) and [sums | coarse gradients]."""
         if self._grads is None:
             n = self.model_coarse.n_params + (self.model_fine.n_params if self.model_fine is not None else 0)
-            self._grads = torch.zeros(n + 2, dtype=torch.float32, device=self.device)  # [+2]: sq-error sums ride along
+            self._grads = torch.zeros(4 + n, dtype=torch.float32, device=self.device)
         return self._grads
+
+    def _grad_views(self):
+        g = self._grad_buffer()
+        nc = self.model_coarse.n_params
+        g_f = g[4 + nc:] if self.model_fine is not None else None
+        return g[0:2], g[4:4 + nc], g_f
 
     def forward_backward(self, rays_orig, rays_dirs, real_rgb, *, n_total_rays=None, ray_offset=0, seed=None, step=None,
                          jitter=None, u=None):
@@ -292,11 +303,9 @@ class NeRF:
         sc, sf = self.n_render_samples_coarse, self.n_render_samples_fine
         seed = self.seed if seed is None else seed
         step = self.step_counter if step is None else step
-        g = self._grad_buffer()
-        g.zero_()
-        g_c = g[:mc.n_params]
-        g_f = g[mc.n_params:mc.n_params + mf.n_params] if mf is not None else None
-        sums = g[-2:]
+        self._grad_buffer().zero_()
+        sums, g_c, g_f = self._grad_views()
+        self._fine_allreduce = None
         o, d, y = rays_orig, rays_dirs, real_rgb
 
         # coarse forward
@@ -322,6 +331,9 @@ class NeRF:
                  ptr(w.d_z_f) if through_z else None)
             self._mlp_bwd(mf, w.xyz_f, w.view_f, w.saved_f, w.d_raw_f, n * sf, g_f, w.d_xyz_f if through_z else None,
                           w.ws_bwd)
+            if self.world_size > 1 and self._overlap_allreduce:
+                # the fine network's gradients are final: their all-reduce runs under the coarse backward
+                self._fine_allreduce = allreduce_sum_(g_f, self._process_group, async_op=True)
             if through_z:
                 # z_f -> xyz -> PE -> fine net, and z_f -> delta in the fine compositing, reach the coarse weights
                 call("nerf_encode_samples_bwd_z", mf.cfg_ref, ptr(o), ptr(d), ptr(w.z_f), ptr(w.d_xyz_f), n, sf,
@@ -388,18 +400,27 @@ class NeRF:
         """
         if self.optimizer is None:
             raise RuntimeError("call compile(optimizer=Adam(lr)) before train_step")
-        self.forward_backward(rays_orig, rays_dirs, real_rgb, n_total_rays=n_total_rays, ray_offset=ray_offset)
+        self._overlap_allreduce = True
+        try:
+            self.forward_backward(rays_orig, rays_dirs, real_rgb, n_total_rays=n_total_rays, ray_offset=ray_offset)
+        finally:
+            self._overlap_allreduce = False
         g = self._grad_buffer()
         if self.world_size > 1:
-            allreduce_sum_(g, self._process_group)
+            if self._fine_allreduce is not None:
+                allreduce_sum_(g[:4 + self.model_coarse.n_params], self._process_group)   # [sums | coarse gradients]
+                self._fine_allreduce.wait()
+                self._fine_allreduce = None
+            else:
+                allreduce_sum_(g, self._process_group)
         self.apply_gradients(g)
         self.step_counter += 1
-        return self._metrics(g[-2:], n_total_rays)
+        return self._metrics(g[0:2], n_total_rays)
 
     def apply_gradients(self, g):
         mc, mf = self.model_coarse, self.model_fine
         n = mc.n_params + (mf.n_params if mf is not None else 0)
-        self.optimizer.apply_flat([mc.params] + ([mf.params] if mf is not None else []), g[:n])
+        self.optimizer.apply_flat([mc.params] + ([mf.params] if mf is not None else []), g[4:4 + n])
         mc.mark_updated()
         if mf is not None:
             mf.mark_updated()

@@ -13,9 +13,13 @@ def shard_bounds(n_total: int, world_size: int, rank: int):
     return lo, min(n_total, lo + per)
 
 
-def allreduce_sum_(flat: torch.Tensor, group=None):
-    """In-place sum over ranks of the flat [grads_coarse | grads_fine | sq_err_c | sq_err_f] buffer."""
+def allreduce_sum_(flat: torch.Tensor, group=None, async_op: bool = False):
+    """In-place sum over ranks of (a contiguous slice of) the flat [sq_err_c, sq_err_f, 0, 0 | grads_coarse | grads_fine]
+    buffer.  async_op=True returns the work handle (None when there is nothing to reduce): the fine-network slice is
+    reduced while the coarse backward still runs."""
     import torch.distributed as dist
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
-        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
-    return flat
+        work = dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group, async_op=async_op)
+        if async_op:
+            return work
+    return None if async_op else flat

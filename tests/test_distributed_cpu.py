@@ -43,8 +43,13 @@ def _worker(rank, world, port, n, out_dir):
     sq_c = ((out["rgb_c"] - y[lo:hi]) ** 2).sum()
     sq_f = ((out["rgb_f"] - y[lo:hi]) ** 2).sum()
     ((sq_c + sq_f) / (3.0 * n)).backward()
-    flat = torch.cat([pcs.grad, pfs.grad, sq_c.detach().reshape(1), sq_f.detach().reshape(1)])
-    parallel.allreduce_sum_(flat)
+    # the step's flat buffer [sq_c, sq_f, 0, 0 | grads_coarse | grads_fine] and its two all-reduces: the fine slice
+    # asynchronously (it overlaps the coarse backward on the GPU), then [sums | coarse gradients]
+    flat = torch.cat([sq_c.detach().reshape(1), sq_f.detach().reshape(1), torch.zeros(2), pcs.grad, pfs.grad])
+    n_c = pcs.numel()
+    work = parallel.allreduce_sum_(flat[4 + n_c:], async_op=True)
+    parallel.allreduce_sum_(flat[:4 + n_c])
+    work.wait()
     if rank == 0:
         np.save(os.path.join(out_dir, "flat.npy"), flat.numpy())
     dist.barrier()
@@ -67,9 +72,10 @@ def test_two_rank_gradient_equals_single_process(tmp_path):
     jit, u = O.stratified_jitter(3, 0, n, 16), O.importance_uniforms(3, 0, n, 16)
     metrics, gc, gf, out = O.train_step(pc, pf, cfg, NEAR, FAR, o, d, y, 16, 16, jit, u)
     np_ = cfg.n_params
-    assert ((flat[:np_] - gc).norm() / gc.norm()).item() < 1e-5
-    assert ((flat[np_:2 * np_] - gf).norm() / gf.norm()).item() < 1e-5
-    loss = (flat[-2] + flat[-1]) / (3.0 * n)
+    assert ((flat[4:4 + np_] - gc).norm() / gc.norm()).item() < 1e-5
+    assert ((flat[4 + np_:] - gf).norm() / gf.norm()).item() < 1e-5
+    assert flat[2:4].abs().max().item() == 0.0
+    loss = (flat[0] + flat[1]) / (3.0 * n)
     assert abs(loss.item() - metrics["loss"].item()) < 1e-6
 
 
