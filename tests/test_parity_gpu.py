@@ -342,6 +342,41 @@ def test_mlp_backward_bf16_is_deterministic(pkg):
     assert torch.equal(grads[0][1], grads[1][1])
 
 
+def test_mlp_tc_repeatable_under_load(pkg):
+    """Race detector for the CTA-pair handshakes (relaxed remote mbarrier arrives, store warps, split-K partials): many
+    back-to-back launches over every SM with a ragged tail must give bit-identical outputs, saved activations' effect
+    (through the backward) and gradients."""
+    call, ptr = pkg._lib.call, pkg._lib.ptr
+    cfg = pkg.NetCfg(5, 4, 2, 256, 128, 0.05)
+    net = pkg.NerfMLP(cfg, mode="bf16", seed=3)
+    n_rays, s = 2048 + 37, 64
+    m = n_rays * s
+    g = torch.Generator(device="cuda").manual_seed(5)
+    o4 = torch.randn(n_rays, 4, device="cuda", generator=g)
+    d4 = torch.randn(n_rays, 4, device="cuda", generator=g)
+    z = torch.sort(torch.rand(n_rays, s, device="cuda", generator=g) * 2 + 0.5, -1).values.contiguous()
+    d_out = torch.randn(m, 4, device="cuda", generator=g)
+    packed = net.packed_for(net.params)
+    saved = torch.empty(net.saved_bytes(m), dtype=torch.uint8, device="cuda")
+    ws = torch.empty(net.workspace_bytes(m, True), dtype=torch.uint8, device="cuda")
+    ref = None
+    for it in range(12):
+        out = torch.empty(m, 4, device="cuda")
+        grads = torch.zeros(net.n_params, device="cuda")
+        d_xyz = torch.empty(m, 33, device="cuda")
+        call("nerf_mlp_fwd_rays", net.cfg_ref, ptr(packed), ptr(o4), ptr(d4), ptr(z), n_rays, s, ptr(out), ptr(saved),
+             net.mode_id)
+        call("nerf_mlp_bwd", net.cfg_ref, ptr(net.params), ptr(packed), None, None, ptr(saved), ptr(d_out), m, ptr(grads),
+             ptr(d_xyz), ptr(ws), net.mode_id)
+        cur = (out, grads, d_xyz)
+        if ref is None:
+            ref = cur
+            assert torch.isfinite(out).all() and torch.isfinite(grads).all()
+        else:
+            for a, b in zip(ref, cur):
+                assert torch.equal(a, b), f"launch {it} differs from launch 0"
+
+
 # ---- render / train step -------------------------------------------------------------------------------------------------
 def _model(pkg, mode, n_angles=2, l_view=4, n_c=64, n_f=128, cls=None, sigma_gain=30.0, **kw):
     ocfg = oracle_cfg(n_angles, l_view)
