@@ -282,7 +282,9 @@ def main():
         else:
             yield
     pkg._lib.event_hook = hook
+    model.overlap_dw = False          # one stream: each kernel is timed alone (the step itself overlaps the fine dW)
     timed(step_device, args.steps)
+    model.overlap_dw = True
     pkg._lib.event_hook = None
     torch.cuda.synchronize()
     call_ms = {k: sum(a.elapsed_time(b) for a, b in v) / len(v) for k, v in per_call.items()}

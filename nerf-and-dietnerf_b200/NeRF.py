@@ -7,6 +7,7 @@ Keras model: parameters are two flat fp32 device vectors, the train step is an e
 backward (no autograd tape) over the C ABI, and ray batches can be sharded over the GPUs of one box with a single
 NCCL all-reduce of the gradients per step.
 """
+import contextlib
 import math
 from pathlib import Path
 from typing import Dict
@@ -59,6 +60,7 @@ class _StepWorkspace:
         m_max = n * max(sc, sf)
         self.ws_fwd = torch.empty(max(mc.workspace_bytes(m_max, False), 16), dtype=torch.uint8, device=dev)
         self.ws_bwd = torch.empty(max(mc.workspace_bytes(m_max, True), 16), dtype=torch.uint8, device=dev)
+        self.ws_bwd_c = self.ws_bwd           # coarse backward workspace (its own buffer when the fine dW overlaps it)
         if model.model_fine is not None:
             self.z_f = f(n, sf)
             self.u = f(n, sf)
@@ -73,6 +75,10 @@ class _StepWorkspace:
             self.d_xyz_f = f(n * sf, mc.dx)
             self.d_w_c = f(n, sc)
             self.saved_f = torch.empty(max(mc.saved_bytes(n * sf), 16), dtype=torch.uint8, device=dev)
+            if mc.tensor_core:
+                # the fine network's weight-gradient kernel runs on a side stream under the coarse backward: the two
+                # must not share the dZ workspace
+                self.ws_bwd_c = torch.empty(max(mc.workspace_bytes(n * sc, True), 16), dtype=torch.uint8, device=dev)
 
 
 class NeRF:
@@ -119,6 +125,8 @@ class NeRF:
         self._grads = None
         self._overlap_allreduce = False
         self._fine_allreduce = None
+        self._side = None
+        self.overlap_dw = True          # False: every kernel of the step runs on one stream (per-kernel timing)
         # data-parallel state (set by distribute())
         self.world_size, self.rank, self._process_group = 1, 0, None
 
@@ -329,11 +337,12 @@ class NeRF:
             through_z = not self.stop_grad_z
             call("nerf_composite_bwd", ptr(w.raw_f), ptr(w.z_f), ptr(w.d_rgb_f), None, n, sf, ptr(w.d_raw_f),
                  ptr(w.d_z_f) if through_z else None)
-            self._mlp_bwd(mf, w.xyz_f, w.view_f, w.saved_f, w.d_raw_f, n * sf, g_f, w.d_xyz_f if through_z else None,
-                          w.ws_bwd)
+            side = self._mlp_bwd(mf, w.xyz_f, w.view_f, w.saved_f, w.d_raw_f, n * sf, g_f,
+                                 w.d_xyz_f if through_z else None, w.ws_bwd, side_stream=self._side_stream())
             if self.world_size > 1 and self._overlap_allreduce:
                 # the fine network's gradients are final: their all-reduce runs under the coarse backward
-                self._fine_allreduce = allreduce_sum_(g_f, self._process_group, async_op=True)
+                with torch.cuda.stream(side) if side is not None else contextlib.nullcontext():
+                    self._fine_allreduce = allreduce_sum_(g_f, self._process_group, async_op=True)
             if through_z:
                 # z_f -> xyz -> PE -> fine net, and z_f -> delta in the fine compositing, reach the coarse weights
                 call("nerf_encode_samples_bwd_z", mf.cfg_ref, ptr(o), ptr(d), ptr(w.z_f), ptr(w.d_xyz_f), n, sf,
@@ -343,20 +352,38 @@ class NeRF:
                 d_w_c = w.d_w_c
         # coarse backward
         call("nerf_composite_bwd", ptr(w.raw_c), ptr(w.z_c), ptr(w.d_rgb_c), ptr(d_w_c), n, sc, ptr(w.d_raw_c), None)
-        self._mlp_bwd(mc, w.xyz_c, w.view_c, w.saved_c, w.d_raw_c, n * sc, g_c, None, w.ws_bwd)
+        self._mlp_bwd(mc, w.xyz_c, w.view_c, w.saved_c, w.d_raw_c, n * sc, g_c, None, w.ws_bwd_c)
+        if mf is not None and self._side is not None:
+            torch.cuda.current_stream().wait_stream(self._side)      # the fine weight gradients join here
         return g_c, g_f, sums
 
+    def _side_stream(self):
+        """Stream of the fine network's weight-gradient kernel (HBM-bound): it runs under the small sampler / compositing
+        backward kernels and the head of the coarse backward instead of in front of them."""
+        if not self.overlap_dw:
+            return None
+        if self._side is None and self.model_coarse.tensor_core:
+            self._side = torch.cuda.Stream(device=self.device)
+        return self._side
+
     @staticmethod
-    def _mlp_bwd(net, xyz, view, saved, d_raw, m, grads, d_xyz, ws):
+    def _mlp_bwd(net, xyz, view, saved, d_raw, m, grads, d_xyz, ws, side_stream=None):
         """TF autodiff of one Keras model (src/NeRF.py:149-167).  The tensor-core path runs its two halves as separate
-        C-ABI calls (input-gradient chain, then weight gradients) so that they can be timed / overlapped separately."""
+        C-ABI calls (input-gradient chain, then weight gradients); with ``side_stream`` the second half is issued there
+        (after the first) and the stream is returned for the caller to join."""
         args = (net.cfg_ref, ptr(net.params), ptr(net.packed_for(net.params)), ptr(xyz), ptr(view), ptr(saved), ptr(d_raw), m,
                 ptr(grads), ptr(d_xyz), ptr(ws), net.mode_id)
         if net.mode_id == MODE_BF16:
             call("nerf_mlp_bwd_dx", *args)
+            if side_stream is not None:
+                side_stream.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(side_stream):
+                    call("nerf_mlp_bwd_dw", *args)
+                return side_stream
             call("nerf_mlp_bwd_dw", *args)
         else:
             call("nerf_mlp_bwd", *args)
+        return None
 
     def _mlp_fwd_train(self, net, o, d, z, n, s, xyz, view, raw, saved, ws):
         """Training-mode MLP forward (activations saved): fused encode+MLP kernel in bf16 mode, two kernels in fp32."""
