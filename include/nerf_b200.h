@@ -164,6 +164,14 @@ int nerf_sample_pdf_bwd(const float* weights, const float* z, const float* u, co
 /* z = sort(concat(z_a, z_b)) per ray (src/NeRF.py:132); both inputs sorted ascending. out: (N,Sa+Sb). */
 int nerf_merge_sorted(const float* z_a, int32_t sa, const float* z_b, int32_t sb, int64_t n_rays, float* out,
                       void* stream);
+/* Same merge, also writing rank_a (N,Sa) int32: out[ray][rank_a[ray][j]] = z_a[ray][j].  Elements of z_a precede
+ * equal elements of z_b (the order of a stable sort of concat(z_a, z_b)). */
+int nerf_merge_sorted_rank(const float* z_a, int32_t sa, const float* z_b, int32_t sb, int64_t n_rays, float* out,
+                           int32_t* rank_a, void* stream);
+/* Gradient of that sort(concat) w.r.t. z_a when it sits inside the tape (DietNeRF's in-tape render_image,
+ * src/DietNeRF.py:215-218 -> src/NeRF.py:132): d_a[ray][j] = d_out[ray][rank_a[ray][j]]. */
+int nerf_merge_sorted_bwd(const float* d_out, const int32_t* rank_a, int32_t sa, int32_t sb, int64_t n_rays,
+                          float* d_a, void* stream);
 
 /* ---- loss / optimizer (src/NeRF.py:151,157,164-176) -------------------------------------------------- */
 /* d_rgb = loss_weight * 2 (rgb-target) / (3*n_total); sums[0] += sum((rgb-target)^2) (caller zeroes). */

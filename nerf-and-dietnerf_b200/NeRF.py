@@ -40,10 +40,13 @@ def net_cfg_from_dict(net_config: Dict) -> NetCfg:
 class _StepWorkspace:
     """Device buffers of one train step for a fixed number of rays (allocated once, reused every step)."""
 
-    def __init__(self, model, n):
+    def __init__(self, model, n, sc=None, sf=None, n_new=None):
+        """``sc``/``sf``: samples per ray the coarse / fine network sees (default: the train step's, src/NeRF.py:146,155);
+        ``n_new``: importance samples drawn when the fine network sees sort(concat(new, coarse)) (in-tape render)."""
         dev = model.device
         f = lambda *shape: torch.empty(shape, dtype=torch.float32, device=dev)
-        sc, sf = model.n_render_samples_coarse, model.n_render_samples_fine
+        sc = model.n_render_samples_coarse if sc is None else sc
+        sf = model.n_render_samples_fine if sf is None else sf
         mc = model.model_coarse
         self.n = n
         self.z_c = f(n, sc)
@@ -75,6 +78,12 @@ class _StepWorkspace:
             self.d_xyz_f = f(n * sf, mc.dx)
             self.d_w_c = f(n, sc)
             self.saved_f = torch.empty(max(mc.saved_bytes(n * sf), 16), dtype=torch.uint8, device=dev)
+            if n_new is not None:
+                self.z_new = f(n, n_new)
+                self.d_z_new = f(n, n_new)
+                self.u = f(n, n_new)
+                self.perm = torch.empty((n, n_new), dtype=torch.int32, device=dev)
+                self.rank = torch.empty((n, n_new), dtype=torch.int32, device=dev)
             if mc.tensor_core:
                 # the fine network's weight-gradient kernel runs on a side stream under the coarse backward: the two
                 # must not share the dZ workspace
@@ -246,7 +255,8 @@ class NeRF:
         return (cat[0].reshape(h, w, 3), cat[1].reshape(h, w, -1), cat[2].reshape(h, w, -1), cat[3].reshape(h, w, -1),
                 cat[4].reshape(h, w, -1, 3), cat[5].reshape(h, w, -1))
 
-    def render_image_lean(self, c2w, fov, h, w, batch_size_input=None, *, seed=None, step=0, ray_begin=0, n_rays=None):
+    def render_image_lean(self, c2w, fov, h, w, batch_size_input=None, n_render_samples_c=None,
+                          n_render_samples_f=None, *, seed=None, step=0, ray_begin=0, n_rays=None):
         """Video-path render (extension): only rgb (n,3), depth (n) = sum w z (src/ExecutionRun.py:346) and acc (n),
         for rays [ray_begin, ray_begin+n_rays) of the frame -- the unit a GPU takes when a frame is row-sharded."""
         n_total = h * w if n_rays is None else int(n_rays)
@@ -254,7 +264,8 @@ class NeRF:
         batch_size = batch_size_input if batch_size_input else self.batch_size_render
         if seed is None:
             seed, step = rng.next_step()
-        n_c, n_f = self.n_render_samples_coarse, self.n_render_samples_fine
+        n_c = n_render_samples_c if n_render_samples_c else self.n_render_samples_coarse
+        n_f = n_render_samples_f if n_render_samples_f else self.n_render_samples_fine
         rgbs, depths, accs = [], [], []
         with torch.no_grad():
             for s0 in range(0, n_total, batch_size):
@@ -275,11 +286,12 @@ class NeRF:
         return torch.cat(rgbs), torch.cat(depths), torch.cat(accs)
 
     # ---- training ----------------------------------------------------------------------------------------------------
-    def _workspace(self, n):
-        ws = self._ws.get(n)
+    def _workspace(self, n, sc=None, sf=None, n_new=None):
+        key = n if sc is None else (n, sc, sf, n_new)
+        ws = self._ws.get(key)
         if ws is None:
-            ws = _StepWorkspace(self, n)
-            self._ws[n] = ws
+            ws = _StepWorkspace(self, n, sc, sf, n_new)
+            self._ws[key] = ws
         return ws
 
     def _grad_buffer(self):
@@ -298,8 +310,11 @@ class NeRF:
         return g[0:2], g[4:4 + nc], g_f
 
     def forward_backward(self, rays_orig, rays_dirs, real_rgb, *, n_total_rays=None, ray_offset=0, seed=None, step=None,
-                         jitter=None, u=None):
+                         jitter=None, u=None, keep_grads=False):
         """Loss and parameter gradients of one batch (src/NeRF.py:145-164 without the optimizer).
+
+        ``keep_grads``: add to the gradients already in the flat buffer (DietNeRF's consistency term) instead of
+        starting from zero.
 
         Returns (grads_coarse, grads_fine, sums) where sums = [sum sq err coarse, sum sq err fine] over THIS
         shard and the gradients are already divided by the GLOBAL element count 3*n_total_rays.
@@ -311,7 +326,8 @@ class NeRF:
         sc, sf = self.n_render_samples_coarse, self.n_render_samples_fine
         seed = self.seed if seed is None else seed
         step = self.step_counter if step is None else step
-        self._grad_buffer().zero_()
+        if not keep_grads:
+            self._grad_buffer().zero_()
         sums, g_c, g_f = self._grad_views()
         self._fine_allreduce = None
         o, d, y = rays_orig, rays_dirs, real_rgb
@@ -356,6 +372,75 @@ class NeRF:
         if mf is not None and self._side is not None:
             torch.cuda.current_stream().wait_stream(self._side)      # the fine weight gradients join here
         return g_c, g_f, sums
+
+    def render_backward(self, rays_orig, rays_dirs, d_rgb, n_render_samples_c=None, n_render_samples_f=None, *,
+                        seed, step=0, ray_offset=0, jitter=None, u=None):
+        """Back-propagate ``d_rgb`` (N,3) = dL/d(rendered rgb) through ``render`` (src/NeRF.py:109-134) for these rays:
+        what TF's tape does when render_image sits inside it (DietNeRF.calc_consistency_loss, src/DietNeRF.py:215-218).
+
+        The render is recomputed in training mode from the same Philox stream (seed, step, ray_offset), so it is the
+        render a previous ``render(..., seed=, step=, ray_offset=)`` call returned; the fine network sees
+        sort(concat(z_from_dist, z_coarse)) (:132) and its loss reaches the coarse network through the importance
+        sampler.  Parameter gradients are ADDED to the flat gradient buffer; returns the recomputed rgb (N,3).
+        """
+        o, d = f32c(rays_orig, self.device), f32c(rays_dirs, self.device)
+        d_rgb = f32c(d_rgb, self.device)
+        n = o.shape[0]
+        mc, mf = self.model_coarse, self.model_fine
+        sc = n_render_samples_c if n_render_samples_c else self.n_render_samples_coarse
+        nf = (n_render_samples_f if n_render_samples_f else self.n_render_samples_fine) if mf is not None else 0
+        sf = nf + sc
+        w = self._workspace(n, sc, sf if mf is not None else 0, nf if mf is not None else None)
+        _, g_c, g_f = self._grad_views()
+        call("nerf_stratified_z", self.near_boundary, self.far_boundary, n, sc, ptr(jitter), seed, step, ray_offset,
+             ptr(w.z_c))
+        self._mlp_fwd_train(mc, o, d, w.z_c, n, sc, w.xyz_c, w.view_c, w.raw_c, w.saved_c, w.ws_fwd)
+        call("nerf_composite_fwd", ptr(w.raw_c), ptr(w.z_c), n, sc, ptr(w.rgb_c), ptr(w.w_c), None, None, None, None,
+             None)
+        if mf is None:
+            call("nerf_composite_bwd", ptr(w.raw_c), ptr(w.z_c), ptr(d_rgb), None, n, sc, ptr(w.d_raw_c), None)
+            self._mlp_bwd(mc, w.xyz_c, w.view_c, w.saved_c, w.d_raw_c, n * sc, g_c, None, w.ws_bwd_c)
+            return w.rgb_c
+        call("nerf_sample_pdf_fwd", ptr(w.w_c), ptr(w.z_c), n, sc, nf, ptr(u), seed, step, ray_offset, ptr(w.z_new),
+             None, ptr(w.perm), ptr(w.u))
+        call("nerf_merge_sorted_rank", ptr(w.z_new), nf, ptr(w.z_c), sc, n, ptr(w.z_f), ptr(w.rank))
+        self._mlp_fwd_train(mf, o, d, w.z_f, n, sf, w.xyz_f, w.view_f, w.raw_f, w.saved_f, w.ws_fwd)
+        call("nerf_composite_fwd", ptr(w.raw_f), ptr(w.z_f), n, sf, ptr(w.rgb_f), None, None, None, None, None, None)
+        # fine backward
+        through_z = not self.stop_grad_z
+        call("nerf_composite_bwd", ptr(w.raw_f), ptr(w.z_f), ptr(d_rgb), None, n, sf, ptr(w.d_raw_f),
+             ptr(w.d_z_f) if through_z else None)
+        self._mlp_bwd(mf, w.xyz_f, w.view_f, w.saved_f, w.d_raw_f, n * sf, g_f, w.d_xyz_f if through_z else None,
+                      w.ws_bwd, side_stream=self._side_stream())
+        if through_z:
+            call("nerf_encode_samples_bwd_z", mf.cfg_ref, ptr(o), ptr(d), ptr(w.z_f), ptr(w.d_xyz_f), n, sf,
+                 ptr(w.d_z_f), 1)
+            call("nerf_merge_sorted_bwd", ptr(w.d_z_f), ptr(w.rank), nf, sc, n, ptr(w.d_z_new))
+            call("nerf_sample_pdf_bwd", ptr(w.w_c), ptr(w.z_c), ptr(w.u), ptr(w.perm), ptr(w.d_z_new), n, sc, nf,
+                 ptr(w.d_w_c))
+            # the rendered image is the fine network's: the coarse rgb carries no loss, only its weights do
+            w.d_rgb_c.zero_()
+            call("nerf_composite_bwd", ptr(w.raw_c), ptr(w.z_c), ptr(w.d_rgb_c), ptr(w.d_w_c), n, sc, ptr(w.d_raw_c),
+                 None)
+            self._mlp_bwd(mc, w.xyz_c, w.view_c, w.saved_c, w.d_raw_c, n * sc, g_c, None, w.ws_bwd_c)
+        if self._side is not None:
+            torch.cuda.current_stream().wait_stream(self._side)
+        return w.rgb_f
+
+    def render_image_backward(self, c2w, fov, h, w, d_image, batch_size_input=None, n_render_samples_c=None,
+                              n_render_samples_f=None, *, seed, step=0, ray_begin=0, n_rays=None):
+        """``render_backward`` over the rays [ray_begin, ray_begin+n_rays) of an h x w image in batches, the way
+        ``render_image`` (src/NeRF.py:206-228) walks them.  ``d_image``: (h,w,3) or (h*w,3) gradient of the loss w.r.t.
+        the image ``render_image(..., seed=seed, step=step)`` returned.  Gradients are added to the flat buffer."""
+        n_total = h * w - ray_begin if n_rays is None else int(n_rays)
+        dirs, orig = get_rays_directions(h, w, fov, c2w, ray_begin=ray_begin, n_rays=n_total, return_origins=True)
+        dirs = dirs.reshape(-1, 4)
+        d_flat = f32c(d_image, self.device).reshape(h * w, 3)
+        batch_size = batch_size_input if batch_size_input else self.batch_size_render
+        for s0 in range(0, n_total, batch_size):
+            e0 = min(n_total, s0 + batch_size)
+            self.render_backward(orig[s0:e0], dirs[s0:e0], d_flat[ray_begin + s0:ray_begin + e0], n_render_samples_c,
+                                 n_render_samples_f, seed=seed, step=step, ray_offset=ray_begin + s0)
 
     def _side_stream(self):
         """Stream of the fine network's weight-gradient kernel (HBM-bound): it runs under the small sampler / compositing
@@ -429,7 +514,8 @@ class NeRF:
             raise RuntimeError("call compile(optimizer=Adam(lr)) before train_step")
         self._overlap_allreduce = True
         try:
-            self.forward_backward(rays_orig, rays_dirs, real_rgb, n_total_rays=n_total_rays, ray_offset=ray_offset)
+            self.forward_backward(rays_orig, rays_dirs, real_rgb, n_total_rays=n_total_rays, ray_offset=ray_offset,
+                                  keep_grads=getattr(self, "_keep_grads", False))
         finally:
             self._overlap_allreduce = False
         g = self._grad_buffer()

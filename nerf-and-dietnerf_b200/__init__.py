@@ -7,7 +7,7 @@ ConfigurationKeys.  All compute goes through libnerf_b200.so (hand-written sm_10
 no CPU fallback.
 """
 from . import ConfigurationKeys, _lib  # noqa: F401
-from . import UtilsCV, UtilsNeuralRadianceField, network, optimizers, parallel  # noqa: F401
+from . import UtilsCV, UtilsNeuralRadianceField, network, optimizers, parallel, poses, vit  # noqa: F401
 from . import NeRF as _nerf_module, DietNeRF as _dietnerf_module  # noqa: F401
 from ._lib import LIB_PATH, NerfLibraryError, NetCfg, load  # noqa: F401
 from .network import NerfMLP  # noqa: F401

@@ -182,7 +182,7 @@ sample_pdf_bwd_kernel(const float* __restrict__ weights, const float* __restrict
 }
 
 __global__ void merge_sorted_kernel(const float* __restrict__ a, int sa, const float* __restrict__ b, int sb,
-                                    int64_t n_rays, float* __restrict__ out) {
+                                    int64_t n_rays, float* __restrict__ out, int32_t* __restrict__ rank_a) {
   const int st = sa + sb;
   int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i >= n_rays * st) return;
@@ -197,6 +197,7 @@ __global__ void merge_sorted_kernel(const float* __restrict__ a, int sa, const f
     int lo = 0, hi = sb;
     while (lo < hi) { int m = (lo + hi) >> 1; if (br[m] < v) lo = m + 1; else hi = m; }
     rank = j + lo;
+    if (rank_a) rank_a[ray * sa + j] = rank;
   } else {       // element of b: rank = jb + #{a <= v}
     int jb = j - sa;
     v = br[jb];
@@ -205,6 +206,16 @@ __global__ void merge_sorted_kernel(const float* __restrict__ a, int sa, const f
     rank = jb + lo;
   }
   out[ray * st + rank] = v;
+}
+
+// d_a[ray][j] = d_out[ray][rank_a[ray][j]]: what the sort(concat) of src/NeRF.py:132 back-propagates to its first
+// operand (a sort's gradient is a gather through its permutation).
+__global__ void merge_sorted_bwd_kernel(const float* __restrict__ d_out, const int32_t* __restrict__ rank_a, int sa,
+                                        int st, int64_t n_rays, float* __restrict__ d_a) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n_rays * sa) return;
+  int64_t ray = i / sa;
+  d_a[i] = d_out[ray * st + rank_a[i]];
 }
 
 }  // namespace nerf
@@ -251,7 +262,31 @@ int nerf_merge_sorted(const float* z_a, int32_t sa, const float* z_b, int32_t sb
   NERF_CHECK_ARG(sa > 0 && sb > 0 && n_rays >= 0, "bad shape");
   if (n_rays == 0) return NERF_OK;
   int64_t total = n_rays * (sa + sb);
-  merge_sorted_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, (cudaStream_t)stream>>>(z_a, sa, z_b, sb, n_rays, out);
+  merge_sorted_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, (cudaStream_t)stream>>>(z_a, sa, z_b, sb, n_rays, out,
+                                                                                         nullptr);
+  NERF_CHECK_LAUNCH();
+  return NERF_OK;
+}
+
+int nerf_merge_sorted_rank(const float* z_a, int32_t sa, const float* z_b, int32_t sb, int64_t n_rays, float* out,
+                           int32_t* rank_a, void* stream) {
+  NERF_CHECK_ARG(z_a && z_b && out && rank_a, "null pointer");
+  NERF_CHECK_ARG(sa > 0 && sb > 0 && n_rays >= 0, "bad shape");
+  if (n_rays == 0) return NERF_OK;
+  int64_t total = n_rays * (sa + sb);
+  merge_sorted_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, (cudaStream_t)stream>>>(z_a, sa, z_b, sb, n_rays, out,
+                                                                                         rank_a);
+  NERF_CHECK_LAUNCH();
+  return NERF_OK;
+}
+
+int nerf_merge_sorted_bwd(const float* d_out, const int32_t* rank_a, int32_t sa, int32_t sb, int64_t n_rays,
+                          float* d_a, void* stream) {
+  NERF_CHECK_ARG(d_out && rank_a && d_a, "null pointer");
+  NERF_CHECK_ARG(sa > 0 && sb > 0 && n_rays >= 0, "bad shape");
+  if (n_rays == 0) return NERF_OK;
+  merge_sorted_bwd_kernel<<<(unsigned)ceil_div(n_rays * sa, 256), 256, 0, (cudaStream_t)stream>>>(d_out, rank_a, sa,
+                                                                                                  sa + sb, n_rays, d_a);
   NERF_CHECK_LAUNCH();
   return NERF_OK;
 }

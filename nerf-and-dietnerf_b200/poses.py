@@ -1,0 +1,85 @@
+"""The two camera-pose helpers DietNeRF's random source pose needs (src/DietNeRF.py:238-259): a pose on a sphere
+looking at the origin (src/UtilsCV.py:41-121) and the slerp/lerp interpolation between two camera-to-world matrices
+(src/UtilsCV.py:175-225).  Host-side NumPy, a handful of 4x4 products per consistency step; the rest of the
+reference's pose geometry (recentering, RANSAC look-at point, video trajectories) is outside the hot path.
+"""
+import numpy as np
+
+
+def get_x_rot_mat(x_deg):
+    a = np.deg2rad(x_deg)
+    return np.asarray([[1, 0, 0, 0], [0, np.cos(a), -np.sin(a), 0], [0, np.sin(a), np.cos(a), 0], [0, 0, 0, 1]])
+
+
+def get_y_rot_mat(y_deg):
+    # the reference's sign convention (src/UtilsCV.py:86-98): -sin in the first row
+    a = np.deg2rad(y_deg)
+    return np.asarray([[np.cos(a), 0, -np.sin(a), 0], [0, 1, 0, 0], [np.sin(a), 0, np.cos(a), 0], [0, 0, 0, 1]])
+
+
+def get_z_rot_mat(z_deg):
+    a = np.deg2rad(z_deg)
+    return np.asarray([[np.cos(a), -np.sin(a), 0, 0], [np.sin(a), np.cos(a), 0, 0], [0, 0, 1, 0], [0, 0, 0, 1]])
+
+
+def get_sphere_matrix(radius, x_rot, y_rot, z_rot):
+    """Camera at distance ``radius`` on the +z axis, rotated about x, then y, then z (degrees), looking at the origin
+    (src/UtilsCV.py:101-121)."""
+    t = np.eye(4)
+    t[2, 3] = radius
+    return get_z_rot_mat(z_rot) @ (get_y_rot_mat(y_rot) @ (get_x_rot_mat(x_rot) @ t))
+
+
+def quaternion_from_rotation_matrix(r):
+    """(x, y, z, w) unit quaternion of a 3x3 rotation matrix (branch on the largest diagonal term)."""
+    r = np.asarray(r, dtype=np.float64)
+    tr = r[0, 0] + r[1, 1] + r[2, 2]
+    if tr > 0:
+        s = 2.0 * np.sqrt(1.0 + tr)
+        q = [(r[2, 1] - r[1, 2]) / s, (r[0, 2] - r[2, 0]) / s, (r[1, 0] - r[0, 1]) / s, 0.25 * s]
+    elif r[0, 0] > r[1, 1] and r[0, 0] > r[2, 2]:
+        s = 2.0 * np.sqrt(1.0 + r[0, 0] - r[1, 1] - r[2, 2])
+        q = [0.25 * s, (r[0, 1] + r[1, 0]) / s, (r[0, 2] + r[2, 0]) / s, (r[2, 1] - r[1, 2]) / s]
+    elif r[1, 1] > r[2, 2]:
+        s = 2.0 * np.sqrt(1.0 + r[1, 1] - r[0, 0] - r[2, 2])
+        q = [(r[0, 1] + r[1, 0]) / s, 0.25 * s, (r[1, 2] + r[2, 1]) / s, (r[0, 2] - r[2, 0]) / s]
+    else:
+        s = 2.0 * np.sqrt(1.0 + r[2, 2] - r[0, 0] - r[1, 1])
+        q = [(r[0, 2] + r[2, 0]) / s, (r[1, 2] + r[2, 1]) / s, 0.25 * s, (r[1, 0] - r[0, 1]) / s]
+    return np.asarray(q)
+
+
+def rotation_matrix_from_quaternion(q):
+    x, y, z, w = q
+    return np.asarray([
+        [1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)],
+        [2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)],
+        [2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)]])
+
+
+def slerp(p0, p1, t):
+    """src/UtilsCV.py:228-247: spherical interpolation of two unit quaternions along the shorter arc."""
+    cos_a = float(np.dot(p0, p1))
+    if cos_a < 0:
+        p1, cos_a = -p1, -cos_a
+    omega = np.arccos(min(cos_a, 1.0))
+    sin_omega = np.sin(omega)
+    if sin_omega < 1e-8:           # identical rotations: the reference divides 0/0 here; keep the rotation
+        return p0
+    return np.sin((1.0 - t) * omega) / sin_omega * p0 + np.sin(t * omega) / sin_omega * p1
+
+
+def interpolation_type_slerp_for_c2w(c2w1, c2w2, alpha):
+    """Slerp the rotations and lerp the translations of two camera-to-world matrices (src/UtilsCV.py:175-210);
+    ``alpha`` a float or a sequence of floats (then a list is returned)."""
+    def one(m1, m2, t):
+        m1, m2 = np.asarray(m1, dtype=np.float64), np.asarray(m2, dtype=np.float64)
+        q = slerp(quaternion_from_rotation_matrix(m1[:3, :3]), quaternion_from_rotation_matrix(m2[:3, :3]), t)
+        out = np.eye(4)
+        out[:3, :3] = rotation_matrix_from_quaternion(q / np.linalg.norm(q))
+        out[:3, 3] = m1[:3, 3] * (1 - t) + m2[:3, 3] * t
+        return out.astype(np.float32)
+    alpha = np.asarray(alpha)
+    if alpha.shape != ():
+        return [one(c2w1, c2w2, float(a)) for a in alpha]
+    return one(c2w1, c2w2, float(alpha))

@@ -480,3 +480,45 @@ def render_image(params_c, params_f, cfg, near, far, c2w, fov, h, w, batch_size,
     rgb_s = cat[4].reshape(h, w, -1, 3)
     z = cat[5].reshape(h, w, -1)
     return rgb, weights, cumprod, alpha, rgb_s, z
+
+
+# --------------------------------------------------------------------------------------------------
+# DietNeRF semantic-consistency term (src/DietNeRF.py:204-222, :261-279)
+# --------------------------------------------------------------------------------------------------
+def embedder_preprocess(images: torch.Tensor) -> torch.Tensor:
+    """src/DietNeRF.py:279: tf.image.resize(images, (224,224)) * 2 - 1 (bilinear, half-pixel centres, antialias off).
+    (B,H,W,3) -> (B,3,224,224)."""
+    x = torch.nn.functional.interpolate(images.permute(0, 3, 1, 2), size=(224, 224), mode="bilinear",
+                                        align_corners=False, antialias=False)
+    return x * 2.0 - 1.0
+
+
+def consistency_loss(embedding_source: torch.Tensor, embedding_target: torch.Tensor) -> torch.Tensor:
+    """src/DietNeRF.py:270: (1 + keras.losses.cosine_similarity(s, t)) / 2, where Keras' cosine_similarity is
+    -sum(l2_normalize(s) * l2_normalize(t)) (a loss: -1 when aligned)."""
+    s = embedding_source / torch.sqrt(torch.clamp((embedding_source ** 2).sum(), min=1e-12))
+    t = embedding_target / torch.sqrt(torch.clamp((embedding_target ** 2).sum(), min=1e-12))
+    return (1.0 + (-(s * t).sum())) / 2.0
+
+
+def consistency_loss_and_grads(params_c, params_f, cfg, near, far, c2w, fov, size, batch_size, n_samples, seed, step,
+                               embed_fn, target_embedding, weight: float = 0.1, emulate_bf16: bool = False):
+    """calc_consistency_loss (src/DietNeRF.py:204-222) with the tape open: render_image(pose, fov, size, size,
+    batch_size, n_samples, n_samples)[0] -> preprocess -> embedder -> weight * consistency_loss, and its gradient
+    w.r.t. both parameter vectors.  Jitter / importance draws come from the shared Philox stream keyed by the global
+    ray index, as in render_image above.  Returns (loss, grad_c, grad_f, image)."""
+    pc = params_c.detach().clone().requires_grad_(True)
+    pf = params_f.detach().clone().requires_grad_(True) if params_f is not None else None
+    orig, dirs = rays_for_image(c2w, fov, size, size)
+    parts = []
+    for s in range(0, size * size, batch_size):
+        e = min(size * size, s + batch_size)
+        jit = stratified_jitter(seed, step, e - s, n_samples, ray_offset=s)
+        u = importance_uniforms(seed, step, e - s, n_samples, ray_offset=s) if pf is not None else None
+        parts.append(render(pc, pf, cfg, near, far, orig[s:e], dirs[s:e], n_samples, n_samples, jit, u,
+                            emulate_bf16)[0])
+    image = torch.cat(parts, dim=0).reshape(size, size, 3)
+    emb = embed_fn(embedder_preprocess(image[None]))[0]
+    loss = weight * consistency_loss(emb, target_embedding)
+    loss.backward()
+    return loss.detach(), pc.grad, (pf.grad if pf is not None else None), image.detach()
