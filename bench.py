@@ -34,6 +34,9 @@ CONFIGS = {
     "100px_robot_72pics_sphere": (2048, 0.3333, 2.0, 0.69111),
     "256px_alexander_71pics_sphere_nerf": (4096, 0.5576, 2.5635, 0.46134),
     "50px_alexander_71pics_sphere_nerf": (4096, 0.5576, 2.5635, 0.46134),
+    # DietNeRF (BASELINE configs[4]): the same ray loss (2*MSE_c + MSE_f) plus, every 13th step, the semantic-consistency
+    # term: a 150x150 in-tape render (55 + 55 samples), random-init ViT-B/32 embedding, cosine loss, full backward
+    "256px_alexander_71pics_sphere_dietnerf": (2048, 0.5576, 2.5635, 0.46134),
 }
 N_C, N_F = 64, 128
 MAC_FWD = 512152                    # MLP forward MAC per sample
@@ -195,8 +198,17 @@ def main():
 
     batch, near, far, fov = CONFIGS[args.config]
     n_total = batch * world
-    model = pkg.NeRFModel(net_config(batch), {"n_render_samples_coarse": N_C, "n_render_samples_fine": N_F}, near, far,
-                          mode=args.mode, seed=0)
+    diet = args.config.endswith("dietnerf")
+    rcfg = {"n_render_samples_coarse": N_C, "n_render_samples_fine": N_F}
+    if diet:
+        import numpy as np
+        g = torch.Generator().manual_seed(0)
+        targets = torch.rand(8, 64, 64, 3, generator=g).numpy()        # stand-ins for the training images (embedded once)
+        poses = np.stack([np.eye(4, dtype=np.float32) for _ in range(8)])
+        model = pkg.DietNeRFModel(net_config(batch), rcfg, near, far, targets, poses, fov, -1, np.zeros(3), np.eye(4),
+                                  mode=args.mode, seed=0, numpy_seed=0, resample_every_call=True)
+    else:
+        model = pkg.NeRFModel(net_config(batch), rcfg, near, far, mode=args.mode, seed=0)
     model.compile(optimizer=pkg.Adam(5e-4))
     if world > 1:
         model.distribute()
@@ -215,9 +227,14 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    def train_local(o, d, y):
+        if diet:       # DietNeRF.train_step: counter, consistency term every 13th step, then the sharded ray step
+            return model.train_step_sharded(o, d, y, n_total, rank * batch)
+        return model.train_step_local(o, d, y, n_total, rank * batch)
+
     def step_device(i):
         o, d, y = devb[i % n_batches]
-        return model.train_step_local(o, d, y, n_total, rank * batch)
+        return train_local(o, d, y)
 
     # e2e: every step copies ITS batch from pinned host memory and its loss is read back to the host inside the timed
     # region.  The read-back is asynchronous (pinned 4-byte slot + event, consumed one step later; the last one before
@@ -233,7 +250,7 @@ def main():
     def step_e2e(i):
         o, d, y = pinned[i % n_batches]
         od, dd, yd = (t.cuda(non_blocking=True) for t in (o, d, y))
-        m = model.train_step_local(od, dd, yd, n_total, rank * batch)
+        m = train_local(od, dd, yd)
         loss_slots[i % 2].copy_(m["loss"].reshape(1), non_blocking=True)     # D2H read of the step's result
         loss_events[i % 2].record()
         if i > 0:
@@ -361,7 +378,9 @@ def main():
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16" if args.mode == "bf16" else "f32", "data": "synthetic",
             "config": {"workload": f"train_step {args.config}: {batch} rays/step/GPU, {N_C} coarse + {N_F} fine samples, "
-                                   "8x256 MLPs + view branch, Adam",
+                                   "8x256 MLPs + view branch, Adam"
+                                   + (", + every 13th step the DietNeRF consistency term (150x150 in-tape render at "
+                                      "55+55 samples, random-init ViT-B/32, cosine loss, backward)" if diet else ""),
                        "global_batch_rays": n_total, "parallelism": f"ray-sharded dp{world}",
                        "l2": "working set per step (saved activations + dZ, ~4.5 GB at 2048 rays) >> 126 MB L2; "
                              "4 distinct ray batches rotate"},

@@ -4,10 +4,21 @@ The key STRINGS are the config-file contract of the reference (src/Configuration
 the reference's config_files/*.yaml load unchanged; only the keys the hot path and its immediate callers read are
 listed here.
 """
-# top-level blocks
+# top-level keys and blocks
+EXISTING_SAVE_DIR_NAME = 'existing_save_dir_name'
+STARTING_EPOCH_NUMBER = 'starting_epoch_number'
+DATASET_TYPE = 'dataset_type'
+DATASET_LOCATION = 'dataset_location'
+PICS_INDICES_TO_USE_IN_DATASET = 'pics_indices_to_use_in_dataset'
+GENERAL_SAVE_LOCATION = 'general_save_location'
+TASKS_TO_PERFORM = 'tasks_to_perform'
+START_TRAINING = 'start_training'
 NEURAL_NET = 'neural_net'
 RENDER = 'render'
 TRAINING = 'training'
+VIDEO = 'video'
+BLENDER = 'blender'
+COLMAP = 'colmap'
 
 # neural_net:
 TYPE_OF_MODEL = 'type_of_model'
@@ -29,6 +40,8 @@ FAR_DEPTH_RENDER = 'far_depth_render'
 # training:
 N_EPOCHS = 'n_epochs'
 OPTIMIZER_LR = 'optimizer_lr'
+TEST_IMG_IDX = 'test_img_idx'
+IDX_TRAIN_IMG_TO_PLOT = 'idx_train_img_to_plot'
 
 NERF_MODEL = 'NeRF'
 DIETNERF_MODEL = 'DietNeRF'

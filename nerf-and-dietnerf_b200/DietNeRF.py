@@ -170,6 +170,14 @@ class DietNeRF(NeRF):
         return loss.detach()
 
     def train_step(self, data) -> Dict:
+        return self._train_step_with_consistency(lambda: super(DietNeRF, self).train_step(data))
+
+    def train_step_sharded(self, rays_orig, rays_dirs, real_rgb, n_total_rays, ray_offset=0) -> Dict:
+        """``train_step`` for callers that already hold THIS rank's shard on the device (see NeRF.train_step_local)."""
+        return self._train_step_with_consistency(
+            lambda: self.train_step_local(rays_orig, rays_dirs, real_rgb, n_total_rays, ray_offset))
+
+    def _train_step_with_consistency(self, ray_step) -> Dict:
         self.counter += 1
         cosine_similarity_loss = 0.0
         extra = None
@@ -184,7 +192,7 @@ class DietNeRF(NeRF):
                 self._keep_grads = True
         self._extra_grads = extra
         try:
-            metrics = super().train_step(data)
+            metrics = ray_step()
         finally:
             self._keep_grads = False
         return self._create_metrics(metrics, cosine_similarity_loss)

@@ -1,0 +1,203 @@
+"""Host train / render loop around the hot path: the slice of src/ExecutionRun.py that feeds it.
+
+Kept: config -> dataset -> model (``get_nerf`` :216-232, ``_init_dietnerf`` :234-264) -> epoch loop (``_training``
+:169-201: ``fit`` over ``steps_per_epoch = (n_images*h*w) // batch`` shuffled ray batches, then PSNR of the held-out test
+image and of one training image, then a weight + PSNR checkpoint per epoch) and the frame loop of ``render_video``
+(:315-356: rgb + depth = sum w z per pose).  Not rebuilt: plots, video encoding, GCS sync, the task switchboard.
+
+Differences from the reference, all in how the loop is driven, none in what a step computes: the ray table lives in HBM
+(``RayDataset``) instead of a tf.data pipeline; metrics stay on the device and are read once per epoch; with
+``torch.distributed`` initialised every rank runs the same loop on its shard of each batch (one gradient all-reduce
+per step) and rank 0 writes the checkpoints.
+"""
+import os
+import re
+import shutil
+import time
+from pathlib import Path, PureWindowsPath
+
+import numpy as np
+import torch
+
+from . import UtilsFiles
+from .ConfigurationKeys import (BLENDER, COLMAP, DATASET_LOCATION, DATASET_TYPE, DIETNERF_MODEL, EXISTING_SAVE_DIR_NAME,
+                                FAR_DEPTH_RENDER, GENERAL_SAVE_LOCATION, IDX_TRAIN_IMG_TO_PLOT, N_EPOCHS,
+                                N_RAYS_IN_BATCH_TRAIN, NEAR_DEPTH_RENDER, NEURAL_NET, OPTIMIZER_LR,
+                                PICS_INDICES_TO_USE_IN_DATASET, RENDER, STARTING_EPOCH_NUMBER, START_TRAINING,
+                                TASKS_TO_PERFORM, TEST_IMG_IDX, TRAINING, TYPE_OF_MODEL)
+from .DietNeRF import DietNeRF
+from .NeRF import NeRF
+from .optimizers import Adam
+from .poses import estimate_point_of_interest_in_scene
+from .UtilsNeuralRadianceField import get_num_of_batches, get_psnr_for_image, prepare_ds
+
+SAVE_DIR_NAME_FORMAT = '{}_save_dir_{}'
+
+
+def get_save_location(path_to_config_file, config) -> Path:
+    """src/UtilsFiles.py:232-281: the named existing directory, or ``<general>/<config stem>_save_dir_<next index>``."""
+    general = Path(config[GENERAL_SAVE_LOCATION])
+    existing = config[EXISTING_SAVE_DIR_NAME]
+    if existing:
+        if not (general / existing).exists():
+            raise Exception('Save location', general / existing, 'does not exists.')
+        return general / existing
+    stem = Path(path_to_config_file).stem
+    os.makedirs(general, exist_ok=True)
+    taken = [int(re.findall(r'\d+', n)[-1]) for n in os.listdir(general) if re.match(rf'^{re.escape(stem)}_save_dir_\d+$', n)]
+    new_dir = general / SAVE_DIR_NAME_FORMAT.format(stem, max(taken) + 1 if taken else 0)
+    os.makedirs(new_dir)
+    return new_dir
+
+
+class ExecutionRun:
+    """``ExecutionRun(path_to_config_file).start()`` as in main.py:26-27; ``from_arrays`` skips the file system."""
+
+    def __init__(self, path_to_config_file=None, *, config=None, data=None, save_location=None, mode="bf16", seed=0):
+        if config is None:
+            config = UtilsFiles.load_config(path_to_config_file)
+        self.config = config
+        self.mode, self.seed = mode, seed
+        self.tasks_to_perform = config.get(TASKS_TO_PERFORM, {START_TRAINING: True})
+        self.dataset_type = config.get(DATASET_TYPE)
+        self.pics_indices_to_use_in_dataset = config.get(PICS_INDICES_TO_USE_IN_DATASET)
+        self.net_config, self.render_config, self.training_config = config[NEURAL_NET], config[RENDER], config[TRAINING]
+        data = self.get_data(config) if data is None else data
+        (self.images, self.camera_poses, self.field_of_view, self.near_boundary, self.far_boundary,
+         self.average_c2w_before_recenter, self.c2w_scale_parameter) = data
+        if save_location is None and path_to_config_file is not None:
+            save_location = get_save_location(path_to_config_file, config)
+            shutil.copyfile(path_to_config_file, Path(save_location) / Path(path_to_config_file).name)
+        self.save_location = Path(save_location) if save_location is not None else None
+        start = config.get(STARTING_EPOCH_NUMBER, -1)
+        self._epoch_number = start if start and start > 0 else 0
+        self.is_main = not (torch.distributed.is_available() and torch.distributed.is_initialized()) or \
+            torch.distributed.get_rank() == 0
+        self.history = []                    # one dict per epoch: epoch, seconds, psnr_test, psnr_train, loss
+
+    @classmethod
+    def from_arrays(cls, config, images, camera_poses, field_of_view, near_boundary, far_boundary, **kw):
+        return cls(config=config, data=(np.asarray(images, dtype=np.float32), np.asarray(camera_poses, dtype=np.float32),
+                                        float(field_of_view), float(near_boundary), float(far_boundary), None, 1.0), **kw)
+
+    def get_data(self, config):
+        location = Path(PureWindowsPath(config[DATASET_LOCATION]))        # the YAMLs use Windows separators
+        if self.dataset_type == BLENDER:
+            return UtilsFiles.get_data_from_blender(location, config[RENDER][NEAR_DEPTH_RENDER],
+                                                    config[RENDER][FAR_DEPTH_RENDER])
+        if self.dataset_type == COLMAP:
+            return UtilsFiles.get_data_from_colmap(location)
+        raise Exception(f"unknown dataset_type {self.dataset_type!r}")
+
+    # ---- model ---------------------------------------------------------------------------------------------------------------
+    def get_train_images_indices(self, idx_test):
+        keep = set(self.pics_indices_to_use_in_dataset) if self.pics_indices_to_use_in_dataset else None
+        return [n for n in range(len(self.images)) if n != idx_test and (keep is None or n in keep)]
+
+    def _get_train_data_from_loaded_dataset(self):
+        idx_test = self.training_config[TEST_IMG_IDX]
+        idx = self.get_train_images_indices(idx_test)
+        return idx_test, self.images[idx], self.camera_poses[idx]
+
+    def get_nerf(self) -> NeRF:
+        """A new model + Adam(lr); loads ``saved_weights/NeRF_model_epoch_<starting epoch>.h5`` when it exists."""
+        kw = dict(mode=self.mode, seed=self.seed)
+        if self.net_config[TYPE_OF_MODEL] == DIETNERF_MODEL:
+            model = self._init_dietnerf(kw)
+        else:
+            model = NeRF(self.net_config, self.render_config, self.near_boundary, self.far_boundary, **kw)
+        model.compile(optimizer=Adam(self.training_config[OPTIMIZER_LR]))
+        if torch.distributed.is_available() and torch.distributed.is_initialized() and \
+                torch.distributed.get_world_size() > 1:
+            model.distribute()
+        if self.save_location is not None:
+            path = NeRF.get_nerf_model_path(self.save_location, self._epoch_number)
+            if os.path.exists(path):
+                model.load_weights(path)
+        return model
+
+    def _init_dietnerf(self, kw):
+        h, w = self.images[0].shape[0], self.images[0].shape[1]
+        _, train_images, train_poses = self._get_train_data_from_loaded_dataset()
+        n_batches = get_num_of_batches(self.net_config[N_RAYS_IN_BATCH_TRAIN], len(train_images), h, w)
+        n_steps = n_batches * (self.training_config[N_EPOCHS] - self._epoch_number)
+        n_steps *= DietNeRF.PERCENTAGE_OF_TRAIN_STEPS_WITH_CONSISTENCY_LOSS
+        point, spherical = estimate_point_of_interest_in_scene(self.camera_poses, rng=np.random.RandomState(self.seed))
+        rot = None
+        if spherical:
+            rot = np.eye(4)
+            rot[:3, :3] = self.camera_poses[self.training_config[TEST_IMG_IDX]][:3, :3]
+        return DietNeRF(self.net_config, self.render_config, self.near_boundary, self.far_boundary, train_images,
+                        train_poses, self.field_of_view, int(n_steps), point if spherical else None, rot, **kw)
+
+    # ---- training ------------------------------------------------------------------------------------------------------------
+    def start(self):
+        if self.tasks_to_perform.get(START_TRAINING, False):
+            self._training()
+            self._epoch_number = self.training_config[N_EPOCHS]
+
+    def fit(self, model, ds, steps_per_epoch):
+        """One Keras ``fit`` epoch: ``steps_per_epoch`` batches of a fresh shuffle; returns the mean metrics."""
+        sums, n = {}, 0
+        for batch in ds:
+            if n >= steps_per_epoch:
+                break
+            for k, v in model.train_step(batch).items():
+                sums[k] = sums.get(k, 0.0) + (v.detach() if isinstance(v, torch.Tensor) else v)
+            n += 1
+        return {k: float(v) / max(n, 1) for k, v in sums.items()}
+
+    def _epoch_psnrs(self, model, train_image, train_c2w, test_image, test_c2w):
+        out = []
+        for img, c2w in ((test_image, test_c2w), (train_image, train_c2w)):
+            h, w = img.shape[0], img.shape[1]
+            render = model.render_image_lean(c2w, self.field_of_view, h, w)[0].reshape(h, w, 3)
+            out.append(float(get_psnr_for_image(render, torch.as_tensor(img, device=render.device))))
+        return out
+
+    def _training(self, on_epoch_end=None):
+        idx_test, train_images, train_poses = self._get_train_data_from_loaded_dataset()
+        idx_plot = self.training_config[IDX_TRAIN_IMG_TO_PLOT]
+        psnrs_test, psnrs_train = ([], []) if self.save_location is None else UtilsFiles.get_psnr_values(
+            UtilsFiles.get_psnr_save_path(self.save_location, self._epoch_number))
+        h, w = self.images[0].shape[0], self.images[0].shape[1]
+        batch = self.net_config[N_RAYS_IN_BATCH_TRAIN]
+        ds = prepare_ds(batch, train_poses, train_images, self.field_of_view, seed=self.seed)
+        n_batches = get_num_of_batches(batch, len(train_poses), h, w)
+        model = self.get_nerf()
+        self.model = model
+        for epoch_number in range(self._epoch_number + 1, self.training_config[N_EPOCHS] + 1):
+            torch.cuda.synchronize()
+            t0 = time.time()
+            metrics = self.fit(model, ds, n_batches)
+            torch.cuda.synchronize()
+            seconds = time.time() - t0
+            p_test, p_train = self._epoch_psnrs(model, self.images[idx_plot], self.camera_poses[idx_plot],
+                                                self.images[idx_test], self.camera_poses[idx_test])
+            psnrs_test.append(p_test)
+            psnrs_train.append(p_train)
+            self.history.append({"epoch": epoch_number, "seconds": seconds, "psnr_test": p_test, "psnr_train": p_train,
+                                 **metrics})
+            if self.save_location is not None and self.is_main:
+                UtilsFiles.save_weights(model, NeRF.get_nerf_model_path(self.save_location, epoch_number))
+                UtilsFiles.save_psnr_values(psnrs_test, psnrs_train,
+                                            UtilsFiles.get_psnr_save_path(self.save_location, epoch_number))
+            if self.is_main:
+                print(f"Done epoch {epoch_number} in {seconds:.2f} sec. ({seconds / max(n_batches, 1) * 1e3:.2f} ms / step) "
+                      f"Test PSNR: {p_test:.3f}")
+            if on_epoch_end is not None:
+                on_epoch_end(self, model, epoch_number)
+        return model
+
+    # ---- rendering ---------------------------------------------------------------------------------------------------------
+    def render_frames(self, model, c2w_matrices, h=None, w=None):
+        """The frame loop of ``render_video`` (:315-356) without the encoder: uint8 rgb (F,h,w,3) and float depth
+        (F,h,w) = sum w z, on the host."""
+        h = self.images[0].shape[0] if h is None else h
+        w = self.images[0].shape[1] if w is None else w
+        rgbs, depths = [], []
+        for c2w in c2w_matrices:
+            rgb, depth, _ = model.render_image_lean(c2w, self.field_of_view, h, w)
+            rgbs.append((rgb.reshape(h, w, 3).clamp(0, 1) * 255).to(torch.uint8).cpu().numpy())
+            depths.append(depth.reshape(h, w).cpu().numpy())
+        return np.stack(rgbs), np.stack(depths)

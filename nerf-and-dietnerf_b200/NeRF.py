@@ -149,6 +149,42 @@ class NeRF:
     def get_nerf_model_path(save_location: Path, epoch_number: int) -> Path:
         return Path(save_location) / DIRNAME_TO_SAVE_WEIGHTS / NAME_NERF_MODEL_FILE.format(epoch_number)
 
+    def save_weights(self, filepath):
+        """Keras ``Model.save_weights`` for this model: ``.h5`` -> the reference's Keras-2.7 HDF5 checkpoint layout
+        (groups ``model`` / ``model_1``, layers ``dense`` ... ``dense_21``; see h5weights.py), anything else -> ``.npz``
+        with the two flat vectors."""
+        from . import h5weights
+        pc = self.model_coarse.params.detach().cpu().numpy()
+        pf = self.model_fine.params.detach().cpu().numpy() if self.model_fine is not None else None
+        filepath = str(filepath)
+        if filepath.endswith((".h5", ".hdf5")):
+            h5weights.save_flat_params(filepath, pc, pf, self.model_coarse.shapes)
+        else:
+            import numpy as np
+            arrays = {"params_coarse": pc}
+            if pf is not None:
+                arrays["params_fine"] = pf
+            with open(filepath, "wb") as f:
+                np.savez(f, **arrays)
+
+    def load_weights(self, filepath):
+        """Keras ``Model.load_weights``: reads a checkpoint written by ``save_weights`` OR by the reference's Keras
+        (e.g. ``Results/.../saved_weights/NeRF_model_epoch_095.h5``)."""
+        from . import h5weights
+        filepath = str(filepath)
+        if filepath.endswith((".h5", ".hdf5")):
+            pc, pf = h5weights.load_flat_params(filepath)
+        else:
+            import numpy as np
+            with np.load(filepath) as z:
+                pc, pf = z["params_coarse"], (z["params_fine"] if "params_fine" in z.files else None)
+        self.model_coarse.set_params(pc)
+        if self.model_fine is not None:
+            if pf is None:
+                raise ValueError(f"{filepath} holds one network but the model has a fine network")
+            self.model_fine.set_params(pf)
+        return self
+
     def compile(self, optimizer=None, **kwargs):
         """Keras-style: attach the optimizer (``Adam(learning_rate)``)."""
         self.optimizer = optimizer if optimizer is not None else Adam(**kwargs)

@@ -9,9 +9,11 @@ no CPU fallback.
 from . import ConfigurationKeys, _lib  # noqa: F401
 from . import UtilsCV, UtilsNeuralRadianceField, network, optimizers, parallel, poses, vit  # noqa: F401
 from . import NeRF as _nerf_module, DietNeRF as _dietnerf_module  # noqa: F401
+from . import ExecutionRun as _execution_run_module, UtilsFiles, h5weights  # noqa: F401
 from ._lib import LIB_PATH, NerfLibraryError, NetCfg, load  # noqa: F401
 from .network import NerfMLP  # noqa: F401
 from .optimizers import Adam  # noqa: F401
 
 NeRFModel = _nerf_module.NeRF
 DietNeRFModel = _dietnerf_module.DietNeRF
+ExecutionRun = _execution_run_module.ExecutionRun

@@ -83,3 +83,72 @@ def interpolation_type_slerp_for_c2w(c2w1, c2w2, alpha):
     if alpha.shape != ():
         return [one(c2w1, c2w2, float(a)) for a in alpha]
     return one(c2w1, c2w2, float(alpha))
+
+
+# ---- scene point of interest (src/UtilsCV.py:333-404, :440-464), used by ExecutionRun._init_dietnerf --------------------
+def _normalize(x):
+    return x / np.linalg.norm(x, axis=-1)[..., None]
+
+
+def get_camera_dir_from_c2w(c2w):
+    """The camera looks down its -z axis (src/UtilsCV.py:602-609)."""
+    return _normalize(-np.asarray(c2w)[:3, 2])
+
+
+def estimate_intersection_between_lines(dirs_and_t):
+    """Least-squares point closest to a set of lines given as (direction, point) pairs."""
+    if dirs_and_t.shape[0] == 1:
+        return None
+    dirs, t = _normalize(dirs_and_t[:, 0]), dirs_and_t[:, 1]
+    proj = np.eye(dirs.shape[-1]) - dirs[..., None] @ dirs[..., None, :]
+    left = np.concatenate(proj, axis=0)
+    right = np.concatenate(np.squeeze(proj @ t[..., None], -1), axis=0)
+    return np.linalg.lstsq(left, right, rcond=None)[0]
+
+
+def get_distance_of_point_from_line(point, dirs_and_t):
+    """SQUARED distance of ``point`` from every line (what the reference compares with its tolerance)."""
+    dirs, t = _normalize(dirs_and_t[:, 0]), dirs_and_t[:, 1]
+    proj = np.eye(dirs.shape[-1]) - dirs[..., None] @ dirs[..., None, :]
+    diff = (t - point)
+    return np.squeeze(diff[..., None, :] @ proj @ diff[..., None], (-1, -2))
+
+
+def ransac_get_estimation_for_intersection_point(dirs_and_t, num_iter=10000, inlier_tol=0.001, n_lines=2, rng=None):
+    rng = np.random if rng is None else rng
+    best_n, best_idx = -1, None
+    for _ in range(num_iter):
+        choice = rng.choice(dirs_and_t.shape[0], n_lines, replace=False)
+        point = estimate_intersection_between_lines(dirs_and_t[choice])
+        inlier = get_distance_of_point_from_line(point, dirs_and_t) < inlier_tol
+        if inlier.sum() > best_n:
+            best_n, best_idx = int(inlier.sum()), np.where(inlier)[0]
+    if best_n > 1:
+        point = estimate_intersection_between_lines(dirs_and_t[best_idx])
+        return point, np.where(get_distance_of_point_from_line(point, dirs_and_t) < inlier_tol)[0]
+    return None, None
+
+
+def estimate_point_of_interest_in_scene(c2w_matrices, num_iter=10000, rng=None):
+    """-> (estimated look-at point or None, is_spherical_dataset): spherical when more than 30 % of the optical axes
+    pass within the tolerance of the estimate."""
+    assert len(c2w_matrices) > 1
+    dirs_and_t = np.asarray([[get_camera_dir_from_c2w(c), np.asarray(c)[:3, 3]] for c in c2w_matrices], dtype=np.float64)
+    point, inliers = ransac_get_estimation_for_intersection_point(dirs_and_t, num_iter=num_iter, rng=rng)
+    if point is not None and inliers is not None:
+        return point, bool(inliers.shape[0] > 0.3 * dirs_and_t.shape[0])
+    return None, False
+
+
+def get_l_to_r_c2w_matrices(total_frames):
+    """Left-to-right dolly looking forward (src/UtilsCV.py:407-426)."""
+    mats = np.tile(np.eye(4, dtype=np.float32), (total_frames, 1, 1))
+    mats[:, 0, 3] = np.linspace(0, 1, total_frames) * 2 - 1
+    return mats
+
+
+def get_sphere_matrices(total_n_matrices):
+    """Orbit about y then about x on the unit sphere (src/UtilsCV.py:429-437): 2 * total_n_matrices poses."""
+    mats = [get_sphere_matrix(1, 0, deg, 0) for deg in np.linspace(0, 360, total_n_matrices)] + \
+           [get_sphere_matrix(1, deg, 0, 0) for deg in np.linspace(0, 360, total_n_matrices)]
+    return np.asarray(mats, dtype=np.float32)
