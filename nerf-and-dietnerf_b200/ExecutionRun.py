@@ -101,7 +101,7 @@ class ExecutionRun:
 
     def get_nerf(self) -> NeRF:
         """A new model + Adam(lr); loads ``saved_weights/NeRF_model_epoch_<starting epoch>.h5`` when it exists."""
-        kw = dict(mode=self.mode, seed=self.seed)
+        kw = dict(mode=self.mode, seed=self.seed, stop_grad_z=getattr(self, "stop_grad_z", False))
         if self.net_config[TYPE_OF_MODEL] == DIETNERF_MODEL:
             model = self._init_dietnerf(kw)
         else:

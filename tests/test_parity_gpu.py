@@ -734,6 +734,5 @@ def test_training_run_tracks_the_reference_psnr_curve(pkg, tmp_path):
                              save_location=str(tmp_path), mode="bf16", seed=5)
     model = again.get_nerf()
     assert torch.equal(model.model_coarse.params, runner.model.model_coarse.params)
-    rgbs, depths = again.render_frames(model, pkg.poses.get_sphere_matrices(2)[:2] * np.array([1, 1, 1, 0.8])[None, None, :]
-                                       + 0 * np.eye(4)[None])
+    rgbs, depths = again.render_frames(model, pkg.poses.get_sphere_matrices(2)[:2])
     assert rgbs.shape == (2, 50, 50, 3) and rgbs.dtype == np.uint8 and depths.shape == (2, 50, 50)

@@ -32,7 +32,7 @@ RUN_CONFIG = {      # Results/50px_alexander_71pics_sphere_nerf_save_dir_4/50px_
 }
 
 
-def run(epochs=95, mode="bf16", seed=0, save_location=None, model_type="NeRF"):
+def run(epochs=95, mode="bf16", seed=0, save_location=None, model_type="NeRF", stop_grad_z=False):
     pkg = importlib.import_module("nerf-and-dietnerf_b200")
     data = np.load(os.path.join(ROOT, "tests", "golden", "alexander50_dataset.npz"))
     pin = np.load(os.path.join(ROOT, "tests", "golden", "alexander50_pin.npz"))
@@ -42,6 +42,7 @@ def run(epochs=95, mode="bf16", seed=0, save_location=None, model_type="NeRF"):
     images = data["images_u8"].astype(np.float32) / 255.0
     runner = pkg.ExecutionRun.from_arrays(config, images, data["c2w"], float(data["fov"]), float(data["near"]),
                                           float(data["far"]), mode=mode, seed=seed, save_location=save_location)
+    runner.stop_grad_z = stop_grad_z
     t0 = time.time()
     runner._training()
     torch.cuda.synchronize()
@@ -64,9 +65,12 @@ def main():
     ap.add_argument("--mode", default="bf16")
     ap.add_argument("--model", default="NeRF", choices=["NeRF", "DietNeRF"])
     ap.add_argument("--out", default=None)
+    ap.add_argument("--seed", type=int, default=0)
+    ap.add_argument("--stop-grad-z", action="store_true", help="detach the importance samples (NOT the reference's behaviour)")
     args = ap.parse_args()
     with tempfile.TemporaryDirectory() as tmp:
-        res, runner = run(args.epochs, args.mode, save_location=tmp, model_type=args.model)
+        res, runner = run(args.epochs, args.mode, seed=args.seed, save_location=tmp, model_type=args.model,
+                          stop_grad_z=args.stop_grad_z)
         # checkpoint round trip through the Keras .h5 layout
         path = runner.model.get_nerf_model_path(tmp, args.epochs)
         before = runner.model.model_fine.params.clone()
