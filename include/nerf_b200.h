@@ -177,6 +177,10 @@ int nerf_merge_sorted_bwd(const float* d_out, const int32_t* rank_a, int32_t sa,
 /* d_rgb = loss_weight * 2 (rgb-target) / (3*n_total); sums[0] += sum((rgb-target)^2) (caller zeroes). */
 int nerf_mse_fwd_bwd(const float* rgb, const float* target, int64_t n_rays, int64_t n_total_rays,
                      float loss_weight, float* sq_err_sum, float* d_rgb, void* stream);
+/* Metrics of the step from the two squared-error sums (src/NeRF.py:170-178; get_psnr src/UtilsNeuralRadianceField.py:
+ * 123-132): out4 = [coarse_loss_weight*MSE_c + MSE_f, psnr_coarse, psnr_fine, MSE_c + MSE_f], MSE = sum / (3*n_total). */
+int nerf_train_metrics(const float* sq_err_sums, int64_t n_total_rays, float coarse_loss_weight, int32_t has_fine,
+                       float* out4, void* stream);
 /* Keras-2.7 Adam update, t = 1-based step. */
 int nerf_adam_step(float* params, const float* grads, float* m, float* v, int64_t n, float lr, float beta1,
                    float beta2, float eps, int64_t t, void* stream);

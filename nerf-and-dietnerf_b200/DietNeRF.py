@@ -204,8 +204,7 @@ class DietNeRF(NeRF):
 
     def _metrics(self, sums, n_total):
         m = super()._metrics(sums, n_total)
-        mse_c = sums[0] / (3.0 * n_total)
-        m["loss_for_rays"] = mse_c + (sums[1] / (3.0 * n_total) if self.model_fine is not None else 0.0)
+        m["loss_for_rays"] = self._metrics_raw[3]          # MSE_c + MSE_f (src/DietNeRF.py:163,168)
         return m
 
     @staticmethod

@@ -134,6 +134,8 @@ class NeRF:
         self._grads = None
         self._overlap_allreduce = False
         self._fine_allreduce = None
+        self._fine_update = None        # set by train_step_local: the fine network's optimizer step, run early
+        self._fine_updated = False
         self._side = None
         self.overlap_dw = True          # False: every kernel of the step runs on one stream (per-kernel timing)
         # data-parallel state (set by distribute())
@@ -395,6 +397,14 @@ class NeRF:
                 # the fine network's gradients are final: their all-reduce runs under the coarse backward
                 with torch.cuda.stream(side) if side is not None else contextlib.nullcontext():
                     self._fine_allreduce = allreduce_sum_(g_f, self._process_group, async_op=True)
+            if self._fine_update is not None:
+                # ... and so do its Adam update and the refresh of its bf16 weight pack
+                with torch.cuda.stream(side) if side is not None else contextlib.nullcontext():
+                    if self._fine_allreduce is not None:
+                        self._fine_allreduce.wait()
+                        self._fine_allreduce = None
+                    self._fine_update(g_f)
+                    self._fine_updated = True
             if through_z:
                 # z_f -> xyz -> PE -> fine net, and z_f -> delta in the fine compositing, reach the coarse weights
                 call("nerf_encode_samples_bwd_z", mf.cfg_ref, ptr(o), ptr(d), ptr(w.z_f), ptr(w.d_xyz_f), n, sf,
@@ -517,15 +527,15 @@ class NeRF:
                  n * s, ptr(raw), ptr(saved), ptr(ws), net.mode_id)
 
     def _metrics(self, sums, n_total):
-        mse_c = sums[0] / (3.0 * n_total)
-        metrics = {}
-        loss = self.COARSE_LOSS_WEIGHT * mse_c
-        metrics["psnr_coarse"] = get_psnr(mse_c)
-        if self.model_fine is not None:
-            mse_f = sums[1] / (3.0 * n_total)
-            loss = loss + mse_f
-            metrics["psnr_fine"] = get_psnr(mse_f)
-        return {"loss": loss, **metrics}
+        """{"loss", "psnr_coarse", "psnr_fine"} as device scalars (src/NeRF.py:170-178), one tiny kernel."""
+        out = torch.empty(4, dtype=torch.float32, device=self.device)
+        has_fine = self.model_fine is not None
+        call("nerf_train_metrics", ptr(sums), int(n_total), float(self.COARSE_LOSS_WEIGHT), 1 if has_fine else 0, ptr(out))
+        metrics = {"loss": out[0], "psnr_coarse": out[1]}
+        if has_fine:
+            metrics["psnr_fine"] = out[2]
+        self._metrics_raw = out
+        return metrics
 
     def train_step(self, data) -> Dict:
         """One optimisation step on a batch (rays_orig (B,4), rays_dirs (B,4), real_rgb (B,3)).
@@ -548,18 +558,31 @@ class NeRF:
         """
         if self.optimizer is None:
             raise RuntimeError("call compile(optimizer=Adam(lr)) before train_step")
+        mc, mf = self.model_coarse, self.model_fine
+        n_all = mc.n_params + (mf.n_params if mf is not None else 0)
+        t_next = self.optimizer.iterations + 1
+        early = mf is not None and hasattr(self.optimizer, "apply_one") and getattr(self, "_extra_grads", None) is None
+
+        def fine_update(g_f):
+            self.optimizer.apply_one(mf.params, g_f, mc.n_params, n_all, t_next)
+            mf.mark_updated()
+            mf.packed_for(mf.params)
+
         self._overlap_allreduce = True
+        self._fine_update, self._fine_updated = (fine_update if early else None), False
         try:
             self.forward_backward(rays_orig, rays_dirs, real_rgb, n_total_rays=n_total_rays, ray_offset=ray_offset,
                                   keep_grads=getattr(self, "_keep_grads", False))
         finally:
             self._overlap_allreduce = False
+            self._fine_update = None
         g = self._grad_buffer()
         if self.world_size > 1:
-            if self._fine_allreduce is not None:
-                allreduce_sum_(g[:4 + self.model_coarse.n_params], self._process_group)   # [sums | coarse gradients]
-                self._fine_allreduce.wait()
-                self._fine_allreduce = None
+            if self._fine_allreduce is not None or self._fine_updated:
+                allreduce_sum_(g[:4 + mc.n_params], self._process_group)   # [sums | coarse gradients]
+                if self._fine_allreduce is not None:
+                    self._fine_allreduce.wait()
+                    self._fine_allreduce = None
             else:
                 allreduce_sum_(g, self._process_group)
         self.apply_gradients(g)
@@ -569,7 +592,13 @@ class NeRF:
     def apply_gradients(self, g):
         mc, mf = self.model_coarse, self.model_fine
         n = mc.n_params + (mf.n_params if mf is not None else 0)
-        self.optimizer.apply_flat([mc.params] + ([mf.params] if mf is not None else []), g[4:4 + n])
+        if self._fine_updated:
+            # the fine network was stepped on the side stream as soon as its gradients were final
+            self.optimizer.iterations += 1
+            self.optimizer.apply_one(mc.params, g[4:4 + mc.n_params], 0, n, self.optimizer.iterations)
+            self._fine_updated = False
+        else:
+            self.optimizer.apply_flat([mc.params] + ([mf.params] if mf is not None else []), g[4:4 + n])
+            if mf is not None:
+                mf.mark_updated()
         mc.mark_updated()
-        if mf is not None:
-            mf.mark_updated()

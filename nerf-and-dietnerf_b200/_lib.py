@@ -66,6 +66,7 @@ SIGNATURES = {
     "nerf_merge_sorted_rank": (c_int32, [_P, c_int32, _P, c_int32, c_int64, _P, _P, _P]),
     "nerf_merge_sorted_bwd": (c_int32, [_P, _P, c_int32, c_int32, c_int64, _P, _P]),
     "nerf_mse_fwd_bwd": (c_int32, [_P, _P, c_int64, c_int64, c_float, _P, _P, _P]),
+    "nerf_train_metrics": (c_int32, [_P, c_int64, c_float, c_int32, _P, _P]),
     "nerf_adam_step": (c_int32, [_P, _P, _P, _P, c_int64, c_float, c_float, c_float, c_float, c_int64, _P]),
 }
 

@@ -39,6 +39,19 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
   p[i] = p[i] - lr_t * mi / (sqrtf(vi) + eps);
 }
 
+// metrics of one train step from the two squared-error sums (src/NeRF.py:170-178, src/UtilsNeuralRadianceField.py:123-132):
+// out = [loss, psnr_coarse, psnr_fine, loss_for_rays]; one thread -- it replaces ~10 elementwise launches per step.
+__global__ void train_metrics_kernel(const float* __restrict__ sums, float inv_count, float coarse_weight, int has_fine,
+                                     float* __restrict__ out) {
+  const float mse_c = sums[0] * inv_count;
+  const float mse_f = has_fine ? sums[1] * inv_count : 0.f;
+  const float k = -10.0f / 2.302585092994046f;           // psnr = -10 ln(mse) / ln(10)
+  out[0] = coarse_weight * mse_c + mse_f;
+  out[1] = k * logf(mse_c);
+  out[2] = has_fine ? k * logf(mse_f) : 0.f;
+  out[3] = mse_c + mse_f;
+}
+
 }  // namespace nerf
 
 using namespace nerf;
@@ -53,6 +66,16 @@ int nerf_mse_fwd_bwd(const float* rgb, const float* target, int64_t n_rays, int6
   int64_t n = n_rays * 3;
   float scale = (float)(2.0 * (double)loss_weight / (3.0 * (double)n_total_rays));
   mse_fwd_bwd_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(rgb, target, n, scale, sq_err_sum, d_rgb);
+  NERF_CHECK_LAUNCH();
+  return NERF_OK;
+}
+
+int nerf_train_metrics(const float* sq_err_sums, int64_t n_total_rays, float coarse_loss_weight, int32_t has_fine,
+                       float* out4, void* stream) {
+  NERF_CHECK_ARG(sq_err_sums && out4, "null pointer");
+  NERF_CHECK_ARG(n_total_rays > 0, "bad ray count");
+  train_metrics_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(sq_err_sums, (float)(1.0 / (3.0 * (double)n_total_rays)),
+                                                          coarse_loss_weight, has_fine, out4);
   NERF_CHECK_LAUNCH();
   return NERF_OK;
 }

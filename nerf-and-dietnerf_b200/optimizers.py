@@ -32,5 +32,19 @@ class Adam:
                  self.iterations)
             off += n
 
+    def _state(self, total, device):
+        if self._m is None:
+            self._m = torch.zeros(total, dtype=torch.float32, device=device)
+            self._v = torch.zeros(total, dtype=torch.float32, device=device)
+
+    def apply_one(self, param, grad, offset, total, t):
+        """Update ONE of the flat parameter tensors (its moments live at ``offset`` of the shared state) as step ``t``;
+        the caller advances ``iterations`` once per step.  Lets the fine network's update run on a side stream as soon
+        as its gradients are final."""
+        self._state(total, grad.device)
+        n = param.numel()
+        call("nerf_adam_step", ptr(param), ptr(grad), ptr(self._m[offset:offset + n]), ptr(self._v[offset:offset + n]), n,
+             self.learning_rate, self.beta_1, self.beta_2, self.epsilon, int(t))
+
     def state_dict(self):
         return {"iterations": self.iterations, "m": self._m, "v": self._v, "learning_rate": self.learning_rate}
