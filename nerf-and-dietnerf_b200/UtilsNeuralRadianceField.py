@@ -181,6 +181,44 @@ class RayDataset:
             yield self.origs[idx], self.dirs[idx], self.rgbs[idx]
 
 
+class DevicePrefetcher:
+    """``Dataset.prefetch`` (src/UtilsNeuralRadianceField.py:159-160) for batches that live in (pinned) HOST memory:
+    yields device tuples, copying batch i+1 on a copy stream while batch i trains, so the PCIe latency of the three
+    small H2D copies of a step is off the compute stream."""
+
+    _streams = {}          # one copy stream per device, shared: its allocator pool stays warm across epochs
+
+    def __init__(self, batches, device=None):
+        self.batches = batches
+        self.device = device or torch.device("cuda", torch.cuda.current_device())
+        key = str(self.device)
+        if key not in DevicePrefetcher._streams:
+            DevicePrefetcher._streams[key] = torch.cuda.Stream(device=self.device)
+        self.stream = DevicePrefetcher._streams[key]
+
+    def _load(self, batch):
+        if batch is None:
+            return None
+        self.stream.wait_stream(torch.cuda.current_stream())       # never run ahead of memory the consumer still uses
+        with torch.cuda.stream(self.stream):
+            dev = tuple(t.to(device=self.device, dtype=torch.float32, non_blocking=True) for t in batch)
+            ready = torch.cuda.Event()
+            ready.record(self.stream)
+        return dev, ready
+
+    def __iter__(self):
+        it = iter(self.batches)
+        nxt = self._load(next(it, None))
+        while nxt is not None:
+            dev, ready = nxt
+            cur = torch.cuda.current_stream()
+            cur.wait_event(ready)
+            for t in dev:
+                t.record_stream(cur)
+            nxt = self._load(next(it, None))
+            yield dev
+
+
 def prepare_ds(batch_size, c2w_matrices, images, fov, seed=None):
     """Training dataset of shuffled ray batches (rays_orig, rays_dirs, rgb)."""
     o, d, c = [], [], []

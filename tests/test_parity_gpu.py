@@ -736,3 +736,18 @@ def test_training_run_tracks_the_reference_psnr_curve(pkg, tmp_path):
     assert torch.equal(model.model_coarse.params, runner.model.model_coarse.params)
     rgbs, depths = again.render_frames(model, pkg.poses.get_sphere_matrices(2)[:2])
     assert rgbs.shape == (2, 50, 50, 3) and rgbs.dtype == np.uint8 and depths.shape == (2, 50, 50)
+
+
+def test_device_prefetcher_yields_every_batch_in_order(pkg):
+    g = torch.Generator().manual_seed(0)
+    host = [tuple(torch.rand(257, k, generator=g).pin_memory() for k in (4, 4, 3)) for _ in range(7)]
+    got = []
+    for o, d, y in pkg.UtilsNeuralRadianceField.DevicePrefetcher(iter(host)):
+        assert o.is_cuda and d.is_cuda and y.is_cuda
+        got.append((o.clone(), d.clone(), y.clone()))
+        torch.cuda._sleep(200000)              # the consumer is busy while the next batch is copied
+    torch.cuda.synchronize()
+    assert len(got) == 7
+    for (o, d, y), (ho, hd, hy) in zip(got, host):
+        assert torch.equal(o.cpu(), ho) and torch.equal(d.cpu(), hd) and torch.equal(y.cpu(), hy)
+    assert list(pkg.UtilsNeuralRadianceField.DevicePrefetcher(iter([]))) == []
