@@ -27,20 +27,21 @@ __device__ __forceinline__ float build_cdf(const float* __restrict__ weights, co
     sz[i] = __ldcs(z + i);
   }
   __syncwarp();
+  // Sequential left-to-right fp32 sum and cumsum, computed REDUNDANTLY by every lane from broadcast shared-memory reads:
+  // the loads do not depend on the running value, so they pipeline and the dependent chain is one FADD per element
+  // (a single lane doing load -> add -> store through the same array paid a shared-memory round trip per element).
   float total = 0.f;
-  if (lane == 0) {
-    for (int i = 0; i < S; ++i) total = __fadd_rn(total, sw[i]);
-  }
-  total = __shfl_sync(kFullMask, total, 0);
+#pragma unroll 8
+  for (int i = 0; i < S; ++i) total = __fadd_rn(total, sw[i]);
   const float denom = __fadd_rn(total, 1e-7f);  // EPS, src/UtilsCV.py:30
-  for (int i = lane; i < S; i += 32) scdf[i] = __fdiv_rn(sw[i], denom);  // pdf for now
   __syncwarp();
-  if (lane == 0) {
-    float run = 0.f;
-    for (int i = 0; i < S; ++i) {
-      run = __fadd_rn(run, scdf[i]);
-      scdf[i] = run;
-    }
+  for (int i = lane; i < S; i += 32) sw[i] = __fdiv_rn(sw[i], denom);   // pdf (the weights are not needed after this)
+  __syncwarp();
+  float run = 0.f;
+#pragma unroll 8
+  for (int i = 0; i < S; ++i) {
+    run = __fadd_rn(run, sw[i]);
+    if ((i & 31) == lane) scdf[i] = run;
   }
   __syncwarp();
   return denom;
@@ -158,26 +159,38 @@ sample_pdf_bwd_kernel(const float* __restrict__ weights, const float* __restrict
     sbt[j] = d.b | (d.t << 16);
   }
   __syncwarp();
-  if (lane == 0) {
-    // deterministic scatter-add of the per-draw cdf gradients, then reverse cumsum -> d pdf (in place)
+  // Per-draw cdf gradients -> d cdf: every cdf entry GATHERS its contributions in draw order (lower end before upper
+  // end of the same draw), i.e. the same sequence of additions a sequential scatter would perform, lane-parallel over
+  // the entries.  Then the reverse cumsum -> d pdf, redundantly in every lane (pipelined broadcast reads, one dependent
+  // FADD per element), 32 entries at a time so no lane overwrites an entry another lane still has to read.
+  for (int i = lane; i < S; i += 32) {
+    float acc = 0.f;
     for (int j = 0; j < Nf; ++j) {
-      int b = sbt[j] & 0xffff, t = sbt[j] >> 16;
-      sdc[b] += sdlo[j];
-      sdc[t] += sdhi[j];
+      const int bt = sbt[j];
+      if ((bt & 0xffff) == i) acc += sdlo[j];
+      if ((bt >> 16) == i) acc += sdhi[j];
     }
-    float run = 0.f;
-    for (int i = S - 1; i >= 0; --i) {
+    sdc[i] = acc;
+  }
+  __syncwarp();
+  float run = 0.f;
+  for (int k0 = ((S - 1) >> 5) << 5; k0 >= 0; k0 -= 32) {
+    float mine = 0.f;
+    for (int i = min(S, k0 + 32) - 1; i >= k0; --i) {
       run += sdc[i];
-      sdc[i] = run;
+      if ((i & 31) == lane) mine = run;
     }
+    __syncwarp();
+    if (k0 + lane < S) sdc[k0 + lane] = mine;
   }
   __syncwarp();
   // pdf = w / denom, denom = sum(w) + eps :  d w_k = dpdf_k/denom - sum_j dpdf_j w_j / denom^2
+  //                                                  = dpdf_k/denom - (sum_j dpdf_j pdf_j) / denom   (sw holds the pdf)
   float part = 0.f;
   for (int i = lane; i < S; i += 32) part += sdc[i] * sw[i];
 #pragma unroll
   for (int d = 16; d > 0; d >>= 1) part += __shfl_xor_sync(kFullMask, part, d);
-  const float corr = part / (denom * denom);
+  const float corr = part / denom;
   for (int i = lane; i < S; i += 32) d_weights[ray * S + i] = sdc[i] / denom - corr;
 }
 

@@ -34,12 +34,28 @@ def main():
     ap.add_argument("--rays", type=int, default=4096)
     ap.add_argument("--mode", default="bf16")
     ap.add_argument("--bwd", action="store_true")
-    ap.add_argument("--only", default="all", choices=["all", "mlp", "composite"])
+    ap.add_argument("--only", default="all", choices=["all", "mlp", "composite", "sampler"])
     args = ap.parse_args()
     call, ptr = pkg._lib.call, pkg._lib.ptr
     cfg = pkg.NetCfg(5, 4, 2, 256, 128, 0.05)
     net = pkg.NerfMLP(cfg, mode=args.mode, seed=0)
-    for s in ((64, 128, 192) if args.only != "composite" else ()):
+    if args.only in ("all", "sampler"):
+        for n in (2048, 65536):
+            sc, nf = 64, 128
+            w = torch.rand(n, sc, device="cuda") ** 4
+            z = torch.sort(torch.rand(n, sc, device="cuda") * 2 + 0.5, -1).values.contiguous()
+            z_new = torch.empty(n, nf, device="cuda"); u = torch.empty(n, nf, device="cuda")
+            perm = torch.empty(n, nf, dtype=torch.int32, device="cuda")
+            d_z = torch.randn(n, nf, device="cuda"); d_w = torch.empty(n, sc, device="cuda")
+            f = lambda: call("nerf_sample_pdf_fwd", ptr(w), ptr(z), n, sc, nf, None, 1, 0, 0, ptr(z_new), None, ptr(perm), ptr(u))
+            med, best = timeit(f)
+            byts = n * (2 * 4 * sc + 3 * 4 * nf)          # w, z in; z_new, perm, u out
+            print(f"sample_pdf_fwd      N={n:6d} S={sc} Nf={nf}: {med * 1e3:8.1f} us  {byts / med / 1e6:8.1f} GB/s")
+            f = lambda: call("nerf_sample_pdf_bwd", ptr(w), ptr(z), ptr(u), ptr(perm), ptr(d_z), n, sc, nf, ptr(d_w))
+            med, best = timeit(f)
+            byts = n * (3 * 4 * sc + 3 * 4 * nf)
+            print(f"sample_pdf_bwd      N={n:6d} S={sc} Nf={nf}: {med * 1e3:8.1f} us  {byts / med / 1e6:8.1f} GB/s")
+    for s in ((64, 128, 192) if args.only in ("all", "mlp") else ()):
         m = args.rays * s
         xyz = torch.randn(m, 33, device="cuda")
         view = torch.randn(m, 24, device="cuda")
@@ -73,7 +89,7 @@ def main():
             flops = 2 * (512152 + 509056) * m
             print(f"mlp_bwd[{args.mode}]                    M={m:8d}: {med:8.3f} ms  {flops / med / 1e9:8.1f} TFLOP/s")
     # compositing: one 256x256 frame
-    for n, s in (((65536, 192), (65536, 64), (4096 * 16, 128)) if args.only != "mlp" else ()):
+    for n, s in (((65536, 192), (65536, 64), (4096 * 16, 128)) if args.only in ("all", "composite") else ()):
         raw = torch.randn(n, s, 4, device="cuda")
         z = torch.sort(torch.rand(n, s, device="cuda"), -1).values
         rgb = torch.empty(n, 3, device="cuda"); w = torch.empty(n, s, device="cuda"); T = torch.empty(n, s, device="cuda")
