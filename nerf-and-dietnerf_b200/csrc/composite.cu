@@ -183,8 +183,6 @@ __global__ void __launch_bounds__(256) composite_bwd_kernel(const float4* __rest
   }
   // reverse exclusive cumsum of g*w, then the per-sample gradients
   float rcarry = 0.f;
-  float dd_first_of_next = 0.f;  // unused placeholder to keep the structure explicit
-  (void)dd_first_of_next;
   float ddelta[C];
 #pragma unroll
   for (int k = C - 1; k >= 0; --k) {

@@ -751,3 +751,100 @@ def test_device_prefetcher_yields_every_batch_in_order(pkg):
     for (o, d, y), (ho, hd, hy) in zip(got, host):
         assert torch.equal(o.cpu(), ho) and torch.equal(d.cpu(), hd) and torch.equal(y.cpu(), hy)
     assert list(pkg.UtilsNeuralRadianceField.DevicePrefetcher(iter([]))) == []
+
+
+# ---- every experiment definition of the reference (config_files/*.yaml) ------------------------------------
+def _census():
+    import json
+    import os
+    from conftest import ROOT
+    with open(os.path.join(ROOT, "tests", "golden", "config_census.json")) as f:
+        return {k: v for k, v in json.load(f).items() if "unparseable" not in v}
+
+
+def test_every_reference_config_constructs_and_steps(pkg):
+    """All parseable YAMLs of the reference build a model from their own `neural_net` / `render` blocks; one train step
+    per distinct (model type, n_angles, view L, sample counts) combination is checked against the oracle's loss."""
+    census = _census()
+    assert len(census) >= 46
+    seen = {}
+    for name, cfg in sorted(census.items()):
+        net, rend = cfg["neural_net"], cfg["render"]
+        key = (net["type_of_model"], net["n_angles_for_model"], net["n_pos_enc_view_dir"],
+               rend["n_render_samples_coarse"], rend["n_render_samples_fine"])
+        cls = pkg.DietNeRFModel if net["type_of_model"] == "DietNeRF" else pkg.NeRFModel
+        mode = "bf16" if net["n_angles_for_model"] > 0 else "fp32"      # xyz-only network: fp32 path (documented gap)
+        import ctypes
+        ncfg = pkg._nerf_module.net_cfg_from_dict(net)                      # strict key look-ups, like the reference
+        assert pkg.load().nerf_param_count(ctypes.byref(ncfg)) == O.NetCfg(5, net["n_pos_enc_view_dir"],
+                                                                            net["n_angles_for_model"]).n_params
+        if key in seen:
+            continue
+        model = cls(net, rend, NEAR, FAR, mode=mode, seed=3)
+        model.compile(optimizer=pkg.Adam(cfg["training"]["optimizer_lr"]))
+        assert model.batch_size_train == net["n_rays_in_batch_train"]
+        ocfg = O.NetCfg(net["n_pos_enc_dim_xyz"], net["n_pos_enc_view_dir"], net["n_angles_for_model"],
+                        net["hidden_layer_dim"], net["last_hidden_layer_dim"], net["leaky_relu_alpha"])
+        assert model.model_coarse.n_params == ocfg.n_params
+        n, n_c, n_f = 96, rend["n_render_samples_coarse"], rend["n_render_samples_fine"]
+        pc, pf = make_params(ocfg, 1, 4.0), make_params(ocfg, 2, 4.0)
+        model.model_coarse.set_params(pc)
+        model.model_fine.set_params(pf)
+        o, d = random_rays(n, 8)
+        y = torch.rand(n, 3, generator=torch.Generator().manual_seed(2))
+        jit, u = O.stratified_jitter(3, 0, n, n_c), O.importance_uniforms(3, 0, n, n_f)
+        ref, _, _, _ = O.train_step(pc, pf, ocfg, NEAR, FAR, o, d, y, n_c, n_f, jit, u,
+                                    dietnerf=(net["type_of_model"] == "DietNeRF"), emulate_bf16=(mode == "bf16"))
+        m = model.train_step((o, d, y))
+        assert abs(float(m["loss"]) - float(ref["loss"])) < (2e-3 if mode == "bf16" else 1e-5), (name, key)
+        rgb = model.render(dev(o), dev(d))[0]
+        assert rgb.shape == (n, 3) and torch.isfinite(rgb).all()
+        seen[key] = name
+    print("distinct combinations:", seen)
+    assert len(seen) == 4          # NeRF with 0 / 1 / 2 view angles, DietNeRF with 2 (SURVEY Appendix B)
+
+
+def test_execution_run_from_a_yaml_file(pkg, tmp_path, monkeypatch):
+    """main.py's path: ExecutionRun(path_to_config_file).start() with a Blender-style dataset on disk -- YAML (Windows path
+    separators like the reference's configs), loader, save-directory allocation, DietNeRF construction incl. the
+    spherical-scene estimate, two epochs, checkpoints in the reference's layout."""
+    import json
+    import yaml
+    from PIL import Image
+    ds = tmp_path / "Assets" / "toy" / "16px"
+    ds.mkdir(parents=True)
+    rng = np.random.default_rng(0)
+    frames = []
+    for i in range(6):
+        name = f"{i:03d}.png"
+        Image.fromarray(rng.integers(0, 256, size=(16, 16, 3), dtype=np.uint8)).save(ds / name)
+        frames.append({"filename": name, "transformation_matrix": sphere_pose(1.0 * i, 0.2, 4.0).astype(float).tolist()})
+    with open(ds / "cam_data.json", "w") as f:
+        json.dump({"field_of_view": 0.69111, "frames": frames}, f)
+    cfg = {"existing_save_dir_name": None, "starting_epoch_number": -1, "dataset_type": "blender",
+           "dataset_location": None, "general_save_location": "Results",
+           "tasks_to_perform": {"start_training": True},
+           "neural_net": dict(net_config(batch_train=256, batch_render=512), type_of_model="DietNeRF"),
+           "render": dict(render_config(), near_depth_render=2.0, far_depth_render=6.0),
+           "training": {"n_epochs": 2, "optimizer_lr": 5e-4, "test_img_idx": 1, "idx_train_img_to_plot": 0},
+           "video": {}}
+    cfg["dataset_location"] = "Assets\\toy\\16px"
+    (tmp_path / "config_files").mkdir()
+    path = tmp_path / "config_files" / "16px_toy.yaml"
+    with open(path, "w") as f:
+        yaml.safe_dump(cfg, f)
+    monkeypatch.chdir(tmp_path)
+    run = pkg.ExecutionRun(str(path))
+    assert run.images.shape == (6, 16, 16, 3) and run.save_location.name == "16px_toy_save_dir_0"
+    assert (run.save_location / "16px_toy.yaml").exists()
+    pkg.DietNeRFModel.IMG_SIZE_FOR_CS_LOSS, old = 16, pkg.DietNeRFModel.IMG_SIZE_FOR_CS_LOSS
+    try:
+        run.start()
+    finally:
+        pkg.DietNeRFModel.IMG_SIZE_FOR_CS_LOSS = old
+    assert isinstance(run.model, pkg.DietNeRFModel) and run.model.is_spherical_dataset
+    assert len(run.history) == 2 and all(math.isfinite(h["loss"]) for h in run.history)
+    assert run.model.counter == 2 * ((5 * 16 * 16) // 256)
+    for e in (1, 2):
+        assert (run.save_location / "saved_weights" / f"NeRF_model_epoch_{e:03d}.h5").exists()
+        assert (run.save_location / "saved_test_train_psnrs" / f"psnrs_train_test_{e:03d}.npy").exists()
