@@ -32,17 +32,23 @@ RUN_CONFIG = {      # Results/50px_alexander_71pics_sphere_nerf_save_dir_4/50px_
 }
 
 
-def run(epochs=95, mode="bf16", seed=0, save_location=None, model_type="NeRF", stop_grad_z=False):
+def run(epochs=95, mode="bf16", seed=0, save_location=None, model_type="NeRF", stop_grad_z=False, lr=None,
+        start_epoch=-1, history=None):
     pkg = importlib.import_module("nerf-and-dietnerf_b200")
     data = np.load(os.path.join(ROOT, "tests", "golden", "alexander50_dataset.npz"))
     pin = np.load(os.path.join(ROOT, "tests", "golden", "alexander50_pin.npz"))
     config = json.loads(json.dumps(RUN_CONFIG))
     config["training"]["n_epochs"] = epochs
+    config["starting_epoch_number"] = start_epoch
+    if lr is not None:
+        config["training"]["optimizer_lr"] = lr
     config["neural_net"]["type_of_model"] = model_type
     images = data["images_u8"].astype(np.float32) / 255.0
     runner = pkg.ExecutionRun.from_arrays(config, images, data["c2w"], float(data["fov"]), float(data["near"]),
                                           float(data["far"]), mode=mode, seed=seed, save_location=save_location)
     runner.stop_grad_z = stop_grad_z
+    if history:
+        runner.history = list(history)
     t0 = time.time()
     runner._training()
     torch.cuda.synchronize()
@@ -53,6 +59,7 @@ def run(epochs=95, mode="bf16", seed=0, save_location=None, model_type="NeRF", s
         e = h["epoch"]
         if e <= len(ref_test):
             h["psnr_test_reference"], h["psnr_train_reference"] = float(ref_test[e - 1]), float(ref_train[e - 1])
+    hist.sort(key=lambda h: h["epoch"])
     train_s = sum(h["seconds"] for h in hist)
     steps = 42 * len(hist)
     return {"epochs": len(hist), "mode": mode, "model": model_type, "wall_s": wall, "train_s": train_s,
@@ -66,11 +73,22 @@ def main():
     ap.add_argument("--model", default="NeRF", choices=["NeRF", "DietNeRF"])
     ap.add_argument("--out", default=None)
     ap.add_argument("--seed", type=int, default=0)
+    ap.add_argument("--stages", default=None, help="e.g. 70:5e-4,95:4e-4 -- train to epoch 70 at 5e-4, then RESUME from the "
+                    "checkpoint (fresh Adam state, as the reference's get_nerf does) to epoch 95 at 4e-4")
     ap.add_argument("--stop-grad-z", action="store_true", help="detach the importance samples (NOT the reference's behaviour)")
     args = ap.parse_args()
     with tempfile.TemporaryDirectory() as tmp:
-        res, runner = run(args.epochs, args.mode, seed=args.seed, save_location=tmp, model_type=args.model,
-                          stop_grad_z=args.stop_grad_z)
+        if args.stages:
+            start, hist = -1, None
+            for stage in args.stages.split(","):
+                end, lr = stage.split(":")
+                res, runner = run(int(end), args.mode, seed=args.seed, save_location=tmp, model_type=args.model,
+                                  stop_grad_z=args.stop_grad_z, lr=float(lr), start_epoch=start, history=hist)
+                start, hist = int(end), res["history"]
+            args.epochs = start
+        else:
+            res, runner = run(args.epochs, args.mode, seed=args.seed, save_location=tmp, model_type=args.model,
+                              stop_grad_z=args.stop_grad_z)
         # checkpoint round trip through the Keras .h5 layout
         path = runner.model.get_nerf_model_path(tmp, args.epochs)
         before = runner.model.model_fine.params.clone()
