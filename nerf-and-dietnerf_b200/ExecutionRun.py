@@ -182,6 +182,8 @@ class ExecutionRun:
                 UtilsFiles.save_weights(model, NeRF.get_nerf_model_path(self.save_location, epoch_number))
                 UtilsFiles.save_psnr_values(psnrs_test, psnrs_train,
                                             UtilsFiles.get_psnr_save_path(self.save_location, epoch_number))
+            if torch.distributed.is_available() and torch.distributed.is_initialized():
+                torch.distributed.barrier()          # the checkpoint is complete before any rank can resume from it
             if self.is_main:
                 print(f"Done epoch {epoch_number} in {seconds:.2f} sec. ({seconds / max(n_batches, 1) * 1e3:.2f} ms / step) "
                       f"Test PSNR: {p_test:.3f}")

@@ -67,6 +67,11 @@ def run(epochs=95, mode="bf16", seed=0, save_location=None, model_type="NeRF", s
 
 
 def main():
+    if "RANK" in os.environ and int(os.environ.get("WORLD_SIZE", "1")) > 1:      # torchrun: shard every batch over the ranks
+        import torch.distributed as dist
+        torch.cuda.set_device(int(os.environ["LOCAL_RANK"]))
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", int(os.environ["LOCAL_RANK"])))
     ap = argparse.ArgumentParser()
     ap.add_argument("--epochs", type=int, default=95)
     ap.add_argument("--mode", default="bf16")
@@ -77,7 +82,13 @@ def main():
                     "checkpoint (fresh Adam state, as the reference's get_nerf does) to epoch 95 at 4e-4")
     ap.add_argument("--stop-grad-z", action="store_true", help="detach the importance samples (NOT the reference's behaviour)")
     args = ap.parse_args()
+    rank0 = int(os.environ.get("RANK", "0")) == 0
     with tempfile.TemporaryDirectory() as tmp:
+        if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+            import torch.distributed as dist
+            box = [tmp]
+            dist.broadcast_object_list(box, src=0)       # every rank resumes from rank 0's checkpoints
+            tmp = box[0]
         if args.stages:
             start, hist = -1, None
             for stage in args.stages.split(","):
@@ -95,6 +106,16 @@ def main():
         runner.model.load_weights(path)
         assert torch.equal(before, runner.model.model_fine.params), "checkpoint round trip changed the weights"
         res["checkpoint_bytes"] = os.path.getsize(path)
+        if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+            import torch.distributed as dist
+            p = runner.model.model_fine.params
+            both = [torch.empty_like(p) for _ in range(dist.get_world_size())]
+            dist.all_gather(both, p)
+            assert all(torch.equal(both[0], t) for t in both), "replicas diverged"
+            res["world_size"] = dist.get_world_size()
+            dist.barrier()
+    if not rank0:
+        return
     print(f"{'epoch':>5} {'test':>7} {'ref':>7} {'train':>7} {'ref':>7}")
     for h in res["history"]:
         if h["epoch"] in (1, 2, 5) or h["epoch"] % 10 == 0 or h["epoch"] == args.epochs:
