@@ -321,6 +321,9 @@ class NeRF:
                 rgbs.append(rgb)
                 depths.append(depth)
                 accs.append(acc)
+        if not rgbs:        # an empty ray range (a rank whose shard of the frame is empty)
+            f = lambda *shape: torch.empty(shape, dtype=torch.float32, device=self.device)
+            return f(0, 3), f(0), f(0)
         return torch.cat(rgbs), torch.cat(depths), torch.cat(accs)
 
     # ---- training ----------------------------------------------------------------------------------------------------

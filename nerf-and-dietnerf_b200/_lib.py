@@ -91,11 +91,21 @@ def load():
     return lib
 
 
+_empty_anchor = {}
+
+
 def ptr(t):
-    """Device pointer of a contiguous tensor (None -> NULL)."""
+    """Device pointer of a contiguous tensor (None -> NULL).  An EMPTY tensor has no storage (data_ptr() == 0), which the
+    C side would take for a missing argument: it gets the address of a small per-device anchor buffer instead, and the
+    entry points return early on a zero count."""
     if t is None:
         return None
     assert t.is_contiguous(), "tensor must be contiguous"
+    if t.numel() == 0 and t.is_cuda:
+        key = t.device.index
+        if key not in _empty_anchor:
+            _empty_anchor[key] = torch.zeros(64, dtype=torch.uint8, device=t.device)
+        return _empty_anchor[key].data_ptr()
     return t.data_ptr()
 
 

@@ -864,3 +864,23 @@ def test_execution_run_from_a_yaml_file(pkg, tmp_path, monkeypatch):
     for e in (1, 2):
         assert (run.save_location / "saved_weights" / f"NeRF_model_epoch_{e:03d}.h5").exists()
         assert (run.save_location / "saved_test_train_psnrs" / f"psnrs_train_test_{e:03d}.npy").exists()
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+def test_degenerate_batches(pkg, mode):
+    """Empty and single-ray batches (the ragged tail of split_to_batches can be any size; a shard can be empty)."""
+    model, ocfg, pc, pf = _model(pkg, mode, sigma_gain=4.0)
+    model.compile(optimizer=pkg.Adam(5e-4))
+    o, d = random_rays(1, 1)
+    out = model.render(dev(o), dev(d), seed=3, step=0)
+    jit, u = O.stratified_jitter(3, 0, 1, 64), O.importance_uniforms(3, 0, 1, 128)
+    ref = O.render(pc, pf, ocfg, NEAR, FAR, o, d, 64, 128, jit, u)
+    assert out[0].shape == (1, 3) and out[5].shape == (1, 192)
+    assert (out[0].cpu() - ref[0]).abs().max().item() < (1e-5 if mode == "fp32" else 5e-3)
+    m = model.train_step((o, d, torch.rand(1, 3)))
+    assert math.isfinite(float(m["loss"]))
+    empty = torch.empty(0, 4, device="cuda")
+    out0 = model.render(empty, empty, seed=3, step=0)
+    assert out0[0].shape == (0, 3) and out0[1].shape == (0, 192)
+    rgb, depth, acc = model.render_image_lean(sphere_pose(0.1, 0.1), 0.6, 4, 4, ray_begin=5, n_rays=0)
+    assert rgb.shape == (0, 3)
