@@ -85,8 +85,10 @@ sample_pdf_fwd_kernel(const float* __restrict__ weights, const float* __restrict
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t ray = blockIdx.x * (int64_t)kWarpsPerBlock + warp;
   if (ray >= n_rays) return;
-  float* base = smem + (size_t)warp * (3 * S + Nf);
-  float *sw = base, *scdf = base + S, *sz = base + 2 * S, *szs = base + 3 * S;
+  // per-warp region [w | cdf | z | new samples]; the last block starts on a 16-byte boundary (float4 loads in the sort)
+  const int s3 = (3 * S + 3) & ~3, nf4 = (Nf + 3) & ~3;
+  float* base = smem + (size_t)warp * (s3 + nf4);
+  float *sw = base, *scdf = base + S, *sz = base + 2 * S, *szs = base + s3;
   build_cdf(weights + ray * S, z + ray * S, S, lane, sw, scdf, sz);
 
   const int n_blocks = (Nf + 3) / 4;
@@ -112,16 +114,35 @@ sample_pdf_fwd_kernel(const float* __restrict__ weights, const float* __restrict
     }
   }
   __syncwarp();
-  // stable rank sort (tf.sort ascending; ties keep draw order like the oracle's stable sort)
-  for (int j = lane; j < Nf; j += 32) {
-    float v = szs[j];
+  // Stable rank sort (tf.sort ascending; ties keep draw order like the oracle's stable sort):
+  //   rank_j = #{k < j : z_k <= z_j} + #{k > j : z_k < z_j}.
+  // The kernel is issue-bound on this O(Nf^2) loop, so it is arranged to cost one compare + one add per pair: in pass m
+  // the warp ranks j = 32 m + lane, so every k below 32 m is "before" and every k from 32 (m + 1) on is "after" for ALL
+  // lanes (warp-uniform bounds, 16-byte shared-memory loads); only the 32 k of the diagonal block need the index test.
+  for (int j0 = 0; j0 < Nf; j0 += 32) {
+    const int j = j0 + lane;
+    const float v = j < Nf ? szs[j] : 0.f;
     int rank = 0;
-    for (int k = 0; k < Nf; ++k) {
-      float o = szs[k];
+    int k = 0;
+    for (; k + 4 <= j0; k += 4) {                       // k < j for every lane
+      const float4 o = *reinterpret_cast<const float4*>(szs + k);
+      rank += (o.x <= v) + (o.y <= v) + (o.z <= v) + (o.w <= v);
+    }
+    const int diag_end = min(Nf, j0 + 32);
+    for (; k < diag_end; ++k) {                         // diagonal block (j0 is a multiple of 4: k == j0 here)
+      const float o = szs[k];
       rank += (o < v) || (o == v && k < j);
     }
-    z_new[ray * Nf + rank] = v;
-    if (perm_out) perm_out[ray * Nf + rank] = j;
+    for (; k < Nf && (k & 3); ++k) rank += szs[k] < v;  // (diag_end is a multiple of 4 unless it is Nf)
+    for (; k + 4 <= Nf; k += 4) {                       // k > j for every lane
+      const float4 o = *reinterpret_cast<const float4*>(szs + k);
+      rank += (o.x < v) + (o.y < v) + (o.z < v) + (o.w < v);
+    }
+    for (; k < Nf; ++k) rank += szs[k] < v;
+    if (j < Nf) {
+      z_new[ray * Nf + rank] = v;
+      if (perm_out) perm_out[ray * Nf + rank] = j;
+    }
   }
 }
 
@@ -244,7 +265,7 @@ int nerf_sample_pdf_fwd(const float* weights, const float* z, int64_t n_rays, in
   NERF_CHECK_ARG(n_rays >= 0 && n_samples >= 2 && n_samples <= 1024 && n_new > 0 && n_new <= 1024,
                  "need 2 <= n_samples <= 1024 and 1 <= n_new <= 1024");
   if (n_rays == 0) return NERF_OK;
-  size_t smem = (size_t)kWarpsPerBlock * (3 * n_samples + n_new) * sizeof(float);
+  size_t smem = (size_t)kWarpsPerBlock * (((3 * n_samples + 3) & ~3) + ((n_new + 3) & ~3)) * sizeof(float);
   if (smem > 48 * 1024)
     NERF_CUDA(cudaFuncSetAttribute(sample_pdf_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   sample_pdf_fwd_kernel<<<(unsigned)ceil_div(n_rays, kWarpsPerBlock), kWarpsPerBlock * 32, smem, (cudaStream_t)stream>>>(

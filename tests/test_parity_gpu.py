@@ -194,7 +194,8 @@ def _weights_and_z(n, s, seed):
     return w.contiguous(), z
 
 
-@pytest.mark.parametrize("n,s,nf", [(2048, 64, 128), (257, 64, 64), (100, 55, 110), (10, 2, 5), (64, 192, 128)])
+@pytest.mark.parametrize("n,s,nf", [(2048, 64, 128), (257, 64, 64), (100, 55, 110), (10, 2, 5), (64, 192, 128), (3001, 64, 128),
+                                    (2500, 33, 7)])
 def test_sample_pdf_bit_exact(pkg, n, s, nf):
     w, z = _weights_and_z(n, s, nf)
     u = O.importance_uniforms(3, 4, n, nf, ray_offset=17)
