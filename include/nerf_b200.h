@@ -149,6 +149,17 @@ int nerf_composite_fwd(const float* raw4, const float* z, int64_t n_rays, int32_
 int nerf_composite_bwd(const float* raw4, const float* z, const float* d_rgb, const float* d_weights_or_null,
                        int64_t n_rays, int32_t n_samples, float* d_raw4, float* d_z_or_null, void* stream);
 
+/* ray_marching + keras MeanSquaredError in one launch (src/NeRF.py:150-151): rgb (N,3), weights (N,S) as above, plus
+ * d_rgb = loss_weight * 2 (rgb-target) / (3*n_total_rays) and sq_err_sum += sum((rgb-target)^2) (caller zeroes). */
+int nerf_composite_mse_fwd(const float* raw4, const float* z, const float* target, int64_t n_rays, int32_t n_samples,
+                           int64_t n_total_rays, float loss_weight, float* rgb, float* weights, float* sq_err_sum,
+                           float* d_rgb, void* stream);
+/* ray_marching + MeanSquaredError + their gradient in one launch (the fine network's part of NeRF.train_step,
+ * src/NeRF.py:156-157 and what the tape returns for it): d_raw4 (N,S,4), d_z (N,S) when non-null, rgb when non-null. */
+int nerf_composite_mse_fwd_bwd(const float* raw4, const float* z, const float* target, int64_t n_rays, int32_t n_samples,
+                               int64_t n_total_rays, float loss_weight, float* rgb_or_null, float* sq_err_sum,
+                               float* d_raw4, float* d_z_or_null, void* stream);
+
 /* ---- hierarchical sampling (get_z_vals_from_prob_dist_func, src/UtilsCV.py:502-539) ------------------- */
 /* weights,z: (N,S); z_new: (N,Nf) sorted.  u_or_null: (N,Nf) uniforms replacing the Philox stream.
  * Optional outputs: idx (N,Nf) int32 searchsorted results in DRAW order, perm (N,Nf) int32 sort

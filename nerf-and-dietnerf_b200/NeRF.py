@@ -377,23 +377,19 @@ class NeRF:
         call("nerf_stratified_z", self.near_boundary, self.far_boundary, n, sc, ptr(jitter), seed, step, ray_offset,
              ptr(w.z_c))
         self._mlp_fwd_train(mc, o, d, w.z_c, n, sc, w.xyz_c, w.view_c, w.raw_c, w.saved_c, w.ws_fwd)
-        call("nerf_composite_fwd", ptr(w.raw_c), ptr(w.z_c), n, sc, ptr(w.rgb_c), ptr(w.w_c), None, None, None, None,
-             None)
-        call("nerf_mse_fwd_bwd", ptr(w.rgb_c), ptr(y), n, n_total, self.COARSE_LOSS_WEIGHT, ptr(sums[0:1]),
-             ptr(w.d_rgb_c))
+        # ray_marching + MSE (+ its gradient) in one launch each: the loss is formed where the ray's colour is reduced
+        call("nerf_composite_mse_fwd", ptr(w.raw_c), ptr(w.z_c), ptr(y), n, sc, n_total, self.COARSE_LOSS_WEIGHT,
+             ptr(w.rgb_c), ptr(w.w_c), ptr(sums[0:1]), ptr(w.d_rgb_c))
         d_w_c = None
         if mf is not None:
             # fine forward on the n_f importance samples only (src/NeRF.py:155-156)
             call("nerf_sample_pdf_fwd", ptr(w.w_c), ptr(w.z_c), n, sc, sf, ptr(u), seed, step, ray_offset, ptr(w.z_f),
                  None, ptr(w.perm), ptr(w.u))
             self._mlp_fwd_train(mf, o, d, w.z_f, n, sf, w.xyz_f, w.view_f, w.raw_f, w.saved_f, w.ws_fwd)
-            call("nerf_composite_fwd", ptr(w.raw_f), ptr(w.z_f), n, sf, ptr(w.rgb_f), None, None, None, None, None,
-                 None)
-            call("nerf_mse_fwd_bwd", ptr(w.rgb_f), ptr(y), n, n_total, 1.0, ptr(sums[1:2]), ptr(w.d_rgb_f))
-            # fine backward
+            # fine compositing, loss and their backward
             through_z = not self.stop_grad_z
-            call("nerf_composite_bwd", ptr(w.raw_f), ptr(w.z_f), ptr(w.d_rgb_f), None, n, sf, ptr(w.d_raw_f),
-                 ptr(w.d_z_f) if through_z else None)
+            call("nerf_composite_mse_fwd_bwd", ptr(w.raw_f), ptr(w.z_f), ptr(y), n, sf, n_total, 1.0, ptr(w.rgb_f),
+                 ptr(sums[1:2]), ptr(w.d_raw_f), ptr(w.d_z_f) if through_z else None)
             side = self._mlp_bwd(mf, w.xyz_f, w.view_f, w.saved_f, w.d_raw_f, n * sf, g_f,
                                  w.d_xyz_f if through_z else None, w.ws_bwd, side_stream=self._side_stream())
             if self.world_size > 1 and self._overlap_allreduce:

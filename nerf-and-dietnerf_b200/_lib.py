@@ -59,6 +59,8 @@ SIGNATURES = {
     "nerf_pack_weights_fp16": (c_int32, [_CFG, _P, _P, _P]),
     "nerf_composite_fwd": (c_int32, [_P, _P, c_int64, c_int32, _P, _P, _P, _P, _P, _P, _P, _P]),
     "nerf_composite_bwd": (c_int32, [_P, _P, _P, _P, c_int64, c_int32, _P, _P, _P]),
+    "nerf_composite_mse_fwd": (c_int32, [_P, _P, _P, c_int64, c_int32, c_int64, c_float, _P, _P, _P, _P, _P]),
+    "nerf_composite_mse_fwd_bwd": (c_int32, [_P, _P, _P, c_int64, c_int32, c_int64, c_float, _P, _P, _P, _P, _P]),
     "nerf_sample_pdf_fwd": (c_int32, [_P, _P, c_int64, c_int32, c_int32, _P, c_uint64, c_uint32, c_uint64, _P, _P, _P,
                                       _P, _P]),
     "nerf_sample_pdf_bwd": (c_int32, [_P, _P, _P, _P, _P, c_int64, c_int32, c_int32, _P, _P]),

@@ -54,15 +54,40 @@ __device__ __forceinline__ SampleFwd sample_fwd(float raw_sigma, float z_cur, fl
   return r;
 }
 
-template <int C>
+// Fused loss (kLoss): keras MeanSquaredError against `target` right where the ray's colour is reduced
+// (src/NeRF.py:151,157): d_rgb = grad_scale * (rgb - target), sq_err_sum += sum (rgb - target)^2 (one atomic per block).
+struct LossArgs {
+  const float* target;   // (N,3)
+  float grad_scale;      // 2 * loss_weight / (3 * n_total_rays)
+  float* sq_err_sum;     // scalar accumulator (caller zeroes)
+  float* d_rgb;          // (N,3) out, may be null
+};
+
+// block-wide sum of one value per warp (lane 0 holds it) -> one atomicAdd; every thread of the block must call it
+__device__ __forceinline__ void block_accumulate(float warp_value, int lane, float* target) {
+  __shared__ float part[8];
+  const int warp = threadIdx.x >> 5;
+  if (lane == 0) part[warp] = warp_value;
+  __syncthreads();
+  if (threadIdx.x == 0 && target) {
+    float sum = 0.f;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) sum += part[w];
+    atomicAdd(target, sum);
+  }
+}
+
+template <int C, bool kLoss>
 __global__ void __launch_bounds__(256) composite_fwd_kernel(const float4* __restrict__ raw4, const float* __restrict__ z,
                                                             int64_t n_rays, int S, float* __restrict__ rgb,
                                                             float* __restrict__ weights, float* __restrict__ cumprod,
                                                             float* __restrict__ alpha_out, float* __restrict__ rgb_s,
-                                                            float* __restrict__ depth, float* __restrict__ acc) {
+                                                            float* __restrict__ depth, float* __restrict__ acc,
+                                                            LossArgs loss) {
   const int lane = threadIdx.x & 31;
-  const int64_t ray = blockIdx.x * (int64_t)(blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (ray >= n_rays) return;
+  int64_t ray = blockIdx.x * (int64_t)(blockDim.x >> 5) + (threadIdx.x >> 5);
+  const bool active = ray < n_rays;
+  if (!kLoss && !active) return;
+  if (!active) ray = n_rays - 1;           // kLoss: keep the warp for the block-wide reduction; it stores nothing
   const float4* raw_r = raw4 + ray * S;
   const float* z_r = z + ray * S;
 
@@ -97,7 +122,7 @@ __global__ void __launch_bounds__(256) composite_fwd_kernel(const float4* __rest
     if (lane == 0) excl = 1.0f;
     float T = carry * excl;
     carry *= __shfl_sync(kFull, incl, 31);
-    if (valid) {
+    if (valid && active) {
       float w = f.alpha * T;
       float cr = sigmoidf_(raw[k].x), cg = sigmoidf_(raw[k].y), cb = sigmoidf_(raw[k].z);
       r_acc += w * cr;
@@ -121,7 +146,7 @@ __global__ void __launch_bounds__(256) composite_fwd_kernel(const float4* __rest
   b_acc = warp_sum(b_acc);
   if (depth) d_acc = warp_sum(d_acc);
   if (acc) a_acc = warp_sum(a_acc);
-  if (lane == 0) {
+  if (lane == 0 && active) {
     if (rgb) {
       rgb[ray * 3 + 0] = r_acc;
       rgb[ray * 3 + 1] = g_acc;
@@ -130,19 +155,39 @@ __global__ void __launch_bounds__(256) composite_fwd_kernel(const float4* __rest
     if (depth) depth[ray] = d_acc;
     if (acc) acc[ray] = a_acc;
   }
+  if (kLoss) {
+    float e = 0.f;
+    if (lane == 0 && active) {
+      const float er = r_acc - loss.target[ray * 3 + 0], eg = g_acc - loss.target[ray * 3 + 1],
+                  eb = b_acc - loss.target[ray * 3 + 2];
+      e = er * er + eg * eg + eb * eb;
+      if (loss.d_rgb) {
+        loss.d_rgb[ray * 3 + 0] = loss.grad_scale * er;
+        loss.d_rgb[ray * 3 + 1] = loss.grad_scale * eg;
+        loss.d_rgb[ray * 3 + 2] = loss.grad_scale * eb;
+      }
+    }
+    block_accumulate(e, lane, loss.sq_err_sum);
+  }
 }
 
-template <int C>
+// kLoss: the ray's colour, its MSE against `target` and d_rgb are computed HERE from the forward scan the backward
+// repeats anyway, so composite_fwd + mse + composite_bwd of the fine network are one launch (rgb_out optional).
+template <int C, bool kLoss>
 __global__ void __launch_bounds__(256) composite_bwd_kernel(const float4* __restrict__ raw4, const float* __restrict__ z,
                                                             const float* __restrict__ d_rgb,
                                                             const float* __restrict__ d_weights, int64_t n_rays, int S,
-                                                            float4* __restrict__ d_raw4, float* __restrict__ d_z) {
+                                                            float4* __restrict__ d_raw4, float* __restrict__ d_z,
+                                                            LossArgs loss, float* __restrict__ rgb_out) {
   const int lane = threadIdx.x & 31;
-  const int64_t ray = blockIdx.x * (int64_t)(blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (ray >= n_rays) return;
+  int64_t ray = blockIdx.x * (int64_t)(blockDim.x >> 5) + (threadIdx.x >> 5);
+  const bool active = ray < n_rays;
+  if (!kLoss && !active) return;
+  if (!active) ray = n_rays - 1;
   const float4* raw_r = raw4 + ray * S;
   const float* z_r = z + ray * S;
-  const float dr = __ldg(d_rgb + ray * 3 + 0), dg = __ldg(d_rgb + ray * 3 + 1), db = __ldg(d_rgb + ray * 3 + 2);
+  float dr = 0.f, dg = 0.f, db = 0.f;
+  if (!kLoss) { dr = __ldg(d_rgb + ray * 3 + 0); dg = __ldg(d_rgb + ray * 3 + 1); db = __ldg(d_rgb + ray * 3 + 2); }
 
   float4 raw[C];
   float zc[C], T[C], gw[C], g[C], col_r[C], col_g[C], col_b[C];
@@ -158,8 +203,9 @@ __global__ void __launch_bounds__(256) composite_bwd_kernel(const float4* __rest
       zc[k] = 0.f;
     }
   }
-  // forward scan: T, w, g = dL/dw
+  // forward scan: T, colours (and, fused, the ray's colour -> loss -> d_rgb)
   float carry = 1.0f;
+  float r_acc = 0.f, g_acc = 0.f, b_acc = 0.f;
 #pragma unroll
   for (int k = 0; k < C; ++k) {
     int s = k * 32 + lane;
@@ -176,7 +222,34 @@ __global__ void __launch_bounds__(256) composite_bwd_kernel(const float4* __rest
     carry *= __shfl_sync(kFull, incl, 31);
     float cr = sigmoidf_(raw[k].x), cg = sigmoidf_(raw[k].y), cb = sigmoidf_(raw[k].z);
     col_r[k] = cr; col_g[k] = cg; col_b[k] = cb;
-    float gi = dr * cr + dg * cg + db * cb;
+    if (kLoss && valid) {
+      const float w = f[k].alpha * T[k];
+      r_acc += w * cr;
+      g_acc += w * cg;
+      b_acc += w * cb;
+    }
+  }
+  if (kLoss) {
+    r_acc = warp_sum(r_acc);
+    g_acc = warp_sum(g_acc);
+    b_acc = warp_sum(b_acc);
+    const float er = r_acc - __ldg(loss.target + ray * 3 + 0), eg = g_acc - __ldg(loss.target + ray * 3 + 1),
+                eb = b_acc - __ldg(loss.target + ray * 3 + 2);
+    dr = loss.grad_scale * er;
+    dg = loss.grad_scale * eg;
+    db = loss.grad_scale * eb;
+    if (lane == 0 && active) {
+      if (rgb_out) { rgb_out[ray * 3 + 0] = r_acc; rgb_out[ray * 3 + 1] = g_acc; rgb_out[ray * 3 + 2] = b_acc; }
+      if (loss.d_rgb) { loss.d_rgb[ray * 3 + 0] = dr; loss.d_rgb[ray * 3 + 1] = dg; loss.d_rgb[ray * 3 + 2] = db; }
+    }
+    block_accumulate((lane == 0 && active) ? er * er + eg * eg + eb * eb : 0.f, lane, loss.sq_err_sum);
+  }
+  // g = dL/dw per sample
+#pragma unroll
+  for (int k = 0; k < C; ++k) {
+    int s = k * 32 + lane;
+    bool valid = s < S;
+    float gi = dr * col_r[k] + dg * col_g[k] + db * col_b[k];
     if (d_weights && valid) gi += __ldcs(d_weights + ray * S + s);
     g[k] = valid ? gi : 0.f;
     gw[k] = valid ? gi * f[k].alpha * T[k] : 0.f;
@@ -199,7 +272,7 @@ __global__ void __launch_bounds__(256) composite_bwd_kernel(const float4* __rest
     float dsig = dalpha * x * f[k].delta;
     float ddel = (s == S - 1) ? 0.f : dalpha * x * f[k].sigma;
     ddelta[k] = valid ? ddel : 0.f;
-    if (valid) {
+    if (valid && active) {
       float w = f[k].alpha * T[k];
       float cr = col_r[k], cg = col_g[k], cb = col_b[k];
       float4 o;
@@ -218,25 +291,35 @@ __global__ void __launch_bounds__(256) composite_bwd_kernel(const float4* __rest
       float prev = __shfl_up_sync(kFull, ddelta[k], 1);
       float prev_blk = __shfl_sync(kFull, ddelta[(k > 0) ? k - 1 : 0], 31);
       if (lane == 0) prev = (k > 0) ? prev_blk : 0.f;
-      if (s < S) __stcs(d_z + ray * S + s, prev - ddelta[k]);
+      if (s < S && active) __stcs(d_z + ray * S + s, prev - ddelta[k]);
     }
   }
 }
 
 template <int C>
 static int launch_fwd(const float* raw4, const float* z, int64_t n, int S, float* rgb, float* w, float* T, float* a,
-                      float* rgb_s, float* depth, float* acc, cudaStream_t st) {
+                      float* rgb_s, float* depth, float* acc, const LossArgs* loss, cudaStream_t st) {
   const int warps = 8;
-  composite_fwd_kernel<C><<<(unsigned)ceil_div(n, warps), warps * 32, 0, st>>>((const float4*)raw4, z, n, S, rgb, w, T, a,
-                                                                              rgb_s, depth, acc);
+  const unsigned grid = (unsigned)ceil_div(n, warps);
+  if (loss)
+    composite_fwd_kernel<C, true><<<grid, warps * 32, 0, st>>>((const float4*)raw4, z, n, S, rgb, w, T, a, rgb_s, depth,
+                                                               acc, *loss);
+  else
+    composite_fwd_kernel<C, false><<<grid, warps * 32, 0, st>>>((const float4*)raw4, z, n, S, rgb, w, T, a, rgb_s, depth,
+                                                                acc, LossArgs{});
   return 0;
 }
 template <int C>
 static int launch_bwd(const float* raw4, const float* z, const float* d_rgb, const float* d_w, int64_t n, int S,
-                      float* d_raw4, float* d_z, cudaStream_t st) {
+                      float* d_raw4, float* d_z, const LossArgs* loss, float* rgb_out, cudaStream_t st) {
   const int warps = 8;
-  composite_bwd_kernel<C><<<(unsigned)ceil_div(n, warps), warps * 32, 0, st>>>((const float4*)raw4, z, d_rgb, d_w, n, S,
-                                                                              (float4*)d_raw4, d_z);
+  const unsigned grid = (unsigned)ceil_div(n, warps);
+  if (loss)
+    composite_bwd_kernel<C, true><<<grid, warps * 32, 0, st>>>((const float4*)raw4, z, nullptr, d_w, n, S, (float4*)d_raw4,
+                                                               d_z, *loss, rgb_out);
+  else
+    composite_bwd_kernel<C, false><<<grid, warps * 32, 0, st>>>((const float4*)raw4, z, d_rgb, d_w, n, S, (float4*)d_raw4,
+                                                                d_z, LossArgs{}, nullptr);
   return 0;
 }
 
@@ -264,7 +347,7 @@ int nerf_composite_fwd(const float* raw4, const float* z, int64_t n_rays, int32_
   NERF_CHECK_ARG(n_rays >= 0 && n_samples > 0 && n_samples <= 1024, "n_samples must be in [1,1024]");
   if (n_rays == 0) return NERF_OK;
   cudaStream_t st = (cudaStream_t)stream;
-#define CALL(C) launch_fwd<C>(raw4, z, n_rays, n_samples, rgb, weights, cumprod, alpha, rgb_s, depth, acc, st)
+#define CALL(C) launch_fwd<C>(raw4, z, n_rays, n_samples, rgb, weights, cumprod, alpha, rgb_s, depth, acc, nullptr, st)
   DISPATCH_C(n_samples, CALL);
 #undef CALL
   NERF_CHECK_LAUNCH();
@@ -277,7 +360,37 @@ int nerf_composite_bwd(const float* raw4, const float* z, const float* d_rgb, co
   NERF_CHECK_ARG(n_rays >= 0 && n_samples > 0 && n_samples <= 1024, "n_samples must be in [1,1024]");
   if (n_rays == 0) return NERF_OK;
   cudaStream_t st = (cudaStream_t)stream;
-#define CALL(C) launch_bwd<C>(raw4, z, d_rgb, d_weights_or_null, n_rays, n_samples, d_raw4, d_z_or_null, st)
+#define CALL(C) launch_bwd<C>(raw4, z, d_rgb, d_weights_or_null, n_rays, n_samples, d_raw4, d_z_or_null, nullptr, nullptr, st)
+  DISPATCH_C(n_samples, CALL);
+#undef CALL
+  NERF_CHECK_LAUNCH();
+  return NERF_OK;
+}
+
+int nerf_composite_mse_fwd(const float* raw4, const float* z, const float* target, int64_t n_rays, int32_t n_samples,
+                           int64_t n_total_rays, float loss_weight, float* rgb, float* weights, float* sq_err_sum,
+                           float* d_rgb, void* stream) {
+  NERF_CHECK_ARG(raw4 && z && target && sq_err_sum, "null pointer");
+  NERF_CHECK_ARG(n_rays >= 0 && n_total_rays > 0 && n_samples > 0 && n_samples <= 1024, "bad shape");
+  if (n_rays == 0) return NERF_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  LossArgs loss{target, (float)(2.0 * (double)loss_weight / (3.0 * (double)n_total_rays)), sq_err_sum, d_rgb};
+#define CALL(C) launch_fwd<C>(raw4, z, n_rays, n_samples, rgb, weights, nullptr, nullptr, nullptr, nullptr, nullptr, &loss, st)
+  DISPATCH_C(n_samples, CALL);
+#undef CALL
+  NERF_CHECK_LAUNCH();
+  return NERF_OK;
+}
+
+int nerf_composite_mse_fwd_bwd(const float* raw4, const float* z, const float* target, int64_t n_rays, int32_t n_samples,
+                               int64_t n_total_rays, float loss_weight, float* rgb_or_null, float* sq_err_sum,
+                               float* d_raw4, float* d_z_or_null, void* stream) {
+  NERF_CHECK_ARG(raw4 && z && target && sq_err_sum && d_raw4, "null pointer");
+  NERF_CHECK_ARG(n_rays >= 0 && n_total_rays > 0 && n_samples > 0 && n_samples <= 1024, "bad shape");
+  if (n_rays == 0) return NERF_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  LossArgs loss{target, (float)(2.0 * (double)loss_weight / (3.0 * (double)n_total_rays)), sq_err_sum, nullptr};
+#define CALL(C) launch_bwd<C>(raw4, z, nullptr, nullptr, n_rays, n_samples, d_raw4, d_z_or_null, &loss, rgb_or_null, st)
   DISPATCH_C(n_samples, CALL);
 #undef CALL
   NERF_CHECK_LAUNCH();

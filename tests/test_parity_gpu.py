@@ -885,3 +885,42 @@ def test_degenerate_batches(pkg, mode):
     assert out0[0].shape == (0, 3) and out0[1].shape == (0, 192)
     rgb, depth, acc = model.render_image_lean(sphere_pose(0.1, 0.1), 0.6, 4, 4, ray_begin=5, n_rays=0)
     assert rgb.shape == (0, 3)
+
+
+@pytest.mark.parametrize("n,s", [(2048, 64), (1001, 128), (77, 110), (9, 200)])
+def test_composite_with_fused_loss_matches_the_separate_kernels(pkg, n, s):
+    """nerf_composite_mse_fwd / _fwd_bwd (ray_marching + MeanSquaredError [+ gradient] in one launch, the train step's
+    path) against the oracle AND bit-for-bit against composite_fwd -> mse -> composite_bwd."""
+    call = pkg._lib.call
+    g = torch.Generator().manual_seed(n + s)
+    raw = (torch.randn(n, s, 4, generator=g) * 2).cuda()
+    raw[..., 3] *= 3
+    z = torch.sort(torch.rand(n, s, generator=g) * 2 + 0.5, -1).values.cuda()
+    y = torch.rand(n, 3, generator=g).cuda()
+    f = lambda *shape: torch.empty(shape, device="cuda")
+    n_total, wgt = 3 * n, 2.0
+    # separate kernels
+    rgb0, w0, d_rgb0, sum0 = f(n, 3), f(n, s), f(n, 3), torch.zeros(1, device="cuda")
+    call("nerf_composite_fwd", raw.data_ptr(), z.data_ptr(), n, s, rgb0.data_ptr(), w0.data_ptr(), None, None, None, None, None)
+    call("nerf_mse_fwd_bwd", rgb0.data_ptr(), y.data_ptr(), n, n_total, wgt, sum0.data_ptr(), d_rgb0.data_ptr())
+    d_raw0, d_z0 = f(n, s, 4), f(n, s)
+    call("nerf_composite_bwd", raw.data_ptr(), z.data_ptr(), d_rgb0.data_ptr(), None, n, s, d_raw0.data_ptr(), d_z0.data_ptr())
+    # fused forward + loss
+    rgb1, w1, d_rgb1, sum1 = f(n, 3), f(n, s), f(n, 3), torch.zeros(1, device="cuda")
+    call("nerf_composite_mse_fwd", raw.data_ptr(), z.data_ptr(), y.data_ptr(), n, s, n_total, wgt, rgb1.data_ptr(),
+         w1.data_ptr(), sum1.data_ptr(), d_rgb1.data_ptr())
+    assert torch.equal(rgb1, rgb0) and torch.equal(w1, w0) and torch.equal(d_rgb1, d_rgb0)
+    assert abs(sum1.item() - sum0.item()) < 1e-5 * max(1.0, sum0.item())
+    # fused forward + loss + backward
+    rgb2, sum2, d_raw2, d_z2 = f(n, 3), torch.zeros(1, device="cuda"), f(n, s, 4), f(n, s)
+    call("nerf_composite_mse_fwd_bwd", raw.data_ptr(), z.data_ptr(), y.data_ptr(), n, s, n_total, wgt, rgb2.data_ptr(),
+         sum2.data_ptr(), d_raw2.data_ptr(), d_z2.data_ptr())
+    assert torch.equal(rgb2, rgb0) and torch.equal(d_raw2, d_raw0) and torch.equal(d_z2, d_z0)
+    assert abs(sum2.item() - sum0.item()) < 1e-5 * max(1.0, sum0.item())
+    # oracle: loss value and gradient w.r.t. raw
+    raw_o = raw.cpu().clone().requires_grad_(True)
+    rgb_o = O.ray_marching(raw_o, z.cpu())[0]
+    loss = wgt * ((rgb_o - y.cpu()) ** 2).sum() / (3 * n_total)
+    loss.backward()
+    assert abs(sum2.item() - ((rgb_o.detach() - y.cpu()) ** 2).sum().item()) < 1e-3
+    assert (d_raw2.cpu() - raw_o.grad).abs().max().item() < 2e-6 * max(1.0, raw_o.grad.abs().max().item() * 1e3)
