@@ -192,7 +192,11 @@ def main():
     torch.cuda.set_device(local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        os.environ["NCCL_DEBUG"] = "WARN"      # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
+        # rank 0 must print ONE JSON line on stdout, and NCCL writes there too: at NCCL_DEBUG=VERSION / WARN its version
+        # banner is a plain printf (drop those levels), at INFO and above the log goes where NCCL_DEBUG_FILE points
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "WARN"):
+            del os.environ["NCCL_DEBUG"]
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     pkg = importlib.import_module("nerf-and-dietnerf_b200")
     pkg.load()
