@@ -13,6 +13,7 @@ per step) and rank 0 writes the checkpoints.
 import os
 import re
 import shutil
+import threading
 import time
 from pathlib import Path, PureWindowsPath
 
@@ -137,15 +138,23 @@ class ExecutionRun:
             self._epoch_number = self.training_config[N_EPOCHS]
 
     def fit(self, model, ds, steps_per_epoch):
-        """One Keras ``fit`` epoch: ``steps_per_epoch`` batches of a fresh shuffle; returns the mean metrics."""
-        sums, n = {}, 0
+        """One Keras ``fit`` epoch: ``steps_per_epoch`` batches of a fresh shuffle; returns the mean metrics.  The
+        per-step metric scalars stay on the device and are reduced once at the end of the epoch."""
+        seen = []
         for batch in ds:
-            if n >= steps_per_epoch:
+            if len(seen) >= steps_per_epoch:
                 break
-            for k, v in model.train_step(batch).items():
-                sums[k] = sums.get(k, 0.0) + (v.detach() if isinstance(v, torch.Tensor) else v)
-            n += 1
-        return {k: float(v) / max(n, 1) for k, v in sums.items()}
+            seen.append(model.train_step(batch))
+        if not seen:
+            return {}
+        out = {}
+        for k in seen[0]:
+            vals = [m[k] for m in seen]
+            tensors = [v.detach().reshape(()).float() for v in vals if isinstance(v, torch.Tensor)]
+            total = float(torch.stack(tensors).sum()) if tensors else 0.0
+            total += float(sum(v for v in vals if not isinstance(v, torch.Tensor)))
+            out[k] = total / len(vals)
+        return out
 
     def _epoch_psnrs(self, model, train_image, train_c2w, test_image, test_c2w):
         out = []
@@ -179,17 +188,35 @@ class ExecutionRun:
             self.history.append({"epoch": epoch_number, "seconds": seconds, "psnr_test": p_test, "psnr_train": p_train,
                                  **metrics})
             if self.save_location is not None and self.is_main:
-                UtilsFiles.save_weights(model, NeRF.get_nerf_model_path(self.save_location, epoch_number))
-                UtilsFiles.save_psnr_values(psnrs_test, psnrs_train,
-                                            UtilsFiles.get_psnr_save_path(self.save_location, epoch_number))
-            if torch.distributed.is_available() and torch.distributed.is_initialized():
-                torch.distributed.barrier()          # the checkpoint is complete before any rank can resume from it
+                # the files are written by a helper thread while the next epoch trains (the GPU does not sit idle
+                # behind a few tens of ms of file formatting); the previous write is joined first
+                self._join_checkpoint()
+                snapshot = model.weights_snapshot()
+                w_path = NeRF.get_nerf_model_path(self.save_location, epoch_number)
+                p_path = UtilsFiles.get_psnr_save_path(self.save_location, epoch_number)
+                hist = (list(psnrs_test), list(psnrs_train))
+
+                def write(snapshot=snapshot, w_path=w_path, p_path=p_path, hist=hist):
+                    os.makedirs(os.path.dirname(str(w_path)), exist_ok=True)
+                    snapshot.write(w_path)
+                    UtilsFiles.save_psnr_values(hist[0], hist[1], p_path)
+                self._checkpoint_thread = threading.Thread(target=write)
+                self._checkpoint_thread.start()
             if self.is_main:
                 print(f"Done epoch {epoch_number} in {seconds:.2f} sec. ({seconds / max(n_batches, 1) * 1e3:.2f} ms / step) "
                       f"Test PSNR: {p_test:.3f}")
             if on_epoch_end is not None:
                 on_epoch_end(self, model, epoch_number)
+        self._join_checkpoint()
+        if torch.distributed.is_available() and torch.distributed.is_initialized():
+            torch.distributed.barrier()              # the last checkpoint is complete before any rank can resume from it
         return model
+
+    def _join_checkpoint(self):
+        t = getattr(self, "_checkpoint_thread", None)
+        if t is not None:
+            t.join()
+            self._checkpoint_thread = None
 
     # ---- rendering ---------------------------------------------------------------------------------------------------------
     def render_frames(self, model, c2w_matrices, h=None, w=None):

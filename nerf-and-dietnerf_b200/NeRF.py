@@ -155,19 +155,30 @@ class NeRF:
         """Keras ``Model.save_weights`` for this model: ``.h5`` -> the reference's Keras-2.7 HDF5 checkpoint layout
         (groups ``model`` / ``model_1``, layers ``dense`` ... ``dense_21``; see h5weights.py), anything else -> ``.npz``
         with the two flat vectors."""
-        from . import h5weights
+        self.weights_snapshot().write(filepath)
+
+    def weights_snapshot(self):
+        """Host copy of the weights (one small D2H copy) whose ``write(path)`` can run on another thread while training
+        continues."""
         pc = self.model_coarse.params.detach().cpu().numpy()
         pf = self.model_fine.params.detach().cpu().numpy() if self.model_fine is not None else None
-        filepath = str(filepath)
-        if filepath.endswith((".h5", ".hdf5")):
-            h5weights.save_flat_params(filepath, pc, pf, self.model_coarse.shapes)
-        else:
-            import numpy as np
-            arrays = {"params_coarse": pc}
-            if pf is not None:
-                arrays["params_fine"] = pf
-            with open(filepath, "wb") as f:
-                np.savez(f, **arrays)
+        shapes = list(self.model_coarse.shapes)
+
+        class _Snapshot:
+            @staticmethod
+            def write(filepath):
+                from . import h5weights
+                filepath = str(filepath)
+                if filepath.endswith((".h5", ".hdf5")):
+                    h5weights.save_flat_params(filepath, pc, pf, shapes)
+                else:
+                    import numpy as np
+                    arrays = {"params_coarse": pc}
+                    if pf is not None:
+                        arrays["params_fine"] = pf
+                    with open(filepath, "wb") as f:
+                        np.savez(f, **arrays)
+        return _Snapshot
 
     def load_weights(self, filepath):
         """Keras ``Model.load_weights``: reads a checkpoint written by ``save_weights`` OR by the reference's Keras

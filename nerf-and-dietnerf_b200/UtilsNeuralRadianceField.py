@@ -175,10 +175,12 @@ class RayDataset:
         return (self.n_rays + self.batch_size - 1) // self.batch_size
 
     def __iter__(self):
+        # one gather of the whole table per epoch; the batches are then contiguous views (no per-step kernels)
         perm = torch.randperm(self.n_rays, device=self.origs.device, generator=self.gen)
+        origs, dirs, rgbs = self.origs[perm], self.dirs[perm], self.rgbs[perm]
         for s in range(0, self.n_rays, self.batch_size):
-            idx = perm[s:s + self.batch_size]
-            yield self.origs[idx], self.dirs[idx], self.rgbs[idx]
+            e = s + self.batch_size
+            yield origs[s:e], dirs[s:e], rgbs[s:e]
 
 
 class DevicePrefetcher:
