@@ -221,12 +221,34 @@ class ExecutionRun:
     # ---- rendering ---------------------------------------------------------------------------------------------------------
     def render_frames(self, model, c2w_matrices, h=None, w=None):
         """The frame loop of ``render_video`` (:315-356) without the encoder: uint8 rgb (F,h,w,3) and float depth
-        (F,h,w) = sum w z, on the host."""
+        (F,h,w) = sum w z, on the host.  With ``torch.distributed`` initialised the frames are dealt round-robin to the
+        ranks (rendering needs no collective) and gathered once at the end; every rank returns all frames."""
         h = self.images[0].shape[0] if h is None else h
         w = self.images[0].shape[1] if w is None else w
-        rgbs, depths = [], []
-        for c2w in c2w_matrices:
-            rgb, depth, _ = model.render_image_lean(c2w, self.field_of_view, h, w)
-            rgbs.append((rgb.reshape(h, w, 3).clamp(0, 1) * 255).to(torch.uint8).cpu().numpy())
-            depths.append(depth.reshape(h, w).cpu().numpy())
-        return np.stack(rgbs), np.stack(depths)
+        dist = torch.distributed
+        world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+        rank = dist.get_rank() if world > 1 else 0
+        n_frames = len(c2w_matrices)
+        mine = list(range(rank, n_frames, world))
+        dev = model.device
+        rgb_dev = torch.empty((len(mine), h, w, 3), dtype=torch.uint8, device=dev)
+        depth_dev = torch.empty((len(mine), h, w), dtype=torch.float32, device=dev)
+        for k, i in enumerate(mine):
+            rgb, depth, _ = model.render_image_lean(c2w_matrices[i], self.field_of_view, h, w)
+            rgb_dev[k] = (rgb.reshape(h, w, 3).clamp(0, 1) * 255).to(torch.uint8)
+            depth_dev[k] = depth.reshape(h, w)
+        if world == 1:
+            return rgb_dev.cpu().numpy(), depth_dev.cpu().numpy()
+        per = (n_frames + world - 1) // world                      # pad every rank's block to the same length
+        pad = lambda t: torch.cat([t, t.new_zeros((per - t.shape[0],) + tuple(t.shape[1:]))]) if t.shape[0] < per else t
+        rgb_all = [torch.empty((per, h, w, 3), dtype=torch.uint8, device=dev) for _ in range(world)]
+        depth_all = [torch.empty((per, h, w), dtype=torch.float32, device=dev) for _ in range(world)]
+        dist.all_gather(rgb_all, pad(rgb_dev))
+        dist.all_gather(depth_all, pad(depth_dev))
+        rgbs = np.empty((n_frames, h, w, 3), dtype=np.uint8)
+        depths = np.empty((n_frames, h, w), dtype=np.float32)
+        for r in range(world):
+            idx = list(range(r, n_frames, world))
+            rgbs[idx] = rgb_all[r][:len(idx)].cpu().numpy()
+            depths[idx] = depth_all[r][:len(idx)].cpu().numpy()
+        return rgbs, depths
