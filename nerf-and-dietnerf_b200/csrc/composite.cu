@@ -174,7 +174,7 @@ __global__ void __launch_bounds__(256) composite_fwd_kernel(const float4* __rest
 // kLoss: the ray's colour, its MSE against `target` and d_rgb are computed HERE from the forward scan the backward
 // repeats anyway, so composite_fwd + mse + composite_bwd of the fine network are one launch (rgb_out optional).
 template <int C, bool kLoss>
-__global__ void __launch_bounds__(256) composite_bwd_kernel(const float4* __restrict__ raw4, const float* __restrict__ z,
+__global__ void __launch_bounds__(256, (C <= 4 ? 4 : (C <= 6 ? 3 : 1))) composite_bwd_kernel(const float4* __restrict__ raw4, const float* __restrict__ z,
                                                             const float* __restrict__ d_rgb,
                                                             const float* __restrict__ d_weights, int64_t n_rays, int S,
                                                             float4* __restrict__ d_raw4, float* __restrict__ d_z,
