@@ -358,13 +358,14 @@ def main():
         peak_tf = peaks.get("bf16_tflops_sustained", 1400.0)
         peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained" if "bf16_tflops_sustained" in peaks else \
             "fallback (B200_PROFILING.md: ~1.4 PFLOP/s sustained)"
-        # Dominant kernel by time (profiles/r01_e_launches_summary.txt: 34 % of the step): mlp_tc_bwd_dw_kernel, the weight
+        # Dominant kernel by time (profiles/r01_i_launches_summary.txt: 35 % of the step): mlp_tc_bwd_dw_kernel, the weight
         # gradients.  Its arithmetic intensity is fixed by the 256x256 output it keeps in TMEM (128 FLOP/B), so its
         # roofline is HBM: it streams every saved activation and every dZ once.  Algorithmic bytes per sample (DESIGN.md
         # 4): bf16 saved activations (64 + 8*256 + 128 columns) + bf16 dZ (8*256 + 144 + 16 columns) = 8896 B.  The
         # launch time is the nerf_mlp_bwd_dw call (dW kernel + its 15 us fixed-order reduce), averaged over the coarse
         # (64 samples/ray) and fine (128) calls of a step; `traffic` is dram read+write of the same two launches from
-        # the ncu --set full capture (profiles/r01_e_mlp_full_summary.txt: 9806 B/sample).
+        # the ncu --set full capture (profiles/r01_i_mlp_full_summary.txt: 1.285 + 2.586 GB for 131072 + 262144 rows
+        # = 9845 B/sample).
         samples_per_launch = batch * (N_C + N_F) / 2
         dw_ms = call_ms.get("nerf_mlp_bwd_dw", float("nan"))
         dx_ms = call_ms.get("nerf_mlp_bwd_dx", float("nan"))
@@ -385,7 +386,7 @@ def main():
             tensor[k]["frac"] = tensor[k]["achieved"] / peak_tf
         roofline = {"bound": "hbm", "kernel": "mlp_tc_bwd_dw_kernel (nerf_mlp_bwd_dw call)",
                     "achieved": ach, "peak": peak_hbm, "unit": "GB/s", "frac": ach / peak_hbm,
-                    "traffic": 9806 * samples_per_launch,
+                    "traffic": 9845 * samples_per_launch,
                     "peak_source": "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6.5 TB/s",
                     "algorithmic_bytes_per_launch": 8896 * samples_per_launch,
                     "tensor_kernels": tensor,
