@@ -16,7 +16,7 @@ import numpy as np
 import torch
 
 from .NeRF import NeRF
-from .parallel import shard_bounds
+from .parallel import all_gather_rows, shard_bounds
 from .poses import get_sphere_matrix, interpolation_type_slerp_for_c2w
 from .vit import ViTB32, consistency_loss, embedder_preprocess
 
@@ -155,11 +155,7 @@ class DietNeRF(NeRF):
         rgb = self.render_image_lean(pose, self.fov, size, size, self.batch_size_train, n_s, n_s, seed=seed, step=step,
                                      ray_begin=lo, n_rays=hi - lo)[0]
         if self.world_size > 1:
-            import torch.distributed as dist
-            parts = [torch.empty((b - a, 3), dtype=torch.float32, device=self.device)
-                     for a, b in (shard_bounds(size * size, self.world_size, r) for r in range(self.world_size))]
-            dist.all_gather(parts, rgb.contiguous(), group=self._process_group)
-            rgb = torch.cat(parts)
+            rgb = all_gather_rows(rgb, size * size, self._process_group)
         image = rgb.reshape(size, size, 3).detach().requires_grad_(True)
         with torch.enable_grad():
             emb = self.embedder(embedder_preprocess(image[None]))[0]

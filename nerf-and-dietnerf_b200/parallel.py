@@ -23,3 +23,23 @@ def allreduce_sum_(flat: torch.Tensor, group=None, async_op: bool = False):
         if async_op:
             return work
     return None if async_op else flat
+
+
+def all_gather_rows(local: torch.Tensor, n_total: int, group=None) -> torch.Tensor:
+    """Concatenate the ranks' contiguous row blocks (``shard_bounds`` of ``n_total`` rows; the last blocks may be shorter
+    or empty) into the full (n_total, ...) tensor on every rank.  Blocks are padded to a common length so that the plain
+    equal-size all-gather of every backend applies."""
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    if world == 1:
+        return local
+    per = (n_total + world - 1) // world
+    padded = local if local.shape[0] == per else torch.cat(
+        [local, local.new_zeros((per - local.shape[0],) + tuple(local.shape[1:]))])
+    parts = [torch.empty_like(padded) for _ in range(world)]
+    dist.all_gather(parts, padded.contiguous(), group=group)
+    out = []
+    for r, part in enumerate(parts):
+        lo, hi = shard_bounds(n_total, world, r)
+        out.append(part[:hi - lo])
+    return torch.cat(out)

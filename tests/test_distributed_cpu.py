@@ -87,3 +87,63 @@ def test_shard_bounds():
     assert spans == [(0, 3), (3, 6), (6, 9), (9, 10)]
     assert [parallel.shard_bounds(2, 4, r) for r in range(4)] == [(0, 1), (1, 2), (2, 2), (2, 2)]   # empty shards
     assert parallel.shard_bounds(7, 1, 0) == (0, 7)
+
+
+def _consistency_worker(rank, world, port, size, n_s, out_dir):
+    """The sharding DietNeRF.calc_consistency_loss uses, with the oracle standing in for the kernels: each rank renders
+    its contiguous block of the image's rays, the blocks are all-gathered (ragged), every rank embeds the full image and
+    back-propagates d(loss)/d(image) through ITS block only; the all-reduced gradient must equal the single-process one."""
+    import importlib
+    import sys
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.set_num_threads(2)
+    from helpers import FAR, NEAR, make_params, oracle_cfg, sphere_pose
+    from oracle import nerf_oracle as O
+    parallel = importlib.import_module("nerf-and-dietnerf_b200.parallel")
+    vit = importlib.import_module("nerf-and-dietnerf_b200.vit")
+    cfg = oracle_cfg()
+    pc, pf = make_params(cfg, 1, 30.0), make_params(cfg, 2, 30.0)
+    emb = vit.ViTB32(layers=1, seed=5).eval()
+    target = torch.randn(768, generator=torch.Generator().manual_seed(1))
+    orig, dirs = O.rays_for_image(sphere_pose(0.4, -0.2, 1.0), 0.6, size, size)
+    n = size * size
+    lo, hi = parallel.shard_bounds(n, world, rank)
+    pcs, pfs = pc.clone().requires_grad_(True), pf.clone().requires_grad_(True)
+    jit = O.stratified_jitter(9, 13, hi - lo, n_s, ray_offset=lo)
+    u = O.importance_uniforms(9, 13, hi - lo, n_s, ray_offset=lo)
+    rgb = O.render(pcs, pfs, cfg, NEAR, FAR, orig[lo:hi], dirs[lo:hi], n_s, n_s, jit, u)[0]
+    image = parallel.all_gather_rows(rgb.detach(), n).reshape(size, size, 3).requires_grad_(True)
+    loss = 0.1 * vit.consistency_loss(emb(vit.embedder_preprocess(image[None]))[0], target)
+    d_image, = torch.autograd.grad(loss, image)
+    (rgb * d_image.reshape(n, 3)[lo:hi]).sum().backward()
+    flat = torch.cat([pcs.grad, pfs.grad])
+    parallel.allreduce_sum_(flat)
+    if rank == 0:
+        np.save(os.path.join(out_dir, "cs.npy"), np.concatenate([[loss.item()], flat.numpy()]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_sharded_consistency_term_equals_single_process(tmp_path):
+    import importlib
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from helpers import FAR, NEAR, make_params, oracle_cfg, sphere_pose
+    from oracle import nerf_oracle as O
+    vit = importlib.import_module("nerf-and-dietnerf_b200.vit")
+    size, n_s = 5, 8                          # 25 rays: ragged shards of 13 and 12
+    mp.spawn(_consistency_worker, args=(2, _free_port(), size, n_s, str(tmp_path)), nprocs=2, join=True)
+    got = torch.from_numpy(np.load(tmp_path / "cs.npy")).float()
+    cfg = oracle_cfg()
+    pc, pf = make_params(cfg, 1, 30.0), make_params(cfg, 2, 30.0)
+    emb = vit.ViTB32(layers=1, seed=5).eval()
+    target = torch.randn(768, generator=torch.Generator().manual_seed(1))
+    loss, gc, gf, _ = O.consistency_loss_and_grads(pc, pf, cfg, NEAR, FAR, sphere_pose(0.4, -0.2, 1.0), 0.6, size, size * size,
+                                                   n_s, 9, 13, emb, target, 0.1)
+    ref = torch.cat([gc, gf])
+    assert abs(got[0].item() - loss.item()) < 1e-6
+    assert ((got[1:] - ref).norm() / ref.norm()).item() < 1e-4

@@ -29,6 +29,7 @@ def main():
         m = pkg.DietNeRFModel(net_config(batch_train=2048), render_config(), NEAR, FAR, targets, poses, 0.6, -1,
                               mode="bf16", seed=3, embedder=pkg.vit.ViTB32(layers=2, seed=5).cuda().eval())
         m.compile(optimizer=pkg.Adam(5e-4))
+        m.IMG_SIZE_FOR_CS_LOSS = 149            # 22201 rays: the ranks' blocks are ragged
         if distributed:
             m.distribute()
         m.counter = 13
