@@ -13,6 +13,10 @@ PICS_INDICES_TO_USE_IN_DATASET = 'pics_indices_to_use_in_dataset'
 GENERAL_SAVE_LOCATION = 'general_save_location'
 TASKS_TO_PERFORM = 'tasks_to_perform'
 START_TRAINING = 'start_training'
+SAVE_DATASET_VIDEO = 'save_dataset_video'
+RENDER_AND_SAVE_TEST_L_TO_R_VIDEO = 'render_and_save_test_left_to_right_video'
+RENDER_AND_SAVE_TEST_SPHERE_VIDEO = 'render_and_save_test_sphere_video'
+RENDER_AND_SAVE_TEST_PATH_VIDEO = 'render_and_save_test_path_video'
 NEURAL_NET = 'neural_net'
 RENDER = 'render'
 TRAINING = 'training'
@@ -45,3 +49,8 @@ IDX_TRAIN_IMG_TO_PLOT = 'idx_train_img_to_plot'
 
 NERF_MODEL = 'NeRF'
 DIETNERF_MODEL = 'DietNeRF'
+
+# video:
+FPS_TRAIN_SET_VIDEO = 'fps_train_set_video'
+FPS_RENDER_VIDEO = 'fps_render_video'
+IMG_INDICES_FOR_PATH_VIDEO = 'img_indices_for_path_video'

@@ -2,8 +2,10 @@
 
 Kept: config -> dataset -> model (``get_nerf`` :216-232, ``_init_dietnerf`` :234-264) -> epoch loop (``_training``
 :169-201: ``fit`` over ``steps_per_epoch = (n_images*h*w) // batch`` shuffled ray batches, then PSNR of the held-out test
-image and of one training image, then a weight + PSNR checkpoint per epoch) and the frame loop of ``render_video``
-(:315-356: rgb + depth = sum w z per pose).  Not rebuilt: plots, video encoding, GCS sync, the task switchboard.
+image and of one training image, then a weight + PSNR checkpoint per epoch), ``render_video`` (:315-356: rgb + equalised depth = sum w z per
+pose, two MJPG files under ``video_save/``) with its three trajectories (left-to-right :358-377, sphere :390-413, path
+between dataset views :426-440), ``save_dataset_video`` (:442-448) and the part of ``start``'s switchboard (:117-152)
+that drives them.  Not rebuilt: matplotlib plots and the plot video, GCS sync.
 
 Differences from the reference, all in how the loop is driven, none in what a step computes: the ray table lives in HBM
 (``RayDataset``) instead of a tf.data pipeline; metrics stay on the device and are read once per epoch; with
@@ -25,14 +27,28 @@ from .ConfigurationKeys import (BLENDER, COLMAP, DATASET_LOCATION, DATASET_TYPE,
                                 FAR_DEPTH_RENDER, GENERAL_SAVE_LOCATION, IDX_TRAIN_IMG_TO_PLOT, N_EPOCHS,
                                 N_RAYS_IN_BATCH_TRAIN, NEAR_DEPTH_RENDER, NEURAL_NET, OPTIMIZER_LR,
                                 PICS_INDICES_TO_USE_IN_DATASET, RENDER, STARTING_EPOCH_NUMBER, START_TRAINING,
-                                TASKS_TO_PERFORM, TEST_IMG_IDX, TRAINING, TYPE_OF_MODEL)
+                                TASKS_TO_PERFORM, TEST_IMG_IDX, TRAINING, TYPE_OF_MODEL, VIDEO, FPS_RENDER_VIDEO,
+                                FPS_TRAIN_SET_VIDEO, IMG_INDICES_FOR_PATH_VIDEO, RENDER_AND_SAVE_TEST_L_TO_R_VIDEO,
+                                RENDER_AND_SAVE_TEST_SPHERE_VIDEO, RENDER_AND_SAVE_TEST_PATH_VIDEO, SAVE_DATASET_VIDEO)
 from .DietNeRF import DietNeRF
 from .NeRF import NeRF
 from .optimizers import Adam
-from .poses import estimate_point_of_interest_in_scene
+from .poses import (estimate_point_of_interest_in_scene, get_c2w_matrices_between_2_c2w_with_stretch,
+                    get_l_to_r_c2w_matrices, get_rotation_matrix_from_source_to_dest_mats, get_sphere_matrices)
+from .UtilsCV import histogram_equalize_frames
 from .UtilsNeuralRadianceField import get_num_of_batches, get_psnr_for_image, prepare_ds
+from .UtilsVideo import save_frames_as_video
 
 SAVE_DIR_NAME_FORMAT = '{}_save_dir_{}'
+DIR_SAVE_VIDEOS = 'video_save'
+# file names of src/UtilsPlots.py:19-25
+FILENAME_TRAIN_SET_VIDEO = 'train_set_video.avi'
+FILENAME_RENDER_DEPTHS_L_TO_R_VIDEO = 'render_depths_l_to_r_video.avi'
+FILENAME_RENDER_L_TO_R_RGB_VIDEO = 'render_l_to_r_rgb_video.avi'
+FILENAME_RENDER_DEPTHS_SPHERE_VIDEO = 'render_depths_sphere_video.avi'
+FILENAME_RENDER_DEPTHS_PATH_VIDEO = 'render_depths_path_video.avi'
+FILENAME_RENDER_RGB_SPHERE_VIDEO = 'render_rgb_sphere_video.avi'
+FILENAME_RENDER_RGB_PATH_VIDEO = 'render_rgb_path_video.avi'
 
 
 def get_save_location(path_to_config_file, config) -> Path:
@@ -63,6 +79,7 @@ class ExecutionRun:
         self.dataset_type = config.get(DATASET_TYPE)
         self.pics_indices_to_use_in_dataset = config.get(PICS_INDICES_TO_USE_IN_DATASET)
         self.net_config, self.render_config, self.training_config = config[NEURAL_NET], config[RENDER], config[TRAINING]
+        self.video_properties = config.get(VIDEO) or {}
         data = self.get_data(config) if data is None else data
         (self.images, self.camera_poses, self.field_of_view, self.near_boundary, self.far_boundary,
          self.average_c2w_before_recenter, self.c2w_scale_parameter) = data
@@ -133,9 +150,18 @@ class ExecutionRun:
 
     # ---- training ------------------------------------------------------------------------------------------------------------
     def start(self):
+        """The tasks of ``tasks_to_perform`` in the reference's order (:117-152); a task missing from the YAML is off."""
         if self.tasks_to_perform.get(START_TRAINING, False):
             self._training()
             self._epoch_number = self.training_config[N_EPOCHS]
+        if self.tasks_to_perform.get(RENDER_AND_SAVE_TEST_L_TO_R_VIDEO, False):
+            self.render_l_to_r_test_video()
+        if self.tasks_to_perform.get(RENDER_AND_SAVE_TEST_SPHERE_VIDEO, False):
+            self.render_sphere_test_video_with_net_weights()
+        if self.tasks_to_perform.get(RENDER_AND_SAVE_TEST_PATH_VIDEO, False):
+            self.render_path_test_video_with_net_weights()
+        if self.tasks_to_perform.get(SAVE_DATASET_VIDEO, False):
+            self.save_dataset_video()
 
     def fit(self, model, ds, steps_per_epoch):
         """One Keras ``fit`` epoch: ``steps_per_epoch`` batches of a fresh shuffle; returns the mean metrics.  The
@@ -219,10 +245,12 @@ class ExecutionRun:
             self._checkpoint_thread = None
 
     # ---- rendering ---------------------------------------------------------------------------------------------------------
-    def render_frames(self, model, c2w_matrices, h=None, w=None):
-        """The frame loop of ``render_video`` (:315-356) without the encoder: uint8 rgb (F,h,w,3) and float depth
-        (F,h,w) = sum w z, on the host.  With ``torch.distributed`` initialised the frames are dealt round-robin to the
-        ranks (rendering needs no collective) and gathered once at the end; every rank returns all frames."""
+    def render_frames(self, model, c2w_matrices, h=None, w=None, equalize_depth=False):
+        """The frame loop of ``render_video`` (:315-356) without the encoder: uint8 rgb (F,h,w,3) = round(255 rgb) and
+        depth (F,h,w) = sum w z, on the host -- float32, or with ``equalize_depth`` the uint8 levels of the reference's
+        ``histogram_equalize`` computed on the GPU.  With ``torch.distributed`` initialised the frames are dealt
+        round-robin to the ranks (rendering needs no collective) and gathered once at the end; every rank returns all
+        frames."""
         h = self.images[0].shape[0] if h is None else h
         w = self.images[0].shape[1] if w is None else w
         dist = torch.distributed
@@ -235,20 +263,103 @@ class ExecutionRun:
         depth_dev = torch.empty((len(mine), h, w), dtype=torch.float32, device=dev)
         for k, i in enumerate(mine):
             rgb, depth, _ = model.render_image_lean(c2w_matrices[i], self.field_of_view, h, w)
-            rgb_dev[k] = (rgb.reshape(h, w, 3).clamp(0, 1) * 255).to(torch.uint8)
+            rgb_dev[k] = (rgb.reshape(h, w, 3).clamp(0, 1) * 255).round().to(torch.uint8)
             depth_dev[k] = depth.reshape(h, w)
+        if equalize_depth:
+            depth_dev = histogram_equalize_frames(depth_dev)
         if world == 1:
             return rgb_dev.cpu().numpy(), depth_dev.cpu().numpy()
         per = (n_frames + world - 1) // world                      # pad every rank's block to the same length
         pad = lambda t: torch.cat([t, t.new_zeros((per - t.shape[0],) + tuple(t.shape[1:]))]) if t.shape[0] < per else t
         rgb_all = [torch.empty((per, h, w, 3), dtype=torch.uint8, device=dev) for _ in range(world)]
-        depth_all = [torch.empty((per, h, w), dtype=torch.float32, device=dev) for _ in range(world)]
+        depth_all = [torch.empty((per, h, w), dtype=depth_dev.dtype, device=dev) for _ in range(world)]
         dist.all_gather(rgb_all, pad(rgb_dev))
         dist.all_gather(depth_all, pad(depth_dev))
         rgbs = np.empty((n_frames, h, w, 3), dtype=np.uint8)
-        depths = np.empty((n_frames, h, w), dtype=np.float32)
+        depths = np.empty((n_frames, h, w), dtype=np.uint8 if equalize_depth else np.float32)
         for r in range(world):
             idx = list(range(r, n_frames, world))
             rgbs[idx] = rgb_all[r][:len(idx)].cpu().numpy()
             depths[idx] = depth_all[r][:len(idx)].cpu().numpy()
         return rgbs, depths
+
+    def render_video(self, c2w_matrices, process_description, filename_rgb, filename_depths, loops=1, model=None):
+        """Render one frame per pose with this run's weights and save ``video_save/<filename_rgb>`` and
+        ``<filename_depths>`` (depth = sum w z, histogram-equalised per frame) at ``fps_render_video`` (:315-356).
+        Returns the two paths; rank 0 writes the files."""
+        model = self.get_nerf() if model is None else model
+        fps = self.video_properties[FPS_RENDER_VIDEO]
+        if self.is_main:
+            print(process_description, f"({len(c2w_matrices)} frames)")
+        rgbs, depths = self.render_frames(model, np.asarray(c2w_matrices, dtype=np.float32), equalize_depth=True)
+        where_rgb = self.save_location / DIR_SAVE_VIDEOS / filename_rgb
+        where_depths = self.save_location / DIR_SAVE_VIDEOS / filename_depths
+        if self.is_main:
+            save_frames_as_video(where_rgb, list(rgbs) * loops, fps)
+            save_frames_as_video(where_depths, list(depths) * loops, fps)
+        return where_rgb, where_depths
+
+    def _point_of_interest(self):
+        if getattr(self, "_poi", None) is None:
+            self._poi = estimate_point_of_interest_in_scene(self.camera_poses, rng=np.random.RandomState(self.seed))
+        return self._poi
+
+    def get_l_to_r_c2w_matrices_to_render(self):
+        """5 s of a left-to-right dolly (:358-377): on a spherical dataset around the test pose with its rotation,
+        otherwise in the frame of the average pose."""
+        matrices = get_l_to_r_c2w_matrices(self.video_properties[FPS_RENDER_VIDEO] * 5)
+        _, is_spherical_dataset = self._point_of_interest()
+        if is_spherical_dataset:
+            test_c2w = self.camera_poses[self.training_config[TEST_IMG_IDX]]
+            matrices[:, :3, 3] = test_c2w[:3, 3] - matrices[:, :3, 3]
+            matrices[:, :3, :3] = test_c2w[:3, :3]
+            return matrices
+        average_c2w = UtilsFiles.change_mats_to_homogeneous(UtilsFiles.poses_avg(self.camera_poses)[..., :4][None])
+        return average_c2w @ matrices
+
+    def get_sphere_c2w_matrices_to_render(self):
+        """6 s per orbit, two orbits (:390-413): the unit-sphere poses turned so the first one has the test pose's
+        rotation and centred on the scene's point of interest (spherical dataset), or pushed out to the Blender
+        cameras' distance."""
+        matrices = get_sphere_matrices(int(self.video_properties[FPS_RENDER_VIDEO] * 6))
+        point, is_spherical_dataset = self._point_of_interest()
+        if is_spherical_dataset:
+            rotation = get_rotation_matrix_from_source_to_dest_mats(
+                matrices[0, :3, :3], self.camera_poses[self.training_config[TEST_IMG_IDX]][:3, :3])
+            matrices = rotation @ matrices
+            matrices[:, :3, 3] += point
+        elif self.dataset_type == BLENDER:
+            distance = self.c2w_scale_parameter * self.average_c2w_before_recenter[2, 3]
+            matrices[:, :3, 3] *= distance
+            matrices[:, :3, 3] += np.asarray([0, 0, -distance])
+        return matrices
+
+    def get_path_c2w_matrices_to_render(self):
+        """2 s (slowing down) from each view of ``img_indices_for_path_video`` to the next and back to the first
+        (:426-440)."""
+        total_frames = int(self.video_properties[FPS_RENDER_VIDEO] * 2)
+        c2ws = self.camera_poses[self.video_properties[IMG_INDICES_FOR_PATH_VIDEO]]
+        matrices = []
+        for c2w1, c2w2 in zip(c2ws, np.roll(c2ws, -1, axis=0)):
+            matrices.extend(get_c2w_matrices_between_2_c2w_with_stretch(c2w1, c2w2, total_frames))
+        return np.asarray(matrices)
+
+    def render_l_to_r_test_video(self, model=None):
+        return self.render_video(self.get_l_to_r_c2w_matrices_to_render(), 'Rendering images for l_to_r video',
+                                 FILENAME_RENDER_L_TO_R_RGB_VIDEO, FILENAME_RENDER_DEPTHS_L_TO_R_VIDEO, model=model)
+
+    def render_sphere_test_video_with_net_weights(self, model=None):
+        return self.render_video(self.get_sphere_c2w_matrices_to_render(), 'Rendering images for sphere video',
+                                 FILENAME_RENDER_RGB_SPHERE_VIDEO, FILENAME_RENDER_DEPTHS_SPHERE_VIDEO, model=model)
+
+    def render_path_test_video_with_net_weights(self, model=None):
+        return self.render_video(self.get_path_c2w_matrices_to_render(), 'Rendering images for path video',
+                                 FILENAME_RENDER_RGB_PATH_VIDEO, FILENAME_RENDER_DEPTHS_PATH_VIDEO, model=model)
+
+    def save_dataset_video(self):
+        """The training images as a video at ``fps_train_set_video`` (:442-448)."""
+        filename = self.save_location / DIR_SAVE_VIDEOS / FILENAME_TRAIN_SET_VIDEO
+        _, train_images, _ = self._get_train_data_from_loaded_dataset()
+        if self.is_main:
+            save_frames_as_video(filename, train_images, self.video_properties[FPS_TRAIN_SET_VIDEO])
+        return filename

@@ -170,3 +170,70 @@ def get_view_directions(coords_3d, rays_dirs, n_angles_for_model):
     out = torch.empty((n * s, n_angles_for_model + 1), dtype=torch.float32, device=d.device)
     call("nerf_view_directions", ptr(d), n, s, int(n_angles_for_model), ptr(out))
     return out
+
+
+# ---- depth-map visualisation (src/UtilsCV.py:700-760), used by ExecutionRun.render_video --------------------------------
+RGB_TO_YIQ = np.array([[0.299, 0.587, 0.114], [0.596, -0.275, -0.321], [0.212, -0.523, 0.311]])
+
+
+def rgb2yiq(im_rgb):
+    return np.dot(im_rgb, RGB_TO_YIQ.T)
+
+
+def yiq2rgb(im_yiq):
+    return np.dot(im_yiq, np.linalg.inv(RGB_TO_YIQ).T)
+
+
+def _histogram_equalize_grays(gray_im):
+    """[0,1]-ish grays -> equalised values in [0,255] (src/UtilsCV.py:724-743): stretch to [0,255], 256-bin histogram of
+    the floor, cumulative lookup table normalised from its first non-zero entry, indexed by the ROUNDED gray."""
+    if np.max(gray_im) == 0:
+        return gray_im, None, None
+    gray_im = gray_im - np.min(gray_im)
+    top = np.max(gray_im)
+    if top == 0:                    # a constant image: the reference divides 0/0 here; an all-zero frame is returned
+        return np.zeros_like(gray_im), None, None
+    gray_im = gray_im / top * 255
+    hist_orig = np.histogram(gray_im, np.arange(257))[0]
+    cum_hist = np.cumsum(hist_orig)
+    nonzero_val = cum_hist[np.nonzero(cum_hist)[0][0]]
+    lookup_table = np.round(((cum_hist - nonzero_val) / (cum_hist[-1] - nonzero_val)) * 255)
+    im_eq = lookup_table[np.round(gray_im).astype('int')]
+    return im_eq, hist_orig, np.histogram(im_eq, np.arange(257))[0]
+
+
+def histogram_equalize(im_orig):
+    """-> [im_eq in [0,1], hist_orig, hist_eq]; RGB images are equalised on the Y channel of YIQ.  Host NumPy, same
+    contract as src/UtilsCV.py:700-721 (the input is not modified)."""
+    im = np.array(im_orig, copy=True)
+    if im.ndim == 3:
+        im_yiq = rgb2yiq(im)
+        im_eq, hist_orig, hist_eq = _histogram_equalize_grays(im_yiq[:, :, 0])
+        if hist_orig is None:
+            return im, hist_orig, hist_eq
+        im_yiq[:, :, 0] = im_eq / 255
+        return yiq2rgb(im_yiq), hist_orig, hist_eq
+    im_eq, hist_orig, hist_eq = _histogram_equalize_grays(im)
+    return (im_eq / 255 if hist_orig is not None else im_eq), hist_orig, hist_eq
+
+
+def histogram_equalize_frames(depth):
+    """The gray branch of ``histogram_equalize`` for a stack of frames (F,h,w) where they are rendered: a torch tensor
+    on any device in, uint8 levels (F,h,w) out -- ``level/255`` is the reference's ``im_eq`` and ``level`` is what its
+    video writer stores (``uint8(round(im_eq*255))``, src/UtilsVideo.py:34).  Same float32 stretch and float64 table as
+    the NumPy version, so the levels are identical; a video frame leaves the GPU as h*w bytes instead of h*w floats."""
+    f = depth.shape[0]
+    g = depth.reshape(f, -1).to(torch.float32)
+    g = g - g.min(dim=1, keepdim=True).values
+    top = g.max(dim=1, keepdim=True).values
+    flat = top == 0                                              # all-zero / constant frames stay zero
+    g = g / torch.where(flat, torch.ones_like(top), top) * 255
+    idx = g.floor().clamp_(0, 255).long()
+    hist = torch.zeros((f, 256), dtype=torch.int64, device=g.device).scatter_add_(1, idx, torch.ones_like(idx))
+    cum = hist.cumsum(1)
+    first = cum.gather(1, (cum > 0).to(torch.int64).argmax(dim=1, keepdim=True))
+    denom = (cum[:, -1:] - first).clamp_(min=1).to(torch.float64)
+    table = torch.round((cum - first).to(torch.float64) / denom * 255)
+    levels = table.gather(1, torch.round(g).long().clamp_(0, 255)).to(torch.uint8)
+    levels = torch.where(flat, torch.zeros_like(levels), levels)
+    return levels.reshape(depth.shape)

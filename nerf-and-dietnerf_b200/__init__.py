@@ -9,7 +9,7 @@ no CPU fallback.
 from . import ConfigurationKeys, _lib  # noqa: F401
 from . import UtilsCV, UtilsNeuralRadianceField, network, optimizers, parallel, poses, vit  # noqa: F401
 from . import NeRF as _nerf_module, DietNeRF as _dietnerf_module  # noqa: F401
-from . import ExecutionRun as _execution_run_module, UtilsFiles, h5weights  # noqa: F401
+from . import ExecutionRun as _execution_run_module, UtilsFiles, UtilsVideo, h5weights  # noqa: F401
 from ._lib import LIB_PATH, NerfLibraryError, NetCfg, load  # noqa: F401
 from .network import NerfMLP  # noqa: F401
 from .optimizers import Adam  # noqa: F401

@@ -1,7 +1,8 @@
-"""The two camera-pose helpers DietNeRF's random source pose needs (src/DietNeRF.py:238-259): a pose on a sphere
-looking at the origin (src/UtilsCV.py:41-121) and the slerp/lerp interpolation between two camera-to-world matrices
-(src/UtilsCV.py:175-225).  Host-side NumPy, a handful of 4x4 products per consistency step; the rest of the
-reference's pose geometry (recentering, RANSAC look-at point, video trajectories) is outside the hot path.
+"""Camera-pose geometry on the host (NumPy, 4x4 matrices): what DietNeRF's random source pose needs
+(src/DietNeRF.py:238-259: a pose on a sphere looking at the origin, src/UtilsCV.py:41-121, and the slerp/lerp
+interpolation between two camera-to-world matrices, :175-225), the RANSAC look-at point (:333-464) and the video
+trajectories of ``ExecutionRun.render_video``'s callers (:146-158, :229-247, :407-437, :612-697).  The reference
+leans on the ``quaternion`` package for the last group; the same algebra is written out here in (x, y, z, w) order.
 """
 import numpy as np
 
@@ -152,3 +153,76 @@ def get_sphere_matrices(total_n_matrices):
     mats = [get_sphere_matrix(1, 0, deg, 0) for deg in np.linspace(0, 360, total_n_matrices)] + \
            [get_sphere_matrix(1, deg, 0, 0) for deg in np.linspace(0, 360, total_n_matrices)]
     return np.asarray(mats, dtype=np.float32)
+
+
+# ---- video trajectories between dataset poses (src/UtilsCV.py:146-158, :229-247) -----------------------------------------
+def get_c2w_matrices_between_2_c2w(c2w1, c2w2, n_renders=16):
+    """``n_renders`` poses from ``c2w1`` to ``c2w2`` at evenly spaced interpolation weights (both ends included)."""
+    return interpolation_type_slerp_for_c2w(c2w1, c2w2, np.linspace(0, 1, n_renders))
+
+
+def get_c2w_matrices_between_2_c2w_with_stretch(c2w1, c2w2, n_renders, stretch_knob=1):
+    """As above with the weights warped by a/(a + 1 + knob) and re-normalised to [0, 1]: the camera starts fast and
+    slows down towards ``c2w2`` (a larger knob stretches less)."""
+    alpha = np.linspace(0, 1, n_renders)
+    stretched = alpha * (1 / (alpha + 1 + stretch_knob))
+    stretched = (stretched - stretched.min()) / (stretched.max() - stretched.min())
+    return interpolation_type_slerp_for_c2w(c2w1, c2w2, stretched)
+
+
+# ---- rotations between vectors / frames (src/UtilsCV.py:612-697) ----------------------------------------------------------
+X_UNIT_VEC = np.asarray([1.0, 0.0, 0.0])
+Y_UNIT_VEC = np.asarray([0.0, 1.0, 0.0])
+
+
+def _quat_mul(a, b):
+    """Hamilton product of two (w, x, y, z) quaternions."""
+    aw, ax, ay, az = a
+    bw, bx, by, bz = b
+    return np.asarray([aw * bw - ax * bx - ay * by - az * bz, aw * bx + ax * bw + ay * bz - az * by,
+                       aw * by - ax * bz + ay * bw + az * bx, aw * bz + ax * by - ay * bx + az * bw])
+
+
+def get_rotation_quaternion_with_axis_vec_and_theta(axis_vec, theta):
+    """(w, x, y, z) rotation by ``theta`` radians about the unit vector ``axis_vec`` (the reference's order here)."""
+    return np.concatenate(([np.cos(theta / 2)], np.asarray(axis_vec, dtype=np.float64) * np.sin(theta / 2)))
+
+
+def get_rotation_quaternion_from_vec1_to_vec2(v1, v2):
+    """(w, x, y, z) rotation taking the direction of ``v1`` onto that of ``v2``; anti-parallel inputs turn by pi about
+    an axis orthogonal to them, parallel ones give the identity."""
+    n1, n2 = _normalize(np.asarray(v1, dtype=np.float64)), _normalize(np.asarray(v2, dtype=np.float64))
+    dot = float(n1.dot(n2))
+    if dot < -0.99999:
+        axis = np.cross(X_UNIT_VEC, n1)
+        if np.linalg.norm(axis) < 0.00001:
+            axis = np.cross(Y_UNIT_VEC, n1)
+        return get_rotation_quaternion_with_axis_vec_and_theta(_normalize(axis), np.pi)
+    if dot > 0.99999:
+        return np.asarray([1.0, 0.0, 0.0, 0.0])
+    return get_rotation_quaternion_with_axis_vec_and_theta(_normalize(np.cross(n1, n2)), np.arccos(dot))
+
+
+def rotate_vec_with_quaternion(vec, q):
+    """q * vec * q^-1 for a unit (w, x, y, z) quaternion."""
+    q = np.asarray(q, dtype=np.float64)
+    q_inv = np.asarray([q[0], -q[1], -q[2], -q[3]])
+    return _quat_mul(_quat_mul(q, np.concatenate(([0.0], np.asarray(vec, dtype=np.float64)))), q_inv)[1:]
+
+
+def get_rotation_matrix_from_v1_to_v2(v1, v2):
+    w, x, y, z = get_rotation_quaternion_from_vec1_to_vec2(v1, v2)
+    return rotation_matrix_from_quaternion((x, y, z, w))
+
+
+def get_rotation_matrix_from_source_to_dest_mats(source_mat, dest_mat):
+    """Homogeneous 4x4 R with R[:3,:3] @ source = dest, through q_dest * q_source^-1 like the reference (for proper
+    rotations this is dest @ source^T; the quaternion round trip also projects slightly non-orthonormal inputs)."""
+    qs, qd = quaternion_from_rotation_matrix(source_mat), quaternion_from_rotation_matrix(dest_mat)
+    qs, qd = qs / np.linalg.norm(qs), qd / np.linalg.norm(qd)
+    to_wxyz = lambda q: np.asarray([q[3], q[0], q[1], q[2]])
+    qs_inv = to_wxyz(qs) * np.asarray([1.0, -1.0, -1.0, -1.0])
+    w, x, y, z = _quat_mul(to_wxyz(qd), qs_inv)
+    out = np.eye(4)
+    out[:3, :3] = rotation_matrix_from_quaternion((x, y, z, w))
+    return out
