@@ -23,6 +23,8 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--frames", type=int, default=48)
     ap.add_argument("--size", type=int, default=256)
+    ap.add_argument("--encode", action="store_true", help="also time render_video: depth equalisation on the GPU + both "
+                    "MJPG files written by rank 0 (src/ExecutionRun.py:315-356 end to end)")
     args = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -60,6 +62,25 @@ def main():
         rays = len(poses) * args.size * args.size
         print(f"{len(poses)} frames {args.size}x{args.size} on {world} GPU(s): {dt:.3f} s = {len(poses) / dt:.1f} frames/s = "
               f"{rays / dt / 1e6:.2f} M rays/s (incl. uint8 conversion, gather and the copy of the video to the host)")
+    if args.encode:
+        import tempfile
+        with tempfile.TemporaryDirectory() as tmp:
+            from pathlib import Path
+            run.save_location = Path(tmp)
+            run.video_properties = {"fps_render_video": 60}
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            where_rgb, where_depth = run.render_video(poses, "video probe", "rgb.avi", "depth.avi", model=model)
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            if rank == 0:
+                t1 = time.perf_counter()
+                rgbs, levels = run.render_frames(model, poses, equalize_depth=True) if world == 1 else (None, None)
+                t_frames = time.perf_counter() - t1
+                print(f"render_video ({len(poses)} frames, equalised depth, 2 MJPG files of {os.path.getsize(where_rgb)} + "
+                      f"{os.path.getsize(where_depth)} bytes): {dt:.3f} s = {len(poses) / dt:.1f} frames/s"
+                      + (f"; frames alone {t_frames:.3f} s, so the OpenCV encoder takes {dt - t_frames:.3f} s"
+                         if world == 1 else ""))
     if world > 1:
         dist.destroy_process_group()
 
