@@ -196,6 +196,65 @@ int nerf_train_metrics(const float* sq_err_sums, int64_t n_total_rays, float coa
 int nerf_adam_step(float* params, const float* grads, float* m, float* v, int64_t n, float lr, float beta1,
                    float beta2, float eps, int64_t t, void* stream);
 
+/* ---- the whole path in one call -------------------------------------------------------------------------- */
+/* The `render:` block of the YAML plus the frustum and the MLP arithmetic (NeRF.__init__, src/NeRF.py:35-66). */
+typedef struct nerf_render_cfg {
+  float near_boundary, far_boundary;
+  int32_t n_samples_coarse; /* n_render_samples_coarse */
+  int32_t n_samples_fine;   /* n_render_samples_fine; 0 = coarse network only (no fine model) */
+  int32_t mode;             /* NERF_MODE_* (FP16: render only) */
+} nerf_render_cfg;
+/* Position in the Philox stream: the draws of ray i use counter (ray_offset + i, ., ., step). */
+typedef struct nerf_rng_state {
+  uint64_t seed;
+  uint64_t ray_offset;
+  uint32_t step;
+  uint32_t reserved;
+} nerf_rng_state;
+/* Outputs of NeRF.render (src/NeRF.py:134) for S = n_samples_coarse + n_samples_fine samples per ray, plus depth / acc;
+ * any pointer may be null (a caller that only needs rgb, weights, depth, acc moves 24 instead of 44 bytes per sample). */
+typedef struct nerf_render_outs {
+  float* rgb;     /* (N,3) */
+  float* weights; /* (N,S) */
+  float* cumprod; /* (N,S) */
+  float* alpha;   /* (N,S) */
+  float* rgb_s;   /* (N,S,3) */
+  float* z;       /* (N,S) */
+  float* depth;   /* (N) = sum w z (src/ExecutionRun.py:346) */
+  float* acc;     /* (N) = sum w */
+} nerf_render_outs;
+/* Loss and optimizer of the train step. */
+typedef struct nerf_train_cfg {
+  float coarse_loss_weight; /* loss = coarse_loss_weight * MSE_c + MSE_f: 1 for NeRF (src/NeRF.py:151-157), 2 for DietNeRF's
+                               aliased sum (src/DietNeRF.py:164-171) */
+  int32_t stop_grad_z;      /* 1: detach the importance samples (NOT the reference's behaviour) */
+  int32_t accumulate_grads; /* 1: add to `grads` instead of zeroing it first (DietNeRF's consistency term came before) */
+  float learning_rate, beta_1, beta_2, epsilon; /* Keras Adam (defaults 1e-3, 0.9, 0.999, 1e-7) */
+} nerf_train_cfg;
+
+/* NeRF.render (src/NeRF.py:109-134) for n_rays rays in one call: stratified z -> coarse render_rays -> inverse-CDF
+ * samples -> sort(concat) -> fine render_rays.  params_* are needed in NERF_MODE_FP32, packed_* (nerf_pack_weights /
+ * _fp16) in the tensor-core modes; the *_f pair is ignored when n_samples_fine == 0.  workspace: 256-byte aligned,
+ * nerf_render_workspace_bytes (-1 for a bad config).  Enqueues the same kernels as the separate entry points. */
+int64_t nerf_render_workspace_bytes(const nerf_net_cfg* cfg, const nerf_render_cfg* rc, int64_t n_rays);
+int nerf_render_fused_fwd(const nerf_net_cfg* cfg, const nerf_render_cfg* rc, const float* params_c,
+                          const void* packed_c, const float* params_f, const void* packed_f, const float* origs4,
+                          const float* dirs4, int64_t n_rays, const nerf_rng_state* rng,
+                          const nerf_render_outs* outs, void* workspace, void* stream);
+
+/* NeRF.train_step (src/NeRF.py:136-178) / DietNeRF's ray loss (src/DietNeRF.py:159-172) on this GPU's n_rays rays of a
+ * global batch of n_total_rays (gradients are normalised by the global count, so ranks only have to sum them).
+ * grads: [sum sq err coarse, sum sq err fine, 0, 0 | d params_c | d params_f] (4 + 1 or 2 x nerf_param_count floats).
+ * adam_m / adam_v (same length as the parameter part, [coarse | fine]) non-null: the Adam update of step adam_t (1-based)
+ * is applied and the bf16 packs are refreshed; null: gradients only (the caller all-reduces, then nerf_adam_step).
+ * metrics4_or_null: nerf_train_metrics of the sums in `grads` (per-rank sums unless n_total_rays == n_rays). */
+int64_t nerf_train_workspace_bytes(const nerf_net_cfg* cfg, const nerf_render_cfg* rc, int64_t n_rays);
+int nerf_train_step_fused(const nerf_net_cfg* cfg, const nerf_render_cfg* rc, const nerf_train_cfg* tc,
+                          float* params_c, void* packed_c, float* params_f, void* packed_f, const float* origs4,
+                          const float* dirs4, const float* target_rgb, int64_t n_rays, int64_t n_total_rays,
+                          const nerf_rng_state* rng, float* grads, float* adam_m, float* adam_v, int64_t adam_t,
+                          float* metrics4_or_null, void* workspace, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

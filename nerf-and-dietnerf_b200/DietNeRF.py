@@ -198,9 +198,9 @@ class DietNeRF(NeRF):
             g[:self._extra_grads.numel()] += self._extra_grads
         super().apply_gradients(g)
 
-    def _metrics(self, sums, n_total):
-        m = super()._metrics(sums, n_total)
-        m["loss_for_rays"] = self._metrics_raw[3]          # MSE_c + MSE_f (src/DietNeRF.py:163,168)
+    def _metrics_dict(self, out):
+        m = super()._metrics_dict(out)
+        m["loss_for_rays"] = out[3]                        # MSE_c + MSE_f (src/DietNeRF.py:163,168)
         return m
 
     @staticmethod

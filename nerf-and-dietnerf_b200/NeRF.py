@@ -8,6 +8,7 @@ backward (no autograd tape) over the C ABI, and ray batches can be sharded over 
 NCCL all-reduce of the gradients per step.
 """
 import contextlib
+import ctypes
 import math
 from pathlib import Path
 from typing import Dict
@@ -280,6 +281,85 @@ class NeRF:
                 out = self._render_rays_fused(self.model_fine, rays_orig, rays_dirs, z)
         return out + (z,)
 
+    # ---- the whole path through ONE C-ABI call each (what a non-Python caller binds) -----------------------------------
+    def _render_cfg(self, n_c=None, n_f=None, infer=True):
+        mc = self.model_coarse
+        mode = (mc.infer_mode_id if infer else mc.mode_id) if mc.tensor_core else _lib.MODE_FP32
+        n_f = (n_f if n_f else self.n_render_samples_fine) if self.model_fine is not None else 0
+        return _lib.RenderCfg(float(self.near_boundary), float(self.far_boundary),
+                              int(n_c if n_c else self.n_render_samples_coarse), int(n_f), int(mode))
+
+    def render_fused(self, rays_orig, rays_dirs, n_render_samples_c=None, n_render_samples_f=None, *, seed, step=0,
+                     ray_offset=0, lean=False):
+        """``render`` as one call of ``nerf_render_fused_fwd``: the same kernels in the same order, enqueued by the C
+        side, so the results are bit-identical to ``render(..., seed=, step=, ray_offset=)``.  Returns the 6-tuple of
+        ``render``, or with ``lean`` (rgb, weights, depth, acc, z)."""
+        o, d = f32c(rays_orig, self.device), f32c(rays_dirs, self.device)
+        n = o.shape[0]
+        mc, mf = self.model_coarse, self.model_fine
+        rc = self._render_cfg(n_render_samples_c, n_render_samples_f)
+        s = rc.n_samples_coarse + rc.n_samples_fine
+        f = lambda *shape: torch.empty(shape, dtype=torch.float32, device=self.device)
+        rgb, weights, z = f(n, 3), f(n, s), f(n, s)
+        extra = (f(n), f(n)) if lean else (f(n, s), f(n, s), f(n, s, 3))
+        outs = _lib.RenderOuts(rgb=ptr(rgb), weights=ptr(weights), z=ptr(z))
+        if lean:
+            outs.depth, outs.acc = ptr(extra[0]), ptr(extra[1])
+        else:
+            outs.cumprod, outs.alpha, outs.rgb_s = ptr(extra[0]), ptr(extra[1]), ptr(extra[2])
+        half = mc.tensor_core and rc.mode == _lib.MODE_FP16
+        nbytes = int(_lib.load().nerf_render_workspace_bytes(mc.cfg_ref, ctypes.byref(rc), n))
+        if nbytes < 0:
+            raise _lib.NerfLibraryError("nerf_render_workspace_bytes: unsupported configuration")
+        ws = mc._buffer("ws_render_fused", nbytes + 256)
+        ws_ptr = (ws.data_ptr() + 255) & ~255
+        rng_state = _lib.RngState(int(seed), int(ray_offset), int(step), 0)
+        call("nerf_render_fused_fwd", mc.cfg_ref, ctypes.byref(rc), ptr(mc.params), ptr(mc.packed_for(mc.params, half=half)),
+             ptr(mf.params) if mf is not None else None,
+             ptr(mf.packed_for(mf.params, half=half)) if mf is not None else None, ptr(o), ptr(d), n,
+             ctypes.byref(rng_state), ctypes.byref(outs), ws_ptr)
+        if lean:
+            return rgb, weights, extra[0], extra[1], z
+        return rgb, weights, extra[0], extra[1], extra[2], z
+
+    def train_step_fused(self, rays_orig, rays_dirs, real_rgb, *, n_total_rays=None, ray_offset=0, update=True):
+        """``train_step_local`` as one call of ``nerf_train_step_fused`` on the current stream (no side-stream overlap:
+        this is the sequence a C caller gets).  Single GPU with ``update``; with ``update=False`` only the gradients and
+        sums are produced (flat buffer ``_grad_buffer()``) for a caller that all-reduces them itself."""
+        if self.optimizer is None:
+            raise RuntimeError("call compile(optimizer=Adam(lr)) before train_step")
+        o, d, y = f32c(rays_orig, self.device), f32c(rays_dirs, self.device), f32c(real_rgb, self.device)
+        n = o.shape[0]
+        n_total = n if n_total_rays is None else int(n_total_rays)
+        mc, mf = self.model_coarse, self.model_fine
+        rc = self._render_cfg(infer=False)
+        opt = self.optimizer
+        tcfg = _lib.TrainCfg(float(self.COARSE_LOSS_WEIGHT), 1 if self.stop_grad_z else 0,
+                             1 if getattr(self, "_keep_grads", False) else 0, opt.learning_rate, opt.beta_1, opt.beta_2,
+                             opt.epsilon)
+        n_all = mc.n_params + (mf.n_params if mf is not None else 0)
+        g = self._grad_buffer()
+        opt._state(n_all, self.device)
+        nbytes = int(_lib.load().nerf_train_workspace_bytes(mc.cfg_ref, ctypes.byref(rc), n))
+        if nbytes < 0:
+            raise _lib.NerfLibraryError("nerf_train_workspace_bytes: unsupported configuration")
+        ws = mc._buffer("ws_train_fused", nbytes + 256)
+        ws_ptr = (ws.data_ptr() + 255) & ~255
+        rng_state = _lib.RngState(int(self.seed), int(ray_offset), int(self.step_counter), 0)
+        out = torch.empty(4, dtype=torch.float32, device=self.device)
+        call("nerf_train_step_fused", mc.cfg_ref, ctypes.byref(rc), ctypes.byref(tcfg), ptr(mc.params),
+             ptr(mc.packed_for(mc.params)), ptr(mf.params) if mf is not None else None,
+             ptr(mf.packed_for(mf.params)) if mf is not None else None, ptr(o), ptr(d), ptr(y), n, n_total,
+             ctypes.byref(rng_state), ptr(g), ptr(opt._m) if update else None, ptr(opt._v) if update else None,
+             opt.iterations + 1, ptr(out), ws_ptr)
+        if update:
+            opt.iterations += 1
+            mc.mark_updated()
+            if mf is not None:
+                mf.mark_updated()
+        self.step_counter += 1
+        return self._metrics_dict(out)
+
     def call(self, inputs, training=None, mask=None):
         rays_orig, rays_dirs = inputs
         return self.render(rays_orig, rays_dirs)[0]
@@ -541,8 +621,12 @@ class NeRF:
         out = torch.empty(4, dtype=torch.float32, device=self.device)
         has_fine = self.model_fine is not None
         call("nerf_train_metrics", ptr(sums), int(n_total), float(self.COARSE_LOSS_WEIGHT), 1 if has_fine else 0, ptr(out))
+        return self._metrics_dict(out)
+
+    def _metrics_dict(self, out):
+        """The metrics dict from nerf_train_metrics' out4 = [loss, psnr_coarse, psnr_fine, MSE_c + MSE_f]."""
         metrics = {"loss": out[0], "psnr_coarse": out[1]}
-        if has_fine:
+        if self.model_fine is not None:
             metrics["psnr_fine"] = out[2]
         self._metrics_raw = out
         return metrics

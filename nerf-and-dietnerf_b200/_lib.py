@@ -24,6 +24,28 @@ class NetCfg(Structure):
                 ("hidden", c_int32), ("last_hidden", c_int32), ("leaky_alpha", c_float)]
 
 
+class RenderCfg(Structure):
+    """Mirror of struct nerf_render_cfg."""
+    _fields_ = [("near_boundary", c_float), ("far_boundary", c_float), ("n_samples_coarse", c_int32),
+                ("n_samples_fine", c_int32), ("mode", c_int32)]
+
+
+class RngState(Structure):
+    """Mirror of struct nerf_rng_state."""
+    _fields_ = [("seed", c_uint64), ("ray_offset", c_uint64), ("step", c_uint32), ("reserved", c_uint32)]
+
+
+class RenderOuts(Structure):
+    """Mirror of struct nerf_render_outs (device pointers, any may be null)."""
+    _fields_ = [(n, c_void_p) for n in ("rgb", "weights", "cumprod", "alpha", "rgb_s", "z", "depth", "acc")]
+
+
+class TrainCfg(Structure):
+    """Mirror of struct nerf_train_cfg."""
+    _fields_ = [("coarse_loss_weight", c_float), ("stop_grad_z", c_int32), ("accumulate_grads", c_int32),
+                ("learning_rate", c_float), ("beta_1", c_float), ("beta_2", c_float), ("epsilon", c_float)]
+
+
 class NerfLibraryError(RuntimeError):
     pass
 
@@ -70,6 +92,12 @@ SIGNATURES = {
     "nerf_mse_fwd_bwd": (c_int32, [_P, _P, c_int64, c_int64, c_float, _P, _P, _P]),
     "nerf_train_metrics": (c_int32, [_P, c_int64, c_float, c_int32, _P, _P]),
     "nerf_adam_step": (c_int32, [_P, _P, _P, _P, c_int64, c_float, c_float, c_float, c_float, c_int64, _P]),
+    "nerf_render_workspace_bytes": (c_int64, [_CFG, POINTER(RenderCfg), c_int64]),
+    "nerf_render_fused_fwd": (c_int32, [_CFG, POINTER(RenderCfg), _P, _P, _P, _P, _P, _P, c_int64, POINTER(RngState),
+                                        POINTER(RenderOuts), _P, _P]),
+    "nerf_train_workspace_bytes": (c_int64, [_CFG, POINTER(RenderCfg), c_int64]),
+    "nerf_train_step_fused": (c_int32, [_CFG, POINTER(RenderCfg), POINTER(TrainCfg), _P, _P, _P, _P, _P, _P, _P, c_int64,
+                                        c_int64, POINTER(RngState), _P, _P, _P, c_int64, _P, _P, _P]),
 }
 
 _lib = None
@@ -122,7 +150,7 @@ def check(status, what):
 
 
 # kernels launched per C-ABI call (bf16 mode; the fp32 MLP launches one GEMM per layer and is counted separately)
-KERNELS_PER_CALL = {"nerf_mlp_fwd": 1, "nerf_mlp_fwd_rays": 1, "nerf_mlp_bwd": 3, "nerf_mlp_bwd_dx": 1, "nerf_mlp_bwd_dw": 2,
+KERNELS_PER_CALL = {"nerf_render_fused_fwd": 7, "nerf_mlp_fwd": 1, "nerf_mlp_fwd_rays": 1, "nerf_mlp_bwd": 3, "nerf_mlp_bwd_dx": 1, "nerf_mlp_bwd_dw": 2,
                     "nerf_pack_weights": 2}
 launch_count = 0            # kernels launched through call() since import (bench.py reads the delta)
 event_hook = None           # optional callable(name) -> context manager, used by bench.py to time single calls

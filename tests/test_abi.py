@@ -75,3 +75,24 @@ def test_missing_library_fails_loudly(pkg, monkeypatch):
     monkeypatch.setattr(pkg._lib, "LIB_PATH", "/nonexistent/libnerf_b200.so")
     with pytest.raises(pkg.NerfLibraryError):
         pkg._lib.load()
+
+
+def test_fused_entry_points_report_argument_errors(pkg):
+    """nerf_render_fused_fwd / nerf_train_step_fused: workspace queries and argument checks need no GPU."""
+    lib = pkg.load()
+    L = pkg._lib
+    cfg = pkg.NetCfg(5, 4, 2, 256, 128, 0.05)
+    rc = L.RenderCfg(0.5576, 2.5635, 64, 128, L.MODE_BF16)
+    n_bytes = lib.nerf_render_workspace_bytes(ctypes.byref(cfg), ctypes.byref(rc), 1000)
+    t_bytes = lib.nerf_train_workspace_bytes(ctypes.byref(cfg), ctypes.byref(rc), 1000)
+    assert n_bytes >= 1000 * (64 + 192 * 4 + 64 + 128 + 192) * 4 and t_bytes > n_bytes
+    assert lib.nerf_render_workspace_bytes(ctypes.byref(cfg), ctypes.byref(L.RenderCfg(0.5576, 2.5635, 0, 128, 1)), 10) == -1
+    assert lib.nerf_train_workspace_bytes(ctypes.byref(cfg), ctypes.byref(L.RenderCfg(0.5576, 2.5635, 64, 128, L.MODE_FP16)), 10) == -1
+    rng, outs = L.RngState(1, 0, 0, 0), L.RenderOuts()
+    st = lib.nerf_render_fused_fwd(ctypes.byref(cfg), ctypes.byref(rc), None, None, None, None, ctypes.c_void_p(256),
+                                   ctypes.c_void_p(256), 4, ctypes.byref(rng), ctypes.byref(outs), ctypes.c_void_p(256), None)
+    assert st == -1 and b"weights missing" in lib.nerf_last_error()
+    st = lib.nerf_render_fused_fwd(ctypes.byref(cfg), ctypes.byref(rc), None, ctypes.c_void_p(256), None, ctypes.c_void_p(256),
+                                   ctypes.c_void_p(256), ctypes.c_void_p(256), 4, ctypes.byref(rng), ctypes.byref(outs),
+                                   ctypes.c_void_p(264), None)
+    assert st == -1 and b"256-byte aligned" in lib.nerf_last_error()

@@ -924,3 +924,84 @@ def test_composite_with_fused_loss_matches_the_separate_kernels(pkg, n, s):
     loss.backward()
     assert abs(sum2.item() - ((rgb_o.detach() - y.cpu()) ** 2).sum().item()) < 1e-3
     assert (d_raw2.cpu() - raw_o.grad).abs().max().item() < 2e-6 * max(1.0, raw_o.grad.abs().max().item() * 1e3)
+
+
+# ---- whole-path C-ABI entry points (nerf_render_fused_fwd, nerf_train_step_fused) ---------------------------
+@pytest.mark.parametrize("mode", ["fp32", "bf16", "fp16"])
+@pytest.mark.parametrize("n_angles,n_c,n_f,n", [(2, 64, 128, 500), (1, 64, 64, 77), (2, 64, 0, 100), (0, 64, 128, 130)])
+def test_render_fused_entry_point_equals_the_call_sequence(pkg, mode, n_angles, n_c, n_f, n):
+    """NeRF.render through ONE C-ABI call enqueues the same kernels as the host package's call sequence (whose parity
+    with the oracle test_render establishes): every output is bit-identical for the same Philox position."""
+    if mode != "fp32" and n_angles == 0:
+        pytest.skip("xyz-only network: fp32 mode only (documented gap of the tensor-core path)")
+    model, _, _, _ = _model(pkg, mode, n_angles, 4, n_c, n_f, sigma_gain=4.0)
+    o, d = random_rays(n, 3)
+    o, d = dev(o), dev(d)
+    ref = model.render(o, d, seed=7, step=2, ray_offset=40)
+    got = model.render_fused(o, d, seed=7, step=2, ray_offset=40)
+    assert len(got) == 6
+    for name, a, b in zip(("rgb", "weights", "cumprod", "alpha", "rgb_s", "z"), ref, got):
+        assert a.shape == b.shape and torch.equal(a, b), name
+    rgb, weights, depth, acc, z = model.render_fused(o, d, seed=7, step=2, ray_offset=40, lean=True)
+    assert torch.equal(z, ref[5]) and torch.equal(weights, ref[1])
+    assert (rgb - ref[0]).abs().max().item() < 1e-6
+    assert (depth - (ref[1] * ref[5]).sum(-1)).abs().max().item() < 1e-4
+    assert (acc - ref[1].sum(-1)).abs().max().item() < 1e-5
+    other = model.render_fused(o, d, seed=7, step=3, ray_offset=40)            # another step of the stream: other samples
+    assert not torch.equal(other[5], ref[5])
+    empty = model.render_fused(o[:0], d[:0], seed=7)
+    assert empty[0].shape == (0, 3) and empty[5].shape == (0, n_c + n_f)
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+@pytest.mark.parametrize("diet,n_f,stop", [(False, 128, False), (True, 128, False), (False, 0, False), (False, 128, True)])
+def test_train_step_fused_entry_point_equals_the_call_sequence(pkg, mode, diet, n_f, stop):
+    """NeRF.train_step (and DietNeRF's ray loss) through ONE C-ABI call against the host package's sequence (side
+    streams and all), two steps from the same state: gradients, Adam-updated parameters and metrics agree -- bit for
+    bit in bf16 mode (deterministic kernels), to fp32 atomics' rounding in the fp32 SIMT mode."""
+    n = 192
+    cls = pkg.DietNeRFModel if diet else None
+    a, _, _, _ = _model(pkg, mode, n_f=n_f, cls=cls, sigma_gain=4.0)
+    b, _, _, _ = _model(pkg, mode, n_f=n_f, cls=cls, sigma_gain=4.0)
+    for m in (a, b):
+        m.stop_grad_z = stop
+        m.compile(optimizer=pkg.Adam(5e-4))
+    o, d = random_rays(n, 4)
+    o, d = dev(o), dev(d)
+    exact = mode == "bf16"
+    for step in range(2):
+        y = dev(torch.rand(n, 3, generator=torch.Generator().manual_seed(5 + step)))
+        ma = a.train_step_local(o, d, y, n)
+        mb = b.train_step_fused(o, d, y)
+        ga, gb = a._grad_buffer(), b._grad_buffer()
+        assert torch.isfinite(gb).all().item()
+        if exact:
+            assert torch.equal(ga[4:], gb[4:]), f"gradients differ at step {step}"
+        else:
+            # the fp32 SIMT dW accumulates with float atomics; through the importance sampler (ill-conditioned, DESIGN 7)
+            # their rounding reaches the coarse gradient at the 1e-4 level (measured 1.2e-4)
+            assert ((ga[4:] - gb[4:]).norm() / ga[4:].norm()).item() < 2e-3
+        assert torch.allclose(ga[:2], gb[:2], rtol=1e-5, atol=0)                  # squared-error sums: atomics
+        for pa, pb in ((a.model_coarse.params, b.model_coarse.params),) + \
+                (((a.model_fine.params, b.model_fine.params),) if n_f else ()):
+            if exact:
+                assert torch.equal(pa, pb), f"parameters differ after step {step}"
+            else:
+                # Adam's first steps move a weight by ~lr = 5e-4; where |g| is near Adam's epsilon the update amplifies
+                # the atomics' rounding by lr / eps, so the tight bound is for weights with a significant gradient
+                assert (pa - pb).abs().max().item() < 5e-4
+                g_part = ga[4:4 + pa.numel()] if pa is a.model_coarse.params else ga[4 + pa.numel():]
+                big = g_part.abs() > 1e-2 * g_part.abs().max()
+                assert big.sum().item() > 100 and (pa - pb)[big].abs().max().item() < 2e-5
+        for k in ma:
+            assert abs(ma[k].item() - mb[k].item()) < 1e-3, k
+        assert set(ma) == set(mb) == {"loss", "psnr_coarse"} | ({"psnr_fine"} if n_f else set()) | \
+            ({"loss_for_rays"} if diet else set())
+    assert a.step_counter == b.step_counter == 2 and a.optimizer.iterations == b.optimizer.iterations == 2
+    # gradients only (what a multi-GPU caller all-reduces before nerf_adam_step): parameters stay put
+    before = b.model_coarse.params.clone()
+    b.train_step_fused(o, d, y, n_total_rays=2 * n, update=False)
+    assert torch.equal(before, b.model_coarse.params) and b.optimizer.iterations == 2
+    a.forward_backward(o, d, y, n_total_rays=2 * n, seed=a.seed, step=2)
+    if exact:
+        assert torch.equal(a._grad_buffer()[4:], b._grad_buffer()[4:])
