@@ -96,3 +96,18 @@ def test_fused_entry_points_report_argument_errors(pkg):
                                    ctypes.c_void_p(256), ctypes.c_void_p(256), 4, ctypes.byref(rng), ctypes.byref(outs),
                                    ctypes.c_void_p(264), None)
     assert st == -1 and b"256-byte aligned" in lib.nerf_last_error()
+
+
+def test_c_caller_links_and_fails_loudly_without_a_gpu(pkg):
+    """tools/c_caller_demo.c (plain C, no Python, no torch) builds against include/nerf_b200.h + libnerf_b200.so; without
+    a CUDA device it stops at the first CUDA call with a message and a non-zero exit code, never with made-up numbers."""
+    import subprocess
+    import torch
+    import __graft_entry__ as entry
+    if not os.path.exists(entry.C_DEMO):
+        entry.build()
+    assert os.path.exists(entry.C_DEMO)
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present: the run itself is test_c_caller_trains_and_renders")
+    r = subprocess.run([entry.C_DEMO, "3"], capture_output=True, text=True, timeout=60)
+    assert r.returncode in (2, 3) and r.stdout.strip() == "" and ("CUDA" in r.stderr or "cuda" in r.stderr)

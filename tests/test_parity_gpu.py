@@ -1005,3 +1005,23 @@ def test_train_step_fused_entry_point_equals_the_call_sequence(pkg, mode, diet, 
     a.forward_backward(o, d, y, n_total_rays=2 * n, seed=a.seed, step=2)
     if exact:
         assert torch.equal(a._grad_buffer()[4:], b._grad_buffer()[4:])
+
+
+def test_c_caller_trains_and_renders(pkg):
+    """The boundary without Python: tools/c_caller_demo.c fits both networks to a synthetic 64x64 view with
+    nerf_train_step_fused (Adam inside the call) and renders it back with nerf_render_fused_fwd, all on cudaMalloc'ed
+    buffers.  The loss must fall and the final render must sit where the last training PSNR is."""
+    import json
+    import os
+    import subprocess
+    import __graft_entry__ as entry
+    if not os.path.exists(entry.C_DEMO):
+        entry.build()
+    for mode, steps in ((1, 60), (0, 12)):
+        r = subprocess.run([entry.C_DEMO, str(steps), str(mode)], capture_output=True, text=True, timeout=120)
+        assert r.returncode == 0, (r.returncode, r.stdout, r.stderr)
+        out = json.loads(r.stdout.strip().splitlines()[-1])
+        print(out)
+        assert out["caller"] == "c" and out["finite"] == 1 and out["rays"] == 4096 and out["steps"] == steps
+        assert out["loss_last"] < (0.8 if mode == 1 else 1.0) * out["loss_first"]
+        assert abs(out["render_psnr"] - out["psnr_fine_last"]) < 3.0
