@@ -223,6 +223,8 @@ def histogram_equalize_frames(depth):
     video writer stores (``uint8(round(im_eq*255))``, src/UtilsVideo.py:34).  Same float32 stretch and float64 table as
     the NumPy version, so the levels are identical; a video frame leaves the GPU as h*w bytes instead of h*w floats."""
     f = depth.shape[0]
+    if depth.numel() == 0:                                       # a rank that was dealt no frame
+        return torch.empty(depth.shape, dtype=torch.uint8, device=depth.device)
     g = depth.reshape(f, -1).to(torch.float32)
     g = g - g.min(dim=1, keepdim=True).values
     top = g.max(dim=1, keepdim=True).values

@@ -147,3 +147,70 @@ def test_sharded_consistency_term_equals_single_process(tmp_path):
     ref = torch.cat([gc, gf])
     assert abs(got[0].item() - loss.item()) < 1e-6
     assert ((got[1:] - ref).norm() / ref.norm()).item() < 1e-4
+
+
+# ---- the video frame loop under torch.distributed (ExecutionRun.render_frames / render_video) ----------------------------
+class _StubModel:
+    """Stands in for NeRF on a CPU rank: the 'render' of a pose is a deterministic function of the pose, so that every
+    frame can be told apart after the gather (the CUDA render itself is covered by the GPU tests)."""
+    device = torch.device("cpu")
+
+    def render_image_lean(self, c2w, fov, h, w):
+        yy, xx = torch.meshgrid(torch.arange(h, dtype=torch.float32), torch.arange(w, dtype=torch.float32), indexing="ij")
+        k = float(np.asarray(c2w)[0, 3])
+        rgb = torch.stack([(xx + k) / (w + 8.0), (yy + k) / (h + 8.0), torch.full_like(xx, (k % 7) / 7.0)], -1)
+        depth = 0.5 + 0.1 * k + xx * 0.01 + (yy * 0.02) ** 2
+        return rgb.reshape(-1, 3), depth.reshape(-1), torch.ones(h * w)
+
+
+def _video_run(save_location=None):
+    import importlib
+    pkg = importlib.import_module("nerf-and-dietnerf_b200")
+    config = {"neural_net": {"type_of_model": "NeRF"}, "render": {}, "training": {"test_img_idx": 0},
+              "video": {"fps_render_video": 10}}
+    images = np.zeros((2, 6, 8, 3), dtype=np.float32)
+    return pkg, pkg.ExecutionRun.from_arrays(config, images, np.stack([np.eye(4, dtype=np.float32)] * 2), 0.6, 0.5, 2.5,
+                                             save_location=save_location)
+
+
+def _video_poses(n_frames):
+    poses = np.tile(np.eye(4, dtype=np.float32), (n_frames, 1, 1))
+    poses[:, 0, 3] = np.arange(n_frames)
+    return poses
+
+
+def _video_worker(rank, world, port, n_frames, out_dir):
+    import sys
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.set_num_threads(1)
+    pkg, run = _video_run(save_location=out_dir)
+    assert run.is_main == (rank == 0)
+    rgbs, depths = run.render_frames(_StubModel(), _video_poses(n_frames))
+    _, levels = run.render_frames(_StubModel(), _video_poses(n_frames), equalize_depth=True)
+    np.savez(os.path.join(out_dir, f"rank{rank}.npz"), rgbs=rgbs, depths=depths, levels=levels)
+    run.render_video(_video_poses(n_frames), "two-rank video", "rgb.avi", "depth.avi", model=_StubModel())
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+@pytest.mark.parametrize("n_frames", [5, 1])
+def test_two_rank_video_frames_equal_single_process(tmp_path, n_frames):
+    """Frames are dealt round-robin to the ranks and gathered once: every rank ends with ALL frames in pose order, equal
+    to the single-process loop -- also when the count does not divide (5 over 2) or a rank gets nothing (1 over 2) -- and
+    only rank 0 writes the two video files."""
+    mp.spawn(_video_worker, args=(2, _free_port(), n_frames, str(tmp_path)), nprocs=2, join=True)
+    pkg, run = _video_run()
+    rgbs, depths = run.render_frames(_StubModel(), _video_poses(n_frames))
+    _, levels = run.render_frames(_StubModel(), _video_poses(n_frames), equalize_depth=True)
+    assert rgbs.shape == (n_frames, 6, 8, 3) and rgbs.dtype == np.uint8 and levels.dtype == np.uint8
+    assert len({rgbs[i].tobytes() for i in range(n_frames)}) == n_frames            # frames are distinguishable
+    for rank in range(2):
+        got = np.load(tmp_path / f"rank{rank}.npz")
+        assert np.array_equal(got["rgbs"], rgbs) and np.array_equal(got["depths"], depths)
+        assert np.array_equal(got["levels"], levels)
+    frames, fps = pkg.UtilsVideo.read_video_frames(tmp_path / "video_save" / "rgb.avi")
+    assert frames.shape == (n_frames, 6, 8, 3) and fps == 10
+    assert sorted(os.listdir(tmp_path / "video_save")) == ["depth.avi", "rgb.avi"]
