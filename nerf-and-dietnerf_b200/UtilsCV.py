@@ -184,37 +184,40 @@ def yiq2rgb(im_yiq):
     return np.dot(im_yiq, np.linalg.inv(RGB_TO_YIQ).T)
 
 
-def _histogram_equalize_grays(gray_im):
-    """[0,1]-ish grays -> equalised values in [0,255] (src/UtilsCV.py:724-743): stretch to [0,255], 256-bin histogram of
-    the floor, cumulative lookup table normalised from its first non-zero entry, indexed by the ROUNDED gray."""
-    if np.max(gray_im) == 0:
-        return gray_im, None, None
-    gray_im = gray_im - np.min(gray_im)
-    top = np.max(gray_im)
-    if top == 0:                    # a constant image: the reference divides 0/0 here; an all-zero frame is returned
-        return np.zeros_like(gray_im), None, None
-    gray_im = gray_im / top * 255
-    hist_orig = np.histogram(gray_im, np.arange(257))[0]
-    cum_hist = np.cumsum(hist_orig)
-    nonzero_val = cum_hist[np.nonzero(cum_hist)[0][0]]
-    lookup_table = np.round(((cum_hist - nonzero_val) / (cum_hist[-1] - nonzero_val)) * 255)
-    im_eq = lookup_table[np.round(gray_im).astype('int')]
-    return im_eq, hist_orig, np.histogram(im_eq, np.arange(257))[0]
+def _equalized_levels(gray):
+    """Grays of any range -> (levels in 0..255 as float64, histogram before, histogram after), or None for an image
+    without contrast.  The algorithm of src/UtilsCV.py:724-743: stretch to [0, 255]; count the stretched values per
+    unit-wide bin (bin = floor); running sum of the counts, re-based at its first non-zero entry and scaled to 255, is
+    the look-up table; the table is read at the stretched value ROUNDED to nearest-even, not at its bin."""
+    gray = np.asarray(gray)
+    lo, hi = gray.min(), gray.max()
+    if hi == lo:
+        return None
+    stretched = (gray - lo) / (hi - lo) * 255
+    counts = np.bincount(np.floor(stretched).astype(np.int64).ravel(), minlength=256)
+    running = np.cumsum(counts)
+    base = running[running > 0][0]
+    table = np.rint((running - base) / (running[-1] - base) * 255)
+    levels = table[np.rint(stretched).astype(np.int64)]
+    return levels, counts, np.bincount(levels.astype(np.int64).ravel(), minlength=256)
 
 
 def histogram_equalize(im_orig):
-    """-> [im_eq in [0,1], hist_orig, hist_eq]; RGB images are equalised on the Y channel of YIQ.  Host NumPy, same
-    contract as src/UtilsCV.py:700-721 (the input is not modified)."""
+    """-> [im_eq in [0,1], hist_orig, hist_eq] (256-bin histograms); RGB images are equalised on the Y channel of YIQ.
+    Host NumPy, the contract of src/UtilsCV.py:700-721; the input is not modified.  An all-zero image comes back as it
+    is with ``None`` histograms (the reference's early return); so does any other constant image, where the reference
+    divides 0 by 0."""
     im = np.array(im_orig, copy=True)
+    luma = rgb2yiq(im)[:, :, 0] if im.ndim == 3 else im
+    res = _equalized_levels(luma)
+    if res is None:
+        return (im if im.ndim == 3 or not im.any() else np.zeros_like(im)), None, None
+    levels, hist_orig, hist_eq = res
     if im.ndim == 3:
-        im_yiq = rgb2yiq(im)
-        im_eq, hist_orig, hist_eq = _histogram_equalize_grays(im_yiq[:, :, 0])
-        if hist_orig is None:
-            return im, hist_orig, hist_eq
-        im_yiq[:, :, 0] = im_eq / 255
-        return yiq2rgb(im_yiq), hist_orig, hist_eq
-    im_eq, hist_orig, hist_eq = _histogram_equalize_grays(im)
-    return (im_eq / 255 if hist_orig is not None else im_eq), hist_orig, hist_eq
+        yiq = rgb2yiq(im)
+        yiq[:, :, 0] = levels / 255
+        return yiq2rgb(yiq), hist_orig, hist_eq
+    return levels / 255, hist_orig, hist_eq
 
 
 def histogram_equalize_frames(depth):

@@ -24,19 +24,19 @@ def save_frames_as_video(filename, frames, fps):
     import cv2
     assert len(frames) > 0
     filename = Path(filename)
-    if not os.path.exists(filename.parent):
-        print(filename.parent, "didn't exist, so I created it.")
-        os.makedirs(filename.parent)
-    height, width = frames[0].shape[0], frames[0].shape[1]
-    writer = cv2.VideoWriter(str(filename), cv2.VideoWriter_fourcc(*"MJPG"), fps, (width, height))
+    os.makedirs(filename.parent, exist_ok=True)
+    first = np.asarray(frames[0])
+    writer = cv2.VideoWriter(str(filename), cv2.VideoWriter_fourcc(*"MJPG"), fps, (first.shape[1], first.shape[0]))
     if not writer.isOpened():
         raise Exception(f"cannot open a MJPG writer for {filename}")
-    for frame in frames:
-        u8 = frame_to_uint8(frame)
-        bgr = cv2.cvtColor(u8, cv2.COLOR_GRAY2BGR) if u8.ndim == 2 else cv2.cvtColor(u8, cv2.COLOR_RGB2BGR)
-        writer.write(np.ascontiguousarray(bgr))
-    writer.release()
-    print("Saved video in path", filename)
+    try:
+        for frame in frames:
+            u8 = frame_to_uint8(frame)
+            to_bgr = cv2.COLOR_GRAY2BGR if u8.ndim == 2 else cv2.COLOR_RGB2BGR
+            writer.write(np.ascontiguousarray(cv2.cvtColor(u8, to_bgr)))
+    finally:
+        writer.release()
+    print(f"video with {len(frames)} frames at {fps} fps: {filename}")
 
 
 def read_video_frames(filename):
