@@ -287,6 +287,8 @@ class ExecutionRun:
         """Render one frame per pose with this run's weights and save ``video_save/<filename_rgb>`` and
         ``<filename_depths>`` (depth = sum w z, histogram-equalised per frame) at ``fps_render_video`` (:315-356).
         Returns the two paths; rank 0 writes the files."""
+        if self.save_location is None:
+            raise Exception('render_video needs a save location (the run was built without one)')
         model = self.get_nerf() if model is None else model
         fps = self.video_properties[FPS_RENDER_VIDEO]
         if self.is_main:

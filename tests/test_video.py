@@ -296,3 +296,46 @@ def test_rendered_videos_match_the_reference_recordings(pkg, tmp_path, videos):
     host = np.uint8(np.round(pkg.UtilsCV.histogram_equalize(depth_f[0])[0] * 255))
     dev = pkg.UtilsCV.histogram_equalize_frames(torch.from_numpy(depth_f).cuda())[0].cpu().numpy()
     assert np.array_equal(host, dev)
+
+
+def test_trajectories_on_a_forward_facing_and_a_blender_scene():
+    """The two other branches of the trajectory builders (src/ExecutionRun.py:372-376, :401-411): cameras that do not
+    look at a common point (forward-facing capture) get the left-to-right dolly in the frame of their average pose and
+    the bare unit-sphere orbit; a Blender scene gets the orbit scaled and pushed to the cameras' distance."""
+    pkg = importlib.import_module("nerf-and-dietnerf_b200")
+    rng = np.random.RandomState(0)
+    poses = np.tile(np.eye(4, dtype=np.float32), (12, 1, 1))
+    poses[:, :2, 3] = rng.uniform(-0.5, 0.5, (12, 2))              # a plane of parallel cameras: optical axes never meet
+    config = json.loads(json.dumps(RUN_CONFIG))
+    config["training"]["test_img_idx"] = 3
+    config["video"]["img_indices_for_path_video"] = [0, 5]
+    images = np.zeros((12, 8, 8, 3), dtype=np.float32)
+    run = pkg.ExecutionRun.from_arrays(config, images, poses, 0.6, 0.5, 2.5)
+    run.dataset_type = "colmap"
+    point, spherical = run._point_of_interest()
+    assert not spherical
+    l_to_r = run.get_l_to_r_c2w_matrices_to_render()
+    average = pkg.UtilsFiles.change_mats_to_homogeneous(pkg.UtilsFiles.poses_avg(poses)[..., :4][None])[0]
+    assert l_to_r.shape == (300, 4, 4)
+    assert np.allclose(l_to_r[:, :3, :3], average[:3, :3], atol=1e-6)
+    assert np.allclose(l_to_r[:, :3, 3] - average[:3, 3], np.linspace(-1, 1, 300)[:, None] * average[:3, 0], atol=1e-5)
+    sphere = run.get_sphere_c2w_matrices_to_render()
+    assert np.array_equal(sphere, pkg.poses.get_sphere_matrices(360))                   # untouched for a COLMAP scene
+    path = run.get_path_c2w_matrices_to_render()
+    assert path.shape == (240, 4, 4) and np.abs(path[0] - poses[0]).max() < 1e-6 and np.abs(path[119] - poses[5]).max() < 1e-6
+    assert np.abs(path[120] - poses[5]).max() < 1e-6 and np.abs(path[239] - poses[0]).max() < 1e-6
+    # Blender: the loader hands over the average pose before recentring and the spherify scale
+    run_b = pkg.ExecutionRun(config=config, data=(images, poses, 0.6, 0.5, 2.5, np.diag([1.0, 1.0, 1.0, 1.0]) +
+                                                   np.array([[0, 0, 0, 0], [0, 0, 0, 0], [0, 0, 0, 4.0], [0, 0, 0, 0]]), 0.25))
+    run_b.dataset_type = "blender"
+    run_b._poi = (None, False)
+    sphere_b = run_b.get_sphere_c2w_matrices_to_render()
+    unit = pkg.poses.get_sphere_matrices(360)
+    assert np.allclose(sphere_b[:, :3, :3], unit[:, :3, :3])
+    assert np.allclose(sphere_b[:, :3, 3], unit[:, :3, 3] * 1.0 + np.array([0, 0, -1.0]), atol=1e-6)   # 0.25 * 4 = 1
+    # a run without a `video:` block or a save directory says so instead of failing somewhere inside
+    bare = pkg.ExecutionRun.from_arrays({k: v for k, v in config.items() if k != "video"}, images, poses, 0.6, 0.5, 2.5)
+    with pytest.raises(KeyError):
+        bare.get_l_to_r_c2w_matrices_to_render()
+    with pytest.raises(Exception, match="save"):
+        run.render_video(poses[:1], "x", "a.avi", "b.avi", model=object())
