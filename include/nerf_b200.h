@@ -247,13 +247,17 @@ int nerf_render_fused_fwd(const nerf_net_cfg* cfg, const nerf_render_cfg* rc, co
  * grads: [sum sq err coarse, sum sq err fine, 0, 0 | d params_c | d params_f] (4 + 1 or 2 x nerf_param_count floats).
  * adam_m / adam_v (same length as the parameter part, [coarse | fine]) non-null: the Adam update of step adam_t (1-based)
  * is applied and the bf16 packs are refreshed; null: gradients only (the caller all-reduces, then nerf_adam_step).
- * metrics4_or_null: nerf_train_metrics of the sums in `grads` (per-rank sums unless n_total_rays == n_rays). */
+ * metrics4_or_null: nerf_train_metrics of the sums in `grads` (per-rank sums unless n_total_rays == n_rays).
+ * side_stream_or_null: a second stream of the caller's (tensor-core mode with a fine network): the fine network's
+ * HBM-bound weight-gradient kernel, its Adam step and pack refresh are enqueued there, under the coarse backward, and
+ * joined before the call's last kernels; everything the call enqueued is complete when `stream` reaches its end.
+ * Same results with and without it. */
 int64_t nerf_train_workspace_bytes(const nerf_net_cfg* cfg, const nerf_render_cfg* rc, int64_t n_rays);
 int nerf_train_step_fused(const nerf_net_cfg* cfg, const nerf_render_cfg* rc, const nerf_train_cfg* tc,
                           float* params_c, void* packed_c, float* params_f, void* packed_f, const float* origs4,
                           const float* dirs4, const float* target_rgb, int64_t n_rays, int64_t n_total_rays,
                           const nerf_rng_state* rng, float* grads, float* adam_m, float* adam_v, int64_t adam_t,
-                          float* metrics4_or_null, void* workspace, void* stream);
+                          float* metrics4_or_null, void* workspace, void* side_stream_or_null, void* stream);
 
 #ifdef __cplusplus
 }

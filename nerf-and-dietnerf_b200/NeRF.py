@@ -323,9 +323,10 @@ class NeRF:
         return rgb, weights, extra[0], extra[1], extra[2], z
 
     def train_step_fused(self, rays_orig, rays_dirs, real_rgb, *, n_total_rays=None, ray_offset=0, update=True):
-        """``train_step_local`` as one call of ``nerf_train_step_fused`` on the current stream (no side-stream overlap:
-        this is the sequence a C caller gets).  Single GPU with ``update``; with ``update=False`` only the gradients and
-        sums are produced (flat buffer ``_grad_buffer()``) for a caller that all-reduces them itself."""
+        """``train_step_local`` as one call of ``nerf_train_step_fused`` on the current stream, with the model's side
+        stream handed to the C side for the fine network's weight gradients (``overlap_dw = False``: one stream).
+        Single GPU with ``update``; with ``update=False`` only the gradients and sums are produced (flat buffer
+        ``_grad_buffer()``) for a caller that all-reduces them itself."""
         if self.optimizer is None:
             raise RuntimeError("call compile(optimizer=Adam(lr)) before train_step")
         o, d, y = f32c(rays_orig, self.device), f32c(rays_dirs, self.device), f32c(real_rgb, self.device)
@@ -347,11 +348,12 @@ class NeRF:
         ws_ptr = (ws.data_ptr() + 255) & ~255
         rng_state = _lib.RngState(int(self.seed), int(ray_offset), int(self.step_counter), 0)
         out = torch.empty(4, dtype=torch.float32, device=self.device)
+        side = self._side_stream() if mf is not None else None      # None with overlap_dw = False: one stream
         call("nerf_train_step_fused", mc.cfg_ref, ctypes.byref(rc), ctypes.byref(tcfg), ptr(mc.params),
              ptr(mc.packed_for(mc.params)), ptr(mf.params) if mf is not None else None,
              ptr(mf.packed_for(mf.params)) if mf is not None else None, ptr(o), ptr(d), ptr(y), n, n_total,
              ctypes.byref(rng_state), ptr(g), ptr(opt._m) if update else None, ptr(opt._v) if update else None,
-             opt.iterations + 1, ptr(out), ws_ptr)
+             opt.iterations + 1, ptr(out), ws_ptr, side.cuda_stream if side is not None else None)
         if update:
             opt.iterations += 1
             mc.mark_updated()

@@ -97,7 +97,7 @@ SIGNATURES = {
                                         POINTER(RenderOuts), _P, _P]),
     "nerf_train_workspace_bytes": (c_int64, [_CFG, POINTER(RenderCfg), c_int64]),
     "nerf_train_step_fused": (c_int32, [_CFG, POINTER(RenderCfg), POINTER(TrainCfg), _P, _P, _P, _P, _P, _P, _P, c_int64,
-                                        c_int64, POINTER(RngState), _P, _P, _P, c_int64, _P, _P, _P]),
+                                        c_int64, POINTER(RngState), _P, _P, _P, c_int64, _P, _P, _P, _P]),
 }
 
 _lib = None

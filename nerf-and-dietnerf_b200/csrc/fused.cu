@@ -82,7 +82,7 @@ struct TrainWs {
   float *z_c, *raw_c, *rgb_c, *w_c, *d_rgb_c, *d_raw_c;
   float *z_f, *u, *raw_f, *d_raw_f, *d_z_f, *d_xyz_f, *d_w_c;
   int32_t* perm;
-  void *saved_c, *saved_f, *ws_bwd;
+  void *saved_c, *saved_f, *ws_bwd, *ws_bwd_c;
   float *xyz_c, *view_c, *xyz_f, *view_f;
   void* ws_fwd;
 };
@@ -113,6 +113,9 @@ int64_t carve_train(const NetGeom& g, const nerf_net_cfg* cfg, const nerf_render
   }
   const int64_t m_max = n * (sc > sf ? sc : sf);
   w->ws_bwd = c.take<uint8_t>(nerf_mlp_workspace_bytes(cfg, m_max, mode, 1));
+  // with a side stream the fine network's weight-gradient kernel runs under the coarse backward: the two must not share
+  // the dZ workspace
+  w->ws_bwd_c = (mode != NERF_MODE_FP32 && sf) ? c.take<uint8_t>(nerf_mlp_workspace_bytes(cfg, n * sc, mode, 1)) : w->ws_bwd;
   if (mode == NERF_MODE_FP32) {
     // the backward of the fp32 mode reads the encodings of BOTH networks: each keeps its own
     w->xyz_c = c.take<float>(n * sc * g.dx);
@@ -124,6 +127,20 @@ int64_t carve_train(const NetGeom& g, const nerf_net_cfg* cfg, const nerf_render
     w->ws_fwd = c.take<uint8_t>(nerf_mlp_workspace_bytes(cfg, m_max, mode, 0));
   }
   return c.off;
+}
+
+// `waiter` waits for everything enqueued on `signaller` so far (an event lives only for this hand-over)
+int stream_wait(cudaStream_t waiter, cudaStream_t signaller) {
+  cudaEvent_t ev;
+  NERF_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+  cudaError_t e = cudaEventRecord(ev, signaller);
+  if (e == cudaSuccess) e = cudaStreamWaitEvent(waiter, ev, 0);
+  cudaEventDestroy(ev);
+  if (e != cudaSuccess) {
+    set_error("stream_wait: %s", cudaGetErrorString(e));
+    return NERF_E_CUDA;
+  }
+  return NERF_OK;
 }
 
 #define NERF_TRY(call)            \
@@ -200,7 +217,7 @@ int nerf_train_step_fused(const nerf_net_cfg* cfg, const nerf_render_cfg* rc, co
                           float* params_c, void* packed_c, float* params_f, void* packed_f, const float* origs4,
                           const float* dirs4, const float* target_rgb, int64_t n_rays, int64_t n_total_rays,
                           const nerf_rng_state* rng, float* grads, float* adam_m, float* adam_v, int64_t adam_t,
-                          float* metrics4, void* workspace, void* stream) {
+                          float* metrics4, void* workspace, void* side_stream, void* stream) {
   NetGeom g;
   NERF_CHECK_ARG(make_geom(cfg, &g), "bad network config");
   NERF_CHECK_ARG(render_cfg_ok(rc) && rc->mode != NERF_MODE_FP16, "bad render config (training runs in FP32 or BF16)");
@@ -221,6 +238,8 @@ int nerf_train_step_fused(const nerf_net_cfg* cfg, const nerf_render_cfg* rc, co
   float* g_f = fine ? grads + 4 + np : nullptr;
   if (!tc_cfg->accumulate_grads) NERF_CUDA(cudaMemsetAsync(grads, 0, (size_t)(4 + n_all) * sizeof(float), st));
   const int32_t sc = rc->n_samples_coarse, sf = rc->n_samples_fine, mode = rc->mode;
+  const bool use_side = tc && fine && side_stream != nullptr && side_stream != stream;
+  bool forked = false, fine_stepped = false;
   if (n > 0) {
     TrainWs w;
     carve_train(g, cfg, rc, n, (uint8_t*)workspace, &w);
@@ -241,8 +260,25 @@ int nerf_train_step_fused(const nerf_net_cfg* cfg, const nerf_render_cfg* rc, co
                            w.view_f, w.ws_fwd, stream));
       NERF_TRY(nerf_composite_mse_fwd_bwd(w.raw_f, w.z_f, target_rgb, n, sf, n_total_rays, 1.0f, nullptr, sums + 1,
                                           w.d_raw_f, through_z ? w.d_z_f : nullptr, stream));
-      NERF_TRY(nerf_mlp_bwd(cfg, params_f, packed_f, w.xyz_f, w.view_f, w.saved_f, w.d_raw_f, n * sf, g_f,
-                            through_z ? w.d_xyz_f : nullptr, w.ws_bwd, mode, stream));
+      if (use_side) {
+        // input-gradient chain here; the HBM-bound weight-gradient kernel, the fine network's Adam step and the refresh
+        // of its bf16 pack go to the side stream and run under the sampler / compositing / coarse backward below
+        NERF_TRY(nerf_mlp_bwd_dx(cfg, params_f, packed_f, w.xyz_f, w.view_f, w.saved_f, w.d_raw_f, n * sf, g_f,
+                                 through_z ? w.d_xyz_f : nullptr, w.ws_bwd, mode, stream));
+        NERF_TRY(stream_wait((cudaStream_t)side_stream, st));
+        NERF_TRY(nerf_mlp_bwd_dw(cfg, params_f, packed_f, w.xyz_f, w.view_f, w.saved_f, w.d_raw_f, n * sf, g_f,
+                                 through_z ? w.d_xyz_f : nullptr, w.ws_bwd, mode, side_stream));
+        if (adam_m) {
+          NERF_TRY(nerf_adam_step(params_f, g_f, adam_m + np, adam_v + np, np, tc_cfg->learning_rate, tc_cfg->beta_1,
+                                  tc_cfg->beta_2, tc_cfg->epsilon, adam_t, side_stream));
+          NERF_TRY(nerf_pack_weights(cfg, params_f, packed_f, side_stream));
+          fine_stepped = true;
+        }
+        forked = true;
+      } else {
+        NERF_TRY(nerf_mlp_bwd(cfg, params_f, packed_f, w.xyz_f, w.view_f, w.saved_f, w.d_raw_f, n * sf, g_f,
+                              through_z ? w.d_xyz_f : nullptr, w.ws_bwd, mode, stream));
+      }
       if (through_z) {
         NERF_TRY(nerf_encode_samples_bwd_z(cfg, origs4, dirs4, w.z_f, w.d_xyz_f, n, sf, w.d_z_f, 1, stream));
         NERF_TRY(nerf_sample_pdf_bwd(w.w_c, w.z_c, w.u, w.perm, w.d_z_f, n, sc, sf, w.d_w_c, stream));
@@ -252,18 +288,19 @@ int nerf_train_step_fused(const nerf_net_cfg* cfg, const nerf_render_cfg* rc, co
     // coarse backward
     NERF_TRY(nerf_composite_bwd(w.raw_c, w.z_c, w.d_rgb_c, d_w_c, n, sc, w.d_raw_c, nullptr, stream));
     NERF_TRY(nerf_mlp_bwd(cfg, params_c, packed_c, w.xyz_c, w.view_c, w.saved_c, w.d_raw_c, n * sc, g_c, nullptr,
-                          w.ws_bwd, mode, stream));
+                          forked ? w.ws_bwd_c : w.ws_bwd, mode, stream));
+    if (forked) NERF_TRY(stream_wait(st, (cudaStream_t)side_stream));      // the fine network's gradients join here
   }
   if (adam_m) {
     // optimizer.apply_gradients over the variables of both models (:164-167); moments laid out [coarse | fine]
     NERF_TRY(nerf_adam_step(params_c, g_c, adam_m, adam_v, np, tc_cfg->learning_rate, tc_cfg->beta_1, tc_cfg->beta_2,
                             tc_cfg->epsilon, adam_t, stream));
-    if (fine)
+    if (fine && !fine_stepped)
       NERF_TRY(nerf_adam_step(params_f, g_f, adam_m + np, adam_v + np, np, tc_cfg->learning_rate, tc_cfg->beta_1,
                               tc_cfg->beta_2, tc_cfg->epsilon, adam_t, stream));
     if (tc) {
       NERF_TRY(nerf_pack_weights(cfg, params_c, packed_c, stream));
-      if (fine) NERF_TRY(nerf_pack_weights(cfg, params_f, packed_f, stream));
+      if (fine && !fine_stepped) NERF_TRY(nerf_pack_weights(cfg, params_f, packed_f, stream));
     }
   }
   if (metrics4)

@@ -956,8 +956,8 @@ def test_render_fused_entry_point_equals_the_call_sequence(pkg, mode, n_angles, 
 @pytest.mark.parametrize("mode", ["fp32", "bf16"])
 @pytest.mark.parametrize("diet,n_f,stop", [(False, 128, False), (True, 128, False), (False, 0, False), (False, 128, True)])
 def test_train_step_fused_entry_point_equals_the_call_sequence(pkg, mode, diet, n_f, stop):
-    """NeRF.train_step (and DietNeRF's ray loss) through ONE C-ABI call against the host package's sequence (side
-    streams and all), two steps from the same state: gradients, Adam-updated parameters and metrics agree -- bit for
+    """NeRF.train_step (and DietNeRF's ray loss) through ONE C-ABI call (given a side stream like the host package uses,
+    or none) against the host package's sequence, two steps from the same state: gradients, Adam-updated parameters and metrics agree -- bit for
     bit in bf16 mode (deterministic kernels), to fp32 atomics' rounding in the fp32 SIMT mode."""
     n = 192
     cls = pkg.DietNeRFModel if diet else None
@@ -966,6 +966,7 @@ def test_train_step_fused_entry_point_equals_the_call_sequence(pkg, mode, diet, 
     for m in (a, b):
         m.stop_grad_z = stop
         m.compile(optimizer=pkg.Adam(5e-4))
+    b.overlap_dw = not stop              # the C call with the caller's side stream, or (last case) on one stream
     o, d = random_rays(n, 4)
     o, d = dev(o), dev(d)
     exact = mode == "bf16"

@@ -5,7 +5,7 @@
  *
  *   nvcc --cudart shared -o tools/c_caller_demo tools/c_caller_demo.c -Lnerf-and-dietnerf_b200 -lnerf_b200 \
  *        -Xlinker -rpath -Xlinker '$ORIGIN/../nerf-and-dietnerf_b200'          (__graft_entry__.build() does this)
- *   tools/c_caller_demo [steps] [mode: 1 = bf16 (default), 0 = fp32]
+ *   tools/c_caller_demo [steps] [mode: 1 = bf16 (default), 0 = fp32] [anything: no side stream]
  */
 #include <cuda_runtime.h>
 #include <math.h>
@@ -68,8 +68,9 @@ int main(int argc, char** argv) {
   nerf_render_cfg rc = {0.5f, 2.5f, 64, 128, mode};
   nerf_train_cfg tc = {1.0f, 0, 0, 5e-4f, 0.9f, 0.999f, 1e-7f};
   const int64_t np = nerf_param_count(&cfg);
-  cudaStream_t st;
+  cudaStream_t st, side;
   CK(cudaStreamCreate(&st));
+  CK(cudaStreamCreate(&side)); /* optional: the fine network's weight gradients overlap the coarse backward */
 
   /* parameters, Adam moments, gradients, bf16 packs */
   float* host_p = (float*)malloc((size_t)np * sizeof(float));
@@ -127,7 +128,7 @@ int main(int argc, char** argv) {
     nerf_rng_state rng = {7, 0, (uint32_t)s, 0};
     if (s == 1) CK(cudaEventRecord(e0, st));
     NK(nerf_train_step_fused(&cfg, &rc, &tc, params[0], packed[0], params[1], packed[1], origs, dirs, target, n, n, &rng,
-                             grads, adam_m, adam_v, s + 1, metrics, ws, st));
+                             grads, adam_m, adam_v, s + 1, metrics, ws, argc > 3 ? NULL : side, st));
     if (s == 0 || s == steps - 1) {
       CK(cudaMemcpyAsync(s == 0 ? first : last, metrics, 4 * sizeof(float), cudaMemcpyDeviceToHost, st));
       CK(cudaStreamSynchronize(st));

@@ -51,10 +51,16 @@ def main():
         d = torch.rand(n, 4, device="cuda", generator=g) - 0.5
         a = pkg.NeRFModel(net, render, 0.5576, 2.5635, mode="bf16", seed=0).compile(optimizer=pkg.Adam(5e-4))
         b = pkg.NeRFModel(net, render, 0.5576, 2.5635, mode="bf16", seed=0).compile(optimizer=pkg.Adam(5e-4))
-        seq = timed(lambda: a.train_step_local(o, d, y, n), 30)
-        one = timed(lambda: b.train_step_fused(o, d, y), 30)
-        print(f"train step {n} rays x (64 + 128): host package (side streams) {seq[0]:.3f} ms/step (host issue {seq[1]:.3f} ms), "
-              f"nerf_train_step_fused (one stream) {one[0]:.3f} ms/step (host issue {one[1]:.3f} ms)")
+        c = pkg.NeRFModel(net, render, 0.5576, 2.5635, mode="bf16", seed=0).compile(optimizer=pkg.Adam(5e-4))
+        c.overlap_dw = False
+        res = {}
+        for rep in range(2):             # interleaved twice: the power-cap state drifts over a run
+            res["seq"] = timed(lambda: a.train_step_local(o, d, y, n), 30)
+            res["side"] = timed(lambda: b.train_step_fused(o, d, y), 30)
+            res["one"] = timed(lambda: c.train_step_fused(o, d, y), 30)
+            print(f"train step {n} rays x (64 + 128) [pass {rep}]: host package {res['seq'][0]:.3f} ms/step (host issue "
+                  f"{res['seq'][1]:.3f} ms), nerf_train_step_fused with a side stream {res['side'][0]:.3f} ms/step (host issue "
+                  f"{res['side'][1]:.3f} ms), on one stream {res['one'][0]:.3f} ms/step")
 
 
 if __name__ == "__main__":
