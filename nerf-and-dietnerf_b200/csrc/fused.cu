@@ -31,6 +31,9 @@ bool render_cfg_ok(const nerf_render_cfg* rc) {
          (rc->mode == NERF_MODE_FP32 || rc->mode == NERF_MODE_BF16 || rc->mode == NERF_MODE_FP16);
 }
 
+// the tensor-core modes exist for the networks nerf_packed_bytes accepts (view-direction variant, 256/128 wide)
+bool mode_supported(const nerf_net_cfg* cfg, int32_t mode) { return mode == NERF_MODE_FP32 || nerf_packed_bytes(cfg) >= 0; }
+
 // fp32 mode materialises the encodings and needs the GEMM scratch; the tensor-core modes encode inside the MLP kernel
 struct EncodeWs {
   float *xyz, *view;
@@ -155,7 +158,7 @@ extern "C" {
 
 int64_t nerf_render_workspace_bytes(const nerf_net_cfg* cfg, const nerf_render_cfg* rc, int64_t n_rays) {
   NetGeom g;
-  if (!make_geom(cfg, &g) || !render_cfg_ok(rc) || n_rays < 0) return -1;
+  if (!make_geom(cfg, &g) || !render_cfg_ok(rc) || n_rays < 0 || !mode_supported(cfg, rc->mode)) return -1;
   RenderWs w;
   return carve_render(g, cfg, rc, n_rays, nullptr, &w);
 }
@@ -167,6 +170,10 @@ int nerf_render_fused_fwd(const nerf_net_cfg* cfg, const nerf_render_cfg* rc, co
   NetGeom g;
   NERF_CHECK_ARG(make_geom(cfg, &g), "bad network config");
   NERF_CHECK_ARG(render_cfg_ok(rc), "bad render config");
+  if (!mode_supported(cfg, rc->mode)) {
+    set_error("%s: this network has no tensor-core path (use NERF_MODE_FP32)", __func__);
+    return NERF_E_UNSUPPORTED;
+  }
   NERF_CHECK_ARG(origs4 && dirs4 && rng && outs && workspace, "null pointer");
   NERF_CHECK_ARG(n_rays >= 0, "bad ray count");
   const bool tc = rc->mode != NERF_MODE_FP32;
@@ -208,7 +215,9 @@ int nerf_render_fused_fwd(const nerf_net_cfg* cfg, const nerf_render_cfg* rc, co
 
 int64_t nerf_train_workspace_bytes(const nerf_net_cfg* cfg, const nerf_render_cfg* rc, int64_t n_rays) {
   NetGeom g;
-  if (!make_geom(cfg, &g) || !render_cfg_ok(rc) || rc->mode == NERF_MODE_FP16 || n_rays < 0) return -1;
+  if (!make_geom(cfg, &g) || !render_cfg_ok(rc) || rc->mode == NERF_MODE_FP16 || n_rays < 0 ||
+      !mode_supported(cfg, rc->mode))
+    return -1;
   TrainWs w;
   return carve_train(g, cfg, rc, n_rays, nullptr, &w);
 }
@@ -221,6 +230,10 @@ int nerf_train_step_fused(const nerf_net_cfg* cfg, const nerf_render_cfg* rc, co
   NetGeom g;
   NERF_CHECK_ARG(make_geom(cfg, &g), "bad network config");
   NERF_CHECK_ARG(render_cfg_ok(rc) && rc->mode != NERF_MODE_FP16, "bad render config (training runs in FP32 or BF16)");
+  if (!mode_supported(cfg, rc->mode)) {
+    set_error("%s: this network has no tensor-core path (use NERF_MODE_FP32)", __func__);
+    return NERF_E_UNSUPPORTED;
+  }
   NERF_CHECK_ARG(tc_cfg && origs4 && dirs4 && target_rgb && rng && grads && workspace && params_c, "null pointer");
   NERF_CHECK_ARG(n_rays >= 0 && n_total_rays >= n_rays && n_total_rays > 0, "bad ray count");
   const bool tc = rc->mode != NERF_MODE_FP32;
