@@ -12,8 +12,11 @@ oracle is instead pinned against an OUTPUT OF THE REFERENCE ITSELF: the trained 
 ``Results/50px_alexander_71pics_sphere_nerf_save_dir_4/saved_weights/NeRF_model_epoch_095.h5`` and the
 test-image PSNR the reference recorded for them (``saved_test_train_psnrs/psnrs_train_test_095.npy``,
 27.83 dB @ epoch 95); tests/golden/make_golden.py renders that image with this oracle and
-tests/test_oracle_pin.py checks the PSNR (see DESIGN.md "Oracle pin").  Everything finer than that
-(bit-level behaviour of TF kernels) is unpinned and stated as such.
+tests/test_oracle_pin.py checks the PSNR (see DESIGN.md "Oracle pin").  A second pin holds it against
+PIXELS the reference rendered: frames decoded from the videos of that run (``video_save/*.avi``;
+tests/golden/make_alexander50_videos.py -> alexander50_videos.npz) are reproduced by this oracle at
+36-43 dB rgb / 36-41 dB equalised depth (tests/test_video.py; the rest is MJPG loss and unseeded
+jitter).  Everything finer than that (bit-level behaviour of TF kernels) is unpinned and stated as such.
 
 Random inputs are explicit arguments (``jitter``, ``u``) or come from oracle.philox so the CUDA
 kernels can be driven with the identical stream.

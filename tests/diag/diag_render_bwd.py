@@ -2,7 +2,7 @@
 importance sampler) under bf16 operand rounding?  Compares oracle fp32 / oracle bf16-emulated / CUDA fp32 / CUDA bf16."""
 import importlib, os, sys
 import torch
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 from helpers import FAR, NEAR, net_config, oracle_cfg, random_rays, render_config, make_params
 from oracle import nerf_oracle as O

@@ -2,7 +2,7 @@
 bf16-emulating oracle vs the fp32 oracle, with and without the sampler path (stop_grad_z)."""
 import importlib, os, sys
 import numpy as np, torch
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 import __graft_entry__ as E
 from oracle import nerf_oracle as O

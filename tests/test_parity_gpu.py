@@ -461,7 +461,7 @@ def test_train_step_gradients(pkg, mode, tol, diet):
         assert rel_c < tol, rel_c
     else:
         # Through the importance sampler the coarse gradient is dominated by a few rays with near-empty cdf bins and is
-        # not reproducible between two evaluations that differ by rounding (tools/diag_smoke.py: two fp32 evaluations
+        # not reproducible between two evaluations that differ by rounding (tests/diag/diag_smoke.py: two fp32 evaluations
         # differ by 30 % at this sigma gain).  So: a loose bound on the full path, and the tight comparison with the
         # importance samples detached on BOTH sides (oracle knob stop_grad_z; not the reference's behaviour).
         assert rel_c < 0.5, rel_c
@@ -608,7 +608,7 @@ def test_render_backward_matches_oracle_autograd(pkg, mode, tol, n_f):
     n, n_c = 200, 55
     # sigma gain 30 in both modes: on this path the coarse network is reached ONLY through the importance sampler, and
     # with soft densities (gain <= 4) that gradient is ill-conditioned under 16-bit operands -- the oracle with bf16
-    # rounding then differs from the fp32 oracle by several times the gradient's norm (tools/diag_render_bwd.py), so
+    # rounding then differs from the fp32 oracle by several times the gradient's norm (tests/diag/diag_render_bwd.py), so
     # no implementation can be compared there.  Opaque surfaces keep it well conditioned.
     model, ocfg, pc, pf = _model(pkg, mode, n_c=n_c, n_f=n_f, sigma_gain=30.0)
     o, d = random_rays(n, 11)
