@@ -140,7 +140,7 @@ class ExecutionRun:
         n_batches = get_num_of_batches(self.net_config[N_RAYS_IN_BATCH_TRAIN], len(train_images), h, w)
         n_steps = n_batches * (self.training_config[N_EPOCHS] - self._epoch_number)
         n_steps *= DietNeRF.PERCENTAGE_OF_TRAIN_STEPS_WITH_CONSISTENCY_LOSS
-        point, spherical = estimate_point_of_interest_in_scene(self.camera_poses, rng=np.random.RandomState(self.seed))
+        point, spherical = self._point_of_interest()
         rot = None
         if spherical:
             rot = np.eye(4)
