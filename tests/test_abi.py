@@ -120,3 +120,29 @@ def test_c_caller_links_and_fails_loudly_without_a_gpu(pkg):
         pytest.skip("a GPU is present: the run itself is test_c_caller_trains_and_renders")
     r = subprocess.run([entry.C_DEMO, "3"], capture_output=True, text=True, timeout=60)
     assert r.returncode in (2, 3) and r.stdout.strip() == "" and ("CUDA" in r.stderr or "cuda" in r.stderr)
+
+
+def test_ctypes_structs_match_the_header(pkg, tmp_path):
+    """sizeof / offsetof of every struct of include/nerf_b200.h as gcc lays them out == the ctypes mirrors in _lib.py."""
+    import subprocess
+    L = pkg._lib
+    structs = {"nerf_net_cfg": L.NetCfg, "nerf_render_cfg": L.RenderCfg, "nerf_rng_state": L.RngState,
+               "nerf_render_outs": L.RenderOuts, "nerf_train_cfg": L.TrainCfg}
+    lines = []
+    for cname, mirror in structs.items():
+        lines.append(f'printf("{cname} %zu", sizeof({cname}));')
+        for field, _ in mirror._fields_:
+            lines.append(f'printf(" %zu", offsetof({cname}, {field}));')
+        lines.append('printf("\\n");')
+    src = tmp_path / "layout.c"
+    src.write_text('#include <stddef.h>\n#include <stdio.h>\n#include "nerf_b200.h"\nint main(void) {\n' + "\n".join(lines) +
+                   "\nreturn 0;\n}\n")
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-std=c99", "-I", os.path.join(ROOT, "include"), "-o", str(exe), str(src)], check=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.strip().splitlines()
+    assert len(out) == len(structs)
+    for line in out:
+        name, size, *offsets = line.split()
+        mirror = structs[name]
+        assert ctypes.sizeof(mirror) == int(size), name
+        assert [getattr(mirror, f).offset for f, _ in mirror._fields_] == [int(o) for o in offsets], name
