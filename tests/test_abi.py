@@ -146,3 +146,31 @@ def test_ctypes_structs_match_the_header(pkg, tmp_path):
         mirror = structs[name]
         assert ctypes.sizeof(mirror) == int(size), name
         assert [getattr(mirror, f).offset for f, _ in mirror._fields_] == [int(o) for o in offsets], name
+
+
+def test_mlp_kernels_are_tcgen05_kernels(pkg):
+    """Static check of the built library (cuobjdump, no GPU): the three MLP kernels issue tcgen05.mma (SASS UTC*MMA), read
+    TMEM (LDTM) and move operands with the TMA engine's bulk copies (UBLKCP); no kernel falls back to legacy mma.sync
+    (HMMA) -- the guide's 'what proves a Blackwell-native kernel'."""
+    import re
+    import shutil
+    import subprocess
+    if shutil.which("cuobjdump") is None:
+        pytest.skip("cuobjdump not on PATH")
+    sass = subprocess.run(["cuobjdump", "-sass", pkg.LIB_PATH], capture_output=True, text=True, check=True).stdout
+    per_kernel, cur = {}, None
+    for line in sass.splitlines():
+        m = re.match(r"\s*Function : (\S+)", line)
+        if m:
+            cur = m.group(1)
+            per_kernel[cur] = []
+        elif cur and "/*" in line:
+            per_kernel[cur].append(line)
+    assert len(per_kernel) >= 40
+    assert not any(re.search(r"\bHMMA", l) for body in per_kernel.values() for l in body)
+    for stem in ("mlp_tc_fwd_kernel", "mlp_tc_bwd_chain_kernel", "mlp_tc_bwd_dw_kernel"):
+        bodies = [b for k, b in per_kernel.items() if stem in k]
+        assert bodies, stem
+        for body in bodies:
+            text = "\n".join(body)
+            assert re.search(r"\bUTC[A-Z]*MMA", text) and "LDTM" in text and "UBLKCP" in text, stem
