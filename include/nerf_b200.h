@@ -251,7 +251,8 @@ int nerf_render_fused_fwd(const nerf_net_cfg* cfg, const nerf_render_cfg* rc, co
  * side_stream_or_null: a second stream of the caller's (tensor-core mode with a fine network): the fine network's
  * HBM-bound weight-gradient kernel, its Adam step and pack refresh are enqueued there, under the coarse backward, and
  * joined before the call's last kernels; everything the call enqueued is complete when `stream` reaches its end.
- * Same results with and without it. */
+ * Same results with and without it.  After an error return the work already enqueued on the two streams is not
+ * joined: synchronise both before reusing the buffers. */
 int64_t nerf_train_workspace_bytes(const nerf_net_cfg* cfg, const nerf_render_cfg* rc, int64_t n_rays);
 int nerf_train_step_fused(const nerf_net_cfg* cfg, const nerf_render_cfg* rc, const nerf_train_cfg* tc,
                           float* params_c, void* packed_c, float* params_f, void* packed_f, const float* origs4,
