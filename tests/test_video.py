@@ -339,3 +339,31 @@ def test_trajectories_on_a_forward_facing_and_a_blender_scene():
         bare.get_l_to_r_c2w_matrices_to_render()
     with pytest.raises(Exception, match="save"):
         run.render_video(poses[:1], "x", "a.avi", "b.avi", model=object())
+
+
+def test_pose_helper_properties():
+    """Property checks over random rotations (hypothesis): source->dest rotation, vector-to-vector rotation, slerp
+    end points / orthonormality, quaternion <-> matrix round trip (all four branches of the conversion)."""
+    from hypothesis import given, settings, strategies as st
+    P = importlib.import_module("nerf-and-dietnerf_b200").poses
+    angle = st.floats(min_value=-360.0, max_value=360.0, allow_nan=False)
+
+    @settings(max_examples=60, deadline=None)
+    @given(angle, angle, angle, angle, angle, angle, st.floats(min_value=0.0, max_value=1.0))
+    def check(ax, ay, az, bx, by, bz, t):
+        a, b = P.get_sphere_matrix(1.0, ax, ay, az), P.get_sphere_matrix(0.7, bx, by, bz)
+        ra, rb = a[:3, :3], b[:3, :3]
+        assert np.abs(ra @ ra.T - np.eye(3)).max() < 1e-12 and abs(np.linalg.det(ra) - 1) < 1e-12
+        q = P.quaternion_from_rotation_matrix(ra)
+        assert np.abs(P.rotation_matrix_from_quaternion(q / np.linalg.norm(q)) - ra).max() < 1e-9
+        r = P.get_rotation_matrix_from_source_to_dest_mats(ra, rb)
+        assert np.abs(r[:3, :3] @ ra - rb).max() < 1e-9
+        m = P.interpolation_type_slerp_for_c2w(a, b, t)
+        assert np.abs(m[:3, :3] @ m[:3, :3].T - np.eye(3)).max() < 1e-5
+        assert np.allclose(m[:3, 3], a[:3, 3] * (1 - t) + b[:3, 3] * t, atol=1e-6)
+        v1, v2 = ra[:, 0] * 2.5, rb[:, 2] * 0.3
+        rot = P.get_rotation_matrix_from_v1_to_v2(v1, v2)
+        assert np.abs(rot @ (v1 / np.linalg.norm(v1)) - v2 / np.linalg.norm(v2)).max() < 1e-6
+    check()
+    for m0, m1 in ((P.get_sphere_matrix(1, 10, 20, 30), P.get_sphere_matrix(1, 10, 20, 30)),):
+        assert np.abs(P.interpolation_type_slerp_for_c2w(m0, m1, 0.4) - m0).max() < 1e-6     # identical poses: no 0/0
