@@ -367,3 +367,20 @@ def test_pose_helper_properties():
     check()
     for m0, m1 in ((P.get_sphere_matrix(1, 10, 20, 30), P.get_sphere_matrix(1, 10, 20, 30)),):
         assert np.abs(P.interpolation_type_slerp_for_c2w(m0, m1, 0.4) - m0).max() < 1e-6     # identical poses: no 0/0
+
+
+def test_histogram_equalize_frames_property():
+    """Random small frames, including few-valued ones where the rounded gray sits on .5 ties: the torch version and
+    the NumPy restatement always give the same levels."""
+    from hypothesis import given, settings, strategies as st
+    from hypothesis.extra import numpy as hnp
+    U = importlib.import_module("nerf-and-dietnerf_b200").UtilsCV
+
+    @settings(max_examples=80, deadline=None)
+    @given(hnp.arrays(np.float32, hnp.array_shapes(min_dims=2, max_dims=2, min_side=1, max_side=9),
+                      elements=st.one_of(st.floats(0.25, 3.0, width=32), st.sampled_from([0.5, 1.0, 1.5, 2.0, 2.5]))))
+    def check(frame):
+        levels = U.histogram_equalize_frames(torch.from_numpy(frame)[None])[0].numpy()
+        eq = U.histogram_equalize(frame)[0]
+        assert np.array_equal(levels, np.uint8(np.round(np.asarray(eq, dtype=np.float64) * 255)))
+    check()
