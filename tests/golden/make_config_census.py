@@ -16,5 +16,6 @@ for path in sorted(glob.glob("/root/reference/config_files/*.yaml")):
         out[os.path.basename(path)] = {"unparseable": str(e).splitlines()[0]}
         continue
     out[os.path.basename(path)] = {k: cfg[k] for k in ("dataset_type", "neural_net", "render", "training")}
+    out[os.path.basename(path)].update({k: cfg.get(k) for k in ("tasks_to_perform", "video")})
 json.dump(out, open(os.path.join(ROOT, "tests/golden/config_census.json"), "w"), indent=0, sort_keys=True)
 print(len(out), "configs")

@@ -384,3 +384,39 @@ def test_histogram_equalize_frames_property():
         eq = U.histogram_equalize(frame)[0]
         assert np.array_equal(levels, np.uint8(np.round(np.asarray(eq, dtype=np.float64) * 255)))
     check()
+
+
+def test_task_switchboard_and_trajectories_for_every_reference_config(monkeypatch):
+    """Every parseable YAML of the reference (tests/golden/config_census.json): ``start()`` runs exactly the tasks its
+    ``tasks_to_perform`` switches on (of the ones in scope: training, three rendered videos, dataset video), in the
+    reference's order, and the trajectory builders give fps*5, 2*fps*6 and len(indices)*fps*2 poses for its ``video:``
+    block."""
+    pkg = importlib.import_module("nerf-and-dietnerf_b200")
+    census = json.load(open(os.path.join(GOLD, "config_census.json")))
+    poses = np.asarray([pkg.poses.get_sphere_matrix(1.0, x, y, 0) for x in (-30, 0, 30) for y in range(0, 360, 15)],
+                       dtype=np.float32)                                         # 72 views looking at the origin
+    images = np.zeros((len(poses), 4, 4, 3), dtype=np.float32)
+    order = ["_training", "render_l_to_r_test_video", "render_sphere_test_video_with_net_weights",
+             "render_path_test_video_with_net_weights", "save_dataset_video"]
+    keys = ["start_training", "render_and_save_test_left_to_right_video", "render_and_save_test_sphere_video",
+            "render_and_save_test_path_video", "save_dataset_video"]
+    checked = 0
+    for name, cfg in sorted(census.items()):
+        if "unparseable" in cfg or not cfg.get("video"):
+            continue
+        run = pkg.ExecutionRun.from_arrays(dict(cfg), images, poses, 0.6, 0.5, 2.5)
+        calls = []
+        for method in order:
+            monkeypatch.setattr(run, method, lambda *a, _m=method, **k: calls.append(_m))
+        run.start()
+        expected = [m for m, k in zip(order, keys) if (cfg.get("tasks_to_perform") or {}).get(k, False)]
+        assert calls == expected, name
+        fps = cfg["video"]["fps_render_video"]
+        run._poi = (np.zeros(3), True)                 # the synthetic cameras look at the origin; skip the RANSAC
+        assert len(run.get_l_to_r_c2w_matrices_to_render()) == fps * 5, name
+        assert len(run.get_sphere_c2w_matrices_to_render()) == 2 * int(fps * 6), name
+        indices = cfg["video"].get("img_indices_for_path_video")
+        if indices and max(indices) < len(poses):
+            assert len(run.get_path_c2w_matrices_to_render()) == len(indices) * int(fps * 2), name
+        checked += 1
+    assert checked >= 40
