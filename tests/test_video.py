@@ -420,3 +420,36 @@ def test_task_switchboard_and_trajectories_for_every_reference_config(monkeypatc
             assert len(run.get_path_c2w_matrices_to_render()) == len(indices) * int(fps * 2), name
         checked += 1
     assert checked >= 40
+
+
+class _StubModel:
+    """A 'model' whose render is a function of the pose only -- lets start() run its video tasks without a GPU."""
+    device = torch.device("cpu")
+
+    def render_image_lean(self, c2w, fov, h, w):
+        k = float(np.abs(np.asarray(c2w)[:3, 3]).sum())
+        yy, xx = torch.meshgrid(torch.arange(h, dtype=torch.float32), torch.arange(w, dtype=torch.float32), indexing="ij")
+        rgb = torch.stack([(xx / w + k) % 1.0, (yy / h + 0.5 * k) % 1.0, torch.full_like(xx, k % 1.0)], -1)
+        return rgb.reshape(-1, 3), (1.0 + xx * 0.1 + yy * yy * 0.01 + k).reshape(-1), torch.ones(h * w)
+
+
+def test_start_writes_the_reference_video_files(tmp_path, monkeypatch, videos):
+    """All four video tasks through start(): the files under video_save/ carry the names of the reference's recorded
+    run, the frame counts follow fps (2 here: 10 / 24 / 8 frames), rgb and depth videos have equal lengths."""
+    pkg, run = alexander_run(save_location=tmp_path, tasks={
+        "render_and_save_test_left_to_right_video": True, "render_and_save_test_sphere_video": True,
+        "render_and_save_test_path_video": True, "save_dataset_video": True})
+    run.video_properties = {"fps_render_video": 2, "fps_train_set_video": 5, "img_indices_for_path_video": [4, 7]}
+    monkeypatch.setattr(run, "get_nerf", lambda: _StubModel())
+    run.start()
+    written = sorted(os.listdir(tmp_path / "video_save"))
+    recorded = sorted({k.split("__")[0] + ".avi" for k in videos.files})
+    assert written == recorded and len(written) == 7
+    for stem, n in (("l_to_r", 10), ("sphere", 24), ("path", 8)):
+        names = [w for w in written if stem in w]
+        assert len(names) == 2
+        for name in names:
+            frames, fps = pkg.UtilsVideo.read_video_frames(tmp_path / "video_save" / name)
+            assert frames.shape == (n, 50, 50, 3) and fps == 2, name
+    depth, _ = pkg.UtilsVideo.read_video_frames(tmp_path / "video_save" / "render_depths_sphere_video.avi")
+    assert depth.min() < 16 and depth.max() > 239                      # equalised: the levels span the range
