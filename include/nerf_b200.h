@@ -132,6 +132,17 @@ int nerf_mlp_bwd_dw(const nerf_net_cfg* cfg, const float* params, const void* pa
                     const float* xyz_enc, const float* view_enc, const void* saved, const float* d_out4,
                     int64_t m, float* grads, float* d_xyz_enc_or_null, void* workspace, int32_t mode,
                     void* stream);
+/* nerf_mlp_bwd with its two halves running AT THE SAME TIME (NERF_MODE_BF16): the input-gradient chain on `stream`, the
+ * weight-gradient kernel and its reduction on `side_stream`, on disjoint SMs, every dZ block handed over through a ready
+ * counter in the workspace so that the weight-gradient kernel reads it from L2 instead of from HBM a kernel later.
+ * d_xyz_enc is complete at the end of `stream`, `grads` at the end of `side_stream`: the caller joins the two.
+ * side_stream null or == stream, or NERF_MODE_FP32: identical to nerf_mlp_bwd (everything on `stream`).  The split-K
+ * partition of the weight gradients follows the number of SMs the kernel gets, so the two variants agree to fp32
+ * rounding, not bit for bit.  Replaces TF autodiff of the Keras models in NeRF.train_step (src/NeRF.py:149-167). */
+int nerf_mlp_bwd_overlapped(const nerf_net_cfg* cfg, const float* params, const void* packed_or_null,
+                            const float* xyz_enc, const float* view_enc, const void* saved, const float* d_out4,
+                            int64_t m, float* grads, float* d_xyz_enc_or_null, void* workspace, int32_t mode,
+                            void* side_stream, void* stream);
 /* bf16 weight pack for the tensor-core path (re-run after every optimizer step). */
 int64_t nerf_packed_bytes(const nerf_net_cfg* cfg);
 int nerf_pack_weights(const nerf_net_cfg* cfg, const float* params, void* packed, void* stream);

@@ -506,9 +506,10 @@ class NeRF:
                 d_w_c = w.d_w_c
         # coarse backward
         call("nerf_composite_bwd", ptr(w.raw_c), ptr(w.z_c), ptr(w.d_rgb_c), ptr(d_w_c), n, sc, ptr(w.d_raw_c), None)
-        self._mlp_bwd(mc, w.xyz_c, w.view_c, w.saved_c, w.d_raw_c, n * sc, g_c, None, w.ws_bwd_c)
-        if mf is not None and self._side is not None:
-            torch.cuda.current_stream().wait_stream(self._side)      # the fine weight gradients join here
+        self._mlp_bwd(mc, w.xyz_c, w.view_c, w.saved_c, w.d_raw_c, n * sc, g_c, None, w.ws_bwd_c,
+                      side_stream=self._side_stream())
+        if self._side is not None:
+            torch.cuda.current_stream().wait_stream(self._side)      # the weight gradients of both networks join here
         return g_c, g_f, sums
 
     def render_backward(self, rays_orig, rays_dirs, d_rgb, n_render_samples_c=None, n_render_samples_f=None, *,
@@ -537,7 +538,10 @@ class NeRF:
              None)
         if mf is None:
             call("nerf_composite_bwd", ptr(w.raw_c), ptr(w.z_c), ptr(d_rgb), None, n, sc, ptr(w.d_raw_c), None)
-            self._mlp_bwd(mc, w.xyz_c, w.view_c, w.saved_c, w.d_raw_c, n * sc, g_c, None, w.ws_bwd_c)
+            self._mlp_bwd(mc, w.xyz_c, w.view_c, w.saved_c, w.d_raw_c, n * sc, g_c, None, w.ws_bwd_c,
+                          side_stream=self._side_stream())
+            if self._side is not None:
+                torch.cuda.current_stream().wait_stream(self._side)
             return w.rgb_c
         call("nerf_sample_pdf_fwd", ptr(w.w_c), ptr(w.z_c), n, sc, nf, ptr(u), seed, step, ray_offset, ptr(w.z_new),
              None, ptr(w.perm), ptr(w.u))
@@ -560,7 +564,8 @@ class NeRF:
             w.d_rgb_c.zero_()
             call("nerf_composite_bwd", ptr(w.raw_c), ptr(w.z_c), ptr(w.d_rgb_c), ptr(w.d_w_c), n, sc, ptr(w.d_raw_c),
                  None)
-            self._mlp_bwd(mc, w.xyz_c, w.view_c, w.saved_c, w.d_raw_c, n * sc, g_c, None, w.ws_bwd_c)
+            self._mlp_bwd(mc, w.xyz_c, w.view_c, w.saved_c, w.d_raw_c, n * sc, g_c, None, w.ws_bwd_c,
+                          side_stream=self._side_stream())
         if self._side is not None:
             torch.cuda.current_stream().wait_stream(self._side)
         return w.rgb_f
@@ -591,21 +596,16 @@ class NeRF:
 
     @staticmethod
     def _mlp_bwd(net, xyz, view, saved, d_raw, m, grads, d_xyz, ws, side_stream=None):
-        """TF autodiff of one Keras model (src/NeRF.py:149-167).  The tensor-core path runs its two halves as separate
-        C-ABI calls (input-gradient chain, then weight gradients); with ``side_stream`` the second half is issued there
-        (after the first) and the stream is returned for the caller to join."""
+        """TF autodiff of one Keras model (src/NeRF.py:149-167).  With ``side_stream`` the tensor-core path runs its two
+        halves AT THE SAME TIME (``nerf_mlp_bwd_overlapped``): the input-gradient chain on the current stream, the
+        weight-gradient kernel on ``side_stream`` on the SMs the chain leaves free, dZ handed over through L2.  The stream
+        is returned for the caller to join before it reads ``grads``."""
         args = (net.cfg_ref, ptr(net.params), ptr(net.packed_for(net.params)), ptr(xyz), ptr(view), ptr(saved), ptr(d_raw), m,
                 ptr(grads), ptr(d_xyz), ptr(ws), net.mode_id)
-        if net.mode_id == MODE_BF16:
-            call("nerf_mlp_bwd_dx", *args)
-            if side_stream is not None:
-                side_stream.wait_stream(torch.cuda.current_stream())
-                with torch.cuda.stream(side_stream):
-                    call("nerf_mlp_bwd_dw", *args)
-                return side_stream
-            call("nerf_mlp_bwd_dw", *args)
-        else:
-            call("nerf_mlp_bwd", *args)
+        if net.mode_id == MODE_BF16 and side_stream is not None:
+            call("nerf_mlp_bwd_overlapped", *args, side_stream.cuda_stream)
+            return side_stream
+        call("nerf_mlp_bwd", *args)
         return None
 
     def _mlp_fwd_train(self, net, o, d, z, n, s, xyz, view, raw, saved, ws):

@@ -36,7 +36,14 @@ void set_error(const char* fmt, ...);
     }                                                                                    \
   } while (0)
 
-constexpr int kNumSMs = 148;  // B200
+constexpr int kMaxSMs = 160;  // upper bound used for scratch sizing (B200: 148)
+
+// SM count of the CURRENT device (cudaDeviceGetAttribute, cached per device; 148 when no device is reachable, so that the
+// host-only size queries keep working on a CPU box).
+int num_sms();
+// true exactly once per (current device, slot): guards per-device one-time setup such as cudaFuncSetAttribute
+// (thread-safe; the ABI is re-entrant per (device, stream)).  Slots: 0 = forward kernels, 1 = backward kernels.
+bool device_first_use(int slot);
 
 inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 

@@ -274,13 +274,11 @@ int nerf_train_step_fused(const nerf_net_cfg* cfg, const nerf_render_cfg* rc, co
       NERF_TRY(nerf_composite_mse_fwd_bwd(w.raw_f, w.z_f, target_rgb, n, sf, n_total_rays, 1.0f, nullptr, sums + 1,
                                           w.d_raw_f, through_z ? w.d_z_f : nullptr, stream));
       if (use_side) {
-        // input-gradient chain here; the HBM-bound weight-gradient kernel, the fine network's Adam step and the refresh
-        // of its bf16 pack go to the side stream and run under the sampler / compositing / coarse backward below
-        NERF_TRY(nerf_mlp_bwd_dx(cfg, params_f, packed_f, w.xyz_f, w.view_f, w.saved_f, w.d_raw_f, n * sf, g_f,
-                                 through_z ? w.d_xyz_f : nullptr, w.ws_bwd, mode, stream));
-        NERF_TRY(stream_wait((cudaStream_t)side_stream, st));
-        NERF_TRY(nerf_mlp_bwd_dw(cfg, params_f, packed_f, w.xyz_f, w.view_f, w.saved_f, w.d_raw_f, n * sf, g_f,
-                                 through_z ? w.d_xyz_f : nullptr, w.ws_bwd, mode, side_stream));
+        // input-gradient chain here, the weight-gradient kernel AT THE SAME TIME on the side stream (disjoint SMs, dZ handed
+        // over through L2); the fine network's Adam step and the refresh of its bf16 pack follow it there and run under
+        // the sampler / compositing / coarse backward below
+        NERF_TRY(nerf_mlp_bwd_overlapped(cfg, params_f, packed_f, w.xyz_f, w.view_f, w.saved_f, w.d_raw_f, n * sf, g_f,
+                                         through_z ? w.d_xyz_f : nullptr, w.ws_bwd, mode, side_stream, stream));
         if (adam_m) {
           NERF_TRY(nerf_adam_step(params_f, g_f, adam_m + np, adam_v + np, np, tc_cfg->learning_rate, tc_cfg->beta_1,
                                   tc_cfg->beta_2, tc_cfg->epsilon, adam_t, side_stream));
@@ -300,9 +298,10 @@ int nerf_train_step_fused(const nerf_net_cfg* cfg, const nerf_render_cfg* rc, co
     }
     // coarse backward
     NERF_TRY(nerf_composite_bwd(w.raw_c, w.z_c, w.d_rgb_c, d_w_c, n, sc, w.d_raw_c, nullptr, stream));
-    NERF_TRY(nerf_mlp_bwd(cfg, params_c, packed_c, w.xyz_c, w.view_c, w.saved_c, w.d_raw_c, n * sc, g_c, nullptr,
-                          forked ? w.ws_bwd_c : w.ws_bwd, mode, stream));
-    if (forked) NERF_TRY(stream_wait(st, (cudaStream_t)side_stream));      // the fine network's gradients join here
+    const bool side_c = tc && side_stream != nullptr && side_stream != stream;
+    NERF_TRY(nerf_mlp_bwd_overlapped(cfg, params_c, packed_c, w.xyz_c, w.view_c, w.saved_c, w.d_raw_c, n * sc, g_c, nullptr,
+                                     forked ? w.ws_bwd_c : w.ws_bwd, mode, side_c ? side_stream : nullptr, stream));
+    if (forked || side_c) NERF_TRY(stream_wait(st, (cudaStream_t)side_stream));   // the weight gradients join here
   }
   if (adam_m) {
     // optimizer.apply_gradients over the variables of both models (:164-167); moments laid out [coarse | fine]

@@ -11,7 +11,7 @@ int mlp_tc_fwd(const nerf_net_cfg* cfg, const NetGeom& g, const float* params, c
                const float* view_enc, int64_t m, float* out4, void* saved, void* workspace, cudaStream_t st, bool half);
 int mlp_tc_bwd(const nerf_net_cfg* cfg, const NetGeom& g, const float* params, const void* packed, const float* xyz_enc,
                const float* view_enc, const void* saved, const float* d_out4, int64_t m, float* grads, float* d_xyz_enc,
-               void* workspace, cudaStream_t st, int parts);
+               void* workspace, cudaStream_t st, int parts, cudaStream_t side);
 int mlp_tc_fwd_rays(const nerf_net_cfg* cfg, const NetGeom& g, const void* packed, const float* origs4, const float* dirs4,
                     const float* z, int64_t n_rays, int n_samples, float* out4, void* saved, cudaStream_t st, bool half);
 int64_t mlp_tc_saved_bytes(const NetGeom& g, int64_t m);
@@ -172,7 +172,7 @@ static int gemm(cudaStream_t st, bool transb, const float* A, int lda, const flo
 static int gemm_tn(cudaStream_t st, const float* A, int lda, const float* B, int ldb, float* dW, int ldw, float* db,
                    int64_t M, int N, int K) {
   int kt = (int)ceil_div(K, TK), nt = (int)ceil_div(N, TN);
-  int64_t target_splits = max((int64_t)1, (int64_t)(kNumSMs * 4) / (kt * nt));
+  int64_t target_splits = max((int64_t)1, (int64_t)(num_sms() * 4) / (kt * nt));
   int64_t rows = ceil_div(ceil_div(M, target_splits), TM) * TM;
   if (rows < 256) rows = 256;
   int64_t splits = ceil_div(M, rows);
@@ -378,7 +378,8 @@ int nerf_mlp_fwd_rays(const nerf_net_cfg* cfg, const void* packed, const float* 
 // and the dZ workspace.  The fp32 path computes both in one pass (parts must be 3).
 static int mlp_bwd_parts(const nerf_net_cfg* cfg, const float* params, const void* packed_or_null, const float* xyz_enc,
                          const float* view_enc, const void* saved, const float* d_out4, int64_t m, float* grads,
-                         float* d_xyz_enc_or_null, void* workspace, int32_t mode, void* stream, int parts) {
+                         float* d_xyz_enc_or_null, void* workspace, int32_t mode, void* stream, int parts,
+                         void* side_stream = nullptr) {
   NetGeom g;
   NERF_CHECK_ARG(make_geom(cfg, &g), "bad net config");
   NERF_CHECK_ARG(params && saved && d_out4 && grads && workspace, "null pointer");
@@ -391,7 +392,7 @@ static int mlp_bwd_parts(const nerf_net_cfg* cfg, const float* params, const voi
   if (mode == NERF_MODE_BF16) {
     NERF_CHECK_ARG(packed_or_null, "NERF_MODE_BF16 needs the packed weights (nerf_pack_weights)");
     return mlp_tc_bwd(cfg, g, params, packed_or_null, xyz_enc, view_enc, saved, d_out4, m, grads, d_xyz_enc_or_null,
-                      workspace, (cudaStream_t)stream, parts);
+                      workspace, (cudaStream_t)stream, parts, (cudaStream_t)side_stream);
   }
   fp32_bwd(cfg, g, params, xyz_enc, view_enc, (const float*)saved, d_out4, m, grads, d_xyz_enc_or_null,
            (float*)workspace, (cudaStream_t)stream);
@@ -404,6 +405,13 @@ int nerf_mlp_bwd(const nerf_net_cfg* cfg, const float* params, const void* packe
                  float* d_xyz_enc_or_null, void* workspace, int32_t mode, void* stream) {
   return mlp_bwd_parts(cfg, params, packed_or_null, xyz_enc, view_enc, saved, d_out4, m, grads, d_xyz_enc_or_null, workspace,
                        mode, stream, 3);
+}
+
+int nerf_mlp_bwd_overlapped(const nerf_net_cfg* cfg, const float* params, const void* packed_or_null, const float* xyz_enc,
+                            const float* view_enc, const void* saved, const float* d_out4, int64_t m, float* grads,
+                            float* d_xyz_enc_or_null, void* workspace, int32_t mode, void* side_stream, void* stream) {
+  return mlp_bwd_parts(cfg, params, packed_or_null, xyz_enc, view_enc, saved, d_out4, m, grads, d_xyz_enc_or_null, workspace,
+                       mode, stream, 3, mode == NERF_MODE_BF16 ? side_stream : nullptr);
 }
 
 int nerf_mlp_bwd_dx(const nerf_net_cfg* cfg, const float* params, const void* packed_or_null, const float* xyz_enc,

@@ -663,7 +663,7 @@ int64_t mlp_tc_workspace_bytes(const NetGeom& g, int64_t m, int backward) {
   if (!backward) return 256;
   int64_t tiles = (m + kTileM - 1) / kTileM;
   tiles = (tiles + 3) / 4 * 4;
-  return tiles * (int64_t)kDzTileBytes + 1024 + kDwScratchBytes;
+  return tiles * (int64_t)kDzTileBytes + 1024 + kDwScratchBytes + mlp_tc_bwd_flag_bytes(m);
 }
 
 // byte offset of the fp16 copy of the forward weight pack inside the packed buffer: [bf16 fwd | bf16 bwd | fp16 fwd]
@@ -679,15 +679,14 @@ static int launch_fwd(const nerf_net_cfg* cfg, const NetGeom& g, const void* pac
               "0 <= leaky_relu_alpha <= 1");
     return NERF_E_UNSUPPORTED;
   }
-  static bool attr_set = false;
-  if (!attr_set) {
+  if (device_first_use(0)) {               // per device: the attribute lives in the device's copy of the function
     NERF_CUDA(cudaFuncSetAttribute(mlp_tc_fwd_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemAlloc));
     NERF_CUDA(cudaFuncSetAttribute(mlp_tc_fwd_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemAlloc));
     NERF_CUDA(cudaFuncSetAttribute(mlp_tc_fwd_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemAlloc));
-    attr_set = true;
   }
   int64_t n_quads = ((m + kTileM - 1) / kTileM + 3) / 4;
-  int grid = 2 * (int)(n_quads < kNumSMs / 2 ? n_quads : kNumSMs / 2);     // CTA pairs
+  const int n_pairs = num_sms() / 2;
+  int grid = 2 * (int)(n_quads < n_pairs ? n_quads : n_pairs);             // CTA pairs
   if (half) {
     if (saved) { set_error("NERF_MODE_FP16 is a forward-only (render) mode: train in NERF_MODE_BF16"); return NERF_E_UNSUPPORTED; }
     mlp_tc_fwd_kernel<false, true><<<grid, kThreadsFwd, kSmemAlloc, st>>>(

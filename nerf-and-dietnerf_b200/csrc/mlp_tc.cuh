@@ -140,7 +140,10 @@ uint32_t tc_debug_flags();
 
 // dW split-K partials (backward workspace, after the dZ tiles): one 256 x 256 fp32 block + 256 bias sums per dW CTA
 constexpr int64_t kDwPartialFloats = 256 * 256 + 256;
-constexpr int64_t kDwScratchBytes = (int64_t)148 * kDwPartialFloats * 4;
+constexpr int64_t kDwScratchBytes = (int64_t)kMaxSMs * kDwPartialFloats * 4;
+
+// bytes of the per-(tile, block) dZ ready counters at the end of the backward workspace (overlapped mode)
+int64_t mlp_tc_bwd_flag_bytes(int64_t m);
 
 // backward half of the bf16 weight pack (defined in mlp_tc_bwd.cu)
 uint32_t bwd_pack_bytes();

@@ -16,9 +16,44 @@
 //      warps sum the bias gradients from the dZ stages in shared memory, and each CTA writes its partial result to a
 //      split-K scratch block; mlp_tc_bwd_dw_reduce_kernel adds the partials of a unit in a FIXED order into the flat
 //      gradient vector (deterministic, and 4x cheaper than the 9.7 M fp32 atomics it replaces).  HBM-bound, see DESIGN.md.
+//
+//  Overlapped mode (a second stream is given): the two kernels run CONCURRENTLY on disjoint SMs -- the chain on 2 P
+//  CTA pairs' SMs of `stream`, the dW kernel on the remaining SMs of `side` -- and hand every dZ block over through a
+//  per-(tile, block) ready counter in global memory (release by the chain's store warps, acquire by the dW kernel's
+//  producer lane) so that the dW kernel reads dZ from L2 right after it was written instead of from HBM a kernel later.
+//  The dependency is one-directional (the chain never waits for the dW kernel), so any serialisation of the two
+//  launches (a profiler, a busy GPU) is still correct.  dW CTAs of a unit take tiles round-robin (tile = split + i n),
+//  i.e. in the order the chain produces them.
 #include "mlp_tc.cuh"
 
 namespace nerf {
+
+// ---- dZ hand-over flags (overlapped mode) ---------------------------------------------------------------------------
+// flags[tile * kFlagsPerTile + b]: b = l - 1 for dZ_l (l = 1..8; two store warps -> target 2), b = 8 for the blocks the
+// chain prologue writes (dZ_L', dOut; eight epilogue warps -> target 8)
+constexpr int kFlagsPerTile = 9;
+constexpr uint32_t kFlagTargetStore = 2, kFlagTargetPrologue = 8;
+__device__ __forceinline__ void flag_signal(uint32_t* p) {
+  // release at gpu scope: this thread's (and, through the preceding __syncwarp, its warp's) global stores are visible
+  // to whoever acquires the incremented counter
+  asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(p) : "memory");
+}
+__device__ __forceinline__ uint32_t flag_load(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void flag_wait(const uint32_t* p, uint32_t target) {
+  if (flag_load(p) >= target) return;
+  for (uint32_t it = 0;; ++it) {
+    __nanosleep(100);
+    if (flag_load(p) >= target) return;
+    if (it > (1u << 25)) {     // seconds: the chain kernel never started or died
+      printf("nerf_b200: dZ hand-over flag timeout (block %d)\n", blockIdx.x);
+      __trap();
+    }
+  }
+}
 
 constexpr int kBwdMaxChunks = 40;
 constexpr int kBwdMaxSteps = 12;
@@ -174,10 +209,20 @@ __device__ __forceinline__ void chain_mask_epilogue(uint32_t taddr_half, const u
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreadsFwd, 1)
 mlp_tc_bwd_chain_kernel(const __grid_constant__ BwdPlan plan, const uint8_t* __restrict__ packed,
                         const uint8_t* __restrict__ saved, const float* __restrict__ d_out4, int64_t M,
-                        uint8_t* __restrict__ dz_ws, float* __restrict__ d_xyz_enc, int dx, float alpha, uint32_t dbg) {
+                        uint8_t* __restrict__ dz_ws, float* __restrict__ d_xyz_enc, int dx, float alpha, uint32_t dbg,
+                        uint32_t* __restrict__ flags, uint32_t stagger_ns) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t sbase = smem_u32(smem);
   if ((sbase & 1023u) != 0u) __trap();
+  if (stagger_ns) {
+    // overlapped mode: spread the pairs over the nine layer phases so that every dW unit sees a steady stream of blocks
+    // instead of one burst per round (keeps the dZ in flight small enough to stay in L2)
+    for (uint32_t ns = (cluster_id_x() % 9u) * stagger_ns; ns;) {
+      const uint32_t d = ns < 20000u ? ns : 20000u;
+      __nanosleep(d);
+      ns -= d;
+    }
+  }
   ChainBars* bars = reinterpret_cast<ChainBars*>(smem + kSmemCBar);
   // L1 is ~3 KB next to 200 KB of shared memory: the head kernels the epilogue needs live in shared memory
   for (int i = threadIdx.x; i < 256 + 384; i += blockDim.x) {
@@ -316,7 +361,10 @@ mlp_tc_bwd_chain_kernel(const __grid_constant__ BwdPlan plan, const uint8_t* __r
             }
           }
           __syncwarp();
-          if (lane == 0) mbar_arrive(smem_u32(&bars->panel_free[t]));
+          if (lane == 0) {
+            mbar_arrive(smem_u32(&bars->panel_free[t]));
+            if (flags) flag_signal(flags + (size_t)tile * kFlagsPerTile + (l - 1));   // dZ_l of this tile: my half is out
+          }
         }
       }
     }
@@ -385,7 +433,10 @@ mlp_tc_bwd_chain_kernel(const __grid_constant__ BwdPlan plan, const uint8_t* __r
       }
       fence_proxy_async();
       __syncwarp();
-      if (lane == 0) mbar_arrive_cluster(act_ready_leader);
+      if (lane == 0) {
+        mbar_arrive_cluster(act_ready_leader);
+        if (flags) flag_signal(flags + (size_t)tile * kFlagsPerTile + 8);      // this warp's part of dZ_L' / dOut is out
+      }
 
       float xs[32];                                      // d(xyz encoding): half 0 -> cols 0..31, half 1 -> cols 32..39
 #pragma unroll
@@ -475,6 +526,8 @@ struct DwUnit {
   int32_t a_region;       // bytes reserved for the A slab inside a stage (the B slab follows)
   int32_t stage_bytes;
   float cost;             // modelled time per 64-row stage, the unit of the CTA allocation
+  int16_t flag_idx;       // overlapped mode: which ready counter of a tile guards the B block, and its final value
+  int16_t flag_target;
 };
 struct DwPlan {
   DwUnit u[16];
@@ -498,6 +551,9 @@ static void make_dw_plan(DwPlan* p, int n_ctas_total) {
     // measured per-CTA cycle counts (NERF_TC_DEBUG=320, all 148 CTAs streaming): a 64-row stage costs ~26 cycles per KB
     // plus ~700 cycles that do not shrink with the ring depth -> a 27 KB-equivalent overhead per stage
     u.cost = (float)((a_chunks == 0 ? 8 : a_chunks) + u.b_load) + 27.f;
+    const bool prologue_block = b_panel >= kDzPanelL;
+    u.flag_idx = (int16_t)(prologue_block ? 8 : b_panel / kActPanels);       // dz_panel(l) = (l - 1) kActPanels
+    u.flag_target = (int16_t)(prologue_block ? kFlagTargetPrologue : kFlagTargetStore);
   };
   // Dense l (input h_l, or the input panel) with the gradient of its pre-activation output dZ_{l+1}
   add(0, 0, dz_panel(1), 32, 256, OUT_INP_XYZ, 0, 1);                                  // Dense 0
@@ -585,10 +641,12 @@ __device__ __forceinline__ float* db_target(const DwUnit& u, const NetGeom& g, f
   return nullptr;
 }
 
-__global__ void __launch_bounds__(kThreadsDw, 1)
+// Clusters of 2 only so that the CTAs fill whole TPCs and leave whole TPCs to the chain kernel's CTA pairs when the two
+// kernels share the GPU (overlapped mode); the two CTAs of a cluster never talk to each other.
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreadsDw, 1)
 mlp_tc_bwd_dw_kernel(const __grid_constant__ DwPlan plan, const __grid_constant__ NetGeom g,
                      const uint8_t* __restrict__ saved, const uint8_t* __restrict__ dz_ws, int64_t M,
-                     float* __restrict__ scratch, uint32_t dbg) {
+                     float* __restrict__ scratch, uint32_t dbg, const uint32_t* __restrict__ flags) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t sbase = smem_u32(smem);
   if ((sbase & 1023u) != 0u) __trap();
@@ -600,10 +658,10 @@ mlp_tc_bwd_dw_kernel(const __grid_constant__ DwPlan plan, const __grid_constant_
   const DwUnit& u = plan.u[ui];
   const int split = blockIdx.x - u.first_cta;
   const int64_t n_tiles = (M + kTileM - 1) / kTileM;
-  const int64_t per = (n_tiles + u.n_ctas - 1) / u.n_ctas;
-  const int64_t tb = min(n_tiles, split * per), te = min(n_tiles, (split + 1) * per);
-  if (tb >= te) return;                       // whole CTA leaves together: nothing to do for this split
-  const uint32_t n_stages_total = (uint32_t)(te - tb) * 2u;
+  // this split's tiles: split, split + n_ctas, split + 2 n_ctas, ... (the order the chain kernel produces them in)
+  if (split >= n_tiles) return;               // whole CTA leaves together: nothing to do for this split
+  const int64_t my_tiles = (n_tiles - split + u.n_ctas - 1) / u.n_ctas;
+  const uint32_t n_stages_total = (uint32_t)my_tiles * 2u;
   const long long t_start = clock64();
 
   // zero the operand slots once: the unused second A block of the input-panel units must read as zeros
@@ -627,9 +685,15 @@ mlp_tc_bwd_dw_kernel(const __grid_constant__ DwPlan plan, const __grid_constant_
   if (warp == 4) {
     if (lane == 0) {
       uint32_t gi = 0;
-      for (int64_t tile = tb; tile < te; ++tile) {
+      for (int64_t tile = split; tile < n_tiles; tile += u.n_ctas) {
         const uint8_t* a_src = saved + (size_t)tile * kSavedTileBytes + (size_t)u.a_off;
         const uint8_t* b_src = dz_ws + (size_t)tile * kDzTileBytes + (size_t)u.b_off;
+        if (flags) {
+          // the chain kernel is writing this block right now: wait for its ready counter, then order the bulk copies
+          // (async proxy) after the acquire
+          flag_wait(flags + (size_t)tile * kFlagsPerTile + u.flag_idx, (uint32_t)u.flag_target);
+          asm volatile("fence.proxy.async;" ::: "memory");
+        }
         for (int half = 0; half < 2; ++half, ++gi) {
           const uint32_t st = gi % n_ring, ph = (gi / n_ring) & 1u;
           mbar_wait(smem_u32(&bars->empty[st]), ph ^ 1u);
@@ -716,7 +780,7 @@ mlp_tc_bwd_dw_kernel(const __grid_constant__ DwPlan plan, const __grid_constant_
     tc_fence_before();
     if ((dbg & kDbgTiming) && threadIdx.x == 0) {
       const long long t_acc = clock64();
-      printf("dw cta %3d unit %2d (dense %d kind %d) tiles %4d  cycles %8lld\n", blockIdx.x, ui, u.dense, u.out_kind, (int)(te - tb),
+      printf("dw cta %3d unit %2d (dense %d kind %d) tiles %4d  cycles %8lld\n", blockIdx.x, ui, u.dense, u.out_kind, (int)my_tiles,
              t_acc - t_start);
     }
   }
@@ -731,9 +795,7 @@ mlp_tc_bwd_dw_reduce_kernel(const __grid_constant__ DwPlan plan, const __grid_co
                             const float* __restrict__ scratch, int64_t M, float* __restrict__ G) {
   const DwUnit& u = plan.u[blockIdx.x];
   const int64_t n_tiles = (M + kTileM - 1) / kTileM;
-  const int64_t per = (n_tiles + u.n_ctas - 1) / u.n_ctas;
-  int live = 0;                                          // splits that had rows (the others left without writing)
-  while (live < u.n_ctas && (int64_t)live * per < n_tiles) ++live;
+  const int live = (int)(n_tiles < u.n_ctas ? n_tiles : u.n_ctas);   // splits that had tiles (the others left without writing)
   const float* base = scratch + (size_t)u.first_cta * kDwPartialFloats;
   const int e4 = blockIdx.y * 256 + threadIdx.x;         // float4 index inside [256][64 float4]
   const int k = e4 >> 6, n0 = (e4 & 63) * 4;
@@ -759,41 +821,80 @@ mlp_tc_bwd_dw_reduce_kernel(const __grid_constant__ DwPlan plan, const __grid_co
 }
 
 // ---- host ---------------------------------------------------------------------------------------------------------------
+// env NERF_BWD_CHAIN_PAIRS: CTA pairs of the chain kernel in overlapped mode (the dW kernel gets the other SMs);
+// env NERF_BWD_STAGGER_NS: start offset between consecutive layer phases of the chain pairs (0 = none)
+static int env_int(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return e ? atoi(e) : dflt;
+}
+
+int64_t mlp_tc_bwd_flag_bytes(int64_t m) {
+  int64_t tiles4 = ((m + kTileM - 1) / kTileM + 3) / 4 * 4;
+  return tiles4 * kFlagsPerTile * (int64_t)sizeof(uint32_t);
+}
+
+// side != nullptr (and parts == 3): overlapped mode -- the chain on `st`, the dW kernel + reduction on `side` at the same
+// time (see the top of this file); the caller joins `side` before it reads `grads`.
 int mlp_tc_bwd(const nerf_net_cfg* cfg, const NetGeom& g, const float* params, const void* packed, const float* xyz_enc,
                const float* view_enc, const void* saved, const float* d_out4, int64_t m, float* grads, float* d_xyz_enc,
-               void* workspace, cudaStream_t st, int parts) {
+               void* workspace, cudaStream_t st, int parts, cudaStream_t side) {
   (void)params; (void)xyz_enc; (void)view_enc;
   TcPlan fplan;
   if (!make_plan(g, &fplan)) {
     set_error("NERF_MODE_BF16 supports hidden=256, last_hidden=128, n_angles in {1,2}, xyz width <= 40, view width <= 24");
     return NERF_E_UNSUPPORTED;
   }
-  static bool attr_set = false;
-  if (!attr_set) {
+  if (device_first_use(1)) {
     NERF_CUDA(cudaFuncSetAttribute(mlp_tc_bwd_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemCAlloc));
     NERF_CUDA(cudaFuncSetAttribute(mlp_tc_bwd_dw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemDwAlloc));
-    attr_set = true;
   }
   BwdPlan bplan;
   make_bwd_plan(&bplan);
   const uint8_t* packed_bwd = (const uint8_t*)packed + ((fplan.total_bytes + 1023u) & ~1023u);
   uint8_t* dz_ws = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(workspace) + 1023) & ~(uintptr_t)1023);
-  int64_t n_quads = ((m + kTileM - 1) / kTileM + 3) / 4;
-  int grid = 2 * (int)(n_quads < kNumSMs / 2 ? n_quads : kNumSMs / 2);     // CTA pairs
+  const int64_t tiles4 = ((m + kTileM - 1) / kTileM + 3) / 4 * 4;
+  const int64_t n_quads = tiles4 / 4;
+  float* scratch = reinterpret_cast<float*>(dz_ws + tiles4 * (int64_t)kDzTileBytes);
+  uint32_t* flag_buf = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(scratch) + kDwScratchBytes);
   const uint32_t dbg = tc_debug_flags();
+  const int sms = num_sms() & ~1;
+  const bool overlap = side != nullptr && side != st && parts == 3 && !(dbg & (kDbgNoChain | kDbgNoDw)) && sms >= 8;
+  int chain_pairs = sms / 2, dw_ctas = sms;
+  uint32_t* flags = nullptr;
+  uint32_t stagger_ns = 0;
+  if (overlap) {
+    // SM split: the chain costs ~2x the SM time of the dW kernel when the latter reads dZ from L2
+    const int env_pairs = env_int("NERF_BWD_CHAIN_PAIRS", 0);
+    const int env_stagger = env_int("NERF_BWD_STAGGER_NS", -1);
+    chain_pairs = env_pairs > 0 ? env_pairs : (sms / 2) * 48 / 74;
+    if (chain_pairs > sms / 2 - 2) chain_pairs = sms / 2 - 2;
+    if (chain_pairs < 1) chain_pairs = 1;
+    dw_ctas = sms - 2 * chain_pairs;
+    flags = flag_buf;
+    stagger_ns = n_quads >= 4 * (int64_t)chain_pairs ? (uint32_t)(env_stagger >= 0 ? env_stagger : 2500) : 0u;
+    NERF_CUDA(cudaMemsetAsync(flags, 0, (size_t)mlp_tc_bwd_flag_bytes(m), st));
+    cudaEvent_t ev;
+    NERF_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    cudaError_t e = cudaEventRecord(ev, st);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(side, ev, 0);
+    cudaEventDestroy(ev);
+    if (e != cudaSuccess) { set_error("mlp_tc_bwd: stream hand-over failed: %s", cudaGetErrorString(e)); return NERF_E_CUDA; }
+  }
+  const int grid = 2 * (int)(n_quads < chain_pairs ? n_quads : chain_pairs);     // CTA pairs
   if (!(dbg & kDbgNoChain) && (parts & 1)) {
     mlp_tc_bwd_chain_kernel<<<grid, kThreadsFwd, kSmemCAlloc, st>>>(bplan, packed_bwd, (const uint8_t*)saved, d_out4, m,
-                                                                   dz_ws, d_xyz_enc, g.dx, cfg->leaky_alpha, dbg);
+                                                                   dz_ws, d_xyz_enc, g.dx, cfg->leaky_alpha, dbg, flags,
+                                                                   stagger_ns);
     NERF_CHECK_LAUNCH();
   }
-  DwPlan dplan;
-  make_dw_plan(&dplan, kNumSMs);
   if (!(dbg & kDbgNoDw) && (parts & 2)) {
-    int64_t tiles4 = ((m + kTileM - 1) / kTileM + 3) / 4 * 4;
-    float* scratch = reinterpret_cast<float*>(dz_ws + tiles4 * (int64_t)kDzTileBytes);
-    mlp_tc_bwd_dw_kernel<<<kNumSMs, kThreadsDw, kSmemDwAlloc, st>>>(dplan, g, (const uint8_t*)saved, dz_ws, m, scratch, dbg);
+    DwPlan dplan;
+    make_dw_plan(&dplan, dw_ctas);
+    cudaStream_t dst = overlap ? side : st;
+    mlp_tc_bwd_dw_kernel<<<dw_ctas, kThreadsDw, kSmemDwAlloc, dst>>>(dplan, g, (const uint8_t*)saved, dz_ws, m, scratch, dbg,
+                                                                     flags);
     NERF_CHECK_LAUNCH();
-    mlp_tc_bwd_dw_reduce_kernel<<<dim3(dplan.n_units, 64), 256, 0, st>>>(dplan, g, scratch, m, grads);
+    mlp_tc_bwd_dw_reduce_kernel<<<dim3(dplan.n_units, 64), 256, 0, dst>>>(dplan, g, scratch, m, grads);
     NERF_CHECK_LAUNCH();
   }
   return NERF_OK;
