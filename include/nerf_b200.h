@@ -132,17 +132,26 @@ int nerf_mlp_bwd_dw(const nerf_net_cfg* cfg, const float* params, const void* pa
                     const float* xyz_enc, const float* view_enc, const void* saved, const float* d_out4,
                     int64_t m, float* grads, float* d_xyz_enc_or_null, void* workspace, int32_t mode,
                     void* stream);
-/* nerf_mlp_bwd with its two halves running AT THE SAME TIME (NERF_MODE_BF16): the input-gradient chain on `stream`, the
- * weight-gradient kernel and its reduction on `side_stream`, on disjoint SMs, every dZ block handed over through a ready
- * counter in the workspace so that the weight-gradient kernel reads it from L2 instead of from HBM a kernel later.
- * d_xyz_enc is complete at the end of `stream`, `grads` at the end of `side_stream`: the caller joins the two.
- * side_stream null or == stream, or NERF_MODE_FP32: identical to nerf_mlp_bwd (everything on `stream`).  The split-K
- * partition of the weight gradients follows the number of SMs the kernel gets, so the two variants agree to fp32
- * rounding, not bit for bit.  Replaces TF autodiff of the Keras models in NeRF.train_step (src/NeRF.py:149-167). */
+/* nerf_mlp_bwd over two streams of the caller's (NERF_MODE_BF16): the input-gradient chain on `stream`, the weight-gradient
+ * kernel and its reduction on `side_stream` -- after the chain, so that it runs under whatever the caller enqueues next on
+ * `stream` (the sampler / compositing backward and the head of the other network's chain in a train step).  d_xyz_enc is
+ * complete at the end of `stream`, `grads` at the end of `side_stream`: the caller joins the two.  side_stream null or ==
+ * stream, or NERF_MODE_FP32: identical to nerf_mlp_bwd.  With the environment variable NERF_BWD_OVERLAP=1 the two kernels
+ * run AT THE SAME TIME on disjoint SMs and hand every dZ block over through a ready counter in the workspace (an
+ * experiment kept for measurement: the weight-gradient kernel is bound by what one SM can pull in, so it loses more from
+ * having fewer SMs than it gains from reading dZ out of L2 -- profiles/r02_a_overlap_probe.log); its split-K partition
+ * follows the SMs it gets, so that variant agrees with nerf_mlp_bwd to fp32 rounding, not bit for bit.
+ * Replaces TF autodiff of the Keras models in NeRF.train_step (src/NeRF.py:149-167). */
 int nerf_mlp_bwd_overlapped(const nerf_net_cfg* cfg, const float* params, const void* packed_or_null,
                             const float* xyz_enc, const float* view_enc, const void* saved, const float* d_out4,
                             int64_t m, float* grads, float* d_xyz_enc_or_null, void* workspace, int32_t mode,
                             void* side_stream, void* stream);
+/* Diagnostic (tests, tools/bwd_pipe_probe.py): ONE stage of the layer-pipelined backward kernel over every SM -- Dense
+ * `layer` (1..7: dZ_layer = (dZ_{layer+1} W^T) * LeakyReLU' written back into the workspace, and dW/db of that layer ADDED
+ * to `grads`; 8: only the weight gradient of Dense 8 / the sigma head w.r.t. the h8 rows), reading dZ_{layer+1} from a
+ * workspace that a previous nerf_mlp_bwd[_dx] call on the same `saved` filled. */
+int nerf_debug_bwd_pipe_layer(const nerf_net_cfg* cfg, const void* packed, const void* saved, int64_t m,
+                              void* workspace, int32_t layer, float* grads, void* stream);
 /* bf16 weight pack for the tensor-core path (re-run after every optimizer step). */
 int64_t nerf_packed_bytes(const nerf_net_cfg* cfg);
 int nerf_pack_weights(const nerf_net_cfg* cfg, const float* params, void* packed, void* stream);

@@ -77,6 +77,7 @@ SIGNATURES = {
     "nerf_mlp_bwd_overlapped": (c_int32, [_CFG, _P, _P, _P, _P, _P, _P, c_int64, _P, _P, _P, c_int32, _P, _P]),
     "nerf_mlp_bwd_dx": (c_int32, [_CFG, _P, _P, _P, _P, _P, _P, c_int64, _P, _P, _P, c_int32, _P]),
     "nerf_mlp_bwd_dw": (c_int32, [_CFG, _P, _P, _P, _P, _P, _P, c_int64, _P, _P, _P, c_int32, _P]),
+    "nerf_debug_bwd_pipe_layer": (c_int32, [_CFG, _P, _P, c_int64, _P, c_int32, _P, _P]),
     "nerf_packed_bytes": (c_int64, [_CFG]),
     "nerf_pack_weights": (c_int32, [_CFG, _P, _P, _P]),
     "nerf_pack_weights_fp16": (c_int32, [_CFG, _P, _P, _P]),

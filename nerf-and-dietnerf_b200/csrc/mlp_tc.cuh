@@ -135,6 +135,9 @@ enum : uint32_t {
   kDbgNoRelay = 512u,      // forward (pair mode): the leader does not wait for the peer's weight halves (racy)
   kDbgStoreL2 = 1024u,     // forward: the activation copies land in a 64-tile window (L2-resident): isolates HBM from the SM store port
   kDbgTiming = 256u,       // dW: every CTA prints its cycle count
+  kDbgWrapDz = 2048u,      // pipe: dZ loads / stores hit super-tile (s mod 128): the 38 MB window stays in L2 (what the
+                           // pipeline's hand-over looks like to a stage that is timed alone)
+  kDbgWrapSaved = 4096u,   // pipe: the saved activations wrap as well (everything from L2)
 };
 uint32_t tc_debug_flags();
 

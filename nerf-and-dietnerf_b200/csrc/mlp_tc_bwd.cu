@@ -25,6 +25,7 @@
 //  launches (a profiler, a busy GPU) is still correct.  dW CTAs of a unit take tiles round-robin (tile = split + i n),
 //  i.e. in the order the chain produces them.
 #include "mlp_tc.cuh"
+#include "mlp_tc_bwd_pipe.cuh"
 
 namespace nerf {
 
@@ -33,28 +34,6 @@ namespace nerf {
 // chain prologue writes (dZ_L', dOut; eight epilogue warps -> target 8)
 constexpr int kFlagsPerTile = 9;
 constexpr uint32_t kFlagTargetStore = 2, kFlagTargetPrologue = 8;
-__device__ __forceinline__ void flag_signal(uint32_t* p) {
-  // release at gpu scope: this thread's (and, through the preceding __syncwarp, its warp's) global stores are visible
-  // to whoever acquires the incremented counter
-  asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(p) : "memory");
-}
-__device__ __forceinline__ uint32_t flag_load(const uint32_t* p) {
-  uint32_t v;
-  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ void flag_wait(const uint32_t* p, uint32_t target) {
-  if (flag_load(p) >= target) return;
-  for (uint32_t it = 0;; ++it) {
-    __nanosleep(100);
-    if (flag_load(p) >= target) return;
-    if (it > (1u << 25)) {     // seconds: the chain kernel never started or died
-      printf("nerf_b200: dZ hand-over flag timeout (block %d)\n", blockIdx.x);
-      __trap();
-    }
-  }
-}
-
 constexpr int kBwdMaxChunks = 40;
 constexpr int kBwdMaxSteps = 12;
 enum : int { STEP_MASK = 0, STEP_XSTASH = 1, STEP_XFINAL = 2 };
@@ -98,6 +77,15 @@ static void make_bwd_plan(BwdPlan* p) {
   p->w_sigma_off = off;  off += 256 * 4;
   p->w_rgb_off = off;    off += 128 * 16;
   p->total_bytes = off;
+}
+
+// byte offset, inside the backward weight pack, of the first K chunk of W_l^T (the STEP_MASK step of layer l)
+uint32_t bwd_pack_layer_offset(int layer) {
+  BwdPlan p;
+  make_bwd_plan(&p);
+  for (int s = 0; s < p.n_steps; ++s)
+    if (p.step_kind[s] == STEP_MASK && p.step_layer[s] == layer) return p.chunk_off[p.step_first[s]];
+  return 0xffffffffu;
 }
 
 uint32_t bwd_pack_bytes() {
@@ -858,7 +846,11 @@ int mlp_tc_bwd(const nerf_net_cfg* cfg, const NetGeom& g, const float* params, c
   uint32_t* flag_buf = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(scratch) + kDwScratchBytes);
   const uint32_t dbg = tc_debug_flags();
   const int sms = num_sms() & ~1;
-  const bool overlap = side != nullptr && side != st && parts == 3 && !(dbg & (kDbgNoChain | kDbgNoDw)) && sms >= 8;
+  // Measured (profiles/r02_a_overlap_probe.log): the dW kernel is bound by what ONE SM can pull in (~35 GB/s per SM whether
+  // dZ comes from L2 or HBM), so giving it fewer SMs costs more than the L2 hand-over saves (1.04 vs 0.76 ms at 262 k
+  // rows).  The overlapped mode therefore stays opt-in (NERF_BWD_OVERLAP=1) as the experiment it was.
+  const bool overlap = side != nullptr && side != st && parts == 3 && !(dbg & (kDbgNoChain | kDbgNoDw)) && sms >= 8 &&
+                       env_int("NERF_BWD_OVERLAP", 0) != 0;
   int chain_pairs = sms / 2, dw_ctas = sms;
   uint32_t* flags = nullptr;
   uint32_t stagger_ns = 0;
@@ -890,7 +882,20 @@ int mlp_tc_bwd(const nerf_net_cfg* cfg, const NetGeom& g, const float* params, c
   if (!(dbg & kDbgNoDw) && (parts & 2)) {
     DwPlan dplan;
     make_dw_plan(&dplan, dw_ctas);
-    cudaStream_t dst = overlap ? side : st;
+    cudaStream_t dst = st;
+    if (side != nullptr && side != st && parts == 3) {
+      // the weight-gradient kernel goes to the caller's side stream: after the chain when the two run one after the
+      // other (it then overlaps whatever the caller enqueues next on `st`), next to it in the overlapped mode
+      dst = side;
+      if (!overlap) {
+        cudaEvent_t ev;
+        NERF_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        cudaError_t e = cudaEventRecord(ev, st);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(side, ev, 0);
+        cudaEventDestroy(ev);
+        if (e != cudaSuccess) { set_error("mlp_tc_bwd: stream hand-over failed: %s", cudaGetErrorString(e)); return NERF_E_CUDA; }
+      }
+    }
     mlp_tc_bwd_dw_kernel<<<dw_ctas, kThreadsDw, kSmemDwAlloc, dst>>>(dplan, g, (const uint8_t*)saved, dz_ws, m, scratch, dbg,
                                                                      flags);
     NERF_CHECK_LAUNCH();

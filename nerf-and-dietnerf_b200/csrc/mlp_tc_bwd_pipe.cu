@@ -1,0 +1,511 @@
+// K4 in NERF_MODE_BF16, layer-pipelined form: TF autodiff of the NeRF MLP inside NeRF.train_step (src/NeRF.py:149-167)
+// with the input-gradient chain and the weight gradients of a layer computed BY THE SAME CTA PAIR from the same dZ, and
+// dZ handed from layer to layer through L2 instead of HBM.
+//
+//   * The 74 CTA pairs (cluster of 2, tcgen05 cta_group::2) are split into GROUPS, one per layer l = 7..1 (plus the
+//     weight gradients of Dense 8's h8 rows and, for the fine network, the xyz-encoding gradient).  A group is
+//     layer-STATIONARY: its pairs keep W_l^T resident in shared memory (64 KB per CTA: each CTA holds the 128 output rows
+//     of every K chunk it contributes to the pair's MMA) and the whole 256 x 256 fp32 accumulator of dW_l in TMEM
+//     (128 lanes x 256 columns per CTA, cta_group::2 M = 256) for the entire launch -- one split-K partial per PAIR
+//     instead of one per CTA and tile range.
+//   * Per 256-row super-tile s (tiles 2s, 2s+1; CTA r owns the rows of tile 2s + r in the chain) a pair of group l
+//       - waits for the ready counter of dZ_{l+1}[s] (written by a pair of group l+1 moments ago, so it sits in L2),
+//       - chain:  dH_l = dZ_{l+1} W_l^T   (A = its own 128 rows, K-major, streamed in four 64-feature panels;
+//                 accumulator D1 = TMEM columns 0..255), epilogue = LeakyReLU' from the saved sign mask, bf16, straight
+//                 from registers to the dZ_l block in global memory (RBCM, 512-byte warp stores), then the ready
+//                 counter of dZ_l[s];
+//       - dW:     dW_l += A_l^T dZ_{l+1}  (both operands MN-major, the pair splits the FEATURES: CTA r streams features
+//                 128 r .. 128 r + 127 of the saved activations and of dZ_{l+1} for all 256 rows, in 64-row slabs;
+//                 accumulator D2 = TMEM columns 256..511), bias gradient = column sums of the same slabs.
+//     The MMA order inside a super-tile is  c0 c1 d0 c2 c3 d1 d2 d3  (c = chain panel, d = dW slab): the tensor pipe
+//     always has work, the chain accumulator drains (16 epilogue warps) under the last three dW slabs, and the bulk
+//     copies are spread evenly (48 KB per 1024 MMA cycles and CTA: two thirds from L2, one third -- the saved
+//     activations -- from HBM).
+//   * Per FLOP an SM moves half the shared-memory bytes of the per-tile chain kernel (no weight ring, no in-place
+//     activation rewrite, no store-warp re-read) and a third of the L2->SM bytes of the stand-alone dW kernel.
+//
+// Layout notes: dZ blocks and saved activations are RBCM (mlp_tc.cuh).  A feature half of a 64-row slab is ONE contiguous
+// 16 KB piece and IS the un-swizzled MN-major operand (SBO = 1024 between 8-feature chunks, LBO = 128 between 8-row
+// groups).  The chain's K-major A operand needs a uniform 128-byte stride over all 128 rows of the tile, i.e. 2 KB per
+// chunk in shared memory: a panel is gathered by 16 one-KB bulk copies (8 chunks x 2 row halves), issued by 16 lanes of
+// the producer warp in one instruction.
+#include <stdlib.h>
+
+#include "mlp_tc.cuh"
+#include "mlp_tc_bwd_pipe.cuh"
+
+namespace nerf {
+
+// ---- shared-memory map ------------------------------------------------------------------------------------------------
+constexpr int kPW = 0;                                   // resident W_l^T half: 4 K-chunks x [128 rows][64] swizzled
+constexpr int kPWBytes = 4 * 16384;
+constexpr int kPCStages = 4, kPCBytes = 16384;           // chain ring: [8 chunks][128 rows][16 B]
+constexpr int kPDStages = 3, kPDBytes = 32768;           // dW ring: A slab [16 chunks][64 rows][16 B] | B slab (same)
+constexpr int kPC = kPW + kPWBytes;
+constexpr int kPD = kPC + kPCStages * kPCBytes;
+constexpr int kPBar = kPD + kPDStages * kPDBytes;
+constexpr int kPAlloc = kPBar + 256;
+static_assert(kPAlloc <= 232448, "pipe kernel exceeds the 227 KB shared-memory limit");
+
+struct PipeBars {
+  uint64_t wfull, cfull[kPCStages], cempty[kPCStages], dfull[kPDStages], dempty[kPDStages];
+  uint64_t acc_full, acc_empty, fin;
+  uint32_t tmem_base;
+};
+static_assert(sizeof(PipeBars) <= 256, "barrier block overflows its slot");
+
+// order of the eight MMA groups of a super-tile: 0 = chain panel, 1 = dW slab
+__device__ __forceinline__ constexpr int seq_kind(int i) { return (i == 2 || i >= 5) ? 1 : 0; }
+
+struct RingPos {
+  uint32_t s, ph;
+  __device__ __forceinline__ void next(uint32_t n) { if (++s == n) { s = 0; ph ^= 1u; } }
+};
+
+// ---- producer (warp 16 of both CTAs) ------------------------------------------------------------------------------------
+template <bool kChain>
+__device__ __forceinline__ void pipe_producer(const PipeGroup& G, PipeBars* bars, uint32_t sbase, uint32_t rank, int lane,
+                                              const uint8_t* __restrict__ packed, const uint8_t* __restrict__ saved,
+                                              const uint8_t* __restrict__ dz_ws, const uint32_t* flags, int64_t s_first,
+                                              int64_t s_step, int64_t n_super, uint32_t dbg) {
+  if (kChain && lane == 0) {
+    const uint32_t wf = smem_u32(&bars->wfull);
+    mbar_arrive_expect_tx(wf, kPWBytes);
+#pragma unroll
+    for (int kp = 0; kp < 4; ++kp)
+      bulk_g2s(sbase + kPW + kp * 16384, packed + G.w_off + (size_t)kp * 32768 + rank * 16384u, 16384, wf);
+  }
+  RingPos c{0, 1}, d{0, 1};
+  const uint32_t a_bytes = 16384u, b_bytes = (uint32_t)G.b_chunks * 1024u;
+  for (int64_t s = s_first; s < n_super; s += s_step) {
+    if (G.wait_flag >= 0) {
+      if (lane == 0) flag_wait(flags + (size_t)s * kPipeFlagsPerSuper + G.wait_flag, kPipeFlagTarget);
+      __syncwarp();
+      asm volatile("fence.proxy.async;" ::: "memory");
+    }
+    const int64_t sz = (dbg & kDbgWrapDz) ? (s & 127) : s, ss = (dbg & kDbgWrapSaved) ? (s & 127) : s;
+    const uint8_t* own_b = dz_ws + (size_t)(2 * sz + rank) * kDzTileBytes + (size_t)G.b_off;   // chain A operand source
+    int kp = 0, j = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      if (seq_kind(i) == 0) {
+        if (kChain) {
+          const uint32_t fb = smem_u32(&bars->cfull[c.s]);
+          if (lane == 0) {
+            mbar_wait_spin(smem_u32(&bars->cempty[c.s]), c.ph);
+            mbar_arrive_expect_tx(fb, kPCBytes);
+          }
+          __syncwarp();
+          if (lane < 16) {
+            const int h = lane >> 3, cc = lane & 7;        // row half, chunk inside the panel
+            bulk_g2s(sbase + kPC + c.s * kPCBytes + cc * 2048 + h * 1024,
+                     own_b + (size_t)h * (32 * 1024) + (size_t)(8 * kp + cc) * 1024, 1024, fb);
+          }
+          c.next(kPCStages);
+        }
+        ++kp;
+      } else {
+        if (lane == 0) {
+          const int64_t tile = 2 * ss + (j >> 1), tile_z = 2 * sz + (j >> 1);
+          const int hh = j & 1;
+          const uint32_t fb = smem_u32(&bars->dfull[d.s]);
+          mbar_wait_spin(smem_u32(&bars->dempty[d.s]), d.ph);
+          mbar_arrive_expect_tx(fb, a_bytes + b_bytes);
+          const uint32_t dst = sbase + kPD + d.s * kPDBytes;
+          bulk_g2s(dst, saved + (size_t)tile * kSavedTileBytes + (size_t)G.a_off + (size_t)hh * 32768 + rank * 16384u, a_bytes, fb);
+          bulk_g2s(dst + 16384, dz_ws + (size_t)tile_z * kDzTileBytes + (size_t)G.b_off + (size_t)hh * ((size_t)G.b_half_chunks * 1024) +
+                                    (size_t)rank * b_bytes, b_bytes, fb);
+        }
+        d.next(kPDStages);
+        ++j;
+      }
+    }
+  }
+}
+
+// ---- relay (warp 17 lane 0 of the PEER CTA): "my half of this stage has landed" -> the leader's full barrier ----------------
+template <bool kChain>
+__device__ __forceinline__ void pipe_relay(PipeBars* bars, int64_t s_first, int64_t s_step, int64_t n_super) {
+  if (kChain) {
+    mbar_wait_spin(smem_u32(&bars->wfull), 0);
+    mbar_arrive_cluster(mapa_shared(smem_u32(&bars->wfull), 0));
+  }
+  const uint32_t cf0 = smem_u32(&bars->cfull[0]), df0 = smem_u32(&bars->dfull[0]);
+  const uint32_t cf0_l = mapa_shared(cf0, 0), df0_l = mapa_shared(df0, 0);
+  RingPos c{0, 0}, d{0, 0};
+  for (int64_t s = s_first; s < n_super; s += s_step) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      if (seq_kind(i) == 0) {
+        if (kChain) {
+          mbar_wait_spin(cf0 + 8u * c.s, c.ph);
+          mbar_arrive_cluster(cf0_l + 8u * c.s);
+          c.next(kPCStages);
+        }
+      } else {
+        mbar_wait_spin(df0 + 8u * d.s, d.ph);
+        mbar_arrive_cluster(df0_l + 8u * d.s);
+        d.next(kPDStages);
+      }
+    }
+  }
+}
+
+// ---- MMA issuer (warp 17 lane 0 of the LEADER CTA) ---------------------------------------------------------------------------
+template <bool kChain>
+__device__ __forceinline__ void pipe_mma(const PipeGroup& G, PipeBars* bars, uint32_t sbase, uint32_t tmem_base,
+                                         int64_t s_first, int64_t s_step, int64_t n_super, uint32_t dbg) {
+  const uint32_t idesc_c = make_idesc(G.n_chain, 0, 0, 1, 256);
+  const uint32_t idesc_d = make_idesc(G.n_dw, 1, 1, 1, 256);
+  const uint32_t d1 = tmem_base, d2 = tmem_base + 256u;
+  const uint64_t a_c0 = make_desc_k_nosw(sbase + kPC, 2048, 128);       // chain A: [chunk][128 rows][16 B]
+  const uint64_t b_c0 = make_desc_kmajor(sbase + kPW);                  // chain B: resident swizzled W chunks
+  const uint64_t a_d0 = make_desc_mn_nosw(sbase + kPD, 128, 1024);      // dW A: saved activations slab
+  const uint64_t b_d0 = make_desc_mn_nosw(sbase + kPD + 16384, 128, 1024);
+  const uint32_t cf0 = smem_u32(&bars->cfull[0]), ce0 = smem_u32(&bars->cempty[0]);
+  const uint32_t df0 = smem_u32(&bars->dfull[0]), de0 = smem_u32(&bars->dempty[0]);
+  const bool no_mma = (dbg & kDbgNoMma) != 0;
+  if (kChain) {
+    mbar_wait_spin(smem_u32(&bars->wfull), 0);
+    tc_fence_after();
+  }
+  RingPos c{0, 0}, d{0, 0};
+  uint32_t it = 0, dacc = 0;
+  for (int64_t s = s_first; s < n_super; s += s_step, ++it) {
+    int kp = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      if (seq_kind(i) == 0) {
+        if (kChain) {
+          if (kp == 0 && it > 0) {
+            mbar_wait_spin(smem_u32(&bars->acc_empty), (it - 1) & 1u);   // both CTAs drained D1 of the previous super-tile
+            tc_fence_after();
+          }
+          mbar_wait_spin(cf0 + 8u * c.s, c.ph);
+          tc_fence_after();
+          if (!no_mma) {
+            const uint64_t a = a_c0 + (uint64_t)(c.s * (uint32_t)(kPCBytes >> 4));
+            const uint64_t b = b_c0 + (uint64_t)(kp * (16384 >> 4));
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              umma_pair(d1, a + (uint64_t)(k * (4096 >> 4)), b + (uint64_t)(2 * k), idesc_c, (kp > 0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit_pair(ce0 + 8u * c.s);
+          if (kp == 3) umma_commit_pair(smem_u32(&bars->acc_full));
+          c.next(kPCStages);
+        }
+        ++kp;
+      } else {
+        mbar_wait_spin(df0 + 8u * d.s, d.ph);
+        tc_fence_after();
+        if (!no_mma) {
+          const uint64_t off = (uint64_t)(d.s * (uint32_t)(kPDBytes >> 4));
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            umma_pair(d2, a_d0 + off + (uint64_t)(k * (256 >> 4)), b_d0 + off + (uint64_t)(k * (256 >> 4)), idesc_d, dacc);
+            dacc = 1u;
+          }
+        }
+        umma_commit_pair(de0 + 8u * d.s);
+        d.next(kPDStages);
+      }
+    }
+  }
+  umma_commit_pair(smem_u32(&bars->fin));
+}
+
+// ---- bias-gradient warps (18, 19): column sums of the dZ slabs this CTA streams (its 128 features) -----------------------------
+__device__ __forceinline__ void pipe_bias(const PipeGroup& G, PipeBars* bars, uint32_t sbase, int tid64, int lane,
+                                          int64_t s_first, int64_t s_step, int64_t n_super, float* s0_out, float* s1_out) {
+  // thread owns feature columns 2 tid64, 2 tid64 + 1 of this CTA's half = chunk tid64 / 4, 32-bit word tid64 % 4
+  const bool col_ok = 2 * tid64 < (int)G.b_chunks * 8;
+  const uint32_t rot = (uint32_t)(tid64 >> 2) & 7u;
+  float s0 = 0.f, s1 = 0.f;
+  RingPos d{0, 0};
+  for (int64_t s = s_first; s < n_super; s += s_step) {
+    for (int j = 0; j < 4; ++j) {
+      mbar_wait(smem_u32(&bars->dfull[d.s]), d.ph);
+      if (col_ok) {
+        const uint32_t pb = sbase + kPD + d.s * kPDBytes + 16384u + (uint32_t)(tid64 >> 2) * 1024u + (uint32_t)(tid64 & 3) * 4u;
+        float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f;
+#pragma unroll 8
+        for (uint32_t i = 0; i < 64; i += 2) {
+          const uint32_t w0 = lds32u(pb + (((i + rot) & 63u) << 4));
+          const uint32_t w1 = lds32u(pb + (((i + 1 + rot) & 63u) << 4));
+          a0 += __uint_as_float(w0 << 16);
+          a1 += __uint_as_float(w0 & 0xffff0000u);
+          b0 += __uint_as_float(w1 << 16);
+          b1 += __uint_as_float(w1 & 0xffff0000u);
+        }
+        s0 += a0 + b0;
+        s1 += a1 + b1;
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&bars->dempty[d.s]));
+      d.next(kPDStages);
+    }
+  }
+  *s0_out = s0;
+  *s1_out = s1;
+}
+
+// sign-mask bit of element e of a 32-column group (layout of neg_mask32, mlp_tc.cu): true on the positive side
+__device__ __forceinline__ bool pipe_mask_bit(uint32_t mw, int e) { return !((mw >> (8 * (e & 3) + 7 - (e >> 2))) & 1u); }
+
+// ---- the kernel -----------------------------------------------------------------------------------------------------------------
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreadsFwd, 1)
+mlp_tc_bwd_pipe_kernel(const __grid_constant__ PipePlan plan, const uint8_t* __restrict__ packed,
+                       const uint8_t* __restrict__ saved, uint8_t* __restrict__ dz_ws, int64_t M,
+                       float* __restrict__ scratch, uint32_t* __restrict__ flags, float alpha, uint32_t dbg) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const uint32_t sbase = smem_u32(smem);
+  if ((sbase & 1023u) != 0u) __trap();
+  PipeBars* bars = reinterpret_cast<PipeBars*>(smem + kPBar);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int pair = (int)cluster_id_x();
+
+  int gi = 0;
+  while (gi + 1 < plan.n_groups && pair >= plan.g[gi].first_pair + plan.g[gi].n_pairs) ++gi;
+  const PipeGroup& G = plan.g[gi];
+  const bool active = pair < G.first_pair + G.n_pairs;
+  const bool chain = G.role == PIPE_ROLE_LAYER;
+  const int64_t n_tiles = (M + kTileM - 1) / kTileM;
+  const int64_t n_super = (n_tiles + 1) / 2;
+  const int64_t s_first = active ? pair - G.first_pair : n_super, s_step = G.n_pairs;
+
+  if (threadIdx.x == 0) {
+    const uint32_t full_count = rank == 0 ? 2u : 1u;       // the leader's copy also counts the peer's relay
+    mbar_init(smem_u32(&bars->wfull), full_count);
+    for (int i = 0; i < kPCStages; ++i) { mbar_init(smem_u32(&bars->cfull[i]), full_count); mbar_init(smem_u32(&bars->cempty[i]), 1); }
+    for (int i = 0; i < kPDStages; ++i) { mbar_init(smem_u32(&bars->dfull[i]), full_count); mbar_init(smem_u32(&bars->dempty[i]), 3); }
+    mbar_init(smem_u32(&bars->acc_full), 1);
+    mbar_init(smem_u32(&bars->acc_empty), 2 * 16);          // one arrive per epilogue warp of BOTH CTAs
+    mbar_init(smem_u32(&bars->fin), 1);
+    fence_barrier_init();
+  }
+  cluster_sync_all();
+  if (warp == kWarpMma) tmem_alloc_pair(smem_u32(&bars->tmem_base), 512);
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = bars->tmem_base;
+  float* part = scratch + (size_t)pair * kDwPartialFloats;   // this pair's split-K partial: [256 k][256 n] fp32 + 256 bias sums
+
+  if (warp == kWarpProducer) {
+    if (chain) pipe_producer<true>(G, bars, sbase, rank, lane, packed, saved, dz_ws, flags, s_first, s_step, n_super, dbg);
+    else pipe_producer<false>(G, bars, sbase, rank, lane, packed, saved, dz_ws, flags, s_first, s_step, n_super, dbg);
+  } else if (warp == kWarpMma) {
+    if (lane == 0) {
+      if (rank == 0) {
+        if (chain) pipe_mma<true>(G, bars, sbase, tmem_base, s_first, s_step, n_super, dbg);
+        else pipe_mma<false>(G, bars, sbase, tmem_base, s_first, s_step, n_super, dbg);
+      } else {
+        if (chain) pipe_relay<true>(bars, s_first, s_step, n_super);
+        else pipe_relay<false>(bars, s_first, s_step, n_super);
+      }
+    }
+  } else if (warp >= kWarpStore) {
+    const int tid64 = (warp - kWarpStore) * 32 + lane;
+    float s0, s1;
+    pipe_bias(G, bars, sbase, tid64, lane, s_first, s_step, n_super, &s0, &s1);
+    if (active && 2 * tid64 < (int)G.b_chunks * 8) {
+      part[256 * 256 + rank * (int)G.b_chunks * 8 + 2 * tid64] = s0;
+      part[256 * 256 + rank * (int)G.b_chunks * 8 + 2 * tid64 + 1] = s1;
+    }
+  } else {
+    // ===== 16 epilogue warps: TMEM lane quarter q = warp % 4, column quarter cq = warp / 4 =====
+    const int q = warp & 3, cq = warp >> 2;
+    const int r = q * 32 + lane;
+    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
+    if (chain) {
+      const uint32_t acc_empty_leader = mapa_shared(smem_u32(&bars->acc_empty), 0);
+      uint32_t it = 0;
+      for (int64_t s = s_first; s < n_super; s += s_step, ++it) {
+        const int64_t tile = 2 * s + rank;
+        const uint32_t* saved_mask =
+            reinterpret_cast<const uint32_t*>(saved + (size_t)tile * kSavedTileBytes + (size_t)kSavedPanels * kPanelBytes);
+        uint32_t mw[2];
+#pragma unroll
+        for (int j = 0; j < 2; ++j) mw[j] = __ldg(saved_mask + ((int)G.mask_row * 8 + cq * 2 + j) * 128 + r);
+        mbar_wait(smem_u32(&bars->acc_full), it & 1u);
+        tc_fence_after();
+        uint32_t acc[2][32];
+        tmem_ld32(taddr + cq * 64, acc[0]);
+        tmem_ld32(taddr + cq * 64 + 32, acc[1]);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(acc_empty_leader);       // D1 may be overwritten by the next super-tile
+        uint8_t* gout = dz_ws + (size_t)((dbg & kDbgWrapDz) ? 2 * (s & 127) + rank : tile) * kDzTileBytes + (size_t)G.out_off;
+        if (!(dbg & kDbgNoStore)) {
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {
+#pragma unroll
+            for (int g8 = 0; g8 < 4; ++g8) {
+              float v[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const float a = __uint_as_float(acc[j][8 * g8 + i]);
+                v[i] = pipe_mask_bit(mw[j], 8 * g8 + i) ? a : alpha * a;
+              }
+              stg128(gout + rbcm_offset(r, cq * 8 + j * 4 + g8, 32),
+                     make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7])));
+            }
+          }
+        }
+        if (G.signal_flag >= 0) {
+          __syncwarp();
+          if (lane == 0) flag_signal(flags + (size_t)s * kPipeFlagsPerSuper + G.signal_flag);
+        }
+      }
+    }
+    // ---- drain this CTA's half of the dW accumulator: rows k = 128 rank + lane, this warp's 64 columns ----
+    if (active) {
+      mbar_wait(smem_u32(&bars->fin), 0);
+      tc_fence_after();
+      if (s_first < n_super && !(dbg & kDbgNoDrain)) {
+        const int k = (int)rank * 128 + r;
+#pragma unroll 1
+        for (int c0 = cq * 64; c0 < cq * 64 + 64 && c0 < (int)G.n_dw; c0 += 16) {
+          uint32_t a[16];
+          tmem_ld16(taddr + 256u + (uint32_t)c0, a);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 16; i += 4) stg128(part + (size_t)k * 256 + c0 + i, make_uint4(a[i], a[i + 1], a[i + 2], a[i + 3]));
+        }
+      }
+      tc_fence_before();
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                                  // the peer's shared memory / TMEM stay valid until both are done
+  if (warp == kWarpMma) tmem_dealloc_pair(tmem_base, 512);
+}
+
+// Adds the per-pair split-K partials of every group into the flat gradient vector, in pair order (deterministic).
+// grid = (n_groups, 64), 256 threads: thread = one float4 of the group's [256][256] block (+ the bias row, block y == 0).
+__global__ void __launch_bounds__(256)
+mlp_tc_bwd_pipe_reduce_kernel(const __grid_constant__ PipePlan plan, const __grid_constant__ NetGeom g,
+                              const float* __restrict__ scratch, int64_t M, float* __restrict__ Gr) {
+  const PipeGroup& G = plan.g[blockIdx.x];
+  const int64_t n_tiles = (M + kTileM - 1) / kTileM;
+  const int64_t n_super = (n_tiles + 1) / 2;
+  const int live = (int)(n_super < G.n_pairs ? n_super : G.n_pairs);      // pairs that had a super-tile
+  const float* base = scratch + (size_t)G.first_pair * kDwPartialFloats;
+  const int e4 = blockIdx.y * 256 + threadIdx.x;                          // float4 index inside [256][64 float4]
+  const int k = e4 >> 6, n0 = (e4 & 63) * 4;
+  const bool head = G.role == PIPE_ROLE_DW_ONLY;                          // Dense 8 (+ sigma head in column 128), h8 rows
+  if (n0 < (int)G.n_dw) {
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int s = 0; s < live; ++s) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(base + (size_t)s * kDwPartialFloats + k * 256 + n0));
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+    const float vals[4] = {acc.x, acc.y, acc.z, acc.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int n = n0 + i;
+      float* tgt = nullptr;
+      if (!head) {
+        const LayerDesc& L = g.layers[G.dense];
+        tgt = Gr + L.w_off + (int64_t)((G.dense == 4 ? g.dx : 0) + k) * L.out + n;
+      } else if (n < 128) {
+        tgt = Gr + g.layers[8].w_off + (int64_t)k * 128 + n;
+      } else if (n == 128) {
+        tgt = Gr + g.layers[10].w_off + k;
+      }
+      if (tgt) *tgt += vals[i];
+    }
+  }
+  if (blockIdx.y == 0 && G.has_bias && threadIdx.x < G.n_dw) {
+    float acc = 0.f;
+    for (int s = 0; s < live; ++s) acc += __ldg(base + (size_t)s * kDwPartialFloats + 256 * 256 + threadIdx.x);
+    const int n = threadIdx.x;
+    float* tgt = nullptr;
+    if (!head) tgt = Gr + g.layers[G.dense].b_off + n;
+    else if (n < 128) tgt = Gr + g.layers[8].b_off + n;
+    else if (n == 128) tgt = Gr + g.layers[10].b_off;
+    if (tgt) *tgt += acc;
+  }
+}
+
+// ---- host ---------------------------------------------------------------------------------------------------------------
+uint32_t bwd_pack_layer_offset(int layer);      // mlp_tc_bwd.cu
+
+static void fill_layer_group(PipeGroup* G, int l) {
+  memset(G, 0, sizeof(*G));
+  G->role = PIPE_ROLE_LAYER;
+  G->layer = (int16_t)l;
+  G->wait_flag = G->signal_flag = -1;
+  G->n_chain = 256; G->n_dw = 256; G->b_chunks = 16; G->b_half_chunks = 32;
+  G->mask_row = (int16_t)(l - 1);
+  G->dense = (int16_t)l;
+  G->has_bias = 1;
+  G->w_off = (int32_t)bwd_pack_layer_offset(l);
+  G->a_off = saved_panel_h(l) * kPanelBytes;
+  G->b_off = dz_panel(l + 1) * kPanelBytes;
+  G->out_off = dz_panel(l) * kPanelBytes;
+}
+
+// Dense 8 + sigma head, h8 rows: dW only (A = h8, B = dZ_L' incl. the sigma column: N = 144, 72 features per CTA)
+static void fill_head_group(PipeGroup* G) {
+  memset(G, 0, sizeof(*G));
+  G->role = PIPE_ROLE_DW_ONLY;
+  G->layer = 8;
+  G->wait_flag = G->signal_flag = -1;
+  G->n_chain = 256; G->n_dw = 144; G->b_chunks = 9; G->b_half_chunks = kDzChunksL;
+  G->dense = 8;
+  G->has_bias = 1;
+  G->a_off = saved_panel_h(8) * kPanelBytes;
+  G->b_off = kDzPanelL * kPanelBytes;
+}
+
+static int pipe_launch(const PipePlan& plan, const NetGeom& g, const uint8_t* packed_bwd, const void* saved, uint8_t* dz_ws,
+                       int64_t m, float* scratch, uint32_t* flags, float* grads, float alpha, cudaStream_t st) {
+  if (device_first_use(2))
+    NERF_CUDA(cudaFuncSetAttribute(mlp_tc_bwd_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPAlloc));
+  int n_pairs = 0;
+  for (int i = 0; i < plan.n_groups; ++i) n_pairs += plan.g[i].n_pairs;
+  mlp_tc_bwd_pipe_kernel<<<2 * n_pairs, kThreadsFwd, kPAlloc, st>>>(plan, packed_bwd, (const uint8_t*)saved, dz_ws, m, scratch,
+                                                                   flags, alpha, tc_debug_flags());
+  NERF_CHECK_LAUNCH();
+  mlp_tc_bwd_pipe_reduce_kernel<<<dim3(plan.n_groups, 64), 256, 0, st>>>(plan, g, scratch, m, grads);
+  NERF_CHECK_LAUNCH();
+  return NERF_OK;
+}
+
+// Diagnostic: ONE group over every CTA pair for Dense `layer` (1..7: chain + dW; 8: dW of the h8 rows only), reading
+// dZ_{layer+1} from a workspace a previous nerf_mlp_bwd[_dx] filled.  Writes dZ_layer back into the workspace and ADDS the
+// weight / bias gradient of that Dense layer to `grads`.
+int mlp_tc_bwd_pipe_single(const nerf_net_cfg* cfg, const NetGeom& g, const uint8_t* packed_bwd, const void* saved,
+                           int64_t m, void* workspace, int layer, float* grads, cudaStream_t st) {
+  PipePlan plan;
+  memset(&plan, 0, sizeof(plan));
+  plan.n_groups = 1;
+  if (layer == 8) fill_head_group(&plan.g[0]);
+  else fill_layer_group(&plan.g[0], layer);
+  plan.g[0].first_pair = 0;
+  plan.g[0].n_pairs = (int16_t)(num_sms() / 2);
+  uint8_t* dz_ws = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(workspace) + 1023) & ~(uintptr_t)1023);
+  const int64_t tiles4 = ((m + kTileM - 1) / kTileM + 3) / 4 * 4;
+  float* scratch = reinterpret_cast<float*>(dz_ws + tiles4 * (int64_t)kDzTileBytes);
+  return pipe_launch(plan, g, packed_bwd, saved, dz_ws, m, scratch, nullptr, grads, cfg->leaky_alpha, st);
+}
+
+}  // namespace nerf
+
+using namespace nerf;
+
+extern "C" int nerf_debug_bwd_pipe_layer(const nerf_net_cfg* cfg, const void* packed, const void* saved, int64_t m,
+                                         void* workspace, int32_t layer, float* grads, void* stream) {
+  NetGeom g;
+  TcPlan fplan;
+  NERF_CHECK_ARG(make_geom(cfg, &g) && make_plan(g, &fplan), "network not supported by NERF_MODE_BF16");
+  NERF_CHECK_ARG(packed && saved && workspace && grads, "null pointer");
+  NERF_CHECK_ARG(layer >= 1 && layer <= 8 && m > 0, "layer must be 1..8");
+  const uint8_t* packed_bwd = (const uint8_t*)packed + ((fplan.total_bytes + 1023u) & ~1023u);
+  return mlp_tc_bwd_pipe_single(cfg, g, packed_bwd, saved, m, workspace, layer, grads, (cudaStream_t)stream);
+}

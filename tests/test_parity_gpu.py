@@ -1029,3 +1029,125 @@ def test_c_caller_trains_and_renders(pkg):
         assert out["caller"] == "c" and out["finite"] == 1 and out["rays"] == 4096 and out["steps"] == steps
         assert out["loss_last"] < (0.8 if mode == 1 else 1.0) * out["loss_first"]
         assert abs(out["render_psnr"] - out["psnr_fine_last"]) < 3.0
+
+
+# ---- round 2: backward variants --------------------------------------------------------------------------------------------
+def _bwd_setup(pkg, n_rays, s, seed=5):
+    call, ptr = pkg._lib.call, pkg._lib.ptr
+    cfg = pkg.NetCfg(5, 4, 2, 256, 128, 0.05)
+    net = pkg.NerfMLP(cfg, mode="bf16", seed=3)
+    m = n_rays * s
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    o4 = torch.randn(n_rays, 4, device="cuda", generator=g)
+    d4 = torch.randn(n_rays, 4, device="cuda", generator=g)
+    z = torch.sort(torch.rand(n_rays, s, device="cuda", generator=g) * 2 + 0.5, -1).values.contiguous()
+    d_out = torch.randn(m, 4, device="cuda", generator=g)
+    out = torch.empty(m, 4, device="cuda")
+    packed = net.packed_for(net.params)
+    saved = torch.empty(net.saved_bytes(m), dtype=torch.uint8, device="cuda")
+    ws = torch.empty(net.workspace_bytes(m, True), dtype=torch.uint8, device="cuda")
+    call("nerf_mlp_fwd_rays", net.cfg_ref, ptr(packed), ptr(o4), ptr(d4), ptr(z), n_rays, s, ptr(out), ptr(saved), net.mode_id)
+    return net, packed, saved, ws, d_out, m
+
+
+@pytest.mark.parametrize("n_rays,s", [(151, 32), (2048 + 37, 64)])
+def test_mlp_backward_two_streams_and_overlapped(pkg, n_rays, s, monkeypatch):
+    """nerf_mlp_bwd_overlapped: (a) default = chain on the stream, dW kernel on the side stream after it -- the same kernels
+    and grids as nerf_mlp_bwd, bit-identical; (b) NERF_BWD_OVERLAP=1 = both at once on disjoint SMs with the dZ hand-over
+    counters: d_xyz bit-identical, weight gradients equal to fp32 summation order, and deterministic."""
+    call, ptr = pkg._lib.call, pkg._lib.ptr
+    net, packed, saved, ws, d_out, m = _bwd_setup(pkg, n_rays, s)
+    side, main = torch.cuda.Stream(), torch.cuda.current_stream()
+
+    def run(entry, *tail):
+        grads = torch.zeros(net.n_params, device="cuda")
+        d_xyz = torch.empty(m, 33, device="cuda")
+        call(entry, net.cfg_ref, ptr(net.params), ptr(packed), None, None, ptr(saved), ptr(d_out), m, ptr(grads), ptr(d_xyz),
+             ptr(ws), net.mode_id, *tail)
+        main.wait_stream(side)
+        torch.cuda.synchronize()
+        return grads, d_xyz
+
+    g0, x0 = run("nerf_mlp_bwd")
+    g1, x1 = run("nerf_mlp_bwd_overlapped", side.cuda_stream)
+    assert torch.equal(g0, g1) and torch.equal(x0, x1)
+    monkeypatch.setenv("NERF_BWD_OVERLAP", "1")
+    g2, x2 = run("nerf_mlp_bwd_overlapped", side.cuda_stream)
+    g3, x3 = run("nerf_mlp_bwd_overlapped", side.cuda_stream)
+    assert torch.equal(x0, x2)
+    rel = ((g2 - g0).norm() / g0.norm()).item()
+    assert rel < 5e-4, f"overlapped weight gradients differ from the sequential ones by {rel:.2e}"
+    assert torch.equal(g2, g3) and torch.equal(x2, x3), "the overlapped backward is not deterministic"
+
+
+@pytest.mark.parametrize("n_rays,s", [(151, 32), (1024 + 5, 64)])
+def test_bwd_pipe_stage_matches_chain_and_dw(pkg, n_rays, s):
+    """One stage of the layer-pipelined backward kernel (chain step + weight gradient of a layer on the same CTA pair,
+    mlp_tc_bwd_pipe.cu) against the two production kernels: dZ_l bit for bit, dW_l / db_l to fp32 summation order."""
+    call, ptr = pkg._lib.call, pkg._lib.ptr
+    net, packed, saved, ws, d_out, m = _bwd_setup(pkg, n_rays, s, seed=6)
+    ref = torch.zeros(net.n_params, device="cuda")
+    call("nerf_mlp_bwd", net.cfg_ref, ptr(net.params), ptr(packed), None, None, ptr(saved), ptr(d_out), m, ptr(ref), None,
+         ptr(ws), net.mode_id)
+    torch.cuda.synchronize()
+    tiles4 = ((m + 127) // 128 + 3) // 4 * 4
+    tile_bytes = 36 * 16384
+    base = (-ws.data_ptr()) % 1024
+    region = slice(base, base + tiles4 * tile_bytes)
+    shapes = [(33, 256)] + [(256, 256)] * 3 + [(289, 256)] + [(256, 256)] * 3 + [(280, 128), (128, 3), (280, 1)]
+    offs, off = [], 0
+    for i, o in shapes:
+        offs.append((off, off + i * o, off + i * o + o))
+        off += i * o + o
+    for layer in (7, 4, 1, 8):
+        ws2 = torch.empty(ws.numel() + 1024, dtype=torch.uint8, device="cuda")
+        shift = (base - ws2.data_ptr()) % 1024          # same 1024-byte phase as the original workspace
+        ws2 = ws2[shift:shift + ws.numel()]
+        ws2.copy_(ws)
+        if layer <= 7:
+            # the stage must rewrite dZ_l of every tile of its super-tiles (the padding tiles of the last quad are not its)
+            n_used = (((m + 127) // 128 + 1) // 2) * 2
+            ws2[region].view(tiles4, tile_bytes)[:n_used, (layer - 1) * 65536:layer * 65536] = 0x7f
+        grads = torch.zeros(net.n_params, device="cuda")
+        call("nerf_debug_bwd_pipe_layer", net.cfg_ref, ptr(packed), ptr(saved), m, ptr(ws2), layer, ptr(grads))
+        torch.cuda.synchronize()
+        assert torch.equal(ws2[region], ws[region]), f"dZ_{layer} differs from the chain kernel's"
+        w0, w1, b1 = offs[layer]
+        gw, rw = grads[w0:w1], ref[w0:w1]
+        if layer == 4:
+            gw, rw = gw[33 * 256:], rw[33 * 256:]                     # the h4 rows of Dense 4
+        if layer == 8:
+            gw, rw = gw[:256 * 128], rw[:256 * 128]                   # the h8 rows of Dense 8 ...
+            s0, s1, _ = offs[10]                                      # ... and of the sigma head
+            assert ((grads[s0:s0 + 256] - ref[s0:s0 + 256]).norm() / ref[s0:s0 + 256].norm()).item() < 1e-4
+            assert abs((grads[s1] - ref[s1]).item()) < 1e-4 * abs(ref[s1].item()) + 1e-7
+        assert ((gw - rw).norm() / rw.norm()).item() < 1e-4, f"dW of Dense {layer}"
+        assert ((grads[w1:b1] - ref[w1:b1]).norm() / ref[w1:b1].norm()).item() < 1e-4, f"db of Dense {layer}"
+
+
+def test_train_step_gradients_at_bench_shape(pkg):
+    """The bench's own shape -- 2048 rays x (64 coarse + 128 fine) samples, bf16 -- against oracle autograd (same bf16
+    operand rounding): 131 072 / 262 144 MLP rows = 256 / 512 quads over 74 CTA pairs, so the persistent multi-quad loops
+    of the forward and chain kernels and the many-tile split-K of all 148 dW CTAs are compared with the ORACLE, not only
+    with themselves.  Importance samples detached on both sides (see test_train_step_gradients for why); the fine
+    network's gradient does not depend on that switch."""
+    n = 2048
+    model, ocfg, pc, pf = _model(pkg, "bf16", sigma_gain=4.0, stop_grad_z=True)
+    o, d = random_rays(n, 4)
+    y = torch.rand(n, 3, generator=torch.Generator().manual_seed(5))
+    jit, u = O.stratified_jitter(7, 0, n, 64), O.importance_uniforms(7, 0, n, 128)
+    metrics, gc, gf, _ = O.train_step(pc, pf, ocfg, NEAR, FAR, o, d, y, 64, 128, jit, u, emulate_bf16=True, stop_grad_z=True)
+    g_c, g_f, sums = model.forward_backward(dev(o), dev(d), dev(y), seed=7, step=0)
+    rel_c = ((g_c.cpu() - gc).norm() / gc.norm()).item()
+    rel_f = ((g_f.cpu() - gf).norm() / gf.norm()).item()
+    per_c = _per_tensor_rel(ocfg.shapes, g_c.cpu(), gc)
+    per_f = _per_tensor_rel(ocfg.shapes, g_f.cpu(), gf)
+    print(f"bench-shape train step: grad rel err coarse {rel_c:.4f} fine {rel_f:.4f}; worst tensor {max(per_c):.3f} / {max(per_f):.3f}")
+    assert rel_c < 3e-2 and rel_f < 3e-2, (rel_c, rel_f)
+    assert max(per_c) < 0.3 and max(per_f) < 0.3, (per_c, per_f)
+    m = model._metrics(sums.clone(), n)
+    assert abs(m["loss"].item() - metrics["loss"].item()) < 2e-3
+    # and the same step again is bit-identical (deterministic split-K at full occupancy)
+    g_c, g_f = g_c.clone(), g_f.clone()
+    g2 = model.forward_backward(dev(o), dev(d), dev(y), seed=7, step=0)
+    assert torch.equal(g2[0], g_c) and torch.equal(g2[1], g_f)

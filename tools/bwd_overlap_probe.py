@@ -24,6 +24,7 @@ def main():
     call, ptr = pkg._lib.call, pkg._lib.ptr
     cfg = pkg.NetCfg(5, 4, 2, 256, 128, 0.05)
     net = pkg.NerfMLP(cfg, mode="bf16", seed=0)
+    os.environ["NERF_BWD_OVERLAP"] = "1"
     side = torch.cuda.Stream()
     main_s = torch.cuda.current_stream()
     for s in [int(x) for x in args.samples.split(",")]:
