@@ -2,18 +2,21 @@
 """Headline benchmark of the NeRF ray-render hot path: rays/s of the full train step
 (render forward of the coarse+fine networks, loss, fused backward, Adam) on synthetic ray batches.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--config NAME] [--mode bf16|fp32]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--config NAME] [--mode fp16|bf16|fp32]
 
-Workload (BASELINE.json configs[1], config_files/100px_robot_72pics_sphere.yaml): 2048 rays per step PER GPU,
-64 coarse + 128 fine samples per ray, 8x256 MLPs with view branch, Glorot-initialised weights, rays from sphere cameras
-(near/far 0.3333/2.0, fov 0.69111), targets U[0,1).  Weak scaling: every rank runs its own 2048-ray shard of a
-global batch of N*2048 rays, with ONE NCCL all-reduce of the 4.1 MB gradient vector per step.
+Workload (BASELINE.json configs[2], config_files/256px_alexander_71pics_sphere_nerf.yaml, the largest single-GPU training
+config): 4096 rays per step PER GPU, 64 coarse + 128 fine samples per ray, 8x256 MLPs with view branch, Glorot-initialised
+weights, rays from sphere cameras (near/far 0.5576/2.5635, fov 0.46134), targets U[0,1).  Weak scaling: every rank runs its
+own 4096-ray shard of a global batch of N*4096 rays, with the gradient all-reduce(s) of the step over NCCL.
 
 Prints ONE JSON line (rank 0).  `value` = rays/s with the ray batch resident in HBM, timed on the device with CUDA
-events over exactly K steps (max over ranks); `e2e` = the same metric through the public API `NeRF.train_step` with
-PINNED HOST batches (H2D copy of the batch and D2H read of the loss inside the timed region, every step).
-`--impl reference` times the CPU oracle port of the reference's train step (TensorFlow is not installable here) on
-all host cores, on a bounded sample of the same workload.
+events over exactly K steps (max over ranks) -- a BURST after an idle second; `sustained` = the same loop run for >= 2 s
+of device time without the idle (power-capped clocks); `e2e` = the same metric through the public API `NeRF.train_step`
+with PINNED HOST batches (H2D copy of the batch and D2H read of the loss inside the timed region, every step).
+Sub-records measured in the same run: `render` (one 256x256 frame, 64 coarse + 192 fine samples), `composite`
+(alpha compositing at 65 536 rays x 192 samples against the HBM peak), `strong` (N > 1: the YAML's 4096-ray batch split
+over the N ranks).  `--impl reference` times the CPU port of the reference's train step (TensorFlow is not installable
+here) on all host cores, on a bounded sample of the same workload.
 """
 import argparse
 import contextlib
@@ -120,10 +123,17 @@ class ClockSampler:
             self.proc.terminate()
 
 
+CPU_SAMPLE_RAYS = 1024              # bounded sample of the batch the CPU arm runs per step (a few seconds on 16 cores)
+
+
 def cpu_reference_rate(cfg_name, n_rays, reps, threads=None):
-    """rays/s of the oracle port of NeRF.train_step (forward + autograd backward + Adam) on the host cores."""
+    """rays/s of the CPU port of NeRF.train_step (forward + autograd backward + Adam) on the host cores.  The port is the
+    oracle with its per-sample Python loops (the canonical summation order of the parity tests) switched to
+    torch.cumprod / cumsum / sum (oracle.FAST_REDUCTIONS): the throughput an optimised CPU implementation gets, on a
+    sample large enough (>= 1024 rays) that every op is a full-width tensor op."""
     import torch
     from oracle import nerf_oracle as O
+    O.FAST_REDUCTIONS = True
     batch, near, far, fov = CONFIGS[cfg_name]
     # all host threads, also under torchrun (which exports OMP_NUM_THREADS=1)
     torch.set_num_threads(threads or os.cpu_count() or 1)
@@ -146,11 +156,11 @@ def cpu_reference_rate(cfg_name, n_rays, reps, threads=None):
 def run_reference(args):
     """--impl reference: the reference's own CPU implementation of the path.  TensorFlow/Keras 2.7 cannot be installed
     in this image (no wheel, no network), so the line-by-line oracle port is what runs, on all host
-    threads, each step = a bounded 128-ray sample of the 2048-ray batch."""
+    threads, each step = a bounded 1024-ray sample of the batch (vectorised reductions, see cpu_reference_rate)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    n_sample = 128
+    n_sample = CPU_SAMPLE_RAYS
     t0 = time.perf_counter()
     rate, cores = cpu_reference_rate(args.config, n_sample, max(1, args.steps), None)
     batch = CONFIGS[args.config][0]
@@ -161,8 +171,8 @@ def run_reference(args):
         "config": {"workload": f"train_step {args.config}: {batch} rays/step/GPU, {N_C} coarse + {N_F} fine samples",
                    "sample": f"{n_sample}-ray sample of the batch per step"},
         "cpu_baseline": {"value": rate, "unit": "rays/s", "cores": cores, "kind": "port",
-                         "sample": f"{n_sample} rays x {N_C + N_F} samples per step, oracle port (PyTorch-CPU fp32) of "
-                                   "NeRF.train_step; TensorFlow unavailable offline"},
+                         "sample": f"{n_sample} rays x {N_C + N_F} samples per step, CPU port (PyTorch-CPU fp32, vectorised "
+                                   "cumprod/cumsum) of NeRF.train_step incl. Adam; TensorFlow unavailable offline"},
         "e2e": {"value": rate, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "wall_s": time.perf_counter() - t0,
     }
@@ -175,10 +185,13 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--config", default="100px_robot_72pics_sphere", choices=sorted(CONFIGS))
-    ap.add_argument("--mode", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--config", default="256px_alexander_71pics_sphere_nerf", choices=sorted(CONFIGS))
+    ap.add_argument("--mode", default="fp16", choices=["fp16", "bf16", "fp32"],
+                    help="fp16 (the product's default): fp16 forward operands, bf16 backward; bf16: bf16 everywhere")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--settle", type=float, default=1.0, help="idle seconds before each timed pass (power-cap state)")
+    ap.add_argument("--sustained-s", type=float, default=2.0, help="device seconds of the sustained pass (0 = skip)")
+    ap.add_argument("--no-extras", action="store_true", help="skip the render / composite / strong sub-records")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -311,13 +324,49 @@ def main():
     ms_dev, t0, t1 = timed(step_device, args.steps)
     launches = pkg._lib.launch_count - launches0
 
-    # per-call device times of the MLP kernels over a second timed pass (events on the launching stream)
+    # ---- sustained pass: the same loop for >= --sustained-s seconds of device time, no idle before it ---------------------
+    sustained = None
+    if args.sustained_s > 0:
+        chunk = max(20, args.steps)
+        barrier()
+        t_s0 = time.time()
+        evs = [torch.cuda.Event(enable_timing=True)]
+        evs[0].record()
+        n_done, dev_ms = 0, 0.0
+        while dev_ms < args.sustained_s * 1e3 and n_done < 200000:
+            for i in range(chunk):
+                step_device(n_done + i)
+            n_done += chunk
+            e = torch.cuda.Event(enable_timing=True)
+            e.record()
+            e.synchronize()
+            evs.append(e)
+            done = torch.tensor([evs[0].elapsed_time(e)], device="cuda")
+            if world > 1:                      # every rank runs the same number of chunks
+                dist.all_reduce(done, op=dist.ReduceOp.MAX)
+            dev_ms = done.item()
+        barrier()
+        t_s1 = time.time()
+        # steady state = the second half of the window (the first chunks still run at burst clocks)
+        half = len(evs) // 2
+        tail_ms = torch.tensor([evs[half].elapsed_time(evs[-1])], device="cuda")
+        if world > 1:
+            dist.all_reduce(tail_ms, op=dist.ReduceOp.MAX)
+        tail_steps = (len(evs) - 1 - half) * chunk
+        sustained = {"window_s": dev_ms * 1e-3, "steps": n_done, "ms_per_step": dev_ms / n_done,
+                     "value": n_total * n_done / (dev_ms * 1e-3), "unit": "rays/s",
+                     "second_half_ms_per_step": tail_ms.item() / max(tail_steps, 1),
+                     "second_half_value": n_total * tail_steps / (tail_ms.item() * 1e-3) if tail_steps else None,
+                     "clocks": sampler.window(t_s0, t_s1) if rank == 0 else None}
+
+    # per-call device times of the MLP kernels over another timed pass (events on the launching stream)
     per_call = {}
 
     @contextlib.contextmanager
     def hook(name):
         if name in ("nerf_mlp_fwd", "nerf_mlp_fwd_rays", "nerf_mlp_bwd", "nerf_mlp_bwd_dx", "nerf_mlp_bwd_dw",
-                    "nerf_composite_fwd", "nerf_composite_bwd"):
+                    "nerf_composite_fwd", "nerf_composite_bwd", "nerf_composite_mse_fwd", "nerf_composite_mse_fwd_bwd",
+                    "nerf_sample_pdf_fwd", "nerf_sample_pdf_bwd"):
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record()
             yield
@@ -326,9 +375,11 @@ def main():
         else:
             yield
     pkg._lib.event_hook = hook
-    model.overlap_dw = False          # one stream: each kernel is timed alone (the step itself overlaps the fine dW)
+    model.overlap_dw = False          # one stream, the backward's two halves as separate calls: each kernel is timed alone
+    type(model).split_bwd_calls = True
     timed(step_device, args.steps)
     model.overlap_dw = True
+    type(model).split_bwd_calls = False
     pkg._lib.event_hook = None
     torch.cuda.synchronize()
     call_ms = {k: sum(a.elapsed_time(b) for a, b in v) / len(v) for k, v in per_call.items()}
@@ -339,11 +390,84 @@ def main():
     ms_e2e, _, t_load1 = timed(run_e2e, args.steps, whole=True)
     assert len(losses) == args.steps and all(math.isfinite(v) for v in losses), "every step's loss must reach the host"
     # the device-timed region alone lasts ~0.1 s (one nvidia-smi sample); report the median over every sample taken
-    # while the GPU ran back-to-back steps (warm-up, device-timed, per-call-timed and e2e passes)
+    # while the GPU ran back-to-back steps (warm-up, device-timed, sustained, per-call-timed and e2e passes)
     clocks = sampler.window(t_load0, t_load1) if rank == 0 else None
     if clocks is not None:
-        clocks["window"] = ("warm-up through e2e pass; the GPU idles %.1f s before each timed pass so that every pass "
-                            "starts from the same power-cap state" % args.settle)
+        clocks["window"] = ("warm-up through e2e pass; the GPU idles %.1f s before each burst-timed pass so that every "
+                            "pass starts from the same power-cap state; the sustained pass has its own clocks record"
+                            % args.settle)
+
+    def dev_time(fn, iters, warm=2):
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(iters):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / iters
+
+    # ---- strong scaling: the YAML's batch split over the ranks (src/NeRF.py:136-147 fixes B from the config) ------------
+    strong = None
+    if world > 1 and not diet and not args.no_extras:
+        per = batch // world
+        sb = [tuple(t[rank * per:(rank + 1) * per].contiguous() for t in db) for db in devb]
+
+        def step_strong(i):
+            o, d, y = sb[i % n_batches]
+            return model.train_step_local(o, d, y, per * world, rank * per)
+        for i in range(5):
+            step_strong(i)
+        ms_strong, _, _ = timed(step_strong, args.steps)
+        strong = {"global_batch_rays": per * world, "rays_per_gpu": per, "ms_per_step": ms_strong / args.steps,
+                  "value": per * world * args.steps / (ms_strong * 1e-3), "unit": "rays/s",
+                  "note": "same optimisation problem at every N (the weak-scaling `value` grows the global batch)"}
+
+    # ---- render: one 256x256 frame, 64 coarse + 192 fine samples per ray (BASELINE configs[3]), this rank's row block ---
+    render = composite = None
+    if not args.no_extras and not diet:
+        h = w = 256
+        import numpy as np
+        c2w = np.eye(4, dtype=np.float32)
+        c2w[:3, 3] = [0.0, 0.0, 1.0]
+        lo, hi = (h * w * rank) // world, (h * w * (rank + 1)) // world
+        with torch.no_grad():
+            frame = lambda: model.render_image_lean(c2w, fov, h, w, 16384, N_C, 192, seed=1, step=0, ray_begin=lo,
+                                                    n_rays=hi - lo)
+            barrier()
+            ms_frame = torch.tensor([dev_time(frame, 3)], device="cuda")
+        if world > 1:
+            dist.all_reduce(ms_frame, op=dist.ReduceOp.MAX)
+        ms_frame = ms_frame.item()
+        flop_ray_render = 2 * MAC_FWD * (N_C + N_C + 192)
+        render = {"what": "render_image_lean, one 256x256 frame, 64 coarse + 192 fine samples/ray "
+                          "(fine network sees 256), rows sharded over the ranks, no collective",
+                  "ms_per_frame": ms_frame, "value": h * w / (ms_frame * 1e-3), "unit": "rays/s",
+                  "mlp_tflops": flop_ray_render * h * w / (ms_frame * 1e-3) / 1e12}
+        if rank == 0:
+            # ---- compositing alone at the size of one frame x 192 samples: all outputs / lean / backward ------------------
+            call, ptr = pkg._lib.call, pkg._lib.ptr
+            n, sm = 65536, 192
+            raw = torch.randn(n, sm, 4, device="cuda")
+            z = torch.sort(torch.rand(n, sm, device="cuda"), -1).values.contiguous()
+            rgb, wt, T = torch.empty(n, 3, device="cuda"), torch.empty(n, sm, device="cuda"), torch.empty(n, sm, device="cuda")
+            al, rs = torch.empty(n, sm, device="cuda"), torch.empty(n, sm, 3, device="cuda")
+            dep, acc = torch.empty(n, device="cuda"), torch.empty(n, device="cuda")
+            d_rgb, d_raw, d_z = torch.randn(n, 3, device="cuda"), torch.empty_like(raw), torch.empty_like(z)
+            full = dev_time(lambda: call("nerf_composite_fwd", ptr(raw), ptr(z), n, sm, ptr(rgb), ptr(wt), ptr(T), ptr(al),
+                                         ptr(rs), None, None), 10)
+            lean = dev_time(lambda: call("nerf_composite_fwd", ptr(raw), ptr(z), n, sm, ptr(rgb), ptr(wt), None, None, None,
+                                         ptr(dep), ptr(acc)), 10)
+            bwd = dev_time(lambda: call("nerf_composite_bwd", ptr(raw), ptr(z), ptr(d_rgb), ptr(wt), n, sm, ptr(d_raw),
+                                        ptr(d_z)), 10)
+            del raw, z, rgb, wt, T, al, rs, d_raw, d_z
+            gbs = lambda byts, ms: byts / (ms * 1e-3) / 1e9
+            composite = {"rays": n, "samples": sm, "unit": "GB/s (algorithmic bytes / device time)",
+                         "fwd_all_outputs": gbs(n * (sm * 44 + 12), full), "fwd_lean": gbs(n * (sm * 24 + 20), lean),
+                         "bwd": gbs(n * (sm * 44 + 12), bwd),
+                         "bytes_per_sample": {"fwd_all_outputs": 44, "fwd_lean": 24, "bwd": 44}}
     sampler.stop()
 
     if rank == 0:
@@ -355,68 +479,90 @@ def main():
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
         except (OSError, ValueError):
             pass
-        peak_tf = peaks.get("bf16_tflops_sustained", 1400.0)
-        peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained" if "bf16_tflops_sustained" in peaks else \
-            "fallback (B200_PROFILING.md: ~1.4 PFLOP/s sustained)"
-        # Dominant kernel by time (profiles/r01_i_launches_summary.txt: 35 % of the step): mlp_tc_bwd_dw_kernel, the weight
-        # gradients.  Its arithmetic intensity is fixed by the 256x256 output it keeps in TMEM (128 FLOP/B), so its
-        # roofline is HBM: it streams every saved activation and every dZ once.  Algorithmic bytes per sample (DESIGN.md
-        # 4): bf16 saved activations (64 + 8*256 + 128 columns) + bf16 dZ (8*256 + 144 + 16 columns) = 8896 B.  The
-        # launch time is the nerf_mlp_bwd_dw call (dW kernel + its 15 us fixed-order reduce), averaged over the coarse
-        # (64 samples/ray) and fine (128) calls of a step; `traffic` is dram read+write of the same two launches from
-        # the ncu --set full capture (profiles/r01_i_mlp_full_summary.txt: 1.285 + 2.586 GB for 131072 + 262144 rows
-        # = 9845 B/sample).
+        peak_burst = peaks.get("bf16_tflops", 1640.0)
+        peak_sust = peaks.get("bf16_tflops_sustained", 1400.0)
+        peak_src = "MEASURED_PEAKS.json bf16_tflops (burst) / bf16_tflops_sustained" if "bf16_tflops" in peaks else \
+            "fallback (B200_PROFILING.md)"
+        peak_hbm = peaks.get("hbm_gbs", 6500.0)
+        # Dominant kernel by time: mlp_tc_bwd_dw_kernel, the weight gradients.  Its arithmetic intensity is fixed by the
+        # 256x256 output it keeps in TMEM (128 FLOP/B), so its roofline is bandwidth: it streams every saved activation and
+        # every dZ once.  Algorithmic bytes per sample: bf16 saved activations (64 + 8*256 + 128 columns) +
+        # bf16 dZ (8*256 + 144 + 16 columns) = 8896 B.  The launch time is the nerf_mlp_bwd_dw call (dW kernel + its
+        # fixed-order reduce), averaged over the coarse (64 samples/ray) and fine (128) calls of a step, timed with CUDA
+        # events in THIS run (the per-call pass above).  `traffic` is NOT measured in this run: it is the dram read+write
+        # of the same two launches in the committed ncu --set full capture (9845 B/sample), scaled to this batch.
         samples_per_launch = batch * (N_C + N_F) / 2
         dw_ms = call_ms.get("nerf_mlp_bwd_dw", float("nan"))
         dx_ms = call_ms.get("nerf_mlp_bwd_dx", float("nan"))
         fwd_ms = call_ms.get("nerf_mlp_fwd_rays", call_ms.get("nerf_mlp_fwd", float("nan")))
-        peak_hbm = peaks.get("hbm_gbs", 6500.0)
         fwd_flops = 2 * batch * (N_C + N_F) * MAC_FWD / 2
         dx_flops = 2 * batch * (N_C * MAC_DX_COARSE + N_F * MAC_DX_FINE) / 2
         dw_flops = fwd_flops
         ach = 8896 * samples_per_launch / (dw_ms * 1e-3) / 1e9
+        step_tf = FLOP_PER_RAY_TRAIN * value / world / 1e12
         tensor = {
-            "peak": peak_tf, "peak_source": peak_src, "unit": "TFLOP/s",
+            "unit": "TFLOP/s", "peak_source": peak_src, "flop_per_ray": FLOP_PER_RAY_TRAIN,
+            "burst": {"peak": peak_burst, "achieved": step_tf, "frac": step_tf / peak_burst,
+                      "window": f"{args.steps} steps after {args.settle} s idle (`value`)"},
             "mlp_tc_fwd_kernel<save>": {"achieved": fwd_flops / (fwd_ms * 1e-3) / 1e12, "ms": fwd_ms},
             "mlp_tc_bwd_chain_kernel": {"achieved": dx_flops / (dx_ms * 1e-3) / 1e12, "ms": dx_ms},
             "mlp_tc_bwd_dw_kernel": {"achieved": dw_flops / (dw_ms * 1e-3) / 1e12, "ms": dw_ms},
-            "step_tensor_frac": FLOP_PER_RAY_TRAIN * value / 1e12 / peak_tf,
+            "step_tensor_frac": step_tf / peak_burst,
         }
+        if sustained is not None:
+            s_tf = FLOP_PER_RAY_TRAIN * sustained["value"] / world / 1e12
+            s2 = sustained.get("second_half_value")
+            tensor["sustained"] = {"peak": peak_sust, "achieved": s_tf, "frac": s_tf / peak_sust,
+                                   "second_half_frac": (FLOP_PER_RAY_TRAIN * s2 / world / 1e12 / peak_sust) if s2 else None,
+                                   "window": "%.2f s of back-to-back steps, no idle before it" % sustained["window_s"]}
         for k in ("mlp_tc_fwd_kernel<save>", "mlp_tc_bwd_chain_kernel", "mlp_tc_bwd_dw_kernel"):
-            tensor[k]["frac"] = tensor[k]["achieved"] / peak_tf
+            tensor[k]["frac_of_burst_peak"] = tensor[k]["achieved"] / peak_burst
+        if render is not None:
+            render["mlp_frac_of_burst_peak"] = render["mlp_tflops"] / world / peak_burst
+        if composite is not None:
+            composite["peak"] = peak_hbm
+            composite["frac"] = {k: composite[k] / peak_hbm for k in ("fwd_all_outputs", "fwd_lean", "bwd")}
         roofline = {"bound": "hbm", "kernel": "mlp_tc_bwd_dw_kernel (nerf_mlp_bwd_dw call)",
                     "achieved": ach, "peak": peak_hbm, "unit": "GB/s", "frac": ach / peak_hbm,
                     "traffic": 9845 * samples_per_launch,
+                    "traffic_source": "not measured in this run: dram__bytes_read+write of these launches in "
+                                      "profiles/r01_i_mlp_full_summary.txt (ncu --set full), 9845 B/sample",
                     "peak_source": "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6.5 TB/s",
                     "algorithmic_bytes_per_launch": 8896 * samples_per_launch,
                     "tensor_kernels": tensor,
                     "avg_call_ms": call_ms, "calls_per_step": call_n}
-        if args.mode != "bf16":
-            roofline["bound"] = "fp32 SIMT parity mode: the bf16 rooflines above do not apply"
+        if args.mode == "fp32":
+            roofline["bound"] = "fp32 SIMT parity mode: the tensor-core rooflines above do not apply"
         cpu = None
         if not args.no_cpu_baseline:
-            rate, cores = cpu_reference_rate(args.config, 128, 3)
+            rate, cores = cpu_reference_rate(args.config, CPU_SAMPLE_RAYS, 2)
             cpu = {"value": rate, "unit": "rays/s", "cores": cores, "kind": "port",
-                   "sample": "128-ray sample of the batch, 3 timed steps after 1 warm-up, oracle port (PyTorch-CPU fp32) "
-                             "of NeRF.train_step incl. Adam; TensorFlow unavailable offline"}
+                   "sample": f"{CPU_SAMPLE_RAYS}-ray sample of the batch, 2 timed steps after 1 warm-up, CPU port (PyTorch-CPU "
+                             "fp32, vectorised cumprod/cumsum reductions) of NeRF.train_step incl. Adam; TensorFlow "
+                             "unavailable offline"}
         line = {
             "metric": "rays/sec render fwd+bwd (train step)", "value": value, "unit": "rays/s", "n_gpus": world,
             "steps": args.steps, "warmup": n_warm, "ms_per_step": ms_dev / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "bf16" if args.mode == "bf16" else "f32", "data": "synthetic",
+            "dtype": {"fp16": "fp16 forward operands / bf16 backward operands, fp32 accumulate", "bf16": "bf16",
+                      "fp32": "f32"}[args.mode], "data": "synthetic",
             "config": {"workload": f"train_step {args.config}: {batch} rays/step/GPU, {N_C} coarse + {N_F} fine samples, "
                                    "8x256 MLPs + view branch, Adam"
                                    + (", + every 13th step the DietNeRF consistency term (150x150 in-tape render at "
                                       "55+55 samples, random-init ViT-B/32, cosine loss, backward)" if diet else ""),
                        "global_batch_rays": n_total, "parallelism": f"ray-sharded dp{world}",
                        "settle_s_before_each_timed_pass": args.settle,
-                       "l2": "working set per step (saved activations + dZ, ~4.5 GB at 2048 rays) >> 126 MB L2; "
+                       "l2": "working set per step (saved activations + dZ, ~9 GB at 4096 rays) >> 126 MB L2; "
                              "4 distinct ray batches rotate"},
             "e2e": {"value": e2e, "unit": "rays/s", "ms_per_step": ms_e2e / args.steps,
                     "h2d_bytes_per_step": batch * (16 + 16 + 12), "d2h_bytes_per_step": 4,
                     "how": "DevicePrefetcher (pinned host batch -> device on a copy stream, one batch ahead) -> "
                            "train step -> loss to a pinned host slot (asynchronous read-back consumed two steps later); "
                            "every copy of every step inside the timed region"},
+            "sustained": sustained,
+            "strong": strong,
+            "render": render,
+            "composite": composite,
             "gpu_launches": launches,
             "clocks": clocks,
             "roofline": roofline,

@@ -194,9 +194,22 @@ class DietNeRF(NeRF):
         return self._create_metrics(metrics, cosine_similarity_loss)
 
     def apply_gradients(self, g):
-        if getattr(self, "_extra_grads", None) is not None:
-            g[:self._extra_grads.numel()] += self._extra_grads
+        """``g`` = [sq_err_c, sq_err_f, 0, 0 | d params_c | d params_f] (NeRF._grad_buffer).  The ``consistency_loss_fn``
+        hook's gradient vector is laid out like the PARAMETERS ([coarse | fine]) and is added behind the four loss slots.
+        It is applied after the all-reduce, so it must already be the global gradient (identical on every rank)."""
+        extra = getattr(self, "_extra_grads", None)
+        if extra is not None:
+            n = g.numel() - 4
+            if extra.numel() != n:
+                raise ValueError(f"consistency_loss_fn returned {extra.numel()} gradient values, the networks have {n} parameters")
+            g[4:] += extra.to(device=g.device, dtype=g.dtype).reshape(-1)
         super().apply_gradients(g)
+
+    def train_step_fused(self, *args, **kwargs):
+        if self.consistency_loss_fn is not None:
+            raise RuntimeError("train_step_fused applies Adam inside the C call: the consistency_loss_fn hook's extra "
+                               "gradients cannot be added; use train_step")
+        return super().train_step_fused(*args, **kwargs)
 
     def _metrics_dict(self, out):
         m = super()._metrics_dict(out)

@@ -25,13 +25,14 @@ import torch
 from . import UtilsFiles
 from .ConfigurationKeys import (BLENDER, COLMAP, DATASET_LOCATION, DATASET_TYPE, DIETNERF_MODEL, EXISTING_SAVE_DIR_NAME,
                                 FAR_DEPTH_RENDER, GENERAL_SAVE_LOCATION, IDX_TRAIN_IMG_TO_PLOT, N_EPOCHS,
-                                N_RAYS_IN_BATCH_TRAIN, NEAR_DEPTH_RENDER, NEURAL_NET, OPTIMIZER_LR,
+                                N_ANGLES_FOR_MODEL, N_RAYS_IN_BATCH_TRAIN, NEAR_DEPTH_RENDER, NEURAL_NET, OPTIMIZER_LR,
                                 PICS_INDICES_TO_USE_IN_DATASET, RENDER, STARTING_EPOCH_NUMBER, START_TRAINING,
                                 TASKS_TO_PERFORM, TEST_IMG_IDX, TRAINING, TYPE_OF_MODEL, VIDEO, FPS_RENDER_VIDEO,
                                 FPS_TRAIN_SET_VIDEO, IMG_INDICES_FOR_PATH_VIDEO, RENDER_AND_SAVE_TEST_L_TO_R_VIDEO,
                                 RENDER_AND_SAVE_TEST_SPHERE_VIDEO, RENDER_AND_SAVE_TEST_PATH_VIDEO, SAVE_DATASET_VIDEO)
 from .DietNeRF import DietNeRF
 from .NeRF import NeRF
+from .network import DEFAULT_MODE
 from .optimizers import Adam
 from .poses import (estimate_point_of_interest_in_scene, get_c2w_matrices_between_2_c2w_with_stretch,
                     get_l_to_r_c2w_matrices, get_rotation_matrix_from_source_to_dest_mats, get_sphere_matrices)
@@ -70,11 +71,11 @@ def get_save_location(path_to_config_file, config) -> Path:
 class ExecutionRun:
     """``ExecutionRun(path_to_config_file).start()`` as in main.py:26-27; ``from_arrays`` skips the file system."""
 
-    def __init__(self, path_to_config_file=None, *, config=None, data=None, save_location=None, mode="bf16", seed=0):
+    def __init__(self, path_to_config_file=None, *, config=None, data=None, save_location=None, mode=None, seed=0):
         if config is None:
             config = UtilsFiles.load_config(path_to_config_file)
         self.config = config
-        self.mode, self.seed = mode, seed
+        self.mode, self.seed = (DEFAULT_MODE if mode is None else mode), seed
         self.tasks_to_perform = config.get(TASKS_TO_PERFORM, {START_TRAINING: True})
         self.dataset_type = config.get(DATASET_TYPE)
         self.pics_indices_to_use_in_dataset = config.get(PICS_INDICES_TO_USE_IN_DATASET)
@@ -83,14 +84,23 @@ class ExecutionRun:
         data = self.get_data(config) if data is None else data
         (self.images, self.camera_poses, self.field_of_view, self.near_boundary, self.far_boundary,
          self.average_c2w_before_recenter, self.c2w_scale_parameter) = data
+        distributed = torch.distributed.is_available() and torch.distributed.is_initialized()
+        self.is_main = not distributed or torch.distributed.get_rank() == 0
         if save_location is None and path_to_config_file is not None:
-            save_location = get_save_location(path_to_config_file, config)
-            shutil.copyfile(path_to_config_file, Path(save_location) / Path(path_to_config_file).name)
+            # ONE save directory per run: rank 0 resolves / creates it (and keeps the config copy, src/ExecutionRun.py:
+            # 83-86), every other rank receives the path -- the ranks would otherwise race on `<stem>_save_dir_<n>` and
+            # ranks > 0 would look for checkpoints in directories of their own
+            if self.is_main:
+                save_location = get_save_location(path_to_config_file, config)
+                shutil.copyfile(path_to_config_file, Path(save_location) / Path(path_to_config_file).name)
+            if distributed and torch.distributed.get_world_size() > 1:
+                box = [str(save_location) if self.is_main else None]
+                torch.distributed.broadcast_object_list(box, src=0)      # also the barrier before any rank reads it
+                save_location = box[0]
         self.save_location = Path(save_location) if save_location is not None else None
         start = config.get(STARTING_EPOCH_NUMBER, -1)
         self._epoch_number = start if start and start > 0 else 0
-        self.is_main = not (torch.distributed.is_available() and torch.distributed.is_initialized()) or \
-            torch.distributed.get_rank() == 0
+        self.model = None                    # set by _training: the videos after it render with THESE weights
         self.history = []                    # one dict per epoch: epoch, seconds, psnr_test, psnr_train, loss
 
     @classmethod
@@ -117,9 +127,26 @@ class ExecutionRun:
         idx = self.get_train_images_indices(idx_test)
         return idx_test, self.images[idx], self.camera_poses[idx]
 
+    def effective_mode(self) -> str:
+        """The arithmetic mode this run's networks get: the requested one, or "fp32" when the network has no tensor-core
+        plan (``n_angles_for_model: 0``, the xyz-only network of src/NeRF.py:248-288 -- 5 of the reference's 47 configs):
+        those run on the SIMT fp32 kernels instead of failing."""
+        if self.mode == "fp32":
+            return "fp32"
+        from . import _lib
+        from .NeRF import net_cfg_from_dict
+        cfg = net_cfg_from_dict(self.net_config)
+        if int(_lib.load().nerf_packed_bytes(_lib.ctypes.byref(cfg))) < 0:
+            if self.is_main and not getattr(self, "_warned_mode", False):
+                print(f"ExecutionRun: mode={self.mode!r} has no tensor-core plan for this network "
+                      f"(n_angles_for_model={self.net_config[N_ANGLES_FOR_MODEL]}); running it in mode='fp32'")
+                self._warned_mode = True
+            return "fp32"
+        return self.mode
+
     def get_nerf(self) -> NeRF:
         """A new model + Adam(lr); loads ``saved_weights/NeRF_model_epoch_<starting epoch>.h5`` when it exists."""
-        kw = dict(mode=self.mode, seed=self.seed, stop_grad_z=getattr(self, "stop_grad_z", False))
+        kw = dict(mode=self.effective_mode(), seed=self.seed, stop_grad_z=getattr(self, "stop_grad_z", False))
         if self.net_config[TYPE_OF_MODEL] == DIETNERF_MODEL:
             model = self._init_dietnerf(kw)
         else:
@@ -128,10 +155,12 @@ class ExecutionRun:
         if torch.distributed.is_available() and torch.distributed.is_initialized() and \
                 torch.distributed.get_world_size() > 1:
             model.distribute()
+        self._loaded_checkpoint = None
         if self.save_location is not None:
             path = NeRF.get_nerf_model_path(self.save_location, self._epoch_number)
             if os.path.exists(path):
                 model.load_weights(path)
+                self._loaded_checkpoint = path
         return model
 
     def _init_dietnerf(self, kw):
@@ -289,7 +318,17 @@ class ExecutionRun:
         Returns the two paths; rank 0 writes the files."""
         if self.save_location is None:
             raise Exception('render_video needs a save location (the run was built without one)')
-        model = self.get_nerf() if model is None else model
+        if model is None:
+            # right after training: the model that was just trained; otherwise a model loaded from this run's checkpoint
+            # -- which must exist: rendering a video with freshly initialised weights helps nobody
+            model = self.model
+        if model is None:
+            self._loaded_checkpoint = "unknown"
+            model = self.get_nerf()
+            if self._loaded_checkpoint is None:
+                path = NeRF.get_nerf_model_path(self.save_location, self._epoch_number)
+                raise Exception(f'render_video: no checkpoint {path} (set starting_epoch_number to a saved epoch, or train '
+                                f'first); refusing to render with randomly initialised weights')
         fps = self.video_properties[FPS_RENDER_VIDEO]
         if self.is_main:
             print(process_description, f"({len(c2w_matrices)} frames)")

@@ -20,7 +20,7 @@ from ._lib import MODE_BF16, NetCfg, call, f32c, ptr
 from .ConfigurationKeys import (HIDDEN_LAYER_DIM, LAST_HIDDEN_LAYER_DIM, LEAKY_RELU_ALPHA, N_ANGLES_FOR_MODEL,
                                 N_POS_ENC_DIM_XYZ, N_POS_ENC_VIEW_DIR, N_RAYS_IN_BATCH_RENDER, N_RAYS_IN_BATCH_TRAIN,
                                 N_RENDER_SAMPLES_COARSE, N_RENDER_SAMPLES_FINE)
-from .network import NerfMLP
+from .network import DEFAULT_MODE, NerfMLP
 from .optimizers import Adam
 from .parallel import allreduce_sum_, shard_bounds
 from .UtilsCV import get_rays_directions, get_z_vals_from_prob_dist_func, get_z_values, rng
@@ -96,14 +96,17 @@ class NeRF:
 
     # loss = COARSE_LOSS_WEIGHT * MSE_coarse + MSE_fine  (1 for NeRF, src/NeRF.py:151-157; DietNeRF overrides)
     COARSE_LOSS_WEIGHT = 1.0
+    # True: the one-stream backward issues its two halves as separate C-ABI calls (bench.py times them one by one)
+    split_bwd_calls = False
 
     def __init__(self, net_config: Dict, render_config: Dict, near_boundary: float, far_boundary: float, *,
-                 mode: str = "bf16", device=None, seed=None, stop_grad_z: bool = False):
+                 mode: str = DEFAULT_MODE, device=None, seed=None, stop_grad_z: bool = False):
         """
         :param net_config:      ``neural_net`` block of the config file.
         :param render_config:   ``render`` block of the config file.
-        :param mode:            (extension) "bf16": tensor-core path (train + render); "fp16": train in bf16, render with
-                                fp16 operands (8x finer rounding, same speed); "fp32": SIMT parity path.
+        :param mode:            (extension) "fp16" (default): tensor-core path with fp16 forward operands (train + render;
+                                the reference's mixed_float16 arithmetic), bf16 gradients; "bf16": bf16 operands
+                                everywhere; "fp32": SIMT parity path.
         :param stop_grad_z:     (extension, default False = reference behaviour) detach the importance samples.
         """
         self.device = device or torch.device("cuda", torch.cuda.current_device())
@@ -144,7 +147,7 @@ class NeRF:
 
     # ---- construction helpers --------------------------------------------------------------------------------
     @staticmethod
-    def init_network(net_config: Dict, mode: str = "bf16", device=None, seed=None) -> NerfMLP:
+    def init_network(net_config: Dict, mode: str = DEFAULT_MODE, device=None, seed=None) -> NerfMLP:
         """Initialise one network from the config (xyz+view when n_angles_for_model > 0, else xyz only)."""
         return NerfMLP(net_cfg_from_dict(net_config), mode=mode, device=device, seed=seed)
 
@@ -356,9 +359,11 @@ class NeRF:
              opt.iterations + 1, ptr(out), ws_ptr, side.cuda_stream if side is not None else None)
         if update:
             opt.iterations += 1
-            mc.mark_updated()
+            # the C side stepped the parameters in place AND refreshed the 16-bit packs this mode reads: only the other
+            # precision's regions are stale now
+            mc.mark_packed()
             if mf is not None:
-                mf.mark_updated()
+                mf.mark_packed()
         self.step_counter += 1
         return self._metrics_dict(out)
 
@@ -602,9 +607,13 @@ class NeRF:
         is returned for the caller to join before it reads ``grads``."""
         args = (net.cfg_ref, ptr(net.params), ptr(net.packed_for(net.params)), ptr(xyz), ptr(view), ptr(saved), ptr(d_raw), m,
                 ptr(grads), ptr(d_xyz), ptr(ws), net.mode_id)
-        if net.mode_id == MODE_BF16 and side_stream is not None:
+        if net.tensor_core and side_stream is not None:
             call("nerf_mlp_bwd_overlapped", *args, side_stream.cuda_stream)
             return side_stream
+        if net.tensor_core and NeRF.split_bwd_calls:
+            call("nerf_mlp_bwd_dx", *args)
+            call("nerf_mlp_bwd_dw", *args)
+            return None
         call("nerf_mlp_bwd", *args)
         return None
 

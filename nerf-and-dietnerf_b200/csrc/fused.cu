@@ -132,6 +132,12 @@ int64_t carve_train(const NetGeom& g, const nerf_net_cfg* cfg, const nerf_render
   return c.off;
 }
 
+// the 16-bit weight pack the mode's kernels read (bf16 regions or fp16 regions of the packed buffer)
+int pack_for_mode(const nerf_net_cfg* cfg, const float* params, void* packed, int32_t mode, void* stream) {
+  return mode == NERF_MODE_FP16 ? nerf_pack_weights_fp16(cfg, params, packed, stream)
+                                : nerf_pack_weights(cfg, params, packed, stream);
+}
+
 // `waiter` waits for everything enqueued on `signaller` so far (an event lives only for this hand-over)
 int stream_wait(cudaStream_t waiter, cudaStream_t signaller) {
   cudaEvent_t ev;
@@ -215,8 +221,7 @@ int nerf_render_fused_fwd(const nerf_net_cfg* cfg, const nerf_render_cfg* rc, co
 
 int64_t nerf_train_workspace_bytes(const nerf_net_cfg* cfg, const nerf_render_cfg* rc, int64_t n_rays) {
   NetGeom g;
-  if (!make_geom(cfg, &g) || !render_cfg_ok(rc) || rc->mode == NERF_MODE_FP16 || n_rays < 0 ||
-      !mode_supported(cfg, rc->mode))
+  if (!make_geom(cfg, &g) || !render_cfg_ok(rc) || n_rays < 0 || !mode_supported(cfg, rc->mode))
     return -1;
   TrainWs w;
   return carve_train(g, cfg, rc, n_rays, nullptr, &w);
@@ -229,7 +234,7 @@ int nerf_train_step_fused(const nerf_net_cfg* cfg, const nerf_render_cfg* rc, co
                           float* metrics4, void* workspace, void* side_stream, void* stream) {
   NetGeom g;
   NERF_CHECK_ARG(make_geom(cfg, &g), "bad network config");
-  NERF_CHECK_ARG(render_cfg_ok(rc) && rc->mode != NERF_MODE_FP16, "bad render config (training runs in FP32 or BF16)");
+  NERF_CHECK_ARG(render_cfg_ok(rc), "bad render config");
   if (!mode_supported(cfg, rc->mode)) {
     set_error("%s: this network has no tensor-core path (use NERF_MODE_FP32)", __func__);
     return NERF_E_UNSUPPORTED;
@@ -253,6 +258,7 @@ int nerf_train_step_fused(const nerf_net_cfg* cfg, const nerf_render_cfg* rc, co
   const int32_t sc = rc->n_samples_coarse, sf = rc->n_samples_fine, mode = rc->mode;
   const bool use_side = tc && fine && side_stream != nullptr && side_stream != stream;
   bool forked = false, fine_stepped = false;
+  const int32_t mode_all = mode;
   if (n > 0) {
     TrainWs w;
     carve_train(g, cfg, rc, n, (uint8_t*)workspace, &w);
@@ -282,7 +288,7 @@ int nerf_train_step_fused(const nerf_net_cfg* cfg, const nerf_render_cfg* rc, co
         if (adam_m) {
           NERF_TRY(nerf_adam_step(params_f, g_f, adam_m + np, adam_v + np, np, tc_cfg->learning_rate, tc_cfg->beta_1,
                                   tc_cfg->beta_2, tc_cfg->epsilon, adam_t, side_stream));
-          NERF_TRY(nerf_pack_weights(cfg, params_f, packed_f, side_stream));
+          NERF_TRY(pack_for_mode(cfg, params_f, packed_f, mode, side_stream));
           fine_stepped = true;
         }
         forked = true;
@@ -311,8 +317,8 @@ int nerf_train_step_fused(const nerf_net_cfg* cfg, const nerf_render_cfg* rc, co
       NERF_TRY(nerf_adam_step(params_f, g_f, adam_m + np, adam_v + np, np, tc_cfg->learning_rate, tc_cfg->beta_1,
                               tc_cfg->beta_2, tc_cfg->epsilon, adam_t, stream));
     if (tc) {
-      NERF_TRY(nerf_pack_weights(cfg, params_c, packed_c, stream));
-      if (fine && !fine_stepped) NERF_TRY(nerf_pack_weights(cfg, params_f, packed_f, stream));
+      NERF_TRY(pack_for_mode(cfg, params_c, packed_c, mode_all, stream));
+      if (fine && !fine_stepped) NERF_TRY(pack_for_mode(cfg, params_f, packed_f, mode_all, stream));
     }
   }
   if (metrics4)

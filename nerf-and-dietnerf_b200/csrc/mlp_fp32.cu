@@ -11,7 +11,7 @@ int mlp_tc_fwd(const nerf_net_cfg* cfg, const NetGeom& g, const float* params, c
                const float* view_enc, int64_t m, float* out4, void* saved, void* workspace, cudaStream_t st, bool half);
 int mlp_tc_bwd(const nerf_net_cfg* cfg, const NetGeom& g, const float* params, const void* packed, const float* xyz_enc,
                const float* view_enc, const void* saved, const float* d_out4, int64_t m, float* grads, float* d_xyz_enc,
-               void* workspace, cudaStream_t st, int parts, cudaStream_t side);
+               void* workspace, cudaStream_t st, int parts, cudaStream_t side, bool half);
 int mlp_tc_fwd_rays(const nerf_net_cfg* cfg, const NetGeom& g, const void* packed, const float* origs4, const float* dirs4,
                     const float* z, int64_t n_rays, int n_samples, float* out4, void* saved, cudaStream_t st, bool half);
 int64_t mlp_tc_saved_bytes(const NetGeom& g, int64_t m);
@@ -326,14 +326,14 @@ int32_t nerf_view_enc_dim(const nerf_net_cfg* cfg) {
 int64_t nerf_mlp_saved_bytes(const nerf_net_cfg* cfg, int64_t m, int32_t mode) {
   NetGeom g;
   if (!make_geom(cfg, &g) || m < 0) { set_error("nerf_mlp_saved_bytes: bad argument"); return NERF_E_ARG; }
-  if (mode == NERF_MODE_BF16) return mlp_tc_saved_bytes(g, m);
+  if (mode == NERF_MODE_BF16 || mode == NERF_MODE_FP16) return mlp_tc_saved_bytes(g, m);
   return fp32_saved_floats(g, m) * (int64_t)sizeof(float);
 }
 
 int64_t nerf_mlp_workspace_bytes(const nerf_net_cfg* cfg, int64_t m, int32_t mode, int32_t backward) {
   NetGeom g;
   if (!make_geom(cfg, &g) || m < 0) { set_error("nerf_mlp_workspace_bytes: bad argument"); return NERF_E_ARG; }
-  if (mode == NERF_MODE_BF16) return mlp_tc_workspace_bytes(g, m, backward);
+  if (mode == NERF_MODE_BF16 || mode == NERF_MODE_FP16) return mlp_tc_workspace_bytes(g, m, backward);
   int64_t fl = backward ? m * (2 * (int64_t)g.hidden + g.last_hidden) : m * 3 * (int64_t)g.hidden;
   return fl * (int64_t)sizeof(float) + 256;
 }
@@ -384,15 +384,16 @@ static int mlp_bwd_parts(const nerf_net_cfg* cfg, const float* params, const voi
   NERF_CHECK_ARG(make_geom(cfg, &g), "bad net config");
   NERF_CHECK_ARG(params && saved && d_out4 && grads && workspace, "null pointer");
   // the bf16 path reads the bf16 input panel it saved in the forward pass; only the fp32 path needs the encodings again
-  NERF_CHECK_ARG(mode == NERF_MODE_BF16 || (xyz_enc && (view_enc || !g.view)), "null pointer");
+  const bool tc = mode == NERF_MODE_BF16 || mode == NERF_MODE_FP16;
+  NERF_CHECK_ARG(tc || (xyz_enc && (view_enc || !g.view)), "null pointer");
   NERF_CHECK_ARG(m >= 0, "negative row count");
-  NERF_CHECK_ARG(mode == NERF_MODE_FP32 || mode == NERF_MODE_BF16, "unknown mode");
-  NERF_CHECK_ARG(mode == NERF_MODE_BF16 || parts == 3, "NERF_MODE_FP32 computes both halves of the backward in one pass");
+  NERF_CHECK_ARG(mode == NERF_MODE_FP32 || tc, "unknown mode");
+  NERF_CHECK_ARG(tc || parts == 3, "NERF_MODE_FP32 computes both halves of the backward in one pass");
   if (m == 0) return NERF_OK;
-  if (mode == NERF_MODE_BF16) {
-    NERF_CHECK_ARG(packed_or_null, "NERF_MODE_BF16 needs the packed weights (nerf_pack_weights)");
+  if (tc) {
+    NERF_CHECK_ARG(packed_or_null, "the tensor-core modes need the packed weights (nerf_pack_weights[_fp16])");
     return mlp_tc_bwd(cfg, g, params, packed_or_null, xyz_enc, view_enc, saved, d_out4, m, grads, d_xyz_enc_or_null,
-                      workspace, (cudaStream_t)stream, parts, (cudaStream_t)side_stream);
+                      workspace, (cudaStream_t)stream, parts, (cudaStream_t)side_stream, mode == NERF_MODE_FP16);
   }
   fp32_bwd(cfg, g, params, xyz_enc, view_enc, (const float*)saved, d_out4, m, grads, d_xyz_enc_or_null,
            (float*)workspace, (cudaStream_t)stream);
@@ -411,7 +412,7 @@ int nerf_mlp_bwd_overlapped(const nerf_net_cfg* cfg, const float* params, const 
                             const float* view_enc, const void* saved, const float* d_out4, int64_t m, float* grads,
                             float* d_xyz_enc_or_null, void* workspace, int32_t mode, void* side_stream, void* stream) {
   return mlp_bwd_parts(cfg, params, packed_or_null, xyz_enc, view_enc, saved, d_out4, m, grads, d_xyz_enc_or_null, workspace,
-                       mode, stream, 3, mode == NERF_MODE_BF16 ? side_stream : nullptr);
+                       mode, stream, 3, mode != NERF_MODE_FP32 ? side_stream : nullptr);
 }
 
 int nerf_mlp_bwd_dx(const nerf_net_cfg* cfg, const float* params, const void* packed_or_null, const float* xyz_enc,

@@ -199,6 +199,15 @@ __device__ __forceinline__ uint4 pack8_16(const float* v) {
                     pack_16x2<kHalf>(v[6], v[7]));
 }
 
+// eight packed fp16 values -> eight packed bf16 values (round to nearest even; fp16's range fits bf16's)
+__device__ __forceinline__ uint32_t half2_to_bf16x2(uint32_t h2) {
+  const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&h2));
+  return pack_bf16x2(f.x, f.y);
+}
+__device__ __forceinline__ uint4 half8_to_bf16(uint4 v) {
+  return make_uint4(half2_to_bf16x2(v.x), half2_to_bf16x2(v.y), half2_to_bf16x2(v.z), half2_to_bf16x2(v.w));
+}
+
 template <bool kSave, bool kHalf>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreadsFwd, 1)
 mlp_tc_fwd_kernel(const __grid_constant__ TcPlan plan, const uint8_t* __restrict__ packed,
@@ -392,8 +401,9 @@ mlp_tc_fwd_kernel(const __grid_constant__ TcPlan plan, const uint8_t* __restrict
               for (int it = 0; it < 64; ++it) {
                 const int j = hw * 16 + (it >> 2), r = (it & 3) * 32 + lane;     // 16-byte column chunk, row
                 const float4 v = lds128f(act_u32 + (j >> 3) * kPanelBytes + r * 128 + (((j & 7) ^ (r & 7)) << 4));
-                stg128(gblock + rbcm_offset(r, j, 32),
-                       make_uint4(__float_as_uint(v.x), __float_as_uint(v.y), __float_as_uint(v.z), __float_as_uint(v.w)));
+                uint4 w = make_uint4(__float_as_uint(v.x), __float_as_uint(v.y), __float_as_uint(v.z), __float_as_uint(v.w));
+                if (kHalf) w = half8_to_bf16(w);          // the backward reads bf16
+                stg128(gblock + rbcm_offset(r, j, 32), w);
               }
             }
             __syncwarp();
@@ -524,7 +534,18 @@ mlp_tc_fwd_kernel(const __grid_constant__ TcPlan plan, const uint8_t* __restrict
       const bool do_store = kSave && !(dbg & kDbgNoStore);
       if (kSave) {
         named_bar_sync(bar_id, kEpiThreadsPerTile);
-        if (gtid == 0 && do_store) {
+        if (kHalf) {
+          // fp16 panel -> bf16 saved copy (same swizzled layout): this thread's half row, four 16-byte chunks
+          if (do_store) {
+#pragma unroll
+            for (int j = half * 4; j < half * 4 + 4; ++j) {
+              const uint32_t off = (uint32_t)r * 128u + (uint32_t)((j ^ (r & 7)) << 4);
+              const float4 v = lds128f(inp_u32 + off);
+              stg128(saved_tile + off, half8_to_bf16(make_uint4(__float_as_uint(v.x), __float_as_uint(v.y), __float_as_uint(v.z),
+                                                                __float_as_uint(v.w))));
+            }
+          }
+        } else if (gtid == 0 && do_store) {
           bulk_s2g(saved_tile, inp_u32, kPanelBytes);
           bulk_commit();
         }
@@ -598,7 +619,7 @@ mlp_tc_fwd_kernel(const __grid_constant__ TcPlan plan, const uint8_t* __restrict
                 rr = fmaf(x0, w0.x, fmaf(x1, w1.x, rr));
                 gg = fmaf(x0, w0.y, fmaf(x1, w1.y, gg));
                 bb = fmaf(x0, w0.z, fmaf(x1, w1.z, bb));
-                pk[i] = pack_16x2<kHalf>(x0, x1);
+                pk[i] = pack_16x2<false>(x0, x1);          // only leaves for the backward (bf16) and the sign mask
               }
               if (kSave) { u[2 * j] = hi_bytes(pk[0], pk[1]); u[2 * j + 1] = hi_bytes(pk[2], pk[3]); }
               if (kSave && grow) stg128(grow + ((c0 >> 3) + j) * 1024, make_uint4(pk[0], pk[1], pk[2], pk[3]));
@@ -666,10 +687,8 @@ int64_t mlp_tc_workspace_bytes(const NetGeom& g, int64_t m, int backward) {
   return tiles * (int64_t)kDzTileBytes + 1024 + kDwScratchBytes + mlp_tc_bwd_flag_bytes(m);
 }
 
-// byte offset of the fp16 copy of the forward weight pack inside the packed buffer: [bf16 fwd | bf16 bwd | fp16 fwd]
-static uint32_t half_region_offset(const TcPlan& plan) {
-  return ((plan.total_bytes + 1023u) & ~1023u) + ((bwd_pack_bytes() + 1023u) & ~1023u);
-}
+// byte offset of the fp16 copy of the forward weight pack inside the packed buffer (layout: mlp_tc.cuh)
+static uint32_t half_region_offset(const TcPlan& plan) { return pack_off_fwd_half(plan); }
 
 static int launch_fwd(const nerf_net_cfg* cfg, const NetGeom& g, const void* packed, const FwdInput& in, int64_t m,
                       float* out4, void* saved, cudaStream_t st, bool half = false) {
@@ -683,12 +702,17 @@ static int launch_fwd(const nerf_net_cfg* cfg, const NetGeom& g, const void* pac
     NERF_CUDA(cudaFuncSetAttribute(mlp_tc_fwd_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemAlloc));
     NERF_CUDA(cudaFuncSetAttribute(mlp_tc_fwd_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemAlloc));
     NERF_CUDA(cudaFuncSetAttribute(mlp_tc_fwd_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemAlloc));
+    NERF_CUDA(cudaFuncSetAttribute(mlp_tc_fwd_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemAlloc));
   }
   int64_t n_quads = ((m + kTileM - 1) / kTileM + 3) / 4;
   const int n_pairs = num_sms() / 2;
   int grid = 2 * (int)(n_quads < n_pairs ? n_quads : n_pairs);             // CTA pairs
-  if (half) {
-    if (saved) { set_error("NERF_MODE_FP16 is a forward-only (render) mode: train in NERF_MODE_BF16"); return NERF_E_UNSUPPORTED; }
+  if (half && saved) {
+    // fp16 operands in training too; what is SAVED for the backward is converted to bf16 on its way out (store warps,
+    // last-layer epilogue, input panel), because the backward's MMAs pair it with bf16 gradients
+    mlp_tc_fwd_kernel<true, true><<<grid, kThreadsFwd, kSmemAlloc, st>>>(
+        plan, (const uint8_t*)packed + half_region_offset(plan), in, m, out4, (uint8_t*)saved, cfg->leaky_alpha, tc_debug_flags());
+  } else if (half) {
     mlp_tc_fwd_kernel<false, true><<<grid, kThreadsFwd, kSmemAlloc, st>>>(
         plan, (const uint8_t*)packed + half_region_offset(plan), in, m, out4, nullptr, cfg->leaky_alpha, tc_debug_flags());
   } else if (saved) {
@@ -730,7 +754,7 @@ int64_t nerf_packed_bytes(const nerf_net_cfg* cfg) {
   TcPlan plan;
   if (!make_geom(cfg, &g)) { set_error("nerf_packed_bytes: bad net config"); return NERF_E_ARG; }
   if (!make_plan(g, &plan)) { set_error("nerf_packed_bytes: config not supported by NERF_MODE_BF16"); return NERF_E_UNSUPPORTED; }
-  return (int64_t)half_region_offset(plan) + plan.total_bytes;
+  return (int64_t)pack_total_bytes(plan);
 }
 
 int nerf_pack_weights(const nerf_net_cfg* cfg, const float* params, void* packed, void* stream) {
@@ -742,7 +766,7 @@ int nerf_pack_weights(const nerf_net_cfg* cfg, const float* params, void* packed
   dim3 grid((256 * 64 + 255) / 256, plan.n_chunks + 1);
   pack_weights_kernel<__nv_bfloat16><<<grid, 256, 0, (cudaStream_t)stream>>>(plan, g, params, (uint8_t*)packed);
   NERF_CHECK_LAUNCH();
-  return bwd_pack_weights(g, params, (uint8_t*)packed + ((plan.total_bytes + 1023u) & ~1023u), (cudaStream_t)stream);
+  return bwd_pack_weights(g, params, (uint8_t*)packed + pack_off_bwd(plan), (cudaStream_t)stream);
 }
 
 int nerf_pack_weights_fp16(const nerf_net_cfg* cfg, const float* params, void* packed, void* stream) {
@@ -754,7 +778,8 @@ int nerf_pack_weights_fp16(const nerf_net_cfg* cfg, const float* params, void* p
   dim3 grid((256 * 64 + 255) / 256, plan.n_chunks + 1);
   pack_weights_kernel<__half><<<grid, 256, 0, (cudaStream_t)stream>>>(plan, g, params, (uint8_t*)packed + half_region_offset(plan));
   NERF_CHECK_LAUNCH();
-  return NERF_OK;
+  // the backward of the fp16 mode is the bf16 backward: keep ITS pack current as well
+  return bwd_pack_weights(g, params, (uint8_t*)packed + pack_off_bwd(plan), (cudaStream_t)stream);
 }
 
 }  // extern "C"

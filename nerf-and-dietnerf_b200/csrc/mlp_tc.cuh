@@ -148,8 +148,15 @@ constexpr int64_t kDwScratchBytes = (int64_t)kMaxSMs * kDwPartialFloats * 4;
 // bytes of the per-(tile, block) dZ ready counters at the end of the backward workspace (overlapped mode)
 int64_t mlp_tc_bwd_flag_bytes(int64_t m);
 
-// backward half of the bf16 weight pack (defined in mlp_tc_bwd.cu)
+// backward half of the 16-bit weight pack (defined in mlp_tc_bwd.cu); half: fp16 instead of bf16
 uint32_t bwd_pack_bytes();
-int bwd_pack_weights(const NetGeom& g, const float* params, uint8_t* packed_bwd, cudaStream_t st);
+int bwd_pack_weights(const NetGeom& g, const float* params, uint8_t* packed_bwd, cudaStream_t st, bool half = false);
+
+// The packed weight buffer of one network: [bf16 forward | bf16 backward | fp16 forward], every region 1024-byte aligned.
+// nerf_pack_weights fills the first two, nerf_pack_weights_fp16 the last two (the backward is bf16 in both 16-bit modes).
+inline uint32_t pack_align(uint32_t b) { return (b + 1023u) & ~1023u; }
+inline uint32_t pack_off_bwd(const TcPlan& plan) { return pack_align(plan.total_bytes); }
+inline uint32_t pack_off_fwd_half(const TcPlan& plan) { return pack_off_bwd(plan) + pack_align(bwd_pack_bytes()); }
+inline uint32_t pack_total_bytes(const TcPlan& plan) { return pack_off_fwd_half(plan) + pack_align(plan.total_bytes); }
 
 }  // namespace nerf

@@ -24,6 +24,8 @@
 //  The dependency is one-directional (the chain never waits for the dW kernel), so any serialisation of the two
 //  launches (a profiler, a busy GPU) is still correct.  dW CTAs of a unit take tiles round-robin (tile = split + i n),
 //  i.e. in the order the chain produces them.
+#include <type_traits>
+
 #include "mlp_tc.cuh"
 #include "mlp_tc_bwd_pipe.cuh"
 
@@ -94,6 +96,7 @@ uint32_t bwd_pack_bytes() {
   return p.total_bytes;
 }
 
+template <typename T16>
 __global__ void pack_bwd_kernel(const __grid_constant__ BwdPlan plan, NetGeom g, const float* __restrict__ P,
                                 uint8_t* __restrict__ packed) {
   const int chunk = blockIdx.y;
@@ -115,7 +118,10 @@ __global__ void pack_bwd_kernel(const __grid_constant__ BwdPlan plan, NetGeom g,
       const LayerDesc& L = g.layers[kind == STEP_XSTASH ? 4 : 0];
       if (j < g.dx) v = P[L.w_off + (int64_t)j * L.out + n];
     }
-    *reinterpret_cast<__nv_bfloat16*>(packed + plan.chunk_off[chunk] + panel_offset(j, kk)) = __float2bfloat16_rn(v);
+    if constexpr (std::is_same<T16, __half>::value)
+      *reinterpret_cast<__half*>(packed + plan.chunk_off[chunk] + panel_offset(j, kk)) = __float2half_rn(v);
+    else
+      *reinterpret_cast<__nv_bfloat16*>(packed + plan.chunk_off[chunk] + panel_offset(j, kk)) = __float2bfloat16_rn(v);
   } else {
     if (e < 256) reinterpret_cast<float*>(packed + plan.w_sigma_off)[e] = P[g.layers[10].w_off + e];
     if (e < 128) {
@@ -126,11 +132,12 @@ __global__ void pack_bwd_kernel(const __grid_constant__ BwdPlan plan, NetGeom g,
   }
 }
 
-int bwd_pack_weights(const NetGeom& g, const float* params, uint8_t* packed_bwd, cudaStream_t st) {
+int bwd_pack_weights(const NetGeom& g, const float* params, uint8_t* packed_bwd, cudaStream_t st, bool half) {
   BwdPlan plan;
   make_bwd_plan(&plan);
   dim3 grid((256 * 64 + 255) / 256, plan.n_chunks + 1);
-  pack_bwd_kernel<<<grid, 256, 0, st>>>(plan, g, params, packed_bwd);
+  if (half) pack_bwd_kernel<__half><<<grid, 256, 0, st>>>(plan, g, params, packed_bwd);
+  else pack_bwd_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(plan, g, params, packed_bwd);
   NERF_CHECK_LAUNCH();
   return NERF_OK;
 }
@@ -825,7 +832,7 @@ int64_t mlp_tc_bwd_flag_bytes(int64_t m) {
 // time (see the top of this file); the caller joins `side` before it reads `grads`.
 int mlp_tc_bwd(const nerf_net_cfg* cfg, const NetGeom& g, const float* params, const void* packed, const float* xyz_enc,
                const float* view_enc, const void* saved, const float* d_out4, int64_t m, float* grads, float* d_xyz_enc,
-               void* workspace, cudaStream_t st, int parts, cudaStream_t side) {
+               void* workspace, cudaStream_t st, int parts, cudaStream_t side, bool half) {
   (void)params; (void)xyz_enc; (void)view_enc;
   TcPlan fplan;
   if (!make_plan(g, &fplan)) {
@@ -838,7 +845,11 @@ int mlp_tc_bwd(const nerf_net_cfg* cfg, const NetGeom& g, const float* params, c
   }
   BwdPlan bplan;
   make_bwd_plan(&bplan);
-  const uint8_t* packed_bwd = (const uint8_t*)packed + ((fplan.total_bytes + 1023u) & ~1023u);
+  // Both 16-bit modes share this backward: tcgen05 kind::f16 wants ONE operand format per MMA (an fp16 A with a bf16 B is
+  // an illegal instruction on sm_100a -- tried), and the gradients need bf16's range, so the forward of the fp16 mode
+  // saves its activations converted to bf16 and the chain reads the bf16 W^T.
+  (void)half;
+  const uint8_t* packed_bwd = (const uint8_t*)packed + pack_off_bwd(fplan);
   uint8_t* dz_ws = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(workspace) + 1023) & ~(uintptr_t)1023);
   const int64_t tiles4 = ((m + kTileM - 1) / kTileM + 3) / 4 * 4;
   const int64_t n_quads = tiles4 / 4;

@@ -265,10 +265,12 @@ __device__ __forceinline__ void stg128(void* p, uint4 v) {
 }
 
 // Instruction descriptor for kind::f16: bf16 x bf16 -> fp32, M = 128, N = n.  a_major/b_major: 0 = K-major, 1 = MN-major.
-// operand_fmt: 1 = bf16 (default), 0 = fp16.
+// operand_fmt: 1 = bf16 (default), 0 = fp16; b_fmt: format of B when it differs from A's (-1 = the same) -- kind::f16
+// carries one format field per operand, so an fp16 activation operand can meet a bf16 gradient operand.
 // m = 128 (cta_group::1) or 256 (cta_group::2).
-__host__ __device__ constexpr uint32_t make_idesc(int n, int a_mn_major = 0, int b_mn_major = 0, int operand_fmt = 1, int m = 128) {
-  return (1u << 4) | ((uint32_t)operand_fmt << 7) | ((uint32_t)operand_fmt << 10) | ((uint32_t)a_mn_major << 15) |
+__host__ __device__ constexpr uint32_t make_idesc(int n, int a_mn_major = 0, int b_mn_major = 0, int operand_fmt = 1, int m = 128,
+                                                  int b_fmt = -1) {
+  return (1u << 4) | ((uint32_t)operand_fmt << 7) | ((uint32_t)(b_fmt < 0 ? operand_fmt : b_fmt) << 10) | ((uint32_t)a_mn_major << 15) |
          ((uint32_t)b_mn_major << 16) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 

@@ -3,8 +3,8 @@
 Replaces the two Keras functional models of src/NeRF.py:248-288 (xyz only) and :290-340 (xyz + view direction).
 Parameters live in ONE fp32 vector laid out [W0 (in,out) row-major, b0, W1, b1, ...] in Keras layer-creation
 order (the order of ``dense … dense_10`` in the reference's saved .h5), initialised like Keras Dense
-(glorot_uniform kernels, zero biases).  ``mode`` selects the arithmetic: "fp32" (SIMT fp32 GEMMs) or "bf16"
-(tcgen05/TMEM tensor-core chain with bf16 operands and fp32 accumulation).
+(glorot_uniform kernels, zero biases).  ``mode`` selects the arithmetic: "fp32" (SIMT fp32 GEMMs), "fp16" (default) or
+"bf16" (tcgen05/TMEM tensor-core chain with 16-bit operands and fp32 accumulation).
 """
 import math
 
@@ -13,8 +13,14 @@ import torch
 from . import _lib
 from ._lib import MODE_BF16, MODE_FP16, MODE_FP32, NetCfg, call, load, ptr
 
-# mode -> (arithmetic of training / differentiable calls, arithmetic of inference-only calls)
-_MODES = {"fp32": (MODE_FP32, MODE_FP32), "bf16": (MODE_BF16, MODE_BF16), "fp16": (MODE_BF16, MODE_FP16)}
+# mode -> (arithmetic of training / differentiable calls, arithmetic of inference-only calls).
+#   "fp16" (default): forward MMAs with fp16 operands in training AND rendering (what the reference's mixed_float16 policy
+#           computes in; 8x finer operand rounding than bf16: the 1e-3 render bound); the backward is the bf16 one (bf16
+#           gradients keep fp32's range, so no loss scaling; tcgen05 wants one operand format per MMA, so the forward
+#           saves its activations converted to bf16);
+#   "bf16": bf16 operands everywhere;  "fp32": SIMT fp32 parity mode.
+_MODES = {"fp32": (MODE_FP32, MODE_FP32), "bf16": (MODE_BF16, MODE_BF16), "fp16": (MODE_FP16, MODE_FP16)}
+DEFAULT_MODE = "fp16"
 
 
 def layer_shapes(cfg: NetCfg):
@@ -53,7 +59,7 @@ class _MlpFn(torch.autograd.Function):
         grads = torch.zeros_like(params)
         d_xyz = torch.empty_like(xyz_enc) if ctx.needs_input_grad[1] else None
         ws = model._buffer("ws_bwd", model.workspace_bytes(m, True))
-        call("nerf_mlp_bwd", model.cfg_ref, ptr(params), ptr(model.packed_for(params)), ptr(xyz_enc),
+        call("nerf_mlp_bwd", model.cfg_ref, ptr(params), ptr(model.packed_for(params, half=model.mode_id == MODE_FP16)), ptr(xyz_enc),
              ptr(view_enc if ctx.has_view else None), ptr(saved), ptr(d_out.contiguous().float()), m, ptr(grads),
              ptr(d_xyz), ptr(ws), model.mode_id)
         return grads, d_xyz, None, None
@@ -62,7 +68,7 @@ class _MlpFn(torch.autograd.Function):
 class NerfMLP:
     """One NeRF network (coarse or fine)."""
 
-    def __init__(self, cfg: NetCfg, mode: str = "bf16", device=None, seed=None):
+    def __init__(self, cfg: NetCfg, mode: str = DEFAULT_MODE, device=None, seed=None):
         if mode not in _MODES:
             raise ValueError("mode must be 'fp32', 'bf16' or 'fp16'")
         load()
@@ -120,6 +126,15 @@ class NerfMLP:
         """Call after an in-place parameter update so the bf16 weight pack is refreshed."""
         self._packed_version = self._packed_half_version = None
 
+    def mark_packed(self):
+        """After a call that updated the parameters in place AND refreshed the pack of this network's mode on the C side
+        (nerf_train_step_fused): that region is current, the other precision's is stale."""
+        key = (self.params.data_ptr(), self.params._version)
+        if self.mode_id == MODE_FP16:
+            self._packed_half_version, self._packed_version = key, None
+        else:
+            self._packed_version, self._packed_half_version = key, None
+
     # -- workspaces ------------------------------------------------------------------------------------------
     def saved_bytes(self, m):
         return int(load().nerf_mlp_saved_bytes(self.cfg_ref, int(m), self.mode_id))
@@ -135,10 +150,13 @@ class NerfMLP:
             self._buffers[name] = buf
         return buf
 
-    def packed_for(self, params, half=False):
-        """The packed 16-bit weight buffer, refreshed when the parameters changed (bf16 regions; fp16 region if half)."""
+    def packed_for(self, params, half=None):
+        """The packed 16-bit weight buffer, refreshed when the parameters changed (bf16 regions, or the fp16 regions with
+        ``half``; default: what the network's mode reads)."""
         if not self.tensor_core:
             return None
+        if half is None:
+            half = self.mode_id == MODE_FP16
         key = (params.data_ptr(), params._version)
         if self._packed is None:
             self._packed = torch.empty(int(load().nerf_packed_bytes(self.cfg_ref)), dtype=torch.uint8,

@@ -215,14 +215,28 @@ class _RoundBF16(torch.autograd.Function):
         return g
 
 
+class _RoundFP16(torch.autograd.Function):
+    """Straight-through fp16 rounding: the operand rounding of the default tensor-core mode (and of the reference's own
+    mixed_float16 policy, contain_dockerfile.../ExecutionRun.py:221)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        return x.to(torch.float16).to(F32)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g
+
+
 def mlp_forward(params: torch.Tensor, shapes, xyz_enc: torch.Tensor, view_enc: Optional[torch.Tensor],
-                alpha: float = 0.05, emulate_bf16: bool = False) -> torch.Tensor:
+                alpha: float = 0.05, emulate_bf16=False) -> torch.Tensor:
     """src/NeRF.py:312-339 (view variant) / :263-287 (xyz-only).  Returns (M,4) = [r,g,b,sigma] raw.
 
-    emulate_bf16 rounds weights and every MMA operand to bf16 (fp32 accumulate, fp32 bias add and
-    activation) the way the tcgen05 path does; the default is plain fp32.
+    emulate_bf16 = True rounds weights and every MMA operand to bf16 (fp32 accumulate, fp32 bias add and
+    activation) the way the tcgen05 path does in mode "bf16"; emulate_bf16 = "fp16" rounds them to fp16 (mode "fp16");
+    the default is plain fp32.
     """
-    rnd = _RoundBF16.apply if emulate_bf16 else (lambda t: t)
+    rnd = _RoundFP16.apply if emulate_bf16 == "fp16" else (_RoundBF16.apply if emulate_bf16 else (lambda t: t))
     layers = unflatten(params, shapes)
 
     def dense(x, idx, act=True):
@@ -262,6 +276,13 @@ def model_predict(params, shapes, n_enc_phi_theta: int, n_pos_enc_for_xyz: int, 
 # --------------------------------------------------------------------------------------------------
 # Alpha compositing (src/UtilsNeuralRadianceField.py:88-115)
 # --------------------------------------------------------------------------------------------------
+# Throughput switch for bench.py's CPU baseline ONLY (never set by a parity test): True replaces the sequential
+# left-to-right Python loops over the samples of a ray (the canonical, bit-defining order of this oracle) by
+# torch.cumprod / cumsum / sum, i.e. what an optimised CPU implementation such as TF-CPU would run.  Same mathematics,
+# different fp32 summation order.
+FAST_REDUCTIONS = False
+
+
 class _ExclusiveCumprodTF(torch.autograd.Function):
     """tf.math.cumprod(x, -1, exclusive=True) with TensorFlow's gradient
     (math_grad._CumprodGrad: div_no_nan(cumsum(out*grad, exclusive, reverse), x) -> 0 where x == 0).
@@ -269,6 +290,10 @@ class _ExclusiveCumprodTF(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x):
+        if FAST_REDUCTIONS:
+            out = torch.cat([torch.ones_like(x[..., :1]), torch.cumprod(x[..., :-1], dim=-1)], dim=-1)
+            ctx.save_for_backward(x, out)
+            return out
         out = torch.empty_like(x)
         run = torch.ones_like(x[..., 0])
         for i in range(x.shape[-1]):
@@ -281,11 +306,14 @@ class _ExclusiveCumprodTF(torch.autograd.Function):
     def backward(ctx, g):
         x, out = ctx.saved_tensors
         prod = out * g
-        rev = torch.zeros_like(prod)
-        run = torch.zeros_like(prod[..., 0])
-        for i in range(x.shape[-1] - 1, -1, -1):
-            rev[..., i] = run
-            run = run + prod[..., i]
+        if FAST_REDUCTIONS:
+            rev = torch.flip(torch.cumsum(torch.flip(prod, [-1]), dim=-1), [-1]) - prod
+        else:
+            rev = torch.zeros_like(prod)
+            run = torch.zeros_like(prod[..., 0])
+            for i in range(x.shape[-1] - 1, -1, -1):
+                rev[..., i] = run
+                run = run + prod[..., i]
         return torch.where(x == 0, torch.zeros_like(rev), rev / torch.where(x == 0, torch.ones_like(x), x))
 
 
@@ -301,6 +329,8 @@ def ray_marching(model_output: torch.Tensor, z_values: torch.Tensor):
     cumprod = _ExclusiveCumprodTF.apply(1.0 - alpha)                             # :112
     weights = alpha * cumprod                                                    # :113
     # reduce_sum over samples, accumulated in sample order
+    if FAST_REDUCTIONS:
+        return (weights[..., None] * net_rgb_output).sum(-2), weights, cumprod, alpha, net_rgb_output
     rgb_image = torch.zeros(weights.shape[:-1] + (3,), dtype=F32)
     for i in range(weights.shape[-1]):
         rgb_image = rgb_image + weights[..., i, None] * net_rgb_output[..., i, :]
@@ -321,6 +351,8 @@ def depth_and_acc(weights: torch.Tensor, z_values: torch.Tensor):
 # Inverse-CDF importance sampling (src/UtilsCV.py:502-539)
 # --------------------------------------------------------------------------------------------------
 def _seq_sum(x: torch.Tensor) -> torch.Tensor:
+    if FAST_REDUCTIONS:
+        return x.sum(-1)
     run = torch.zeros_like(x[..., 0])
     for i in range(x.shape[-1]):
         run = run + x[..., i]
@@ -328,6 +360,8 @@ def _seq_sum(x: torch.Tensor) -> torch.Tensor:
 
 
 def _seq_cumsum(x: torch.Tensor) -> torch.Tensor:
+    if FAST_REDUCTIONS:
+        return torch.cumsum(x, dim=-1)
     outs = []
     run = torch.zeros_like(x[..., 0])
     for i in range(x.shape[-1]):

@@ -87,7 +87,9 @@ def test_fused_entry_points_report_argument_errors(pkg):
     t_bytes = lib.nerf_train_workspace_bytes(ctypes.byref(cfg), ctypes.byref(rc), 1000)
     assert n_bytes >= 1000 * (64 + 192 * 4 + 64 + 128 + 192) * 4 and t_bytes > n_bytes
     assert lib.nerf_render_workspace_bytes(ctypes.byref(cfg), ctypes.byref(L.RenderCfg(0.5576, 2.5635, 0, 128, 1)), 10) == -1
-    assert lib.nerf_train_workspace_bytes(ctypes.byref(cfg), ctypes.byref(L.RenderCfg(0.5576, 2.5635, 64, 128, L.MODE_FP16)), 10) == -1
+    # the fp16-operand mode trains too (round 2): same workspace as the bf16 mode, whose backward it shares
+    assert lib.nerf_train_workspace_bytes(ctypes.byref(cfg), ctypes.byref(L.RenderCfg(0.5576, 2.5635, 64, 128, L.MODE_FP16)), 1000) == t_bytes
+    assert lib.nerf_train_workspace_bytes(ctypes.byref(cfg), ctypes.byref(L.RenderCfg(0.5576, 2.5635, 64, 128, 7)), 10) == -1
     rng, outs = L.RngState(1, 0, 0, 0), L.RenderOuts()
     st = lib.nerf_render_fused_fwd(ctypes.byref(cfg), ctypes.byref(rc), None, None, None, None, ctypes.c_void_p(256),
                                    ctypes.c_void_p(256), 4, ctypes.byref(rng), ctypes.byref(outs), ctypes.c_void_p(256), None)
