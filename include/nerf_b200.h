@@ -114,6 +114,14 @@ int nerf_mlp_fwd(const nerf_net_cfg* cfg, const float* params, const void* packe
 int nerf_mlp_fwd_rays(const nerf_net_cfg* cfg, const void* packed, const float* origs4, const float* dirs4,
                       const float* z, int64_t n_rays, int32_t n_samples, float* out4, void* saved_or_null,
                       int32_t mode, void* stream);
+/* The coarse pass of NeRF.render / train_step with the stratified sampling fused in as well: get_z_values
+ * (src/UtilsCV.py:565-581; call sites src/NeRF.py:127,146) is evaluated in the MLP prologue from the Philox stream -- the
+ * same draws and arithmetic as nerf_stratified_z, bit for bit -- so the coarse depths go straight from registers into the
+ * positional encoding; they are also written to z_out (N,S) for the compositing and importance-sampling kernels. */
+int nerf_mlp_fwd_rays_stratified(const nerf_net_cfg* cfg, const void* packed, const float* origs4, const float* dirs4,
+                                 float z_start, float z_end, uint64_t seed, uint32_t step, uint64_t ray_offset,
+                                 int64_t n_rays, int32_t n_samples, float* z_out, float* out4, void* saved_or_null,
+                                 int32_t mode, void* stream);
 /* grads (+= , same layout as params); d_xyz_enc_or_null (M, Dx) is written when non-null.  xyz_enc / view_enc may be
  * null in NERF_MODE_BF16 (the forward pass saved its bf16 input panel). */
 int nerf_mlp_bwd(const nerf_net_cfg* cfg, const float* params, const void* packed_or_null,

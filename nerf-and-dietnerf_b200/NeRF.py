@@ -237,6 +237,41 @@ class NeRF:
         return _unrf.render_rays(model, rays_orig, rays_dirs, z, self.n_pos_enc_dim_xyz, self.n_pos_enc_view_dir,
                                  self.n_angles_for_model)
 
+    def _coarse_pass(self, model, rays_orig, rays_dirs, n, n_c, seed, step, ray_offset, jitter, z, raw, saved=None, mode_id=None,
+                     xyz=None, view=None, ws=None):
+        """Stratified depths + coarse MLP on them, into the caller's ``z`` (n, n_c) and ``raw`` (n, n_c, 4) buffers.
+        Tensor-core modes with the Philox stream: ONE kernel (``nerf_mlp_fwd_rays_stratified``: get_z_values, sample_along_rays,
+        both encodings and the network; north_star's kernel (1) fused into kernel (2)).  Explicit ``jitter`` or the fp32
+        mode: ``nerf_stratified_z`` first -- same depths, bit for bit."""
+        mode_id = model.mode_id if mode_id is None else mode_id
+        if model.tensor_core and jitter is None:
+            call("nerf_mlp_fwd_rays_stratified", model.cfg_ref, ptr(model.packed_for(model.params, half=mode_id == _lib.MODE_FP16)),
+                 ptr(rays_orig), ptr(rays_dirs), self.near_boundary, self.far_boundary, int(seed), int(step), int(ray_offset),
+                 n, n_c, ptr(z), ptr(raw), ptr(saved), mode_id)
+            return
+        call("nerf_stratified_z", self.near_boundary, self.far_boundary, n, n_c, ptr(jitter), int(seed or 0), int(step or 0),
+             int(ray_offset), ptr(z))
+        if model.tensor_core:
+            call("nerf_mlp_fwd_rays", model.cfg_ref, ptr(model.packed_for(model.params, half=mode_id == _lib.MODE_FP16)),
+                 ptr(rays_orig), ptr(rays_dirs), ptr(z), n, n_c, ptr(raw), ptr(saved), mode_id)
+        else:
+            if xyz is None:
+                xyz = torch.empty((n * n_c, model.dx), dtype=torch.float32, device=z.device)
+                view = torch.empty((n * n_c, model.dv), dtype=torch.float32, device=z.device) if model.dv else None
+            if ws is None:
+                ws = model._buffer("ws_fwd", model.workspace_bytes(n * n_c, False))
+            call("nerf_encode_samples", model.cfg_ref, ptr(rays_orig), ptr(rays_dirs), ptr(z), n, n_c, ptr(xyz), ptr(view))
+            call("nerf_mlp_fwd", model.cfg_ref, ptr(model.params), ptr(model.packed_for(model.params)), ptr(xyz), ptr(view),
+                 n * n_c, ptr(raw), ptr(saved), ptr(ws), mode_id)
+
+    def _coarse_render(self, rays_orig, rays_dirs, n, n_c, seed, step, ray_offset, jitter, lean=False):
+        """Coarse half of ``render``: (z, ray_marching outputs)."""
+        z = torch.empty((n, n_c), dtype=torch.float32, device=self.device)
+        raw = torch.empty((n, n_c, 4), dtype=torch.float32, device=self.device)
+        mc = self.model_coarse
+        self._coarse_pass(mc, rays_orig, rays_dirs, n, n_c, seed, step, ray_offset, jitter, z, raw, mode_id=mc.infer_mode_id)
+        return z, (_unrf.ray_marching_lean(raw, z) if lean else _unrf.ray_marching(raw, z))
+
     def _render_rays_fused(self, model, rays_orig, rays_dirs, z, lean=False):
         """Inference-only fast path: fused encode -> MLP -> compositing, no autograd bookkeeping."""
         n, s = z.shape
@@ -271,9 +306,8 @@ class NeRF:
         if seed is None and jitter is None:
             seed, step = rng.next_step()
         with torch.no_grad():
-            z = get_z_values(self.near_boundary, self.far_boundary, n, 1, n_c, jitter=jitter, seed=seed, step=step,
-                             ray_offset=ray_offset)[:, 0, :]
-            out = self._render_rays_fused(self.model_coarse, rays_orig, rays_dirs, z)
+            z, out = self._coarse_render(rays_orig, rays_dirs, n, n_c, seed, step, ray_offset,
+                                         None if jitter is None else f32c(jitter, self.device))
             if self.model_fine is not None:
                 n_f = n_render_samples_f if n_render_samples_f else self.n_render_samples_fine
                 z_from_dist = get_z_vals_from_prob_dist_func(out[1], z, n_f, u=u, seed=seed if u is None else None,
@@ -408,9 +442,7 @@ class NeRF:
                 o, d = orig[s0:s0 + batch_size], dirs[s0:s0 + batch_size]
                 n = o.shape[0]
                 off = ray_begin + s0
-                z = get_z_values(self.near_boundary, self.far_boundary, n, 1, n_c, seed=seed, step=step,
-                                 ray_offset=off)[:, 0, :]
-                rgb, wts, depth, acc = self._render_rays_fused(self.model_coarse, o, d, z, lean=True)
+                z, (rgb, wts, depth, acc) = self._coarse_render(o, d, n, n_c, seed, step, off, None, lean=True)
                 if self.model_fine is not None:
                     z_f = get_z_vals_from_prob_dist_func(wts, z, n_f, seed=seed, step=step, ray_offset=off)
                     z_all = torch.empty((n, n_f + n_c), dtype=torch.float32, device=self.device)
@@ -472,9 +504,8 @@ class NeRF:
         o, d, y = rays_orig, rays_dirs, real_rgb
 
         # coarse forward
-        call("nerf_stratified_z", self.near_boundary, self.far_boundary, n, sc, ptr(jitter), seed, step, ray_offset,
-             ptr(w.z_c))
-        self._mlp_fwd_train(mc, o, d, w.z_c, n, sc, w.xyz_c, w.view_c, w.raw_c, w.saved_c, w.ws_fwd)
+        self._coarse_pass(mc, o, d, n, sc, seed, step, ray_offset, jitter, w.z_c, w.raw_c, saved=w.saved_c, xyz=w.xyz_c,
+                          view=w.view_c, ws=w.ws_fwd)
         # ray_marching + MSE (+ its gradient) in one launch each: the loss is formed where the ray's colour is reduced
         call("nerf_composite_mse_fwd", ptr(w.raw_c), ptr(w.z_c), ptr(y), n, sc, n_total, self.COARSE_LOSS_WEIGHT,
              ptr(w.rgb_c), ptr(w.w_c), ptr(sums[0:1]), ptr(w.d_rgb_c))
@@ -536,9 +567,8 @@ class NeRF:
         sf = nf + sc
         w = self._workspace(n, sc, sf if mf is not None else 0, nf if mf is not None else None)
         _, g_c, g_f = self._grad_views()
-        call("nerf_stratified_z", self.near_boundary, self.far_boundary, n, sc, ptr(jitter), seed, step, ray_offset,
-             ptr(w.z_c))
-        self._mlp_fwd_train(mc, o, d, w.z_c, n, sc, w.xyz_c, w.view_c, w.raw_c, w.saved_c, w.ws_fwd)
+        self._coarse_pass(mc, o, d, n, sc, seed, step, ray_offset, jitter, w.z_c, w.raw_c, saved=w.saved_c, xyz=w.xyz_c,
+                          view=w.view_c, ws=w.ws_fwd)
         call("nerf_composite_fwd", ptr(w.raw_c), ptr(w.z_c), n, sc, ptr(w.rgb_c), ptr(w.w_c), None, None, None, None,
              None)
         if mf is None:

@@ -73,6 +73,8 @@ SIGNATURES = {
     "nerf_mlp_workspace_bytes": (c_int64, [_CFG, c_int64, c_int32, c_int32]),
     "nerf_mlp_fwd": (c_int32, [_CFG, _P, _P, _P, _P, c_int64, _P, _P, _P, c_int32, _P]),
     "nerf_mlp_fwd_rays": (c_int32, [_CFG, _P, _P, _P, _P, c_int64, c_int32, _P, _P, c_int32, _P]),
+    "nerf_mlp_fwd_rays_stratified": (c_int32, [_CFG, _P, _P, _P, c_float, c_float, c_uint64, c_uint32, c_uint64, c_int64, c_int32,
+                                               _P, _P, _P, c_int32, _P]),
     "nerf_mlp_bwd": (c_int32, [_CFG, _P, _P, _P, _P, _P, _P, c_int64, _P, _P, _P, c_int32, _P]),
     "nerf_mlp_bwd_overlapped": (c_int32, [_CFG, _P, _P, _P, _P, _P, _P, c_int64, _P, _P, _P, c_int32, _P, _P]),
     "nerf_mlp_bwd_dx": (c_int32, [_CFG, _P, _P, _P, _P, _P, _P, c_int64, _P, _P, _P, c_int32, _P]),
@@ -152,7 +154,7 @@ def check(status, what):
 
 
 # kernels launched per C-ABI call (bf16 mode; the fp32 MLP launches one GEMM per layer and is counted separately)
-KERNELS_PER_CALL = {"nerf_render_fused_fwd": 7, "nerf_train_step_fused": 22, "nerf_mlp_fwd": 1, "nerf_mlp_fwd_rays": 1, "nerf_mlp_bwd": 3, "nerf_mlp_bwd_overlapped": 3, "nerf_mlp_bwd_dx": 1, "nerf_mlp_bwd_dw": 2,
+KERNELS_PER_CALL = {"nerf_render_fused_fwd": 7, "nerf_train_step_fused": 22, "nerf_mlp_fwd": 1, "nerf_mlp_fwd_rays": 1, "nerf_mlp_fwd_rays_stratified": 1, "nerf_mlp_bwd": 3, "nerf_mlp_bwd_overlapped": 3, "nerf_mlp_bwd_dx": 1, "nerf_mlp_bwd_dw": 2,
                     "nerf_pack_weights": 2}
 launch_count = 0            # kernels launched through call() since import (bench.py reads the delta)
 event_hook = None           # optional callable(name) -> context manager, used by bench.py to time single calls

@@ -47,6 +47,14 @@ bool device_first_use(int slot);
 
 inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
+// coarse depths drawn inside the MLP prologue (nerf_mlp_fwd_rays_stratified)
+struct StratifiedZ {
+  float z_start, z_end;
+  uint64_t seed, ray_offset;
+  uint32_t step;
+  float* z_out;
+};
+
 // ---- network geometry ---------------------------------------------------------------------------------
 struct LayerDesc {
   int in, out;
@@ -115,6 +123,21 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
 
 __device__ __forceinline__ float bits_to_uniform(uint32_t w) {
   return __uint_as_float((w & 0x7FFFFFu) | 0x3F800000u) - 1.0f;
+}
+
+// tf.linspace(start, stop, n)[i] in fp32 (src/UtilsCV.py:573): exact end points, start + delta * i in between
+__device__ __forceinline__ float linspace_tf(float start, float stop, float delta, int i, int n) {
+  if (i == 0) return start;
+  if (i == n - 1) return stop;
+  return __fadd_rn(start, __fmul_rn(delta, (float)i));
+}
+
+// get_z_values (src/UtilsCV.py:565-581) for sample s of a ray: linspace + jitter u * span / n.  ONE definition shared by
+// the stand-alone kernel (nerf_stratified_z) and the MLP prologue that generates the coarse depths itself.
+__device__ __forceinline__ float stratified_z_value(float z_start, float z_end, float span, int n_samples, int s, float u) {
+  const float delta = n_samples > 1 ? __fdiv_rn(__fsub_rn(z_end, z_start), (float)(n_samples - 1)) : 0.f;
+  const float lin = linspace_tf(z_start, z_end, delta, s, n_samples);
+  return __fadd_rn(lin, __fdiv_rn(__fmul_rn(u, span), (float)n_samples));
 }
 
 // four uniforms: draws 4*block .. 4*block+3 of (ray, stream, step)

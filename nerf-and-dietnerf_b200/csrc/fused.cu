@@ -50,6 +50,21 @@ void carve_encode(Carver& c, const NetGeom& g, const nerf_net_cfg* cfg, int32_t 
   e->mlp_ws = c.take<uint8_t>(nerf_mlp_workspace_bytes(cfg, m_max, mode, backward ? 1 : 0));
 }
 
+// the coarse pass: stratified depths (src/NeRF.py:127,146) + model_predict on them -- one kernel in the tensor-core modes
+int coarse_forward(const nerf_net_cfg* cfg, const nerf_render_cfg* rc, const nerf_rng_state* rng, const float* params,
+                   const void* packed, const float* o, const float* d, float* z, int64_t n, float* raw, void* saved,
+                   float* xyz, float* view, void* mlp_ws, void* stream) {
+  const int32_t s = rc->n_samples_coarse;
+  if (rc->mode != NERF_MODE_FP32)
+    return nerf_mlp_fwd_rays_stratified(cfg, packed, o, d, rc->near_boundary, rc->far_boundary, rng->seed, rng->step,
+                                        rng->ray_offset, n, s, z, raw, saved, rc->mode, stream);
+  int r = nerf_stratified_z(rc->near_boundary, rc->far_boundary, n, s, nullptr, rng->seed, rng->step, rng->ray_offset, z, stream);
+  if (r != NERF_OK) return r;
+  r = nerf_encode_samples(cfg, o, d, z, n, s, xyz, view, stream);
+  if (r != NERF_OK) return r;
+  return nerf_mlp_fwd(cfg, params, packed, xyz, view, n * s, raw, saved, mlp_ws, rc->mode, stream);
+}
+
 // model_predict on the samples of n rays (src/UtilsNeuralRadianceField.py:204-207, :214-234)
 int net_forward(const nerf_net_cfg* cfg, int32_t mode, const float* params, const void* packed, const float* o,
                 const float* d, const float* z, int64_t n, int32_t s, float* raw, void* saved, float* xyz, float* view,
@@ -192,12 +207,9 @@ int nerf_render_fused_fwd(const nerf_net_cfg* cfg, const nerf_render_cfg* rc, co
   carve_render(g, cfg, rc, n_rays, (uint8_t*)workspace, &w);
   const int32_t sc = rc->n_samples_coarse, nf = rc->n_samples_fine;
   const int64_t n = n_rays;
-  // z = get_z_values(near, far, N, 1, S_c)[:, 0, :]                                                  (:127)
-  NERF_TRY(nerf_stratified_z(rc->near_boundary, rc->far_boundary, n, sc, nullptr, rng->seed, rng->step, rng->ray_offset,
-                             w.z_c, stream));
-  // coarse render_rays                                                                                 (:128-129)
-  NERF_TRY(net_forward(cfg, rc->mode, params_c, packed_c, origs4, dirs4, w.z_c, n, sc, w.raw, nullptr, w.enc.xyz,
-                       w.enc.view, w.enc.mlp_ws, stream));
+  // z = get_z_values(near, far, N, 1, S_c)[:, 0, :] and the coarse render_rays                         (:127-129)
+  NERF_TRY(coarse_forward(cfg, rc, rng, params_c, packed_c, origs4, dirs4, w.z_c, n, w.raw, nullptr, w.enc.xyz, w.enc.view,
+                          w.enc.mlp_ws, stream));
   if (!fine) {
     NERF_TRY(nerf_composite_fwd(w.raw, w.z_c, n, sc, outs->rgb, outs->weights, outs->cumprod, outs->alpha, outs->rgb_s,
                                 outs->depth, outs->acc, stream));
@@ -264,10 +276,8 @@ int nerf_train_step_fused(const nerf_net_cfg* cfg, const nerf_render_cfg* rc, co
     carve_train(g, cfg, rc, n, (uint8_t*)workspace, &w);
     const bool through_z = fine && !tc_cfg->stop_grad_z;
     // coarse forward + loss                                                            (src/NeRF.py:146-151)
-    NERF_TRY(nerf_stratified_z(rc->near_boundary, rc->far_boundary, n, sc, nullptr, rng->seed, rng->step,
-                               rng->ray_offset, w.z_c, stream));
-    NERF_TRY(net_forward(cfg, mode, params_c, packed_c, origs4, dirs4, w.z_c, n, sc, w.raw_c, w.saved_c, w.xyz_c,
-                         w.view_c, w.ws_fwd, stream));
+    NERF_TRY(coarse_forward(cfg, rc, rng, params_c, packed_c, origs4, dirs4, w.z_c, n, w.raw_c, w.saved_c, w.xyz_c, w.view_c,
+                            w.ws_fwd, stream));
     NERF_TRY(nerf_composite_mse_fwd(w.raw_c, w.z_c, target_rgb, n, sc, n_total_rays, tc_cfg->coarse_loss_weight, w.rgb_c,
                                     w.w_c, sums, w.d_rgb_c, stream));
     const float* d_w_c = nullptr;

@@ -13,7 +13,8 @@ int mlp_tc_bwd(const nerf_net_cfg* cfg, const NetGeom& g, const float* params, c
                const float* view_enc, const void* saved, const float* d_out4, int64_t m, float* grads, float* d_xyz_enc,
                void* workspace, cudaStream_t st, int parts, cudaStream_t side, bool half);
 int mlp_tc_fwd_rays(const nerf_net_cfg* cfg, const NetGeom& g, const void* packed, const float* origs4, const float* dirs4,
-                    const float* z, int64_t n_rays, int n_samples, float* out4, void* saved, cudaStream_t st, bool half);
+                    const float* z, int64_t n_rays, int n_samples, float* out4, void* saved, cudaStream_t st, bool half,
+                    const StratifiedZ* gen = nullptr);
 int64_t mlp_tc_saved_bytes(const NetGeom& g, int64_t m);
 int64_t mlp_tc_workspace_bytes(const NetGeom& g, int64_t m, int backward);
 
@@ -372,6 +373,25 @@ int nerf_mlp_fwd_rays(const nerf_net_cfg* cfg, const void* packed, const float* 
   if (n_rays == 0) return NERF_OK;
   return mlp_tc_fwd_rays(cfg, g, packed, origs4, dirs4, z, n_rays, n_samples, out4, saved_or_null, (cudaStream_t)stream,
                          mode == NERF_MODE_FP16);
+}
+
+int nerf_mlp_fwd_rays_stratified(const nerf_net_cfg* cfg, const void* packed, const float* origs4, const float* dirs4,
+                                 float z_start, float z_end, uint64_t seed, uint32_t step, uint64_t ray_offset,
+                                 int64_t n_rays, int32_t n_samples, float* z_out, float* out4, void* saved_or_null,
+                                 int32_t mode, void* stream) {
+  NetGeom g;
+  NERF_CHECK_ARG(make_geom(cfg, &g), "bad net config");
+  NERF_CHECK_ARG(packed && origs4 && dirs4 && z_out && out4, "null pointer");
+  NERF_CHECK_ARG(n_rays >= 0 && n_samples > 0, "bad shape");
+  if (mode != NERF_MODE_BF16 && mode != NERF_MODE_FP16) {
+    set_error("nerf_mlp_fwd_rays_stratified: only the tensor-core modes fuse the sampling into the MLP kernel "
+              "(fp32 mode: nerf_stratified_z + nerf_encode_samples + nerf_mlp_fwd)");
+    return NERF_E_UNSUPPORTED;
+  }
+  if (n_rays == 0) return NERF_OK;
+  StratifiedZ gen = {z_start, z_end, seed, ray_offset, step, z_out};
+  return mlp_tc_fwd_rays(cfg, g, packed, origs4, dirs4, nullptr, n_rays, n_samples, out4, saved_or_null, (cudaStream_t)stream,
+                         mode == NERF_MODE_FP16, &gen);
 }
 
 // parts: bit 0 = input-gradient chain (dZ of every layer, d_xyz_enc), bit 1 = weight gradients from the saved activations

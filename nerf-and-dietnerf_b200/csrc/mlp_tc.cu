@@ -131,6 +131,9 @@ static_assert(sizeof(FwdBars) <= 192, "barrier block overflows its shared-memory
 // Where the MLP input comes from: pre-encoded rows (xyz_enc / view_enc, the standalone model_predict entry point) or,
 // when xyz_enc == nullptr, rays + depths: then the sample position o + d z and both sin/cos encodings are computed in
 // the prologue and written straight into the shared-memory input panel (K1 fused into K2; nothing touches HBM).
+// With gen_z the depths are not read either: the prologue draws the stratified coarse depths itself (get_z_values,
+// src/UtilsCV.py:565-581 -- the same Philox stream and arithmetic as nerf_stratified_z, bit for bit) and writes them to
+// z_out for the compositing / sampler kernels that follow.
 struct FwdInput {
   const float* xyz_enc;
   const float* view_enc;
@@ -138,7 +141,30 @@ struct FwdInput {
   const float4* dirs;
   const float* z;
   int32_t n_samples, Lx, Lv, ncomp, dx, dv;
+  int32_t gen_z;
+  float z_start, z_end, span;
+  uint32_t step;
+  uint64_t seed, ray_offset;
+  float* z_out;
 };
+
+// A real call on purpose: inlined, the ten Philox rounds cost the kernel's hot loops their last spare registers (96 cap).
+__device__ __noinline__ float draw_stratified_z(float z_start, float z_end, float span, int n_samples, int s, uint64_t seed,
+                                                uint32_t ray, uint32_t step) {
+  const float4 u4 = philox_uniform4(seed, ray, (uint32_t)(s >> 2), 0u, step);
+  const float u = (s & 3) == 0 ? u4.x : (s & 3) == 1 ? u4.y : (s & 3) == 2 ? u4.z : u4.w;
+  return stratified_z_value(z_start, z_end, span, n_samples, s, u);
+}
+
+// depth of MLP row `row` (ray-major): read, or drawn here (and published) when in.gen_z
+__device__ __forceinline__ float row_depth(const FwdInput& in, int64_t row, int64_t ray) {
+  if (!in.gen_z) return __ldg(in.z + row);
+  const int s = (int)(row - ray * in.n_samples);
+  const float zz = draw_stratified_z(in.z_start, in.z_end, in.span, in.n_samples, s, in.seed,
+                                     (uint32_t)(ray + (int64_t)in.ray_offset), in.step);
+  in.z_out[row] = zz;
+  return zz;
+}
 
 template <bool kHalf>
 __device__ __forceinline__ void sts_16(uint32_t panel_row_addr, int r, int col, float v) {
@@ -443,7 +469,7 @@ mlp_tc_fwd_kernel(const __grid_constant__ TcPlan plan, const uint8_t* __restrict
         const float4 d = row_ok ? __ldg(in.dirs + ray) : make_float4(0.f, 0.f, 0.f, 0.f);
         if (half == 0) {
           const float4 o = row_ok ? __ldg(in.origs + ray) : make_float4(0.f, 0.f, 0.f, 0.f);
-          const float zz = row_ok ? __ldg(in.z + row) : 0.f;
+          const float zz = row_ok ? row_depth(in, row, ray) : 0.f;
           float v[40];
 #pragma unroll
           for (int c = 0; c < 3; ++c) {
@@ -497,7 +523,7 @@ mlp_tc_fwd_kernel(const __grid_constant__ TcPlan plan, const uint8_t* __restrict
             const float4 d = __ldg(in.dirs + ray);
             if (half == 0) {
               const float4 o = __ldg(in.origs + ray);
-              const float zz = __ldg(in.z + row);
+              const float zz = row_depth(in, row, ray);
               const int per = 1 + 2 * in.Lx;
 #pragma unroll
               for (int c = 0; c < 3; ++c) {
@@ -736,9 +762,16 @@ int mlp_tc_fwd(const nerf_net_cfg* cfg, const NetGeom& g, const float* params, c
 }
 
 int mlp_tc_fwd_rays(const nerf_net_cfg* cfg, const NetGeom& g, const void* packed, const float* origs4, const float* dirs4,
-                    const float* z, int64_t n_rays, int n_samples, float* out4, void* saved, cudaStream_t st, bool half) {
+                    const float* z, int64_t n_rays, int n_samples, float* out4, void* saved, cudaStream_t st, bool half,
+                    const StratifiedZ* gen) {
   FwdInput in = {};
   in.origs = (const float4*)origs4; in.dirs = (const float4*)dirs4; in.z = z; in.n_samples = n_samples;
+  if (gen) {
+    in.gen_z = 1; in.z_start = gen->z_start; in.z_end = gen->z_end;
+    // (z_end - z_start) is formed in double from the Python floats and then cast (src/UtilsCV.py:580), as in nerf_stratified_z
+    in.span = (float)((double)gen->z_end - (double)gen->z_start);
+    in.seed = gen->seed; in.step = gen->step; in.ray_offset = gen->ray_offset; in.z_out = gen->z_out;
+  }
   in.dx = g.dx; in.dv = g.dv; in.Lx = cfg->n_pos_enc_xyz; in.Lv = cfg->n_pos_enc_view; in.ncomp = cfg->n_angles + 1;
   return launch_fwd(cfg, g, packed, in, n_rays * n_samples, out4, saved, st, half);
 }

@@ -43,11 +43,6 @@ __global__ void ray_directions_kernel(C2W c2w, float tan_half_fov, int h, int w,
 }
 
 // ---- stratified z ------------------------------------------------------------------------------------------
-__device__ __forceinline__ float linspace_tf(float start, float stop, float delta, int i, int n) {
-  if (i == 0) return start;
-  if (i == n - 1) return stop;
-  return __fadd_rn(start, __fmul_rn(delta, (float)i));
-}
 
 __global__ void stratified_z_kernel(float z_start, float z_end, float span, int64_t n_rays, int n_samples,
                                     const float* __restrict__ jitter, uint64_t seed, uint32_t step,
@@ -57,7 +52,6 @@ __global__ void stratified_z_kernel(float z_start, float z_end, float span, int6
   if (t >= n_rays * blocks_per_ray) return;
   int64_t ray = t / blocks_per_ray;
   int blk = (int)(t % blocks_per_ray);
-  float delta = n_samples > 1 ? __fdiv_rn(__fsub_rn(z_end, z_start), (float)(n_samples - 1)) : 0.f;
   float u[4];
   if (jitter) {
 #pragma unroll
@@ -72,10 +66,7 @@ __global__ void stratified_z_kernel(float z_start, float z_end, float span, int6
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
     int s = blk * 4 + k;
-    if (s < n_samples) {
-      float lin = linspace_tf(z_start, z_end, delta, s, n_samples);
-      z[ray * n_samples + s] = __fadd_rn(lin, __fdiv_rn(__fmul_rn(u[k], span), (float)n_samples));
-    }
+    if (s < n_samples) z[ray * n_samples + s] = stratified_z_value(z_start, z_end, span, n_samples, s, u[k]);
   }
 }
 

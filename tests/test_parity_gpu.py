@@ -1261,3 +1261,29 @@ def test_dietnerf_consistency_hook_gradient_layout(pkg):
     assert abs(ma["cosine_similarity_loss"].item() - 0.25) < 1e-7
     with pytest.raises(RuntimeError, match="consistency_loss_fn"):
         a.train_step_fused(dev(o), dev(d), dev(y))
+
+
+@pytest.mark.parametrize("mode", ["fp16", "bf16"])
+@pytest.mark.parametrize("n_rays,s", [(333, 64), (100, 55), (2048 + 37, 64), (7, 1)])
+def test_fused_coarse_pass_draws_the_same_depths(pkg, mode, n_rays, s):
+    """north_star kernel (1) inside kernel (2): nerf_mlp_fwd_rays_stratified draws get_z_values (src/UtilsCV.py:565-581) in
+    the MLP prologue.  Depths bit-identical to nerf_stratified_z (and so to the oracle's Philox stream), network output
+    bit-identical to the two-kernel sequence."""
+    call, ptr = pkg._lib.call, pkg._lib.ptr
+    net = pkg.NerfMLP(pkg.NetCfg(5, 4, 2, 256, 128, 0.05), mode=mode, seed=3)
+    g = torch.Generator(device="cuda").manual_seed(5)
+    o4 = torch.randn(n_rays, 4, device="cuda", generator=g)
+    d4 = torch.randn(n_rays, 4, device="cuda", generator=g)
+    packed = net.packed_for(net.params)
+    z_ref = torch.empty(n_rays, s, device="cuda")
+    out_ref = torch.empty(n_rays * s, 4, device="cuda")
+    call("nerf_stratified_z", NEAR, FAR, n_rays, s, None, 9, 4, 1000, ptr(z_ref))
+    call("nerf_mlp_fwd_rays", net.cfg_ref, ptr(packed), ptr(o4), ptr(d4), ptr(z_ref), n_rays, s, ptr(out_ref), None, net.mode_id)
+    z = torch.full((n_rays, s), float("nan"), device="cuda")
+    out = torch.empty(n_rays * s, 4, device="cuda")
+    call("nerf_mlp_fwd_rays_stratified", net.cfg_ref, ptr(packed), ptr(o4), ptr(d4), NEAR, FAR, 9, 4, 1000, n_rays, s, ptr(z),
+         ptr(out), None, net.mode_id)
+    assert torch.equal(z, z_ref), "depths drawn in the MLP prologue differ from nerf_stratified_z"
+    assert torch.equal(out, out_ref)
+    jit = O.stratified_jitter(9, 4, n_rays, s, ray_offset=1000)
+    assert torch.equal(z.cpu(), O.get_z_values(NEAR, FAR, n_rays, s, jit)), "Philox stream differs from the oracle's"
