@@ -376,9 +376,11 @@ def main():
             yield
     pkg._lib.event_hook = hook
     model.overlap_dw = False          # one stream, the backward's two halves as separate calls: each kernel is timed alone
+    model.use_fused_step = False      # ... through the host package's call sequence (the same kernels as the one C call)
     type(model).split_bwd_calls = True
     timed(step_device, args.steps)
     model.overlap_dw = True
+    model.use_fused_step = True
     type(model).split_bwd_calls = False
     pkg._lib.event_hook = None
     torch.cuda.synchronize()

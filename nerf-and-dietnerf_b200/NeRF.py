@@ -98,6 +98,10 @@ class NeRF:
     COARSE_LOSS_WEIGHT = 1.0
     # True: the one-stream backward issues its two halves as separate C-ABI calls (bench.py times them one by one)
     split_bwd_calls = False
+    # True (default): on one GPU ``train_step_local`` IS one call of ``nerf_train_step_fused`` (the same kernels, enqueued by
+    # the C side: half the host time per step); False: the host package's own call sequence (what a sharded run uses, whose
+    # all-reduces sit between the calls)
+    use_fused_step = True
 
     def __init__(self, net_config: Dict, render_config: Dict, near_boundary: float, far_boundary: float, *,
                  mode: str = DEFAULT_MODE, device=None, seed=None, stop_grad_z: bool = False):
@@ -694,6 +698,9 @@ class NeRF:
         if self.optimizer is None:
             raise RuntimeError("call compile(optimizer=Adam(lr)) before train_step")
         mc, mf = self.model_coarse, self.model_fine
+        if (self.use_fused_step and self.world_size == 1 and getattr(self, "_extra_grads", None) is None
+                and hasattr(self.optimizer, "apply_one") and int(n_total_rays) == rays_orig.shape[0]):
+            return self.train_step_fused(rays_orig, rays_dirs, real_rgb, n_total_rays=n_total_rays, ray_offset=ray_offset)
         n_all = mc.n_params + (mf.n_params if mf is not None else 0)
         t_next = self.optimizer.iterations + 1
         early = mf is not None and hasattr(self.optimizer, "apply_one") and getattr(self, "_extra_grads", None) is None

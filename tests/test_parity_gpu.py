@@ -956,7 +956,7 @@ def test_render_fused_entry_point_equals_the_call_sequence(pkg, mode, n_angles, 
     assert empty[0].shape == (0, 3) and empty[5].shape == (0, n_c + n_f)
 
 
-@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+@pytest.mark.parametrize("mode", ["fp32", "bf16", "fp16"])
 @pytest.mark.parametrize("diet,n_f,stop", [(False, 128, False), (True, 128, False), (False, 0, False), (False, 128, True)])
 def test_train_step_fused_entry_point_equals_the_call_sequence(pkg, mode, diet, n_f, stop):
     """NeRF.train_step (and DietNeRF's ray loss) through ONE C-ABI call (given a side stream like the host package uses,
@@ -973,9 +973,10 @@ def test_train_step_fused_entry_point_equals_the_call_sequence(pkg, mode, diet, 
     # case) everything on one stream; the split-K partition of dW follows the SMs the kernel gets, so both sides of a
     # bit-for-bit comparison run the same variant
     a.overlap_dw = b.overlap_dw = not stop
+    a.use_fused_step = False             # a = the host package's own call sequence (one GPU now defaults to the C call)
     o, d = random_rays(n, 4)
     o, d = dev(o), dev(d)
-    exact = mode == "bf16"
+    exact = mode != "fp32"
     for step in range(2):
         y = dev(torch.rand(n, 3, generator=torch.Generator().manual_seed(5 + step)))
         ma = a.train_step_local(o, d, y, n)
@@ -1241,6 +1242,7 @@ def test_dietnerf_consistency_hook_gradient_layout(pkg):
     o, d = random_rays(n, 4)
     y = torch.rand(n, 3)
     a, b = build(hook), build(None)
+    b.use_fused_step = False                    # both through apply_gradients, where the spy below looks
     seen = {}
     orig_apply = pkg.NeRFModel.apply_gradients
 
