@@ -224,6 +224,20 @@ int nerf_train_metrics(const float* sq_err_sums, int64_t n_total_rays, float coa
 int nerf_adam_step(float* params, const float* grads, float* m, float* v, int64_t n, float lr, float beta1,
                    float beta2, float eps, int64_t t, void* stream);
 
+/* ---- gradient exchange of the ray-sharded train step over NVLink peer memory (replaces the all-reduce a
+ * tf.distribute strategy would insert around optimizer.apply_gradients, src/NeRF.py:164-167) -------------------------- */
+/* Barrier over the GPUs of one box.  pads_dev: DEVICE array of `world` pointers, entry r = rank r's signal pad (>= 1 KB of
+ * zero-initialised uint32, peer-mapped symmetric memory).  `epoch` must grow from call to call on the same `slot` (0..3;
+ * one slot per stream that issues barriers). */
+int nerf_peer_barrier(void* const* pads_dev, int32_t rank, int32_t world, uint32_t epoch, int32_t slot, void* stream);
+/* One-shot all-reduce (sum, rank order: bit-identical on every GPU) of floats [offset, offset + n) of the `world` flat
+ * gradient buffers grads_dev[r] (DEVICE array of peer-mapped base pointers), fused with nerf_adam_step's update of
+ * params / m / v (n floats each; same arithmetic).  params_or_null == NULL: reduction only.  reduced_or_null: local copy of
+ * the summed slice.  Call after nerf_peer_barrier on the same stream; offset must be a multiple of 4. */
+int nerf_peer_reduce_adam(float* params_or_null, void* const* grads_dev, int32_t world, int64_t offset, int64_t n, float* m,
+                          float* v, float lr, float beta1, float beta2, float eps, int64_t t, float* reduced_or_null,
+                          void* stream);
+
 /* ---- the whole path in one call -------------------------------------------------------------------------- */
 /* The `render:` block of the YAML plus the frustum and the MLP arithmetic (NeRF.__init__, src/NeRF.py:35-66). */
 typedef struct nerf_render_cfg {

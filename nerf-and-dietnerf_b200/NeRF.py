@@ -143,11 +143,13 @@ class NeRF:
         self._overlap_allreduce = False
         self._fine_allreduce = None
         self._fine_update = None        # set by train_step_local: the fine network's optimizer step, run early
+        self._peer_step = None          # set by train_step_local while a step exchanges its gradients over peer memory
         self._fine_updated = False
         self._side = None
         self.overlap_dw = True          # False: every kernel of the step runs on one stream (per-kernel timing)
         # data-parallel state (set by distribute())
         self.world_size, self.rank, self._process_group = 1, 0, None
+        self._peer = None               # parallel.PeerExchange once distribute() set one up
 
     # ---- construction helpers --------------------------------------------------------------------------------
     @staticmethod
@@ -211,12 +213,36 @@ class NeRF:
         self.optimizer = optimizer if optimizer is not None else Adam(**kwargs)
         return self
 
-    def distribute(self, process_group=None):
-        """Shard every train batch over the ranks of ``process_group`` (one process per GPU, NCCL)."""
+    def distribute(self, process_group=None, peer_exchange=None):
+        """Shard every train batch over the ranks of ``process_group`` (one process per GPU, NCCL).
+
+        ``peer_exchange`` (default: on when the GPUs of the box can map each other's memory; env NERF_PEER_EXCHANGE=0/1
+        overrides): the gradient exchange runs as our own one-shot reduce + Adam kernel over NVLink peer memory
+        (parallel.PeerExchange) instead of NCCL all-reduces followed by the Adam kernels."""
+        import os
         import torch.distributed as dist
         self._process_group = process_group
         self.world_size = dist.get_world_size(process_group)
         self.rank = dist.get_rank(process_group)
+        self._peer = None
+        env = os.environ.get("NERF_PEER_EXCHANGE")
+        want = (env != "0") if env is not None else (peer_exchange is not False)
+        if want and self.world_size > 1 and self.device.type == "cuda" and dist.get_backend(process_group) == "nccl":
+            from .parallel import PeerExchange
+            n = self.model_coarse.n_params + (self.model_fine.n_params if self.model_fine is not None else 0)
+            try:
+                self._peer = PeerExchange(4 + n, self.device, process_group)
+            except Exception as e:                          # no peer access / no symmetric memory: NCCL it is
+                if peer_exchange or env == "1":
+                    raise
+                if self.rank == 0:
+                    print(f"NeRF.distribute: peer exchange unavailable ({type(e).__name__}: {e}); using NCCL all-reduce")
+                self._peer = None
+            # the ranks must agree (a rank that failed alone would wait in a barrier nobody else enters)
+            ok = torch.tensor([1 if self._peer is not None else 0], device=self.device)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=process_group)
+            if int(ok.item()) == 0:
+                self._peer = None
         return self
 
     @property
@@ -473,6 +499,8 @@ class NeRF:
         """Flat gradient buffer [sq_err_coarse, sq_err_fine, 0, 0 | grads_coarse | grads_fine].  The two squared-error sums
         ride in FRONT of the coarse gradients so that the buffer splits into the two all-reduces of a step: the fine
         gradients (final before the coarse backward starts, overlapped with it) and [sums | coarse gradients]."""
+        if self._peer is not None:
+            return self._peer.grads        # symmetric memory: the peers read it in place
         if self._grads is None:
             n = self.model_coarse.n_params + (self.model_fine.n_params if self.model_fine is not None else 0)
             self._grads = torch.zeros(4 + n, dtype=torch.float32, device=self.device)
@@ -525,7 +553,7 @@ class NeRF:
                  ptr(sums[1:2]), ptr(w.d_raw_f), ptr(w.d_z_f) if through_z else None)
             side = self._mlp_bwd(mf, w.xyz_f, w.view_f, w.saved_f, w.d_raw_f, n * sf, g_f,
                                  w.d_xyz_f if through_z else None, w.ws_bwd, side_stream=self._side_stream())
-            if self.world_size > 1 and self._overlap_allreduce:
+            if self.world_size > 1 and self._overlap_allreduce and self._peer_step is None:
                 # the fine network's gradients are final: their all-reduce runs under the coarse backward
                 with torch.cuda.stream(side) if side is not None else contextlib.nullcontext():
                     self._fine_allreduce = allreduce_sum_(g_f, self._process_group, async_op=True)
@@ -705,20 +733,46 @@ class NeRF:
         t_next = self.optimizer.iterations + 1
         early = mf is not None and hasattr(self.optimizer, "apply_one") and getattr(self, "_extra_grads", None) is None
 
+        peer = self._peer if (self.world_size > 1 and hasattr(self.optimizer, "apply_one")
+                              and getattr(self, "_extra_grads", None) is None) else None
+        if peer is not None:
+            self.optimizer._state(n_all, self.device)
+
         def fine_update(g_f):
-            self.optimizer.apply_one(mf.params, g_f, mc.n_params, n_all, t_next)
+            if peer is not None:
+                # one-shot exchange over NVLink fused with Adam, on the side stream under the coarse backward
+                peer.barrier(t_next, 0)
+                peer.reduce_adam(mf.params, 4 + mc.n_params, mf.n_params, self.optimizer, mc.n_params, t_next)
+            else:
+                self.optimizer.apply_one(mf.params, g_f, mc.n_params, n_all, t_next)
             mf.mark_updated()
             mf.packed_for(mf.params)
 
         self._overlap_allreduce = True
         self._fine_update, self._fine_updated = (fine_update if early else None), False
+        self._peer_step = peer
         try:
             self.forward_backward(rays_orig, rays_dirs, real_rgb, n_total_rays=n_total_rays, ray_offset=ray_offset,
                                   keep_grads=getattr(self, "_keep_grads", False))
         finally:
             self._overlap_allreduce = False
             self._fine_update = None
+            self._peer_step = None
         g = self._grad_buffer()
+        if peer is not None:
+            # the tail of the step: barrier, then [loss sums] and [coarse gradients -> Adam] straight from the peers' buffers
+            peer.barrier(t_next, 1)
+            peer.reduce_adam(None, 0, 4, self.optimizer, 0, t_next, reduced=peer.sums)
+            self.optimizer.iterations += 1
+            peer.reduce_adam(mc.params, 4, mc.n_params, self.optimizer, 0, self.optimizer.iterations)
+            if mf is not None and not self._fine_updated:
+                peer.reduce_adam(mf.params, 4 + mc.n_params, mf.n_params, self.optimizer, mc.n_params, self.optimizer.iterations)
+                mf.mark_updated()
+            self._fine_updated = False
+            mc.mark_updated()
+            peer.flip()
+            self.step_counter += 1
+            return self._metrics(peer.sums[0:2], n_total_rays)
         if self.world_size > 1:
             if self._fine_allreduce is not None or self._fine_updated:
                 allreduce_sum_(g[:4 + mc.n_params], self._process_group)   # [sums | coarse gradients]

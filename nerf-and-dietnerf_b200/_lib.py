@@ -96,6 +96,9 @@ SIGNATURES = {
     "nerf_mse_fwd_bwd": (c_int32, [_P, _P, c_int64, c_int64, c_float, _P, _P, _P]),
     "nerf_train_metrics": (c_int32, [_P, c_int64, c_float, c_int32, _P, _P]),
     "nerf_adam_step": (c_int32, [_P, _P, _P, _P, c_int64, c_float, c_float, c_float, c_float, c_int64, _P]),
+    "nerf_peer_barrier": (c_int32, [_P, c_int32, c_int32, c_uint32, c_int32, _P]),
+    "nerf_peer_reduce_adam": (c_int32, [_P, _P, c_int32, c_int64, c_int64, _P, _P, c_float, c_float, c_float, c_float, c_int64,
+                                        _P, _P]),
     "nerf_render_workspace_bytes": (c_int64, [_CFG, POINTER(RenderCfg), c_int64]),
     "nerf_render_fused_fwd": (c_int32, [_CFG, POINTER(RenderCfg), _P, _P, _P, _P, _P, _P, c_int64, POINTER(RngState),
                                         POINTER(RenderOuts), _P, _P]),

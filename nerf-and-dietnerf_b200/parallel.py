@@ -43,3 +43,54 @@ def all_gather_rows(local: torch.Tensor, n_total: int, group=None) -> torch.Tens
         lo, hi = shard_bounds(n_total, world, r)
         out.append(part[:hi - lo])
     return torch.cat(out)
+
+
+class PeerExchange:
+    """Gradient exchange over NVLink peer memory (``nerf_peer_barrier`` + ``nerf_peer_reduce_adam``): the flat gradient
+    buffer lives in symmetric memory (torch.distributed._symmetric_memory: one allocation per GPU, mapped into every peer),
+    every rank reads every peer's slice directly and applies Adam in the same kernel.  Two buffers alternate from step to
+    step, so a buffer is rewritten two barriers after its last remote read.  Raises when the box has no peer access or the
+    torch build has no symmetric memory: the caller then keeps the NCCL all-reduce."""
+
+    def __init__(self, n_floats: int, device, group=None):
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm_mem
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        group = dist.group.WORLD if group is None else group
+        try:
+            symm_mem.enable_symm_mem_for_group(group.group_name)
+        except Exception:
+            pass                                            # newer torch enables it at rendezvous
+        self.bufs, self.handles = [], []
+        for _ in range(2):
+            t = symm_mem.empty(n_floats, dtype=torch.float32, device=device)
+            t.zero_()
+            self.bufs.append(t)
+            self.handles.append(symm_mem.rendezvous(t, group))
+        self.pad = symm_mem.empty(256, dtype=torch.int32, device=device)
+        self.pad.zero_()
+        torch.cuda.synchronize(device)
+        self.pad_handle = symm_mem.rendezvous(self.pad, group)
+        dist.barrier(group)                                 # every pad is zero before anybody signals
+        self.parity = 0
+        self.sums = torch.zeros(4, dtype=torch.float32, device=device)
+
+    @property
+    def grads(self):
+        return self.bufs[self.parity]
+
+    def flip(self):
+        self.parity ^= 1
+
+    def barrier(self, epoch: int, slot: int):
+        from ._lib import call
+        call("nerf_peer_barrier", int(self.pad_handle.buffer_ptrs_dev), self.rank, self.world, int(epoch) & 0xFFFFFFFF, int(slot))
+
+    def reduce_adam(self, params, offset, n, opt, state_offset, t, reduced=None):
+        """Sum floats [offset, offset+n) of the current gradient buffer over the ranks and (``params`` given) apply step
+        ``t`` of ``opt`` (Adam) to ``params`` with the moments at ``state_offset``."""
+        from ._lib import call, ptr
+        m = opt._m[state_offset:state_offset + n] if params is not None else None
+        v = opt._v[state_offset:state_offset + n] if params is not None else None
+        call("nerf_peer_reduce_adam", ptr(params), int(self.handles[self.parity].buffer_ptrs_dev), self.world, int(offset), int(n),
+             ptr(m), ptr(v), opt.learning_rate, opt.beta_1, opt.beta_2, opt.epsilon, int(t), ptr(reduced))
