@@ -364,7 +364,8 @@ def main():
 
     @contextlib.contextmanager
     def hook(name):
-        if name in ("nerf_mlp_fwd", "nerf_mlp_fwd_rays", "nerf_mlp_bwd", "nerf_mlp_bwd_dx", "nerf_mlp_bwd_dw",
+        if name in ("nerf_mlp_fwd", "nerf_mlp_fwd_rays", "nerf_mlp_fwd_rays_stratified", "nerf_mlp_bwd", "nerf_mlp_bwd_dx",
+                    "nerf_mlp_bwd_dw",
                     "nerf_composite_fwd", "nerf_composite_bwd", "nerf_composite_mse_fwd", "nerf_composite_mse_fwd_bwd",
                     "nerf_sample_pdf_fwd", "nerf_sample_pdf_bwd"):
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -384,6 +385,10 @@ def main():
     type(model).split_bwd_calls = False
     pkg._lib.event_hook = None
     torch.cuda.synchronize()
+    # the coarse forward (stratified sampling fused in) and the fine forward are the same kernel: one average over both
+    fwd_events = per_call.pop("nerf_mlp_fwd_rays_stratified", []) + per_call.pop("nerf_mlp_fwd_rays", [])
+    if fwd_events:
+        per_call["nerf_mlp_fwd_rays"] = fwd_events
     call_ms = {k: sum(a.elapsed_time(b) for a, b in v) / len(v) for k, v in per_call.items()}
     call_n = {k: len(v) // args.steps for k, v in per_call.items()}
 

@@ -41,7 +41,7 @@ __device__ __forceinline__ void split_bias<__half>(float b, __half* hi, __half* 
 }
 
 __device__ __forceinline__ float layer_bias(const NetGeom& g, const float* P, int layer, int n) {
-  if (layer < 8) return P[g.layers[layer].b_off + n];
+  if (layer < 8 || !g.view) return n < g.layers[layer].out ? P[g.layers[layer].b_off + n] : 0.f;   // xyz-only: Dense l = layer l
   if (n < 128) return P[g.layers[8].b_off + n];
   if (n == 128) return P[g.layers[10].b_off];       // sigma head shares the [h8 ; view] input
   return 0.f;
@@ -77,8 +77,8 @@ __global__ void pack_weights_kernel(const __grid_constant__ TcPlan plan, NetGeom
     const int n = e >> 6, k = e & 63;
     // source Dense layer and output column
     int dense = layer, col = n;
-    bool valid = true;
-    if (layer == 8) {
+    bool valid = n < g.layers[layer].out || (g.view && layer == 8);
+    if (g.view && layer == 8) {
       if (n < 128) { dense = 8; col = n; }
       else if (n == 128) { dense = 10; col = 0; }   // sigma head shares the [h8 ; view] input
       else valid = false;
@@ -90,7 +90,7 @@ __global__ void pack_weights_kernel(const __grid_constant__ TcPlan plan, NetGeom
       row = (layer == 4) ? g.dx + feat : feat;         // layer 4 kernel rows: [xyz (dx) ; h4 (256)]
     } else {
       if (layer == 0 || layer == 4) { if (k < g.dx) row = k; }                       // xyz columns
-      else if (layer == 8) { if (k >= kInpViewCol && k < kInpViewCol + g.dv) row = g.hidden + (k - kInpViewCol); }
+      else if (layer == 8 && g.view) { if (k >= kInpViewCol && k < kInpViewCol + g.dv) row = g.hidden + (k - kInpViewCol); }
     }
     T16 v = to16<T16>(0.f);
     if (valid && row >= 0) {
@@ -104,13 +104,15 @@ __global__ void pack_weights_kernel(const __grid_constant__ TcPlan plan, NetGeom
     }
     *reinterpret_cast<T16*>(packed + plan.chunk_off[chunk] + panel_offset(n, k)) = v;
   } else {
-    // fp32 tail: rgb head
+    // tail: fp32 rgb head; xyz-only network: the sigma head (Dense 11, input h8) in the operand format, fp32 bias
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
-    const LayerDesc& L = g.layers[9];
+    const LayerDesc& L = g.layers[g.view ? 9 : 10];
     if (e < 128)
       reinterpret_cast<float4*>(packed + plan.w_rgb_off)[e] =
           make_float4(P[L.w_off + e * 3 + 0], P[L.w_off + e * 3 + 1], P[L.w_off + e * 3 + 2], 0.f);
     if (e == 128) reinterpret_cast<float4*>(packed + plan.w_rgb_off)[128] = make_float4(P[L.b_off], P[L.b_off + 1], P[L.b_off + 2], 0.f);
+    if (e < 256) reinterpret_cast<T16*>(packed + plan.w_sig_off)[e] = to16<T16>(g.view ? 0.f : P[g.layers[11].w_off + e]);
+    if (e == 256) *reinterpret_cast<float*>(packed + plan.w_sig_off + 512) = g.view ? 0.f : P[g.layers[11].b_off];
   }
 }
 
@@ -186,8 +188,17 @@ __device__ __forceinline__ uint32_t neg_mask32(const uint32_t (&u)[8]) {
 // Epilogue of one 32-column group: acc (bias already inside, it rode in the MMA) -> LeakyReLU -> 16-bit -> swizzled
 // panel row.  kMask: returns the negative-sign mask of the 32 values.
 // pbx = (panel row address) | ((row & 7) << 4): a 16-byte chunk address is one XOR with an immediate.
-template <bool kMask, bool kHalf>
-__device__ __forceinline__ uint32_t epi_group32(const uint32_t (&acc)[32], float alpha, uint32_t pbx, int chunk_base) {
+template <bool kHalf>
+__device__ __forceinline__ float2 unpack_16x2(uint32_t v) {
+  if (kHalf) return __half22float2(*reinterpret_cast<const __half2*>(&v));
+  return __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&v));
+}
+
+// kSig (xyz-only network, layer 7): also accumulates this thread's part of the sigma head, the dot product of the 16-bit
+// activations just formed with the 16-bit sigma kernel (wsig_u32 = shared-memory address of this group's 32 weights).
+template <bool kMask, bool kHalf, bool kSig = false>
+__device__ __forceinline__ uint32_t epi_group32(const uint32_t (&acc)[32], float alpha, uint32_t pbx, int chunk_base,
+                                                uint32_t wsig_u32 = 0u, float* sig = nullptr) {
   uint32_t u[8];
   const uint64_t alpha2 = pack_f32x2(alpha, alpha);
 #pragma unroll
@@ -201,6 +212,10 @@ __device__ __forceinline__ uint32_t epi_group32(const uint32_t (&acc)[32], float
       unpack_f32x2(x, x0, x1);
       unpack_f32x2(lo, l0, l1);
       pk[i] = pack_16x2<kHalf>(fmaxf(x0, l0), fmaxf(x1, l1)); // LeakyReLU for 0 <= alpha <= 1
+      if (kSig) {
+        const float2 a = unpack_16x2<kHalf>(pk[i]), w = unpack_16x2<kHalf>(lds32u(wsig_u32 + (uint32_t)(8 * j + 2 * i) * 2u));
+        *sig = fmaf(a.x, w.x, fmaf(a.y, w.y, *sig));
+      }
     }
     if (kMask) { u[2 * j] = hi_bytes(pk[0], pk[1]); u[2 * j + 1] = hi_bytes(pk[2], pk[3]); }
     sts128(pbx ^ (uint32_t)((chunk_base + j) << 4), make_uint4(pk[0], pk[1], pk[2], pk[3]));
@@ -234,7 +249,9 @@ __device__ __forceinline__ uint4 half8_to_bf16(uint4 v) {
   return make_uint4(half2_to_bf16x2(v.x), half2_to_bf16x2(v.y), half2_to_bf16x2(v.z), half2_to_bf16x2(v.w));
 }
 
-template <bool kSave, bool kHalf>
+// kXyz: the xyz-only network (src/NeRF.py:248-288): ten layers, no view columns, sigma head = a dot product with h8 in the
+// epilogue of layer 7 (partial sums ride in a register to the last layer).
+template <bool kSave, bool kHalf, bool kXyz>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreadsFwd, 1)
 mlp_tc_fwd_kernel(const __grid_constant__ TcPlan plan, const uint8_t* __restrict__ packed,
                   const __grid_constant__ FwdInput in, int64_t M, float* __restrict__ out4, uint8_t* __restrict__ saved,
@@ -267,6 +284,9 @@ mlp_tc_fwd_kernel(const __grid_constant__ TcPlan plan, const uint8_t* __restrict
   // L1 is ~3 KB next to 225 KB of shared memory: the fp32 rgb head lives in shared memory
   for (int i = threadIdx.x; i < 129; i += blockDim.x)
     reinterpret_cast<float4*>(smem + kSmemWrgb)[i] = __ldg(reinterpret_cast<const float4*>(packed + plan.w_rgb_off) + i);
+  if (kXyz)
+    for (int i = threadIdx.x; i < (256 * 2 + 16) / 4; i += blockDim.x)
+      reinterpret_cast<uint32_t*>(smem + kSmemWsig)[i] = __ldg(reinterpret_cast<const uint32_t*>(packed + plan.w_sig_off) + i);
   tc_fence_before();
   __syncthreads();
   cluster_sync_all();
@@ -301,9 +321,9 @@ mlp_tc_fwd_kernel(const __grid_constant__ TcPlan plan, const uint8_t* __restrict
         // layer's chunks are streamed once per super-tile (they come from L2)
         const uint8_t* layer_base = packed;
 #pragma unroll 1
-        for (int l = 0; l < 9; ++l) {
-          const uint32_t chunk_bytes = (l == 8 ? 144u : 256u) * 128u;
-          const bool slab = !(l == 0 || l == 4 || l == 8);
+        for (int l = 0; l < tc_n_layers(kXyz); ++l) {
+          const uint32_t chunk_bytes = tc_layer_rows(kXyz, l) * 128u;
+          const bool slab = tc_layer_slab(kXyz, l);
 #pragma unroll
           for (int t = 0; t < 2; ++t) {
             const uint8_t* p = layer_base;
@@ -311,7 +331,8 @@ mlp_tc_fwd_kernel(const __grid_constant__ TcPlan plan, const uint8_t* __restrict
 #pragma unroll
               for (int ci = 0; ci < 4; ++ci, p += chunk_bytes) load(p, chunk_bytes >> 1);
             }
-            load(p, slab ? (uint32_t)(kBiasSlabBytes >> 1) : (chunk_bytes >> 1));
+            // bias slab [256][16]: 32 bytes per output row, this CTA's N/2 rows (N = 128 in the xyz-only network's last layer)
+            load(p, slab ? (chunk_bytes >> 3) : (chunk_bytes >> 1));
           }
           layer_base += (l == 0 ? chunk_bytes : 4u * chunk_bytes + (slab ? (uint32_t)kBiasSlabBytes : chunk_bytes));
         }
@@ -339,7 +360,8 @@ mlp_tc_fwd_kernel(const __grid_constant__ TcPlan plan, const uint8_t* __restrict
       long long t_begin = clock64(), t_act = 0, t_full = 0, t_issue = 0;
       int n_tr = 0;
       const uint32_t fmt = kHalf ? 0 : 1;
-      const uint32_t idesc256 = make_idesc(256, 0, 0, fmt, 256), idesc144 = make_idesc(144, 0, 0, fmt, 256);
+      const uint32_t idesc256 = make_idesc(256, 0, 0, fmt, 256);
+      const uint32_t idesc_last = make_idesc((int)tc_layer_rows(kXyz, tc_n_layers(kXyz) - 1), 0, 0, fmt, 256);
       const uint64_t b_sw = make_desc_kmajor(sbase + kSmemStage), b_slab = make_desc_k_nosw(sbase + kSmemStage, 128, 256);
       const uint32_t full0 = smem_u32(&bars->full[0]), empty0 = smem_u32(&bars->empty[0]);
       const bool no_mma = (dbg & kDbgNoMma) != 0;
@@ -368,7 +390,7 @@ mlp_tc_fwd_kernel(const __grid_constant__ TcPlan plan, const uint8_t* __restrict
       };
       for (int64_t quad = quad0; quad < n_quads; quad += quad_step) {
 #pragma unroll 1
-        for (int l = 0; l < 9; ++l) {
+        for (int l = 0; l < tc_n_layers(kXyz); ++l) {
 #pragma unroll
           for (int t = 0; t < 2; ++t) {
             long long tw = timing ? clock64() : 0;
@@ -381,12 +403,12 @@ mlp_tc_fwd_kernel(const __grid_constant__ TcPlan plan, const uint8_t* __restrict
             if (l == 0) {
               chunk(d_tmem, a_inp, false, idesc256, 0u);
             } else {
-              const uint32_t idesc = l == 8 ? idesc144 : idesc256;
+              const uint32_t idesc = l == tc_n_layers(kXyz) - 1 ? idesc_last : idesc256;
               chunk(d_tmem, a_act, false, idesc, 0u);
               chunk(d_tmem, a_act + 1 * (kPanelBytes >> 4), false, idesc, 1u);
               chunk(d_tmem, a_act + 2 * (kPanelBytes >> 4), false, idesc, 1u);
               chunk(d_tmem, a_act + 3 * (kPanelBytes >> 4), false, idesc, 1u);
-              chunk(d_tmem, a_inp, !(l == 4 || l == 8), idesc, 1u);   // input-panel chunk (layers 4, 8) or bias slab
+              chunk(d_tmem, a_inp, tc_layer_slab(kXyz, l), idesc, 1u);   // input-panel chunk (skip / view layer) or bias slab
             }
             umma_commit_pair(smem_u32(&bars->acc_full[t]));
             trace(timing, 2, n_tr, l * 4 + t * 2 + 1);
@@ -414,7 +436,7 @@ mlp_tc_fwd_kernel(const __grid_constant__ TcPlan plan, const uint8_t* __restrict
       const bool do_store = !(dbg & kDbgNoStore);
       uint32_t ph = 0;
       for (int64_t quad = quad0; quad < n_quads; quad += quad_step) {
-        for (int l = 0; l < 8; ++l, ph ^= 1u) {
+        for (int l = 0; l < tc_n_layers(kXyz) - 1; ++l, ph ^= 1u) {
 #pragma unroll
           for (int t = 0; t < 2; ++t) {
             const uint32_t act_u32 = sbase + kSmemAct + t * kActPanels * kPanelBytes;
@@ -577,7 +599,8 @@ mlp_tc_fwd_kernel(const __grid_constant__ TcPlan plan, const uint8_t* __restrict
         }
       }
 
-      for (int l = 0; l < plan.n_layers; ++l) {
+      float sig_part = 0.f;                              // xyz-only: this thread's half of the sigma head's dot product
+      for (int l = 0; l < tc_n_layers(kXyz); ++l) {
         tw = timing ? clock64() : 0;
         mbar_wait(smem_u32(&bars->acc_full[t]), acc_cnt & 1u);
         ++acc_cnt;
@@ -590,7 +613,7 @@ mlp_tc_fwd_kernel(const __grid_constant__ TcPlan plan, const uint8_t* __restrict
           copy_ph ^= 1u;
           copy_pending = false;
         }
-        if (l < 8) {
+        if (l < tc_n_layers(kXyz) - 1) {
           // TMEM loads are double-buffered: group cc+1 is in flight while group cc is processed
           uint32_t acc[kTmemBuffers][32];
           uint32_t mw[4] = {0u, 0u, 0u, 0u};
@@ -603,7 +626,11 @@ mlp_tc_fwd_kernel(const __grid_constant__ TcPlan plan, const uint8_t* __restrict
             tmem_ld_wait();
             if (kTmemBuffers == 2 && cc + 1 < 4) tmem_ld32(taddr + c0 + 32, acc[(cc + 1) & 1]);
             const uint32_t pbx = (act_u32 + (c0 >> 6) * kPanelBytes + r * 128) | ((uint32_t)(r & 7) << 4);
-            mw[cc] = epi_group32<kSave, kHalf>(acc[cc & (kTmemBuffers - 1)], alpha, pbx, (c0 & 63) >> 3);
+            if (kXyz && l == 7)
+              mw[cc] = epi_group32<kSave, kHalf, true>(acc[cc & (kTmemBuffers - 1)], alpha, pbx, (c0 & 63) >> 3,
+                                                       sbase + kSmemWsig + (uint32_t)c0 * 2u, &sig_part);
+            else
+              mw[cc] = epi_group32<kSave, kHalf>(acc[cc & (kTmemBuffers - 1)], alpha, pbx, (c0 & 63) >> 3);
           }
           tc_fence_before();
           fence_proxy_async();
@@ -650,21 +677,25 @@ mlp_tc_fwd_kernel(const __grid_constant__ TcPlan plan, const uint8_t* __restrict
               if (kSave) { u[2 * j] = hi_bytes(pk[0], pk[1]); u[2 * j + 1] = hi_bytes(pk[2], pk[3]); }
               if (kSave && grow) stg128(grow + ((c0 >> 3) + j) * 1024, make_uint4(pk[0], pk[1], pk[2], pk[3]));
             }
-            if (do_store) saved_mask[(8 * 8 + (c0 >> 5)) * 128 + r] = neg_mask32(u);
+            if (do_store) saved_mask[(kMaskRowHL * 8 + (c0 >> 5)) * 128 + r] = neg_mask32(u);
           }
           const uint32_t xch = act_u32 + r * 16;                  // activation panels are dead after this layer's MMAs
           if (half == 1) {
-            uint32_t sg[16];
-            tmem_ld16(taddr + 128, sg);
-            tmem_ld_wait();
-            const float sigma = __uint_as_float(sg[0]);
+            float sigma = sig_part;                          // xyz-only: this half of the dot product with h8
+            if (!kXyz) {
+              uint32_t sg[16];
+              tmem_ld16(taddr + 128, sg);
+              tmem_ld_wait();
+              sigma = __uint_as_float(sg[0]);
+            }
             sts128(xch, make_uint4(__float_as_uint(rr), __float_as_uint(gg), __float_as_uint(bb), __float_as_uint(sigma)));
           }
           tc_fence_before();
           named_bar_sync(bar_id, kEpiThreadsPerTile);
           if (half == 0 && row_ok) {
             const float4 o = lds128f(xch), br = lds128f(wrgb_u32 + 128 * 16);
-            reinterpret_cast<float4*>(out4)[row] = make_float4(rr + o.x + br.x, gg + o.y + br.y, bb + o.z + br.z, o.w);
+            const float sigma = kXyz ? o.w + sig_part + lds32f(sbase + kSmemWsig + 512) : o.w;
+            reinterpret_cast<float4*>(out4)[row] = make_float4(rr + o.x + br.x, gg + o.y + br.y, bb + o.z + br.z, sigma);
           }
           // the next quad's first epilogue overwrites the exchange rows, its prologue the input panel (whose saved copy,
           // a bulk S2G issued after this pair's prologue, must have been read out by now)
@@ -720,34 +751,42 @@ static int launch_fwd(const nerf_net_cfg* cfg, const NetGeom& g, const void* pac
                       float* out4, void* saved, cudaStream_t st, bool half = false) {
   TcPlan plan;
   if (!make_plan(g, &plan) || cfg->leaky_alpha < 0.f || cfg->leaky_alpha > 1.f) {
-    set_error("NERF_MODE_BF16 supports hidden=256, last_hidden=128, n_angles in {1,2}, xyz width <= 40, view width <= 24, "
+    set_error("the tensor-core modes support hidden=256, last_hidden=128, xyz width <= 38, view width <= 24, "
               "0 <= leaky_relu_alpha <= 1");
     return NERF_E_UNSUPPORTED;
   }
   if (device_first_use(0)) {               // per device: the attribute lives in the device's copy of the function
-    NERF_CUDA(cudaFuncSetAttribute(mlp_tc_fwd_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemAlloc));
-    NERF_CUDA(cudaFuncSetAttribute(mlp_tc_fwd_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemAlloc));
-    NERF_CUDA(cudaFuncSetAttribute(mlp_tc_fwd_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemAlloc));
-    NERF_CUDA(cudaFuncSetAttribute(mlp_tc_fwd_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemAlloc));
+    NERF_CUDA(cudaFuncSetAttribute(mlp_tc_fwd_kernel<false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemAlloc));
+    NERF_CUDA(cudaFuncSetAttribute(mlp_tc_fwd_kernel<true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemAlloc));
+    NERF_CUDA(cudaFuncSetAttribute(mlp_tc_fwd_kernel<false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemAlloc));
+    NERF_CUDA(cudaFuncSetAttribute(mlp_tc_fwd_kernel<true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemAlloc));
+    NERF_CUDA(cudaFuncSetAttribute(mlp_tc_fwd_kernel<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemAlloc));
+    NERF_CUDA(cudaFuncSetAttribute(mlp_tc_fwd_kernel<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemAlloc));
+    NERF_CUDA(cudaFuncSetAttribute(mlp_tc_fwd_kernel<false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemAlloc));
+    NERF_CUDA(cudaFuncSetAttribute(mlp_tc_fwd_kernel<true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemAlloc));
   }
   int64_t n_quads = ((m + kTileM - 1) / kTileM + 3) / 4;
   const int n_pairs = num_sms() / 2;
   int grid = 2 * (int)(n_quads < n_pairs ? n_quads : n_pairs);             // CTA pairs
-  if (half && saved) {
-    // fp16 operands in training too; what is SAVED for the backward is converted to bf16 on its way out (store warps,
-    // last-layer epilogue, input panel), because the backward's MMAs pair it with bf16 gradients
-    mlp_tc_fwd_kernel<true, true><<<grid, kThreadsFwd, kSmemAlloc, st>>>(
-        plan, (const uint8_t*)packed + half_region_offset(plan), in, m, out4, (uint8_t*)saved, cfg->leaky_alpha, tc_debug_flags());
-  } else if (half) {
-    mlp_tc_fwd_kernel<false, true><<<grid, kThreadsFwd, kSmemAlloc, st>>>(
-        plan, (const uint8_t*)packed + half_region_offset(plan), in, m, out4, nullptr, cfg->leaky_alpha, tc_debug_flags());
-  } else if (saved) {
-    mlp_tc_fwd_kernel<true, false><<<grid, kThreadsFwd, kSmemAlloc, st>>>(plan, (const uint8_t*)packed, in, m, out4,
-                                                                         (uint8_t*)saved, cfg->leaky_alpha, tc_debug_flags());
-  } else {
-    mlp_tc_fwd_kernel<false, false><<<grid, kThreadsFwd, kSmemAlloc, st>>>(plan, (const uint8_t*)packed, in, m, out4, nullptr,
-                                                                          cfg->leaky_alpha, tc_debug_flags());
+  // fp16 operands in training too; what is SAVED for the backward is converted to bf16 on its way out (store warps,
+  // last-layer epilogue, input panel), because the backward's MMAs pair it with bf16 gradients
+  const uint8_t* pk = (const uint8_t*)packed + (half ? half_region_offset(plan) : 0u);
+  const uint32_t dbg = tc_debug_flags();
+#define NERF_LAUNCH_FWD(SAVE, HALF, XYZ)                                                                                  \
+  mlp_tc_fwd_kernel<SAVE, HALF, XYZ><<<grid, kThreadsFwd, kSmemAlloc, st>>>(plan, pk, in, m, out4, (uint8_t*)saved,       \
+                                                                            cfg->leaky_alpha, dbg)
+  const int variant = (saved ? 1 : 0) | (half ? 2 : 0) | (plan.xyz_only ? 4 : 0);
+  switch (variant) {
+    case 0: NERF_LAUNCH_FWD(false, false, false); break;
+    case 1: NERF_LAUNCH_FWD(true, false, false); break;
+    case 2: NERF_LAUNCH_FWD(false, true, false); break;
+    case 3: NERF_LAUNCH_FWD(true, true, false); break;
+    case 4: NERF_LAUNCH_FWD(false, false, true); break;
+    case 5: NERF_LAUNCH_FWD(true, false, true); break;
+    case 6: NERF_LAUNCH_FWD(false, true, true); break;
+    default: NERF_LAUNCH_FWD(true, true, true); break;
   }
+#undef NERF_LAUNCH_FWD
   NERF_CHECK_LAUNCH();
   return NERF_OK;
 }
@@ -757,7 +796,7 @@ int mlp_tc_fwd(const nerf_net_cfg* cfg, const NetGeom& g, const float* params, c
   (void)params; (void)workspace;
   FwdInput in = {};
   in.xyz_enc = xyz_enc; in.view_enc = view_enc; in.dx = g.dx; in.dv = g.dv;
-  in.Lx = cfg->n_pos_enc_xyz; in.Lv = cfg->n_pos_enc_view; in.ncomp = cfg->n_angles + 1; in.n_samples = 1;
+  in.Lx = cfg->n_pos_enc_xyz; in.Lv = cfg->n_pos_enc_view; in.ncomp = g.view ? cfg->n_angles + 1 : 0; in.n_samples = 1;
   return launch_fwd(cfg, g, packed, in, m, out4, saved, st, half);
 }
 
@@ -772,7 +811,7 @@ int mlp_tc_fwd_rays(const nerf_net_cfg* cfg, const NetGeom& g, const void* packe
     in.span = (float)((double)gen->z_end - (double)gen->z_start);
     in.seed = gen->seed; in.step = gen->step; in.ray_offset = gen->ray_offset; in.z_out = gen->z_out;
   }
-  in.dx = g.dx; in.dv = g.dv; in.Lx = cfg->n_pos_enc_xyz; in.Lv = cfg->n_pos_enc_view; in.ncomp = cfg->n_angles + 1;
+  in.dx = g.dx; in.dv = g.dv; in.Lx = cfg->n_pos_enc_xyz; in.Lv = cfg->n_pos_enc_view; in.ncomp = g.view ? cfg->n_angles + 1 : 0;
   return launch_fwd(cfg, g, packed, in, n_rays * n_samples, out4, saved, st, half);
 }
 

@@ -23,7 +23,7 @@ constexpr int kInpOneCol = 38;                    // input-panel columns 38, 39 
                                                   // meet carry bf16(b) and bf16(b - bf16(b)), so the bias rides in the MMA
 constexpr int kBiasSlabBytes = 256 * 32;          // [256][16] bf16, un-swizzled K-major: the K = 16 slice (input-panel
                                                   // columns 32..47) that adds the bias of a layer without input-panel chunk
-constexpr int kMaxChunks = 48;
+constexpr int kMaxChunks = 56;
 // -DNERF_TC_TRACE=1 compiles the in-kernel handshake timing / event trace in (NERF_TC_DEBUG=256 then prints it); off by
 // default because its 64-bit counters cost registers in kernels that run at the 96-register limit
 #ifndef NERF_TC_TRACE
@@ -41,29 +41,34 @@ constexpr int kWarpStore = 18;                    // warps 18, 19: train-mode co
 constexpr int kThreadsFwd = 20 * 32;              // 5 warps per SM sub-partition: the register cap stays at 96
 // Saved activations of one 128-row tile (forward -> backward), bf16:
 //   block 0            input panel (xyz | view encodings), [128 rows][64 cols] in the 128-byte-swizzled smem layout (16 KB)
-//   blocks h_1 .. h_8  64 KB each, "row-block chunk-major" (RBCM): [row half 0/1][16-byte column chunk j][row 0..63][8 cols].
+//   blocks h_1 .. h_9  64 KB each, "row-block chunk-major" (RBCM): [row half 0/1][16-byte column chunk j][row 0..63][8 cols].
+//                      (nine slots: the xyz-only network of src/NeRF.py:248-288 has nine 256-wide hidden layers; the
+//                      view-direction network leaves slot 9 unwritten -- address space, not traffic)
 //                      An epilogue warp (32 consecutive rows, one chunk) stores 512 contiguous bytes straight from its
 //                      registers, and a 64-row K-slab of the block is ONE contiguous 32 KB bulk copy that lands in shared
 //                      memory as the canonical un-swizzled MN-major UMMA operand of the dW kernel (core matrix = 8 rows x
 //                      16 B, SBO = 1024 B between column chunks, LBO = 128 B between 8-row groups)
 //   block h_L          last hidden (128 cols), RBCM with 16 chunks (32 KB)
-//   then uint32 sign masks [9 layers][8 words][128 rows]: bit i of word w = (activation[32 w + i] > 0)
-constexpr int kSavedPanels = 1 + 8 * kActPanels + 2;
-constexpr int kSavedMaskBytes = 9 * 8 * 128 * 4;
+//   then uint32 sign masks [10 rows][8 words][128 rows]: bit i of word w = (activation[32 w + i] > 0); row l - 1 = h_l,
+//   row kMaskRowHL = the last hidden layer
+constexpr int kHiddenSlots = 9;
+constexpr int kSavedPanels = 1 + kHiddenSlots * kActPanels + 2;
+constexpr int kMaskRowHL = kHiddenSlots;
+constexpr int kSavedMaskBytes = (kHiddenSlots + 1) * 8 * 128 * 4;
 constexpr int kSavedTileBytes = kSavedPanels * kPanelBytes + kSavedMaskBytes;
-__host__ __device__ constexpr int saved_panel_h(int l) { return 1 + (l - 1) * kActPanels; }  // l = 1..8
-constexpr int kSavedPanelHL = 1 + 8 * kActPanels;
+__host__ __device__ constexpr int saved_panel_h(int l) { return 1 + (l - 1) * kActPanels; }  // l = 1..9
+constexpr int kSavedPanelHL = 1 + kHiddenSlots * kActPanels;
 // byte offset of (row r, 16-byte chunk j) inside an RBCM block with n_chunks column chunks
 __host__ __device__ constexpr uint32_t rbcm_offset(int r, int j, int n_chunks) {
   return (uint32_t)(r >> 6) * (uint32_t)(n_chunks * 1024) + (uint32_t)j * 1024u + (uint32_t)(r & 63) * 16u;
 }
-// Backward workspace of one tile (chain kernel -> dW kernel), RBCM blocks: dZ_1..dZ_8 (32 chunks each), dZ_L' (24
+// Backward workspace of one tile (chain kernel -> dW kernel), RBCM blocks: dZ_1..dZ_9 (32 chunks each), dZ_L' (24
 // chunks: 0..15 = dZ_L, chunk 16 = [d sigma, 0 ...], 17 zero, 18..23 unused), dOut (8 chunks: chunk 0 = d_out4, 1 zero)
-constexpr int kDzPanels = 8 * kActPanels + 3 + 1;
+constexpr int kDzPanels = kHiddenSlots * kActPanels + 3 + 1;
 constexpr int kDzTileBytes = kDzPanels * kPanelBytes;
-__host__ __device__ constexpr int dz_panel(int l) { return (l - 1) * kActPanels; }            // l = 1..8
-constexpr int kDzPanelL = 8 * kActPanels;
-constexpr int kDzPanelOut = 8 * kActPanels + 3;
+__host__ __device__ constexpr int dz_panel(int l) { return (l - 1) * kActPanels; }            // l = 1..9
+constexpr int kDzPanelL = kHiddenSlots * kActPanels;
+constexpr int kDzPanelOut = kHiddenSlots * kActPanels + 3;
 constexpr int kDzChunksL = 24, kDzChunksOut = 8;
 
 // shared memory map (offsets from a 1024-aligned base)
@@ -72,7 +77,8 @@ constexpr int kSmemInp = kSmemAct + 2 * kActPanels * kPanelBytes;    // [2 tiles
 constexpr int kSmemStage = kSmemInp + 2 * kPanelBytes;               // [kStages]
 constexpr int kSmemBar = kSmemStage + kStages * kStageBytes;
 constexpr int kSmemWrgb = kSmemBar + 192;                            // float4 [128] rgb-head kernel rows + float4 rgb bias
-constexpr int kSmemTotal = kSmemWrgb + 129 * 16;
+constexpr int kSmemWsig = kSmemWrgb + 129 * 16;                      // xyz-only network: 16-bit sigma-head kernel [256], fp32 bias
+constexpr int kSmemTotal = kSmemWsig + 256 * 2 + 16;
 // no alignment slack: the kernels check that the dynamic shared memory window is 1024-byte aligned and trap otherwise
 constexpr int kSmemAlloc = kSmemTotal;
 static_assert(kSmemAlloc <= 232448, "forward kernel exceeds the 227 KB shared-memory limit");
@@ -84,12 +90,25 @@ struct TcPlan {
   int8_t layer_first[12], layer_nchunks[12];
   int16_t layer_n[12];               // UMMA N of the layer
   int32_t n_layers, n_chunks;
-  uint32_t w_rgb_off;                // fp32 float4 [128] = (W9[j][0], W9[j][1], W9[j][2], 0), then float4 (b9, 0)
+  int32_t xyz_only;                  // 1: the xyz-only network (ten layers, sigma head off h8)
+  uint32_t w_rgb_off;                // fp32 float4 [128] = (Wrgb[j][0], Wrgb[j][1], Wrgb[j][2], 0), then float4 (b_rgb, 0)
+  uint32_t w_sig_off;                // xyz-only: 16-bit sigma-head kernel [256] (operand format of the pack), fp32 bias
   uint32_t total_bytes;
 };
 
+// Forward schedule of the two networks of the reference (MMA layers; every layer ends with the chunk that carries its
+// bias: the input-panel chunk or the bias slab):
+//   view network (src/NeRF.py:290-340), 9 layers: 0 inp | 1-3 | 4 (+inp: skip) | 5-7 | 8 = [h8 ; view] -> last hidden (128) +
+//       sigma head in column 128 (N = 144, + inp chunk for the view columns); rgb head on CUDA cores in the last epilogue;
+//   xyz-only network (:248-288), 10 layers: 0 inp | 1-3 | 4 (+inp) | 5-7 | 8 = h8 -> h9 (256) | 9 = h9 -> last hidden (128);
+//       the sigma head reads h8: a dot product in the epilogue of layer 7; rgb head as above.
+__host__ __device__ constexpr int tc_n_layers(bool xyz) { return xyz ? 10 : 9; }
+__host__ __device__ constexpr uint32_t tc_layer_rows(bool xyz, int l) { return xyz ? (l == 9 ? 128u : 256u) : (l == 8 ? 144u : 256u); }
+__host__ __device__ constexpr bool tc_layer_slab(bool xyz, int l) { return xyz ? !(l == 0 || l == 4) : !(l == 0 || l == 4 || l == 8); }
+
 inline bool make_plan(const NetGeom& g, TcPlan* p) {
-  if (!g.view || g.hidden != 256 || g.last_hidden != 128 || g.dx > kInpOneCol || g.dv > 64 - kInpViewCol) return false;
+  if (g.hidden != 256 || g.last_hidden != 128 || g.dx > kInpOneCol || g.dv > 64 - kInpViewCol) return false;
+  const bool xyz = !g.view;
   memset(p, 0, sizeof(*p));
   int c = 0;
   uint32_t off = 0;
@@ -104,17 +123,17 @@ inline bool make_plan(const NetGeom& g, TcPlan* p) {
     p->layer_n[layer] = (int16_t)n;
     ++c;
   };
-  // every layer ends with the chunk that carries its bias: the input-panel chunk (layers 0, 4, 8) or the bias slab
-  add(0, 256, 4);
-  for (int l = 1; l <= 3; ++l) { for (int k = 0; k < 4; ++k) add(l, 256, k); add(l, 256, 5); }
-  for (int k = 0; k < 4; ++k) add(4, 256, k);
-  add(4, 256, 4);
-  for (int l = 5; l <= 7; ++l) { for (int k = 0; k < 4; ++k) add(l, 256, k); add(l, 256, 5); }
-  for (int k = 0; k < 4; ++k) add(8, 144, k);
-  add(8, 144, 4);
-  p->n_layers = 9;
+  const int nl = tc_n_layers(xyz);
+  for (int l = 0; l < nl; ++l) {
+    const int n = (int)tc_layer_rows(xyz, l);
+    if (l > 0) for (int k = 0; k < 4; ++k) add(l, n, k);
+    add(l, n, tc_layer_slab(xyz, l) ? 5 : 4);
+  }
+  p->n_layers = nl;
   p->n_chunks = c;
+  p->xyz_only = xyz ? 1 : 0;
   p->w_rgb_off = off;       off += 129 * 16;
+  p->w_sig_off = off;       off += 256 * 2 + 16;     // xyz-only: 16-bit sigma-head kernel [256], then its fp32 bias
   p->total_bytes = off;
   return true;
 }

@@ -32,11 +32,11 @@
 namespace nerf {
 
 // ---- dZ hand-over flags (overlapped mode) ---------------------------------------------------------------------------
-// flags[tile * kFlagsPerTile + b]: b = l - 1 for dZ_l (l = 1..8; two store warps -> target 2), b = 8 for the blocks the
+// flags[tile * kFlagsPerTile + b]: b = l - 1 for dZ_l (l = 1..9; two store warps -> target 2), b = 9 for the blocks the
 // chain prologue writes (dZ_L', dOut; eight epilogue warps -> target 8)
-constexpr int kFlagsPerTile = 9;
+constexpr int kFlagsPerTile = kHiddenSlots + 1;
 constexpr uint32_t kFlagTargetStore = 2, kFlagTargetPrologue = 8;
-constexpr int kBwdMaxChunks = 40;
+constexpr int kBwdMaxChunks = 48;
 constexpr int kBwdMaxSteps = 12;
 enum : int { STEP_MASK = 0, STEP_XSTASH = 1, STEP_XFINAL = 2 };
 
@@ -46,13 +46,17 @@ struct BwdPlan {
   int8_t step_first[kBwdMaxSteps], step_nch[kBwdMaxSteps], step_kind[kBwdMaxSteps], step_layer[kBwdMaxSteps];
   int16_t step_n[kBwdMaxSteps];
   int32_t n_steps, n_chunks;
+  int32_t n_hidden;      // 256-wide hidden layers whose dZ the chain writes: 8 (view network) or 9 (xyz-only network)
   uint32_t w_sigma_off;  // fp32 [256]: sigma-head kernel rows 0..255
   uint32_t w_rgb_off;    // fp32 float4 [128]: rgb-head kernel rows
   uint32_t total_bytes;
 };
 
-static void make_bwd_plan(BwdPlan* p) {
+// xyz: the xyz-only network (src/NeRF.py:248-288): one more step in front (dH9 = dZ_L W9^T), W8 is 256 x 256, and the
+// sigma head's rank-1 term still enters at the step that produces dH8 (the chain kernel keys it on layer 8).
+static void make_bwd_plan(BwdPlan* p, bool xyz = false) {
   memset(p, 0, sizeof(*p));
+  p->n_hidden = xyz ? 9 : 8;
   int c = 0, s = 0;
   uint32_t off = 0;
   auto step = [&](int kind, int layer, int n, int nch) {
@@ -68,7 +72,12 @@ static void make_bwd_plan(BwdPlan* p) {
     }
     ++s;
   };
-  step(STEP_MASK, 8, 256, 2);                       // dH8 = dZ_L W8[0:256]^T  (+ sigma term in the epilogue)
+  if (xyz) {
+    step(STEP_MASK, 9, 256, 2);                     // dH9 = dZ_L W9^T
+    step(STEP_MASK, 8, 256, 4);                     // dH8 = dZ_9 W8^T  (+ sigma term in the epilogue)
+  } else {
+    step(STEP_MASK, 8, 256, 2);                     // dH8 = dZ_L W8[0:256]^T  (+ sigma term in the epilogue)
+  }
   for (int l = 7; l >= 5; --l) step(STEP_MASK, l, 256, 4);
   step(STEP_XSTASH, 4, 64, 4);                      // d xyz  = dZ5 W4[0:dx]^T
   step(STEP_MASK, 4, 256, 4);                       // dH4 = dZ5 W4[dx:dx+256]^T
@@ -84,7 +93,7 @@ static void make_bwd_plan(BwdPlan* p) {
 // byte offset, inside the backward weight pack, of the first K chunk of W_l^T (the STEP_MASK step of layer l)
 uint32_t bwd_pack_layer_offset(int layer) {
   BwdPlan p;
-  make_bwd_plan(&p);
+  make_bwd_plan(&p);          // (view network: the only one the pipe prototype handles)
   for (int s = 0; s < p.n_steps; ++s)
     if (p.step_kind[s] == STEP_MASK && p.step_layer[s] == layer) return p.chunk_off[p.step_first[s]];
   return 0xffffffffu;
@@ -92,7 +101,7 @@ uint32_t bwd_pack_layer_offset(int layer) {
 
 uint32_t bwd_pack_bytes() {
   BwdPlan p;
-  make_bwd_plan(&p);
+  make_bwd_plan(&p, true);    // the larger of the two networks' packs: one size for both
   return p.total_bytes;
 }
 
@@ -123,9 +132,9 @@ __global__ void pack_bwd_kernel(const __grid_constant__ BwdPlan plan, NetGeom g,
     else
       *reinterpret_cast<__nv_bfloat16*>(packed + plan.chunk_off[chunk] + panel_offset(j, kk)) = __float2bfloat16_rn(v);
   } else {
-    if (e < 256) reinterpret_cast<float*>(packed + plan.w_sigma_off)[e] = P[g.layers[10].w_off + e];
+    if (e < 256) reinterpret_cast<float*>(packed + plan.w_sigma_off)[e] = P[g.layers[g.view ? 10 : 11].w_off + e];
     if (e < 128) {
-      const LayerDesc& L = g.layers[9];
+      const LayerDesc& L = g.layers[g.view ? 9 : 10];
       reinterpret_cast<float4*>(packed + plan.w_rgb_off)[e] =
           make_float4(P[L.w_off + e * 3 + 0], P[L.w_off + e * 3 + 1], P[L.w_off + e * 3 + 2], 0.f);
     }
@@ -134,7 +143,7 @@ __global__ void pack_bwd_kernel(const __grid_constant__ BwdPlan plan, NetGeom g,
 
 int bwd_pack_weights(const NetGeom& g, const float* params, uint8_t* packed_bwd, cudaStream_t st, bool half) {
   BwdPlan plan;
-  make_bwd_plan(&plan);
+  make_bwd_plan(&plan, !g.view);
   dim3 grid((256 * 64 + 255) / 256, plan.n_chunks + 1);
   if (half) pack_bwd_kernel<__half><<<grid, 256, 0, st>>>(plan, g, params, packed_bwd);
   else pack_bwd_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(plan, g, params, packed_bwd);
@@ -339,7 +348,7 @@ mlp_tc_bwd_chain_kernel(const __grid_constant__ BwdPlan plan, const uint8_t* __r
     const bool do_store = !(dbg & kDbgNoStore);
     uint32_t ph = 0;
     for (int64_t quad = quad0; quad < n_quads; quad += quad_step) {
-      for (int l = 8; l >= 1; --l, ph ^= 1u) {
+      for (int l = plan.n_hidden; l >= 1; --l, ph ^= 1u) {
 #pragma unroll
         for (int t = 0; t < 2; ++t) {
           const uint32_t act_u32 = sbase + kSmemCAct + t * kActPanels * kPanelBytes;
@@ -388,7 +397,7 @@ mlp_tc_bwd_chain_kernel(const __grid_constant__ BwdPlan plan, const uint8_t* __r
       if (row_ok) d4 = __ldg(reinterpret_cast<const float4*>(d_out4) + row);
       uint32_t mwl[2];
 #pragma unroll
-      for (int w = 0; w < 2; ++w) mwl[w] = __ldg(saved_mask + (8 * 8 + half * 2 + w) * 128 + r);
+      for (int w = 0; w < 2; ++w) mwl[w] = __ldg(saved_mask + (kMaskRowHL * 8 + half * 2 + w) * 128 + r);
       // the previous tile's last epilogue wrote these panel rows from other threads, and its store warp may still read them
       if (copy_pending) {
         mbar_wait(smem_u32(&bars->panel_free[t]), copy_ph);
@@ -430,7 +439,7 @@ mlp_tc_bwd_chain_kernel(const __grid_constant__ BwdPlan plan, const uint8_t* __r
       __syncwarp();
       if (lane == 0) {
         mbar_arrive_cluster(act_ready_leader);
-        if (flags) flag_signal(flags + (size_t)tile * kFlagsPerTile + 8);      // this warp's part of dZ_L' / dOut is out
+        if (flags) flag_signal(flags + (size_t)tile * kFlagsPerTile + kHiddenSlots);   // this warp's part of dZ_L' / dOut is out
       }
 
       float xs[32];                                      // d(xyz encoding): half 0 -> cols 0..31, half 1 -> cols 32..39
@@ -503,7 +512,7 @@ mlp_tc_bwd_chain_kernel(const __grid_constant__ BwdPlan plan, const uint8_t* __r
 // =====================================================================================================================
 // (2) dW
 // =====================================================================================================================
-enum : int { OUT_MAIN = 0, OUT_D8A = 1, OUT_INP_XYZ = 2, OUT_INP_VIEW = 3, OUT_D9 = 4 };
+enum : int { OUT_MAIN = 0, OUT_D8A = 1, OUT_INP_XYZ = 2, OUT_INP_VIEW = 3, OUT_RGB = 4, OUT_SIGMA_X = 5 };
 
 constexpr int kDwMaxStages = 10;
 constexpr int kDwRingBytes = 196608;
@@ -529,7 +538,7 @@ struct DwPlan {
   int32_t n_units;
 };
 
-static void make_dw_plan(DwPlan* p, int n_ctas_total) {
+static void make_dw_plan(DwPlan* p, int n_ctas_total, bool xyz = false) {
   memset(p, 0, sizeof(*p));
   int n = 0;
   auto add = [&](int a_panel, int a_chunks, int b_panel, int b_chunks, int nn, int out_kind, int dense, int has_bias) {
@@ -547,16 +556,23 @@ static void make_dw_plan(DwPlan* p, int n_ctas_total) {
     // plus ~700 cycles that do not shrink with the ring depth -> a 27 KB-equivalent overhead per stage
     u.cost = (float)((a_chunks == 0 ? 8 : a_chunks) + u.b_load) + 27.f;
     const bool prologue_block = b_panel >= kDzPanelL;
-    u.flag_idx = (int16_t)(prologue_block ? 8 : b_panel / kActPanels);       // dz_panel(l) = (l - 1) kActPanels
+    u.flag_idx = (int16_t)(prologue_block ? kHiddenSlots : b_panel / kActPanels);   // dz_panel(l) = (l - 1) kActPanels
     u.flag_target = (int16_t)(prologue_block ? kFlagTargetPrologue : kFlagTargetStore);
   };
   // Dense l (input h_l, or the input panel) with the gradient of its pre-activation output dZ_{l+1}
   add(0, 0, dz_panel(1), 32, 256, OUT_INP_XYZ, 0, 1);                                  // Dense 0
   for (int l = 1; l <= 7; ++l) add(saved_panel_h(l), 32, dz_panel(l + 1), 32, 256, OUT_MAIN, l, 1);  // Dense 1..7 (4: h4 rows)
   add(0, 0, dz_panel(5), 32, 256, OUT_INP_XYZ, 4, 0);                                  // Dense 4, xyz rows
-  add(saved_panel_h(8), 32, kDzPanelL, kDzChunksL, 144, OUT_D8A, 8, 1);                // Dense 8 + sigma head, h8 rows
-  add(0, 0, kDzPanelL, kDzChunksL, 144, OUT_INP_VIEW, 8, 0);                           // Dense 8 + sigma head, view rows
-  add(kSavedPanelHL, 16, kDzPanelOut, kDzChunksOut, 16, OUT_D9, 9, 1);                 // rgb head
+  if (xyz) {
+    add(saved_panel_h(8), 32, dz_panel(9), 32, 256, OUT_MAIN, 8, 1);                   // Dense 8: h8 -> h9
+    add(saved_panel_h(9), 32, kDzPanelL, kDzChunksL, 128, OUT_MAIN, 9, 1);             // Dense 9: h9 -> last hidden
+    add(kSavedPanelHL, 16, kDzPanelOut, kDzChunksOut, 16, OUT_RGB, 10, 1);             // rgb head (Dense 10)
+    add(saved_panel_h(8), 32, kDzPanelOut, kDzChunksOut, 16, OUT_SIGMA_X, 11, 1);      // sigma head (Dense 11): h8^T d sigma
+  } else {
+    add(saved_panel_h(8), 32, kDzPanelL, kDzChunksL, 144, OUT_D8A, 8, 1);              // Dense 8 + sigma head, h8 rows
+    add(0, 0, kDzPanelL, kDzChunksL, 144, OUT_INP_VIEW, 8, 0);                         // Dense 8 + sigma head, view rows
+    add(kSavedPanelHL, 16, kDzPanelOut, kDzChunksOut, 16, OUT_RGB, 9, 1);              // rgb head (Dense 9)
+  }
   p->n_units = n;
   // CTAs in proportion to the modelled cost (largest-remainder rounding, at least one each)
   float total = 0.f;
@@ -616,8 +632,11 @@ __device__ __forceinline__ float* dw_target(const DwUnit& u, const NetGeom& g, f
       if (n == 128) return G + g.layers[10].w_off + row;
       return nullptr;
     }
-    case OUT_D9:
-      if (n < 3) return G + g.layers[9].w_off + (int64_t)k * 3 + n;
+    case OUT_RGB:
+      if (n < 3) return G + g.layers[u.dense].w_off + (int64_t)k * 3 + n;
+      return nullptr;
+    case OUT_SIGMA_X:                      // dOut block = [d r, d g, d b, d sigma, 0 ...]: column 3 is the sigma head's
+      if (n == 3) return G + g.layers[u.dense].w_off + k;
       return nullptr;
   }
   return nullptr;
@@ -631,7 +650,8 @@ __device__ __forceinline__ float* db_target(const DwUnit& u, const NetGeom& g, f
       if (n < 128) return G + g.layers[8].b_off + n;
       if (n == 128) return G + g.layers[10].b_off;
       return nullptr;
-    case OUT_D9: return n < 3 ? G + g.layers[9].b_off + n : nullptr;
+    case OUT_RGB: return n < 3 ? G + g.layers[u.dense].b_off + n : nullptr;
+    case OUT_SIGMA_X: return n == 3 ? G + g.layers[u.dense].b_off : nullptr;
   }
   return nullptr;
 }
@@ -836,7 +856,7 @@ int mlp_tc_bwd(const nerf_net_cfg* cfg, const NetGeom& g, const float* params, c
   (void)params; (void)xyz_enc; (void)view_enc;
   TcPlan fplan;
   if (!make_plan(g, &fplan)) {
-    set_error("NERF_MODE_BF16 supports hidden=256, last_hidden=128, n_angles in {1,2}, xyz width <= 40, view width <= 24");
+    set_error("the tensor-core modes support hidden=256, last_hidden=128, xyz width <= 38, view width <= 24");
     return NERF_E_UNSUPPORTED;
   }
   if (device_first_use(1)) {
@@ -844,7 +864,7 @@ int mlp_tc_bwd(const nerf_net_cfg* cfg, const NetGeom& g, const float* params, c
     NERF_CUDA(cudaFuncSetAttribute(mlp_tc_bwd_dw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemDwAlloc));
   }
   BwdPlan bplan;
-  make_bwd_plan(&bplan);
+  make_bwd_plan(&bplan, !g.view);
   // Both 16-bit modes share this backward: tcgen05 kind::f16 wants ONE operand format per MMA (an fp16 A with a bf16 B is
   // an illegal instruction on sm_100a -- tried), and the gradients need bf16's range, so the forward of the fp16 mode
   // saves its activations converted to bf16 and the chain reads the bf16 W^T.
@@ -892,7 +912,7 @@ int mlp_tc_bwd(const nerf_net_cfg* cfg, const NetGeom& g, const float* params, c
   }
   if (!(dbg & kDbgNoDw) && (parts & 2)) {
     DwPlan dplan;
-    make_dw_plan(&dplan, dw_ctas);
+    make_dw_plan(&dplan, dw_ctas, !g.view);
     cudaStream_t dst = st;
     if (side != nullptr && side != st && parts == 3) {
       // the weight-gradient kernel goes to the caller's side stream: after the chain when the two run one after the

@@ -503,7 +503,7 @@ extern "C" int nerf_debug_bwd_pipe_layer(const nerf_net_cfg* cfg, const void* pa
                                          void* workspace, int32_t layer, float* grads, void* stream) {
   NetGeom g;
   TcPlan fplan;
-  NERF_CHECK_ARG(make_geom(cfg, &g) && make_plan(g, &fplan), "network not supported by NERF_MODE_BF16");
+  NERF_CHECK_ARG(make_geom(cfg, &g) && make_plan(g, &fplan) && g.view, "the pipe prototype handles the view-direction network");
   NERF_CHECK_ARG(packed && saved && workspace && grads, "null pointer");
   NERF_CHECK_ARG(layer >= 1 && layer <= 8 && m > 0, "layer must be 1..8");
   const uint8_t* packed_bwd = (const uint8_t*)packed + ((fplan.total_bytes + 1023u) & ~1023u);

@@ -98,12 +98,17 @@ def test_fused_entry_points_report_argument_errors(pkg):
                                    ctypes.c_void_p(256), ctypes.c_void_p(256), 4, ctypes.byref(rng), ctypes.byref(outs),
                                    ctypes.c_void_p(264), None)
     assert st == -1 and b"256-byte aligned" in lib.nerf_last_error()
-    # the xyz-only network has no tensor-core path: the whole-path calls say so (and size only the fp32 mode)
+    # the xyz-only network (n_angles_for_model: 0, src/NeRF.py:248-288) has a tensor-core plan as well (round 2); a network
+    # outside the plans (hidden width != 256) still says so and sizes only the fp32 mode
     cfg0 = pkg.NetCfg(5, 4, 0, 256, 128, 0.05)
-    assert lib.nerf_render_workspace_bytes(ctypes.byref(cfg0), ctypes.byref(rc), 10) == -1
-    assert lib.nerf_train_workspace_bytes(ctypes.byref(cfg0), ctypes.byref(rc), 10) == -1
-    assert lib.nerf_render_workspace_bytes(ctypes.byref(cfg0), ctypes.byref(L.RenderCfg(0.5576, 2.5635, 64, 128, L.MODE_FP32)), 10) > 0
-    st = lib.nerf_render_fused_fwd(ctypes.byref(cfg0), ctypes.byref(rc), None, ctypes.c_void_p(256), None, ctypes.c_void_p(256),
+    assert lib.nerf_packed_bytes(ctypes.byref(cfg0)) > 0
+    assert lib.nerf_render_workspace_bytes(ctypes.byref(cfg0), ctypes.byref(rc), 10) > 0
+    assert lib.nerf_train_workspace_bytes(ctypes.byref(cfg0), ctypes.byref(rc), 10) > 0
+    cfg1 = pkg.NetCfg(5, 4, 2, 128, 128, 0.05)
+    assert lib.nerf_render_workspace_bytes(ctypes.byref(cfg1), ctypes.byref(rc), 10) == -1
+    assert lib.nerf_train_workspace_bytes(ctypes.byref(cfg1), ctypes.byref(rc), 10) == -1
+    assert lib.nerf_render_workspace_bytes(ctypes.byref(cfg1), ctypes.byref(L.RenderCfg(0.5576, 2.5635, 64, 128, L.MODE_FP32)), 10) > 0
+    st = lib.nerf_render_fused_fwd(ctypes.byref(cfg1), ctypes.byref(rc), None, ctypes.c_void_p(256), None, ctypes.c_void_p(256),
                                    ctypes.c_void_p(256), ctypes.c_void_p(256), 4, ctypes.byref(rng), ctypes.byref(outs),
                                    ctypes.c_void_p(256), None)
     assert st == -3 and b"no tensor-core path" in lib.nerf_last_error()

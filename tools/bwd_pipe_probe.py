@@ -12,7 +12,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 pkg = importlib.import_module("nerf-and-dietnerf_b200")
 
-DZ_TILE_BYTES = 36 * 16384
+DZ_TILE_BYTES = 40 * 16384
 SHAPES = [(33, 256)] + [(256, 256)] * 3 + [(289, 256)] + [(256, 256)] * 3 + [(280, 128), (128, 3), (280, 1)]
 
 
