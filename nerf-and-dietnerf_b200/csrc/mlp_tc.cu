@@ -295,25 +295,29 @@ mlp_tc_fwd_kernel(const __grid_constant__ TcPlan plan, const uint8_t* __restrict
 
   if (warp == kWarpProducer) {
     // ===== producer: weight chunks (ring) =====
-    if (lane == 0) {
-      // Static walk over the packed weights (the chunk order of make_plan): no table look-ups, no divisions -- this
-      // thread's own instruction latency sits on the path from "stage released" to "stage full".
-      const bool timing = kTcTrace && (dbg & kDbgTiming) && blockIdx.x == 0;
-      long long t_begin = clock64(), t_rel = 0;
+    // kProdLanes lanes issue the copies of consecutive ring stages side by side.  Measured (tools/l2_bw_probe.cu,
+    // profiles/r02_g_l2_bw_probe.log): ONE thread gets ~3.5 M bulk copies per second out of the TMA path whatever their
+    // size (a 16 KB copy every ~550 cycles -- the four MMAs it feeds take 512), two lanes twice that.  With a single
+    // producer lane the weight stream, not the tensor pipe or shared memory, set the pace of this kernel.
+    if (lane < kProdLanes) {
+      // Every producer lane walks the SAME static sequence (the chunk order of make_plan: pointer adds only -- no table
+      // look-ups or divisions on the path from "stage released" to "stage full") and issues the items whose index is its
+      // own modulo kProdLanes.
       const uint32_t full0 = smem_u32(&bars->full[0]), empty0 = smem_u32(&bars->empty[0]);
       const bool no_copy = (dbg & kDbgNoWeightCopy) != 0;
-      uint32_t s = 0, ph = 1;                            // ring stage, parity of the "stage is free" phase
+      uint32_t s = 0, ph = 1, k = 0;                     // ring stage, parity of the "stage is free" phase, item index
       // this CTA's half of a chunk: rows [rank N/2, (rank + 1) N/2) of [N][64] (or of the [256][16] bias slab)
       auto load = [&](const uint8_t* src, uint32_t half_bytes) {
-        long long tw = timing ? clock64() : 0;
-        mbar_wait_spin(empty0 + 8u * s, ph);
-        if (timing) t_rel += clock64() - tw;
-        if (no_copy) {
-          mbar_arrive(full0 + 8u * s);
-        } else {
-          mbar_arrive_expect_tx(full0 + 8u * s, half_bytes);
-          bulk_g2s(sbase + kSmemStage + s * kStageBytes, src + rank * half_bytes, half_bytes, full0 + 8u * s);
+        if ((k & (uint32_t)(kProdLanes - 1)) == (uint32_t)lane) {
+          mbar_wait_spin(empty0 + 8u * s, ph);
+          if (no_copy) {
+            mbar_arrive(full0 + 8u * s);
+          } else {
+            mbar_arrive_expect_tx(full0 + 8u * s, half_bytes);
+            bulk_g2s(sbase + kSmemStage + s * kStageBytes, src + rank * half_bytes, half_bytes, full0 + 8u * s);
+          }
         }
+        ++k;
         if (++s == kStages) { s = 0; ph ^= 1u; }
       };
       for (int64_t quad = quad0; quad < n_quads; quad += quad_step) {
@@ -337,7 +341,6 @@ mlp_tc_fwd_kernel(const __grid_constant__ TcPlan plan, const uint8_t* __restrict
           layer_base += (l == 0 ? chunk_bytes : 4u * chunk_bytes + (slab ? (uint32_t)kBiasSlabBytes : chunk_bytes));
         }
       }
-      if (timing) printf("fwd producer: total %lld  wait stage release %lld (cycles)\n", clock64() - t_begin, t_rel);
     }
   } else if (warp == kWarpMma) {
     // ===== MMA issuer (leader CTA) / weight-arrival relay (peer CTA) =====

@@ -18,6 +18,14 @@ constexpr int kActPanels = 4;                     // 256 features
 // 2 x 32 KB single-CTA ring every 512-cycle chunk of MMAs waited ~300 cycles for its weights (L2 latency ~700 cycles).
 constexpr int kStageBytes = 16384;                // this CTA's half of one weight chunk
 constexpr int kStages = 4;                        // forward ring
+#ifndef NERF_PROD_LANES
+#define NERF_PROD_LANES 1
+#endif
+// Producer lanes issuing the weight copies side by side (power of two, < kStages).  One thread gets ~3.5 M bulk copies per
+// second out of the TMA path (tools/l2_bw_probe.cu); two lanes were tried here and change nothing (1393 TFLOP/s either
+// way): at one 16 KB copy per 512 MMA cycles these kernels are not copy-issue-bound.  The layer-pipelined backward, which
+// needs six 32 KB copies per 4096 MMA cycles from L2 and HBM, is where it matters.
+constexpr int kProdLanes = NERF_PROD_LANES;
 constexpr int kInpViewCol = 40;                   // first view-encoding column of the input panel
 constexpr int kInpOneCol = 38;                    // input-panel columns 38, 39 hold the constant 1: the weight rows they
                                                   // meet carry bf16(b) and bf16(b - bf16(b)), so the bias rides in the MMA
@@ -62,6 +70,16 @@ constexpr int kSavedPanelHL = 1 + kHiddenSlots * kActPanels;
 __host__ __device__ constexpr uint32_t rbcm_offset(int r, int j, int n_chunks) {
   return (uint32_t)(r >> 6) * (uint32_t)(n_chunks * 1024) + (uint32_t)j * 1024u + (uint32_t)(r & 63) * 16u;
 }
+// "Tile chunk-major" (TCM) variant of the same blocks, used by the layer-pipelined backward: [16-byte column chunk j][row
+// 0..127][8 cols].  A warp still stores 512 contiguous bytes, a 128-row tile of 64 features is one contiguous 16 KB piece
+// with a uniform 128-byte stride between 8-row groups over all 128 rows (what a K-major UMMA A operand needs), and a
+// feature half of the tile (16 chunks) is one contiguous 32 KB piece = the un-swizzled MN-major operand (SBO = 2048).
+__host__ __device__ constexpr uint32_t tcm_offset(int r, int j) { return (uint32_t)j * 2048u + (uint32_t)r * 16u; }
+// byte offset of (row r, chunk j) in a block with n_chunks chunks: RBCM (tcm == false) or TCM
+__host__ __device__ constexpr uint32_t block_offset(bool tcm, int r, int j, int n_chunks) {
+  return tcm ? tcm_offset(r, j) : rbcm_offset(r, j, n_chunks);
+}
+
 // Backward workspace of one tile (chain kernel -> dW kernel), RBCM blocks: dZ_1..dZ_9 (32 chunks each), dZ_L' (24
 // chunks: 0..15 = dZ_L, chunk 16 = [d sigma, 0 ...], 17 zero, 18..23 unused), dOut (8 chunks: chunk 0 = d_out4, 1 zero)
 constexpr int kDzPanels = kHiddenSlots * kActPanels + 3 + 1;

@@ -266,10 +266,12 @@ mlp_tc_bwd_chain_kernel(const __grid_constant__ BwdPlan plan, const uint8_t* __r
   const uint32_t tmem_base = bars->tmem_base;
 
   if (warp == kWarpProducer) {
-    if (lane == 0) {
+    // kProdLanes lanes walk the same sequence and issue alternate items: one thread gets a bulk copy out every ~550 cycles,
+    // the four MMAs a chunk feeds take 512 (mlp_tc.cu, tools/l2_bw_probe.cu)
+    if (lane < kProdLanes) {
       const uint32_t full0 = smem_u32(&bars->full[0]), empty0 = smem_u32(&bars->empty[0]);
       const bool no_copy = (dbg & kDbgNoWeightCopy) != 0;
-      uint32_t st = 0, ph = 1;                           // ring stage, parity of the "stage is free" phase
+      uint32_t st = 0, ph = 1, k = 0;                    // ring stage, parity of the "stage is free" phase, item index
       for (int64_t quad = quad0; quad < n_quads; quad += quad_step) {
         for (int s = 0; s < plan.n_steps; ++s) {
           if (!need_dx && plan.step_kind[s] != STEP_MASK) continue;
@@ -277,13 +279,15 @@ mlp_tc_bwd_chain_kernel(const __grid_constant__ BwdPlan plan, const uint8_t* __r
           const uint32_t half_bytes = plan.chunk_bytes[first] >> 1;     // rows [rank N/2, (rank + 1) N/2) of [N][64]
           const uint8_t* src = packed + plan.chunk_off[first] + rank * half_bytes;
           for (int t = 0; t < 2; ++t) {      // staggered: every step's chunks are streamed once per super-tile
-            for (int ci = 0; ci < nch; ++ci) {
-              mbar_wait_spin(empty0 + 8u * st, ph);
-              if (no_copy) {
-                mbar_arrive(full0 + 8u * st);
-              } else {
-                mbar_arrive_expect_tx(full0 + 8u * st, half_bytes);
-                bulk_g2s(sbase + kSmemCStage + st * kCStageBytes, src + (size_t)ci * 2u * half_bytes, half_bytes, full0 + 8u * st);
+            for (int ci = 0; ci < nch; ++ci, ++k) {
+              if ((k & (uint32_t)(kProdLanes - 1)) == (uint32_t)lane) {
+                mbar_wait_spin(empty0 + 8u * st, ph);
+                if (no_copy) {
+                  mbar_arrive(full0 + 8u * st);
+                } else {
+                  mbar_arrive_expect_tx(full0 + 8u * st, half_bytes);
+                  bulk_g2s(sbase + kSmemCStage + st * kCStageBytes, src + (size_t)ci * 2u * half_bytes, half_bytes, full0 + 8u * st);
+                }
               }
               if (++st == kCStages) { st = 0; ph ^= 1u; }
             }

@@ -2,33 +2,27 @@
 // with the input-gradient chain and the weight gradients of a layer computed BY THE SAME CTA PAIR from the same dZ, and
 // dZ handed from layer to layer through L2 instead of HBM.
 //
-//   * The 74 CTA pairs (cluster of 2, tcgen05 cta_group::2) are split into GROUPS, one per layer l = 7..1 (plus the
-//     weight gradients of Dense 8's h8 rows and, for the fine network, the xyz-encoding gradient).  A group is
+//   * The CTA pairs (cluster of 2, tcgen05 cta_group::2) are split into GROUPS, one per layer.  A group is
 //     layer-STATIONARY: its pairs keep W_l^T resident in shared memory (64 KB per CTA: each CTA holds the 128 output rows
 //     of every K chunk it contributes to the pair's MMA) and the whole 256 x 256 fp32 accumulator of dW_l in TMEM
-//     (128 lanes x 256 columns per CTA, cta_group::2 M = 256) for the entire launch -- one split-K partial per PAIR
-//     instead of one per CTA and tile range.
+//     (128 lanes x 256 columns per CTA, cta_group::2 M = 256) for the entire launch -- one split-K partial per PAIR.
 //   * Per 256-row super-tile s (tiles 2s, 2s+1; CTA r owns the rows of tile 2s + r in the chain) a pair of group l
 //       - waits for the ready counter of dZ_{l+1}[s] (written by a pair of group l+1 moments ago, so it sits in L2),
-//       - chain:  dH_l = dZ_{l+1} W_l^T   (A = its own 128 rows, K-major, streamed in four 64-feature panels;
-//                 accumulator D1 = TMEM columns 0..255), epilogue = LeakyReLU' from the saved sign mask, bf16, straight
-//                 from registers to the dZ_l block in global memory (RBCM, 512-byte warp stores), then the ready
-//                 counter of dZ_l[s];
+//       - chain:  dH_l = dZ_{l+1} W_l^T   (A = its own 128 rows, K-major; accumulator D1 = TMEM columns 0..255), epilogue =
+//                 LeakyReLU' from the saved sign mask, bf16, straight from registers to the dZ_l block in global memory
+//                 (512-byte warp stores), then the ready counter of dZ_l[s];
 //       - dW:     dW_l += A_l^T dZ_{l+1}  (both operands MN-major, the pair splits the FEATURES: CTA r streams features
-//                 128 r .. 128 r + 127 of the saved activations and of dZ_{l+1} for all 256 rows, in 64-row slabs;
-//                 accumulator D2 = TMEM columns 256..511), bias gradient = column sums of the same slabs.
-//     The MMA order inside a super-tile is  c0 c1 d0 c2 c3 d1 d2 d3  (c = chain panel, d = dW slab): the tensor pipe
-//     always has work, the chain accumulator drains (16 epilogue warps) under the last three dW slabs, and the bulk
-//     copies are spread evenly (48 KB per 1024 MMA cycles and CTA: two thirds from L2, one third -- the saved
-//     activations -- from HBM).
-//   * Per FLOP an SM moves half the shared-memory bytes of the per-tile chain kernel (no weight ring, no in-place
-//     activation rewrite, no store-warp re-read) and a third of the L2->SM bytes of the stand-alone dW kernel.
-//
-// Layout notes: dZ blocks and saved activations are RBCM (mlp_tc.cuh).  A feature half of a 64-row slab is ONE contiguous
-// 16 KB piece and IS the un-swizzled MN-major operand (SBO = 1024 between 8-feature chunks, LBO = 128 between 8-row
-// groups).  The chain's K-major A operand needs a uniform 128-byte stride over all 128 rows of the tile, i.e. 2 KB per
-// chunk in shared memory: a panel is gathered by 16 one-KB bulk copies (8 chunks x 2 row halves), issued by 16 lanes of
-// the producer warp in one instruction.
+//                 128 r .. 128 r + 127 of the saved activations and of dZ_{l+1} for all 256 rows; accumulator D2 = TMEM
+//                 columns 256..511), bias gradient = column sums of the same dZ pieces.
+//   * Everything a CTA needs arrives as SIX 32 KB bulk copies per super-tile (blocks are tile chunk-major, TCM, mlp_tc.cuh):
+//       c01, c23   its own tile's dZ, feature chunks 0..15 / 16..31: the chain's A operand, two 64-feature K panels each
+//       B0, A0     tile 2s:    dZ and saved activations, this CTA's feature half -> dW, 8 K-steps of 16 rows
+//       B1, A1     tile 2s+1:  the same
+//     through ONE in-order ring of five 32 KB slots; the MMA groups C01 C23 D0 D1 take 1024 tensor cycles each, so every
+//     copy is issued >= 2048 cycles before its data is needed and the chain accumulator drains (16 epilogue warps) under
+//     D0 / D1.  Copy size and issue rate are what the first prototype of this kernel got wrong (16 x 1 KB gathers and 16 KB
+//     pieces from one lane: 6.8 TB/s aggregate where the same ring moves 17-20 TB/s in 32 KB copies -- a thread gets one
+//     bulk copy out every ~290 ns whatever its size, tools/l2_bw_probe.cu): here two producer lanes issue alternate items.
 #include <stdlib.h>
 
 #include "mlp_tc.cuh"
@@ -39,30 +33,29 @@ namespace nerf {
 // ---- shared-memory map ------------------------------------------------------------------------------------------------
 constexpr int kPW = 0;                                   // resident W_l^T half: 4 K-chunks x [128 rows][64] swizzled
 constexpr int kPWBytes = 4 * 16384;
-constexpr int kPCStages = 4, kPCBytes = 16384;           // chain ring: [8 chunks][128 rows][16 B]
-constexpr int kPDStages = 3, kPDBytes = 32768;           // dW ring: A slab [16 chunks][64 rows][16 B] | B slab (same)
-constexpr int kPC = kPW + kPWBytes;
-constexpr int kPD = kPC + kPCStages * kPCBytes;
-constexpr int kPBar = kPD + kPDStages * kPDBytes;
+constexpr int kPSlots = 5, kPSlotBytes = 32768;          // the ring
+constexpr int kPRing = kPW + kPWBytes;
+constexpr int kPBar = kPRing + kPSlots * kPSlotBytes;
 constexpr int kPAlloc = kPBar + 256;
 static_assert(kPAlloc <= 232448, "pipe kernel exceeds the 227 KB shared-memory limit");
+constexpr int kPipeProdLanes = 2;
 
 struct PipeBars {
-  uint64_t wfull, cfull[kPCStages], cempty[kPCStages], dfull[kPDStages], dempty[kPDStages];
+  uint64_t wfull, full[kPSlots], empty[kPSlots];
   uint64_t acc_full, acc_empty, fin;
   uint32_t tmem_base;
 };
 static_assert(sizeof(PipeBars) <= 256, "barrier block overflows its slot");
 
-// order of the eight MMA groups of a super-tile: 0 = chain panel, 1 = dW slab
-__device__ __forceinline__ constexpr int seq_kind(int i) { return (i == 2 || i >= 5) ? 1 : 0; }
+// items of a super-tile in ring order (PIPE_ROLE_LAYER: all six; PIPE_ROLE_DW_ONLY: the last four)
+enum : int { IT_C01 = 0, IT_C23 = 1, IT_B0 = 2, IT_A0 = 3, IT_B1 = 4, IT_A1 = 5 };
 
 struct RingPos {
   uint32_t s, ph;
-  __device__ __forceinline__ void next(uint32_t n) { if (++s == n) { s = 0; ph ^= 1u; } }
+  __device__ __forceinline__ void next() { if (++s == (uint32_t)kPSlots) { s = 0; ph ^= 1u; } }
 };
 
-// ---- producer (warp 16 of both CTAs) ------------------------------------------------------------------------------------
+// ---- producer (warp 16 of both CTAs, kPipeProdLanes lanes) ----------------------------------------------------------------
 template <bool kChain>
 __device__ __forceinline__ void pipe_producer(const PipeGroup& G, PipeBars* bars, uint32_t sbase, uint32_t rank, int lane,
                                               const uint8_t* __restrict__ packed, const uint8_t* __restrict__ saved,
@@ -75,78 +68,63 @@ __device__ __forceinline__ void pipe_producer(const PipeGroup& G, PipeBars* bars
     for (int kp = 0; kp < 4; ++kp)
       bulk_g2s(sbase + kPW + kp * 16384, packed + G.w_off + (size_t)kp * 32768 + rank * 16384u, 16384, wf);
   }
-  RingPos c{0, 1}, d{0, 1};
-  const uint32_t a_bytes = 16384u, b_bytes = (uint32_t)G.b_chunks * 1024u;
+  RingPos p{0, 1};
+  uint32_t k = 0;
+  const uint32_t b_bytes = (uint32_t)G.b_chunks * 2048u;
   for (int64_t s = s_first; s < n_super; s += s_step) {
     if (G.wait_flag >= 0) {
       if (lane == 0) flag_wait(flags + (size_t)s * kPipeFlagsPerSuper + G.wait_flag, kPipeFlagTarget);
-      __syncwarp();
+      __syncwarp((1u << kPipeProdLanes) - 1u);
       asm volatile("fence.proxy.async;" ::: "memory");
     }
     const int64_t sz = (dbg & kDbgWrapDz) ? (s & 127) : s, ss = (dbg & kDbgWrapSaved) ? (s & 127) : s;
-    const uint8_t* own_b = dz_ws + (size_t)(2 * sz + rank) * kDzTileBytes + (size_t)G.b_off;   // chain A operand source
-    int kp = 0, j = 0;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      if (seq_kind(i) == 0) {
-        if (kChain) {
-          const uint32_t fb = smem_u32(&bars->cfull[c.s]);
-          if (lane == 0) {
-            mbar_wait_spin(smem_u32(&bars->cempty[c.s]), c.ph);
-            mbar_arrive_expect_tx(fb, kPCBytes);
+    for (int it = kChain ? 0 : 2; it < 6; ++it, ++k) {
+      if ((k & (uint32_t)(kPipeProdLanes - 1)) == (uint32_t)lane) {
+        const uint8_t* src;
+        uint32_t bytes;
+        if (it <= IT_C23) {
+          src = dz_ws + (size_t)(2 * sz + rank) * kDzTileBytes + (size_t)G.b_off + (size_t)it * 32768;
+          bytes = 32768;
+        } else {
+          const int t = (it - 2) >> 1;
+          if ((it & 1) == 0) {           // B: dZ_{l+1}, this CTA's feature half
+            src = dz_ws + (size_t)(2 * sz + t) * kDzTileBytes + (size_t)G.b_off + (size_t)rank * b_bytes;
+            bytes = b_bytes;
+          } else {                       // A: saved activations, this CTA's feature half
+            src = saved + (size_t)(2 * ss + t) * kSavedTileBytes + (size_t)G.a_off + (size_t)rank * 32768;
+            bytes = 32768;
           }
-          __syncwarp();
-          if (lane < 16) {
-            const int h = lane >> 3, cc = lane & 7;        // row half, chunk inside the panel
-            bulk_g2s(sbase + kPC + c.s * kPCBytes + cc * 2048 + h * 1024,
-                     own_b + (size_t)h * (32 * 1024) + (size_t)(8 * kp + cc) * 1024, 1024, fb);
-          }
-          c.next(kPCStages);
         }
-        ++kp;
-      } else {
-        if (lane == 0) {
-          const int64_t tile = 2 * ss + (j >> 1), tile_z = 2 * sz + (j >> 1);
-          const int hh = j & 1;
-          const uint32_t fb = smem_u32(&bars->dfull[d.s]);
-          mbar_wait_spin(smem_u32(&bars->dempty[d.s]), d.ph);
-          mbar_arrive_expect_tx(fb, a_bytes + b_bytes);
-          const uint32_t dst = sbase + kPD + d.s * kPDBytes;
-          bulk_g2s(dst, saved + (size_t)tile * kSavedTileBytes + (size_t)G.a_off + (size_t)hh * 32768 + rank * 16384u, a_bytes, fb);
-          bulk_g2s(dst + 16384, dz_ws + (size_t)tile_z * kDzTileBytes + (size_t)G.b_off + (size_t)hh * ((size_t)G.b_half_chunks * 1024) +
-                                    (size_t)rank * b_bytes, b_bytes, fb);
+        const uint32_t fb = smem_u32(&bars->full[p.s]);
+        mbar_wait_spin(smem_u32(&bars->empty[p.s]), p.ph);
+        if (dbg & kDbgNoWeightCopy) {
+          mbar_arrive(fb);
+        } else {
+          mbar_arrive_expect_tx(fb, bytes);
+          bulk_g2s(sbase + kPRing + p.s * kPSlotBytes, src, bytes, fb);
         }
-        d.next(kPDStages);
-        ++j;
       }
+      p.next();
     }
   }
 }
 
-// ---- relay (warp 17 lane 0 of the PEER CTA): "my half of this stage has landed" -> the leader's full barrier ----------------
+// ---- relay (warp 17 lane 0 of the PEER CTA): "my half of this item has landed" -> the leader's full barrier --------------
 template <bool kChain>
 __device__ __forceinline__ void pipe_relay(PipeBars* bars, int64_t s_first, int64_t s_step, int64_t n_super) {
   if (kChain) {
     mbar_wait_spin(smem_u32(&bars->wfull), 0);
     mbar_arrive_cluster(mapa_shared(smem_u32(&bars->wfull), 0));
   }
-  const uint32_t cf0 = smem_u32(&bars->cfull[0]), df0 = smem_u32(&bars->dfull[0]);
-  const uint32_t cf0_l = mapa_shared(cf0, 0), df0_l = mapa_shared(df0, 0);
-  RingPos c{0, 0}, d{0, 0};
+  const uint32_t f0 = smem_u32(&bars->full[0]), f0_l = mapa_shared(f0, 0);
+  RingPos p{0, 0};
   for (int64_t s = s_first; s < n_super; s += s_step) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      if (seq_kind(i) == 0) {
-        if (kChain) {
-          mbar_wait_spin(cf0 + 8u * c.s, c.ph);
-          mbar_arrive_cluster(cf0_l + 8u * c.s);
-          c.next(kPCStages);
-        }
-      } else {
-        mbar_wait_spin(df0 + 8u * d.s, d.ph);
-        mbar_arrive_cluster(df0_l + 8u * d.s);
-        d.next(kPDStages);
-      }
+    for (int it = kChain ? 0 : 2; it < 6; ++it) {
+      mbar_wait_spin(f0 + 8u * p.s, p.ph);
+      mbar_arrive_cluster(f0_l + 8u * p.s);
+      p.next();
     }
   }
 }
@@ -158,80 +136,87 @@ __device__ __forceinline__ void pipe_mma(const PipeGroup& G, PipeBars* bars, uin
   const uint32_t idesc_c = make_idesc(G.n_chain, 0, 0, 1, 256);
   const uint32_t idesc_d = make_idesc(G.n_dw, 1, 1, 1, 256);
   const uint32_t d1 = tmem_base, d2 = tmem_base + 256u;
-  const uint64_t a_c0 = make_desc_k_nosw(sbase + kPC, 2048, 128);       // chain A: [chunk][128 rows][16 B]
+  const uint64_t a_c0 = make_desc_k_nosw(sbase + kPRing, 2048, 128);    // chain A: [16 chunks][128 rows][16 B]
   const uint64_t b_c0 = make_desc_kmajor(sbase + kPW);                  // chain B: resident swizzled W chunks
-  const uint64_t a_d0 = make_desc_mn_nosw(sbase + kPD, 128, 1024);      // dW A: saved activations slab
-  const uint64_t b_d0 = make_desc_mn_nosw(sbase + kPD + 16384, 128, 1024);
-  const uint32_t cf0 = smem_u32(&bars->cfull[0]), ce0 = smem_u32(&bars->cempty[0]);
-  const uint32_t df0 = smem_u32(&bars->dfull[0]), de0 = smem_u32(&bars->dempty[0]);
+  const uint64_t mn0 = make_desc_mn_nosw(sbase + kPRing, 128, 2048);    // dW A / B: [chunk][128 rows][16 B], K = rows
+  const uint32_t f0 = smem_u32(&bars->full[0]), e0 = smem_u32(&bars->empty[0]);
   const bool no_mma = (dbg & kDbgNoMma) != 0;
   if (kChain) {
     mbar_wait_spin(smem_u32(&bars->wfull), 0);
     tc_fence_after();
   }
-  RingPos c{0, 0}, d{0, 0};
+  RingPos p{0, 0};
   uint32_t it = 0, dacc = 0;
   for (int64_t s = s_first; s < n_super; s += s_step, ++it) {
-    int kp = 0;
+    if (kChain) {
+      if (it > 0) {
+        mbar_wait_spin(smem_u32(&bars->acc_empty), (it - 1) & 1u);   // both CTAs drained D1 of the previous super-tile
+        tc_fence_after();
+      }
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      if (seq_kind(i) == 0) {
-        if (kChain) {
-          if (kp == 0 && it > 0) {
-            mbar_wait_spin(smem_u32(&bars->acc_empty), (it - 1) & 1u);   // both CTAs drained D1 of the previous super-tile
-            tc_fence_after();
-          }
-          mbar_wait_spin(cf0 + 8u * c.s, c.ph);
-          tc_fence_after();
-          if (!no_mma) {
-            const uint64_t a = a_c0 + (uint64_t)(c.s * (uint32_t)(kPCBytes >> 4));
-            const uint64_t b = b_c0 + (uint64_t)(kp * (16384 >> 4));
-#pragma unroll
-            for (int k = 0; k < 4; ++k)
-              umma_pair(d1, a + (uint64_t)(k * (4096 >> 4)), b + (uint64_t)(2 * k), idesc_c, (kp > 0 || k > 0) ? 1u : 0u);
-          }
-          umma_commit_pair(ce0 + 8u * c.s);
-          if (kp == 3) umma_commit_pair(smem_u32(&bars->acc_full));
-          c.next(kPCStages);
-        }
-        ++kp;
-      } else {
-        mbar_wait_spin(df0 + 8u * d.s, d.ph);
+      for (int h = 0; h < 2; ++h) {                                  // c01, c23: two K panels each
+        mbar_wait_spin(f0 + 8u * p.s, p.ph);
         tc_fence_after();
         if (!no_mma) {
-          const uint64_t off = (uint64_t)(d.s * (uint32_t)(kPDBytes >> 4));
+          const uint64_t a = a_c0 + (uint64_t)(p.s * (uint32_t)(kPSlotBytes >> 4));
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            umma_pair(d2, a_d0 + off + (uint64_t)(k * (256 >> 4)), b_d0 + off + (uint64_t)(k * (256 >> 4)), idesc_d, dacc);
-            dacc = 1u;
-          }
+          for (int kk = 0; kk < 8; ++kk)
+            umma_pair(d1, a + (uint64_t)(kk * (4096 >> 4)),
+                      b_c0 + (uint64_t)((2 * h + (kk >> 2)) * (16384 >> 4) + 2 * (kk & 3)), idesc_c, (h > 0 || kk > 0) ? 1u : 0u);
         }
-        umma_commit_pair(de0 + 8u * d.s);
-        d.next(kPDStages);
+        umma_commit_pair(e0 + 8u * p.s);
+        p.next();
       }
+      umma_commit_pair(smem_u32(&bars->acc_full));
+    }
+#pragma unroll
+    for (int t = 0; t < 2; ++t) {                                    // (B0, A0), (B1, A1)
+      const RingPos pb = p;
+      p.next();
+      const RingPos pa = p;
+      p.next();
+      mbar_wait_spin(f0 + 8u * pb.s, pb.ph);
+      mbar_wait_spin(f0 + 8u * pa.s, pa.ph);
+      tc_fence_after();
+      if (!no_mma) {
+        const uint64_t a = mn0 + (uint64_t)(pa.s * (uint32_t)(kPSlotBytes >> 4));
+        const uint64_t b = mn0 + (uint64_t)(pb.s * (uint32_t)(kPSlotBytes >> 4));
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk) {
+          umma_pair(d2, a + (uint64_t)(kk * (256 >> 4)), b + (uint64_t)(kk * (256 >> 4)), idesc_d, dacc);
+          dacc = 1u;
+        }
+      }
+      umma_commit_pair(e0 + 8u * pb.s);
+      umma_commit_pair(e0 + 8u * pa.s);
     }
   }
   umma_commit_pair(smem_u32(&bars->fin));
 }
 
-// ---- bias-gradient warps (18, 19): column sums of the dZ slabs this CTA streams (its 128 features) -----------------------------
+// ---- bias-gradient warps (18, 19): column sums of the dZ pieces this CTA streams (its feature half) ---------------------------
+// They follow EVERY item of the ring (one arrival per warp on every slot's empty barrier keeps its count uniform) and read
+// the B items.
+template <bool kChain>
 __device__ __forceinline__ void pipe_bias(const PipeGroup& G, PipeBars* bars, uint32_t sbase, int tid64, int lane,
-                                          int64_t s_first, int64_t s_step, int64_t n_super, float* s0_out, float* s1_out) {
+                                          int64_t s_first, int64_t s_step, int64_t n_super, float* s0_out, float* s1_out,
+                                          uint32_t dbg) {
   // thread owns feature columns 2 tid64, 2 tid64 + 1 of this CTA's half = chunk tid64 / 4, 32-bit word tid64 % 4
   const bool col_ok = 2 * tid64 < (int)G.b_chunks * 8;
   const uint32_t rot = (uint32_t)(tid64 >> 2) & 7u;
   float s0 = 0.f, s1 = 0.f;
-  RingPos d{0, 0};
+  RingPos p{0, 0};
   for (int64_t s = s_first; s < n_super; s += s_step) {
-    for (int j = 0; j < 4; ++j) {
-      mbar_wait(smem_u32(&bars->dfull[d.s]), d.ph);
-      if (col_ok) {
-        const uint32_t pb = sbase + kPD + d.s * kPDBytes + 16384u + (uint32_t)(tid64 >> 2) * 1024u + (uint32_t)(tid64 & 3) * 4u;
+#pragma unroll 1
+    for (int it = kChain ? 0 : 2; it < 6; ++it) {
+      mbar_wait(smem_u32(&bars->full[p.s]), p.ph);
+      if ((it == IT_B0 || it == IT_B1) && col_ok && !(dbg & kDbgNoBiasSum)) {
+        const uint32_t pb = sbase + kPRing + p.s * kPSlotBytes + (uint32_t)(tid64 >> 2) * 2048u + (uint32_t)(tid64 & 3) * 4u;
         float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f;
 #pragma unroll 8
-        for (uint32_t i = 0; i < 64; i += 2) {
-          const uint32_t w0 = lds32u(pb + (((i + rot) & 63u) << 4));
-          const uint32_t w1 = lds32u(pb + (((i + 1 + rot) & 63u) << 4));
+        for (uint32_t i = 0; i < 128; i += 2) {
+          const uint32_t w0 = lds32u(pb + (((i + rot) & 127u) << 4));
+          const uint32_t w1 = lds32u(pb + (((i + 1 + rot) & 127u) << 4));
           a0 += __uint_as_float(w0 << 16);
           a1 += __uint_as_float(w0 & 0xffff0000u);
           b0 += __uint_as_float(w1 << 16);
@@ -241,8 +226,8 @@ __device__ __forceinline__ void pipe_bias(const PipeGroup& G, PipeBars* bars, ui
         s1 += a1 + b1;
       }
       __syncwarp();
-      if (lane == 0) mbar_arrive(smem_u32(&bars->dempty[d.s]));
-      d.next(kPDStages);
+      if (lane == 0) mbar_arrive(smem_u32(&bars->empty[p.s]));
+      p.next();
     }
   }
   *s0_out = s0;
@@ -277,8 +262,7 @@ mlp_tc_bwd_pipe_kernel(const __grid_constant__ PipePlan plan, const uint8_t* __r
   if (threadIdx.x == 0) {
     const uint32_t full_count = rank == 0 ? 2u : 1u;       // the leader's copy also counts the peer's relay
     mbar_init(smem_u32(&bars->wfull), full_count);
-    for (int i = 0; i < kPCStages; ++i) { mbar_init(smem_u32(&bars->cfull[i]), full_count); mbar_init(smem_u32(&bars->cempty[i]), 1); }
-    for (int i = 0; i < kPDStages; ++i) { mbar_init(smem_u32(&bars->dfull[i]), full_count); mbar_init(smem_u32(&bars->dempty[i]), 3); }
+    for (int i = 0; i < kPSlots; ++i) { mbar_init(smem_u32(&bars->full[i]), full_count); mbar_init(smem_u32(&bars->empty[i]), 3); }
     mbar_init(smem_u32(&bars->acc_full), 1);
     mbar_init(smem_u32(&bars->acc_empty), 2 * 16);          // one arrive per epilogue warp of BOTH CTAs
     mbar_init(smem_u32(&bars->fin), 1);
@@ -294,8 +278,10 @@ mlp_tc_bwd_pipe_kernel(const __grid_constant__ PipePlan plan, const uint8_t* __r
   float* part = scratch + (size_t)pair * kDwPartialFloats;   // this pair's split-K partial: [256 k][256 n] fp32 + 256 bias sums
 
   if (warp == kWarpProducer) {
-    if (chain) pipe_producer<true>(G, bars, sbase, rank, lane, packed, saved, dz_ws, flags, s_first, s_step, n_super, dbg);
-    else pipe_producer<false>(G, bars, sbase, rank, lane, packed, saved, dz_ws, flags, s_first, s_step, n_super, dbg);
+    if (lane < kPipeProdLanes) {
+      if (chain) pipe_producer<true>(G, bars, sbase, rank, lane, packed, saved, dz_ws, flags, s_first, s_step, n_super, dbg);
+      else pipe_producer<false>(G, bars, sbase, rank, lane, packed, saved, dz_ws, flags, s_first, s_step, n_super, dbg);
+    }
   } else if (warp == kWarpMma) {
     if (lane == 0) {
       if (rank == 0) {
@@ -309,7 +295,8 @@ mlp_tc_bwd_pipe_kernel(const __grid_constant__ PipePlan plan, const uint8_t* __r
   } else if (warp >= kWarpStore) {
     const int tid64 = (warp - kWarpStore) * 32 + lane;
     float s0, s1;
-    pipe_bias(G, bars, sbase, tid64, lane, s_first, s_step, n_super, &s0, &s1);
+    if (chain) pipe_bias<true>(G, bars, sbase, tid64, lane, s_first, s_step, n_super, &s0, &s1, dbg);
+    else pipe_bias<false>(G, bars, sbase, tid64, lane, s_first, s_step, n_super, &s0, &s1, dbg);
     if (active && 2 * tid64 < (int)G.b_chunks * 8) {
       part[256 * 256 + rank * (int)G.b_chunks * 8 + 2 * tid64] = s0;
       part[256 * 256 + rank * (int)G.b_chunks * 8 + 2 * tid64 + 1] = s1;
@@ -350,7 +337,7 @@ mlp_tc_bwd_pipe_kernel(const __grid_constant__ PipePlan plan, const uint8_t* __r
                 const float a = __uint_as_float(acc[j][8 * g8 + i]);
                 v[i] = pipe_mask_bit(mw[j], 8 * g8 + i) ? a : alpha * a;
               }
-              stg128(gout + rbcm_offset(r, cq * 8 + j * 4 + g8, 32),
+              stg128(gout + tcm_offset(r, cq * 8 + j * 4 + g8),
                      make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7])));
             }
           }
@@ -450,7 +437,7 @@ static void fill_layer_group(PipeGroup* G, int l) {
   G->out_off = dz_panel(l) * kPanelBytes;
 }
 
-// Dense 8 + sigma head, h8 rows: dW only (A = h8, B = dZ_L' incl. the sigma column: N = 144, 72 features per CTA)
+// Dense 8 + sigma head, h8 rows: dW only (A = h8, B = dZ_L' incl. the sigma column: N = 144, 72 features = 9 chunks per CTA)
 static void fill_head_group(PipeGroup* G) {
   memset(G, 0, sizeof(*G));
   G->role = PIPE_ROLE_DW_ONLY;

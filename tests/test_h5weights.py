@@ -65,3 +65,29 @@ def test_reads_the_checkpoint_the_reference_trained(tmp_path):
     from conftest import ROOT
     pin = np.load(os.path.join(ROOT, "tests", "golden", "alexander50_pin.npz"))
     assert np.array_equal(pin["params_coarse"], pc) and np.array_equal(pin["params_fine"], pf)
+
+
+def test_written_checkpoint_opens_with_libhdf5(tmp_path):
+    """Opt-in cross-check of the hand-written HDF5 writer with the real library (h5py / libhdf5 are not in this image, so
+    the test skips here; anywhere they exist it opens a written file and compares names, shapes and values)."""
+    h5py = pytest.importorskip("h5py")
+    import importlib
+    h5w = importlib.import_module("nerf-and-dietnerf_b200.h5weights")
+    net = importlib.import_module("nerf-and-dietnerf_b200.network")
+    ncfg = importlib.import_module("nerf-and-dietnerf_b200._lib").NetCfg(5, 4, 2, 256, 128, 0.05)
+    shapes = net.layer_shapes(ncfg)
+    n = sum(i * o + o for i, o in shapes)
+    rng = np.random.default_rng(0)
+    pc, pf = rng.standard_normal(n).astype(np.float32), rng.standard_normal(n).astype(np.float32)
+    path = tmp_path / "NeRF_model_epoch_001.h5"
+    h5w.save_flat_params(str(path), pc, pf, shapes)
+    found = {}
+    with h5py.File(path, "r") as f:
+        f.visititems(lambda name, obj: found.__setitem__(name, np.asarray(obj)) if isinstance(obj, h5py.Dataset) else None)
+        assert "layer_names" in f.attrs
+    kernels = sorted(k for k in found if k.endswith("kernel:0"))
+    assert len(kernels) == 2 * len(shapes)
+    back_c, back_f = h5w.load_flat_params(str(path))
+    assert np.array_equal(back_c, pc) and np.array_equal(back_f, pf)
+    total = sum(v.size for v in found.values())
+    assert total == 2 * n

@@ -1087,10 +1087,21 @@ def test_bwd_pipe_stage_matches_chain_and_dw(pkg, n_rays, s):
     call("nerf_mlp_bwd", net.cfg_ref, ptr(net.params), ptr(packed), None, None, ptr(saved), ptr(d_out), m, ptr(ref), None,
          ptr(ws), net.mode_id)
     torch.cuda.synchronize()
+    import os
+    import sys
+    from conftest import ROOT
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    from tcm_layout import DZ_BLOCKS, DZ_TILE_BYTES, SAVED_BLOCKS, SAVED_TILE_BYTES, to_tcm
     tiles4 = ((m + 127) // 128 + 3) // 4 * 4
-    tile_bytes = 40 * 16384
+    tile_bytes = DZ_TILE_BYTES
     base = (-ws.data_ptr()) % 1024
     region = slice(base, base + tiles4 * tile_bytes)
+    # the stage works on tile chunk-major (TCM) blocks: re-lay the production kernels' RBCM buffers
+    ws_tcm = ws.clone()
+    ws_tcm[region] = to_tcm(ws[region], tiles4, DZ_TILE_BYTES, DZ_BLOCKS)
+    saved_tcm = saved.clone()
+    saved_tcm[:tiles4 * SAVED_TILE_BYTES] = to_tcm(saved[:tiles4 * SAVED_TILE_BYTES], tiles4, SAVED_TILE_BYTES, SAVED_BLOCKS)
+    ws, saved = ws_tcm, saved_tcm
     shapes = [(33, 256)] + [(256, 256)] * 3 + [(289, 256)] + [(256, 256)] * 3 + [(280, 128), (128, 3), (280, 1)]
     offs, off = [], 0
     for i, o in shapes:
@@ -1283,3 +1294,25 @@ def test_fused_coarse_pass_draws_the_same_depths(pkg, mode, n_rays, s):
     assert torch.equal(out, out_ref)
     jit = O.stratified_jitter(9, 4, n_rays, s, ray_offset=1000)
     assert torch.equal(z.cpu(), O.get_z_values(NEAR, FAR, n_rays, s, jit)), "Philox stream differs from the oracle's"
+
+
+def test_two_devices_in_one_process(pkg):
+    """The ABI's per-device state (SM count, the kernels' shared-memory attribute: csrc/api.cu device_first_use) with two
+    GPUs driven from ONE process: the second device's first tensor-core call must not inherit 'already configured' from
+    the first.  Same seeds -> bit-identical renders and train steps on both devices."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs in one process")
+    outs = []
+    for dev_id in (0, 1):
+        with torch.cuda.device(dev_id):
+            model = pkg.NeRFModel(net_config(), render_config(), NEAR, FAR, seed=5, device=torch.device("cuda", dev_id))
+            model.compile(optimizer=pkg.Adam(5e-4))
+            o, d = random_rays(300, 3)
+            y = torch.rand(300, 3, generator=torch.Generator().manual_seed(1))
+            o, d, y = o.to(f"cuda:{dev_id}"), d.to(f"cuda:{dev_id}"), y.to(f"cuda:{dev_id}")
+            rgb = model.render(o, d, seed=7, step=0)[0]
+            m = model.train_step_local(o, d, y, 300)
+            torch.cuda.synchronize(dev_id)
+            outs.append((rgb.cpu(), m["loss"].cpu(), model.model_coarse.params.cpu()))
+    for a, b in zip(outs[0], outs[1]):
+        assert torch.equal(a, b)

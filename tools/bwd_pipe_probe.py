@@ -8,11 +8,13 @@ import sys
 
 import torch
 
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 pkg = importlib.import_module("nerf-and-dietnerf_b200")
 
-DZ_TILE_BYTES = 40 * 16384
+from tcm_layout import DZ_BLOCKS, DZ_TILE_BYTES, SAVED_BLOCKS, SAVED_TILE_BYTES, to_tcm  # noqa: E402
+
 SHAPES = [(33, 256)] + [(256, 256)] * 3 + [(289, 256)] + [(256, 256)] * 3 + [(280, 128), (128, 3), (280, 1)]
 
 
@@ -54,6 +56,12 @@ def main():
     tiles4 = ((m + 127) // 128 + 3) // 4 * 4
     base = (-ws.data_ptr()) % 1024
     region = slice(base, base + tiles4 * DZ_TILE_BYTES)
+    # the stage reads and writes tile chunk-major (TCM) blocks: re-lay the chain kernel's RBCM output and the saved activations
+    ws_tcm = ws.clone()
+    ws_tcm[region] = to_tcm(ws[region], tiles4, DZ_TILE_BYTES, DZ_BLOCKS)
+    saved_tcm = saved.clone()
+    saved_tcm[:tiles4 * SAVED_TILE_BYTES] = to_tcm(saved[:tiles4 * SAVED_TILE_BYTES], tiles4, SAVED_TILE_BYTES, SAVED_BLOCKS)
+    ws, saved = ws_tcm, saved_tcm
     sl = dense_slices()
     for layer in [int(x) for x in args.layers.split(",")]:
         ws2 = ws.clone()
