@@ -135,7 +135,10 @@ __device__ __forceinline__ void pipe_mma(const PipeGroup& G, PipeBars* bars, uin
                                          int64_t s_first, int64_t s_step, int64_t n_super, uint32_t dbg) {
   const uint32_t idesc_c = make_idesc(G.n_chain, 0, 0, 1, 256);
   const uint32_t idesc_d = make_idesc(G.n_dw, 1, 1, 1, 256);
-  const uint32_t d1 = tmem_base, d2 = tmem_base + 256u;
+  // the whole warp runs this loop (see elect_one); the CTA pair owns all 512 TMEM columns, so its base is column 0 (checked
+  // by the caller) and the accumulator addresses are literals
+  (void)tmem_base;
+  const uint32_t d1 = 0u, d2 = 256u;
   const uint64_t a_c0 = make_desc_k_nosw(sbase + kPRing, 2048, 128);    // chain A: [16 chunks][128 rows][16 B]
   const uint64_t b_c0 = make_desc_kmajor(sbase + kPW);                  // chain B: resident swizzled W chunks
   const uint64_t mn0 = make_desc_mn_nosw(sbase + kPRing, 128, 2048);    // dW A / B: [chunk][128 rows][16 B], K = rows
@@ -147,27 +150,36 @@ __device__ __forceinline__ void pipe_mma(const PipeGroup& G, PipeBars* bars, uin
   }
   RingPos p{0, 0};
   uint32_t it = 0, dacc = 0;
+  const bool timing = (dbg & kDbgTiming) != 0 && s_first == 0;
+  long long t_acc = 0, t_c = 0, t_d = 0, t0 = clock64();
   for (int64_t s = s_first; s < n_super; s += s_step, ++it) {
     if (kChain) {
       if (it > 0) {
+        const long long ta = timing ? clock64() : 0;
         mbar_wait_spin(smem_u32(&bars->acc_empty), (it - 1) & 1u);   // both CTAs drained D1 of the previous super-tile
         tc_fence_after();
+        if (timing) t_acc += clock64() - ta;
       }
 #pragma unroll
       for (int h = 0; h < 2; ++h) {                                  // c01, c23: two K panels each
+        const long long ta = timing ? clock64() : 0;
         mbar_wait_spin(f0 + 8u * p.s, p.ph);
         tc_fence_after();
-        if (!no_mma) {
-          const uint64_t a = a_c0 + (uint64_t)(p.s * (uint32_t)(kPSlotBytes >> 4));
+        if (timing) t_c += clock64() - ta;
+        if (elect_one()) {
+          if (!no_mma) {
+            const uint64_t a = a_c0 + (uint64_t)(p.s * (uint32_t)(kPSlotBytes >> 4));
 #pragma unroll
-          for (int kk = 0; kk < 8; ++kk)
-            umma_pair(d1, a + (uint64_t)(kk * (4096 >> 4)),
-                      b_c0 + (uint64_t)((2 * h + (kk >> 2)) * (16384 >> 4) + 2 * (kk & 3)), idesc_c, (h > 0 || kk > 0) ? 1u : 0u);
+            for (int kk = 0; kk < 8; ++kk)
+              umma_pair(d1, a + (uint64_t)(kk * (4096 >> 4)),
+                        b_c0 + (uint64_t)((2 * h + (kk >> 2)) * (16384 >> 4) + 2 * (kk & 3)), idesc_c, (h > 0 || kk > 0) ? 1u : 0u);
+          }
+          umma_commit_pair(e0 + 8u * p.s);
+          if (h == 1) umma_commit_pair(smem_u32(&bars->acc_full));
         }
-        umma_commit_pair(e0 + 8u * p.s);
+        __syncwarp();
         p.next();
       }
-      umma_commit_pair(smem_u32(&bars->acc_full));
     }
 #pragma unroll
     for (int t = 0; t < 2; ++t) {                                    // (B0, A0), (B1, A1)
@@ -175,23 +187,31 @@ __device__ __forceinline__ void pipe_mma(const PipeGroup& G, PipeBars* bars, uin
       p.next();
       const RingPos pa = p;
       p.next();
+      const long long ta = timing ? clock64() : 0;
       mbar_wait_spin(f0 + 8u * pb.s, pb.ph);
       mbar_wait_spin(f0 + 8u * pa.s, pa.ph);
       tc_fence_after();
-      if (!no_mma) {
-        const uint64_t a = mn0 + (uint64_t)(pa.s * (uint32_t)(kPSlotBytes >> 4));
-        const uint64_t b = mn0 + (uint64_t)(pb.s * (uint32_t)(kPSlotBytes >> 4));
+      if (timing) t_d += clock64() - ta;
+      if (elect_one()) {
+        if (!no_mma) {
+          const uint64_t a = mn0 + (uint64_t)(pa.s * (uint32_t)(kPSlotBytes >> 4));
+          const uint64_t b = mn0 + (uint64_t)(pb.s * (uint32_t)(kPSlotBytes >> 4));
 #pragma unroll
-        for (int kk = 0; kk < 8; ++kk) {
-          umma_pair(d2, a + (uint64_t)(kk * (256 >> 4)), b + (uint64_t)(kk * (256 >> 4)), idesc_d, dacc);
-          dacc = 1u;
+          for (int kk = 0; kk < 8; ++kk)
+            umma_pair(d2, a + (uint64_t)(kk * (256 >> 4)), b + (uint64_t)(kk * (256 >> 4)), idesc_d, (dacc | (uint32_t)kk) ? 1u : 0u);
         }
+        umma_commit_pair(e0 + 8u * pb.s);
+        umma_commit_pair(e0 + 8u * pa.s);
       }
-      umma_commit_pair(e0 + 8u * pb.s);
-      umma_commit_pair(e0 + 8u * pa.s);
+      __syncwarp();
+      dacc = 1u;
     }
   }
-  umma_commit_pair(smem_u32(&bars->fin));
+  if (elect_one()) umma_commit_pair(smem_u32(&bars->fin));
+  __syncwarp();
+  if (timing && (threadIdx.x & 31) == 0)
+    printf("pipe mma (layer %d): %u super-tiles, %lld cycles each; waits per super-tile: acc_empty %lld, chain items %lld, dW items %lld\n",
+           (int)G.layer, it, (clock64() - t0) / it, t_acc / it, t_c / it, t_d / it);
 }
 
 // ---- bias-gradient warps (18, 19): column sums of the dZ pieces this CTA streams (its feature half) ---------------------------
@@ -283,14 +303,13 @@ mlp_tc_bwd_pipe_kernel(const __grid_constant__ PipePlan plan, const uint8_t* __r
       else pipe_producer<false>(G, bars, sbase, rank, lane, packed, saved, dz_ws, flags, s_first, s_step, n_super, dbg);
     }
   } else if (warp == kWarpMma) {
-    if (lane == 0) {
-      if (rank == 0) {
-        if (chain) pipe_mma<true>(G, bars, sbase, tmem_base, s_first, s_step, n_super, dbg);
-        else pipe_mma<false>(G, bars, sbase, tmem_base, s_first, s_step, n_super, dbg);
-      } else {
-        if (chain) pipe_relay<true>(bars, s_first, s_step, n_super);
-        else pipe_relay<false>(bars, s_first, s_step, n_super);
-      }
+    if (rank == 0) {
+      if (tmem_base != 0u) __trap();                   // 512 of 512 columns: the allocation starts at column 0
+      if (chain) pipe_mma<true>(G, bars, sbase, tmem_base, s_first, s_step, n_super, dbg);
+      else pipe_mma<false>(G, bars, sbase, tmem_base, s_first, s_step, n_super, dbg);
+    } else if (lane == 0) {
+      if (chain) pipe_relay<true>(bars, s_first, s_step, n_super);
+      else pipe_relay<false>(bars, s_first, s_step, n_super);
     }
   } else if (warp >= kWarpStore) {
     const int tid64 = (warp - kWarpStore) * 32 + lane;
@@ -316,8 +335,10 @@ mlp_tc_bwd_pipe_kernel(const __grid_constant__ PipePlan plan, const uint8_t* __r
         uint32_t mw[2];
 #pragma unroll
         for (int j = 0; j < 2; ++j) mw[j] = __ldg(saved_mask + ((int)G.mask_row * 8 + cq * 2 + j) * 128 + r);
+        const long long te0 = (dbg & kDbgTiming) ? clock64() : 0;
         mbar_wait(smem_u32(&bars->acc_full), it & 1u);
         tc_fence_after();
+        const long long te1 = (dbg & kDbgTiming) ? clock64() : 0;
         uint32_t acc[2][32];
         tmem_ld32(taddr + cq * 64, acc[0]);
         tmem_ld32(taddr + cq * 64 + 32, acc[1]);
@@ -327,18 +348,27 @@ mlp_tc_bwd_pipe_kernel(const __grid_constant__ PipePlan plan, const uint8_t* __r
         if (lane == 0) mbar_arrive_cluster(acc_empty_leader);       // D1 may be overwritten by the next super-tile
         uint8_t* gout = dz_ws + (size_t)((dbg & kDbgWrapDz) ? 2 * (s & 127) + rank : tile) * kDzTileBytes + (size_t)G.out_off;
         if (!(dbg & kDbgNoStore)) {
+          // experiments (bits 13..15): math but no store / raw accumulator words stored without math / half of the stores
+          const bool x_math_only = (dbg & 8192u) != 0, x_raw = (dbg & 16384u) != 0, x_half = (dbg & 32768u) != 0;
 #pragma unroll
           for (int j = 0; j < 2; ++j) {
 #pragma unroll
             for (int g8 = 0; g8 < 4; ++g8) {
+              if (x_raw) {
+                stg128(gout + tcm_offset(r, cq * 8 + j * 4 + g8),
+                       make_uint4(acc[j][8 * g8], acc[j][8 * g8 + 1], acc[j][8 * g8 + 2], acc[j][8 * g8 + 3]));
+                continue;
+              }
               float v[8];
 #pragma unroll
               for (int i = 0; i < 8; ++i) {
                 const float a = __uint_as_float(acc[j][8 * g8 + i]);
                 v[i] = pipe_mask_bit(mw[j], 8 * g8 + i) ? a : alpha * a;
               }
+              if (x_math_only ? (v[0] + v[3] + v[5] + v[7] == 1.2345e-33f) : (x_half ? (g8 & 1) == 0 : true))
               stg128(gout + tcm_offset(r, cq * 8 + j * 4 + g8),
                      make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7])));
+              if (dbg >> 16) __nanosleep(dbg >> 16);       // experiment: pace the store burst (ns between a warp's stores)
             }
           }
         }
@@ -346,6 +376,9 @@ mlp_tc_bwd_pipe_kernel(const __grid_constant__ PipePlan plan, const uint8_t* __r
           __syncwarp();
           if (lane == 0) flag_signal(flags + (size_t)s * kPipeFlagsPerSuper + G.signal_flag);
         }
+        if ((dbg & kDbgTiming) && s_first == 0 && threadIdx.x == 0 && rank == 0 && it == 8)
+          printf("pipe epilogue (layer %d, super-tile %u): waited %lld cycles for the accumulator, then %lld cycles of loads, math and stores\n",
+                 (int)G.layer, it, te1 - te0, clock64() - te1);
       }
     }
     // ---- drain this CTA's half of the dW accumulator: rows k = 128 rank + lane, this warp's 64 columns ----
@@ -482,6 +515,33 @@ int mlp_tc_bwd_pipe_single(const nerf_net_cfg* cfg, const NetGeom& g, const uint
   return pipe_launch(plan, g, packed_bwd, saved, dz_ws, m, scratch, nullptr, grads, cfg->leaky_alpha, st);
 }
 
+// Diagnostic: the layer groups hi, hi - 1, ..., lo (7 >= hi >= lo >= 1) in ONE launch, the CTA pairs split evenly over them;
+// dZ_{hi+1} comes from the workspace, every other dZ is handed from group to group through the ready counters.
+int mlp_tc_bwd_pipe_range(const nerf_net_cfg* cfg, const NetGeom& g, const uint8_t* packed_bwd, const void* saved, int64_t m,
+                          void* workspace, int hi, int lo, float* grads, cudaStream_t st) {
+  PipePlan plan;
+  memset(&plan, 0, sizeof(plan));
+  const int n_groups = hi - lo + 1, pairs = num_sms() / 2;
+  plan.n_groups = n_groups;
+  int first = 0;
+  for (int i = 0; i < n_groups; ++i) {
+    const int l = hi - i;
+    PipeGroup& G = plan.g[i];
+    fill_layer_group(&G, l);
+    G.first_pair = (int16_t)first;
+    G.n_pairs = (int16_t)(pairs / n_groups + (i < pairs % n_groups ? 1 : 0));
+    first += G.n_pairs;
+    G.wait_flag = (int16_t)(i == 0 ? -1 : l + 1);
+    G.signal_flag = (int16_t)(i == n_groups - 1 ? -1 : l);
+  }
+  uint8_t* dz_ws = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(workspace) + 1023) & ~(uintptr_t)1023);
+  const int64_t tiles4 = ((m + kTileM - 1) / kTileM + 3) / 4 * 4;
+  float* scratch = reinterpret_cast<float*>(dz_ws + tiles4 * (int64_t)kDzTileBytes);
+  uint32_t* flags = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(scratch) + kDwScratchBytes);
+  NERF_CUDA(cudaMemsetAsync(flags, 0, (size_t)(tiles4 / 2) * kPipeFlagsPerSuper * sizeof(uint32_t), st));
+  return pipe_launch(plan, g, packed_bwd, saved, dz_ws, m, scratch, flags, grads, cfg->leaky_alpha, st);
+}
+
 }  // namespace nerf
 
 using namespace nerf;
@@ -492,7 +552,10 @@ extern "C" int nerf_debug_bwd_pipe_layer(const nerf_net_cfg* cfg, const void* pa
   TcPlan fplan;
   NERF_CHECK_ARG(make_geom(cfg, &g) && make_plan(g, &fplan) && g.view, "the pipe prototype handles the view-direction network");
   NERF_CHECK_ARG(packed && saved && workspace && grads, "null pointer");
-  NERF_CHECK_ARG(layer >= 1 && layer <= 8 && m > 0, "layer must be 1..8");
+  const int hi = layer / 100, lo = layer % 100;
+  NERF_CHECK_ARG(m > 0 && (hi == 0 ? (layer >= 1 && layer <= 8) : (hi <= 7 && lo >= 1 && hi > lo)),
+                 "layer must be 1..8, or 100 hi + lo for the groups hi..lo of one launch");
   const uint8_t* packed_bwd = (const uint8_t*)packed + ((fplan.total_bytes + 1023u) & ~1023u);
+  if (hi) return mlp_tc_bwd_pipe_range(cfg, g, packed_bwd, saved, m, workspace, hi, lo, grads, (cudaStream_t)stream);
   return mlp_tc_bwd_pipe_single(cfg, g, packed_bwd, saved, m, workspace, layer, grads, (cudaStream_t)stream);
 }

@@ -189,6 +189,18 @@ __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
 
+// One lane of a CONVERGED warp (elect.sync): the warp runs the issue loop together so that ring positions, descriptors and
+// barrier addresses stay in uniform registers; under `if (lane == 0)` the same code is divergent for the compiler and every
+// tcgen05.mma pays an ELECT / R2UR.BROADCAST waterfall loop (~14 instructions, three dependent R2URs) for its descriptors.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
 // CTA-pair MMA (M = 256: 128 rows per CTA; each CTA supplies its own A rows and N/2 rows of B from the SAME smem offsets).
 // Issued by one thread of the leader CTA (cluster rank 0) only.
 __device__ __forceinline__ void umma_pair(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {

@@ -67,17 +67,26 @@ def main():
         ws2 = ws.clone()
         # same alignment offset as the original (clone keeps 256-byte alignment classes in practice; assert it)
         assert (-ws2.data_ptr()) % 1024 == base, "clone changed the 1024-byte phase of the workspace"
-        if 1 <= layer <= 7:                 # wipe dZ_layer so that equality proves the stage wrote it
+        hi, lo = (layer // 100, layer % 100) if layer >= 100 else (layer, layer)
+        if 1 <= layer <= 7 or layer >= 100:  # wipe the dZ blocks the launch produces so that equality proves it wrote them
             v = ws2[region].view(tiles4, DZ_TILE_BYTES)
-            v[:, (layer - 1) * 65536:layer * 65536] = 0x7f
+            v[:, (lo - 1) * 65536:hi * 65536] = 0x7f
         grads = torch.zeros(net.n_params, device="cuda")
         call("nerf_debug_bwd_pipe_layer", net.cfg_ref, ptr(packed), ptr(saved), m, ptr(ws2), layer, ptr(grads))
         torch.cuda.synchronize()
         same = torch.equal(ws2[region], ws[region])
         nbad = (ws2[region] != ws[region]).sum().item() if not same else 0
-        w0, w1, b1 = sl[layer]
-        gw, gb = grads[w0:w1], grads[w1:b1]
-        rw, rb = grads_ref[w0:w1], grads_ref[w1:b1]
+        if layer >= 100:
+            parts = []
+            for l in range(lo, hi + 1):
+                w0, w1, b1 = sl[l]
+                skip = 33 * 256 if l == 4 else 0
+                parts.append((grads[w0 + skip:w1], grads[w1:b1], grads_ref[w0 + skip:w1], grads_ref[w1:b1]))
+            gw, gb, rw, rb = (torch.cat([p[i] for p in parts]) for i in range(4))
+        else:
+            w0, w1, b1 = sl[layer]
+            gw, gb = grads[w0:w1], grads[w1:b1]
+            rw, rb = grads_ref[w0:w1], grads_ref[w1:b1]
         if layer == 4:      # the stage covers the h4 rows of Dense 4 (rows 33..288)
             gw, rw = gw[33 * 256:], rw[33 * 256:]
         if layer == 8:      # h8 rows of Dense 8; the sigma head's h8 rows are checked separately
@@ -102,7 +111,7 @@ def main():
         torch.cuda.synchronize()
         ts = sorted(a.elapsed_time(b) for a, b in evs)
         med = ts[len(ts) // 2]
-        flops = (4 if layer <= 7 else 2 * 144 / 256) * 256 * 256 * m
+        flops = (4 * (hi - lo + 1) if layer != 8 else 2 * 144 / 256) * 256 * 256 * m
         print(f"layer {layer} M={m}: dZ region equal {same} (bad bytes {nbad})  dW rel {rel_w:.2e}  db rel {rel_b:.2e}{extra}  "
               f"{med * 1e3:7.1f} us  {flops / med / 1e9:7.1f} TFLOP/s", flush=True)
 

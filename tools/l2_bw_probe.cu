@@ -63,6 +63,81 @@ __global__ void __launch_bounds__(32, 1) probe(const uint8_t* __restrict__ base,
   if (lane == 0) cycles[blockIdx.x] = clock64() - t0;
 }
 
+// Loads and stores at the same time: warp 0 streams 32 KB bulk copies (as above), `store_warps` more warps write
+// 512-byte warp stores (st.global.v4, what the epilogues of the MLP kernels issue) into an L2-resident window of their own.
+// Each role reports its own cycle count: do the SM's load requests and its store data share a path?
+__global__ void __launch_bounds__(32 * 17, 1) probe_ls(const uint8_t* __restrict__ base, size_t slice_bytes, int n_chunks,
+                                                       uint8_t* __restrict__ st_base, size_t st_slice, long long st_iters,
+                                                       int store_warps, long long* cyc_load, long long* cyc_store) {
+  constexpr int kChunk = 32768, kStages = 5;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint64_t full[kStages];
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kStages; ++s) mbar_init(smem_u32(&full[s]), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long t0 = clock64();
+  if (warp == 0) {
+    const uint8_t* src = base + (size_t)blockIdx.x * slice_bytes;
+    const size_t per_slice = slice_bytes / kChunk;
+    for (int i = 0; i < n_chunks + kStages; ++i) {
+      const int s = i % kStages;
+      if (i >= kStages) {
+        const uint32_t ph = ((i - kStages) / kStages) & 1u;
+        if (lane == 0) while (!mbar_try_wait(smem_u32(&full[s]), ph)) {}
+        __syncwarp();
+      }
+      if (i < n_chunks && lane == 0) {
+        mbar_arrive_expect_tx(smem_u32(&full[s]), kChunk);
+        bulk_g2s(smem_u32(smem) + s * kChunk, src + (size_t)(i % per_slice) * kChunk, kChunk, smem_u32(&full[s]));
+      }
+    }
+    if (lane == 0) cyc_load[blockIdx.x] = clock64() - t0;
+  } else if (warp <= store_warps) {
+    uint8_t* dst = st_base + (size_t)blockIdx.x * st_slice + (size_t)(warp - 1) * 512 + lane * 16;
+    const size_t stride = (size_t)store_warps * 512, wrap = st_slice / stride;
+    for (long long i = 0; i < st_iters; ++i) {
+      const uint4 v = make_uint4((uint32_t)i, lane, warp, 7u);
+      asm volatile("st.global.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(dst + (size_t)(i % wrap) * stride), "r"(v.x), "r"(v.y), "r"(v.z),
+                   "r"(v.w) : "memory");
+    }
+    if (lane == 0 && warp == 1) cyc_store[blockIdx.x] = clock64() - t0;
+  }
+}
+
+static void run_ls(const uint8_t* buf, uint8_t* stbuf, int sms, long long* cyc, size_t load_mb, size_t store_mb, int store_warps,
+                   bool hbm_loads) {
+  cudaFuncSetAttribute(probe_ls, cudaFuncAttributeMaxDynamicSharedMemorySize, 5 * 32768);
+  const size_t slice = hbm_loads ? ((size_t)40 << 20) : (((size_t)48 << 20) / sms / 32768 * 32768);
+  const size_t st_slice = ((size_t)24 << 20) / sms / 8192 * 8192;
+  const int n_chunks = (int)((load_mb << 20) / 32768);
+  const long long st_iters = store_warps ? (long long)((store_mb << 20) / ((size_t)store_warps * 512)) : 0;
+  long long h[2][160];
+  for (int rep = 0; rep < 2; ++rep) {
+    cudaMemset(cyc, 0, 2 * 160 * sizeof(long long));
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    cudaEventRecord(e0);
+    probe_ls<<<sms, 32 * 17, 5 * 32768>>>(buf, slice, n_chunks, stbuf, st_slice, st_iters, store_warps, cyc, cyc + 160);
+    cudaEventRecord(e1);
+    cudaError_t err = cudaDeviceSynchronize();
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    cudaMemcpy(h, cyc, sizeof(h), cudaMemcpyDeviceToHost);
+    if (rep == 1) {
+      double cl = 0, cs = 0;
+      for (int i = 0; i < sms; ++i) { cl += (double)h[0][i] / sms; cs += (double)h[1][i] / sms; }
+      printf("loads %4zu MB/SM (%s) + stores %4zu MB/SM by %2d warps: kernel %7.3f ms | load role %9.0f cycles = %5.1f B/clk/SM | "
+             "store role %9.0f cycles = %5.1f B/clk/SM  %s\n",
+             n_chunks ? load_mb : 0, hbm_loads ? "HBM" : "L2", store_warps ? store_mb : 0, store_warps, ms, cl,
+             cl > 0 ? (double)n_chunks * 32768 / cl : 0.0, cs, cs > 0 ? (double)st_iters * store_warps * 512 / cs : 0.0,
+             cudaGetErrorString(err));
+    }
+  }
+}
+
 template <int kChunk, int kLanes, int kRingBytes = kRing>
 static void run(const char* name, const uint8_t* buf, size_t slice, size_t stride, int sms, long long* cyc) {
   constexpr int kStage = kChunk * kLanes;
@@ -95,8 +170,23 @@ int main(int argc, char** argv) {
   if (cudaMalloc(&buf, big) != cudaSuccess) { printf("cudaMalloc failed\n"); return 1; }
   cudaMemset(buf, 1, big);
   long long* cyc;
-  cudaMalloc(&cyc, sms * sizeof(long long));
+  cudaMalloc(&cyc, 2 * 160 * sizeof(long long));
   const size_t l2 = ((size_t)64 << 20) / sms, hbm = (size_t)50 << 20;
+  if (argc > 1 && atoi(argv[1]) == 1) {
+    // loads and stores together (see probe_ls)
+    uint8_t* stbuf = buf + ((size_t)7 << 30);
+    printf("-- bulk loads alone, stores alone, both (5 x 32 KB in flight; stores = 512-byte warp stores into an L2-resident window)\n");
+    run_ls(buf, stbuf, sms, cyc, 96, 0, 0, false);
+    run_ls(buf, stbuf, sms, cyc, 0, 32, 16, false);
+    run_ls(buf, stbuf, sms, cyc, 0, 32, 4, false);
+    run_ls(buf, stbuf, sms, cyc, 96, 32, 16, false);
+    run_ls(buf, stbuf, sms, cyc, 96, 16, 16, false);
+    run_ls(buf, stbuf, sms, cyc, 96, 8, 16, false);
+    run_ls(buf, stbuf, sms, cyc, 96, 32, 4, false);
+    run_ls(buf, stbuf, sms, cyc, 96, 0, 0, true);
+    run_ls(buf, stbuf, sms, cyc, 96, 32, 16, true);
+    return 0;
+  }
   printf("bytes in flight per SM: %d\n", kRing);
   run<32768, 1>("distinct data, 64 MB window (L2-resident)", buf, l2, 1, sms, cyc);
   run<16384, 1>("distinct data, 64 MB window (L2-resident)", buf, l2, 1, sms, cyc);
