@@ -275,7 +275,7 @@ mlp_tc_fwd_kernel(const __grid_constant__ TcPlan plan, const uint8_t* __restrict
       mbar_init(smem_u32(&bars->act_ready[t]), 2 * 8);   // leader's copy: one arrive per epilogue warp of BOTH CTAs
       mbar_init(smem_u32(&bars->acc_full[t]), 1);
       mbar_init(smem_u32(&bars->panel_full[t]), 8);      // one arrive per epilogue warp of the tile
-      mbar_init(smem_u32(&bars->panel_free[t]), 2);      // both store warps
+      mbar_init(smem_u32(&bars->panel_free[t]), kStoreWarps);   // every store warp
     }
     fence_barrier_init();
   }
@@ -449,12 +449,13 @@ mlp_tc_fwd_kernel(const __grid_constant__ TcPlan plan, const uint8_t* __restrict
             mbar_wait(smem_u32(&bars->panel_full[t]), ph);
             if (do_store) {
 #pragma unroll 8
-              for (int it = 0; it < 64; ++it) {
-                const int j = hw * 16 + (it >> 2), r = (it & 3) * 32 + lane;     // 16-byte column chunk, row
+              for (int it = 0; it < 128 / kStoreWarps; ++it) {
+                const int j = hw * (32 / kStoreWarps) + (it >> 2), r = (it & 3) * 32 + lane;     // 16-byte column chunk, row
                 const float4 v = lds128f(act_u32 + (j >> 3) * kPanelBytes + r * 128 + (((j & 7) ^ (r & 7)) << 4));
                 uint4 w = make_uint4(__float_as_uint(v.x), __float_as_uint(v.y), __float_as_uint(v.z), __float_as_uint(v.w));
                 if (kHalf) w = half8_to_bf16(w);          // the backward reads bf16
                 stg128(gblock + rbcm_offset(r, j, 32), w);
+                if ((dbg >> 16) && (it & 7) == 7) __nanosleep(dbg >> 16);   // experiment: throttle the store stream
               }
             }
             __syncwarp();

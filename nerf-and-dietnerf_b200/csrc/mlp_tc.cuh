@@ -45,8 +45,12 @@ constexpr int kTmemBuffers = NERF_TMEM_BUFFERS;   // 2: tcgen05.ld of column gro
 constexpr int kEpiWarps = 16;                     // 8 per tile: 4 TMEM lane quarters x 2 column halves
 constexpr int kEpiThreadsPerTile = 256;
 constexpr int kWarpProducer = 16, kWarpMma = 17;
-constexpr int kWarpStore = 18;                    // warps 18, 19: train-mode copy of tile 0 / 1's panels to HBM (RBCM)
-constexpr int kThreadsFwd = 20 * 32;              // 5 warps per SM sub-partition: the register cap stays at 96
+constexpr int kWarpStore = 18;                    // warps 18 ...: train-mode copy of tile 0 / 1's panels to HBM (RBCM)
+#ifndef NERF_STORE_WARPS
+#define NERF_STORE_WARPS 2
+#endif
+constexpr int kStoreWarps = NERF_STORE_WARPS;     // every store warp works on every copy (32 / kStoreWarps column chunks each)
+constexpr int kThreadsFwd = (18 + kStoreWarps) * 32;   // 20 warps = 5 per SM sub-partition: the register cap stays at 96
 // Saved activations of one 128-row tile (forward -> backward), bf16:
 //   block 0            input panel (xyz | view encodings), [128 rows][64 cols] in the 128-byte-swizzled smem layout (16 KB)
 //   blocks h_1 .. h_9  64 KB each, "row-block chunk-major" (RBCM): [row half 0/1][16-byte column chunk j][row 0..63][8 cols].

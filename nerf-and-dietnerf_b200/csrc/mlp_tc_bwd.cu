@@ -35,7 +35,7 @@ namespace nerf {
 // flags[tile * kFlagsPerTile + b]: b = l - 1 for dZ_l (l = 1..9; two store warps -> target 2), b = 9 for the blocks the
 // chain prologue writes (dZ_L', dOut; eight epilogue warps -> target 8)
 constexpr int kFlagsPerTile = kHiddenSlots + 1;
-constexpr uint32_t kFlagTargetStore = 2, kFlagTargetPrologue = 8;
+constexpr uint32_t kFlagTargetStore = kStoreWarps, kFlagTargetPrologue = 8;
 constexpr int kBwdMaxChunks = 48;
 constexpr int kBwdMaxSteps = 12;
 enum : int { STEP_MASK = 0, STEP_XSTASH = 1, STEP_XFINAL = 2 };
@@ -253,7 +253,7 @@ mlp_tc_bwd_chain_kernel(const __grid_constant__ BwdPlan plan, const uint8_t* __r
       mbar_init(smem_u32(&bars->act_ready[t]), 2 * 8);    // leader's copy: one arrive per epilogue warp of BOTH CTAs
       mbar_init(smem_u32(&bars->acc_full[t]), 1);
       mbar_init(smem_u32(&bars->panel_full[t]), 8);
-      mbar_init(smem_u32(&bars->panel_free[t]), 2);       // both store warps
+      mbar_init(smem_u32(&bars->panel_free[t]), kStoreWarps);   // every store warp
     }
     fence_barrier_init();
   }
@@ -361,11 +361,12 @@ mlp_tc_bwd_chain_kernel(const __grid_constant__ BwdPlan plan, const uint8_t* __r
           mbar_wait(smem_u32(&bars->panel_full[t]), ph);
           if (do_store) {
 #pragma unroll 8
-            for (int it = 0; it < 64; ++it) {
-              const int j = hw * 16 + (it >> 2), r = (it & 3) * 32 + lane;     // 16-byte column chunk, row
+            for (int it = 0; it < 128 / kStoreWarps; ++it) {
+              const int j = hw * (32 / kStoreWarps) + (it >> 2), r = (it & 3) * 32 + lane;     // 16-byte column chunk, row
               const float4 v = lds128f(act_u32 + (j >> 3) * kPanelBytes + r * 128 + (((j & 7) ^ (r & 7)) << 4));
               stg128(gblock + rbcm_offset(r, j, 32),
                      make_uint4(__float_as_uint(v.x), __float_as_uint(v.y), __float_as_uint(v.z), __float_as_uint(v.w)));
+              if ((dbg >> 16) && (it & 7) == 7) __nanosleep(dbg >> 16);     // experiment: throttle the store stream
             }
           }
           __syncwarp();

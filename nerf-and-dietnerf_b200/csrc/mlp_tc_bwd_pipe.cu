@@ -311,6 +311,8 @@ mlp_tc_bwd_pipe_kernel(const __grid_constant__ PipePlan plan, const uint8_t* __r
       if (chain) pipe_relay<true>(bars, s_first, s_step, n_super);
       else pipe_relay<false>(bars, s_first, s_step, n_super);
     }
+  } else if (warp >= kWarpStore + 2) {
+    // (only two bias warps; further store warps of the forward / chain launch shape have nothing to do here)
   } else if (warp >= kWarpStore) {
     const int tid64 = (warp - kWarpStore) * 32 + lane;
     float s0, s1;

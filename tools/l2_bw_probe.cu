@@ -68,7 +68,7 @@ __global__ void __launch_bounds__(32, 1) probe(const uint8_t* __restrict__ base,
 // Each role reports its own cycle count: do the SM's load requests and its store data share a path?
 __global__ void __launch_bounds__(32 * 17, 1) probe_ls(const uint8_t* __restrict__ base, size_t slice_bytes, int n_chunks,
                                                        uint8_t* __restrict__ st_base, size_t st_slice, long long st_iters,
-                                                       int store_warps, long long* cyc_load, long long* cyc_store) {
+                                                       int store_warps, long long* cyc_load, long long* cyc_store, int st_kind) {
   constexpr int kChunk = 32768, kStages = 5;
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ uint64_t full[kStages];
@@ -98,17 +98,42 @@ __global__ void __launch_bounds__(32 * 17, 1) probe_ls(const uint8_t* __restrict
   } else if (warp <= store_warps) {
     uint8_t* dst = st_base + (size_t)blockIdx.x * st_slice + (size_t)(warp - 1) * 512 + lane * 16;
     const size_t stride = (size_t)store_warps * 512, wrap = st_slice / stride;
-    for (long long i = 0; i < st_iters; ++i) {
-      const uint4 v = make_uint4((uint32_t)i, lane, warp, 7u);
-      asm volatile("st.global.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(dst + (size_t)(i % wrap) * stride), "r"(v.x), "r"(v.y), "r"(v.z),
-                   "r"(v.w) : "memory");
+    if (st_kind == 0) {
+      for (long long i = 0; i < st_iters; ++i) {
+        const uint4 v = make_uint4((uint32_t)i, lane, warp, 7u);
+        asm volatile("st.global.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(dst + (size_t)(i % wrap) * stride), "r"(v.x), "r"(v.y), "r"(v.z),
+                     "r"(v.w) : "memory");
+      }
+    } else if (st_kind == 1) {
+      // 256-bit stores: a warp writes 1 KB per instruction (half as many instructions for the same bytes)
+      uint8_t* d8 = st_base + (size_t)blockIdx.x * st_slice + (size_t)(warp - 1) * 1024 + lane * 32;
+      const size_t stride8 = (size_t)store_warps * 1024, wrap8 = st_slice / stride8;
+      for (long long i = 0; i < st_iters / 2; ++i) {
+        const uint32_t a = (uint32_t)i;
+        asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(d8 + (size_t)(i % wrap8) * stride8), "r"(a),
+                     "r"(a), "r"(a), "r"(a), "r"(a), "r"(a), "r"(a), "r"(a) : "memory");
+      }
+    } else {
+      // bulk shared -> global copies of 16 KB (TMA engine) out of the ring's memory, one lane per warp, 4 in flight per warp
+      if (lane == 0) {
+        uint8_t* db = st_base + (size_t)blockIdx.x * st_slice;
+        const size_t pieces = st_slice / 16384;
+        const long long n = st_iters * 512 / 16384;
+        for (long long i = 0; i < n; ++i) {
+          asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(db + (size_t)((i * store_warps + warp - 1) % pieces) * 16384),
+                       "r"(smem_u32(smem) + (uint32_t)((warp - 1) & 7) * 16384u), "r"(16384) : "memory");
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          asm volatile("cp.async.bulk.wait_group.read 3;" ::: "memory");
+        }
+        asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+      }
     }
     if (lane == 0 && warp == 1) cyc_store[blockIdx.x] = clock64() - t0;
   }
 }
 
 static void run_ls(const uint8_t* buf, uint8_t* stbuf, int sms, long long* cyc, size_t load_mb, size_t store_mb, int store_warps,
-                   bool hbm_loads) {
+                   bool hbm_loads, int st_kind = 0) {
   cudaFuncSetAttribute(probe_ls, cudaFuncAttributeMaxDynamicSharedMemorySize, 5 * 32768);
   const size_t slice = hbm_loads ? ((size_t)40 << 20) : (((size_t)48 << 20) / sms / 32768 * 32768);
   const size_t st_slice = ((size_t)24 << 20) / sms / 8192 * 8192;
@@ -120,7 +145,7 @@ static void run_ls(const uint8_t* buf, uint8_t* stbuf, int sms, long long* cyc, 
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0); cudaEventCreate(&e1);
     cudaEventRecord(e0);
-    probe_ls<<<sms, 32 * 17, 5 * 32768>>>(buf, slice, n_chunks, stbuf, st_slice, st_iters, store_warps, cyc, cyc + 160);
+    probe_ls<<<sms, 32 * 17, 5 * 32768>>>(buf, slice, n_chunks, stbuf, st_slice, st_iters, store_warps, cyc, cyc + 160, st_kind);
     cudaEventRecord(e1);
     cudaError_t err = cudaDeviceSynchronize();
     float ms = 0.f;
@@ -129,9 +154,9 @@ static void run_ls(const uint8_t* buf, uint8_t* stbuf, int sms, long long* cyc, 
     if (rep == 1) {
       double cl = 0, cs = 0;
       for (int i = 0; i < sms; ++i) { cl += (double)h[0][i] / sms; cs += (double)h[1][i] / sms; }
-      printf("loads %4zu MB/SM (%s) + stores %4zu MB/SM by %2d warps: kernel %7.3f ms | load role %9.0f cycles = %5.1f B/clk/SM | "
+      printf("[%s] loads %4zu MB/SM (%s) + stores %4zu MB/SM by %2d warps: kernel %7.3f ms | load role %9.0f cycles = %5.1f B/clk/SM | "
              "store role %9.0f cycles = %5.1f B/clk/SM  %s\n",
-             n_chunks ? load_mb : 0, hbm_loads ? "HBM" : "L2", store_warps ? store_mb : 0, store_warps, ms, cl,
+             st_kind == 0 ? "st.v4" : st_kind == 1 ? "st.v8" : "bulk S2G", n_chunks ? load_mb : 0, hbm_loads ? "HBM" : "L2", store_warps ? store_mb : 0, store_warps, ms, cl,
              cl > 0 ? (double)n_chunks * 32768 / cl : 0.0, cs, cs > 0 ? (double)st_iters * store_warps * 512 / cs : 0.0,
              cudaGetErrorString(err));
     }
@@ -185,6 +210,12 @@ int main(int argc, char** argv) {
     run_ls(buf, stbuf, sms, cyc, 96, 32, 4, false);
     run_ls(buf, stbuf, sms, cyc, 96, 0, 0, true);
     run_ls(buf, stbuf, sms, cyc, 96, 32, 16, true);
+    for (int kind = 1; kind <= 2; ++kind) {
+      run_ls(buf, stbuf, sms, cyc, 0, 32, 16, false, kind);
+      run_ls(buf, stbuf, sms, cyc, 0, 32, 4, false, kind);
+      run_ls(buf, stbuf, sms, cyc, 96, 32, 16, false, kind);
+      run_ls(buf, stbuf, sms, cyc, 96, 32, 4, false, kind);
+    }
     return 0;
   }
   printf("bytes in flight per SM: %d\n", kRing);
