@@ -157,7 +157,9 @@ int nerf_mlp_bwd_overlapped(const nerf_net_cfg* cfg, const float* params, const 
 /* Diagnostic (tests, tools/bwd_pipe_probe.py): ONE stage of the layer-pipelined backward kernel over every SM -- Dense
  * `layer` (1..7: dZ_layer = (dZ_{layer+1} W^T) * LeakyReLU' written back into the workspace, and dW/db of that layer ADDED
  * to `grads`; 8: only the weight gradient of Dense 8 / the sigma head w.r.t. the h8 rows), reading dZ_{layer+1} from a
- * workspace that a previous nerf_mlp_bwd[_dx] call on the same `saved` filled. */
+ * workspace that a previous nerf_mlp_bwd[_dx] call on the same `saved` filled.  layer = 100 hi + lo (7 >= hi > lo >= 1): the
+ * layer groups hi ... lo in ONE launch, the CTA pairs split evenly over them, dZ handed from group to group through ready
+ * counters in L2 (blocks in the tile chunk-major layout, tools/tcm_layout.py). */
 int nerf_debug_bwd_pipe_layer(const nerf_net_cfg* cfg, const void* packed, const void* saved, int64_t m,
                               void* workspace, int32_t layer, float* grads, void* stream);
 /* bf16 weight pack for the tensor-core path (re-run after every optimizer step). */

@@ -1131,6 +1131,26 @@ def test_bwd_pipe_stage_matches_chain_and_dw(pkg, n_rays, s):
             assert abs((grads[s1] - ref[s1]).item()) < 1e-4 * abs(ref[s1].item()) + 1e-7
         assert ((gw - rw).norm() / rw.norm()).item() < 1e-4, f"dW of Dense {layer}"
         assert ((grads[w1:b1] - ref[w1:b1]).norm() / ref[w1:b1].norm()).item() < 1e-4, f"db of Dense {layer}"
+    # the seven layer groups 7 ... 1 in ONE launch (layer code 100 hi + lo): only dZ_8 comes from the workspace, every other
+    # dZ is handed from group to group through the ready counters; twice, so a stale counter or a race would show
+    for _ in range(2):
+        ws2 = torch.empty(ws.numel() + 1024, dtype=torch.uint8, device="cuda")
+        shift = (base - ws2.data_ptr()) % 1024
+        ws2 = ws2[shift:shift + ws.numel()]
+        ws2.copy_(ws)
+        n_used = (((m + 127) // 128 + 1) // 2) * 2
+        ws2[region].view(tiles4, tile_bytes)[:n_used, :7 * 65536] = 0x7f
+        grads = torch.zeros(net.n_params, device="cuda")
+        call("nerf_debug_bwd_pipe_layer", net.cfg_ref, ptr(packed), ptr(saved), m, ptr(ws2), 701, ptr(grads))
+        torch.cuda.synchronize()
+        assert torch.equal(ws2[region], ws[region]), "dZ_1..7 of the seven-group launch differ from the chain kernel's"
+        for layer in range(1, 8):
+            w0, w1, b1 = offs[layer]
+            gw, rw = grads[w0:w1], ref[w0:w1]
+            if layer == 4:
+                gw, rw = gw[33 * 256:], rw[33 * 256:]
+            assert ((gw - rw).norm() / rw.norm()).item() < 1e-4, f"dW of Dense {layer} (seven-group launch)"
+            assert ((grads[w1:b1] - ref[w1:b1]).norm() / ref[w1:b1].norm()).item() < 1e-4, f"db of Dense {layer}"
 
 
 def test_train_step_gradients_at_bench_shape(pkg):
