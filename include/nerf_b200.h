@@ -304,6 +304,28 @@ int nerf_train_step_fused(const nerf_net_cfg* cfg, const nerf_render_cfg* rc, co
                           const nerf_rng_state* rng, float* grads, float* adam_m, float* adam_v, int64_t adam_t,
                           float* metrics4_or_null, void* workspace, void* side_stream_or_null, void* stream);
 
+/* The ray-sharded train step of one rank as ONE call: nerf_train_step_fused with the optimizer step replaced by the
+ * gradient exchange over NVLink peer memory (nerf_peer_barrier + nerf_peer_reduce_adam: sum over the ranks in rank order,
+ * fused with Adam).  `grads` must be THIS rank's buffer of the symmetric set, i.e. grads_dev[rank]; the fine network's
+ * exchange + Adam + pack refresh run on the side stream under the coarse backward, [loss sums | coarse gradients] at the
+ * tail; metrics4 are formed from the summed loss sums (peer->reduced_sums).  epoch must grow from step to step (the
+ * 1-based Adam step does); the caller alternates between two symmetric buffer sets from step to step (a buffer is rewritten
+ * two barriers after its last remote read).  Same kernels and results as the host package's sharded call sequence. */
+typedef struct nerf_peer_exchange {
+  void* const* pads_dev;   /* nerf_peer_barrier: DEVICE array of `world` signal pads */
+  void* const* grads_dev;  /* nerf_peer_reduce_adam: DEVICE array of the `world` peer-mapped gradient buffers */
+  float* reduced_sums;     /* (4) device floats: the loss sums added over the ranks */
+  int32_t rank, world;
+  uint32_t epoch;
+  uint32_t reserved;
+} nerf_peer_exchange;
+int nerf_train_step_fused_sharded(const nerf_net_cfg* cfg, const nerf_render_cfg* rc, const nerf_train_cfg* tc,
+                                  float* params_c, void* packed_c, float* params_f, void* packed_f, const float* origs4,
+                                  const float* dirs4, const float* target_rgb, int64_t n_rays, int64_t n_total_rays,
+                                  const nerf_rng_state* rng, float* grads, float* adam_m, float* adam_v, int64_t adam_t,
+                                  float* metrics4_or_null, void* workspace, void* side_stream_or_null,
+                                  const nerf_peer_exchange* peer, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

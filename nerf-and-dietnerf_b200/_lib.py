@@ -46,6 +46,12 @@ class TrainCfg(Structure):
                 ("learning_rate", c_float), ("beta_1", c_float), ("beta_2", c_float), ("epsilon", c_float)]
 
 
+class PeerExchangeCfg(Structure):
+    """Mirror of struct nerf_peer_exchange."""
+    _fields_ = [("pads_dev", c_void_p), ("grads_dev", c_void_p), ("reduced_sums", c_void_p), ("rank", c_int32),
+                ("world", c_int32), ("epoch", c_uint32), ("reserved", c_uint32)]
+
+
 class NerfLibraryError(RuntimeError):
     pass
 
@@ -105,6 +111,9 @@ SIGNATURES = {
     "nerf_train_workspace_bytes": (c_int64, [_CFG, POINTER(RenderCfg), c_int64]),
     "nerf_train_step_fused": (c_int32, [_CFG, POINTER(RenderCfg), POINTER(TrainCfg), _P, _P, _P, _P, _P, _P, _P, c_int64,
                                         c_int64, POINTER(RngState), _P, _P, _P, c_int64, _P, _P, _P, _P]),
+    "nerf_train_step_fused_sharded": (c_int32, [_CFG, POINTER(RenderCfg), POINTER(TrainCfg), _P, _P, _P, _P, _P, _P, _P, c_int64,
+                                                c_int64, POINTER(RngState), _P, _P, _P, c_int64, _P, _P, _P,
+                                                POINTER(PeerExchangeCfg), _P]),
 }
 
 _lib = None
@@ -157,7 +166,7 @@ def check(status, what):
 
 
 # kernels launched per C-ABI call (bf16 mode; the fp32 MLP launches one GEMM per layer and is counted separately)
-KERNELS_PER_CALL = {"nerf_render_fused_fwd": 7, "nerf_train_step_fused": 21, "nerf_mlp_fwd": 1, "nerf_mlp_fwd_rays": 1, "nerf_mlp_fwd_rays_stratified": 1, "nerf_mlp_bwd": 3, "nerf_mlp_bwd_overlapped": 3, "nerf_mlp_bwd_dx": 1, "nerf_mlp_bwd_dw": 2,
+KERNELS_PER_CALL = {"nerf_render_fused_fwd": 7, "nerf_train_step_fused": 21, "nerf_train_step_fused_sharded": 24, "nerf_mlp_fwd": 1, "nerf_mlp_fwd_rays": 1, "nerf_mlp_fwd_rays_stratified": 1, "nerf_mlp_bwd": 3, "nerf_mlp_bwd_overlapped": 3, "nerf_mlp_bwd_dx": 1, "nerf_mlp_bwd_dw": 2,
                     "nerf_pack_weights": 2}
 launch_count = 0            # kernels launched through call() since import (bench.py reads the delta)
 event_hook = None           # optional callable(name) -> context manager, used by bench.py to time single calls

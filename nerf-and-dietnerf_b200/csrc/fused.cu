@@ -239,11 +239,14 @@ int64_t nerf_train_workspace_bytes(const nerf_net_cfg* cfg, const nerf_render_cf
   return carve_train(g, cfg, rc, n_rays, nullptr, &w);
 }
 
-int nerf_train_step_fused(const nerf_net_cfg* cfg, const nerf_render_cfg* rc, const nerf_train_cfg* tc_cfg,
-                          float* params_c, void* packed_c, float* params_f, void* packed_f, const float* origs4,
-                          const float* dirs4, const float* target_rgb, int64_t n_rays, int64_t n_total_rays,
-                          const nerf_rng_state* rng, float* grads, float* adam_m, float* adam_v, int64_t adam_t,
-                          float* metrics4, void* workspace, void* side_stream, void* stream) {
+}  // extern "C"
+
+static int train_step_impl(const nerf_net_cfg* cfg, const nerf_render_cfg* rc, const nerf_train_cfg* tc_cfg,
+                           float* params_c, void* packed_c, float* params_f, void* packed_f, const float* origs4,
+                           const float* dirs4, const float* target_rgb, int64_t n_rays, int64_t n_total_rays,
+                           const nerf_rng_state* rng, float* grads, float* adam_m, float* adam_v, int64_t adam_t,
+                           float* metrics4, void* workspace, void* side_stream, const nerf_peer_exchange* peer,
+                           void* stream) {
   NetGeom g;
   NERF_CHECK_ARG(make_geom(cfg, &g), "bad network config");
   NERF_CHECK_ARG(render_cfg_ok(rc), "bad render config");
@@ -260,8 +263,20 @@ int nerf_train_step_fused(const nerf_net_cfg* cfg, const nerf_render_cfg* rc, co
   NERF_CHECK_ARG((adam_m == nullptr) == (adam_v == nullptr), "adam_m and adam_v go together");
   NERF_CHECK_ARG(!adam_m || adam_t >= 1, "adam_t is the 1-based step");
   NERF_CHECK_ARG(((uintptr_t)workspace & 255) == 0, "workspace must be 256-byte aligned");
+  NERF_CHECK_ARG(!peer || (adam_m && peer->pads_dev && peer->grads_dev && peer->reduced_sums && peer->world >= 1 &&
+                           peer->rank >= 0 && peer->rank < peer->world),
+                 "the sharded step needs the Adam state, the peer tables and a valid rank");
   cudaStream_t st = (cudaStream_t)stream;
   const int64_t np = g.n_params, n = n_rays;
+  // optimizer step of one network (parameter offset `off` in the [coarse | fine] layout) on stream `s`: Adam on the local
+  // gradients, or -- sharded -- the sum over the ranks straight from the peers' buffers fused with the same update
+  auto step_net = [&](float* params, int64_t off, void* s) -> int {
+    if (peer)
+      return nerf_peer_reduce_adam(params, peer->grads_dev, peer->world, 4 + off, np, adam_m + off, adam_v + off,
+                                   tc_cfg->learning_rate, tc_cfg->beta_1, tc_cfg->beta_2, tc_cfg->epsilon, adam_t, nullptr, s);
+    return nerf_adam_step(params, grads + 4 + off, adam_m + off, adam_v + off, np, tc_cfg->learning_rate, tc_cfg->beta_1,
+                          tc_cfg->beta_2, tc_cfg->epsilon, adam_t, s);
+  };
   const int64_t n_all = np * (fine ? 2 : 1);
   float* sums = grads;                       // [sum sq err coarse, sum sq err fine, 0, 0]
   float* g_c = grads + 4;
@@ -296,8 +311,8 @@ int nerf_train_step_fused(const nerf_net_cfg* cfg, const nerf_render_cfg* rc, co
         NERF_TRY(nerf_mlp_bwd_overlapped(cfg, params_f, packed_f, w.xyz_f, w.view_f, w.saved_f, w.d_raw_f, n * sf, g_f,
                                          through_z ? w.d_xyz_f : nullptr, w.ws_bwd, mode, side_stream, stream));
         if (adam_m) {
-          NERF_TRY(nerf_adam_step(params_f, g_f, adam_m + np, adam_v + np, np, tc_cfg->learning_rate, tc_cfg->beta_1,
-                                  tc_cfg->beta_2, tc_cfg->epsilon, adam_t, side_stream));
+          if (peer) NERF_TRY(nerf_peer_barrier(peer->pads_dev, peer->rank, peer->world, peer->epoch, 0, side_stream));
+          NERF_TRY(step_net(params_f, np, side_stream));
           NERF_TRY(pack_for_mode(cfg, params_f, packed_f, mode, side_stream));
           fine_stepped = true;
         }
@@ -321,11 +336,16 @@ int nerf_train_step_fused(const nerf_net_cfg* cfg, const nerf_render_cfg* rc, co
   }
   if (adam_m) {
     // optimizer.apply_gradients over the variables of both models (:164-167); moments laid out [coarse | fine]
-    NERF_TRY(nerf_adam_step(params_c, g_c, adam_m, adam_v, np, tc_cfg->learning_rate, tc_cfg->beta_1, tc_cfg->beta_2,
-                            tc_cfg->epsilon, adam_t, stream));
-    if (fine && !fine_stepped)
-      NERF_TRY(nerf_adam_step(params_f, g_f, adam_m + np, adam_v + np, np, tc_cfg->learning_rate, tc_cfg->beta_1,
-                              tc_cfg->beta_2, tc_cfg->epsilon, adam_t, stream));
+    if (peer) {
+      // every rank's [sums | coarse gradients] are final: barrier, then the loss sums and the coarse network straight
+      // from the peers' buffers
+      NERF_TRY(nerf_peer_barrier(peer->pads_dev, peer->rank, peer->world, peer->epoch, 1, stream));
+      NERF_TRY(nerf_peer_reduce_adam(nullptr, peer->grads_dev, peer->world, 0, 4, nullptr, nullptr, 0.f, 0.f, 0.f, 0.f, 1,
+                                     peer->reduced_sums, stream));
+      sums = peer->reduced_sums;
+    }
+    NERF_TRY(step_net(params_c, 0, stream));
+    if (fine && !fine_stepped) NERF_TRY(step_net(params_f, np, stream));
     if (tc) {
       NERF_TRY(pack_for_mode(cfg, params_c, packed_c, mode_all, stream));
       if (fine && !fine_stepped) NERF_TRY(pack_for_mode(cfg, params_f, packed_f, mode_all, stream));
@@ -334,6 +354,28 @@ int nerf_train_step_fused(const nerf_net_cfg* cfg, const nerf_render_cfg* rc, co
   if (metrics4)
     NERF_TRY(nerf_train_metrics(sums, n_total_rays, tc_cfg->coarse_loss_weight, fine ? 1 : 0, metrics4, stream));
   return NERF_OK;
+}
+
+extern "C" {
+
+int nerf_train_step_fused(const nerf_net_cfg* cfg, const nerf_render_cfg* rc, const nerf_train_cfg* tc_cfg,
+                          float* params_c, void* packed_c, float* params_f, void* packed_f, const float* origs4,
+                          const float* dirs4, const float* target_rgb, int64_t n_rays, int64_t n_total_rays,
+                          const nerf_rng_state* rng, float* grads, float* adam_m, float* adam_v, int64_t adam_t,
+                          float* metrics4, void* workspace, void* side_stream, void* stream) {
+  return train_step_impl(cfg, rc, tc_cfg, params_c, packed_c, params_f, packed_f, origs4, dirs4, target_rgb, n_rays,
+                         n_total_rays, rng, grads, adam_m, adam_v, adam_t, metrics4, workspace, side_stream, nullptr, stream);
+}
+
+int nerf_train_step_fused_sharded(const nerf_net_cfg* cfg, const nerf_render_cfg* rc, const nerf_train_cfg* tc_cfg,
+                                  float* params_c, void* packed_c, float* params_f, void* packed_f, const float* origs4,
+                                  const float* dirs4, const float* target_rgb, int64_t n_rays, int64_t n_total_rays,
+                                  const nerf_rng_state* rng, float* grads, float* adam_m, float* adam_v, int64_t adam_t,
+                                  float* metrics4, void* workspace, void* side_stream, const nerf_peer_exchange* peer,
+                                  void* stream) {
+  NERF_CHECK_ARG(peer != nullptr, "null peer exchange");
+  return train_step_impl(cfg, rc, tc_cfg, params_c, packed_c, params_f, packed_f, origs4, dirs4, target_rgb, n_rays,
+                         n_total_rays, rng, grads, adam_m, adam_v, adam_t, metrics4, workspace, side_stream, peer, stream);
 }
 
 }  // extern "C"

@@ -134,7 +134,7 @@ def test_ctypes_structs_match_the_header(pkg, tmp_path):
     import subprocess
     L = pkg._lib
     structs = {"nerf_net_cfg": L.NetCfg, "nerf_render_cfg": L.RenderCfg, "nerf_rng_state": L.RngState,
-               "nerf_render_outs": L.RenderOuts, "nerf_train_cfg": L.TrainCfg}
+               "nerf_render_outs": L.RenderOuts, "nerf_train_cfg": L.TrainCfg, "nerf_peer_exchange": L.PeerExchangeCfg}
     lines = []
     for cname, mirror in structs.items():
         lines.append(f'printf("{cname} %zu", sizeof({cname}));')
