@@ -112,6 +112,19 @@ def test_fused_entry_points_report_argument_errors(pkg):
                                    ctypes.c_void_p(256), ctypes.c_void_p(256), 4, ctypes.byref(rng), ctypes.byref(outs),
                                    ctypes.c_void_p(256), None)
     assert st == -3 and b"no tensor-core path" in lib.nerf_last_error()
+    # the sharded one-call step: a peer exchange is mandatory, and it needs the Adam state and a rank inside the world
+    tcfg = L.TrainCfg(1.0, 0, 0, 5e-4, 0.9, 0.999, 1e-7)
+    p256 = ctypes.c_void_p(256)
+    common = (ctypes.byref(cfg), ctypes.byref(rc), ctypes.byref(tcfg), p256, p256, p256, p256, p256, p256, p256, 4, 8,
+              ctypes.byref(rng), p256)
+    st = lib.nerf_train_step_fused_sharded(*common, p256, p256, 1, None, p256, None, None, None)
+    assert st == -1 and b"null peer exchange" in lib.nerf_last_error()
+    peer = L.PeerExchangeCfg(256, 256, 256, 2, 2, 1, 0)                 # rank 2 of a world of 2
+    st = lib.nerf_train_step_fused_sharded(*common, p256, p256, 1, None, p256, None, ctypes.byref(peer), None)
+    assert st == -1 and b"valid rank" in lib.nerf_last_error()
+    peer = L.PeerExchangeCfg(256, 256, 256, 0, 2, 1, 0)
+    st = lib.nerf_train_step_fused_sharded(*common, None, None, 1, None, p256, None, ctypes.byref(peer), None)
+    assert st == -1 and b"Adam state" in lib.nerf_last_error()
 
 
 def test_c_caller_links_and_fails_loudly_without_a_gpu(pkg):
