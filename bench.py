@@ -363,7 +363,9 @@ def main():
     per_call = {}
 
     @contextlib.contextmanager
-    def hook(name):
+    def hook(name, args=()):
+        if name == "nerf_mlp_bwd_rays":        # the fine network's backward with d z formed in the chain: parts 1 / 2
+            name = {1: "nerf_mlp_bwd_dx", 2: "nerf_mlp_bwd_dw"}.get(args[14], name)
         if name in ("nerf_mlp_fwd", "nerf_mlp_fwd_rays", "nerf_mlp_fwd_rays_stratified", "nerf_mlp_bwd", "nerf_mlp_bwd_dx",
                     "nerf_mlp_bwd_dw",
                     "nerf_composite_fwd", "nerf_composite_bwd", "nerf_composite_mse_fwd", "nerf_composite_mse_fwd_bwd",

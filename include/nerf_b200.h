@@ -154,6 +154,18 @@ int nerf_mlp_bwd_overlapped(const nerf_net_cfg* cfg, const float* params, const 
                             const float* xyz_enc, const float* view_enc, const void* saved, const float* d_out4,
                             int64_t m, float* grads, float* d_xyz_enc_or_null, void* workspace, int32_t mode,
                             void* side_stream, void* stream);
+/* nerf_mlp_bwd of the rows of n_rays x n_samples ray samples (tensor-core modes, n_pos_enc_dim_xyz = 5), for callers
+ * that need the gradient w.r.t. the DEPTHS instead of the gradient w.r.t. the xyz encoding (the reference does not
+ * detach the importance samples, src/NeRF.py:155, so the fine loss reaches the coarse network through z): the chain
+ * kernel's last epilogue contracts d(xyz encoding) with PE'(o + d z) and the ray direction itself and writes (or, with
+ * accumulate_d_z, adds) 4 bytes per row -- nerf_encode_samples_bwd_z and its 132-byte-per-row round trip disappear.
+ * parts: 1 = input-gradient chain only, 2 = weight gradients only, 3 = both (then side_stream_or_null works as in
+ * nerf_mlp_bwd_overlapped).  Replaces TF autodiff of model_predict o positional_encoding_for_xyz o sample_along_rays
+ * (src/UtilsNeuralRadianceField.py:52-69,204-234, src/UtilsCV.py:584-599). */
+int nerf_mlp_bwd_rays(const nerf_net_cfg* cfg, const void* packed, const void* saved, const float* d_out4,
+                      const float* origs4, const float* dirs4, const float* z, int64_t n_rays, int32_t n_samples,
+                      float* grads, float* d_z, int32_t accumulate_d_z, void* workspace, int32_t mode, int32_t parts,
+                      void* side_stream_or_null, void* stream);
 /* Diagnostic (tests, tools/bwd_pipe_probe.py): ONE stage of the layer-pipelined backward kernel over every SM -- Dense
  * `layer` (1..7: dZ_layer = (dZ_{layer+1} W^T) * LeakyReLU' written back into the workspace, and dW/db of that layer ADDED
  * to `grads`; 8: only the weight gradient of Dense 8 / the sigma head w.r.t. the h8 rows), reading dZ_{layer+1} from a

@@ -562,8 +562,13 @@ class NeRF:
             through_z = not self.stop_grad_z
             call("nerf_composite_mse_fwd_bwd", ptr(w.raw_f), ptr(w.z_f), ptr(y), n, sf, n_total, 1.0, ptr(w.rgb_f),
                  ptr(sums[1:2]), ptr(w.d_raw_f), ptr(w.d_z_f) if through_z else None)
-            side = self._mlp_bwd(mf, w.xyz_f, w.view_f, w.saved_f, w.d_raw_f, n * sf, g_f,
-                                 w.d_xyz_f if through_z else None, w.ws_bwd, side_stream=self._side_stream())
+            dz_in_chain = through_z and self._dz_in_chain(mf)
+            if dz_in_chain:
+                side = self._mlp_bwd_rays(mf, w.saved_f, w.d_raw_f, o, d, w.z_f, n, sf, g_f, w.d_z_f, w.ws_bwd,
+                                          side_stream=self._side_stream())
+            else:
+                side = self._mlp_bwd(mf, w.xyz_f, w.view_f, w.saved_f, w.d_raw_f, n * sf, g_f,
+                                     w.d_xyz_f if through_z else None, w.ws_bwd, side_stream=self._side_stream())
             if self.world_size > 1 and self._overlap_allreduce and self._peer_step is None:
                 # the fine network's gradients are final: their all-reduce runs under the coarse backward
                 with torch.cuda.stream(side) if side is not None else contextlib.nullcontext():
@@ -578,8 +583,9 @@ class NeRF:
                     self._fine_updated = True
             if through_z:
                 # z_f -> xyz -> PE -> fine net, and z_f -> delta in the fine compositing, reach the coarse weights
-                call("nerf_encode_samples_bwd_z", mf.cfg_ref, ptr(o), ptr(d), ptr(w.z_f), ptr(w.d_xyz_f), n, sf,
-                     ptr(w.d_z_f), 1)
+                if not dz_in_chain:
+                    call("nerf_encode_samples_bwd_z", mf.cfg_ref, ptr(o), ptr(d), ptr(w.z_f), ptr(w.d_xyz_f), n, sf,
+                         ptr(w.d_z_f), 1)
                 call("nerf_sample_pdf_bwd", ptr(w.w_c), ptr(w.z_c), ptr(w.u), ptr(w.perm), ptr(w.d_z_f), n, sc, sf,
                      ptr(w.d_w_c))
                 d_w_c = w.d_w_c
@@ -630,11 +636,17 @@ class NeRF:
         through_z = not self.stop_grad_z
         call("nerf_composite_bwd", ptr(w.raw_f), ptr(w.z_f), ptr(d_rgb), None, n, sf, ptr(w.d_raw_f),
              ptr(w.d_z_f) if through_z else None)
-        self._mlp_bwd(mf, w.xyz_f, w.view_f, w.saved_f, w.d_raw_f, n * sf, g_f, w.d_xyz_f if through_z else None,
-                      w.ws_bwd, side_stream=self._side_stream())
+        dz_in_chain = through_z and self._dz_in_chain(mf)
+        if dz_in_chain:
+            self._mlp_bwd_rays(mf, w.saved_f, w.d_raw_f, o, d, w.z_f, n, sf, g_f, w.d_z_f, w.ws_bwd,
+                               side_stream=self._side_stream())
+        else:
+            self._mlp_bwd(mf, w.xyz_f, w.view_f, w.saved_f, w.d_raw_f, n * sf, g_f, w.d_xyz_f if through_z else None,
+                          w.ws_bwd, side_stream=self._side_stream())
         if through_z:
-            call("nerf_encode_samples_bwd_z", mf.cfg_ref, ptr(o), ptr(d), ptr(w.z_f), ptr(w.d_xyz_f), n, sf,
-                 ptr(w.d_z_f), 1)
+            if not dz_in_chain:
+                call("nerf_encode_samples_bwd_z", mf.cfg_ref, ptr(o), ptr(d), ptr(w.z_f), ptr(w.d_xyz_f), n, sf,
+                     ptr(w.d_z_f), 1)
             call("nerf_merge_sorted_bwd", ptr(w.d_z_f), ptr(w.rank), nf, sc, n, ptr(w.d_z_new))
             call("nerf_sample_pdf_bwd", ptr(w.w_c), ptr(w.z_c), ptr(w.u), ptr(w.perm), ptr(w.d_z_new), n, sc, nf,
                  ptr(w.d_w_c))
@@ -671,6 +683,28 @@ class NeRF:
         if self._side is None and self.model_coarse.tensor_core:
             self._side = torch.cuda.Stream(device=self.device)
         return self._side
+
+    @staticmethod
+    def _dz_in_chain(net):
+        """Tensor-core view network with the reference's xyz encoding width: the chain kernel forms d z itself
+        (``nerf_mlp_bwd_rays``), no ``nerf_encode_samples_bwd_z`` afterwards."""
+        return net.tensor_core and net.dx == 33 and net.dv > 0
+
+    @staticmethod
+    def _mlp_bwd_rays(net, saved, d_raw, o, d, z, n, s, grads, d_z, ws, side_stream=None):
+        """``_mlp_bwd`` for the rows of n x s ray samples with the gradient w.r.t. the depths ADDED to ``d_z`` by the chain
+        kernel itself (see ``_dz_in_chain``)."""
+        args = (net.cfg_ref, ptr(net.packed_for(net.params)), ptr(saved), ptr(d_raw), ptr(o), ptr(d), ptr(z), n, s, ptr(grads),
+                ptr(d_z), 1, ptr(ws), net.mode_id)
+        if side_stream is not None:
+            call("nerf_mlp_bwd_rays", *args, 3, side_stream.cuda_stream)
+            return side_stream
+        if NeRF.split_bwd_calls:
+            call("nerf_mlp_bwd_rays", *args, 1, None)
+            call("nerf_mlp_bwd_rays", *args, 2, None)
+            return None
+        call("nerf_mlp_bwd_rays", *args, 3, None)
+        return None
 
     @staticmethod
     def _mlp_bwd(net, xyz, view, saved, d_raw, m, grads, d_xyz, ws, side_stream=None):

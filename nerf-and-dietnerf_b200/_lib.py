@@ -85,6 +85,7 @@ SIGNATURES = {
     "nerf_mlp_bwd_overlapped": (c_int32, [_CFG, _P, _P, _P, _P, _P, _P, c_int64, _P, _P, _P, c_int32, _P, _P]),
     "nerf_mlp_bwd_dx": (c_int32, [_CFG, _P, _P, _P, _P, _P, _P, c_int64, _P, _P, _P, c_int32, _P]),
     "nerf_mlp_bwd_dw": (c_int32, [_CFG, _P, _P, _P, _P, _P, _P, c_int64, _P, _P, _P, c_int32, _P]),
+    "nerf_mlp_bwd_rays": (c_int32, [_CFG, _P, _P, _P, _P, _P, _P, c_int64, c_int32, _P, _P, c_int32, _P, c_int32, c_int32, _P, _P]),
     "nerf_debug_bwd_pipe_layer": (c_int32, [_CFG, _P, _P, c_int64, _P, c_int32, _P, _P]),
     "nerf_packed_bytes": (c_int64, [_CFG]),
     "nerf_pack_weights": (c_int32, [_CFG, _P, _P, _P]),
@@ -166,10 +167,10 @@ def check(status, what):
 
 
 # kernels launched per C-ABI call (bf16 mode; the fp32 MLP launches one GEMM per layer and is counted separately)
-KERNELS_PER_CALL = {"nerf_render_fused_fwd": 7, "nerf_train_step_fused": 21, "nerf_train_step_fused_sharded": 24, "nerf_mlp_fwd": 1, "nerf_mlp_fwd_rays": 1, "nerf_mlp_fwd_rays_stratified": 1, "nerf_mlp_bwd": 3, "nerf_mlp_bwd_overlapped": 3, "nerf_mlp_bwd_dx": 1, "nerf_mlp_bwd_dw": 2,
+KERNELS_PER_CALL = {"nerf_render_fused_fwd": 7, "nerf_train_step_fused": 21, "nerf_train_step_fused_sharded": 24, "nerf_mlp_fwd": 1, "nerf_mlp_fwd_rays": 1, "nerf_mlp_fwd_rays_stratified": 1, "nerf_mlp_bwd": 3, "nerf_mlp_bwd_overlapped": 3, "nerf_mlp_bwd_dx": 1, "nerf_mlp_bwd_dw": 2, "nerf_mlp_bwd_rays": 3,
                     "nerf_pack_weights": 2}
 launch_count = 0            # kernels launched through call() since import (bench.py reads the delta)
-event_hook = None           # optional callable(name) -> context manager, used by bench.py to time single calls
+event_hook = None           # optional callable(name, args) -> context manager, used by bench.py to time single calls
 
 
 def call(name, *args):
@@ -177,7 +178,7 @@ def call(name, *args):
     global launch_count
     lib = load()
     if event_hook is not None:
-        with event_hook(name):
+        with event_hook(name, args):
             status = getattr(lib, name)(*args, stream())
     else:
         status = getattr(lib, name)(*args, stream())

@@ -47,6 +47,18 @@ bool device_first_use(int slot);
 
 inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
+// The rays behind the rows of a backward call (nerf_mlp_bwd_rays): with them the dX chain turns d(xyz encoding) into
+// d z = d . PE'(o + d z) in the epilogue of its last step instead of writing the 33 floats per row out for
+// encode_samples_bwd_z to read back.
+struct BwdRays {
+  const float4* origs;
+  const float4* dirs;
+  const float* z;          // (n_rays, n_samples) depths of the rows
+  float* d_z;              // (n_rays, n_samples); null = no ray inputs
+  int32_t n_samples;
+  int32_t accumulate;      // 1: d_z += (the compositing backward wrote its share first)
+};
+
 // coarse depths drawn inside the MLP prologue (nerf_mlp_fwd_rays_stratified)
 struct StratifiedZ {
   float z_start, z_end;

@@ -304,10 +304,16 @@ static int train_step_impl(const nerf_net_cfg* cfg, const nerf_render_cfg* rc, c
                            w.view_f, w.ws_fwd, stream));
       NERF_TRY(nerf_composite_mse_fwd_bwd(w.raw_f, w.z_f, target_rgb, n, sf, n_total_rays, 1.0f, nullptr, sums + 1,
                                           w.d_raw_f, through_z ? w.d_z_f : nullptr, stream));
+      // tensor-core modes, the reference's encoding width: the chain kernel turns d(xyz encoding) into d z in its last
+      // epilogue (nerf_mlp_bwd_rays) -- no d_xyz round trip, no nerf_encode_samples_bwd_z launch
+      const bool dz_in_chain = tc && through_z && g.dx == 33 && g.view;
       if (use_side) {
-        // input-gradient chain here, the weight-gradient kernel AT THE SAME TIME on the side stream (disjoint SMs, dZ handed
-        // over through L2); the fine network's Adam step and the refresh of its bf16 pack follow it there and run under
-        // the sampler / compositing / coarse backward below
+        // input-gradient chain here, the weight-gradient kernel on the side stream; the fine network's Adam step and the
+        // refresh of its bf16 pack follow it there and run under the sampler / compositing / coarse backward below
+        if (dz_in_chain)
+          NERF_TRY(nerf_mlp_bwd_rays(cfg, packed_f, w.saved_f, w.d_raw_f, origs4, dirs4, w.z_f, n, sf, g_f, w.d_z_f, 1, w.ws_bwd,
+                                     mode, 3, side_stream, stream));
+        else
         NERF_TRY(nerf_mlp_bwd_overlapped(cfg, params_f, packed_f, w.xyz_f, w.view_f, w.saved_f, w.d_raw_f, n * sf, g_f,
                                          through_z ? w.d_xyz_f : nullptr, w.ws_bwd, mode, side_stream, stream));
         if (adam_m) {
@@ -317,12 +323,16 @@ static int train_step_impl(const nerf_net_cfg* cfg, const nerf_render_cfg* rc, c
           fine_stepped = true;
         }
         forked = true;
+      } else if (dz_in_chain) {
+        NERF_TRY(nerf_mlp_bwd_rays(cfg, packed_f, w.saved_f, w.d_raw_f, origs4, dirs4, w.z_f, n, sf, g_f, w.d_z_f, 1, w.ws_bwd,
+                                   mode, 3, nullptr, stream));
       } else {
         NERF_TRY(nerf_mlp_bwd(cfg, params_f, packed_f, w.xyz_f, w.view_f, w.saved_f, w.d_raw_f, n * sf, g_f,
                               through_z ? w.d_xyz_f : nullptr, w.ws_bwd, mode, stream));
       }
       if (through_z) {
-        NERF_TRY(nerf_encode_samples_bwd_z(cfg, origs4, dirs4, w.z_f, w.d_xyz_f, n, sf, w.d_z_f, 1, stream));
+        if (!dz_in_chain)
+          NERF_TRY(nerf_encode_samples_bwd_z(cfg, origs4, dirs4, w.z_f, w.d_xyz_f, n, sf, w.d_z_f, 1, stream));
         NERF_TRY(nerf_sample_pdf_bwd(w.w_c, w.z_c, w.u, w.perm, w.d_z_f, n, sc, sf, w.d_w_c, stream));
         d_w_c = w.d_w_c;
       }

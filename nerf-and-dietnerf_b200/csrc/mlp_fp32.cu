@@ -11,7 +11,7 @@ int mlp_tc_fwd(const nerf_net_cfg* cfg, const NetGeom& g, const float* params, c
                const float* view_enc, int64_t m, float* out4, void* saved, void* workspace, cudaStream_t st, bool half);
 int mlp_tc_bwd(const nerf_net_cfg* cfg, const NetGeom& g, const float* params, const void* packed, const float* xyz_enc,
                const float* view_enc, const void* saved, const float* d_out4, int64_t m, float* grads, float* d_xyz_enc,
-               void* workspace, cudaStream_t st, int parts, cudaStream_t side, bool half);
+               void* workspace, cudaStream_t st, int parts, cudaStream_t side, bool half, const BwdRays* rays = nullptr);
 int mlp_tc_fwd_rays(const nerf_net_cfg* cfg, const NetGeom& g, const void* packed, const float* origs4, const float* dirs4,
                     const float* z, int64_t n_rays, int n_samples, float* out4, void* saved, cudaStream_t st, bool half,
                     const StratifiedZ* gen = nullptr);
@@ -440,6 +440,24 @@ int nerf_mlp_bwd_dx(const nerf_net_cfg* cfg, const float* params, const void* pa
                     float* d_xyz_enc_or_null, void* workspace, int32_t mode, void* stream) {
   return mlp_bwd_parts(cfg, params, packed_or_null, xyz_enc, view_enc, saved, d_out4, m, grads, d_xyz_enc_or_null, workspace,
                        mode, stream, 1);
+}
+
+int nerf_mlp_bwd_rays(const nerf_net_cfg* cfg, const void* packed, const void* saved, const float* d_out4, const float* origs4,
+                      const float* dirs4, const float* z, int64_t n_rays, int32_t n_samples, float* grads, float* d_z,
+                      int32_t accumulate_d_z, void* workspace, int32_t mode, int32_t parts, void* side_stream_or_null,
+                      void* stream) {
+  NetGeom g;
+  NERF_CHECK_ARG(make_geom(cfg, &g), "bad net config");
+  NERF_CHECK_ARG(packed && saved && d_out4 && grads && workspace && origs4 && dirs4 && z && d_z, "null pointer");
+  NERF_CHECK_ARG(n_rays >= 0 && n_samples > 0 && parts >= 1 && parts <= 3, "bad shape / parts");
+  if (mode != NERF_MODE_BF16 && mode != NERF_MODE_FP16) {
+    set_error("nerf_mlp_bwd_rays: tensor-core modes only (NERF_MODE_FP32: nerf_mlp_bwd + nerf_encode_samples_bwd_z)");
+    return NERF_E_UNSUPPORTED;
+  }
+  if (n_rays == 0) return NERF_OK;
+  BwdRays rays{(const float4*)origs4, (const float4*)dirs4, z, d_z, n_samples, accumulate_d_z};
+  return mlp_tc_bwd(cfg, g, nullptr, packed, nullptr, nullptr, saved, d_out4, n_rays * n_samples, grads, nullptr, workspace,
+                    (cudaStream_t)stream, parts, (cudaStream_t)side_stream_or_null, mode == NERF_MODE_FP16, &rays);
 }
 
 int nerf_mlp_bwd_dw(const nerf_net_cfg* cfg, const float* params, const void* packed_or_null, const float* xyz_enc,

@@ -182,6 +182,7 @@ enum : uint32_t {
 };
 uint32_t tc_debug_flags();
 
+
 // dW split-K partials (backward workspace, after the dZ tiles): one 256 x 256 fp32 block + 256 bias sums per dW CTA
 constexpr int64_t kDwPartialFloats = 256 * 256 + 256;
 constexpr int64_t kDwScratchBytes = (int64_t)kMaxSMs * kDwPartialFloats * 4;

@@ -210,11 +210,34 @@ __device__ __forceinline__ void chain_mask_epilogue(uint32_t taddr_half, const u
   }
 }
 
+// d z of one row from its 33 gradients w.r.t. the xyz encoding (L = 5): d z = sum_c d_c (g_c0 + sum_k 2^k pi (g_sin cos - g_cos
+// sin)(2^k pi p_c)), p = o + d z -- positional_encoding_for_xyz and sample_along_rays differentiated
+// (src/UtilsNeuralRadianceField.py:52-69, src/UtilsCV.py:598), with the sin / cos of the forward prologue
+// (exact range reduction, then the SFU).  Inlined with compile-time indices: as a real call the 33 gradients went through
+// local memory (L1 is ~3 KB next to 225 KB of shared memory) and cost the chain 3 us per tile.
+__device__ __forceinline__ float dz_from_enc_grad(const float (&g)[33], float4 o, float4 d, float zz) {
+  float gz = 0.f;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const float oc = c == 0 ? o.x : (c == 1 ? o.y : o.z), dc = c == 0 ? d.x : (c == 1 ? d.y : d.z);
+    const float pc = __fadd_rn(oc, __fmul_rn(dc, zz));
+    float acc = g[11 * c], t = pc, scale = 3.14159265358979f;
+#pragma unroll
+    for (int k = 0; k < 5; ++k, t *= 2.f, scale *= 2.f) {
+      const float q = rintf(0.5f * t);
+      const float a = fmaf(-2.f, q, t) * 3.14159265358979f;
+      acc += (g[11 * c + 1 + 2 * k] * __cosf(a) - g[11 * c + 2 + 2 * k] * __sinf(a)) * scale;
+    }
+    gz = fmaf(acc, dc, gz);
+  }
+  return gz;
+}
+
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreadsFwd, 1)
 mlp_tc_bwd_chain_kernel(const __grid_constant__ BwdPlan plan, const uint8_t* __restrict__ packed,
                         const uint8_t* __restrict__ saved, const float* __restrict__ d_out4, int64_t M,
                         uint8_t* __restrict__ dz_ws, float* __restrict__ d_xyz_enc, int dx, float alpha, uint32_t dbg,
-                        uint32_t* __restrict__ flags, uint32_t stagger_ns) {
+                        uint32_t* __restrict__ flags, uint32_t stagger_ns, const BwdRays rays) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t sbase = smem_u32(smem);
   if ((sbase & 1023u) != 0u) __trap();
@@ -236,7 +259,7 @@ mlp_tc_bwd_chain_kernel(const __grid_constant__ BwdPlan plan, const uint8_t* __r
                 : reinterpret_cast<const float*>(packed + plan.w_rgb_off)[(j / 3) * 4 + (j % 3)];
   }
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const bool need_dx = d_xyz_enc != nullptr;
+  const bool need_dx = d_xyz_enc != nullptr || rays.d_z != nullptr;
   // a "quad" = the four 128-row tiles a CTA pair works on at a time: tile = 4 quad + 2 t + rank (t = super-tile 0/1)
   const uint32_t rank = cluster_ctarank();
   const int64_t n_tiles = (M + kTileM - 1) / kTileM;
@@ -447,9 +470,10 @@ mlp_tc_bwd_chain_kernel(const __grid_constant__ BwdPlan plan, const uint8_t* __r
         if (flags) flag_signal(flags + (size_t)tile * kFlagsPerTile + kHiddenSlots);   // this warp's part of dZ_L' / dOut is out
       }
 
-      float xs[32];                                      // d(xyz encoding): half 0 -> cols 0..31, half 1 -> cols 32..39
+      float xs[33];                                      // d(xyz encoding): half 0 -> cols 0..31 (+ col 32 when it forms d z
+                                                         // itself), half 1 -> cols 32..39
 #pragma unroll
-      for (int i = 0; i < 32; ++i) xs[i] = 0.f;
+      for (int i = 0; i < 33; ++i) xs[i] = 0.f;
       for (int s = 0; s < plan.n_steps; ++s) {
         const int kind = plan.step_kind[s];
         if (!need_dx && kind != STEP_MASK) continue;
@@ -482,11 +506,13 @@ mlp_tc_bwd_chain_kernel(const __grid_constant__ BwdPlan plan, const uint8_t* __r
           copy_pending = true;
         } else {
           if (half == 0) {
-            uint32_t a0[32];
+            uint32_t a0[32], a32 = 0u;
             tmem_ld32(taddr, a0);
+            if (rays.d_z) tmem_ld1(taddr + 32, a32);      // column 32 = the last cosine of the z coordinate
             tmem_ld_wait();
 #pragma unroll
             for (int i = 0; i < 32; ++i) xs[i] += __uint_as_float(a0[i]);
+            xs[32] += __uint_as_float(a32);
           } else {
             uint32_t a1[16];
             tmem_ld16(taddr + 32, a1);
@@ -499,10 +525,17 @@ mlp_tc_bwd_chain_kernel(const __grid_constant__ BwdPlan plan, const uint8_t* __r
             __syncwarp();
             if (lane == 0) mbar_arrive_cluster(act_ready_leader);
           } else if (row_ok) {
-            float* dst = d_xyz_enc + row * dx + half * 32;
-            const int lim = dx - half * 32;
+            if (rays.d_z && half == 0) {
+              const int64_t ray = row / rays.n_samples;
+              const float gz = dz_from_enc_grad(xs, __ldg(rays.origs + ray), __ldg(rays.dirs + ray), __ldg(rays.z + row));
+              rays.d_z[row] = rays.accumulate ? rays.d_z[row] + gz : gz;
+            }
+            if (d_xyz_enc) {
+              float* dst = d_xyz_enc + row * dx + half * 32;
+              const int lim = dx - half * 32;
 #pragma unroll
-            for (int i = 0; i < 32; ++i) if (i < lim && (half == 0 || i < 8)) dst[i] = xs[i];
+              for (int i = 0; i < 32; ++i) if (i < lim && (half == 0 || i < 8)) dst[i] = xs[i];
+            }
           }
         }
       }
@@ -857,8 +890,17 @@ int64_t mlp_tc_bwd_flag_bytes(int64_t m) {
 // time (see the top of this file); the caller joins `side` before it reads `grads`.
 int mlp_tc_bwd(const nerf_net_cfg* cfg, const NetGeom& g, const float* params, const void* packed, const float* xyz_enc,
                const float* view_enc, const void* saved, const float* d_out4, int64_t m, float* grads, float* d_xyz_enc,
-               void* workspace, cudaStream_t st, int parts, cudaStream_t side, bool half) {
+               void* workspace, cudaStream_t st, int parts, cudaStream_t side, bool half, const BwdRays* rays) {
   (void)params; (void)xyz_enc; (void)view_enc;
+  BwdRays br;
+  memset(&br, 0, sizeof(br));
+  if (rays) {
+    if (g.dx != 33 || !g.view) {
+      set_error("nerf_mlp_bwd_rays: d z in the chain epilogue is built for n_pos_enc_dim_xyz = 5 view networks");
+      return NERF_E_UNSUPPORTED;
+    }
+    br = *rays;
+  }
   TcPlan fplan;
   if (!make_plan(g, &fplan)) {
     set_error("the tensor-core modes support hidden=256, last_hidden=128, xyz width <= 38, view width <= 24");
@@ -912,7 +954,7 @@ int mlp_tc_bwd(const nerf_net_cfg* cfg, const NetGeom& g, const float* params, c
   if (!(dbg & kDbgNoChain) && (parts & 1)) {
     mlp_tc_bwd_chain_kernel<<<grid, kThreadsFwd, kSmemCAlloc, st>>>(bplan, packed_bwd, (const uint8_t*)saved, d_out4, m,
                                                                    dz_ws, d_xyz_enc, g.dx, cfg->leaky_alpha, dbg, flags,
-                                                                   stagger_ns);
+                                                                   stagger_ns, br);
     NERF_CHECK_LAUNCH();
   }
   if (!(dbg & kDbgNoDw) && (parts & 2)) {

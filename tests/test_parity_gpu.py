@@ -1047,6 +1047,58 @@ def _bwd_setup(pkg, n_rays, s, seed=5):
     return net, packed, saved, ws, d_out, m
 
 
+@pytest.mark.parametrize("n_rays,s,side", [(151, 32, False), (1024 + 37, 128, True)])
+def test_mlp_bwd_rays_forms_dz_in_the_chain(pkg, n_rays, s, side):
+    """nerf_mlp_bwd_rays: the chain kernel's last epilogue contracts d(xyz encoding) with PE'(o + d z) and the ray direction
+    itself.  Against nerf_mlp_bwd (d_xyz_enc out) + nerf_encode_samples_bwd_z: weight gradients bit-identical (same
+    kernels), d z equal up to the sin / cos formulation (the forward prologue's exact range reduction + SFU against sincosf of a rounded 2^k pi: 1e-4 of its scale); accumulate adds."""
+    call, ptr = pkg._lib.call, pkg._lib.ptr
+    cfg = pkg.NetCfg(5, 4, 2, 256, 128, 0.05)
+    net = pkg.NerfMLP(cfg, mode="bf16", seed=3)
+    m = n_rays * s
+    g = torch.Generator(device="cuda").manual_seed(11)
+    o4 = torch.randn(n_rays, 4, device="cuda", generator=g)
+    d4 = torch.randn(n_rays, 4, device="cuda", generator=g)
+    z = torch.sort(torch.rand(n_rays, s, device="cuda", generator=g) * 2 + 0.5, -1).values.contiguous()
+    d_out = torch.randn(m, 4, device="cuda", generator=g)
+    out = torch.empty(m, 4, device="cuda")
+    packed = net.packed_for(net.params)
+    saved = torch.empty(net.saved_bytes(m), dtype=torch.uint8, device="cuda")
+    ws = torch.empty(net.workspace_bytes(m, True), dtype=torch.uint8, device="cuda")
+    call("nerf_mlp_fwd_rays", net.cfg_ref, ptr(packed), ptr(o4), ptr(d4), ptr(z), n_rays, s, ptr(out), ptr(saved), net.mode_id)
+    g_ref = torch.zeros(net.n_params, device="cuda")
+    d_xyz = torch.empty(m, 33, device="cuda")
+    call("nerf_mlp_bwd", net.cfg_ref, ptr(net.params), ptr(packed), None, None, ptr(saved), ptr(d_out), m, ptr(g_ref),
+         ptr(d_xyz), ptr(ws), net.mode_id)
+    base = torch.randn(n_rays, s, device="cuda", generator=g)
+    dz_ref = base.clone()
+    call("nerf_encode_samples_bwd_z", net.cfg_ref, ptr(o4), ptr(d4), ptr(z), ptr(d_xyz), n_rays, s, ptr(dz_ref), 1)
+    g_new = torch.zeros(net.n_params, device="cuda")
+    dz = base.clone()
+    stream = torch.cuda.Stream() if side else None
+    call("nerf_mlp_bwd_rays", net.cfg_ref, ptr(packed), ptr(saved), ptr(d_out), ptr(o4), ptr(d4), ptr(z), n_rays, s, ptr(g_new),
+         ptr(dz), 1, ptr(ws), net.mode_id, 3, stream.cuda_stream if side else None)
+    if side:
+        torch.cuda.current_stream().wait_stream(stream)
+    torch.cuda.synchronize()
+    assert torch.equal(g_new, g_ref)
+    scale = (dz_ref - base).abs().max().item()
+    err = (dz - dz_ref).abs().max().item()
+    assert err < 1e-4 * scale, (err, scale)
+    # accumulate = 0 overwrites; the two halves as separate calls (parts 1, 2) give the same result
+    dz0 = torch.full((n_rays, s), 7.0, device="cuda")
+    g_two = torch.zeros(net.n_params, device="cuda")
+    for parts in (1, 2):
+        call("nerf_mlp_bwd_rays", net.cfg_ref, ptr(packed), ptr(saved), ptr(d_out), ptr(o4), ptr(d4), ptr(z), n_rays, s,
+             ptr(g_two), ptr(dz0), 0, ptr(ws), net.mode_id, parts, None)
+    torch.cuda.synchronize()
+    assert torch.equal(g_two, g_ref) and torch.equal(dz0, dz - base) or (dz0 - (dz - base)).abs().max().item() < 1e-6 * scale
+    # fp32 mode has no such path
+    with pytest.raises(pkg.NerfLibraryError):
+        call("nerf_mlp_bwd_rays", net.cfg_ref, ptr(packed), ptr(saved), ptr(d_out), ptr(o4), ptr(d4), ptr(z), n_rays, s,
+             ptr(g_two), ptr(dz0), 0, ptr(ws), 0, 3, None)
+
+
 @pytest.mark.parametrize("n_rays,s", [(151, 32), (2048 + 37, 64)])
 def test_mlp_backward_two_streams_and_overlapped(pkg, n_rays, s, monkeypatch):
     """nerf_mlp_bwd_overlapped: (a) default = chain on the stream, dW kernel on the side stream after it -- the same kernels
