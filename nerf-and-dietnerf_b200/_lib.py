@@ -167,7 +167,7 @@ def check(status, what):
 
 
 # kernels launched per C-ABI call (bf16 mode; the fp32 MLP launches one GEMM per layer and is counted separately)
-KERNELS_PER_CALL = {"nerf_render_fused_fwd": 7, "nerf_train_step_fused": 21, "nerf_train_step_fused_sharded": 24, "nerf_mlp_fwd": 1, "nerf_mlp_fwd_rays": 1, "nerf_mlp_fwd_rays_stratified": 1, "nerf_mlp_bwd": 3, "nerf_mlp_bwd_overlapped": 3, "nerf_mlp_bwd_dx": 1, "nerf_mlp_bwd_dw": 2, "nerf_mlp_bwd_rays": 3,
+KERNELS_PER_CALL = {"nerf_render_fused_fwd": 7, "nerf_train_step_fused": 20, "nerf_train_step_fused_sharded": 23, "nerf_mlp_fwd": 1, "nerf_mlp_fwd_rays": 1, "nerf_mlp_fwd_rays_stratified": 1, "nerf_mlp_bwd": 3, "nerf_mlp_bwd_overlapped": 3, "nerf_mlp_bwd_dx": 1, "nerf_mlp_bwd_dw": 2, "nerf_mlp_bwd_rays": 3,
                     "nerf_pack_weights": 2}
 launch_count = 0            # kernels launched through call() since import (bench.py reads the delta)
 event_hook = None           # optional callable(name, args) -> context manager, used by bench.py to time single calls
