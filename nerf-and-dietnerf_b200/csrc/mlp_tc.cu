@@ -455,7 +455,6 @@ mlp_tc_fwd_kernel(const __grid_constant__ TcPlan plan, const uint8_t* __restrict
                 uint4 w = make_uint4(__float_as_uint(v.x), __float_as_uint(v.y), __float_as_uint(v.z), __float_as_uint(v.w));
                 if (kHalf) w = half8_to_bf16(w);          // the backward reads bf16
                 stg128(gblock + rbcm_offset(r, j, 32), w);
-                if ((dbg >> 16) && (it & 7) == 7) __nanosleep(dbg >> 16);   // experiment: throttle the store stream
               }
             }
             __syncwarp();

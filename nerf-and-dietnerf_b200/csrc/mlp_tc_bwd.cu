@@ -389,7 +389,6 @@ mlp_tc_bwd_chain_kernel(const __grid_constant__ BwdPlan plan, const uint8_t* __r
               const float4 v = lds128f(act_u32 + (j >> 3) * kPanelBytes + r * 128 + (((j & 7) ^ (r & 7)) << 4));
               stg128(gblock + rbcm_offset(r, j, 32),
                      make_uint4(__float_as_uint(v.x), __float_as_uint(v.y), __float_as_uint(v.z), __float_as_uint(v.w)));
-              if ((dbg >> 16) && (it & 7) == 7) __nanosleep(dbg >> 16);     // experiment: throttle the store stream
             }
           }
           __syncwarp();
