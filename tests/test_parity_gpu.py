@@ -194,8 +194,10 @@ def _weights_and_z(n, s, seed):
     return w.contiguous(), z
 
 
+# n_f: 5 / 7 (one element per lane), 64 (two), 110 / 128 (four), 192 / 256 (eight: the render configs' 192) of the bitonic
+# network, 300 (beyond it: the rank sort)
 @pytest.mark.parametrize("n,s,nf", [(2048, 64, 128), (257, 64, 64), (100, 55, 110), (10, 2, 5), (64, 192, 128), (3001, 64, 128),
-                                    (2500, 33, 7)])
+                                    (2500, 33, 7), (300, 64, 192), (70, 64, 256), (40, 64, 300), (33, 64, 33)])
 def test_sample_pdf_bit_exact(pkg, n, s, nf):
     w, z = _weights_and_z(n, s, nf)
     u = O.importance_uniforms(3, 4, n, nf, ray_offset=17)
