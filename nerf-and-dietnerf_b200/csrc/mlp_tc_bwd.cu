@@ -301,19 +301,19 @@ mlp_tc_bwd_chain_kernel(const __grid_constant__ BwdPlan plan, const uint8_t* __r
           const int first = plan.step_first[s], nch = plan.step_nch[s];
           const uint32_t half_bytes = plan.chunk_bytes[first] >> 1;     // rows [rank N/2, (rank + 1) N/2) of [N][64]
           const uint8_t* src = packed + plan.chunk_off[first] + rank * half_bytes;
-          for (int t = 0; t < 2; ++t) {      // staggered: every step's chunks are streamed once per super-tile
-            for (int ci = 0; ci < nch; ++ci, ++k) {
-              if ((k & (uint32_t)(kProdLanes - 1)) == (uint32_t)lane) {
-                mbar_wait_spin(empty0 + 8u * st, ph);
-                if (no_copy) {
-                  mbar_arrive(full0 + 8u * st);
-                } else {
-                  mbar_arrive_expect_tx(full0 + 8u * st, half_bytes);
-                  bulk_g2s(sbase + kSmemCStage + st * kCStageBytes, src + (size_t)ci * 2u * half_bytes, half_bytes, full0 + 8u * st);
-                }
+          // A step's chunks (at most four) are streamed ONCE per quad: the six-stage ring holds them for both super-tiles
+          // (the MMA issuer releases a stage after its second use) and still has two stages to run ahead into the next step
+          for (int ci = 0; ci < nch; ++ci, ++k) {
+            if ((k & (uint32_t)(kProdLanes - 1)) == (uint32_t)lane) {
+              mbar_wait_spin(empty0 + 8u * st, ph);
+              if (no_copy) {
+                mbar_arrive(full0 + 8u * st);
+              } else {
+                mbar_arrive_expect_tx(full0 + 8u * st, half_bytes);
+                bulk_g2s(sbase + kSmemCStage + st * kCStageBytes, src + (size_t)ci * 2u * half_bytes, half_bytes, full0 + 8u * st);
               }
-              if (++st == kCStages) { st = 0; ph ^= 1u; }
             }
+            if (++st == kCStages) { st = 0; ph ^= 1u; }
           }
         }
       }
@@ -324,7 +324,7 @@ mlp_tc_bwd_chain_kernel(const __grid_constant__ BwdPlan plan, const uint8_t* __r
       const uint32_t full0 = smem_u32(&bars->full[0]), full0_leader = mapa_shared(full0, 0);
       int per_quad = 0;
       for (int s = 0; s < plan.n_steps; ++s)
-        if (need_dx || plan.step_kind[s] == STEP_MASK) per_quad += 2 * plan.step_nch[s];
+        if (need_dx || plan.step_kind[s] == STEP_MASK) per_quad += plan.step_nch[s];      // one fill per chunk and quad
       uint32_t st = 0, ph = 0;
       for (int64_t quad = quad0; quad < n_quads; quad += quad_step)
         for (int i = 0; i < per_quad; ++i) {
@@ -344,14 +344,18 @@ mlp_tc_bwd_chain_kernel(const __grid_constant__ BwdPlan plan, const uint8_t* __r
           if (!need_dx && plan.step_kind[s] != STEP_MASK) continue;
           const int nch = plan.step_nch[s];
           const uint32_t idesc = make_idesc(plan.step_n[s], 0, 0, 1, 256);
+          const uint32_t st0 = st, ph0 = ph;               // the step's first stage: super-tile 1 walks the same stages again
 #pragma unroll
           for (int t = 0; t < 2; ++t) {
             mbar_wait_spin(smem_u32(&bars->act_ready[t]), act_ph);
             const uint32_t d_tmem = tmem_base + (uint32_t)t * 256u;
             uint64_t a = make_desc_kmajor(sbase + kSmemCAct + t * kActPanels * kPanelBytes);
+            st = st0; ph = ph0;
             for (int ci = 0; ci < nch; ++ci, a += (kPanelBytes >> 4)) {
-              mbar_wait_spin(full0 + 8u * st, ph);
-              tc_fence_after();
+              if (t == 0) {                                // super-tile 0 waits for the chunk; it stays for super-tile 1
+                mbar_wait_spin(full0 + 8u * st, ph);
+                tc_fence_after();
+              }
               const uint64_t b = b0 + (uint64_t)(st * (uint32_t)(kCStageBytes >> 4));
               if (!no_mma) {
                 umma_pair(d_tmem, a, b, idesc, ci > 0 ? 1u : 0u);
@@ -359,7 +363,7 @@ mlp_tc_bwd_chain_kernel(const __grid_constant__ BwdPlan plan, const uint8_t* __r
                 umma_pair(d_tmem, a + 4, b + 4, idesc, 1u);
                 umma_pair(d_tmem, a + 6, b + 6, idesc, 1u);
               }
-              umma_commit_pair(empty0 + 8u * st);          // releases this stage in both CTAs
+              if (t == 1) umma_commit_pair(empty0 + 8u * st);      // second use done: releases this stage in both CTAs
               if (++st == kCStages) { st = 0; ph ^= 1u; }
             }
             umma_commit_pair(smem_u32(&bars->acc_full[t]));
