@@ -154,6 +154,16 @@ int nerf_mlp_bwd_overlapped(const nerf_net_cfg* cfg, const float* params, const 
                             const float* xyz_enc, const float* view_enc, const void* saved, const float* d_out4,
                             int64_t m, float* grads, float* d_xyz_enc_or_null, void* workspace, int32_t mode,
                             void* side_stream, void* stream);
+/* nerf_mlp_fwd_rays for the pixels [ray_begin, ray_begin + n_rays) of an h x w image seen from c2w_host (16 floats,
+ * row-major, HOST memory) -- the rays are generated in the kernel's prologue with nerf_ray_directions' arithmetic (bit for
+ * bit), so get_rays_directions + get_z_values + sample_along_rays + both encodings + model_predict are ONE kernel and no ray
+ * ever reaches HBM (north_star kernel (1) folded into kernel (2); src/NeRF.py:206-228 render_image's rays).  z_or_null:
+ * (n_rays, n_samples) depths (the fine pass); null: stratified depths of [z_start, z_end] drawn in the prologue from the
+ * Philox stream (seed, step, ray counter = pixel index) and written to z_out.  Inference only; tensor-core modes. */
+int nerf_mlp_fwd_camera(const nerf_net_cfg* cfg, const void* packed, const float* c2w_host, float fov, int32_t h, int32_t w,
+                        int64_t ray_begin, int64_t n_rays, int32_t n_samples, const float* z_or_null, float z_start,
+                        float z_end, uint64_t seed, uint32_t step, float* z_out_or_null, float* out4, int32_t mode,
+                        void* stream);
 /* nerf_mlp_bwd of the rows of n_rays x n_samples ray samples (tensor-core modes, n_pos_enc_dim_xyz = 5), for callers
  * that need the gradient w.r.t. the DEPTHS instead of the gradient w.r.t. the xyz encoding (the reference does not
  * detach the importance samples, src/NeRF.py:155, so the fine loss reaches the coarse network through z): the chain

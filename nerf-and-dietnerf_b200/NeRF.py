@@ -13,6 +13,7 @@ import math
 from pathlib import Path
 from typing import Dict
 
+import numpy as np
 import torch
 
 from . import _lib
@@ -102,6 +103,7 @@ class NeRF:
     # the C side: half the host time per step); False: the host package's own call sequence (what a sharded run uses, whose
     # all-reduces sit between the calls)
     use_fused_step = True
+    rays_in_kernel = True      # render_image_lean: rays generated inside the MLP kernel (tensor-core modes)
 
     def __init__(self, net_config: Dict, render_config: Dict, near_boundary: float, far_boundary: float, *,
                  mode: str = DEFAULT_MODE, device=None, seed=None, stop_grad_z: bool = False):
@@ -471,13 +473,47 @@ class NeRF:
         """Video-path render (extension): only rgb (n,3), depth (n) = sum w z (src/ExecutionRun.py:346) and acc (n),
         for rays [ray_begin, ray_begin+n_rays) of the frame -- the unit a GPU takes when a frame is row-sharded."""
         n_total = h * w if n_rays is None else int(n_rays)
-        dirs, orig = get_rays_directions(h, w, fov, c2w, ray_begin=ray_begin, n_rays=n_total, return_origins=True)
         batch_size = batch_size_input if batch_size_input else self.batch_size_render
         if seed is None:
             seed, step = rng.next_step()
         n_c = n_render_samples_c if n_render_samples_c else self.n_render_samples_coarse
         n_f = n_render_samples_f if n_render_samples_f else self.n_render_samples_fine
         rgbs, depths, accs = [], [], []
+        mc, mf = self.model_coarse, self.model_fine
+        if self.rays_in_kernel and mc.tensor_core and (mf is None or mf.tensor_core):
+            # tensor-core modes: the MLP kernel generates its own rays from the camera (nerf_mlp_fwd_camera) -- ray generation,
+            # stratified depths, positions, encodings and the network are one kernel, no ray buffer exists
+            c2w_np = np.ascontiguousarray(c2w.detach().cpu().numpy() if isinstance(c2w, torch.Tensor) else np.asarray(c2w),
+                                          dtype=np.float32)
+            if c2w_np.shape != (4, 4):
+                raise ValueError("c2w must be a 4x4 camera-to-world matrix")
+            c2w_p = c2w_np.ctypes.data_as(ctypes.POINTER(ctypes.c_float))
+            f = lambda *shape: torch.empty(shape, dtype=torch.float32, device=self.device)
+
+            def mlp(net, off, n, s, z, z_out, raw):
+                half = net.infer_mode_id == _lib.MODE_FP16
+                call("nerf_mlp_fwd_camera", net.cfg_ref, ptr(net.packed_for(net.params, half=half)), c2w_p, float(fov), int(h),
+                     int(w), int(off), n, s, ptr(z), self.near_boundary, self.far_boundary, int(seed), int(step), ptr(z_out),
+                     ptr(raw), net.infer_mode_id)
+            with torch.no_grad():
+                for s0 in range(0, n_total, batch_size):
+                    n, off = min(batch_size, n_total - s0), ray_begin + s0
+                    z, raw = f(n, n_c), f(n, n_c, 4)
+                    mlp(mc, off, n, n_c, None, z, raw)
+                    rgb, wts, depth, acc = _unrf.ray_marching_lean(raw, z)
+                    if mf is not None:
+                        z_f = get_z_vals_from_prob_dist_func(wts, z, n_f, seed=seed, step=step, ray_offset=off)
+                        z_all, raw_f = f(n, n_f + n_c), f(n, n_f + n_c, 4)
+                        call("nerf_merge_sorted", ptr(z_f), n_f, ptr(z), n_c, n, ptr(z_all))
+                        mlp(mf, off, n, n_f + n_c, z_all, None, raw_f)
+                        rgb, wts, depth, acc = _unrf.ray_marching_lean(raw_f, z_all)
+                    rgbs.append(rgb)
+                    depths.append(depth)
+                    accs.append(acc)
+            if not rgbs:
+                return f(0, 3), f(0), f(0)
+            return torch.cat(rgbs), torch.cat(depths), torch.cat(accs)
+        dirs, orig = get_rays_directions(h, w, fov, c2w, ray_begin=ray_begin, n_rays=n_total, return_origins=True)
         with torch.no_grad():
             for s0 in range(0, n_total, batch_size):
                 o, d = orig[s0:s0 + batch_size], dirs[s0:s0 + batch_size]

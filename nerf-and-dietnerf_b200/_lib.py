@@ -85,6 +85,8 @@ SIGNATURES = {
     "nerf_mlp_bwd_overlapped": (c_int32, [_CFG, _P, _P, _P, _P, _P, _P, c_int64, _P, _P, _P, c_int32, _P, _P]),
     "nerf_mlp_bwd_dx": (c_int32, [_CFG, _P, _P, _P, _P, _P, _P, c_int64, _P, _P, _P, c_int32, _P]),
     "nerf_mlp_bwd_dw": (c_int32, [_CFG, _P, _P, _P, _P, _P, _P, c_int64, _P, _P, _P, c_int32, _P]),
+    "nerf_mlp_fwd_camera": (c_int32, [_CFG, _P, POINTER(c_float), c_float, c_int32, c_int32, c_int64, c_int64, c_int32, _P, c_float, c_float,
+                                      c_uint64, c_uint32, _P, _P, c_int32, _P]),
     "nerf_mlp_bwd_rays": (c_int32, [_CFG, _P, _P, _P, _P, _P, _P, c_int64, c_int32, _P, _P, c_int32, _P, c_int32, c_int32, _P, _P]),
     "nerf_debug_bwd_pipe_layer": (c_int32, [_CFG, _P, _P, c_int64, _P, c_int32, _P, _P]),
     "nerf_packed_bytes": (c_int64, [_CFG]),

@@ -59,6 +59,35 @@ struct BwdRays {
   int32_t accumulate;      // 1: d_z += (the compositing backward wrote its share first)
 };
 
+// Pinhole ray of pixel index r = y w + x (get_rays_directions, src/UtilsCV.py:467-499): ONE definition for the stand-alone
+// generator (rays.cu) and for the MLP prologue that generates its rays itself (nerf_mlp_fwd_camera), so the two agree bit
+// for bit.  c2w: row-major 4 x 4.
+__device__ __forceinline__ float4 pinhole_ray_dir(const float* c2w, float tan_half_fov, int h, int w, int64_t r) {
+  const int y = (int)(r / w), x = (int)(r - (int64_t)y * w);
+  const float xr = __fadd_rn((float)x, 0.5f), yr = __fadd_rn((float)y, 0.5f);
+  const float x_ndc = __fdiv_rn(xr, (float)w), y_ndc = __fdiv_rn(yr, (float)h);
+  const float xs = __fsub_rn(__fmul_rn(2.f, x_ndc), 1.f);
+  const float ys = __fsub_rn(1.f, __fmul_rn(2.f, y_ndc));
+  const float d0 = __fmul_rn(xs, tan_half_fov), d1 = __fmul_rn(ys, tan_half_fov), d2 = -1.f, d3 = 0.f;
+  float o[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    float acc = __fmul_rn(c2w[k * 4 + 0], d0);
+    acc = __fadd_rn(acc, __fmul_rn(c2w[k * 4 + 1], d1));
+    acc = __fadd_rn(acc, __fmul_rn(c2w[k * 4 + 2], d2));
+    acc = __fadd_rn(acc, __fmul_rn(c2w[k * 4 + 3], d3));
+    o[k] = acc;
+  }
+  return make_float4(o[0], o[1], o[2], o[3]);
+}
+// the camera behind the rays of a forward call (nerf_mlp_fwd_camera): ray i of the call is pixel ray_begin + i
+struct CameraRays {
+  float c2w[16];
+  float tan_half_fov;
+  int32_t h, w;
+  int64_t ray_begin;
+};
+
 // coarse depths drawn inside the MLP prologue (nerf_mlp_fwd_rays_stratified)
 struct StratifiedZ {
   float z_start, z_end;

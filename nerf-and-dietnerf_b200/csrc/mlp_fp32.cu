@@ -14,7 +14,7 @@ int mlp_tc_bwd(const nerf_net_cfg* cfg, const NetGeom& g, const float* params, c
                void* workspace, cudaStream_t st, int parts, cudaStream_t side, bool half, const BwdRays* rays = nullptr);
 int mlp_tc_fwd_rays(const nerf_net_cfg* cfg, const NetGeom& g, const void* packed, const float* origs4, const float* dirs4,
                     const float* z, int64_t n_rays, int n_samples, float* out4, void* saved, cudaStream_t st, bool half,
-                    const StratifiedZ* gen = nullptr);
+                    const StratifiedZ* gen = nullptr, const CameraRays* cam = nullptr);
 int64_t mlp_tc_saved_bytes(const NetGeom& g, int64_t m);
 int64_t mlp_tc_workspace_bytes(const NetGeom& g, int64_t m, int backward);
 
@@ -392,6 +392,30 @@ int nerf_mlp_fwd_rays_stratified(const nerf_net_cfg* cfg, const void* packed, co
   StratifiedZ gen = {z_start, z_end, seed, ray_offset, step, z_out};
   return mlp_tc_fwd_rays(cfg, g, packed, origs4, dirs4, nullptr, n_rays, n_samples, out4, saved_or_null, (cudaStream_t)stream,
                          mode == NERF_MODE_FP16, &gen);
+}
+
+int nerf_mlp_fwd_camera(const nerf_net_cfg* cfg, const void* packed, const float* c2w_host, float fov, int32_t h, int32_t w,
+                        int64_t ray_begin, int64_t n_rays, int32_t n_samples, const float* z_or_null, float z_start, float z_end,
+                        uint64_t seed, uint32_t step, float* z_out_or_null, float* out4, int32_t mode, void* stream) {
+  NetGeom g;
+  NERF_CHECK_ARG(make_geom(cfg, &g), "bad net config");
+  NERF_CHECK_ARG(packed && c2w_host && out4 && (z_or_null || z_out_or_null), "null pointer");
+  NERF_CHECK_ARG(h > 0 && w > 0 && ray_begin >= 0 && n_rays >= 0 && ray_begin + n_rays <= (int64_t)h * w && n_samples > 0,
+                 "ray range outside the image");
+  if (mode != NERF_MODE_BF16 && mode != NERF_MODE_FP16) {
+    set_error("nerf_mlp_fwd_camera: only the tensor-core modes generate their rays in the MLP kernel "
+              "(fp32 mode: nerf_ray_directions + nerf_encode_samples + nerf_mlp_fwd)");
+    return NERF_E_UNSUPPORTED;
+  }
+  if (n_rays == 0) return NERF_OK;
+  CameraRays cam;
+  for (int i = 0; i < 16; ++i) cam.c2w[i] = c2w_host[i];
+  cam.tan_half_fov = tanf(fov / 2.0f);
+  cam.h = h; cam.w = w; cam.ray_begin = ray_begin;
+  // depths: given, or drawn in the prologue from the Philox stream of pixel ray_begin + i (nerf_mlp_fwd_rays_stratified)
+  StratifiedZ gen = {z_start, z_end, seed, (uint64_t)ray_begin, step, z_out_or_null};
+  return mlp_tc_fwd_rays(cfg, g, packed, nullptr, nullptr, z_or_null, n_rays, n_samples, out4, nullptr, (cudaStream_t)stream,
+                         mode == NERF_MODE_FP16, z_or_null ? nullptr : &gen, &cam);
 }
 
 // parts: bit 0 = input-gradient chain (dZ of every layer, d_xyz_enc), bit 1 = weight gradients from the saved activations

@@ -148,7 +148,23 @@ struct FwdInput {
   uint32_t step;
   uint64_t seed, ray_offset;
   float* z_out;
+  int32_t cam;             // 1: the rays are generated here from `camera` (origs / dirs unused)
+  CameraRays camera;
 };
+
+// origin / direction of ray `ray` of the call: read, or generated from the camera (pinhole_ray_dir: the arithmetic of
+// nerf_ray_directions, bit for bit).  A real call for the same reason as draw_stratified_z.
+__device__ __noinline__ float4 camera_dir(const float* c2w, float tan_half_fov, int h, int w, int64_t r) {
+  return pinhole_ray_dir(c2w, tan_half_fov, h, w, r);
+}
+__device__ __forceinline__ float4 ray_dir(const FwdInput& in, int64_t ray) {
+  if (!in.cam) return __ldg(in.dirs + ray);
+  return camera_dir(in.camera.c2w, in.camera.tan_half_fov, in.camera.h, in.camera.w, in.camera.ray_begin + ray);
+}
+__device__ __forceinline__ float4 ray_orig(const FwdInput& in, int64_t ray) {
+  if (!in.cam) return __ldg(in.origs + ray);
+  return make_float4(in.camera.c2w[3], in.camera.c2w[7], in.camera.c2w[11], in.camera.c2w[15]);
+}
 
 // A real call on purpose: inlined, the ten Philox rounds cost the kernel's hot loops their last spare registers (96 cap).
 __device__ __noinline__ float draw_stratified_z(float z_start, float z_end, float span, int n_samples, int s, uint64_t seed,
@@ -491,9 +507,9 @@ mlp_tc_fwd_kernel(const __grid_constant__ TcPlan plan, const uint8_t* __restrict
         // column indices and leaves as 16-byte chunks
         const uint32_t prow = inp_u32 + r * 128;
         const int64_t ray = row_ok ? row / in.n_samples : 0;
-        const float4 d = row_ok ? __ldg(in.dirs + ray) : make_float4(0.f, 0.f, 0.f, 0.f);
+        const float4 d = row_ok ? ray_dir(in, ray) : make_float4(0.f, 0.f, 0.f, 0.f);
         if (half == 0) {
-          const float4 o = row_ok ? __ldg(in.origs + ray) : make_float4(0.f, 0.f, 0.f, 0.f);
+          const float4 o = row_ok ? ray_orig(in, ray) : make_float4(0.f, 0.f, 0.f, 0.f);
           const float zz = row_ok ? row_depth(in, row, ray) : 0.f;
           float v[40];
 #pragma unroll
@@ -545,9 +561,9 @@ mlp_tc_fwd_kernel(const __grid_constant__ TcPlan plan, const uint8_t* __restrict
             }
           } else {
             const int64_t ray = row / in.n_samples;
-            const float4 d = __ldg(in.dirs + ray);
+            const float4 d = ray_dir(in, ray);
             if (half == 0) {
-              const float4 o = __ldg(in.origs + ray);
+              const float4 o = ray_orig(in, ray);
               const float zz = row_depth(in, row, ray);
               const int per = 1 + 2 * in.Lx;
 #pragma unroll
@@ -805,9 +821,10 @@ int mlp_tc_fwd(const nerf_net_cfg* cfg, const NetGeom& g, const float* params, c
 
 int mlp_tc_fwd_rays(const nerf_net_cfg* cfg, const NetGeom& g, const void* packed, const float* origs4, const float* dirs4,
                     const float* z, int64_t n_rays, int n_samples, float* out4, void* saved, cudaStream_t st, bool half,
-                    const StratifiedZ* gen) {
+                    const StratifiedZ* gen, const CameraRays* cam) {
   FwdInput in = {};
   in.origs = (const float4*)origs4; in.dirs = (const float4*)dirs4; in.z = z; in.n_samples = n_samples;
+  if (cam) { in.cam = 1; in.camera = *cam; }
   if (gen) {
     in.gen_z = 1; in.z_start = gen->z_start; in.z_end = gen->z_end;
     // (z_end - z_start) is formed in double from the Python floats and then cast (src/UtilsCV.py:580), as in nerf_stratified_z

@@ -21,23 +21,7 @@ __global__ void ray_directions_kernel(C2W c2w, float tan_half_fov, int h, int w,
                                       float* __restrict__ dirs4, float* __restrict__ origs4) {
   int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i >= n_rays) return;
-  int64_t r = ray_begin + i;
-  int y = (int)(r / w), x = (int)(r % w);
-  float xr = __fadd_rn((float)x, 0.5f), yr = __fadd_rn((float)y, 0.5f);
-  float x_ndc = __fdiv_rn(xr, (float)w), y_ndc = __fdiv_rn(yr, (float)h);
-  float xs = __fsub_rn(__fmul_rn(2.f, x_ndc), 1.f);
-  float ys = __fsub_rn(1.f, __fmul_rn(2.f, y_ndc));
-  float d0 = __fmul_rn(xs, tan_half_fov), d1 = __fmul_rn(ys, tan_half_fov), d2 = -1.f, d3 = 0.f;
-  float4 out;
-  float* o = reinterpret_cast<float*>(&out);
-#pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    float acc = __fmul_rn(c2w.m[k * 4 + 0], d0);
-    acc = __fadd_rn(acc, __fmul_rn(c2w.m[k * 4 + 1], d1));
-    acc = __fadd_rn(acc, __fmul_rn(c2w.m[k * 4 + 2], d2));
-    acc = __fadd_rn(acc, __fmul_rn(c2w.m[k * 4 + 3], d3));
-    o[k] = acc;
-  }
+  const float4 out = pinhole_ray_dir(c2w.m, tan_half_fov, h, w, ray_begin + i);
   reinterpret_cast<float4*>(dirs4)[i] = out;
   if (origs4) reinterpret_cast<float4*>(origs4)[i] = make_float4(c2w.m[3], c2w.m[7], c2w.m[11], c2w.m[15]);
 }

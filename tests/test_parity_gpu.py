@@ -1370,6 +1370,37 @@ def test_fused_coarse_pass_draws_the_same_depths(pkg, mode, n_rays, s):
     assert torch.equal(z.cpu(), O.get_z_values(NEAR, FAR, n_rays, s, jit)), "Philox stream differs from the oracle's"
 
 
+@pytest.mark.parametrize("mode,n_angles", [("fp16", 2), ("bf16", 2), ("fp16", 0), ("fp16", 1)])
+def test_rays_generated_inside_the_mlp_kernel(pkg, mode, n_angles):
+    """render_image_lean with the rays generated in the MLP prologue (nerf_mlp_fwd_camera: get_rays_directions +
+    get_z_values + sample_along_rays + encodings + network in one kernel) against the same render from ray buffers
+    (nerf_ray_directions + nerf_mlp_fwd_rays[_stratified]): bit-identical, for a whole frame in ragged batches and for a
+    row-sharded range."""
+    import numpy as np
+    ncfg = net_config()
+    ncfg["n_angles_for_model"] = n_angles
+    model = pkg.NeRFModel(ncfg, render_config(), NEAR, FAR, seed=5, mode=mode)
+    c2w = np.eye(4, dtype=np.float32)
+    c2w[:3, :3] = np.array([[0.36, 0.48, -0.8], [-0.8, 0.6, 0.0], [0.48, 0.64, 0.6]], dtype=np.float32)
+    c2w[:3, 3] = [0.1, -0.2, 1.3]
+    h, w = 30, 41
+    for kwargs in ({}, {"ray_begin": 123, "n_rays": 777}, {"ray_begin": h * w - 5, "n_rays": 5}):
+        outs = []
+        for in_kernel in (True, False):
+            model.rays_in_kernel = in_kernel
+            outs.append(model.render_image_lean(c2w, 0.6, h, w, 500, 16, 24, seed=3, step=2, **kwargs))
+        for a, b in zip(*outs):
+            assert torch.equal(a, b), kwargs
+    # the fp32 parity mode keeps the ray buffers
+    m32 = pkg.NeRFModel(net_config(), render_config(), NEAR, FAR, seed=5, mode="fp32")
+    rgb, depth, acc = m32.render_image_lean(c2w, 0.6, 8, 8, 64, 8, 8, seed=3, step=2)
+    assert rgb.shape == (64, 3) and torch.isfinite(rgb).all()
+    with pytest.raises(pkg.NerfLibraryError):
+        net = m32.model_coarse
+        pkg._lib.call("nerf_mlp_fwd_camera", net.cfg_ref, pkg._lib.ptr(net.params), c2w.ctypes.data_as(__import__("ctypes").POINTER(__import__("ctypes").c_float)),
+                      0.6, 8, 8, 0, 64, 8, None, NEAR, FAR, 3, 2, pkg._lib.ptr(depth), pkg._lib.ptr(rgb), 0)
+
+
 def test_two_devices_in_one_process(pkg):
     """The ABI's per-device state (SM count, the kernels' shared-memory attribute: csrc/api.cu device_first_use) with two
     GPUs driven from ONE process: the second device's first tensor-core call must not inherit 'already configured' from
