@@ -268,7 +268,7 @@ __device__ __forceinline__ uint4 half8_to_bf16(uint4 v) {
 // kXyz: the xyz-only network (src/NeRF.py:248-288): ten layers, no view columns, sigma head = a dot product with h8 in the
 // epilogue of layer 7 (partial sums ride in a register to the last layer).
 template <bool kSave, bool kHalf, bool kXyz>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreadsFwd, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(fwd_threads(kSave, kHalf), 1)
 mlp_tc_fwd_kernel(const __grid_constant__ TcPlan plan, const uint8_t* __restrict__ packed,
                   const __grid_constant__ FwdInput in, int64_t M, float* __restrict__ out4, uint8_t* __restrict__ saved,
                   float alpha, uint32_t dbg) {
@@ -291,7 +291,7 @@ mlp_tc_fwd_kernel(const __grid_constant__ TcPlan plan, const uint8_t* __restrict
       mbar_init(smem_u32(&bars->act_ready[t]), 2 * 8);   // leader's copy: one arrive per epilogue warp of BOTH CTAs
       mbar_init(smem_u32(&bars->acc_full[t]), 1);
       mbar_init(smem_u32(&bars->panel_full[t]), 8);      // one arrive per epilogue warp of the tile
-      mbar_init(smem_u32(&bars->panel_free[t]), kStoreWarps);   // every store warp
+      mbar_init(smem_u32(&bars->panel_free[t]), fwd_store_warps(kSave, kHalf));   // every store warp
     }
     fence_barrier_init();
   }
@@ -465,8 +465,9 @@ mlp_tc_fwd_kernel(const __grid_constant__ TcPlan plan, const uint8_t* __restrict
             mbar_wait(smem_u32(&bars->panel_full[t]), ph);
             if (do_store) {
 #pragma unroll 8
-              for (int it = 0; it < 128 / kStoreWarps; ++it) {
-                const int j = hw * (32 / kStoreWarps) + (it >> 2), r = (it & 3) * 32 + lane;     // 16-byte column chunk, row
+              constexpr int kSW = fwd_store_warps(kSave, kHalf);
+              for (int it = 0; it < 128 / kSW; ++it) {
+                const int j = hw * (32 / kSW) + (it >> 2), r = (it & 3) * 32 + lane;     // 16-byte column chunk, row
                 const float4 v = lds128f(act_u32 + (j >> 3) * kPanelBytes + r * 128 + (((j & 7) ^ (r & 7)) << 4));
                 uint4 w = make_uint4(__float_as_uint(v.x), __float_as_uint(v.y), __float_as_uint(v.z), __float_as_uint(v.w));
                 if (kHalf) w = half8_to_bf16(w);          // the backward reads bf16
@@ -792,7 +793,7 @@ static int launch_fwd(const nerf_net_cfg* cfg, const NetGeom& g, const void* pac
   const uint8_t* pk = (const uint8_t*)packed + (half ? half_region_offset(plan) : 0u);
   const uint32_t dbg = tc_debug_flags();
 #define NERF_LAUNCH_FWD(SAVE, HALF, XYZ)                                                                                  \
-  mlp_tc_fwd_kernel<SAVE, HALF, XYZ><<<grid, kThreadsFwd, kSmemAlloc, st>>>(plan, pk, in, m, out4, (uint8_t*)saved,       \
+  mlp_tc_fwd_kernel<SAVE, HALF, XYZ><<<grid, fwd_threads(SAVE, HALF), kSmemAlloc, st>>>(plan, pk, in, m, out4, (uint8_t*)saved,       \
                                                                             cfg->leaky_alpha, dbg)
   const int variant = (saved ? 1 : 0) | (half ? 2 : 0) | (plan.xyz_only ? 4 : 0);
   switch (variant) {

@@ -51,6 +51,12 @@ constexpr int kWarpStore = 18;                    // warps 18 ...: train-mode co
 #endif
 constexpr int kStoreWarps = NERF_STORE_WARPS;     // every store warp works on every copy (32 / kStoreWarps column chunks each)
 constexpr int kThreadsFwd = (18 + kStoreWarps) * 32;   // 20 warps = 5 per SM sub-partition: the register cap stays at 96
+// The forward that saves activations in the fp16 mode converts every value to bf16 on its way out (the backward is the bf16
+// one): 12 more instructions per 16 bytes, and two store warps no longer keep up (771 vs 918 TFLOP/s at 524 k rows).  That
+// variant runs four store warps (22 warps -> 80 registers, 24 bytes of spills): 871 TFLOP/s.  Every other variant keeps
+// two: with bf16 operands four change nothing, and the chain kernel loses 5 % to the spills of the smaller register file.
+__host__ __device__ constexpr int fwd_store_warps(bool save, bool half) { return save && half ? 4 : kStoreWarps; }
+__host__ __device__ constexpr int fwd_threads(bool save, bool half) { return (18 + fwd_store_warps(save, half)) * 32; }
 // Saved activations of one 128-row tile (forward -> backward), bf16:
 //   block 0            input panel (xyz | view encodings), [128 rows][64 cols] in the 128-byte-swizzled smem layout (16 KB)
 //   blocks h_1 .. h_9  64 KB each, "row-block chunk-major" (RBCM): [row half 0/1][16-byte column chunk j][row 0..63][8 cols].
