@@ -55,7 +55,10 @@ constexpr int kThreadsFwd = (18 + kStoreWarps) * 32;   // 20 warps = 5 per SM su
 // one): 12 more instructions per 16 bytes, and two store warps no longer keep up (771 vs 918 TFLOP/s at 524 k rows).  That
 // variant runs four store warps (22 warps -> 80 registers, 24 bytes of spills): 871 TFLOP/s.  Every other variant keeps
 // two: with bf16 operands four change nothing, and the chain kernel loses 5 % to the spills of the smaller register file.
-__host__ __device__ constexpr int fwd_store_warps(bool save, bool half) { return save && half ? 4 : kStoreWarps; }
+#ifndef NERF_FWD_HALF_STORE_WARPS
+#define NERF_FWD_HALF_STORE_WARPS 4
+#endif
+__host__ __device__ constexpr int fwd_store_warps(bool save, bool half) { return save && half ? NERF_FWD_HALF_STORE_WARPS : kStoreWarps; }
 __host__ __device__ constexpr int fwd_threads(bool save, bool half) { return (18 + fwd_store_warps(save, half)) * 32; }
 // Saved activations of one 128-row tile (forward -> backward), bf16:
 //   block 0            input panel (xyz | view encodings), [128 rows][64 cols] in the 128-byte-swizzled smem layout (16 KB)
