@@ -466,8 +466,8 @@ mlp_tc_fwd_kernel(const __grid_constant__ TcPlan plan, const uint8_t* __restrict
             if (do_store) {
 #pragma unroll 8
               constexpr int kSW = fwd_store_warps(kSave, kHalf);
-              for (int it = hw; it < 128; it += kSW) {                 // the 128 (chunk, row group) pieces, dealt round-robin
-                const int j = it >> 2, r = (it & 3) * 32 + lane;       // 16-byte column chunk, row
+              for (int it = 0; it < 128 / kSW; ++it) {
+                const int j = hw * (32 / kSW) + (it >> 2), r = (it & 3) * 32 + lane;     // 16-byte column chunk, row
                 const float4 v = lds128f(act_u32 + (j >> 3) * kPanelBytes + r * 128 + (((j & 7) ^ (r & 7)) << 4));
                 uint4 w = make_uint4(__float_as_uint(v.x), __float_as_uint(v.y), __float_as_uint(v.z), __float_as_uint(v.w));
                 if (kHalf) w = half8_to_bf16(w);          // the backward reads bf16

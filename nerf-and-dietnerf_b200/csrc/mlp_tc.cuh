@@ -54,7 +54,8 @@ constexpr int kThreadsFwd = (18 + kStoreWarps) * 32;   // 20 warps = 5 per SM su
 // The forward that saves activations in the fp16 mode converts every value to bf16 on its way out (the backward is the bf16
 // one): 12 more instructions per 16 bytes, and two store warps no longer keep up (771 vs 918 TFLOP/s at 524 k rows).  That
 // variant runs four store warps (22 warps -> 80 registers, 24 bytes of spills): 871 TFLOP/s.  Every other variant keeps
-// two: with bf16 operands four change nothing, and the chain kernel loses 5 % to the spills of the smaller register file.
+// two: with bf16 operands four change nothing, and the chain kernel loses 5 % to the spills of the smaller register file
+// (three store warps do not help: 21 warps put six on one SM sub-partition, the same 80-register cap as 22).
 #ifndef NERF_FWD_HALF_STORE_WARPS
 #define NERF_FWD_HALF_STORE_WARPS 4
 #endif

@@ -388,8 +388,8 @@ mlp_tc_bwd_chain_kernel(const __grid_constant__ BwdPlan plan, const uint8_t* __r
           mbar_wait(smem_u32(&bars->panel_full[t]), ph);
           if (do_store) {
 #pragma unroll 8
-            for (int it = hw; it < 128; it += kStoreWarps) {           // the 128 (chunk, row group) pieces, dealt round-robin
-              const int j = it >> 2, r = (it & 3) * 32 + lane;         // 16-byte column chunk, row
+            for (int it = 0; it < 128 / kStoreWarps; ++it) {
+              const int j = hw * (32 / kStoreWarps) + (it >> 2), r = (it & 3) * 32 + lane;     // 16-byte column chunk, row
               const float4 v = lds128f(act_u32 + (j >> 3) * kPanelBytes + r * 128 + (((j & 7) ^ (r & 7)) << 4));
               stg128(gblock + rbcm_offset(r, j, 32),
                      make_uint4(__float_as_uint(v.x), __float_as_uint(v.y), __float_as_uint(v.z), __float_as_uint(v.w)));
