@@ -596,6 +596,15 @@ static void make_dw_plan(DwPlan* p, int n_ctas_total, bool xyz = false) {
     // measured per-CTA cycle counts (NERF_TC_DEBUG=320, all 148 CTAs streaming): a 64-row stage costs ~26 cycles per KB
     // plus ~700 cycles that do not shrink with the ring depth -> a 27 KB-equivalent overhead per stage
     u.cost = (float)((a_chunks == 0 ? 8 : a_chunks) + u.b_load) + 27.f;
+    // the view network's units, measured one by one (tools/dw_balance_probe.py, slowest CTA of the unit, cycles per tile
+    // relative to a 256 x 256 unit = 91; profiles/r02_ah_dw_balance.log): the short-N units cost more than their bytes say
+    // (Dense 8 + sigma head) and the input-panel / rgb-head units less
+    if (!xyz) {
+      if (out_kind == OUT_D8A) u.cost = 81.5f;
+      else if (out_kind == OUT_INP_XYZ) u.cost = 60.2f;
+      else if (out_kind == OUT_INP_VIEW) u.cost = 50.4f;
+      else if (out_kind == OUT_RGB) u.cost = 40.1f;
+    }
     const bool prologue_block = b_panel >= kDzPanelL;
     u.flag_idx = (int16_t)(prologue_block ? kHiddenSlots : b_panel / kActPanels);   // dz_panel(l) = (l - 1) kActPanels
     u.flag_target = (int16_t)(prologue_block ? kFlagTargetPrologue : kFlagTargetStore);
@@ -615,28 +624,27 @@ static void make_dw_plan(DwPlan* p, int n_ctas_total, bool xyz = false) {
     add(kSavedPanelHL, 16, kDzPanelOut, kDzChunksOut, 16, OUT_RGB, 9, 1);              // rgb head (Dense 9)
   }
   p->n_units = n;
-  // CTAs in proportion to the modelled cost (largest-remainder rounding, at least one each)
+  // CTAs by modelled cost: the floor of the proportional share (at least one each), then every CTA that is left goes to
+  // the unit with the largest cost per CTA -- the kernel ends with its slowest unit, so the split minimises the maximum
   float total = 0.f;
   for (int i = 0; i < n; ++i) total += p->u[i].cost;
   int used = 0;
-  float frac[16];
   for (int i = 0; i < n; ++i) {
-    const float share = (float)n_ctas_total * p->u[i].cost / total;
-    int c = (int)share;
+    int c = (int)((float)n_ctas_total * p->u[i].cost / total);
     if (c < 1) c = 1;
-    frac[i] = share - (float)c;
     p->u[i].n_ctas = (int16_t)c;
     used += c;
   }
+  auto load = [&](int i) { return p->u[i].cost / (float)p->u[i].n_ctas; };
   while (used < n_ctas_total) {
     int best = 0;
-    for (int i = 1; i < n; ++i) if (frac[i] > frac[best]) best = i;
-    p->u[best].n_ctas++; frac[best] -= 1.f; ++used;
+    for (int i = 1; i < n; ++i) if (load(i) > load(best)) best = i;
+    p->u[best].n_ctas++; ++used;
   }
-  while (used > n_ctas_total) {
+  while (used > n_ctas_total) {               // fewer CTAs than units x 1 would need: take from the lightest loads
     int best = -1;
-    for (int i = 0; i < n; ++i) if (p->u[i].n_ctas > 1 && (best < 0 || frac[i] < frac[best])) best = i;
-    p->u[best].n_ctas--; frac[best] += 1.f; --used;
+    for (int i = 0; i < n; ++i) if (p->u[i].n_ctas > 1 && (best < 0 || load(i) < load(best))) best = i;
+    p->u[best].n_ctas--; --used;
   }
   int first = 0;
   for (int i = 0; i < n; ++i) { p->u[i].first_cta = (int16_t)first; first += p->u[i].n_ctas; }
