@@ -499,7 +499,7 @@ def main():
         # bf16 dZ (8*256 + 144 + 16 columns) = 8896 B.  The launch time is the nerf_mlp_bwd_dw call (dW kernel + its
         # fixed-order reduce), averaged over the coarse (64 samples/ray) and fine (128) calls of a step, timed with CUDA
         # events in THIS run (the per-call pass above).  `traffic` is NOT measured in this run: it is the dram read+write
-        # of the same two launches in the committed ncu --set full capture (9660 B/sample), scaled to this batch.
+        # of the same two launches in the committed ncu --set full capture (9431 B/sample), scaled to this batch.
         samples_per_launch = batch * (N_C + N_F) / 2
         dw_ms = call_ms.get("nerf_mlp_bwd_dw", float("nan"))
         dx_ms = call_ms.get("nerf_mlp_bwd_dx", float("nan"))
@@ -533,10 +533,10 @@ def main():
             composite["frac"] = {k: composite[k] / peak_hbm for k in ("fwd_all_outputs", "fwd_lean", "bwd")}
         roofline = {"bound": "hbm", "kernel": "mlp_tc_bwd_dw_kernel (nerf_mlp_bwd_dw call)",
                     "achieved": ach, "peak": peak_hbm, "unit": "GB/s", "frac": ach / peak_hbm,
-                    "traffic": 9660 * samples_per_launch,
+                    "traffic": 9431 * samples_per_launch,
                     "traffic_source": "not measured in this run: dram__bytes_read+write of these two launches in "
-                                      "profiles/r02_n_mlp_full_summary.txt (ncu --set full of the same command): "
-                                      "2.506 + 5.091 GB for 262144 + 524288 samples = 9660 B/sample",
+                                      "profiles/r02_al_mlp_full_summary.txt (ncu --set full of the same command): "
+                                      "2.432 + 4.985 GB for 262144 + 524288 samples = 9431 B/sample",
                     "peak_source": "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6.5 TB/s",
                     "algorithmic_bytes_per_launch": 8896 * samples_per_launch,
                     "tensor_kernels": tensor,
