@@ -109,7 +109,7 @@ __device__ __forceinline__ void bitonic_sort_rows(const float* szs, int Nf, int 
           const unsigned long long o = __shfl_xor_sync(kFullMask, k[i], lane_stride);
           const bool asc = (((lane * E + i) & size) == 0) || size == 32 * E;
           const bool take_min = lower == asc;
-          k[i] = take_min ? (o < k[i] ? o : k[i]) : (o > k[i] ? o : k[i]);
+          k[i] = ((o < k[i]) == take_min) ? o : k[i];                 // min or max with ONE compare (equal keys: either)
         }
       } else {
 #pragma unroll
