@@ -37,8 +37,22 @@ __device__ __forceinline__ float warp_sum(float v) {
 
 // sigmoid and exp(-sigma*delta) on the SFU (ex2.approx / rcp.approx, ~2 ulp): the kernels are issue-bound, not
 // HBM-bound, with libm's expf and an IEEE division per colour channel; the absolute error (< 2e-7) is below the
-// 2e-6 parity bound of the compositing tests and far below the 1e-5 render bound.
-__device__ __forceinline__ float sigmoidf_(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+// 2e-6 parity bound of the compositing tests and far below the 1e-5 render bound.  The .ftz forms are used directly:
+// __expf / __fdividef wrap every MUFU in a denormal-range test and two predicated scalings (three issue slots per
+// call, twelve per 32-sample block), and a flushed denormal changes nothing here (1 + 1e-39 and 1 - 1e-39 are 1).
+__device__ __forceinline__ float ex2_ftz(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float rcp_ftz(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+constexpr float kLog2e = 1.4426950408889634f;
+__device__ __forceinline__ float exp_neg(float x) { return ex2_ftz(x * -kLog2e); }          // exp(-x)
+__device__ __forceinline__ float sigmoidf_(float x) { return rcp_ftz(1.0f + exp_neg(x)); }
 
 // per-sample forward quantities
 struct SampleFwd {
@@ -49,7 +63,7 @@ __device__ __forceinline__ SampleFwd sample_fwd(float raw_sigma, float z_cur, fl
   SampleFwd r;
   r.sigma = fmaxf(raw_sigma, 0.f);
   r.delta = last ? 1e9f : z_next - z_cur;
-  r.alpha = 1.0f - __expf(-r.sigma * r.delta);
+  r.alpha = 1.0f - exp_neg(r.sigma * r.delta);
   r.x = 1.0f - r.alpha;
   return r;
 }
@@ -76,8 +90,15 @@ __device__ __forceinline__ void block_accumulate(float warp_value, int lane, flo
   }
 }
 
-template <int C, bool kLoss>
-__global__ void __launch_bounds__(256) composite_fwd_kernel(const float4* __restrict__ raw4, const float* __restrict__ z,
+// kExtras = false: cumprod, alpha_out and rgb_s are all null (the lean call of render / train), so the per-block pointer
+// tests (two 64-bit compares each) are compiled out.  kExact: S == 32 C (64, 128, 192, 256: every train / render shape
+// of the reference configs), so every `s < S` test, its selects and the predicate spills they cause are compiled out too.
+#ifndef NERF_COMPOSITE_FWD_MIN_BLOCKS
+#define NERF_COMPOSITE_FWD_MIN_BLOCKS 5   // 48 registers: 40 resident warps per SM instead of 32 (S = 192 lean: 8 bytes of spill)
+#endif
+template <int C, bool kLoss, bool kExtras, bool kExact>
+__global__ void __launch_bounds__(256, (C <= 4 || (C <= 6 && !kExtras && !kLoss)) ? NERF_COMPOSITE_FWD_MIN_BLOCKS : 1)
+composite_fwd_kernel(const float4* __restrict__ raw4, const float* __restrict__ z,
                                                             int64_t n_rays, int S, float* __restrict__ rgb,
                                                             float* __restrict__ weights, float* __restrict__ cumprod,
                                                             float* __restrict__ alpha_out, float* __restrict__ rgb_s,
@@ -96,7 +117,7 @@ __global__ void __launch_bounds__(256) composite_fwd_kernel(const float4* __rest
 #pragma unroll
   for (int k = 0; k < C; ++k) {
     int s = k * 32 + lane;
-    if (s < S) {
+    if (kExact || s < S) {
       raw[k] = __ldcs(raw_r + s);
       zc[k] = __ldcs(z_r + s);
     } else {
@@ -109,13 +130,13 @@ __global__ void __launch_bounds__(256) composite_fwd_kernel(const float4* __rest
 #pragma unroll
   for (int k = 0; k < C; ++k) {
     int s = k * 32 + lane;
-    if (k * 32 >= S) break;
+    if (!kExact && k * 32 >= S) break;
     // z of the next sample: lane+1 of this block, or lane 0 of the next block
     float z_next = __shfl_down_sync(kFull, zc[k], 1);
     float z_next_blk = (k + 1 < C) ? __shfl_sync(kFull, zc[(k + 1 < C) ? k + 1 : k], 0) : 0.f;
     if (lane == 31) z_next = z_next_blk;
-    bool valid = s < S;
-    SampleFwd f = sample_fwd(raw[k].w, zc[k], z_next, s == S - 1);
+    const bool valid = kExact || s < S;
+    SampleFwd f = sample_fwd(raw[k].w, zc[k], z_next, kExact ? (k == C - 1 && lane == 31) : (s == S - 1));
     float x = valid ? f.x : 1.0f;
     float incl = warp_incl_scan_mul(x, lane);
     float excl = __shfl_up_sync(kFull, incl, 1);
@@ -125,16 +146,16 @@ __global__ void __launch_bounds__(256) composite_fwd_kernel(const float4* __rest
     if (valid && active) {
       float w = f.alpha * T;
       float cr = sigmoidf_(raw[k].x), cg = sigmoidf_(raw[k].y), cb = sigmoidf_(raw[k].z);
-      r_acc += w * cr;
-      g_acc += w * cg;
-      b_acc += w * cb;
-      d_acc += w * zc[k];
+      r_acc = __fmaf_rn(w, cr, r_acc);      // explicit contractions: every instantiation (fused loss or not, exact
+      g_acc = __fmaf_rn(w, cg, g_acc);      // block count or not) must round identically - the fused-kernel tests
+      b_acc = __fmaf_rn(w, cb, b_acc);      // compare them bit for bit
+      d_acc = __fmaf_rn(w, zc[k], d_acc);
       a_acc += w;
       int64_t o = ray * S + s;
       if (weights) __stcs(weights + o, w);
-      if (cumprod) __stcs(cumprod + o, T);
-      if (alpha_out) __stcs(alpha_out + o, f.alpha);
-      if (rgb_s) {
+      if (kExtras && cumprod) __stcs(cumprod + o, T);
+      if (kExtras && alpha_out) __stcs(alpha_out + o, f.alpha);
+      if (kExtras && rgb_s) {
         __stcs(rgb_s + o * 3 + 0, cr);
         __stcs(rgb_s + o * 3 + 1, cg);
         __stcs(rgb_s + o * 3 + 2, cb);
@@ -173,8 +194,12 @@ __global__ void __launch_bounds__(256) composite_fwd_kernel(const float4* __rest
 
 // kLoss: the ray's colour, its MSE against `target` and d_rgb are computed HERE from the forward scan the backward
 // repeats anyway, so composite_fwd + mse + composite_bwd of the fine network are one launch (rgb_out optional).
-template <int C, bool kLoss>
-__global__ void __launch_bounds__(256, (C <= 4 ? 4 : (C <= 6 ? 3 : 1))) composite_bwd_kernel(const float4* __restrict__ raw4, const float* __restrict__ z,
+#ifndef NERF_COMPOSITE_BWD6_MIN_BLOCKS
+#define NERF_COMPOSITE_BWD6_MIN_BLOCKS 3
+#endif
+template <int C, bool kLoss, bool kExact>
+__global__ void __launch_bounds__(256, (C <= 4 ? 4 : (C <= 6 ? NERF_COMPOSITE_BWD6_MIN_BLOCKS : 1)))
+composite_bwd_kernel(const float4* __restrict__ raw4, const float* __restrict__ z,
                                                             const float* __restrict__ d_rgb,
                                                             const float* __restrict__ d_weights, int64_t n_rays, int S,
                                                             float4* __restrict__ d_raw4, float* __restrict__ d_z,
@@ -195,7 +220,7 @@ __global__ void __launch_bounds__(256, (C <= 4 ? 4 : (C <= 6 ? 3 : 1))) composit
 #pragma unroll
   for (int k = 0; k < C; ++k) {
     int s = k * 32 + lane;
-    if (s < S) {
+    if (kExact || s < S) {
       raw[k] = __ldcs(raw_r + s);
       zc[k] = __ldcs(z_r + s);
     } else {
@@ -212,8 +237,8 @@ __global__ void __launch_bounds__(256, (C <= 4 ? 4 : (C <= 6 ? 3 : 1))) composit
     float z_next = __shfl_down_sync(kFull, zc[k], 1);
     float z_next_blk = __shfl_sync(kFull, zc[(k + 1 < C) ? k + 1 : k], 0);
     if (lane == 31) z_next = z_next_blk;
-    bool valid = s < S;
-    f[k] = sample_fwd(raw[k].w, zc[k], z_next, s == S - 1);
+    const bool valid = kExact || s < S;
+    f[k] = sample_fwd(raw[k].w, zc[k], z_next, kExact ? (k == C - 1 && lane == 31) : (s == S - 1));
     float x = valid ? f[k].x : 1.0f;
     float incl = warp_incl_scan_mul(x, lane);
     float excl = __shfl_up_sync(kFull, incl, 1);
@@ -224,9 +249,9 @@ __global__ void __launch_bounds__(256, (C <= 4 ? 4 : (C <= 6 ? 3 : 1))) composit
     col_r[k] = cr; col_g[k] = cg; col_b[k] = cb;
     if (kLoss && valid) {
       const float w = f[k].alpha * T[k];
-      r_acc += w * cr;
-      g_acc += w * cg;
-      b_acc += w * cb;
+      r_acc = __fmaf_rn(w, cr, r_acc);
+      g_acc = __fmaf_rn(w, cg, g_acc);
+      b_acc = __fmaf_rn(w, cb, b_acc);
     }
   }
   if (kLoss) {
@@ -248,8 +273,8 @@ __global__ void __launch_bounds__(256, (C <= 4 ? 4 : (C <= 6 ? 3 : 1))) composit
 #pragma unroll
   for (int k = 0; k < C; ++k) {
     int s = k * 32 + lane;
-    bool valid = s < S;
-    float gi = dr * col_r[k] + dg * col_g[k] + db * col_b[k];
+    const bool valid = kExact || s < S;
+    float gi = __fmaf_rn(db, col_b[k], __fmaf_rn(dg, col_g[k], __fmul_rn(dr, col_r[k])));
     if (d_weights && valid) gi += __ldcs(d_weights + ray * S + s);
     g[k] = valid ? gi : 0.f;
     gw[k] = valid ? gi * f[k].alpha * T[k] : 0.f;
@@ -260,7 +285,7 @@ __global__ void __launch_bounds__(256, (C <= 4 ? 4 : (C <= 6 ? 3 : 1))) composit
 #pragma unroll
   for (int k = C - 1; k >= 0; --k) {
     int s = k * 32 + lane;
-    bool valid = s < S;
+    const bool valid = kExact || s < S;
     float incl = warp_incl_rscan_add(gw[k], lane);
     float excl = __shfl_down_sync(kFull, incl, 1);
     if (lane == 31) excl = 0.f;
@@ -268,9 +293,10 @@ __global__ void __launch_bounds__(256, (C <= 4 ? 4 : (C <= 6 ? 3 : 1))) composit
     rcarry += __shfl_sync(kFull, incl, 0);
     float x = f[k].x;
     // TF: d cumprod / d x = div_no_nan(R, x); d alpha = g*T - that
-    float dalpha = g[k] * T[k] - (x == 0.f ? 0.f : R / x);
-    float dsig = dalpha * x * f[k].delta;
-    float ddel = (s == S - 1) ? 0.f : dalpha * x * f[k].sigma;
+    // x = 1 - alpha is 0 or >= 2^-24, never denormal
+    float dalpha = __fmaf_rn(g[k], T[k], -(x == 0.f ? 0.f : __fmul_rn(R, rcp_ftz(x))));
+    float dsig = __fmul_rn(__fmul_rn(dalpha, x), f[k].delta);
+    float ddel = (kExact ? (k == C - 1 && lane == 31) : (s == S - 1)) ? 0.f : dalpha * x * f[k].sigma;
     ddelta[k] = valid ? ddel : 0.f;
     if (valid && active) {
       float w = f[k].alpha * T[k];
@@ -291,36 +317,51 @@ __global__ void __launch_bounds__(256, (C <= 4 ? 4 : (C <= 6 ? 3 : 1))) composit
       float prev = __shfl_up_sync(kFull, ddelta[k], 1);
       float prev_blk = __shfl_sync(kFull, ddelta[(k > 0) ? k - 1 : 0], 31);
       if (lane == 0) prev = (k > 0) ? prev_blk : 0.f;
-      if (s < S && active) __stcs(d_z + ray * S + s, prev - ddelta[k]);
+      if ((kExact || s < S) && active) __stcs(d_z + ray * S + s, prev - ddelta[k]);
     }
   }
 }
 
-template <int C>
-static int launch_fwd(const float* raw4, const float* z, int64_t n, int S, float* rgb, float* w, float* T, float* a,
-                      float* rgb_s, float* depth, float* acc, const LossArgs* loss, cudaStream_t st) {
+template <int C, bool kExact>
+static int launch_fwd_(const float* raw4, const float* z, int64_t n, int S, float* rgb, float* w, float* T, float* a,
+                       float* rgb_s, float* depth, float* acc, const LossArgs* loss, cudaStream_t st) {
   const int warps = 8;
   const unsigned grid = (unsigned)ceil_div(n, warps);
   if (loss)
-    composite_fwd_kernel<C, true><<<grid, warps * 32, 0, st>>>((const float4*)raw4, z, n, S, rgb, w, T, a, rgb_s, depth,
-                                                               acc, *loss);
+    composite_fwd_kernel<C, true, false, kExact><<<grid, warps * 32, 0, st>>>((const float4*)raw4, z, n, S, rgb, w, nullptr,
+                                                                              nullptr, nullptr, depth, acc, *loss);
+  else if (T || a || rgb_s)
+    composite_fwd_kernel<C, false, true, kExact><<<grid, warps * 32, 0, st>>>((const float4*)raw4, z, n, S, rgb, w, T, a,
+                                                                              rgb_s, depth, acc, LossArgs{});
   else
-    composite_fwd_kernel<C, false><<<grid, warps * 32, 0, st>>>((const float4*)raw4, z, n, S, rgb, w, T, a, rgb_s, depth,
-                                                                acc, LossArgs{});
+    composite_fwd_kernel<C, false, false, kExact><<<grid, warps * 32, 0, st>>>((const float4*)raw4, z, n, S, rgb, w, nullptr,
+                                                                               nullptr, nullptr, depth, acc, LossArgs{});
+  return 0;
+}
+template <int C>
+static int launch_fwd(const float* raw4, const float* z, int64_t n, int S, float* rgb, float* w, float* T, float* a,
+                      float* rgb_s, float* depth, float* acc, const LossArgs* loss, cudaStream_t st) {
+  return S == 32 * C ? launch_fwd_<C, true>(raw4, z, n, S, rgb, w, T, a, rgb_s, depth, acc, loss, st)
+                     : launch_fwd_<C, false>(raw4, z, n, S, rgb, w, T, a, rgb_s, depth, acc, loss, st);
+}
+template <int C, bool kExact>
+static int launch_bwd_(const float* raw4, const float* z, const float* d_rgb, const float* d_w, int64_t n, int S,
+                       float* d_raw4, float* d_z, const LossArgs* loss, float* rgb_out, cudaStream_t st) {
+  const int warps = 8;
+  const unsigned grid = (unsigned)ceil_div(n, warps);
+  if (loss)
+    composite_bwd_kernel<C, true, kExact><<<grid, warps * 32, 0, st>>>((const float4*)raw4, z, nullptr, d_w, n, S,
+                                                                       (float4*)d_raw4, d_z, *loss, rgb_out);
+  else
+    composite_bwd_kernel<C, false, kExact><<<grid, warps * 32, 0, st>>>((const float4*)raw4, z, d_rgb, d_w, n, S,
+                                                                        (float4*)d_raw4, d_z, LossArgs{}, nullptr);
   return 0;
 }
 template <int C>
 static int launch_bwd(const float* raw4, const float* z, const float* d_rgb, const float* d_w, int64_t n, int S,
                       float* d_raw4, float* d_z, const LossArgs* loss, float* rgb_out, cudaStream_t st) {
-  const int warps = 8;
-  const unsigned grid = (unsigned)ceil_div(n, warps);
-  if (loss)
-    composite_bwd_kernel<C, true><<<grid, warps * 32, 0, st>>>((const float4*)raw4, z, nullptr, d_w, n, S, (float4*)d_raw4,
-                                                               d_z, *loss, rgb_out);
-  else
-    composite_bwd_kernel<C, false><<<grid, warps * 32, 0, st>>>((const float4*)raw4, z, d_rgb, d_w, n, S, (float4*)d_raw4,
-                                                                d_z, LossArgs{}, nullptr);
-  return 0;
+  return S == 32 * C ? launch_bwd_<C, true>(raw4, z, d_rgb, d_w, n, S, d_raw4, d_z, loss, rgb_out, st)
+                     : launch_bwd_<C, false>(raw4, z, d_rgb, d_w, n, S, d_raw4, d_z, loss, rgb_out, st);
 }
 
 }  // namespace nerf
