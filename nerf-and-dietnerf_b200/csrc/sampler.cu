@@ -13,35 +13,73 @@ namespace nerf {
 constexpr unsigned kFullMask = 0xffffffffu;
 constexpr int kWarpsPerBlock = 4;
 
-struct RayCdf {
-  float* w;    // [S] weights, then pdf
-  float* cdf;  // [S]
-  float* z;    // [S]
-};
+// The forward kernel is instruction-bound (ncu, profiles/r02_ay_*: 0.9 TB/s of algorithmic traffic, issue slots busy), so
+// the hot shapes (64 coarse samples, 128 / 192 draws: every train / render step of the bench configs) are compile-time
+// template arguments kS / kNf: every loop unrolls, the searches read shared memory at immediate offsets and the row
+// moves 16 bytes at a time.  kS = kNf = 0 is the same code with run-time extents (any 2 <= S, Nf <= 1024).
 
-// Stage one ray and build pdf/cdf in the canonical order. Returns (sum + eps).
-__device__ __forceinline__ float build_cdf(const float* __restrict__ weights, const float* __restrict__ z, int S,
+// Stage one ray and build pdf/cdf in the canonical order. Returns (sum + eps).  `sz` receives the MID-POINTS
+// 0.5 (z[i+1] + z[i]), i < S-1 (the only way the depths enter, src/UtilsCV.py:519), so a draw reads two values, not four.
+template <int kS>
+__device__ __forceinline__ float build_cdf(const float* __restrict__ weights, const float* __restrict__ z, int S_rt,
                                            int lane, float* sw, float* scdf, float* sz) {
-  for (int i = lane; i < S; i += 32) {
-    sw[i] = __ldcs(weights + i);
-    sz[i] = __ldcs(z + i);
+  const int S = kS ? kS : S_rt;
+#pragma unroll(kS ? (kS + 31) / 32 : 1)
+  for (int i0 = 0; i0 < S; i0 += 32) {
+    const int i = i0 + lane;
+    if (i < S) {
+      sw[i] = __ldcs(weights + i);
+      const float zi = __ldg(z + i), zn = __ldg(z + min(i + 1, S - 1));
+      sz[i] = __fmul_rn(0.5f, __fadd_rn(zn, zi));
+    }
   }
   __syncwarp();
   // Sequential left-to-right fp32 sum and cumsum, computed REDUNDANTLY by every lane from broadcast shared-memory reads:
   // the loads do not depend on the running value, so they pipeline and the dependent chain is one FADD per element
   // (a single lane doing load -> add -> store through the same array paid a shared-memory round trip per element).
+  // 16-byte accesses when S is a multiple of four: 16 + 64 issue slots for the sum of 64 weights, 16 + 64 + 16 for the
+  // cumsum (lane 0 stores it).
+  const bool vec = (S & 3) == 0;
   float total = 0.f;
+  if (vec) {
+    const float4* sw4 = reinterpret_cast<const float4*>(sw);
+#pragma unroll(kS ? kS / 4 : 4)
+    for (int i = 0; i < (S >> 2); ++i) {
+      const float4 v = sw4[i];
+      total = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(total, v.x), v.y), v.z), v.w);
+    }
+  } else {
 #pragma unroll 8
-  for (int i = 0; i < S; ++i) total = __fadd_rn(total, sw[i]);
+    for (int i = 0; i < S; ++i) total = __fadd_rn(total, sw[i]);
+  }
   const float denom = __fadd_rn(total, 1e-7f);  // EPS, src/UtilsCV.py:30
   __syncwarp();
-  for (int i = lane; i < S; i += 32) sw[i] = __fdiv_rn(sw[i], denom);   // pdf (the weights are not needed after this)
+#pragma unroll(kS ? (kS + 31) / 32 : 1)
+  for (int i0 = 0; i0 < S; i0 += 32) {            // pdf (the weights are not needed after this)
+    const int i = i0 + lane;
+    if (i < S) sw[i] = __fdiv_rn(sw[i], denom);
+  }
   __syncwarp();
   float run = 0.f;
+  if (vec) {
+    const float4* sw4 = reinterpret_cast<const float4*>(sw);
+    float4* sc4 = reinterpret_cast<float4*>(scdf);
+#pragma unroll(kS ? kS / 4 : 4)
+    for (int i = 0; i < (S >> 2); ++i) {
+      const float4 v = sw4[i];
+      float4 o;
+      o.x = run = __fadd_rn(run, v.x);
+      o.y = run = __fadd_rn(run, v.y);
+      o.z = run = __fadd_rn(run, v.z);
+      o.w = run = __fadd_rn(run, v.w);
+      if (lane == 0) sc4[i] = o;
+    }
+  } else {
 #pragma unroll 8
-  for (int i = 0; i < S; ++i) {
-    run = __fadd_rn(run, sw[i]);
-    if ((i & 31) == lane) scdf[i] = run;
+    for (int i = 0; i < S; ++i) {
+      run = __fadd_rn(run, sw[i]);
+      if ((i & 31) == lane) scdf[i] = run;
+    }
   }
   __syncwarp();
   return denom;
@@ -53,107 +91,222 @@ struct Draw {
   bool floored;
 };
 
-__device__ __forceinline__ Draw locate(const float* scdf, const float* sz, int S, float u, int* idx_out) {
-  // idx = #{i : cdf_i < u}  (tf.searchsorted side='left')
-  int lo_i = 0, hi_i = S;
-  while (lo_i < hi_i) {
-    int mid = (lo_i + hi_i) >> 1;
-    if (scdf[mid] < u) lo_i = mid + 1; else hi_i = mid;
+// #{i < n : a_i < v} for a sorted row in shared memory (tf.searchsorted side='left'): branch-free halving.  With a
+// compile-time extent every probe is one LDS at an immediate offset, one compare and one predicated pointer add.
+template <int N, typename T>
+__device__ __forceinline__ const T* lower_bound_steps(const T* p, T v) {
+  if constexpr (N > 1) {
+    constexpr int half = N >> 1;
+    if (p[half - 1] < v) p += half;
+    return lower_bound_steps<N - half, T>(p, v);
+  } else {
+    return p;
   }
-  int idx = lo_i;
-  if (idx_out) *idx_out = idx;
+}
+template <int kN, typename T>
+__device__ __forceinline__ int lower_bound(const T* a, int n_rt, T v) {
+  const T* p = a;
+  if constexpr (kN > 0) {
+    p = lower_bound_steps<kN, T>(p, v);
+  } else {
+    int n = n_rt;
+    while (n > 1) {
+      const int half = n >> 1;
+      if (p[half - 1] < v) p += half;
+      n -= half;
+    }
+  }
+  return (int)(p - a) + ((p[0] < v) ? 1 : 0);
+}
+
+// `szm`: the mid-points build_cdf left in shared memory
+__device__ __forceinline__ Draw locate(const float* scdf, const float* szm, int S, int idx) {
   Draw d;
   d.b = max(0, idx - 1);
   d.t = min(S - 1, idx);
   d.lo = scdf[d.b];
   d.hi = scdf[d.t];
-  int zb = min(max(d.b, 0), S - 2), zt = min(max(d.t, 0), S - 2);
-  d.zlo = __fmul_rn(0.5f, __fadd_rn(sz[zb + 1], sz[zb]));
-  d.zhi = __fmul_rn(0.5f, __fadd_rn(sz[zt + 1], sz[zt]));
+  d.zlo = szm[min(d.b, S - 2)];
+  d.zhi = szm[min(d.t, S - 2)];
   float den = __fsub_rn(d.hi, d.lo);
   d.floored = den < 1e-5f;
   d.den = d.floored ? 1e-5f : den;
   return d;
 }
 
-// Stable ascending sort of the Nf <= 32 E new samples of a ray by a warp-wide bitonic network on 64-bit keys
-// (order-preserving bits of z in the high word, the draw index in the low word: ties keep draw order, exactly the stable
-// sort the oracle performs, and no two keys are equal).  Element e = lane E + i lives in register i of lane `lane`, so the
-// strides below E are register swaps and the others one 64-bit shuffle per element: log^2 steps (28 for 128 samples)
-// instead of the Nf^2 / 32 pair tests per lane of the rank sort.
-template <int E>
-__device__ __forceinline__ void bitonic_sort_rows(const float* szs, int Nf, int lane, float* __restrict__ z_out,
-                                                  int* __restrict__ perm_out) {
-  unsigned long long k[E];
+__device__ __forceinline__ uint32_t order_key(float v) {   // unsigned order == float order; -0 sorts with (and leaves as) +0
+  uint32_t u = __float_as_uint(v);
+  if ((u << 1) == 0u) u = 0u;
+  return u ^ ((u >> 31) ? 0xffffffffu : 0x80000000u);
+}
+__device__ __forceinline__ float key_value(uint32_t k) {
+  return __uint_as_float((k & 0x80000000u) ? (k ^ 0x80000000u) : ~k);
+}
+
+// Stable ascending sort of the Nf <= 32 E new samples of a ray (tf.sort of src/NeRF.py:132; ties keep draw order, like
+// the oracle's stable sort) and the permutation the backward needs.
+//  * Values: a warp-wide bitonic network on bare 32-bit order-preserving keys, element e = lane E + i in register i of
+//    lane `lane`.  All-ascending form: a merge of width `size` starts with a FLIP (e against e ^ (size - 1)) and continues
+//    with half-cleaners (e against e ^ stride); the smaller index always keeps the minimum, so no compare-exchange needs
+//    a direction select.  Partners across lanes cost one shuffle + a predicated min/max, partners inside a lane are
+//    register pairs with compile-time indices (min + max).  28 steps for 128 samples.
+//  * Permutation: every draw looks its own key up in the sorted row (lower bound in shared memory) = its rank when the
+//    key is unique.  Runs of EQUAL keys (draws below the first / above the last cdf entry collapse onto one mid-point,
+//    src/UtilsCV.py:519-527) are resolved one distinct value at a time: rank = first occurrence + the number of equal
+//    draws with a smaller draw index (ballots over the E registers) - the stable order.
+//  * Rays whose samples are all equal (empty rays) are already sorted: identity permutation.
+// Replaces the 64-bit (z, draw index) network of the previous version: same results bit for bit
+// (test_sample_pdf_bit_exact), about a third of its issue slots.
+template <int E, int kNf>
+__device__ __forceinline__ void sort_new_samples(const float* szs, uint32_t* ssort, int Nf_rt, int lane, bool vec_out,
+                                                 float* __restrict__ z_out, int* __restrict__ perm_out) {
+  const int Nf = kNf ? kNf : Nf_rt;
+  uint32_t k[E], orig[E];
+  if (kNf == 32 * E && E == 4) {
+    const float4 v = *reinterpret_cast<const float4*>(szs + lane * 4);
+    k[0] = order_key(v.x); k[1] = order_key(v.y); k[2] = order_key(v.z); k[3] = order_key(v.w);
+  } else {
 #pragma unroll
-  for (int i = 0; i < E; ++i) {
-    const int j = lane * E + i;
-    if (j < Nf) {
-      uint32_t u = __float_as_uint(szs[j]);
-      if ((u << 1) == 0u) u = 0u;                                  // -0 sorts with +0 (a float compare calls them equal)
-      u ^= (u >> 31) ? 0xffffffffu : 0x80000000u;
-      k[i] = ((unsigned long long)u << 32) | (uint32_t)j;
-    } else {
-      k[i] = ~0ull;                                                // padding sorts to the end
+    for (int i = 0; i < E; ++i) {
+      const int j = lane * E + i;
+      k[i] = j < Nf ? order_key(szs[j]) : 0xffffffffu;               // padding sorts to the end
     }
   }
 #pragma unroll
-  for (int size = 2; size <= 32 * E; size <<= 1) {
+  for (int i = 0; i < E; ++i) orig[i] = k[i];
+  const uint32_t k0 = __shfl_sync(kFullMask, k[0], 0);
+  bool same = true;
 #pragma unroll
-    for (int stride = size >> 1; stride >= 1; stride >>= 1) {
+  for (int i = 0; i < E; ++i) same = same && (k[i] == k0 || lane * E + i >= Nf);
+  if (__all_sync(kFullMask, same)) {
+#pragma unroll
+    for (int i = 0; i < E; ++i) {
+      const int e = lane * E + i;
+      if (e < Nf) {
+        z_out[e] = szs[e];
+        if (perm_out) perm_out[e] = e;
+      }
+    }
+    return;
+  }
+#pragma unroll
+  for (int size = 2; size <= 32 * E; size <<= 1) {
+    if (size > E) {                                  // flip across lanes: lane ^ (size / E - 1), register E - 1 - i
+      const bool lower = (lane & (size / (2 * E))) == 0;
+      uint32_t o[E];
+#pragma unroll
+      for (int i = 0; i < E; ++i) o[i] = __shfl_xor_sync(kFullMask, k[E - 1 - i], size / E - 1);
+#pragma unroll
+      for (int i = 0; i < E; ++i) k[i] = lower ? min(k[i], o[i]) : max(k[i], o[i]);
+    } else {                                         // flip inside the lane
+#pragma unroll
+      for (int i = 0; i < E; ++i) {
+        if ((i & (size >> 1)) == 0) {
+          const int p = i ^ (size - 1);
+          const uint32_t a = k[i], b = k[p];
+          k[i] = min(a, b);
+          k[p] = max(a, b);
+        }
+      }
+    }
+#pragma unroll
+    for (int stride = size >> 2; stride >= 1; stride >>= 1) {
       if (stride >= E) {
-        const int lane_stride = stride / E;
-        const bool lower = (lane & lane_stride) == 0;
+        const bool lower = (lane & (stride / E)) == 0;
 #pragma unroll
         for (int i = 0; i < E; ++i) {
-          const unsigned long long o = __shfl_xor_sync(kFullMask, k[i], lane_stride);
-          const bool asc = (((lane * E + i) & size) == 0) || size == 32 * E;
-          const bool take_min = lower == asc;
-          k[i] = ((o < k[i]) == take_min) ? o : k[i];                 // min or max with ONE compare (equal keys: either)
+          const uint32_t o = __shfl_xor_sync(kFullMask, k[i], stride / E);
+          k[i] = lower ? min(k[i], o) : max(k[i], o);
         }
       } else {
 #pragma unroll
         for (int i = 0; i < E; ++i) {
           if ((i & stride) == 0) {
-            const int p = i | stride;
-            const bool asc = (((lane * E + i) & size) == 0) || size == 32 * E;
-            const unsigned long long a = k[i], b = k[p];
-            const bool swap = asc ? (a > b) : (a < b);
-            k[i] = swap ? b : a;
-            k[p] = swap ? a : b;
+            const uint32_t a = k[i], b = k[i | stride];
+            k[i] = min(a, b);
+            k[i | stride] = max(a, b);
           }
         }
       }
     }
   }
+  if (vec_out && kNf == 32 * E && (E == 4 || E == 8)) {
+#pragma unroll
+    for (int q = 0; q < E / 4; ++q)
+      *reinterpret_cast<float4*>(z_out + lane * E + 4 * q) =
+          make_float4(key_value(k[4 * q]), key_value(k[4 * q + 1]), key_value(k[4 * q + 2]), key_value(k[4 * q + 3]));
+  } else {
+#pragma unroll
+    for (int i = 0; i < E; ++i)
+      if (lane * E + i < Nf) z_out[lane * E + i] = key_value(k[i]);
+  }
+  if (!perm_out) return;
+#pragma unroll
+  for (int i = 0; i < E; ++i)
+    if (lane * E + i < Nf) ssort[lane * E + i] = k[i];
+  __syncwarp();
+  int rank[E];
+  unsigned unresolved = 0u;
 #pragma unroll
   for (int i = 0; i < E; ++i) {
-    const int e = lane * E + i;
-    if (e < Nf) {
-      const int j = (int)(uint32_t)k[i];
-      z_out[e] = szs[j];
-      if (perm_out) perm_out[e] = j;
+    rank[i] = lower_bound<kNf, uint32_t>(ssort, Nf, orig[i]);
+    if (lane * E + i < Nf && rank[i] + 1 < Nf && ssort[rank[i] + 1] == orig[i]) unresolved |= 1u << i;
+  }
+  const unsigned lanes_below = (1u << lane) - 1u;
+  for (;;) {
+    const unsigned pending = __ballot_sync(kFullMask, unresolved != 0u);
+    if (!pending) break;
+    uint32_t mine = 0u;
+#pragma unroll
+    for (int i = E - 1; i >= 0; --i)
+      if ((unresolved >> i) & 1u) mine = orig[i];
+    const uint32_t v = __shfl_sync(kFullMask, mine, __ffs(pending) - 1);
+    int before = 0;
+    bool eq[E];
+#pragma unroll
+    for (int i = 0; i < E; ++i) {
+      eq[i] = orig[i] == v && lane * E + i < Nf;
+      before += __popc(__ballot_sync(kFullMask, eq[i]) & lanes_below);
+    }
+#pragma unroll
+    for (int i = 0; i < E; ++i) {
+      if (eq[i]) {
+        rank[i] += before;
+        ++before;
+        unresolved &= ~(1u << i);
+      }
     }
   }
+#pragma unroll
+  for (int i = 0; i < E; ++i)
+    if (lane * E + i < Nf) perm_out[rank[i]] = lane * E + i;
 }
 
+// vec_io: z_new, u_out and idx_out rows start on 16-byte boundaries (checked by the launcher)
+template <int kS, int kNf>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
-sample_pdf_fwd_kernel(const float* __restrict__ weights, const float* __restrict__ z, int64_t n_rays, int S, int Nf,
+sample_pdf_fwd_kernel(const float* __restrict__ weights, const float* __restrict__ z, int64_t n_rays, int S_rt, int Nf_rt,
                       const float* __restrict__ u_in, uint64_t seed, uint32_t step, uint64_t ray_offset,
                       float* __restrict__ z_new, int* __restrict__ idx_out, int* __restrict__ perm_out,
-                      float* __restrict__ u_out) {
+                      float* __restrict__ u_out, bool vec_io) {
   extern __shared__ float smem[];
+  const int S = kS ? kS : S_rt, Nf = kNf ? kNf : Nf_rt;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t ray = blockIdx.x * (int64_t)kWarpsPerBlock + warp;
   if (ray >= n_rays) return;
-  // per-warp region [w | cdf | z | new samples]; the last block starts on a 16-byte boundary (float4 loads in the sort)
+  // per-warp region [w | cdf | z mid-points | new samples | sorted keys]; the last two start on 16-byte boundaries
   const int s3 = (3 * S + 3) & ~3, nf4 = (Nf + 3) & ~3;
-  float* base = smem + (size_t)warp * (s3 + nf4);
+  float* base = smem + (size_t)warp * (s3 + 2 * nf4);
   float *sw = base, *scdf = base + S, *sz = base + 2 * S, *szs = base + s3;
-  build_cdf(weights + ray * S, z + ray * S, S, lane, sw, scdf, sz);
+  uint32_t* ssort = reinterpret_cast<uint32_t*>(base + s3 + nf4);
+  build_cdf<kS>(weights + ray * S, z + ray * S, S, lane, sw, scdf, sz);
 
   const int n_blocks = (Nf + 3) / 4;
-  for (int blk = lane; blk < n_blocks; blk += 32) {
+  const bool vec = vec_io && (Nf & 3) == 0;
+#pragma unroll(kNf ? (kNf + 127) / 128 : 1)
+  for (int blk0 = 0; blk0 < n_blocks; blk0 += 32) {
+    const int blk = blk0 + lane;
+    if (blk >= n_blocks) break;
     float u4[4];
     if (u_in) {
 #pragma unroll
@@ -162,32 +315,49 @@ sample_pdf_fwd_kernel(const float* __restrict__ weights, const float* __restrict
       float4 r = philox_uniform4(seed, (uint32_t)(ray + ray_offset), (uint32_t)blk, 1u, step);
       u4[0] = r.x; u4[1] = r.y; u4[2] = r.z; u4[3] = r.w;
     }
+    int idx4[4];
+    float zn[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) idx4[k] = lower_bound<kS, float>(scdf, S, u4[k]);
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      int j = blk * 4 + k;
-      if (j >= Nf) break;
-      int idx;
-      Draw d = locate(scdf, sz, S, u4[k], &idx);
-      float t = __fdiv_rn(__fsub_rn(u4[k], d.lo), d.den);
-      szs[j] = __fadd_rn(d.zlo, __fmul_rn(t, __fsub_rn(d.zhi, d.zlo)));
-      if (idx_out) idx_out[ray * Nf + j] = idx;
-      if (u_out) u_out[ray * Nf + j] = u4[k];
+      const Draw d = locate(scdf, sz, S, idx4[k]);
+      const float t = __fdiv_rn(__fsub_rn(u4[k], d.lo), d.den);
+      zn[k] = __fadd_rn(d.zlo, __fmul_rn(t, __fsub_rn(d.zhi, d.zlo)));
+    }
+    if (vec) {
+      *reinterpret_cast<float4*>(szs + 4 * blk) = make_float4(zn[0], zn[1], zn[2], zn[3]);
+      if (idx_out) *reinterpret_cast<int4*>(idx_out + ray * Nf + 4 * blk) = make_int4(idx4[0], idx4[1], idx4[2], idx4[3]);
+      if (u_out) *reinterpret_cast<float4*>(u_out + ray * Nf + 4 * blk) = make_float4(u4[0], u4[1], u4[2], u4[3]);
+    } else {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int j = blk * 4 + k;
+        if (j < Nf) {
+          szs[j] = zn[k];
+          if (idx_out) idx_out[ray * Nf + j] = idx4[k];
+          if (u_out) u_out[ray * Nf + j] = u4[k];
+        }
+      }
     }
   }
   __syncwarp();
-  // Up to 256 new samples (every reference config: 64 ... 192): bitonic network, see bitonic_sort_rows.  More: the stable
+  // Up to 256 new samples (every reference config: 64 ... 192): bitonic network, see sort_new_samples.  More: the stable
   // rank sort below (tf.sort ascending; ties keep draw order like the oracle's stable sort):
-  //   rank_j = #{k < j : z_k <= z_j} + #{k > j : z_k < z_j}.
-  // The kernel is issue-bound on this O(Nf^2) loop, so it is arranged to cost one compare + one add per pair: in pass m
-  // the warp ranks j = 32 m + lane, so every k below 32 m is "before" and every k from 32 (m + 1) on is "after" for ALL
-  // lanes (warp-uniform bounds, 16-byte shared-memory loads); only the 32 k of the diagonal block need the index test.
+  //   rank_j = #{k < j : z_k <= z_j} + #{k > j : z_k < z_j},
+  // one compare + one add per pair: in pass m the warp ranks j = 32 m + lane, so every k below 32 m is "before" and every
+  // k from 32 (m + 1) on is "after" for ALL lanes (warp-uniform bounds, 16-byte shared-memory loads); only the 32 k of the
+  // diagonal block need the index test.
   if (Nf <= 256) {
     float* zo = z_new + ray * Nf;
     int* po = perm_out ? perm_out + ray * Nf : nullptr;
-    if (Nf <= 32) bitonic_sort_rows<1>(szs, Nf, lane, zo, po);
-    else if (Nf <= 64) bitonic_sort_rows<2>(szs, Nf, lane, zo, po);
-    else if (Nf <= 128) bitonic_sort_rows<4>(szs, Nf, lane, zo, po);
-    else bitonic_sort_rows<8>(szs, Nf, lane, zo, po);
+    if (kNf) {
+      constexpr int E = kNf <= 32 ? 1 : (kNf <= 64 ? 2 : (kNf <= 128 ? 4 : 8));
+      sort_new_samples<E, kNf>(szs, ssort, Nf, lane, vec, zo, po);
+    } else if (Nf <= 32) sort_new_samples<1, 0>(szs, ssort, Nf, lane, false, zo, po);
+    else if (Nf <= 64) sort_new_samples<2, 0>(szs, ssort, Nf, lane, false, zo, po);
+    else if (Nf <= 128) sort_new_samples<4, 0>(szs, ssort, Nf, lane, false, zo, po);
+    else sort_new_samples<8, 0>(szs, ssort, Nf, lane, false, zo, po);
     return;
   }
   for (int j0 = 0; j0 < Nf; j0 += 32) {
@@ -230,14 +400,14 @@ sample_pdf_bwd_kernel(const float* __restrict__ weights, const float* __restrict
   float *sw = base, *scdf = base + S, *sz = base + 2 * S, *sdc = base + 3 * S;
   float *sdz = base + 4 * S, *sdlo = sdz + Nf, *sdhi = sdlo + Nf;
   int* sbt = reinterpret_cast<int*>(sdhi + Nf);
-  const float denom = build_cdf(weights + ray * S, z + ray * S, S, lane, sw, scdf, sz);
+  const float denom = build_cdf<0>(weights + ray * S, z + ray * S, S, lane, sw, scdf, sz);
 
   for (int k = lane; k < Nf; k += 32) sdz[perm[ray * Nf + k]] = __ldcs(d_z_new + ray * Nf + k);
   for (int i = lane; i < S; i += 32) sdc[i] = 0.f;
   __syncwarp();
   for (int j = lane; j < Nf; j += 32) {
     float uj = __ldcs(u + ray * Nf + j);
-    Draw d = locate(scdf, sz, S, uj, nullptr);
+    Draw d = locate(scdf, sz, S, lower_bound<0, float>(scdf, S, uj));
     float dt = sdz[j] * (d.zhi - d.zlo);
     float num = uj - d.lo;
     float dlo = -dt / d.den, dhi = 0.f;
@@ -336,12 +506,22 @@ int nerf_sample_pdf_fwd(const float* weights, const float* z, int64_t n_rays, in
   NERF_CHECK_ARG(n_rays >= 0 && n_samples >= 2 && n_samples <= 1024 && n_new > 0 && n_new <= 1024,
                  "need 2 <= n_samples <= 1024 and 1 <= n_new <= 1024");
   if (n_rays == 0) return NERF_OK;
-  size_t smem = (size_t)kWarpsPerBlock * (((3 * n_samples + 3) & ~3) + ((n_new + 3) & ~3)) * sizeof(float);
-  if (smem > 48 * 1024)
-    NERF_CUDA(cudaFuncSetAttribute(sample_pdf_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  sample_pdf_fwd_kernel<<<(unsigned)ceil_div(n_rays, kWarpsPerBlock), kWarpsPerBlock * 32, smem, (cudaStream_t)stream>>>(
-      weights, z, n_rays, n_samples, n_new, u_or_null, seed, step, ray_offset, z_new, idx_or_null, perm_or_null,
-      u_out_or_null);
+  size_t smem = (size_t)kWarpsPerBlock * (((3 * n_samples + 3) & ~3) + 2 * ((n_new + 3) & ~3)) * sizeof(float);
+  const bool vec_io = (((uintptr_t)z_new | (uintptr_t)idx_or_null | (uintptr_t)u_out_or_null) & 15) == 0;
+  const unsigned grid = (unsigned)ceil_div(n_rays, kWarpsPerBlock);
+#define NERF_SAMPLER_LAUNCH(KS, KNF)                                                                                   \
+  do {                                                                                                                 \
+    if (smem > 48 * 1024)                                                                                              \
+      NERF_CUDA(cudaFuncSetAttribute(sample_pdf_fwd_kernel<KS, KNF>, cudaFuncAttributeMaxDynamicSharedMemorySize,      \
+                                     (int)smem));                                                                      \
+    sample_pdf_fwd_kernel<KS, KNF><<<grid, kWarpsPerBlock * 32, smem, (cudaStream_t)stream>>>(                         \
+        weights, z, n_rays, n_samples, n_new, u_or_null, seed, step, ray_offset, z_new, idx_or_null, perm_or_null,     \
+        u_out_or_null, vec_io);                                                                                        \
+  } while (0)
+  if (n_samples == 64 && n_new == 128) NERF_SAMPLER_LAUNCH(64, 128);
+  else if (n_samples == 64 && n_new == 192) NERF_SAMPLER_LAUNCH(64, 192);
+  else NERF_SAMPLER_LAUNCH(0, 0);
+#undef NERF_SAMPLER_LAUNCH
   NERF_CHECK_LAUNCH();
   return NERF_OK;
 }
