@@ -20,9 +20,17 @@ constexpr int kWarpsPerBlock = 4;
 
 // Stage one ray and build pdf/cdf in the canonical order. Returns (sum + eps).  `sz` receives the MID-POINTS
 // 0.5 (z[i+1] + z[i]), i < S-1 (the only way the depths enter, src/UtilsCV.py:519), so a draw reads two values, not four.
+// Rows that are SEARCHED (cdf, mid-points, sorted keys) are stored with one word of padding per 32 entries in the
+// compile-time instantiations (kPad = 1): the probes of a binary search sit a power of two apart, i.e. in the same
+// bank, and the kernel was bound by shared-memory wavefronts (2-way conflicts on the 64-entry cdf, 4-way on 128 keys).
+template <int kPad>
+__device__ __forceinline__ int padded(int i) { return i + kPad * (i >> 5); }
+
+// scdf: linear cumsum row (lane 0 writes it 16 bytes at a time); scdfp: its padded copy (== scdf when kS = 0)
 template <int kS>
 __device__ __forceinline__ float build_cdf(const float* __restrict__ weights, const float* __restrict__ z, int S_rt,
-                                           int lane, float* sw, float* scdf, float* sz) {
+                                           int lane, float* sw, float* scdf, float* sz, float* scdfp) {
+  constexpr int kPad = kS ? 1 : 0;
   const int S = kS ? kS : S_rt;
 #pragma unroll(kS ? (kS + 31) / 32 : 1)
   for (int i0 = 0; i0 < S; i0 += 32) {
@@ -30,7 +38,7 @@ __device__ __forceinline__ float build_cdf(const float* __restrict__ weights, co
     if (i < S) {
       sw[i] = __ldcs(weights + i);
       const float zi = __ldg(z + i), zn = __ldg(z + min(i + 1, S - 1));
-      sz[i] = __fmul_rn(0.5f, __fadd_rn(zn, zi));
+      sz[padded<kPad>(i)] = __fmul_rn(0.5f, __fadd_rn(zn, zi));
     }
   }
   __syncwarp();
@@ -82,6 +90,14 @@ __device__ __forceinline__ float build_cdf(const float* __restrict__ weights, co
     }
   }
   __syncwarp();
+  if (kS) {
+#pragma unroll(kS ? (kS + 31) / 32 : 1)
+    for (int i0 = 0; i0 < S; i0 += 32) {
+      const int i = i0 + lane;
+      if (i < S) scdfp[padded<kPad>(i)] = scdf[i];
+    }
+    __syncwarp();
+  }
   return denom;
 }
 
@@ -92,42 +108,90 @@ struct Draw {
 };
 
 // #{i < n : a_i < v} for a sorted row in shared memory (tf.searchsorted side='left'): branch-free halving.  With a
-// compile-time extent every probe is one LDS at an immediate offset, one compare and one predicated pointer add.
-template <int N, typename T>
-__device__ __forceinline__ const T* lower_bound_steps(const T* p, T v) {
+// compile-time extent the probes are written in PTX so that each level is exactly LDS [addr + imm] / SETP / predicated
+// ADD (the C++ form compiled to ~7 issue slots per level: pointer selects and re-derived addresses) and the kE
+// independent chains of a lane are interleaved level by level.
+template <typename T> struct SharedProbe;
+template <> struct SharedProbe<float> {
+  template <int kLoad, int kStep>
+  static __device__ __forceinline__ void step(uint32_t& addr, float v) {
+    asm volatile("{\n\t.reg .pred p;\n\t.reg .f32 x;\n\tld.shared.f32 x, [%0+%2];\n\tsetp.lt.f32 p, x, %1;\n\t@p add.u32 %0, %0, %3;\n\t}"
+                 : "+r"(addr) : "f"(v), "n"(kLoad), "n"(kStep));
+  }
+  static __device__ __forceinline__ uint32_t last(uint32_t addr, float v) {
+    uint32_t inc;
+    asm volatile("{\n\t.reg .pred p;\n\t.reg .f32 x;\n\tld.shared.f32 x, [%1];\n\tsetp.lt.f32 p, x, %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(inc) : "r"(addr), "f"(v));
+    return inc;
+  }
+};
+template <> struct SharedProbe<uint32_t> {
+  template <int kLoad, int kStep>
+  static __device__ __forceinline__ void step(uint32_t& addr, uint32_t v) {
+    asm volatile("{\n\t.reg .pred p;\n\t.reg .u32 x;\n\tld.shared.u32 x, [%0+%2];\n\tsetp.lt.u32 p, x, %1;\n\t@p add.u32 %0, %0, %3;\n\t}"
+                 : "+r"(addr) : "r"(v), "n"(kLoad), "n"(kStep));
+  }
+  static __device__ __forceinline__ uint32_t last(uint32_t addr, uint32_t v) {
+    uint32_t inc;
+    asm volatile("{\n\t.reg .pred p;\n\t.reg .u32 x;\n\tld.shared.u32 x, [%1];\n\tsetp.lt.u32 p, x, %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(inc) : "r"(addr), "r"(v));
+    return inc;
+  }
+};
+// (N a power of two >= 32 in a padded row: the base of a level is a multiple of 2 half, so padded(base + x) - padded(base)
+// is the same for every base)
+template <int N, int kE, typename T>
+__device__ __forceinline__ void lower_bound_levels(uint32_t (&addr)[kE], const T (&v)[kE]) {
   if constexpr (N > 1) {
     constexpr int half = N >> 1;
-    if (p[half - 1] < v) p += half;
-    return lower_bound_steps<N - half, T>(p, v);
-  } else {
-    return p;
+    constexpr int load = (half - 1) + ((half - 1) >> 5), step = half + (half >> 5);
+#pragma unroll
+    for (int e = 0; e < kE; ++e) SharedProbe<T>::template step<load * 4, step * 4>(addr[e], v[e]);
+    lower_bound_levels<N - half, kE, T>(addr, v);
   }
 }
-template <int kN, typename T>
-__device__ __forceinline__ int lower_bound(const T* a, int n_rt, T v) {
-  const T* p = a;
+// kE searches of one lane over the same row; kN > 0: compile-time extent (a power of two), PADDED row
+template <int kN, int kE, typename T>
+__device__ __forceinline__ void lower_bound(const T* a, int n_rt, const T (&v)[kE], int (&idx)[kE]) {
   if constexpr (kN > 0) {
-    p = lower_bound_steps<kN, T>(p, v);
+    static_assert((kN & (kN - 1)) == 0 && kN >= 32, "padded search: power-of-two extent");
+    const uint32_t a0 = (uint32_t)__cvta_generic_to_shared(a);
+    uint32_t addr[kE];
+#pragma unroll
+    for (int e = 0; e < kE; ++e) addr[e] = a0;
+    lower_bound_levels<kN, kE, T>(addr, v);
+#pragma unroll
+    for (int e = 0; e < kE; ++e) {
+      const uint32_t pos = (addr[e] - a0) >> 2;                      // padded position: 33 words per 32 entries
+      idx[e] = (int)(pos - pos / 33u + SharedProbe<T>::last(addr[e], v[e]));
+    }
   } else {
+    const T* p[kE];
+#pragma unroll
+    for (int e = 0; e < kE; ++e) p[e] = a;
     int n = n_rt;
     while (n > 1) {
       const int half = n >> 1;
-      if (p[half - 1] < v) p += half;
+#pragma unroll
+      for (int e = 0; e < kE; ++e)
+        if (p[e][half - 1] < v[e]) p[e] += half;
       n -= half;
     }
+#pragma unroll
+    for (int e = 0; e < kE; ++e) idx[e] = (int)(p[e] - a) + ((p[e][0] < v[e]) ? 1 : 0);
   }
-  return (int)(p - a) + ((p[0] < v) ? 1 : 0);
 }
 
-// `szm`: the mid-points build_cdf left in shared memory
+// `szm`: the mid-points build_cdf left in shared memory; both rows padded<kPad>
+template <int kPad>
 __device__ __forceinline__ Draw locate(const float* scdf, const float* szm, int S, int idx) {
   Draw d;
   d.b = max(0, idx - 1);
   d.t = min(S - 1, idx);
-  d.lo = scdf[d.b];
-  d.hi = scdf[d.t];
-  d.zlo = szm[min(d.b, S - 2)];
-  d.zhi = szm[min(d.t, S - 2)];
+  d.lo = scdf[padded<kPad>(d.b)];
+  d.hi = scdf[padded<kPad>(d.t)];
+  d.zlo = szm[padded<kPad>(min(d.b, S - 2))];
+  d.zhi = szm[padded<kPad>(min(d.t, S - 2))];
   float den = __fsub_rn(d.hi, d.lo);
   d.floored = den < 1e-5f;
   d.den = d.floored ? 1e-5f : den;
@@ -241,17 +305,17 @@ __device__ __forceinline__ void sort_new_samples(const float* szs, uint32_t* sso
       if (lane * E + i < Nf) z_out[lane * E + i] = key_value(k[i]);
   }
   if (!perm_out) return;
+  constexpr int kPad = kNf ? 1 : 0;                  // compile-time shapes: all 32 E keys (padding included) in a padded row
 #pragma unroll
   for (int i = 0; i < E; ++i)
-    if (lane * E + i < Nf) ssort[lane * E + i] = k[i];
+    if (kNf || lane * E + i < Nf) ssort[padded<kPad>(lane * E + i)] = k[i];
   __syncwarp();
   int rank[E];
   unsigned unresolved = 0u;
+  lower_bound<(kNf ? 32 * E : 0), E, uint32_t>(ssort, Nf, orig, rank);
 #pragma unroll
-  for (int i = 0; i < E; ++i) {
-    rank[i] = lower_bound<kNf, uint32_t>(ssort, Nf, orig[i]);
-    if (lane * E + i < Nf && rank[i] + 1 < Nf && ssort[rank[i] + 1] == orig[i]) unresolved |= 1u << i;
-  }
+  for (int i = 0; i < E; ++i)
+    if (lane * E + i < Nf && rank[i] + 1 < Nf && ssort[padded<kPad>(rank[i] + 1)] == orig[i]) unresolved |= 1u << i;
   const unsigned lanes_below = (1u << lane) - 1u;
   for (;;) {
     const unsigned pending = __ballot_sync(kFullMask, unresolved != 0u);
@@ -282,6 +346,21 @@ __device__ __forceinline__ void sort_new_samples(const float* szs, uint32_t* sso
     if (lane * E + i < Nf) perm_out[rank[i]] = lane * E + i;
 }
 
+// Shared-memory layout of one warp of the forward kernel, in floats; `padded_rows`: the compile-time instantiations
+struct SamplerSmem {
+  int cdf, zm, cdfp, szs, keys, per_warp;
+  __host__ __device__ SamplerSmem(int S, int Nf, bool padded_rows) {
+    const int pad_s = padded_rows ? ((S + 31) >> 5) : 0;
+    cdf = S;
+    zm = 2 * S;
+    cdfp = padded_rows ? zm + S + pad_s : cdf;                       // run-time extents: the searches read the linear row
+    szs = ((padded_rows ? cdfp + S + pad_s : 3 * S) + 3) & ~3;      // 16-byte boundary (float4 accesses)
+    keys = szs + ((Nf + 3) & ~3);
+    const int n_keys = Nf <= 32 ? 32 : (Nf <= 64 ? 64 : (Nf <= 128 ? 128 : 256));   // all 32 E keys of the network
+    per_warp = (keys + (padded_rows ? n_keys + (n_keys >> 5) : ((Nf + 3) & ~3)) + 3) & ~3;
+  }
+};
+
 // vec_io: z_new, u_out and idx_out rows start on 16-byte boundaries (checked by the launcher)
 template <int kS, int kNf>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
@@ -294,12 +373,13 @@ sample_pdf_fwd_kernel(const float* __restrict__ weights, const float* __restrict
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t ray = blockIdx.x * (int64_t)kWarpsPerBlock + warp;
   if (ray >= n_rays) return;
-  // per-warp region [w | cdf | z mid-points | new samples | sorted keys]; the last two start on 16-byte boundaries
-  const int s3 = (3 * S + 3) & ~3, nf4 = (Nf + 3) & ~3;
-  float* base = smem + (size_t)warp * (s3 + 2 * nf4);
-  float *sw = base, *scdf = base + S, *sz = base + 2 * S, *szs = base + s3;
-  uint32_t* ssort = reinterpret_cast<uint32_t*>(base + s3 + nf4);
-  build_cdf<kS>(weights + ray * S, z + ray * S, S, lane, sw, scdf, sz);
+  // per-warp region (SamplerSmem): [w | cdf | z mid-points | padded cdf | new samples | sorted keys]
+  constexpr int kPad = kS ? 1 : 0;
+  const SamplerSmem L(S, Nf, kS != 0);
+  float* base = smem + (size_t)warp * L.per_warp;
+  float *sw = base, *scdf = base + L.cdf, *sz = base + L.zm, *scdfp = base + L.cdfp, *szs = base + L.szs;
+  uint32_t* ssort = reinterpret_cast<uint32_t*>(base + L.keys);
+  build_cdf<kS>(weights + ray * S, z + ray * S, S, lane, sw, scdf, sz, scdfp);
 
   const int n_blocks = (Nf + 3) / 4;
   const bool vec = vec_io && (Nf & 3) == 0;
@@ -317,11 +397,10 @@ sample_pdf_fwd_kernel(const float* __restrict__ weights, const float* __restrict
     }
     int idx4[4];
     float zn[4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) idx4[k] = lower_bound<kS, float>(scdf, S, u4[k]);
+    lower_bound<kS, 4, float>(scdfp, S, u4, idx4);
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      const Draw d = locate(scdf, sz, S, idx4[k]);
+      const Draw d = locate<kPad>(scdfp, sz, S, idx4[k]);
       const float t = __fdiv_rn(__fsub_rn(u4[k], d.lo), d.den);
       zn[k] = __fadd_rn(d.zlo, __fmul_rn(t, __fsub_rn(d.zhi, d.zlo)));
     }
@@ -400,14 +479,17 @@ sample_pdf_bwd_kernel(const float* __restrict__ weights, const float* __restrict
   float *sw = base, *scdf = base + S, *sz = base + 2 * S, *sdc = base + 3 * S;
   float *sdz = base + 4 * S, *sdlo = sdz + Nf, *sdhi = sdlo + Nf;
   int* sbt = reinterpret_cast<int*>(sdhi + Nf);
-  const float denom = build_cdf<0>(weights + ray * S, z + ray * S, S, lane, sw, scdf, sz);
+  const float denom = build_cdf<0>(weights + ray * S, z + ray * S, S, lane, sw, scdf, sz, scdf);
 
   for (int k = lane; k < Nf; k += 32) sdz[perm[ray * Nf + k]] = __ldcs(d_z_new + ray * Nf + k);
   for (int i = lane; i < S; i += 32) sdc[i] = 0.f;
   __syncwarp();
   for (int j = lane; j < Nf; j += 32) {
     float uj = __ldcs(u + ray * Nf + j);
-    Draw d = locate(scdf, sz, S, lower_bound<0, float>(scdf, S, uj));
+    const float uj1[1] = {uj};
+    int idx1[1];
+    lower_bound<0, 1, float>(scdf, S, uj1, idx1);
+    Draw d = locate<0>(scdf, sz, S, idx1[0]);
     float dt = sdz[j] * (d.zhi - d.zlo);
     float num = uj - d.lo;
     float dlo = -dt / d.den, dhi = 0.f;
@@ -506,7 +588,8 @@ int nerf_sample_pdf_fwd(const float* weights, const float* z, int64_t n_rays, in
   NERF_CHECK_ARG(n_rays >= 0 && n_samples >= 2 && n_samples <= 1024 && n_new > 0 && n_new <= 1024,
                  "need 2 <= n_samples <= 1024 and 1 <= n_new <= 1024");
   if (n_rays == 0) return NERF_OK;
-  size_t smem = (size_t)kWarpsPerBlock * (((3 * n_samples + 3) & ~3) + 2 * ((n_new + 3) & ~3)) * sizeof(float);
+  const bool fixed = n_samples == 64 && (n_new == 128 || n_new == 192);
+  size_t smem = (size_t)kWarpsPerBlock * SamplerSmem(n_samples, n_new, fixed).per_warp * sizeof(float);
   const bool vec_io = (((uintptr_t)z_new | (uintptr_t)idx_or_null | (uintptr_t)u_out_or_null) & 15) == 0;
   const unsigned grid = (unsigned)ceil_div(n_rays, kWarpsPerBlock);
 #define NERF_SAMPLER_LAUNCH(KS, KNF)                                                                                   \
