@@ -466,66 +466,160 @@ sample_pdf_fwd_kernel(const float* __restrict__ weights, const float* __restrict
   }
 }
 
+// Shared-memory layout of one warp of the backward kernel, in floats
+struct SamplerBwdSmem {
+  int cdf, zm, cdfp, dc, dz, lo, hi, bt, llo, lhi, cnt, start, per_warp;
+  __host__ __device__ SamplerBwdSmem(int S, int Nf, bool padded_rows) {
+    const int pad_s = padded_rows ? ((S + 31) >> 5) : 0;
+    cdf = S;
+    zm = 2 * S;
+    cdfp = padded_rows ? zm + S + pad_s : cdf;
+    dc = ((padded_rows ? cdfp + S + pad_s : 3 * S) + 3) & ~3;        // 16-byte boundary (float4 reverse cumsum)
+    dz = dc + ((S + 3) & ~3);
+    lo = dz + Nf; hi = lo + Nf; bt = hi + Nf; llo = bt + Nf; lhi = llo + Nf;
+    cnt = lhi + Nf;
+    start = cnt + S + 2;
+    per_warp = (start + S + 3 + 3) & ~3;
+  }
+};
+
+// Gradient w.r.t. the weights.  Per draw: d z_new -> d cdf[b], d cdf[t] (b = max(0, idx - 1), t = min(S - 1, idx)).  The
+// per-draw contributions are then summed into d cdf DETERMINISTICALLY without the O(S Nf) gather of the previous version
+// (every entry scanning every draw: 2 000 of the kernel's 3 000 issue slots per ray): a counting sort by idx.  Draws get a
+// ticket inside their bin in a fixed order (register slot, then lane: __match_any_sync + the lanes below), a warp scan of
+// the 65 bin counts gives the bin starts, the values are placed into two bin-ordered lists and every cdf entry adds up
+// ITS contiguous list ranges in a fixed order (upper ends of bin i, lower ends of bin i + 1, the two clamped edge bins).
+// Same inputs -> same additions in the same order on every run and every device.
+template <int kS, int kNf>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 sample_pdf_bwd_kernel(const float* __restrict__ weights, const float* __restrict__ z, const float* __restrict__ u,
-                      const int* __restrict__ perm, const float* __restrict__ d_z_new, int64_t n_rays, int S, int Nf,
+                      const int* __restrict__ perm, const float* __restrict__ d_z_new, int64_t n_rays, int S_rt, int Nf_rt,
                       float* __restrict__ d_weights) {
   extern __shared__ float smem[];
+  constexpr int kPad = kS ? 1 : 0;
+  const int S = kS ? kS : S_rt, Nf = kNf ? kNf : Nf_rt;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t ray = blockIdx.x * (int64_t)kWarpsPerBlock + warp;
   if (ray >= n_rays) return;
-  // layout per warp: w[S] cdf[S] z[S] dcdf[S] | dzs[Nf] dlo[Nf] dhi[Nf] bt[Nf] (ints)
-  float* base = smem + (size_t)warp * (4 * S + 4 * Nf);
-  float *sw = base, *scdf = base + S, *sz = base + 2 * S, *sdc = base + 3 * S;
-  float *sdz = base + 4 * S, *sdlo = sdz + Nf, *sdhi = sdlo + Nf;
-  int* sbt = reinterpret_cast<int*>(sdhi + Nf);
-  const float denom = build_cdf<0>(weights + ray * S, z + ray * S, S, lane, sw, scdf, sz, scdf);
+  const SamplerBwdSmem L(S, Nf, kS != 0);
+  float* base = smem + (size_t)warp * L.per_warp;
+  float *sw = base, *scdf = base + L.cdf, *sz = base + L.zm, *scdfp = base + L.cdfp, *sdc = base + L.dc;
+  float *sdz = base + L.dz, *slo = base + L.lo, *shi = base + L.hi, *llo = base + L.llo, *lhi = base + L.lhi;
+  int *sbt = reinterpret_cast<int*>(base + L.bt), *cnt = reinterpret_cast<int*>(base + L.cnt),
+      *start = reinterpret_cast<int*>(base + L.start);
+  const float denom = build_cdf<kS>(weights + ray * S, z + ray * S, S, lane, sw, scdf, sz, scdfp);
 
-  for (int k = lane; k < Nf; k += 32) sdz[perm[ray * Nf + k]] = __ldcs(d_z_new + ray * Nf + k);
-  for (int i = lane; i < S; i += 32) sdc[i] = 0.f;
+#pragma unroll(kNf ? (kNf + 31) / 32 : 1)
+  for (int k0 = 0; k0 < Nf; k0 += 32)
+    if (k0 + lane < Nf) sdz[perm[ray * Nf + k0 + lane]] = __ldcs(d_z_new + ray * Nf + k0 + lane);
+#pragma unroll(kS ? (kS + 33) / 32 : 1)
+  for (int i0 = 0; i0 <= S; i0 += 32)
+    if (i0 + lane <= S) cnt[i0 + lane] = 0;
   __syncwarp();
-  for (int j = lane; j < Nf; j += 32) {
-    float uj = __ldcs(u + ray * Nf + j);
-    const float uj1[1] = {uj};
-    int idx1[1];
-    lower_bound<0, 1, float>(scdf, S, uj1, idx1);
-    Draw d = locate<0>(scdf, sz, S, idx1[0]);
-    float dt = sdz[j] * (d.zhi - d.zlo);
-    float num = uj - d.lo;
-    float dlo = -dt / d.den, dhi = 0.f;
-    if (!d.floored) {
-      float q = dt * num / (d.den * d.den);
-      dlo += q;
-      dhi = -q;
+  const unsigned lanes_below = (1u << lane) - 1u;
+  const int n_blocks = (Nf + 3) / 4;
+#pragma unroll(kNf ? (kNf + 127) / 128 : 1)
+  for (int blk0 = 0; blk0 < n_blocks; blk0 += 32) {          // every lane stays in the loop: __match_any_sync below
+    const int blk = blk0 + lane;
+    float u4[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) u4[k] = (blk < n_blocks && blk * 4 + k < Nf) ? __ldcs(u + ray * Nf + blk * 4 + k) : 0.f;
+    int idx4[4];
+    lower_bound<kS, 4, float>(scdfp, S, u4, idx4);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int j = blk * 4 + k;
+      const bool valid = blk < n_blocks && j < Nf;
+      if (valid) {
+        const Draw d = locate<kPad>(scdfp, sz, S, idx4[k]);
+        const float dt = sdz[j] * (d.zhi - d.zlo);
+        const float num = u4[k] - d.lo;
+        float dlo = -dt / d.den, dhi = 0.f;
+        if (!d.floored) {
+          const float q = dt * num / (d.den * d.den);
+          dlo += q;
+          dhi = -q;
+        }
+        slo[j] = dlo;
+        shi[j] = dhi;
+      }
+      const int key = valid ? idx4[k] : -1 - lane;              // idle lanes match nobody
+      const unsigned peers = __match_any_sync(kFullMask, key);
+      const int taken = valid ? cnt[idx4[k]] : 0;
+      if (valid) sbt[j] = idx4[k] | ((taken + __popc(peers & lanes_below)) << 16);
+      __syncwarp();
+      if (valid && (peers & lanes_below) == 0u) cnt[idx4[k]] = taken + __popc(peers);
+      __syncwarp();
     }
-    sdlo[j] = dlo;
-    sdhi[j] = dhi;
-    sbt[j] = d.b | (d.t << 16);
   }
+  // bin starts: exclusive scan of the S + 1 counts
+  int carry = 0;
+#pragma unroll(kS ? (kS + 32) / 32 : 1)
+  for (int c0 = 0; c0 <= S; c0 += 32) {
+    const int i = c0 + lane;
+    const int v = i <= S ? cnt[i] : 0;
+    int incl = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const int o = __shfl_up_sync(kFullMask, incl, d);
+      if (lane >= d) incl += o;
+    }
+    if (i <= S) start[i] = carry + incl - v;
+    carry += __shfl_sync(kFullMask, incl, 31);
+  }
+  if (lane == 0) start[S + 1] = carry;
   __syncwarp();
-  // Per-draw cdf gradients -> d cdf: every cdf entry GATHERS its contributions in draw order (lower end before upper
-  // end of the same draw), i.e. the same sequence of additions a sequential scatter would perform, lane-parallel over
-  // the entries.  Then the reverse cumsum -> d pdf, redundantly in every lane (pipelined broadcast reads, one dependent
-  // FADD per element), 32 entries at a time so no lane overwrites an entry another lane still has to read.
-  for (int i = lane; i < S; i += 32) {
-    float acc = 0.f;
-    for (int j = 0; j < Nf; ++j) {
+#pragma unroll(kNf ? (kNf + 31) / 32 : 1)
+  for (int j0 = 0; j0 < Nf; j0 += 32) {
+    const int j = j0 + lane;
+    if (j < Nf) {
       const int bt = sbt[j];
-      if ((bt & 0xffff) == i) acc += sdlo[j];
-      if ((bt >> 16) == i) acc += sdhi[j];
+      const int pos = start[bt & 0xffff] + (bt >> 16);
+      llo[pos] = slo[j];
+      lhi[pos] = shi[j];
     }
-    sdc[i] = acc;
   }
   __syncwarp();
-  float run = 0.f;
-  for (int k0 = ((S - 1) >> 5) << 5; k0 >= 0; k0 -= 32) {
-    float mine = 0.f;
-    for (int i = min(S, k0 + 32) - 1; i >= k0; --i) {
-      run += sdc[i];
-      if ((i & 31) == lane) mine = run;
+#pragma unroll(kS ? (kS + 31) / 32 : 1)
+  for (int i0 = 0; i0 < S; i0 += 32) {
+    const int i = i0 + lane;
+    if (i < S) {
+      const int a = start[i], b = start[i + 1], c = start[i + 2];
+      float acc = 0.f;
+      for (int p = a; p < b; ++p) acc += lhi[p];               // t == i: draws of bin i
+      for (int p = b; p < c; ++p) acc += llo[p];               // b == i: draws of bin i + 1
+      if (i == 0)
+        for (int p = a; p < b; ++p) acc += llo[p];             // idx == 0: b == t == 0
+      if (i == S - 1)
+        for (int p = b; p < c; ++p) acc += lhi[p];             // idx == S: b == t == S - 1
+      sdc[i] = acc;
     }
-    __syncwarp();
-    if (k0 + lane < S) sdc[k0 + lane] = mine;
+  }
+  __syncwarp();
+  // reverse cumsum -> d pdf, redundantly in every lane (pipelined broadcast reads, one dependent FADD per element)
+  float run = 0.f;
+  if ((S & 3) == 0) {
+    float4* dc4 = reinterpret_cast<float4*>(sdc);
+#pragma unroll(kS ? kS / 4 : 4)
+    for (int i = (S >> 2) - 1; i >= 0; --i) {
+      const float4 v = dc4[i];
+      float4 o;
+      o.w = run = run + v.w;
+      o.z = run = run + v.z;
+      o.y = run = run + v.y;
+      o.x = run = run + v.x;
+      if (lane == 0) dc4[i] = o;
+    }
+  } else {
+    for (int k0 = ((S - 1) >> 5) << 5; k0 >= 0; k0 -= 32) {   // 32 entries at a time: no lane overwrites an entry another
+      float mine = 0.f;                                        // lane still has to read
+      for (int i = min(S, k0 + 32) - 1; i >= k0; --i) {
+        run += sdc[i];
+        if ((i & 31) == lane) mine = run;
+      }
+      __syncwarp();
+      if (k0 + lane < S) sdc[k0 + lane] = mine;
+    }
   }
   __syncwarp();
   // pdf = w / denom, denom = sum(w) + eps :  d w_k = dpdf_k/denom - sum_j dpdf_j w_j / denom^2
@@ -615,11 +709,20 @@ int nerf_sample_pdf_bwd(const float* weights, const float* z, const float* u, co
   NERF_CHECK_ARG(n_rays >= 0 && n_samples >= 2 && n_samples <= 1024 && n_new > 0 && n_new <= 1024,
                  "need 2 <= n_samples <= 1024 and 1 <= n_new <= 1024");
   if (n_rays == 0) return NERF_OK;
-  size_t smem = (size_t)kWarpsPerBlock * (4 * n_samples + 4 * n_new) * sizeof(float);
-  if (smem > 48 * 1024)
-    NERF_CUDA(cudaFuncSetAttribute(sample_pdf_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  sample_pdf_bwd_kernel<<<(unsigned)ceil_div(n_rays, kWarpsPerBlock), kWarpsPerBlock * 32, smem, (cudaStream_t)stream>>>(
-      weights, z, u, perm, d_z_new, n_rays, n_samples, n_new, d_weights);
+  const bool fixed = n_samples == 64 && n_new == 128;
+  size_t smem = (size_t)kWarpsPerBlock * SamplerBwdSmem(n_samples, n_new, fixed).per_warp * sizeof(float);
+  const unsigned grid = (unsigned)ceil_div(n_rays, kWarpsPerBlock);
+#define NERF_SAMPLER_BWD_LAUNCH(KS, KNF)                                                                               \
+  do {                                                                                                                 \
+    if (smem > 48 * 1024)                                                                                              \
+      NERF_CUDA(cudaFuncSetAttribute(sample_pdf_bwd_kernel<KS, KNF>, cudaFuncAttributeMaxDynamicSharedMemorySize,      \
+                                     (int)smem));                                                                      \
+    sample_pdf_bwd_kernel<KS, KNF><<<grid, kWarpsPerBlock * 32, smem, (cudaStream_t)stream>>>(                         \
+        weights, z, u, perm, d_z_new, n_rays, n_samples, n_new, d_weights);                                            \
+  } while (0)
+  if (fixed) NERF_SAMPLER_BWD_LAUNCH(64, 128);
+  else NERF_SAMPLER_BWD_LAUNCH(0, 0);
+#undef NERF_SAMPLER_BWD_LAUNCH
   NERF_CHECK_LAUNCH();
   return NERF_OK;
 }
