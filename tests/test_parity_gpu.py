@@ -230,6 +230,51 @@ def test_sample_pdf_backward(pkg):
     assert err < 1e-4 * wr.grad.abs().max().item(), err
 
 
+# Several DISTINCT groups of equal samples in one ray (equal uniforms give equal samples): the 32-bit key network sorts the
+# values, the ranks of tied draws come from ballots over the equal keys - stable order, bit for bit like the oracle's
+# stable sort.  Shapes: the compile-time instantiations (64 x 128, 64 x 192) and run-time extents.
+@pytest.mark.parametrize("n,s,nf,n_distinct", [(257, 64, 128, 9), (130, 64, 192, 30), (90, 55, 110, 5), (64, 64, 64, 3),
+                                               (33, 64, 128, 1), (40, 40, 256, 100)])
+def test_sample_pdf_tie_groups_bit_exact(pkg, n, s, nf, n_distinct):
+    w, z = _weights_and_z(n, s, 1000 + nf)
+    g = torch.Generator().manual_seed(n_distinct)
+    pool = torch.rand(n, n_distinct, generator=g) * 0.998 + 0.001
+    u = torch.gather(pool, 1, torch.randint(0, n_distinct, (n, nf), generator=g)).contiguous()
+    ref_z, ref_idx, ref_perm, _ = O.get_z_vals_from_prob_dist_func(w, z, nf, u, return_aux=True)
+    got_z, got_idx, got_perm = pkg.UtilsCV.get_z_vals_from_prob_dist_func(dev(w), dev(z), nf, u=dev(u), return_aux=True)
+    assert torch.equal(got_idx.cpu(), ref_idx)
+    assert torch.equal(got_z.cpu(), ref_z)
+    assert torch.equal(got_perm.cpu().long(), ref_perm.long()), "ties must keep draw order (stable sort)"
+    # the lean call (no permutation wanted) gives the same samples
+    assert torch.equal(pkg.UtilsCV.get_z_vals_from_prob_dist_func(dev(w), dev(z), nf, u=dev(u)).cpu(), ref_z)
+
+
+# Backward on the shapes of both instantiations with the distributions that stress the bin lists: peaked weights (most
+# draws in two or three bins), empty rays (every draw in the last bin), tied uniforms; twice -> bit-identical.
+@pytest.mark.parametrize("n,s,nf", [(300, 64, 128), (100, 55, 110), (64, 64, 192), (50, 33, 7)])
+def test_sample_pdf_backward_heavy_bins(pkg, n, s, nf):
+    g = torch.Generator().manual_seed(n + nf)
+    centre = torch.rand(n, 1, generator=g) * s
+    w = torch.exp(-0.5 * ((torch.arange(s)[None, :] - centre) / 0.8) ** 2) + 1e-6 * torch.rand(n, s, generator=g)
+    w[: n // 8] = 0.0
+    z = torch.sort(torch.rand(n, s, generator=g) * 2 + 0.5, -1).values
+    u = torch.rand(n, nf, generator=g)
+    m = u[:, 1::3].shape[1]
+    u[n // 2:, 0:3 * m:3] = u[n // 2:, 1::3]                               # tied uniforms in half of the rays
+    gz = torch.randn(n, nf, generator=g)
+    wr = w.clone().requires_grad_(True)
+    O.get_z_vals_from_prob_dist_func(wr, z, nf, u).backward(gz)
+    grads = []
+    for _ in range(2):
+        wg = dev(w).requires_grad_(True)
+        pkg.UtilsCV.get_z_vals_from_prob_dist_func(wg, dev(z), nf, u=dev(u)).backward(dev(gz))
+        grads.append(wg.grad.cpu())
+    assert torch.equal(grads[0], grads[1]), "the backward must be bit-reproducible"
+    scale = wr.grad.abs().max().item()
+    err = (grads[0] - wr.grad).abs().max().item()
+    assert err < 2e-4 * scale, (err, scale)
+
+
 def test_sample_pdf_full_size_properties(pkg):
     n, s, nf = 65536, 64, 128
     g = torch.Generator(device="cuda").manual_seed(0)
