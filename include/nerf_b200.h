@@ -220,6 +220,14 @@ int nerf_sample_pdf_fwd(const float* weights, const float* z, int64_t n_rays, in
                         int32_t n_new, const float* u_or_null, uint64_t seed, uint32_t step,
                         uint64_t ray_offset, float* z_new, int32_t* idx_or_null, int32_t* perm_or_null,
                         float* u_out_or_null, void* stream);
+/* The hierarchical-sampling step of NeRF.render as ONE launch (src/NeRF.py:129-132 between the two networks): the coarse
+ * weights of ray_marching (src/UtilsNeuralRadianceField.py:101-108: alpha, exclusive-cumprod transmittance) formed from
+ * raw4_coarse (N,S,4), get_z_vals_from_prob_dist_func (src/UtilsCV.py:502-539, Philox stream of nerf_sample_pdf_fwd)
+ * and z_all = sort(concat(z_from_dist, z_coarse)) (N,S+Nf).  Bit-identical to nerf_composite_fwd (weights) ->
+ * nerf_sample_pdf_fwd -> nerf_merge_sorted; n_new <= 256. */
+int nerf_hierarchical_sample(const float* raw4_coarse, const float* z_coarse, int64_t n_rays, int32_t n_samples,
+                             int32_t n_new, uint64_t seed, uint32_t step, uint64_t ray_offset, float* z_all,
+                             void* stream);
 /* d_weights (N,S) written: gradient of z_new w.r.t. weights contracted with d_z_new (N,Nf, sorted order). */
 int nerf_sample_pdf_bwd(const float* weights, const float* z, const float* u, const int32_t* perm,
                         const float* d_z_new, int64_t n_rays, int32_t n_samples, int32_t n_new,

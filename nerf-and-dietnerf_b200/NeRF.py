@@ -500,11 +500,18 @@ class NeRF:
                     n, off = min(batch_size, n_total - s0), ray_begin + s0
                     z, raw = f(n, n_c), f(n, n_c, 4)
                     mlp(mc, off, n, n_c, None, z, raw)
-                    rgb, wts, depth, acc = _unrf.ray_marching_lean(raw, z)
-                    if mf is not None:
-                        z_f = get_z_vals_from_prob_dist_func(wts, z, n_f, seed=seed, step=step, ray_offset=off)
+                    if mf is None:
+                        rgb, wts, depth, acc = _unrf.ray_marching_lean(raw, z)
+                    else:
                         z_all, raw_f = f(n, n_f + n_c), f(n, n_f + n_c, 4)
-                        call("nerf_merge_sorted", ptr(z_f), n_f, ptr(z), n_c, n, ptr(z_all))
+                        if n_f <= 256:
+                            # coarse weights + importance draws + sort + merge with the coarse depths: one launch
+                            call("nerf_hierarchical_sample", ptr(raw), ptr(z), n, n_c, n_f, int(seed), int(step), int(off),
+                                 ptr(z_all))
+                        else:
+                            rgb, wts, depth, acc = _unrf.ray_marching_lean(raw, z)
+                            z_f = get_z_vals_from_prob_dist_func(wts, z, n_f, seed=seed, step=step, ray_offset=off)
+                            call("nerf_merge_sorted", ptr(z_f), n_f, ptr(z), n_c, n, ptr(z_all))
                         mlp(mf, off, n, n_f + n_c, z_all, None, raw_f)
                         rgb, wts, depth, acc = _unrf.ray_marching_lean(raw_f, z_all)
                     rgbs.append(rgb)

@@ -98,6 +98,7 @@ SIGNATURES = {
     "nerf_composite_mse_fwd_bwd": (c_int32, [_P, _P, _P, c_int64, c_int32, c_int64, c_float, _P, _P, _P, _P, _P]),
     "nerf_sample_pdf_fwd": (c_int32, [_P, _P, c_int64, c_int32, c_int32, _P, c_uint64, c_uint32, c_uint64, _P, _P, _P,
                                       _P, _P]),
+    "nerf_hierarchical_sample": (c_int32, [_P, _P, c_int64, c_int32, c_int32, c_uint64, c_uint32, c_uint64, _P, _P]),
     "nerf_sample_pdf_bwd": (c_int32, [_P, _P, _P, _P, _P, c_int64, c_int32, c_int32, _P, _P]),
     "nerf_merge_sorted": (c_int32, [_P, c_int32, _P, c_int32, c_int64, _P, _P]),
     "nerf_merge_sorted_rank": (c_int32, [_P, c_int32, _P, c_int32, c_int64, _P, _P, _P]),
@@ -169,7 +170,7 @@ def check(status, what):
 
 
 # kernels launched per C-ABI call (bf16 mode; the fp32 MLP launches one GEMM per layer and is counted separately)
-KERNELS_PER_CALL = {"nerf_render_fused_fwd": 7, "nerf_train_step_fused": 20, "nerf_train_step_fused_sharded": 23, "nerf_mlp_fwd": 1, "nerf_mlp_fwd_rays": 1, "nerf_mlp_fwd_rays_stratified": 1, "nerf_mlp_bwd": 3, "nerf_mlp_bwd_overlapped": 3, "nerf_mlp_bwd_dx": 1, "nerf_mlp_bwd_dw": 2, "nerf_mlp_bwd_rays": 3,
+KERNELS_PER_CALL = {"nerf_render_fused_fwd": 5, "nerf_train_step_fused": 20, "nerf_train_step_fused_sharded": 23, "nerf_mlp_fwd": 1, "nerf_mlp_fwd_rays": 1, "nerf_mlp_fwd_rays_stratified": 1, "nerf_mlp_bwd": 3, "nerf_mlp_bwd_overlapped": 3, "nerf_mlp_bwd_dx": 1, "nerf_mlp_bwd_dw": 2, "nerf_mlp_bwd_rays": 3,
                     "nerf_pack_weights": 2}
 launch_count = 0            # kernels launched through call() since import (bench.py reads the delta)
 event_hook = None           # optional callable(name, args) -> context manager, used by bench.py to time single calls

@@ -218,12 +218,17 @@ int nerf_render_fused_fwd(const nerf_net_cfg* cfg, const nerf_render_cfg* rc, co
                                 (cudaStream_t)stream));
     return NERF_OK;
   }
-  NERF_TRY(nerf_composite_fwd(w.raw, w.z_c, n, sc, nullptr, w.w_c, nullptr, nullptr, nullptr, nullptr, nullptr, stream));
   // z_from_dist = get_z_vals_from_prob_dist_func(weights, z, N_f); z = sort(concat(z_from_dist, z))   (:131-132)
-  NERF_TRY(nerf_sample_pdf_fwd(w.w_c, w.z_c, n, sc, nf, nullptr, rng->seed, rng->step, rng->ray_offset, w.z_f, nullptr,
-                               nullptr, nullptr, stream));
   float* z_all = outs->z ? outs->z : w.z_all;
-  NERF_TRY(nerf_merge_sorted(w.z_f, nf, w.z_c, sc, n, z_all, stream));
+  if (nf <= 256) {
+    // coarse weights, draws, sort and merge in one launch (bit-identical to the three calls below)
+    NERF_TRY(nerf_hierarchical_sample(w.raw, w.z_c, n, sc, nf, rng->seed, rng->step, rng->ray_offset, z_all, stream));
+  } else {
+    NERF_TRY(nerf_composite_fwd(w.raw, w.z_c, n, sc, nullptr, w.w_c, nullptr, nullptr, nullptr, nullptr, nullptr, stream));
+    NERF_TRY(nerf_sample_pdf_fwd(w.w_c, w.z_c, n, sc, nf, nullptr, rng->seed, rng->step, rng->ray_offset, w.z_f, nullptr,
+                                 nullptr, nullptr, stream));
+    NERF_TRY(nerf_merge_sorted(w.z_f, nf, w.z_c, sc, n, z_all, stream));
+  }
   // fine render_rays                                                                                   (:133)
   NERF_TRY(net_forward(cfg, rc->mode, params_f, packed_f, origs4, dirs4, z_all, n, sc + nf, w.raw, nullptr, w.enc.xyz,
                        w.enc.view, w.enc.mlp_ws, stream));

@@ -6,7 +6,7 @@
 // The canonical order (shared with oracle/nerf_oracle.py) is sequential left-to-right fp32 with IEEE division,
 // so one lane walks the S<=1024 entries of a ray that the whole warp staged in shared memory with coalesced
 // loads; everything else (pdf, search, interpolation, rank sort) is lane-parallel.  1 KB/ray of HBM traffic.
-#include "common.cuh"
+#include "composite.cuh"
 
 namespace nerf {
 
@@ -27,18 +27,38 @@ template <int kPad>
 __device__ __forceinline__ int padded(int i) { return i + kPad * (i >> 5); }
 
 // scdf: linear cumsum row (lane 0 writes it 16 bytes at a time); scdfp: its padded copy (== scdf when kS = 0)
-template <int kS>
-__device__ __forceinline__ float build_cdf(const float* __restrict__ weights, const float* __restrict__ z, int S_rt,
-                                           int lane, float* sw, float* scdf, float* sz, float* scdfp) {
+// raw4 != null (nerf_hierarchical_sample): the weights are not read but FORMED here from the coarse network's raw output -
+// ray_marching's alpha / transmittance / weight with the arithmetic of composite_fwd_kernel (composite.cuh), bit for bit -
+// and `szc` keeps the raw depths (padded row) for the merge at the end.
+template <int kS, bool kFromRaw>
+__device__ __forceinline__ float build_cdf(const float* __restrict__ weights, const float4* __restrict__ raw4,
+                                           const float* __restrict__ z, int S_rt, int lane, float* sw, float* scdf,
+                                           float* sz, float* scdfp, float* szc) {
   constexpr int kPad = kS ? 1 : 0;
   const int S = kS ? kS : S_rt;
+  float carry = 1.0f;
 #pragma unroll(kS ? (kS + 31) / 32 : 1)
   for (int i0 = 0; i0 < S; i0 += 32) {
     const int i = i0 + lane;
-    if (i < S) {
-      sw[i] = __ldcs(weights + i);
-      const float zi = __ldg(z + i), zn = __ldg(z + min(i + 1, S - 1));
+    const bool valid = i < S;
+    float zi = 0.f, zn = 0.f;
+    if (valid) {
+      zi = __ldg(z + i);
+      zn = __ldg(z + min(i + 1, S - 1));
       sz[padded<kPad>(i)] = __fmul_rn(0.5f, __fadd_rn(zn, zi));
+      if (!kFromRaw) sw[i] = __ldcs(weights + i);
+    }
+    if (kFromRaw) {                                     // every lane: warp scan
+      const SampleFwd f = sample_fwd(valid ? __ldg(&raw4[i].w) : 0.f, zi, zn, i == S - 1);
+      const float incl = warp_incl_scan_mul(valid ? f.x : 1.0f, lane);
+      float excl = __shfl_up_sync(kFullMask, incl, 1);
+      if (lane == 0) excl = 1.0f;
+      const float T = carry * excl;
+      carry *= __shfl_sync(kFullMask, incl, 31);
+      if (valid) {
+        sw[i] = f.alpha * T;
+        szc[padded<kPad>(i)] = zi;
+      }
     }
   }
   __syncwarp();
@@ -221,9 +241,14 @@ __device__ __forceinline__ float key_value(uint32_t k) {
 //  * Rays whose samples are all equal (empty rays) are already sorted: identity permutation.
 // Replaces the 64-bit (z, draw index) network of the previous version: same results bit for bit
 // (test_sample_pdf_bit_exact), about a third of its issue slots.
-template <int E, int kNf>
+//  * kMerge (nerf_hierarchical_sample): instead of z_new the kernel writes z_all = sort(concat(z_new, z_c)) of
+//    src/NeRF.py:132 - a sorted new sample lands at e + #{z_c < v}, a coarse depth at j + #{z_new <= v} (new samples precede
+//    equal coarse ones: the stable order of the concatenation, the rule of merge_sorted_kernel), both counts by the same
+//    searches over the padded rows.
+template <int E, int kNf, int kS, bool kMerge>
 __device__ __forceinline__ void sort_new_samples(const float* szs, uint32_t* ssort, int Nf_rt, int lane, bool vec_out,
-                                                 float* __restrict__ z_out, int* __restrict__ perm_out) {
+                                                 float* __restrict__ z_out, int* __restrict__ perm_out,
+                                                 const float* szc, int S_rt, float* __restrict__ z_all) {
   const int Nf = kNf ? kNf : Nf_rt;
   uint32_t k[E], orig[E];
   if (kNf == 32 * E && E == 4) {
@@ -242,7 +267,7 @@ __device__ __forceinline__ void sort_new_samples(const float* szs, uint32_t* sso
   bool same = true;
 #pragma unroll
   for (int i = 0; i < E; ++i) same = same && (k[i] == k0 || lane * E + i >= Nf);
-  if (__all_sync(kFullMask, same)) {
+  if (!kMerge && __all_sync(kFullMask, same)) {
 #pragma unroll
     for (int i = 0; i < E; ++i) {
       const int e = lane * E + i;
@@ -294,6 +319,32 @@ __device__ __forceinline__ void sort_new_samples(const float* szs, uint32_t* sso
       }
     }
   }
+  constexpr int kPad = kNf ? 1 : 0;                  // compile-time shapes: all 32 E keys (padding included) in a padded row
+  if (kMerge) {
+    const int S = kS ? kS : S_rt;
+#pragma unroll
+    for (int i = 0; i < E; ++i)
+      if (kNf || lane * E + i < Nf) ssort[padded<kPad>(lane * E + i)] = k[i];
+    __syncwarp();
+    float v[E];
+    int below[E];
+#pragma unroll
+    for (int i = 0; i < E; ++i) v[i] = key_value(k[i]);
+    lower_bound<kS, E, float>(szc, S, v, below);                      // #{z_c < v}
+#pragma unroll
+    for (int i = 0; i < E; ++i)
+      if (lane * E + i < Nf) z_all[lane * E + i + below[i]] = v[i];
+#pragma unroll(kS ? (kS + 31) / 32 : 1)
+    for (int j0 = 0; j0 < S; j0 += 32) {
+      const int j = min(j0 + lane, S - 1);
+      const float zc[1] = {szc[padded<kPad>(j)]};
+      const uint32_t next_key[1] = {order_key(zc[0]) + 1u};           // #{key <= key(v)} = #{key < key(v) + 1}
+      int not_above[1];
+      lower_bound<(kNf ? 32 * E : 0), 1, uint32_t>(ssort, Nf, next_key, not_above);
+      if (j0 + lane < S) z_all[j + not_above[0]] = zc[0];
+    }
+    return;
+  }
   if (vec_out && kNf == 32 * E && (E == 4 || E == 8)) {
 #pragma unroll
     for (int q = 0; q < E / 4; ++q)
@@ -305,7 +356,6 @@ __device__ __forceinline__ void sort_new_samples(const float* szs, uint32_t* sso
       if (lane * E + i < Nf) z_out[lane * E + i] = key_value(k[i]);
   }
   if (!perm_out) return;
-  constexpr int kPad = kNf ? 1 : 0;                  // compile-time shapes: all 32 E keys (padding included) in a padded row
 #pragma unroll
   for (int i = 0; i < E; ++i)
     if (kNf || lane * E + i < Nf) ssort[padded<kPad>(lane * E + i)] = k[i];
@@ -348,8 +398,8 @@ __device__ __forceinline__ void sort_new_samples(const float* szs, uint32_t* sso
 
 // Shared-memory layout of one warp of the forward kernel, in floats; `padded_rows`: the compile-time instantiations
 struct SamplerSmem {
-  int cdf, zm, cdfp, szs, keys, per_warp;
-  __host__ __device__ SamplerSmem(int S, int Nf, bool padded_rows) {
+  int cdf, zm, cdfp, szs, keys, zc, per_warp;
+  __host__ __device__ SamplerSmem(int S, int Nf, bool padded_rows, bool merge = false) {
     const int pad_s = padded_rows ? ((S + 31) >> 5) : 0;
     cdf = S;
     zm = 2 * S;
@@ -357,12 +407,15 @@ struct SamplerSmem {
     szs = ((padded_rows ? cdfp + S + pad_s : 3 * S) + 3) & ~3;      // 16-byte boundary (float4 accesses)
     keys = szs + ((Nf + 3) & ~3);
     const int n_keys = Nf <= 32 ? 32 : (Nf <= 64 ? 64 : (Nf <= 128 ? 128 : 256));   // all 32 E keys of the network
-    per_warp = (keys + (padded_rows ? n_keys + (n_keys >> 5) : ((Nf + 3) & ~3)) + 3) & ~3;
+    zc = (keys + (padded_rows ? n_keys + (n_keys >> 5) : ((Nf + 3) & ~3)) + 3) & ~3;       // raw depths (merge only)
+    per_warp = (zc + (merge ? S + pad_s : 0) + 3) & ~3;
   }
 };
 
 // vec_io: z_new, u_out and idx_out rows start on 16-byte boundaries (checked by the launcher)
-template <int kS, int kNf>
+// kMerge: `weights` is the coarse network's raw output (N,S,4) and `z_new` receives z_all (N,S+Nf): the coarse weights, the
+// draws, their sort and the merge with the coarse depths in ONE launch (nerf_hierarchical_sample).
+template <int kS, int kNf, bool kMerge>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 sample_pdf_fwd_kernel(const float* __restrict__ weights, const float* __restrict__ z, int64_t n_rays, int S_rt, int Nf_rt,
                       const float* __restrict__ u_in, uint64_t seed, uint32_t step, uint64_t ray_offset,
@@ -375,11 +428,14 @@ sample_pdf_fwd_kernel(const float* __restrict__ weights, const float* __restrict
   if (ray >= n_rays) return;
   // per-warp region (SamplerSmem): [w | cdf | z mid-points | padded cdf | new samples | sorted keys]
   constexpr int kPad = kS ? 1 : 0;
-  const SamplerSmem L(S, Nf, kS != 0);
+  const SamplerSmem L(S, Nf, kS != 0, kMerge);
   float* base = smem + (size_t)warp * L.per_warp;
   float *sw = base, *scdf = base + L.cdf, *sz = base + L.zm, *scdfp = base + L.cdfp, *szs = base + L.szs;
+  float* szc = base + L.zc;
   uint32_t* ssort = reinterpret_cast<uint32_t*>(base + L.keys);
-  build_cdf<kS>(weights + ray * S, z + ray * S, S, lane, sw, scdf, sz, scdfp);
+  build_cdf<kS, kMerge>(kMerge ? nullptr : weights + ray * S,
+                        kMerge ? reinterpret_cast<const float4*>(weights) + ray * S : nullptr, z + ray * S, S, lane, sw,
+                        scdf, sz, scdfp, szc);
 
   const int n_blocks = (Nf + 3) / 4;
   const bool vec = vec_io && (Nf & 3) == 0;
@@ -428,15 +484,16 @@ sample_pdf_fwd_kernel(const float* __restrict__ weights, const float* __restrict
   // k from 32 (m + 1) on is "after" for ALL lanes (warp-uniform bounds, 16-byte shared-memory loads); only the 32 k of the
   // diagonal block need the index test.
   if (Nf <= 256) {
-    float* zo = z_new + ray * Nf;
-    int* po = perm_out ? perm_out + ray * Nf : nullptr;
+    float* zo = kMerge ? nullptr : z_new + ray * Nf;
+    float* za = kMerge ? z_new + ray * (S + Nf) : nullptr;
+    int* po = (perm_out && !kMerge) ? perm_out + ray * Nf : nullptr;
     if (kNf) {
       constexpr int E = kNf <= 32 ? 1 : (kNf <= 64 ? 2 : (kNf <= 128 ? 4 : 8));
-      sort_new_samples<E, kNf>(szs, ssort, Nf, lane, vec, zo, po);
-    } else if (Nf <= 32) sort_new_samples<1, 0>(szs, ssort, Nf, lane, false, zo, po);
-    else if (Nf <= 64) sort_new_samples<2, 0>(szs, ssort, Nf, lane, false, zo, po);
-    else if (Nf <= 128) sort_new_samples<4, 0>(szs, ssort, Nf, lane, false, zo, po);
-    else sort_new_samples<8, 0>(szs, ssort, Nf, lane, false, zo, po);
+      sort_new_samples<E, kNf, kS, kMerge>(szs, ssort, Nf, lane, vec, zo, po, szc, S, za);
+    } else if (Nf <= 32) sort_new_samples<1, 0, 0, kMerge>(szs, ssort, Nf, lane, false, zo, po, szc, S, za);
+    else if (Nf <= 64) sort_new_samples<2, 0, 0, kMerge>(szs, ssort, Nf, lane, false, zo, po, szc, S, za);
+    else if (Nf <= 128) sort_new_samples<4, 0, 0, kMerge>(szs, ssort, Nf, lane, false, zo, po, szc, S, za);
+    else sort_new_samples<8, 0, 0, kMerge>(szs, ssort, Nf, lane, false, zo, po, szc, S, za);
     return;
   }
   for (int j0 = 0; j0 < Nf; j0 += 32) {
@@ -507,7 +564,7 @@ sample_pdf_bwd_kernel(const float* __restrict__ weights, const float* __restrict
   float *sdz = base + L.dz, *slo = base + L.lo, *shi = base + L.hi, *llo = base + L.llo, *lhi = base + L.lhi;
   int *sbt = reinterpret_cast<int*>(base + L.bt), *cnt = reinterpret_cast<int*>(base + L.cnt),
       *start = reinterpret_cast<int*>(base + L.start);
-  const float denom = build_cdf<kS>(weights + ray * S, z + ray * S, S, lane, sw, scdf, sz, scdfp);
+  const float denom = build_cdf<kS, false>(weights + ray * S, nullptr, z + ray * S, S, lane, sw, scdf, sz, scdfp, nullptr);
 
 #pragma unroll(kNf ? (kNf + 31) / 32 : 1)
   for (int k0 = 0; k0 < Nf; k0 += 32)
@@ -689,9 +746,10 @@ int nerf_sample_pdf_fwd(const float* weights, const float* z, int64_t n_rays, in
 #define NERF_SAMPLER_LAUNCH(KS, KNF)                                                                                   \
   do {                                                                                                                 \
     if (smem > 48 * 1024)                                                                                              \
-      NERF_CUDA(cudaFuncSetAttribute(sample_pdf_fwd_kernel<KS, KNF>, cudaFuncAttributeMaxDynamicSharedMemorySize,      \
+      NERF_CUDA(cudaFuncSetAttribute(sample_pdf_fwd_kernel<KS, KNF, false>,                                            \
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize,                                      \
                                      (int)smem));                                                                      \
-    sample_pdf_fwd_kernel<KS, KNF><<<grid, kWarpsPerBlock * 32, smem, (cudaStream_t)stream>>>(                         \
+    sample_pdf_fwd_kernel<KS, KNF, false><<<grid, kWarpsPerBlock * 32, smem, (cudaStream_t)stream>>>(                  \
         weights, z, n_rays, n_samples, n_new, u_or_null, seed, step, ray_offset, z_new, idx_or_null, perm_or_null,     \
         u_out_or_null, vec_io);                                                                                        \
   } while (0)
@@ -699,6 +757,32 @@ int nerf_sample_pdf_fwd(const float* weights, const float* z, int64_t n_rays, in
   else if (n_samples == 64 && n_new == 192) NERF_SAMPLER_LAUNCH(64, 192);
   else NERF_SAMPLER_LAUNCH(0, 0);
 #undef NERF_SAMPLER_LAUNCH
+  NERF_CHECK_LAUNCH();
+  return NERF_OK;
+}
+
+int nerf_hierarchical_sample(const float* raw4_coarse, const float* z_coarse, int64_t n_rays, int32_t n_samples,
+                             int32_t n_new, uint64_t seed, uint32_t step, uint64_t ray_offset, float* z_all, void* stream) {
+  NERF_CHECK_ARG(raw4_coarse && z_coarse && z_all, "null pointer");
+  NERF_CHECK_ARG(n_rays >= 0 && n_samples >= 2 && n_samples <= 1024 && n_new > 0 && n_new <= 256,
+                 "need 2 <= n_samples <= 1024 and 1 <= n_new <= 256");
+  NERF_CHECK_ARG(((uintptr_t)raw4_coarse & 15) == 0, "raw4_coarse must be 16-byte aligned");
+  if (n_rays == 0) return NERF_OK;
+  const bool fixed = n_samples == 64 && n_new == 192;
+  size_t smem = (size_t)kWarpsPerBlock * SamplerSmem(n_samples, n_new, fixed, true).per_warp * sizeof(float);
+  const unsigned grid = (unsigned)ceil_div(n_rays, kWarpsPerBlock);
+#define NERF_HSAMPLE_LAUNCH(KS, KNF)                                                                                   \
+  do {                                                                                                                 \
+    if (smem > 48 * 1024)                                                                                              \
+      NERF_CUDA(cudaFuncSetAttribute(sample_pdf_fwd_kernel<KS, KNF, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                     (int)smem));                                                                      \
+    sample_pdf_fwd_kernel<KS, KNF, true><<<grid, kWarpsPerBlock * 32, smem, (cudaStream_t)stream>>>(                   \
+        raw4_coarse, z_coarse, n_rays, n_samples, n_new, nullptr, seed, step, ray_offset, z_all, nullptr, nullptr,     \
+        nullptr, true);                                                                                                \
+  } while (0)
+  if (fixed) NERF_HSAMPLE_LAUNCH(64, 192);
+  else NERF_HSAMPLE_LAUNCH(0, 0);
+#undef NERF_HSAMPLE_LAUNCH
   NERF_CHECK_LAUNCH();
   return NERF_OK;
 }
