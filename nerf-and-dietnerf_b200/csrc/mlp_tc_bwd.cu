@@ -865,6 +865,7 @@ mlp_tc_bwd_dw_reduce_kernel(const __grid_constant__ DwPlan plan, const __grid_co
   const int k = e4 >> 6, n0 = (e4 & 63) * 4;
   if (k < u.m_blocks * 128 && n0 < u.n) {
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 8                                           // eight independent 16-byte loads in flight per thread; same order of additions
     for (int s = 0; s < live; ++s) {
       const float4 v = __ldg(reinterpret_cast<const float4*>(base + (size_t)s * kDwPartialFloats + k * 256 + n0));
       acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;

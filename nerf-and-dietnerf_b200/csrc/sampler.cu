@@ -4,8 +4,11 @@
 //
 // Bit-exact indices: the searchsorted result depends on the fp32 summation order of reduce_sum and cumsum.
 // The canonical order (shared with oracle/nerf_oracle.py) is sequential left-to-right fp32 with IEEE division,
-// so one lane walks the S<=1024 entries of a ray that the whole warp staged in shared memory with coalesced
-// loads; everything else (pdf, search, interpolation, rank sort) is lane-parallel.  1 KB/ray of HBM traffic.
+// so every lane walks the S<=1024 entries of a ray that the whole warp staged in shared memory with coalesced
+// loads (redundantly: the dependent chain is one FADD per entry); everything else (pdf, search, interpolation, sort) is
+// lane-parallel.  1 KB/ray of HBM traffic.  nerf_hierarchical_sample runs the same kernel with the coarse ray_marching
+// weights formed in place of the load and the merge with the coarse depths in place of the store (one launch between the
+// two networks of a render).
 #include "composite.cuh"
 
 namespace nerf {
