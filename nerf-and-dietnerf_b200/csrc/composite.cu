@@ -155,9 +155,12 @@ composite_bwd_kernel(const float4* __restrict__ raw4, const float* __restrict__ 
   float dr = 0.f, dg = 0.f, db = 0.f;
   if (!kLoss) { dr = __ldg(d_rgb + ray * 3 + 0); dg = __ldg(d_rgb + ray * 3 + 1); db = __ldg(d_rgb + ray * 3 + 2); }
 
+  // Per 32-sample block only EIGHT values stay live between the phases (transmittance, weight, 1 - alpha, delta, sigma and
+  // the three colours; each is overwritten by its successor - g T, g w, the colour gradients, d delta - as soon as it is
+  // dead), so S = 192 fits 64 registers = 4 resident blocks per SM: the kernel had become latency-bound at 3 (ncu: 33 % of
+  // the warp slots, 36 % of the issue slots, 59 % of DRAM).
   float4 raw[C];
-  float zc[C], T[C], gw[C], g[C], col_r[C], col_g[C], col_b[C];
-  SampleFwd f[C];
+  float zc[C], T[C], w[C], x[C], dl[C], sg[C], cr[C], cg[C], cb[C];
 #pragma unroll
   for (int k = 0; k < C; ++k) {
     int s = k * 32 + lane;
@@ -169,7 +172,7 @@ composite_bwd_kernel(const float4* __restrict__ raw4, const float* __restrict__ 
       zc[k] = 0.f;
     }
   }
-  // forward scan: T, colours (and, fused, the ray's colour -> loss -> d_rgb)
+  // forward scan: T, w, colours (and, fused, the ray's colour -> loss -> d_rgb)
   float carry = 1.0f;
   float r_acc = 0.f, g_acc = 0.f, b_acc = 0.f;
 #pragma unroll
@@ -179,20 +182,23 @@ composite_bwd_kernel(const float4* __restrict__ raw4, const float* __restrict__ 
     float z_next_blk = __shfl_sync(kFull, zc[(k + 1 < C) ? k + 1 : k], 0);
     if (lane == 31) z_next = z_next_blk;
     const bool valid = kExact || s < S;
-    f[k] = sample_fwd(raw[k].w, zc[k], z_next, kExact ? (k == C - 1 && lane == 31) : (s == S - 1));
-    float x = valid ? f[k].x : 1.0f;
-    float incl = warp_incl_scan_mul(x, lane);
+    const SampleFwd f = sample_fwd(raw[k].w, zc[k], z_next, kExact ? (k == C - 1 && lane == 31) : (s == S - 1));
+    x[k] = f.x;
+    dl[k] = f.delta;
+    sg[k] = f.sigma;
+    float incl = warp_incl_scan_mul(valid ? f.x : 1.0f, lane);
     float excl = __shfl_up_sync(kFull, incl, 1);
     if (lane == 0) excl = 1.0f;
     T[k] = carry * excl;
     carry *= __shfl_sync(kFull, incl, 31);
-    float cr = sigmoidf_(raw[k].x), cg = sigmoidf_(raw[k].y), cb = sigmoidf_(raw[k].z);
-    col_r[k] = cr; col_g[k] = cg; col_b[k] = cb;
+    w[k] = f.alpha * T[k];
+    cr[k] = sigmoidf_(raw[k].x);
+    cg[k] = sigmoidf_(raw[k].y);
+    cb[k] = sigmoidf_(raw[k].z);
     if (kLoss && valid) {
-      const float w = f[k].alpha * T[k];
-      r_acc = __fmaf_rn(w, cr, r_acc);
-      g_acc = __fmaf_rn(w, cg, g_acc);
-      b_acc = __fmaf_rn(w, cb, b_acc);
+      r_acc = __fmaf_rn(w[k], cr[k], r_acc);
+      g_acc = __fmaf_rn(w[k], cg[k], g_acc);
+      b_acc = __fmaf_rn(w[k], cb[k], b_acc);
     }
   }
   if (kLoss) {
@@ -210,46 +216,41 @@ composite_bwd_kernel(const float4* __restrict__ raw4, const float* __restrict__ 
     }
     block_accumulate((lane == 0 && active) ? er * er + eg * eg + eb * eb : 0.f, lane, loss.sq_err_sum);
   }
-  // g = dL/dw per sample
+  // g = dL/dw per sample; from here on T holds g T, w holds g w and the colours hold the colour gradients
+  // (every product written out: the loss-fused and the plain instantiations must round identically)
 #pragma unroll
   for (int k = 0; k < C; ++k) {
     int s = k * 32 + lane;
     const bool valid = kExact || s < S;
-    float gi = __fmaf_rn(db, col_b[k], __fmaf_rn(dg, col_g[k], __fmul_rn(dr, col_r[k])));
+    float gi = __fmaf_rn(db, cb[k], __fmaf_rn(dg, cg[k], __fmul_rn(dr, cr[k])));
     if (d_weights && valid) gi += __ldcs(d_weights + ray * S + s);
-    g[k] = valid ? gi : 0.f;
-    gw[k] = valid ? gi * f[k].alpha * T[k] : 0.f;
+    if (!valid) gi = 0.f;
+    cr[k] = __fmul_rn(__fmul_rn(__fmul_rn(w[k], dr), cr[k]), 1.f - cr[k]);
+    cg[k] = __fmul_rn(__fmul_rn(__fmul_rn(w[k], dg), cg[k]), 1.f - cg[k]);
+    cb[k] = __fmul_rn(__fmul_rn(__fmul_rn(w[k], db), cb[k]), 1.f - cb[k]);
+    T[k] = __fmul_rn(gi, T[k]);
+    w[k] = __fmul_rn(gi, w[k]);
   }
-  // reverse exclusive cumsum of g*w, then the per-sample gradients
+  // reverse exclusive cumsum of g*w, then the per-sample gradients (dl becomes d delta)
   float rcarry = 0.f;
-  float ddelta[C];
 #pragma unroll
   for (int k = C - 1; k >= 0; --k) {
     int s = k * 32 + lane;
     const bool valid = kExact || s < S;
-    float incl = warp_incl_rscan_add(gw[k], lane);
+    float incl = warp_incl_rscan_add(w[k], lane);
     float excl = __shfl_down_sync(kFull, incl, 1);
     if (lane == 31) excl = 0.f;
     float R = rcarry + excl;
     rcarry += __shfl_sync(kFull, incl, 0);
-    float x = f[k].x;
-    // TF: d cumprod / d x = div_no_nan(R, x); d alpha = g*T - that
-    // x = 1 - alpha is 0 or >= 2^-24, never denormal
-    float dalpha = __fmaf_rn(g[k], T[k], -(x == 0.f ? 0.f : __fmul_rn(R, rcp_ftz(x))));
-    float dsig = __fmul_rn(__fmul_rn(dalpha, x), f[k].delta);
-    float ddel = (kExact ? (k == C - 1 && lane == 31) : (s == S - 1)) ? 0.f : dalpha * x * f[k].sigma;
-    ddelta[k] = valid ? ddel : 0.f;
-    if (valid && active) {
-      float w = f[k].alpha * T[k];
-      float cr = col_r[k], cg = col_g[k], cb = col_b[k];
-      float4 o;
-      o.x = w * dr * cr * (1.f - cr);
-      o.y = w * dg * cg * (1.f - cg);
-      o.z = w * db * cb * (1.f - cb);
-      o.w = raw[k].w > 0.f ? dsig : 0.f;
-      __stcs(d_raw4 + ray * S + s, o);
-    }
+    // TF: d cumprod / d x = div_no_nan(R, x); d alpha = g*T - that.  x = 1 - alpha is 0 or >= 2^-24, never denormal
+    const float dalpha = __fsub_rn(T[k], x[k] == 0.f ? 0.f : __fmul_rn(R, rcp_ftz(x[k])));
+    const float dax = __fmul_rn(dalpha, x[k]);
+    const float dsig = __fmul_rn(dax, dl[k]);
+    const float ddel = (kExact ? (k == C - 1 && lane == 31) : (s == S - 1)) ? 0.f : __fmul_rn(dax, sg[k]);
+    dl[k] = valid ? ddel : 0.f;
+    if (valid && active) __stcs(d_raw4 + ray * S + s, make_float4(cr[k], cg[k], cb[k], sg[k] > 0.f ? dsig : 0.f));
   }
+  float (&ddelta)[C] = dl;
   if (d_z) {
     // d z_s = d delta_{s-1} - d delta_s
 #pragma unroll
