@@ -133,18 +133,19 @@ struct Draw {
 // #{i < n : a_i < v} for a sorted row in shared memory (tf.searchsorted side='left'): branch-free halving.  With a
 // compile-time extent the probes are written in PTX so that each level is exactly LDS [addr + imm] / SETP / predicated
 // ADD (the C++ form compiled to ~7 issue slots per level: pointer selects and re-derived addresses) and the kE
-// independent chains of a lane are interleaved level by level.
+// independent chains of a lane are interleaved level by level.  ("memory": the rows were written by other lanes before a
+// __syncwarp; the probes must stay behind it.)
 template <typename T> struct SharedProbe;
 template <> struct SharedProbe<float> {
   template <int kLoad, int kStep>
   static __device__ __forceinline__ void step(uint32_t& addr, float v) {
     asm volatile("{\n\t.reg .pred p;\n\t.reg .f32 x;\n\tld.shared.f32 x, [%0+%2];\n\tsetp.lt.f32 p, x, %1;\n\t@p add.u32 %0, %0, %3;\n\t}"
-                 : "+r"(addr) : "f"(v), "n"(kLoad), "n"(kStep));
+                 : "+r"(addr) : "f"(v), "n"(kLoad), "n"(kStep) : "memory");
   }
   static __device__ __forceinline__ uint32_t last(uint32_t addr, float v) {
     uint32_t inc;
     asm volatile("{\n\t.reg .pred p;\n\t.reg .f32 x;\n\tld.shared.f32 x, [%1];\n\tsetp.lt.f32 p, x, %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                 : "=r"(inc) : "r"(addr), "f"(v));
+                 : "=r"(inc) : "r"(addr), "f"(v) : "memory");
     return inc;
   }
 };
@@ -152,12 +153,12 @@ template <> struct SharedProbe<uint32_t> {
   template <int kLoad, int kStep>
   static __device__ __forceinline__ void step(uint32_t& addr, uint32_t v) {
     asm volatile("{\n\t.reg .pred p;\n\t.reg .u32 x;\n\tld.shared.u32 x, [%0+%2];\n\tsetp.lt.u32 p, x, %1;\n\t@p add.u32 %0, %0, %3;\n\t}"
-                 : "+r"(addr) : "r"(v), "n"(kLoad), "n"(kStep));
+                 : "+r"(addr) : "r"(v), "n"(kLoad), "n"(kStep) : "memory");
   }
   static __device__ __forceinline__ uint32_t last(uint32_t addr, uint32_t v) {
     uint32_t inc;
     asm volatile("{\n\t.reg .pred p;\n\t.reg .u32 x;\n\tld.shared.u32 x, [%1];\n\tsetp.lt.u32 p, x, %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                 : "=r"(inc) : "r"(addr), "r"(v));
+                 : "=r"(inc) : "r"(addr), "r"(v) : "memory");
     return inc;
   }
 };
