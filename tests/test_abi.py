@@ -77,6 +77,20 @@ def test_missing_library_fails_loudly(pkg, monkeypatch):
         pkg._lib.load()
 
 
+def test_hierarchical_sample_reports_argument_errors(pkg):
+    """nerf_hierarchical_sample (the step between the two networks of NeRF.render, src/NeRF.py:129-132, as one launch):
+    its argument checks need no GPU."""
+    lib = pkg.load()
+    p256 = ctypes.c_void_p(256)
+    args = lambda raw, z, n, s, nf, out: (raw, z, n, s, nf, 1, 0, 0, out, None)
+    assert lib.nerf_hierarchical_sample(*args(None, p256, 4, 64, 128, p256)) == -1 and b"null pointer" in lib.nerf_last_error()
+    assert lib.nerf_hierarchical_sample(*args(p256, p256, 4, 64, 300, p256)) == -1 and b"n_new <= 256" in lib.nerf_last_error()
+    assert lib.nerf_hierarchical_sample(*args(p256, p256, 4, 1, 128, p256)) == -1
+    assert lib.nerf_hierarchical_sample(*args(ctypes.c_void_p(260), p256, 4, 64, 128, p256)) == -1
+    assert b"16-byte aligned" in lib.nerf_last_error()
+    assert lib.nerf_hierarchical_sample(*args(p256, p256, 0, 64, 128, p256)) == 0       # an empty ray range is not an error
+
+
 def test_fused_entry_points_report_argument_errors(pkg):
     """nerf_render_fused_fwd / nerf_train_step_fused: workspace queries and argument checks need no GPU."""
     lib = pkg.load()

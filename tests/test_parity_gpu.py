@@ -301,6 +301,40 @@ def test_hierarchical_sample_matches_the_three_kernels(pkg, n, s, nf):
     assert ((z_got.cpu() - z_o).abs() > 1e-5).float().mean().item() < 2e-3
 
 
+# The largest shapes the entry points accept (S, N_f <= 1024; 256 draws for the one-launch variant): the shared-memory
+# carve-outs go beyond 48 KB (opt-in attribute, set per launch = per device) and the draws take the rank-sort path.
+def test_sampler_maximum_sizes(pkg):
+    n, s, nf = 5, 1024, 1024
+    w, z = _weights_and_z(n, s, 4242)
+    w = w + 1e-4 * torch.rand(n, s, generator=torch.Generator().manual_seed(7))
+    w[0] = 0.0
+    u = torch.rand(n, nf, generator=torch.Generator().manual_seed(8))
+    ref_z, ref_idx, ref_perm, _ = O.get_z_vals_from_prob_dist_func(w, z, nf, u, return_aux=True)
+    got_z, got_idx, got_perm = pkg.UtilsCV.get_z_vals_from_prob_dist_func(dev(w), dev(z), nf, u=dev(u), return_aux=True)
+    assert torch.equal(got_idx.cpu(), ref_idx) and torch.equal(got_z.cpu(), ref_z)
+    assert torch.equal(got_perm.cpu().long(), ref_perm.long())
+    gz = torch.randn(n, nf, generator=torch.Generator().manual_seed(9))
+    wr = w.clone().requires_grad_(True)
+    O.get_z_vals_from_prob_dist_func(wr, z, nf, u).backward(gz)
+    wg = dev(w).requires_grad_(True)
+    pkg.UtilsCV.get_z_vals_from_prob_dist_func(wg, dev(z), nf, u=dev(u)).backward(dev(gz))
+    assert (wg.grad.cpu() - wr.grad).abs().max().item() < 2e-4 * wr.grad.abs().max().item()
+    # one-launch hierarchical sampling at its limits: 1024 coarse samples, 256 draws
+    call = pkg._lib.call
+    n, s, nf = 7, 1024, 256
+    raw, z = _raw_and_z(n, s, 99, sigma_scale=2.0)
+    raw, z = dev(raw), dev(z)
+    f = lambda *shape: torch.empty(shape, device="cuda")
+    w, z_new, z_ref, z_got = f(n, s), f(n, nf), f(n, s + nf), f(n, s + nf)
+    call("nerf_composite_fwd", raw.data_ptr(), z.data_ptr(), n, s, None, w.data_ptr(), None, None, None, None, None)
+    call("nerf_sample_pdf_fwd", w.data_ptr(), z.data_ptr(), n, s, nf, None, 1, 2, 3, z_new.data_ptr(), None, None, None)
+    call("nerf_merge_sorted", z_new.data_ptr(), nf, z.data_ptr(), s, n, z_ref.data_ptr())
+    call("nerf_hierarchical_sample", raw.data_ptr(), z.data_ptr(), n, s, nf, 1, 2, 3, z_got.data_ptr())
+    assert torch.equal(z_got, z_ref)
+    with pytest.raises(pkg._lib.NerfLibraryError):                  # more than 256 draws: the three-kernel sequence
+        call("nerf_hierarchical_sample", raw.data_ptr(), z.data_ptr(), n, s, 300, 1, 2, 3, z_got.data_ptr())
+
+
 def test_sample_pdf_full_size_properties(pkg):
     n, s, nf = 65536, 64, 128
     g = torch.Generator(device="cuda").manual_seed(0)
