@@ -500,29 +500,31 @@ sample_pdf_fwd_kernel(const float* __restrict__ weights, const float* __restrict
     else sort_new_samples<8, 0, 0, kMerge>(szs, ssort, Nf, lane, false, zo, po, szc, S, za);
     return;
   }
-  for (int j0 = 0; j0 < Nf; j0 += 32) {
-    const int j = j0 + lane;
-    const float v = j < Nf ? szs[j] : 0.f;
-    int rank = 0;
-    int k = 0;
-    for (; k + 4 <= j0; k += 4) {                       // k < j for every lane
-      const float4 o = *reinterpret_cast<const float4*>(szs + k);
-      rank += (o.x <= v) + (o.y <= v) + (o.z <= v) + (o.w <= v);
-    }
-    const int diag_end = min(Nf, j0 + 32);
-    for (; k < diag_end; ++k) {                         // diagonal block (j0 is a multiple of 4: k == j0 here)
-      const float o = szs[k];
-      rank += (o < v) || (o == v && k < j);
-    }
-    for (; k < Nf && (k & 3); ++k) rank += szs[k] < v;  // (diag_end is a multiple of 4 unless it is Nf)
-    for (; k + 4 <= Nf; k += 4) {                       // k > j for every lane
-      const float4 o = *reinterpret_cast<const float4*>(szs + k);
-      rank += (o.x < v) + (o.y < v) + (o.z < v) + (o.w < v);
-    }
-    for (; k < Nf; ++k) rank += szs[k] < v;
-    if (j < Nf) {
-      z_new[ray * Nf + rank] = v;
-      if (perm_out) perm_out[ray * Nf + rank] = j;
+  if constexpr (kNf == 0 && !kMerge) {                 // (the compile-time shapes and the merge never get here: <= 256 draws)
+    for (int j0 = 0; j0 < Nf; j0 += 32) {
+      const int j = j0 + lane;
+      const float v = j < Nf ? szs[j] : 0.f;
+      int rank = 0;
+      int k = 0;
+      for (; k + 4 <= j0; k += 4) {                       // k < j for every lane
+        const float4 o = *reinterpret_cast<const float4*>(szs + k);
+        rank += (o.x <= v) + (o.y <= v) + (o.z <= v) + (o.w <= v);
+      }
+      const int diag_end = min(Nf, j0 + 32);
+      for (; k < diag_end; ++k) {                         // diagonal block (j0 is a multiple of 4: k == j0 here)
+        const float o = szs[k];
+        rank += (o < v) || (o == v && k < j);
+      }
+      for (; k < Nf && (k & 3); ++k) rank += szs[k] < v;  // (diag_end is a multiple of 4 unless it is Nf)
+      for (; k + 4 <= Nf; k += 4) {                       // k > j for every lane
+        const float4 o = *reinterpret_cast<const float4*>(szs + k);
+        rank += (o.x < v) + (o.y < v) + (o.z < v) + (o.w < v);
+      }
+      for (; k < Nf; ++k) rank += szs[k] < v;
+      if (j < Nf) {
+        z_new[ray * Nf + rank] = v;
+        if (perm_out) perm_out[ray * Nf + rank] = j;
+      }
     }
   }
 }
