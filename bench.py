@@ -13,7 +13,7 @@ Prints ONE JSON line (rank 0).  `value` = rays/s with the ray batch resident in 
 events over exactly K steps (max over ranks) -- a BURST after an idle second; `sustained` = the same loop run for >= 2 s
 of device time without the idle (power-capped clocks); `e2e` = the same metric through the public API `NeRF.train_step`
 with PINNED HOST batches (H2D copy of the batch and D2H read of the loss inside the timed region, every step).
-Sub-records measured in the same run: `render` (one 256x256 frame, 64 coarse + 192 fine samples), `composite`
+Sub-records measured in the same run: `render` (one 256x256 frame, 64 coarse + 128 new = 192 fine samples), `composite`
 (alpha compositing at 65 536 rays x 192 samples against the HBM peak), `strong` (N > 1: the YAML's 4096-ray batch split
 over the N ranks).  `--impl reference` times the CPU port of the reference's train step (TensorFlow is not installable
 here) on all host cores, on a bounded sample of the same workload.
@@ -434,7 +434,9 @@ def main():
                   "value": per * world * args.steps / (ms_strong * 1e-3), "unit": "rays/s",
                   "note": "same optimisation problem at every N (the weak-scaling `value` grows the global batch)"}
 
-    # ---- render: one 256x256 frame, 64 coarse + 192 fine samples per ray (BASELINE configs[3]), this rank's row block ---
+    # ---- render: one 256x256 frame at the reference's render setting (BASELINE configs[3], every YAML: 64 coarse samples +
+    #      128 importance draws, the fine network sees the 192 merged depths = 256 network rows = 262.2 MFLOP per ray,
+    #      BASELINE.md), this rank's row block ---
     render = composite = None
     if not args.no_extras and not diet:
         h = w = 256
@@ -443,16 +445,18 @@ def main():
         c2w[:3, 3] = [0.0, 0.0, 1.0]
         lo, hi = (h * w * rank) // world, (h * w * (rank + 1)) // world
         with torch.no_grad():
-            frame = lambda: model.render_image_lean(c2w, fov, h, w, 16384, N_C, 192, seed=1, step=0, ray_begin=lo,
+            frame = lambda: model.render_image_lean(c2w, fov, h, w, 16384, N_C, N_F, seed=1, step=0, ray_begin=lo,
                                                     n_rays=hi - lo)
             barrier()
             ms_frame = torch.tensor([dev_time(frame, 3)], device="cuda")
         if world > 1:
             dist.all_reduce(ms_frame, op=dist.ReduceOp.MAX)
         ms_frame = ms_frame.item()
-        flop_ray_render = 2 * MAC_FWD * (N_C + N_C + 192)
-        render = {"what": "render_image_lean, one 256x256 frame, 64 coarse + 192 fine samples/ray "
-                          "(fine network sees 256), rows sharded over the ranks, no collective",
+        flop_ray_render = 2 * MAC_FWD * (N_C + N_C + N_F)
+        render = {"what": "render_image_lean, one 256x256 frame, n_render_samples_coarse 64 + n_render_samples_fine 128 as in "
+                          "every reference YAML (the fine network sees the 192 merged depths: 256 network rows = 262.2 "
+                          "MFLOP per ray), rows sharded over the ranks, no collective; records before r02_bk drew 192 new "
+                          "samples (320 rows per ray)",
                   "ms_per_frame": ms_frame, "value": h * w / (ms_frame * 1e-3), "unit": "rays/s",
                   "mlp_tflops": flop_ray_render * h * w / (ms_frame * 1e-3) / 1e12}
         if rank == 0:
@@ -476,7 +480,12 @@ def main():
             composite = {"rays": n, "samples": sm, "unit": "GB/s (algorithmic bytes / device time)",
                          "fwd_all_outputs": gbs(n * (sm * 44 + 12), full), "fwd_lean": gbs(n * (sm * 24 + 20), lean),
                          "bwd": gbs(n * (sm * 44 + 12), bwd),
-                         "bytes_per_sample": {"fwd_all_outputs": 44, "fwd_lean": 24, "bwd": 44}}
+                         "bytes_per_sample": {"fwd_all_outputs": 44, "fwd_lean": 24, "bwd": 44},
+                         "note": "inputs of a call (252-302 MB) exceed the 126 MB L2, no flush between the 10 timed calls; "
+                                 "`peak` is the measured COPY bandwidth (reads = writes): a read-dominated call can pass it "
+                                 "(ncu: 7.05 TB/s of DRAM reads on this part) and the lean forward's 50 MB of weights may "
+                                 "still sit in the write-back L2 when the call ends (ncu: 26 MB of DRAM writes), so its "
+                                 "fraction can exceed 1"}
     sampler.stop()
 
     if rank == 0:

@@ -774,7 +774,7 @@ int nerf_hierarchical_sample(const float* raw4_coarse, const float* z_coarse, in
                  "need 2 <= n_samples <= 1024 and 1 <= n_new <= 256");
   NERF_CHECK_ARG(((uintptr_t)raw4_coarse & 15) == 0, "raw4_coarse must be 16-byte aligned");
   if (n_rays == 0) return NERF_OK;
-  const bool fixed = n_samples == 64 && n_new == 192;
+  const bool fixed = n_samples == 64 && (n_new == 128 || n_new == 192);   // 128: the render setting of every reference YAML
   size_t smem = (size_t)kWarpsPerBlock * SamplerSmem(n_samples, n_new, fixed, true).per_warp * sizeof(float);
   const unsigned grid = (unsigned)ceil_div(n_rays, kWarpsPerBlock);
 #define NERF_HSAMPLE_LAUNCH(KS, KNF)                                                                                   \
@@ -786,7 +786,8 @@ int nerf_hierarchical_sample(const float* raw4_coarse, const float* z_coarse, in
         raw4_coarse, z_coarse, n_rays, n_samples, n_new, nullptr, seed, step, ray_offset, z_all, nullptr, nullptr,     \
         nullptr, true);                                                                                                \
   } while (0)
-  if (fixed) NERF_HSAMPLE_LAUNCH(64, 192);
+  if (fixed && n_new == 128) NERF_HSAMPLE_LAUNCH(64, 128);
+  else if (fixed) NERF_HSAMPLE_LAUNCH(64, 192);
   else NERF_HSAMPLE_LAUNCH(0, 0);
 #undef NERF_HSAMPLE_LAUNCH
   NERF_CHECK_LAUNCH();

@@ -56,22 +56,24 @@ def main():
             byts = n * (3 * 4 * sc + 3 * 4 * nf)
             print(f"sample_pdf_bwd      N={n:6d} S={sc} Nf={nf}: {med * 1e3:8.1f} us  {byts / med / 1e6:8.1f} GB/s")
     if args.only in ("all", "sampler"):
-        # the step between the two networks of a render (64 coarse samples, 192 draws): three launches against one
-        n, sc, nf = 65536, 64, 192
-        raw = torch.randn(n, sc, 4, device="cuda"); raw[..., 3] *= 10
-        z = torch.sort(torch.rand(n, sc, device="cuda") * 2 + 0.5, -1).values.contiguous()
-        w = torch.empty(n, sc, device="cuda"); z_new = torch.empty(n, nf, device="cuda")
-        z_all = torch.empty(n, sc + nf, device="cuda"); z_one = torch.empty(n, sc + nf, device="cuda")
+        # the step between the two networks of a render (64 coarse samples; 128 draws = the reference's render setting, 192):
+        # three launches against one
+        for nf in (128, 192):
+            n, sc = 65536, 64
+            raw = torch.randn(n, sc, 4, device="cuda"); raw[..., 3] *= 10
+            z = torch.sort(torch.rand(n, sc, device="cuda") * 2 + 0.5, -1).values.contiguous()
+            w = torch.empty(n, sc, device="cuda"); z_new = torch.empty(n, nf, device="cuda")
+            z_all = torch.empty(n, sc + nf, device="cuda"); z_one = torch.empty(n, sc + nf, device="cuda")
 
-        def three():
-            call("nerf_composite_fwd", ptr(raw), ptr(z), n, sc, None, ptr(w), None, None, None, None, None)
-            call("nerf_sample_pdf_fwd", ptr(w), ptr(z), n, sc, nf, None, 1, 0, 0, ptr(z_new), None, None, None)
-            call("nerf_merge_sorted", ptr(z_new), nf, ptr(z), sc, n, ptr(z_all))
-        one = lambda: call("nerf_hierarchical_sample", ptr(raw), ptr(z), n, sc, nf, 1, 0, 0, ptr(z_one))
-        m3, _ = timeit(three)
-        m1, _ = timeit(one)
-        print(f"weights + sampler + merge, three launches N={n} S={sc} Nf={nf}: {m3 * 1e3:8.1f} us")
-        print(f"nerf_hierarchical_sample,  one launch     N={n} S={sc} Nf={nf}: {m1 * 1e3:8.1f} us  equal={torch.equal(z_all, z_one)}")
+            def three():
+                call("nerf_composite_fwd", ptr(raw), ptr(z), n, sc, None, ptr(w), None, None, None, None, None)
+                call("nerf_sample_pdf_fwd", ptr(w), ptr(z), n, sc, nf, None, 1, 0, 0, ptr(z_new), None, None, None)
+                call("nerf_merge_sorted", ptr(z_new), nf, ptr(z), sc, n, ptr(z_all))
+            one = lambda: call("nerf_hierarchical_sample", ptr(raw), ptr(z), n, sc, nf, 1, 0, 0, ptr(z_one))
+            m3, _ = timeit(three)
+            m1, _ = timeit(one)
+            print(f"weights + sampler + merge, three launches N={n} S={sc} Nf={nf}: {m3 * 1e3:8.1f} us")
+            print(f"nerf_hierarchical_sample,  one launch     N={n} S={sc} Nf={nf}: {m1 * 1e3:8.1f} us  equal={torch.equal(z_all, z_one)}")
     for s in ((64, 128, 192) if args.only in ("all", "mlp") else ()):
         m = args.rays * s
         xyz = torch.randn(m, 33, device="cuda")
